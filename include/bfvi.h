@@ -1,0 +1,257 @@
+/*
+ * bfvi.h — C ABI of the B200-native BFVI training-step library (libbfvi_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of ztangent/multimodal-dmm: the
+ * Backward-Forward Variational Inference ELBO forward+backward step of MultiDMM.
+ * Every entry point names the reference interface it replaces (paths relative to
+ * the reference repository root).  The Python host side
+ * (multimodal-dmm_b200/models/*.py) binds these symbols with ctypes; see
+ * INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types in any signature;
+ *   - every data pointer is CALLER-ALLOCATED DEVICE memory (fp32 unless noted);
+ *     the library never allocates or frees device memory and keeps no mutable
+ *     global state, so calls on different streams may run concurrently;
+ *   - every call is asynchronous on the `stream` argument (a cudaStream_t passed
+ *     as void*); results are valid after that stream is synchronised;
+ *   - return value: 0 = ok, <0 = error (BFVI_ERR_*); bfvi_last_error() returns a
+ *     thread-local description;
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails
+ *     with BFVI_ERR_CUDA.
+ *
+ * Tensor layouts follow the reference: time first, (T, B, feature) fp32,
+ * missing data = NaN (datasets/multiseq.py:340-353), sequence mask (T, B) u8.
+ * Parameters live in ONE flat fp32 buffer whose layout bfvi_param_layout()
+ * defines (each tensor is a PyTorch nn.Linear (out,in) row-major block, 16-byte
+ * aligned) so the host can alias torch Parameters onto it and all-reduce the
+ * matching flat gradient buffer with a single NCCL call.
+ */
+#ifndef BFVI_H_
+#define BFVI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFVI_VERSION 100 /* 0.1.0 */
+
+#define BFVI_MAX_MODS 16
+#define BFVI_MAX_SETS (BFVI_MAX_MODS + 1)
+#define BFVI_MAX_EXPERTS (BFVI_MAX_MODS + 2)
+
+enum {
+  BFVI_OK = 0,
+  BFVI_ERR_ARG = -1,         /* invalid argument */
+  BFVI_ERR_UNSUPPORTED = -2, /* shape / distribution not covered by a kernel */
+  BFVI_ERR_CUDA = -3,        /* CUDA runtime error (or no device) */
+  BFVI_ERR_WORKSPACE = -4    /* workspace too small */
+};
+
+enum { BFVI_DIST_NORMAL = 0, BFVI_DIST_BERNOULLI = 1, BFVI_DIST_CATEGORICAL = 2 };
+enum { BFVI_DIR_FWD = 0, BFVI_DIR_BWD = 1 };
+/* forward() modes, models/dmm.py:432-433 */
+enum { BFVI_MODE_BFILTER = 0, BFVI_MODE_FFILTER = 1, BFVI_MODE_FSMOOTH = 2, BFVI_MODE_BSMOOTH = 3 };
+/* expert kinds for bfvi_filter_* */
+enum { BFVI_EXPERT_TENSOR = 0, BFVI_EXPERT_INV_PRIOR = 1 };
+
+/* Static description of a MultiDMM (constructor args, models/dmm.py:29-32). */
+typedef struct bfvi_model {
+  int32_t n_mods;               /* M */
+  int32_t z_dim;                /* latent dims */
+  int32_t h_dim;                /* hidden width of every MLP / GTF */
+  int32_t dims[BFVI_MAX_MODS];  /* flattened feature dim per modality */
+  int32_t dists[BFVI_MAX_MODS]; /* BFVI_DIST_* */
+  float min_std;                /* models/dmm.py:31 (GTF + global prior) */
+} bfvi_model;
+
+/* Offsets (in floats) of every parameter tensor inside the flat buffer.
+ * Names are the reference state_dict keys. */
+typedef struct bfvi_mlp_layout { /* common.GaussianMLP, models/common.py:25-41 */
+  int64_t in_to_h_w, in_to_h_b;  /* in_to_h.0.{weight (H,in), bias (H)} */
+  int64_t mean_w, mean_b;        /* h_to_mean.{weight (out,H), bias} */
+  int64_t std_w, std_b;          /* h_to_std.0.{weight (out,H), bias} */
+  int64_t begin, end;            /* [begin,end) covers the whole block */
+} bfvi_mlp_layout;
+
+typedef struct bfvi_gtf_layout { /* common.GaussianGTF, models/common.py:43-68 */
+  int64_t gate0_w, gate0_b;      /* z_to_gate.0 (H,Z) */
+  int64_t gate2_w, gate2_b;      /* z_to_gate.2 (Z,H) */
+  int64_t lin_w, lin_b;          /* z_lin (Z,Z) */
+  int64_t nonlin0_w, nonlin0_b;  /* z_nonlin.0 (H,Z) */
+  int64_t nonlin2_w, nonlin2_b;  /* z_nonlin.2 (Z,H) */
+  int64_t std_w, std_b;          /* z_to_std.0 (Z,Z) */
+  int64_t begin, end;
+} bfvi_gtf_layout;
+
+typedef struct bfvi_layout {
+  int64_t z0_mean, z0_log_std;            /* (1,Z) each, models/dmm.py:115-116 */
+  bfvi_mlp_layout enc[BFVI_MAX_MODS];     /* enc.<m>  (Normal/Bernoulli MLP encoders) */
+  bfvi_mlp_layout dec[BFVI_MAX_MODS];     /* dec.<m>  (Normal MLP decoders) */
+  bfvi_gtf_layout trans[2];               /* [BFVI_DIR_FWD], [BFVI_DIR_BWD] */
+  int64_t total;                          /* floats in the flat buffer */
+} bfvi_layout;
+
+/* One Gaussian expert stream fed to the filter (product_of_experts inputs,
+ * models/dgts.py:15-51).  mean/std address = base + s*stride_s + t*stride_t +
+ * b*stride_b + z; a stride of 0 broadcasts.  d_mean/d_std (nullable) receive
+ * gradients with the same strides, accumulated with atomic adds. */
+typedef struct bfvi_expert {
+  const float* mean;
+  const float* std;
+  const uint8_t* mask;             /* nullable = all ones */
+  int64_t stride_s, stride_t, stride_b;
+  int64_t mstride_s, mstride_t, mstride_b;
+  float* d_mean;
+  float* d_std;
+  int32_t kind;                    /* BFVI_EXPERT_* ; INV_PRIOR ignores the pointers */
+  int32_t zero_mask_last_t;        /* flt_mask[-1] = 0, models/dmm.py:482 */
+} bfvi_expert;
+
+/* Reparameterisation noise source (replaces MultiDGTS._sample_gauss,
+ * models/dgts.py:177-180).  Either an external tensor of N(0,1) draws laid out
+ * (S, T, B, K, Z) and indexed by the time step at which the draw is consumed,
+ * or (eps == NULL) a counter-based Philox4x32-10 stream keyed by
+ * (seed, stream_id) and indexed by (s, t, b, k, z). */
+typedef struct bfvi_noise {
+  const float* eps;
+  uint64_t seed;
+  uint32_t stream_id;
+  uint32_t b_offset;  /* global batch index of local b = 0 (data-parallel shards) */
+} bfvi_noise;
+
+/* MultiDMM.z_filter (models/dmm.py:319-412) over S independent chain sets. */
+typedef struct bfvi_filter_args {
+  int32_t T, B, S;
+  int32_t n_experts;
+  bfvi_expert experts[BFVI_MAX_EXPERTS];
+  uint32_t set_expert_bits[BFVI_MAX_SETS]; /* bit e set: chain set s uses expert e */
+  int32_t direction;      /* BFVI_DIR_* */
+  int32_t n_particles;    /* K */
+  int32_t sample;         /* models/dmm.py:398 */
+  int32_t sample_init;
+  bfvi_noise noise;
+  /* outputs, each (S, T, B, Z) */
+  float* infer_mean; float* infer_std;
+  float* prior_mean; float* prior_std;
+  float* samples;         /* nullable */
+  /* optional fused KL(infer || prior) term, losses.kld_gauss (models/losses.py:14-21):
+   * loss_acc[0] += kl_weight * KL over (t,b) with seq_mask set */
+  const uint8_t* seq_mask; /* (T,B) u8, nullable = ones */
+  float kl_weight;
+  double* loss_acc;        /* nullable */
+  /* backward inputs (nullable), each (S, T, B, Z) */
+  const float* d_infer_mean; const float* d_infer_std;
+  const float* d_prior_mean; const float* d_prior_std;
+  const float* d_samples;
+} bfvi_filter_args;
+
+/* Arguments of one MultiDMM.step (models/dmm.py:503-554) as driven by
+ * Trainer.train (trainer.py:237-243). */
+typedef struct bfvi_step_args {
+  int32_t T, B;
+  const float* inputs[BFVI_MAX_MODS];   /* (T,B,D_m), NaN = missing */
+  const float* targets[BFVI_MAX_MODS];  /* (T,B,D_m) */
+  const uint8_t* seq_mask;              /* (T,B) u8 from len_to_mask */
+  float kld_mult;
+  float rec_mults[BFVI_MAX_MODS];
+  int32_t uni_loss;
+  int32_t f_mode, s_mode;               /* BFVI_MODE_* */
+  float f_mult, s_mult, match_mult;
+  int32_t train_particles, match_particles;
+  int32_t sample, sample_init;
+  /* noise: external tensors (all NULL => Philox with `seed`) */
+  const float* eps_match;               /* (2, K_match, Z) */
+  const float* eps_filt;                /* (S, T, B, 1, Z)   f_mode pass */
+  const float* eps_sflt;                /* (S, T, B, K, Z)   s_mode filtering pass */
+  const float* eps_ssmt;                /* (S, T, B, 1, Z)   s_mode smoothing pass */
+  uint64_t seed;
+  uint32_t b_offset;                    /* see bfvi_noise */
+  float match_count;                    /* mask.sum() used by the prior-matching term
+                                           (models/dmm.py:541); < 0 = count seq_mask here */
+} bfvi_step_args;
+
+int bfvi_version(void);
+const char* bfvi_last_error(void);
+
+/* Flat parameter layout for a model (all-default MLP encoders/decoders). */
+int bfvi_param_layout(const bfvi_model* model, bfvi_layout* out);
+
+/* Which kernel family serves this model: 1 = register-resident small-dim path,
+ * 2 = generic path, 0 = unsupported. */
+int bfvi_kernel_family(const bfvi_model* model);
+
+/* MultiDMM.encode for one default Gaussian-MLP encoder (models/dmm.py:165-173 +
+ * models/common.py:38-41): NaN -> mask, zero fill, MLP.  x (n_rows, D_m). */
+int bfvi_encode_fwd(const bfvi_model* model, const float* params, int32_t mod,
+                    const float* x, int64_t n_rows, float* mean, float* std,
+                    uint8_t* mask, void* stream);
+/* Backward of the above: accumulates into grads (flat, same layout). */
+int bfvi_encode_bwd(const bfvi_model* model, const float* params, float* grads,
+                    int32_t mod, const float* x, int64_t n_rows,
+                    const float* d_mean, const float* d_std, void* stream);
+
+/* MultiDMM.decode for one default Gaussian-MLP decoder (models/dmm.py:207-211). */
+int bfvi_decode_fwd(const bfvi_model* model, const float* params, int32_t mod,
+                    const float* z, int64_t n_rows, float* mean, float* std,
+                    void* stream);
+/* Decoder + losses.nll_gauss (models/losses.py:68-89) fused, forward and
+ * backward in one pass: loss_acc[0] += weight * NLL; d_z (+=, nullable) and
+ * grads (nullable) receive gradients scaled by weight.  row_mask (n_rows) u8 is
+ * the sequence mask broadcast to rows (nullable). */
+int bfvi_decode_nll(const bfvi_model* model, const float* params, float* grads,
+                    int32_t mod, const float* z, const float* target,
+                    const uint8_t* row_mask, int64_t n_rows, float weight,
+                    double* loss_acc, float* d_z, void* stream);
+
+/* z_filter forward / backward (models/dmm.py:319-412).  Backward needs the
+ * forward outputs in `args` plus the upstream gradients; it accumulates the
+ * transition / prior gradients into `grads` and expert gradients into
+ * experts[e].d_mean / d_std. */
+int bfvi_filter_fwd(const bfvi_model* model, const float* params,
+                    const bfvi_filter_args* args, void* stream);
+int bfvi_filter_bwd(const bfvi_model* model, const float* params, float* grads,
+                    const bfvi_filter_args* args, void* stream);
+
+/* losses.kld_gauss (models/losses.py:14-21) with an optional (n_rows) u8 mask:
+ * out[0] = 0.5 * sum(...).  Backward writes the four gradients scaled by g. */
+int bfvi_kld_fwd(const float* mean1, const float* std1, const float* mean2,
+                 const float* std2, const uint8_t* row_mask, int64_t n_rows,
+                 int32_t z_dim, double* out, void* stream);
+int bfvi_kld_bwd(const float* mean1, const float* std1, const float* mean2,
+                 const float* std2, const uint8_t* row_mask, int64_t n_rows,
+                 int32_t z_dim, float g, float* d_mean1, float* d_std1,
+                 float* d_mean2, float* d_std2, void* stream);
+
+/* losses.nll_gauss (models/losses.py:68-89): x may hold NaN; row_mask (n_rows). */
+int bfvi_nll_gauss_fwd(const float* mean, const float* std, const float* x,
+                       const uint8_t* row_mask, int64_t n_rows, int32_t d,
+                       double* out, void* stream);
+int bfvi_nll_gauss_bwd(const float* mean, const float* std, const float* x,
+                       const uint8_t* row_mask, int64_t n_rows, int32_t d, float g,
+                       float* d_mean, float* d_std, void* stream);
+
+/* Whole MultiDMM.step + backward (models/dmm.py:503-554, trainer.py:237-243).
+ * loss_out[0] (device fp32) = un-normalised summed loss; grads (nullable: forward
+ * only) = d loss / d params, OVERWRITTEN.  `launches` (nullable, host) receives
+ * the number of kernels launched. */
+int bfvi_step_workspace(const bfvi_model* model, const bfvi_step_args* args,
+                        size_t* bytes);
+int bfvi_step_fwd_bwd(const bfvi_model* model, const float* params, float* grads,
+                      const bfvi_step_args* args, void* workspace,
+                      size_t workspace_bytes, float* loss_out, int32_t* launches,
+                      void* stream);
+
+/* Materialise the Philox stream (same generator the kernels use) as an external
+ * noise tensor (S, T, B, K, Z) so the oracle can be run on identical draws. */
+int bfvi_dump_noise(uint64_t seed, uint32_t stream_id, uint32_t b_offset, int32_t S,
+                    int32_t T, int32_t B, int32_t K, int32_t Z, float* out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BFVI_H_ */

@@ -1,0 +1,694 @@
+// bfvi_api.cu — the C ABI declared in include/bfvi.h: argument checking, kernel
+// dispatch on (z_dim, h_dim), workspace carving and the orchestration of one whole
+// MultiDMM.step (models/dmm.py:503-554) + backward as a fixed sequence of launches
+// on the caller's stream.  No device allocation, no global mutable state.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "bfvi_small.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define BFVI_CHECK_CUDA()                                                                 \
+  do {                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess) return fail(BFVI_ERR_CUDA, "CUDA error: %s (%s:%d)",           \
+                                       cudaGetErrorString(e_), __FILE__, __LINE__);       \
+  } while (0)
+
+using bfvi::pad4;
+
+int check_model(const bfvi_model* m) {
+  if (m == nullptr) return fail(BFVI_ERR_ARG, "model is null");
+  if (m->n_mods < 1 || m->n_mods > BFVI_MAX_MODS) return fail(BFVI_ERR_ARG, "n_mods %d out of range", m->n_mods);
+  if (m->z_dim < 1 || m->h_dim < 1) return fail(BFVI_ERR_ARG, "bad z_dim/h_dim");
+  for (int i = 0; i < m->n_mods; ++i)
+    if (m->dims[i] < 1) return fail(BFVI_ERR_ARG, "dims[%d] < 1", i);
+  return BFVI_OK;
+}
+
+int64_t take(int64_t& cur, int n) { int64_t o = cur; cur += pad4(n); return o; }
+
+void mlp_layout(int64_t& cur, int n_in, int n_out, int H, bfvi_mlp_layout* l) {
+  l->begin = cur;
+  l->in_to_h_w = take(cur, H * n_in);
+  l->in_to_h_b = take(cur, H);
+  l->mean_w = take(cur, n_out * H);
+  l->mean_b = take(cur, n_out);
+  l->std_w = take(cur, n_out * H);
+  l->std_b = take(cur, n_out);
+  l->end = cur;
+}
+
+void gtf_layout(int64_t& cur, int Z, int H, bfvi_gtf_layout* l) {
+  l->begin = cur;
+  l->gate0_w = take(cur, H * Z); l->gate0_b = take(cur, H);
+  l->gate2_w = take(cur, Z * H); l->gate2_b = take(cur, Z);
+  l->lin_w = take(cur, Z * Z);   l->lin_b = take(cur, Z);
+  l->nonlin0_w = take(cur, H * Z); l->nonlin0_b = take(cur, H);
+  l->nonlin2_w = take(cur, Z * H); l->nonlin2_b = take(cur, Z);
+  l->std_w = take(cur, Z * Z);   l->std_b = take(cur, Z);
+  l->end = cur;
+}
+
+bfvi::MlpOffsets mlp_offsets(const bfvi_mlp_layout& l) {
+  bfvi::MlpOffsets o;
+  o.w1 = (int)(l.in_to_h_w - l.begin); o.b1 = (int)(l.in_to_h_b - l.begin);
+  o.wm = (int)(l.mean_w - l.begin);    o.bm = (int)(l.mean_b - l.begin);
+  o.ws = (int)(l.std_w - l.begin);     o.bs = (int)(l.std_b - l.begin);
+  o.size = (int)(l.end - l.begin);
+  return o;
+}
+
+int num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return n;
+}
+
+int grid_for(int64_t work_items, int per_block, int blocks_per_sm) {
+  const int sms = num_sms();
+  int64_t need = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)(sms > 0 ? sms : 1) * blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---- (Z, H) dispatch for the register-resident family -------------------------
+#define BFVI_SMALL_DIMS(X) X(5, 20) X(4, 8) X(3, 6) X(6, 12)
+
+bool small_supported(int Z, int H) {
+#define X(z, h) if (Z == z && H == h) return true;
+  BFVI_SMALL_DIMS(X)
+#undef X
+  return false;
+}
+
+#define BFVI_MLP_H(X) X(20) X(8) X(6) X(12)
+
+template <int Z, int H>
+int layout_matches(const bfvi_gtf_layout& l) {
+  using L = bfvi::GtfLayout<Z, H>;
+  const int64_t b = l.begin;
+  return l.gate0_w - b == L::G0W && l.gate0_b - b == L::G0B && l.gate2_w - b == L::G2W &&
+         l.gate2_b - b == L::G2B && l.lin_w - b == L::LW && l.lin_b - b == L::LB &&
+         l.nonlin0_w - b == L::N0W && l.nonlin0_b - b == L::N0B && l.nonlin2_w - b == L::N2W &&
+         l.nonlin2_b - b == L::N2B && l.std_w - b == L::SW && l.std_b - b == L::SB &&
+         l.end - b == L::SIZE;
+}
+
+template <int Z, int H>
+int launch_filter_fwd(const bfvi::FilterParams& fp, cudaStream_t st) {
+  const bfvi_filter_args& a = fp.a;
+  const int64_t chains = (int64_t)a.S * a.B;
+  if (a.n_particles > 1) {
+    auto k = bfvi::filter_fwd_kernel<Z, H, true>;
+    const int wpb = bfvi::kFilterFwdThreads / 32;
+    BFVI_LAUNCH(k, dim3(grid_for(chains, wpb, 16)), dim3(bfvi::kFilterFwdThreads), 0, st, fp);
+  } else {
+    auto k = bfvi::filter_fwd_kernel<Z, H, false>;
+    const int tpb = 64;     // few sequences per CTA: spread K == 1 chains over all SMs
+    BFVI_LAUNCH(k, dim3(grid_for(chains, tpb, 16)), dim3(tpb), 0, st, fp);
+  }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+template <int Z, int H>
+int launch_filter_bwd(const bfvi::FilterParams& fp, cudaStream_t st) {
+  const bfvi_filter_args& a = fp.a;
+  const int64_t chains = (int64_t)a.S * a.B;
+  const size_t smem = bfvi::filter_bwd_smem_bytes<Z, H>();
+  const int threads = bfvi::kFilterBwdWarps * 32;
+  if (a.n_particles > 1) {
+    auto k = bfvi::filter_bwd_kernel<Z, H, true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    BFVI_LAUNCH(k, dim3(grid_for(chains, bfvi::kFilterBwdWarps, 2)), dim3(threads), smem, st, fp);
+  } else {
+    auto k = bfvi::filter_bwd_kernel<Z, H, false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    BFVI_LAUNCH(k, dim3(grid_for(chains, threads, 2)), dim3(threads), smem, st, fp);
+  }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+template <int Z, int H>
+int launch_match(const bfvi::MatchParams& mp, cudaStream_t st) {
+  auto k = bfvi::match_kernel<Z, H>;
+  const size_t smem = bfvi::match_smem_bytes<Z, H>();
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  BFVI_LAUNCH(k, dim3(2), dim3(32), smem, st, mp);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int launch_mlp_fwd(int H, const bfvi::MlpParams& mp, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)mp.off.size;
+  const int grid = grid_for(mp.n_rows, 128, 8);
+#define X(h)                                                                       \
+  if (H == h) {                                                                    \
+    auto k = bfvi::mlp_fwd_kernel<h>;                                              \
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    BFVI_LAUNCH(k, dim3(grid), dim3(128), smem, st, mp);                           \
+    BFVI_CHECK_CUDA();                                                             \
+    return BFVI_OK;                                                                \
+  }
+  BFVI_MLP_H(X)
+#undef X
+  return fail(BFVI_ERR_UNSUPPORTED, "no MLP kernel for h_dim=%d", H);
+}
+
+int launch_mlp_bwd(int H, bool decoder, const bfvi::MlpParams& mp, cudaStream_t st) {
+  const size_t smem = bfvi::mlp_bwd_smem_bytes(mp.n_in, mp.n_out, H, mp.off);
+  if (smem > 200 * 1024) return fail(BFVI_ERR_UNSUPPORTED, "MLP too wide for the small-dim path");
+  const int threads = bfvi::kMlpWarps * 32;
+  const int grid = grid_for(mp.n_rows, threads, 2);
+#define X(h)                                                                         \
+  if (H == h) {                                                                      \
+    if (decoder) {                                                                   \
+      auto k = bfvi::mlp_bwd_kernel<h, true>;                                        \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      BFVI_LAUNCH(k, dim3(grid), dim3(threads), smem, st, mp);                       \
+    } else {                                                                         \
+      auto k = bfvi::mlp_bwd_kernel<h, false>;                                       \
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+      BFVI_LAUNCH(k, dim3(grid), dim3(threads), smem, st, mp);                       \
+    }                                                                                \
+    BFVI_CHECK_CUDA();                                                               \
+    return BFVI_OK;                                                                  \
+  }
+  BFVI_MLP_H(X)
+#undef X
+  return fail(BFVI_ERR_UNSUPPORTED, "no MLP kernel for h_dim=%d", H);
+}
+
+int dispatch_filter(const bfvi_model* m, const bfvi_layout& lay, bool backward,
+                    const bfvi::FilterParams& fp, cudaStream_t st) {
+#define X(z, h)                                                                      \
+  if (m->z_dim == z && m->h_dim == h) {                                              \
+    if (!layout_matches<z, h>(lay.trans[0]))                                         \
+      return fail(BFVI_ERR_ARG, "internal: GTF layout mismatch");                    \
+    return backward ? launch_filter_bwd<z, h>(fp, st) : launch_filter_fwd<z, h>(fp, st); \
+  }
+  BFVI_SMALL_DIMS(X)
+#undef X
+  return fail(BFVI_ERR_UNSUPPORTED, "no filter kernel for z_dim=%d h_dim=%d", m->z_dim, m->h_dim);
+}
+
+int dispatch_match(const bfvi_model* m, const bfvi::MatchParams& mp, cudaStream_t st) {
+#define X(z, h) if (m->z_dim == z && m->h_dim == h) return launch_match<z, h>(mp, st);
+  BFVI_SMALL_DIMS(X)
+#undef X
+  return fail(BFVI_ERR_UNSUPPORTED, "no match kernel for z_dim=%d h_dim=%d", m->z_dim, m->h_dim);
+}
+
+int check_filter_args(const bfvi_model* m, const bfvi_filter_args* a) {
+  if (a == nullptr) return fail(BFVI_ERR_ARG, "filter args null");
+  if (a->T < 1 || a->B < 1 || a->S < 1 || a->S > BFVI_MAX_SETS) return fail(BFVI_ERR_ARG, "bad T/B/S");
+  if (a->n_experts < 0 || a->n_experts > BFVI_MAX_EXPERTS) return fail(BFVI_ERR_ARG, "bad n_experts");
+  if (a->n_particles < 1) return fail(BFVI_ERR_ARG, "n_particles < 1");
+  if ((int64_t)a->S * a->B > 0x7fffffff / 2) return fail(BFVI_ERR_ARG, "too many chains for one call");
+  if (!a->infer_mean || !a->infer_std || !a->prior_mean || !a->prior_std)
+    return fail(BFVI_ERR_ARG, "filter outputs must be non-null");
+  for (int e = 0; e < a->n_experts; ++e)
+    if (a->experts[e].kind == BFVI_EXPERT_TENSOR && (!a->experts[e].mean || !a->experts[e].std))
+      return fail(BFVI_ERR_ARG, "expert %d has null tensors", e);
+  (void)m;
+  return BFVI_OK;
+}
+
+bfvi::FilterParams make_filter_params(const bfvi_model* m, const bfvi_layout& lay, const float* params,
+                                      float* grads, const bfvi_filter_args* a) {
+  bfvi::FilterParams fp;
+  fp.a = *a;
+  const int d = a->direction == BFVI_DIR_BWD ? 1 : 0;
+  fp.trans_w = params + lay.trans[d].begin;
+  fp.z0_mean = params + lay.z0_mean;
+  fp.z0_log_std = params + lay.z0_log_std;
+  fp.g_trans = grads ? grads + lay.trans[d].begin : nullptr;
+  fp.g_z0_mean = grads ? grads + lay.z0_mean : nullptr;
+  fp.g_z0_log_std = grads ? grads + lay.z0_log_std : nullptr;
+  fp.min_std = m->min_std;
+  return fp;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct StepPlan {
+  int S;
+  unsigned set_bits[BFVI_MAX_SETS];     // modalities in each input set
+  size_t n_tbz, n_obs;                  // T*B*Z, M*T*B*Z
+  // workspace offsets (bytes)
+  size_t off_acc, off_count, off_obs_mean, off_obs_std, off_obs_mask, off_dobs_mean, off_dobs_std;
+  size_t off_a[6], off_b[6], off_c[6];  // infer_m, infer_s, prior_m, prior_s, samples / d_prior_m, d_samples / d_prior_s
+  size_t zero_begin, zero_end;          // region cleared at step start
+  size_t total;
+};
+
+// sets of one DGTS step in evaluation order (models/dgts.py:119-129)
+void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, StepPlan* pl) {
+  int S = 0;
+  const int M = m->n_mods;
+  if (M > 1) pl->set_bits[S++] = (M >= 32) ? 0xffffffffu : ((1u << M) - 1u);
+  if (a->uni_loss)
+    for (int i = 0; i < M; ++i) pl->set_bits[S++] = 1u << i;
+  pl->S = S;
+  const size_t tb = (size_t)a->T * a->B;
+  pl->n_tbz = tb * m->z_dim;
+  pl->n_obs = pl->n_tbz * M;
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  const size_t fS = sizeof(float) * pl->n_tbz * (size_t)(S > 0 ? S : 1);
+  // --- zeroed region: accumulators and gradient scratch ---
+  pl->zero_begin = cur;
+  pl->off_acc = carve(sizeof(double));
+  pl->off_count = carve(sizeof(float));
+  pl->off_dobs_mean = carve(with_grad ? sizeof(float) * pl->n_obs : 0);
+  pl->off_dobs_std = carve(with_grad ? sizeof(float) * pl->n_obs : 0);
+  pl->off_a[5] = carve(with_grad ? fS : 0);   // d_samples A
+  pl->off_b[4] = carve(with_grad ? fS : 0);   // d_prior_mean B
+  pl->off_b[5] = carve(with_grad ? fS : 0);   // d_prior_std B
+  pl->off_c[5] = carve(with_grad ? fS : 0);   // d_samples C
+  pl->zero_end = cur;
+  pl->off_obs_mean = carve(sizeof(float) * pl->n_obs);
+  pl->off_obs_std = carve(sizeof(float) * pl->n_obs);
+  pl->off_obs_mask = carve(tb * M);
+  for (int i = 0; i < 5; ++i) pl->off_a[i] = carve(fS);
+  for (int i = 0; i < 4; ++i) pl->off_b[i] = carve(fS);
+  for (int i = 0; i < 5; ++i) pl->off_c[i] = carve(fS);
+  pl->total = cur;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+int bfvi_version(void) { return BFVI_VERSION; }
+const char* bfvi_last_error(void) { return g_err.c_str(); }
+
+int bfvi_param_layout(const bfvi_model* m, bfvi_layout* out) {
+  if (int rc = check_model(m)) return rc;
+  if (out == nullptr) return fail(BFVI_ERR_ARG, "layout out is null");
+  memset(out, 0, sizeof(*out));
+  int64_t cur = 0;
+  // registration order of the reference module tree (models/dmm.py:75-116):
+  // direct parameters first, then enc.*, dec.*, trans.fwd, trans.bwd
+  out->z0_mean = take(cur, m->z_dim);
+  out->z0_log_std = take(cur, m->z_dim);
+  for (int i = 0; i < m->n_mods; ++i) mlp_layout(cur, m->dims[i], m->z_dim, m->h_dim, &out->enc[i]);
+  for (int i = 0; i < m->n_mods; ++i) mlp_layout(cur, m->z_dim, m->dims[i], m->h_dim, &out->dec[i]);
+  gtf_layout(cur, m->z_dim, m->h_dim, &out->trans[0]);
+  gtf_layout(cur, m->z_dim, m->h_dim, &out->trans[1]);
+  out->total = cur;
+  return BFVI_OK;
+}
+
+int bfvi_kernel_family(const bfvi_model* m) {
+  if (check_model(m)) return 0;
+  return small_supported(m->z_dim, m->h_dim) ? 1 : 0;
+}
+
+int bfvi_encode_fwd(const bfvi_model* m, const float* params, int32_t mod, const float* x,
+                    int64_t n_rows, float* mean, float* std, uint8_t* mask, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (mod < 0 || mod >= m->n_mods) return fail(BFVI_ERR_ARG, "bad modality index");
+  if (m->dists[mod] == BFVI_DIST_CATEGORICAL) return fail(BFVI_ERR_UNSUPPORTED, "categorical encoder is a host-side module");
+  if (!params || !x || !mean || !std || !mask || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.enc[mod].begin;
+  mp.off = mlp_offsets(lay.enc[mod]);
+  mp.n_in = m->dims[mod]; mp.n_out = m->z_dim; mp.n_rows = n_rows;
+  mp.x = x; mp.mean = mean; mp.std = std; mp.mask = mask;
+  return launch_mlp_fwd(m->h_dim, mp, (cudaStream_t)stream);
+}
+
+int bfvi_encode_bwd(const bfvi_model* m, const float* params, float* grads, int32_t mod,
+                    const float* x, int64_t n_rows, const float* d_mean, const float* d_std,
+                    void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (mod < 0 || mod >= m->n_mods) return fail(BFVI_ERR_ARG, "bad modality index");
+  if (!params || !grads || !x || !d_mean || !d_std || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.enc[mod].begin;
+  mp.g = grads + lay.enc[mod].begin;
+  mp.off = mlp_offsets(lay.enc[mod]);
+  mp.n_in = m->dims[mod]; mp.n_out = m->z_dim; mp.n_rows = n_rows;
+  mp.x = x; mp.d_mean = d_mean; mp.d_std = d_std;
+  return launch_mlp_bwd(m->h_dim, false, mp, (cudaStream_t)stream);
+}
+
+int bfvi_decode_fwd(const bfvi_model* m, const float* params, int32_t mod, const float* z,
+                    int64_t n_rows, float* mean, float* std, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (mod < 0 || mod >= m->n_mods) return fail(BFVI_ERR_ARG, "bad modality index");
+  if (m->dists[mod] != BFVI_DIST_NORMAL) return fail(BFVI_ERR_UNSUPPORTED, "only Normal decoders are fused");
+  if (!params || !z || !mean || !std || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.dec[mod].begin;
+  mp.off = mlp_offsets(lay.dec[mod]);
+  mp.n_in = m->z_dim; mp.n_out = m->dims[mod]; mp.n_rows = n_rows;
+  mp.x = z; mp.mean = mean; mp.std = std; mp.mask = nullptr;
+  return launch_mlp_fwd(m->h_dim, mp, (cudaStream_t)stream);
+}
+
+int bfvi_decode_nll(const bfvi_model* m, const float* params, float* grads, int32_t mod,
+                    const float* z, const float* target, const uint8_t* row_mask, int64_t n_rows,
+                    float weight, double* loss_acc, float* d_z, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (mod < 0 || mod >= m->n_mods) return fail(BFVI_ERR_ARG, "bad modality index");
+  if (m->dists[mod] != BFVI_DIST_NORMAL) return fail(BFVI_ERR_UNSUPPORTED, "only Normal decoders are fused");
+  if (!params || !z || !target || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.dec[mod].begin;
+  mp.g = grads ? grads + lay.dec[mod].begin : nullptr;
+  mp.off = mlp_offsets(lay.dec[mod]);
+  mp.n_in = m->z_dim; mp.n_out = m->dims[mod]; mp.n_rows = n_rows;
+  mp.x = z; mp.target = target; mp.row_mask = row_mask; mp.weight = weight;
+  mp.loss_acc = loss_acc; mp.d_x = d_z;
+  return launch_mlp_bwd(m->h_dim, true, mp, (cudaStream_t)stream);
+}
+
+int bfvi_filter_fwd(const bfvi_model* m, const float* params, const bfvi_filter_args* a, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (int rc = check_filter_args(m, a)) return rc;
+  if (!params) return fail(BFVI_ERR_ARG, "params null");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  return dispatch_filter(m, lay, false, make_filter_params(m, lay, params, nullptr, a), (cudaStream_t)stream);
+}
+
+int bfvi_filter_bwd(const bfvi_model* m, const float* params, float* grads, const bfvi_filter_args* a,
+                    void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (int rc = check_filter_args(m, a)) return rc;
+  if (!params || !grads) return fail(BFVI_ERR_ARG, "params/grads null");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  return dispatch_filter(m, lay, true, make_filter_params(m, lay, params, grads, a), (cudaStream_t)stream);
+}
+
+int bfvi_kld_fwd(const float* m1, const float* s1, const float* m2, const float* s2,
+                 const uint8_t* row_mask, int64_t n_rows, int32_t z_dim, double* out, void* stream) {
+  if (!m1 || !s1 || !m2 || !s2 || !out || n_rows < 1 || z_dim < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  auto k = bfvi::kld_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows * z_dim, 256, 8)), dim3(256), 0, st, m1, s1, m2, s2, row_mask, n_rows,
+              (int)z_dim, out, 0.f, (float*)nullptr, (float*)nullptr, (float*)nullptr, (float*)nullptr);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_kld_bwd(const float* m1, const float* s1, const float* m2, const float* s2,
+                 const uint8_t* row_mask, int64_t n_rows, int32_t z_dim, float g, float* d_m1,
+                 float* d_s1, float* d_m2, float* d_s2, void* stream) {
+  if (!m1 || !s1 || !m2 || !s2 || !d_m1 || !d_s1 || !d_m2 || !d_s2 || n_rows < 1 || z_dim < 1)
+    return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::kld_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows * z_dim, 256, 8)), dim3(256), 0, (cudaStream_t)stream, m1, s1, m2, s2,
+              row_mask, n_rows, (int)z_dim, (double*)nullptr, g, d_m1, d_s1, d_m2, d_s2);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_nll_gauss_fwd(const float* mean, const float* std, const float* x, const uint8_t* row_mask,
+                       int64_t n_rows, int32_t d, double* out, void* stream) {
+  if (!mean || !std || !x || !out || n_rows < 1 || d < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  auto k = bfvi::nll_gauss_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows * d, 256, 8)), dim3(256), 0, st, mean, std, x, row_mask, n_rows, (int)d,
+              out, 0.f, (float*)nullptr, (float*)nullptr);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_nll_gauss_bwd(const float* mean, const float* std, const float* x, const uint8_t* row_mask,
+                       int64_t n_rows, int32_t d, float g, float* d_mean, float* d_std, void* stream) {
+  if (!mean || !std || !x || !d_mean || !d_std || n_rows < 1 || d < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::nll_gauss_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows * d, 256, 8)), dim3(256), 0, (cudaStream_t)stream, mean, std, x, row_mask,
+              n_rows, (int)d, (double*)nullptr, g, d_mean, d_std);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_dump_noise(uint64_t seed, uint32_t stream_id, uint32_t b_offset, int32_t S, int32_t T, int32_t B,
+                    int32_t K, int32_t Z, float* out, void* stream) {
+  if (!out || S < 1 || T < 1 || B < 1 || K < 1 || Z < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::dump_noise_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for((int64_t)S * T * B * K, 256, 8)), dim3(256), 0, (cudaStream_t)stream, seed,
+              (unsigned)stream_id, (unsigned)b_offset, (int)S, (int)T, (int)B, (int)K, (int)Z, out);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
+  if (int rc = check_model(m)) return rc;
+  if (a == nullptr) return fail(BFVI_ERR_ARG, "step args null");
+  if (a->T < 1 || a->B < 1) return fail(BFVI_ERR_ARG, "bad T/B");
+  if (!small_supported(m->z_dim, m->h_dim))
+    return fail(BFVI_ERR_UNSUPPORTED, "no fused step kernels for z_dim=%d h_dim=%d", m->z_dim, m->h_dim);
+  for (int i = 0; i < m->n_mods; ++i)
+    if (m->dists[i] != BFVI_DIST_NORMAL)
+      return fail(BFVI_ERR_UNSUPPORTED, "fused step covers Normal modalities; compose the ops for others");
+  if (a->f_mode != BFVI_MODE_BFILTER && a->f_mode != BFVI_MODE_FFILTER) return fail(BFVI_ERR_ARG, "bad f_mode");
+  if (a->s_mode != BFVI_MODE_FSMOOTH && a->s_mode != BFVI_MODE_BSMOOTH) return fail(BFVI_ERR_ARG, "bad s_mode");
+  if (a->train_particles < 1 || a->match_particles < 1) return fail(BFVI_ERR_ARG, "particle counts must be >= 1");
+  return BFVI_OK;
+}
+
+int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* bytes) {
+  if (int rc = check_step(m, a)) return rc;
+  if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
+  StepPlan pl;
+  plan_step(m, a, true, &pl);
+  *bytes = pl.total;
+  return BFVI_OK;
+}
+
+int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
+                      void* workspace, size_t workspace_bytes, float* loss_out, int32_t* launches,
+                      void* stream) {
+  if (int rc = check_step(m, a)) return rc;
+  if (!params || !workspace || !loss_out) return fail(BFVI_ERR_ARG, "null argument");
+  if (!a->seq_mask) return fail(BFVI_ERR_ARG, "seq_mask null");
+  const int M = m->n_mods, Z = m->z_dim, T = a->T, B = a->B;
+  for (int i = 0; i < M; ++i)
+    if (!a->inputs[i] || !a->targets[i]) return fail(BFVI_ERR_ARG, "inputs/targets[%d] null", i);
+  const bool with_grad = grads != nullptr;
+  StepPlan pl;
+  plan_step(m, a, with_grad, &pl);
+  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  int n_launch = 0;
+
+  double* acc = (double*)(ws + pl.off_acc);
+  float* count = (float*)(ws + pl.off_count);
+  float* obs_mean = (float*)(ws + pl.off_obs_mean);
+  float* obs_std = (float*)(ws + pl.off_obs_std);
+  uint8_t* obs_mask = (uint8_t*)(ws + pl.off_obs_mask);
+  float* dobs_mean = with_grad ? (float*)(ws + pl.off_dobs_mean) : nullptr;
+  float* dobs_std = with_grad ? (float*)(ws + pl.off_dobs_std) : nullptr;
+  auto A = [&](int i) { return (float*)(ws + pl.off_a[i]); };
+  auto Bf = [&](int i) { return (float*)(ws + pl.off_b[i]); };
+  auto C = [&](int i) { return (float*)(ws + pl.off_c[i]); };
+
+  cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
+  if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
+  BFVI_CHECK_CUDA();
+
+  const int64_t tb = (int64_t)T * B;
+  const bool external = a->eps_filt != nullptr || a->eps_sflt != nullptr || a->eps_ssmt != nullptr ||
+                        a->eps_match != nullptr;
+  const int S = pl.S;
+
+  // ---- prior-matching term (models/dmm.py:540-545) ------------------------------
+  if (a->match_mult > 0.f) {
+    if (external && !a->eps_match) return fail(BFVI_ERR_ARG, "eps_match missing");
+    bfvi::MatchParams mp;
+    memset(&mp, 0, sizeof(mp));
+    for (int d = 0; d < 2; ++d) {
+      mp.trans_w[d] = params + lay.trans[d].begin;
+      mp.g_trans[d] = with_grad ? grads + lay.trans[d].begin : nullptr;
+    }
+    mp.z0_mean = params + lay.z0_mean; mp.z0_log_std = params + lay.z0_log_std;
+    mp.g_z0_mean = with_grad ? grads + lay.z0_mean : nullptr;
+    mp.g_z0_log_std = with_grad ? grads + lay.z0_log_std : nullptr;
+    mp.eps = a->eps_match; mp.seed = a->seed; mp.K = a->match_particles; mp.min_std = m->min_std;
+    mp.coef_static = a->match_mult * a->kld_mult;
+    if (a->match_count < 0.f) {
+      auto k = bfvi::count_mask_kernel;
+      BFVI_LAUNCH(k, dim3(grid_for(tb, 256, 4)), dim3(256), 0, st, a->seq_mask, tb, count);
+      BFVI_CHECK_CUDA();
+      ++n_launch;
+      mp.count = count;
+    } else {
+      mp.count = nullptr;
+      mp.coef_static *= a->match_count;
+    }
+    mp.loss_acc = acc; mp.with_grad = with_grad ? 1 : 0;
+    if (int rc = dispatch_match(m, mp, st)) return rc;
+    ++n_launch;
+  }
+
+  if (S > 0 && (a->f_mult != 0.f || a->s_mult != 0.f)) {
+    // ---- encode every modality once (models/dmm.py:165-173) ----------------------
+    for (int i = 0; i < M; ++i) {
+      if (int rc = bfvi_encode_fwd(m, params, i, a->inputs[i], tb, obs_mean + (size_t)i * pl.n_tbz,
+                                   obs_std + (size_t)i * pl.n_tbz, obs_mask + (size_t)i * tb, stream))
+        return rc;
+      ++n_launch;
+    }
+    auto obs_expert = [&](int i) {
+      bfvi_expert e;
+      memset(&e, 0, sizeof(e));
+      e.mean = obs_mean + (size_t)i * pl.n_tbz; e.std = obs_std + (size_t)i * pl.n_tbz;
+      e.mask = obs_mask + (size_t)i * tb;
+      e.stride_s = 0; e.stride_t = (int64_t)B * Z; e.stride_b = Z;
+      e.mstride_s = 0; e.mstride_t = B; e.mstride_b = 1;
+      e.d_mean = with_grad ? dobs_mean + (size_t)i * pl.n_tbz : nullptr;
+      e.d_std = with_grad ? dobs_std + (size_t)i * pl.n_tbz : nullptr;
+      e.kind = BFVI_EXPERT_TENSOR;
+      return e;
+    };
+    auto base_args = [&]() {
+      bfvi_filter_args f;
+      memset(&f, 0, sizeof(f));
+      f.T = T; f.B = B; f.S = S;
+      f.n_experts = M;
+      for (int i = 0; i < M; ++i) f.experts[i] = obs_expert(i);
+      for (int s = 0; s < S; ++s) f.set_expert_bits[s] = pl.set_bits[s];
+      f.sample = a->sample; f.sample_init = a->sample_init;
+      f.noise.seed = a->seed; f.noise.b_offset = a->b_offset;
+      f.seq_mask = a->seq_mask;
+      f.loss_acc = acc;
+      return f;
+    };
+
+    // pass A: f_mode filtering ELBO (models/dmm.py:547-549)
+    bfvi_filter_args fa = base_args();
+    fa.direction = a->f_mode == BFVI_MODE_BFILTER ? BFVI_DIR_BWD : BFVI_DIR_FWD;
+    fa.n_particles = 1;
+    fa.noise.eps = a->eps_filt; fa.noise.stream_id = 1;
+    fa.infer_mean = A(0); fa.infer_std = A(1); fa.prior_mean = A(2); fa.prior_std = A(3); fa.samples = A(4);
+    fa.kl_weight = a->f_mult * a->kld_mult;
+    // pass B: filtering pass of s_mode with K particles (models/dmm.py:465-470,551-553)
+    bfvi_filter_args fb = base_args();
+    fb.direction = a->s_mode == BFVI_MODE_FSMOOTH ? BFVI_DIR_BWD : BFVI_DIR_FWD;
+    fb.n_particles = a->train_particles;
+    fb.sample_init = 0;
+    fb.noise.eps = a->eps_sflt; fb.noise.stream_id = 2;
+    fb.infer_mean = Bf(0); fb.infer_std = Bf(1); fb.prior_mean = Bf(2); fb.prior_std = Bf(3);
+    fb.samples = nullptr; fb.kl_weight = 0.f; fb.loss_acc = nullptr;
+    // pass C: smoothing pass (models/dmm.py:473-489)
+    bfvi_filter_args fc = base_args();
+    fc.direction = a->s_mode == BFVI_MODE_FSMOOTH ? BFVI_DIR_FWD : BFVI_DIR_BWD;
+    fc.n_particles = 1;
+    fc.noise.eps = a->eps_ssmt; fc.noise.stream_id = 3;
+    {
+      bfvi_expert e;
+      memset(&e, 0, sizeof(e));
+      e.mean = Bf(2); e.std = Bf(3); e.mask = nullptr;
+      e.stride_s = (int64_t)pl.n_tbz; e.stride_t = (int64_t)B * Z; e.stride_b = Z;
+      e.d_mean = with_grad ? Bf(4) : nullptr; e.d_std = with_grad ? Bf(5) : nullptr;
+      e.kind = BFVI_EXPERT_TENSOR; e.zero_mask_last_t = 1;
+      fc.experts[M] = e;
+      memset(&e, 0, sizeof(e));
+      e.kind = BFVI_EXPERT_INV_PRIOR;
+      fc.experts[M + 1] = e;
+      fc.n_experts = M + 2;
+      for (int s = 0; s < S; ++s) fc.set_expert_bits[s] = pl.set_bits[s] | (1u << M) | (1u << (M + 1));
+    }
+    fc.infer_mean = C(0); fc.infer_std = C(1); fc.prior_mean = C(2); fc.prior_std = C(3); fc.samples = C(4);
+    fc.kl_weight = a->s_mult * a->kld_mult;
+    if (external) {
+      if (a->f_mult != 0.f && !fa.noise.eps && (a->sample || a->sample_init)) return fail(BFVI_ERR_ARG, "eps_filt missing");
+      if (a->s_mult != 0.f && a->train_particles > 0 && !fb.noise.eps) return fail(BFVI_ERR_ARG, "eps_sflt missing");
+      if (a->s_mult != 0.f && !fc.noise.eps && (a->sample || a->sample_init)) return fail(BFVI_ERR_ARG, "eps_ssmt missing");
+    }
+
+    const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
+    if (do_f) { if (int rc = bfvi_filter_fwd(m, params, &fa, stream)) return rc; ++n_launch; }
+    if (do_s) {
+      if (int rc = bfvi_filter_fwd(m, params, &fb, stream)) return rc; ++n_launch;
+      if (int rc = bfvi_filter_fwd(m, params, &fc, stream)) return rc; ++n_launch;
+    }
+    // ---- decoders + NLL (+ their backward) on the samples of passes A and C --------
+    for (int pass = 0; pass < 2; ++pass) {
+      if ((pass == 0 && !do_f) || (pass == 1 && !do_s)) continue;
+      const float mult = pass == 0 ? a->f_mult : a->s_mult;
+      float* samp = pass == 0 ? A(4) : C(4);
+      float* dsamp = with_grad ? (pass == 0 ? A(5) : C(5)) : nullptr;
+      for (int s = 0; s < S; ++s)
+        for (int i = 0; i < M; ++i) {
+          if (!((pl.set_bits[s] >> i) & 1u) || a->rec_mults[i] == 0.f) continue;
+          if (int rc = bfvi_decode_nll(m, params, grads, i, samp + (size_t)s * pl.n_tbz, a->targets[i],
+                                       a->seq_mask, tb, mult * a->rec_mults[i], acc,
+                                       dsamp ? dsamp + (size_t)s * pl.n_tbz : nullptr, stream))
+            return rc;
+          ++n_launch;
+        }
+    }
+    // ---- backward through the three passes and the encoders ------------------------
+    if (with_grad) {
+      if (do_s) {
+        fc.d_samples = C(5);
+        if (int rc = bfvi_filter_bwd(m, params, grads, &fc, stream)) return rc; ++n_launch;
+        fb.d_prior_mean = Bf(4); fb.d_prior_std = Bf(5);
+        if (int rc = bfvi_filter_bwd(m, params, grads, &fb, stream)) return rc; ++n_launch;
+      }
+      if (do_f) {
+        fa.d_samples = A(5);
+        if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream)) return rc; ++n_launch;
+      }
+      for (int i = 0; i < M; ++i) {
+        if (int rc = bfvi_encode_bwd(m, params, grads, i, a->inputs[i], tb, dobs_mean + (size_t)i * pl.n_tbz,
+                                     dobs_std + (size_t)i * pl.n_tbz, stream))
+          return rc;
+        ++n_launch;
+      }
+    }
+  }
+  auto k = bfvi::finalize_loss_kernel;
+  BFVI_LAUNCH(k, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
+  BFVI_CHECK_CUDA();
+  ++n_launch;
+  if (launches) *launches = n_launch;
+  return BFVI_OK;
+}
+
+}  // extern "C"

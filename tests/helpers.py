@@ -1,0 +1,111 @@
+"""Shared test plumbing: call the C ABI directly on torch tensors.
+
+The same code drives (a) the emulated kernels on CPU tensors (tests/emu, a
+development check of kernel logic) and (b) the real CUDA library on cuda tensors
+(`-m gpu`, the parity tests proper)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+
+from multimodal_dmm_b200 import _lib  # noqa: E402
+
+
+def emu_library():
+    import build_emu
+    return _lib.Library(build_emu.build())
+
+
+def aligned_empty(nbytes, device, align=256):
+    buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
+    off = (-buf.data_ptr()) % align
+    return buf[off:off + nbytes]
+
+
+def fixture_model(fx):
+    dists = ['Normal'] * len(fx['modalities'])
+    return _lib.make_model(fx['dims'], dists, fx['z_dim'], fx['h_dim'], fx['min_std']), dists
+
+
+def pack_params(lib, model, modalities, dists, state_dict, device):
+    lay = lib.layout(model)
+    flat = torch.zeros(lay.total, dtype=torch.float32)
+    for key, off in _lib.param_slots(modalities, dists, lay):
+        v = state_dict[key].reshape(-1).float()
+        flat[off:off + v.numel()] = v
+    return flat.to(device), lay
+
+
+def unpack(lib, model, modalities, dists, flat, like):
+    lay = lib.layout(model)
+    out = {}
+    flat = flat.cpu()
+    for key, off in _lib.param_slots(modalities, dists, lay):
+        n = like[key].numel()
+        out[key] = flat[off:off + n].reshape(like[key].shape).clone()
+    return out
+
+
+def step_args(fx, device, noise=None, seed=0, kwargs=None):
+    """Builds bfvi_step_args for a golden fixture; returns (args, keepalive)."""
+    kw = dict(fx['step_kwargs'])
+    kw.update(kwargs or {})
+    mods = fx['modalities']
+    t_max, b_dim = fx['mask'].shape[:2]
+    a = _lib.StepArgs()
+    keep = []
+    a.T, a.B = t_max, b_dim
+    for i, m in enumerate(mods):
+        x = fx['inputs'][m].to(device).contiguous()
+        y = fx['targets'][m].to(device).contiguous()
+        keep += [x, y]
+        a.inputs[i], a.targets[i] = x.data_ptr(), y.data_ptr()
+        a.rec_mults[i] = float(fx['rec_mults'].get(m, 1.0))
+    mask = fx['mask'].reshape(t_max, b_dim).to(torch.uint8).to(device).contiguous()
+    keep.append(mask)
+    a.seq_mask = mask.data_ptr()
+    a.kld_mult = float(fx['kld_mult'])
+    a.uni_loss = int(kw.get('uni_loss', True))
+    a.f_mode = _lib.MODE_CODES[kw.get('f_mode', 'bfilter')]
+    a.s_mode = _lib.MODE_CODES[kw.get('s_mode', 'fsmooth')]
+    a.f_mult, a.s_mult = float(kw.get('f_mult', 0.5)), float(kw.get('s_mult', 0.5))
+    a.match_mult = float(kw.get('match_mult', 0.01))
+    a.train_particles = int(kw.get('train_particles', 25))
+    a.match_particles = int(kw.get('match_particles', 50))
+    a.sample, a.sample_init = int(kw.get('sample', True)), int(kw.get('sample_init', False))
+    a.seed, a.b_offset, a.match_count = seed, 0, -1.0
+    if noise is not None:
+        for name, field in (('match', 'eps_match'), ('filt', 'eps_filt'), ('sflt', 'eps_sflt'),
+                            ('ssmt', 'eps_ssmt')):
+            t = noise[name].to(device).contiguous()
+            keep.append(t)
+            setattr(a, field, t.data_ptr())
+    return a, keep
+
+
+def run_step(lib, fx, device, with_grad=True, noise='fixture', seed=0, kwargs=None):
+    """Calls bfvi_step_fwd_bwd; returns (loss float, {param: grad of the summed loss})."""
+    model, dists = fixture_model(fx)
+    mods = fx['modalities']
+    flat, lay = pack_params(lib, model, mods, dists, fx['state_dict'], device)
+    nz = fx['noise'] if noise == 'fixture' else noise
+    a, keep = step_args(fx, device, nz, seed, kwargs)
+    nbytes = C.c_size_t(0)
+    lib.call('bfvi_step_workspace', C.byref(model), C.byref(a), C.byref(nbytes))
+    ws = aligned_empty(nbytes.value, device)
+    grads = torch.full((lay.total,), float('nan'), dtype=torch.float32, device=device) if with_grad else None
+    loss = torch.zeros(1, dtype=torch.float32, device=device)
+    launches = C.c_int32(0)
+    stream = None
+    if device != 'cpu':
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.call('bfvi_step_fwd_bwd', C.byref(model), _lib.ptr(flat), _lib.ptr(grads), C.byref(a),
+             _lib.ptr(ws), C.c_size_t(nbytes.value), _lib.ptr(loss), C.byref(launches), stream)
+    if device != 'cpu':
+        torch.cuda.synchronize()
+    g = unpack(lib, model, mods, dists, grads, fx['state_dict']) if with_grad else None
+    return loss.item(), g, launches.value

@@ -1,0 +1,30 @@
+"""Kernel-logic check on CPU: the CUDA sources compiled against the SIMT emulator
+(tests/emu) must reproduce the reference's golden step outputs.  Development
+tool; the parity tests proper are the `-m gpu` ones."""
+import pytest
+
+from conftest import golden_names, load_golden, rel_err
+import helpers
+
+SMALL = [n for n in golden_names() if n != 'medium_dims']
+
+
+@pytest.fixture(scope='module')
+def lib():
+    return helpers.emu_library()
+
+
+@pytest.mark.parametrize('name', SMALL)
+def test_step_loss_and_grads(lib, name):
+    fx = load_golden(name)
+    loss, grads, launches = helpers.run_step(lib, fx, 'cpu')
+    assert launches > 0
+    ref = fx['ref_loss_fp64']
+    assert abs(loss - ref) / abs(ref) < 1e-4, (loss, ref)
+    n = float(sum(fx['lengths']))
+    for k, g_ref in fx['ref_grads_fp64'].items():
+        g = grads[k] / n
+        if g_ref.norm() == 0:
+            assert g.norm() == 0, k
+        else:
+            assert rel_err(g, g_ref) < 1e-3, (k, rel_err(g, g_ref))
