@@ -198,6 +198,10 @@ int bfvi_encode_bwd(const bfvi_model* model, const float* params, float* grads,
 int bfvi_decode_fwd(const bfvi_model* model, const float* params, int32_t mod,
                     const float* z, int64_t n_rows, float* mean, float* std,
                     void* stream);
+/* Backward of bfvi_decode_fwd: accumulates into grads and d_z (+=, nullable). */
+int bfvi_decode_bwd(const bfvi_model* model, const float* params, float* grads,
+                    int32_t mod, const float* z, int64_t n_rows, const float* d_mean,
+                    const float* d_std, float* d_z, void* stream);
 /* Decoder + losses.nll_gauss (models/losses.py:68-89) fused, forward and
  * backward in one pass: loss_acc[0] += weight * NLL; d_z (+=, nullable) and
  * grads (nullable) receive gradients scaled by weight.  row_mask (n_rows) u8 is

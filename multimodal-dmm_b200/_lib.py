@@ -103,6 +103,8 @@ SYMBOLS = {
                                   C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'bfvi_decode_fwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    'bfvi_decode_bwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
+                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'bfvi_decode_nll': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),

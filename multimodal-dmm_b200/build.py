@@ -1,0 +1,38 @@
+"""In-tree nvcc build of libbfvi_b200.so for sm_100a (B200)."""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+OUT = os.path.join(HERE, 'libbfvi_b200.so')
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+              '--shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [
+        os.path.join(os.path.dirname(HERE), 'include', 'bfvi.h')]
+
+
+def up_to_date():
+    return os.path.exists(OUT) and all(
+        os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources())
+
+
+def build(force=False, verbose=False):
+    """Compiles every CUDA source into one shared library next to this file."""
+    if not force and up_to_date():
+        return OUT
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: cannot build libbfvi_b200.so')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [
+        os.path.join(CSRC, 'bfvi_api.cu'), '-o', OUT]
+    subprocess.run(cmd, check=True)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force=True, verbose=True))

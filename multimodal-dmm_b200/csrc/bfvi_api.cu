@@ -377,6 +377,25 @@ int bfvi_decode_fwd(const bfvi_model* m, const float* params, int32_t mod, const
   return launch_mlp_fwd(m->h_dim, mp, (cudaStream_t)stream);
 }
 
+int bfvi_decode_bwd(const bfvi_model* m, const float* params, float* grads, int32_t mod,
+                    const float* z, int64_t n_rows, const float* d_mean, const float* d_std,
+                    float* d_z, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (mod < 0 || mod >= m->n_mods) return fail(BFVI_ERR_ARG, "bad modality index");
+  if (m->dists[mod] != BFVI_DIST_NORMAL) return fail(BFVI_ERR_UNSUPPORTED, "only Normal decoders are fused");
+  if (!params || !grads || !z || !d_mean || !d_std || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.dec[mod].begin;
+  mp.g = grads + lay.dec[mod].begin;
+  mp.off = mlp_offsets(lay.dec[mod]);
+  mp.n_in = m->z_dim; mp.n_out = m->dims[mod]; mp.n_rows = n_rows;
+  mp.x = z; mp.d_mean = d_mean; mp.d_std = d_std; mp.d_x = d_z;
+  return launch_mlp_bwd(m->h_dim, false, mp, (cudaStream_t)stream);
+}
+
 int bfvi_decode_nll(const bfvi_model* m, const float* params, float* grads, int32_t mod,
                     const float* z, const float* target, const uint8_t* row_mask, int64_t n_rows,
                     float weight, double* loss_acc, float* d_z, void* stream) {

@@ -892,7 +892,7 @@ __global__ void __launch_bounds__(kMlpWarps * 32) mlp_bwd_kernel(const __grid_co
     }
 #pragma unroll
     for (int j = 0; j < H; ++j) dh[j] = h[j] > 0.f ? dh[j] : 0.f;
-    if (DECODER && p.d_x != nullptr && ok) {
+    if (p.d_x != nullptr && ok) {
       for (int i = 0; i < p.n_in; ++i) {
         float v = 0.f;
 #pragma unroll

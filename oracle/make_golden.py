@@ -235,6 +235,14 @@ def main():
         fixture['ref_grads_fp32'] = grads32
         fixture['ref_grads_fp64'] = {k: v.to(torch.float64) for k, v in grads64.items()}
         fixture['ref_forward_fp32'] = fwd
+        if case['name'] == 'spirals_ragged':
+            # seeded construction of the reference (spirals.py:44-51 shapes): lets a
+            # CPU test check that our module tree initialises bit-identically
+            models = ref_shim.import_reference_models()
+            torch.manual_seed(1)
+            ref0 = models.MultiDMM(case['modalities'], case['dims'], h_dim=case['h_dim'],
+                                   z_dim=case['z_dim'], device=torch.device('cpu'))
+            fixture['seeded_init_seed1'] = {k: v.clone() for k, v in ref0.state_dict().items()}
         fixture['provenance'] = (
             'generated by oracle/make_golden.py from the unmodified reference '
             '/root/reference/models/dmm.py (torch %s, CPU); grads are of '

@@ -1,0 +1,163 @@
+"""Parity of the Python drop-in API (MultiDMM.step / forward / losses) on CUDA
+against the reference's golden outputs and the oracle."""
+import pytest
+import torch
+
+import bfvi_oracle as bo
+from conftest import golden_names, load_golden, rel_err
+import multimodal_dmm_b200.models as models
+
+SMALL = [n for n in golden_names() if n != 'medium_dims']
+ELBO_TOL, GRAD_TOL = 1e-4, 1e-3
+pytestmark = pytest.mark.gpu
+
+
+def build(fx):
+    m = models.MultiDMM(fx['modalities'], fx['dims'], h_dim=fx['h_dim'], z_dim=fx['z_dim'],
+                        min_std=fx['min_std'], device=torch.device('cuda:0'))
+    m.load_state_dict(fx['state_dict'])
+    return m
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.parametrize('name', SMALL)
+def test_step_api_matches_reference_golden(name):
+    fx = load_golden(name)
+    m = build(fx)
+    m.train()
+    loss = m.step(cuda(fx['inputs']), fx['mask'].cuda(), fx['kld_mult'], fx['rec_mults'],
+                  targets=cuda(fx['targets']), lengths=fx['lengths'], noise=fx['noise'],
+                  **fx['step_kwargs'])
+    assert loss.dim() == 0 and loss.requires_grad
+    ref = fx['ref_loss_fp64']
+    assert abs(loss.item() - ref) / abs(ref) < ELBO_TOL
+    loss /= sum(fx['lengths'])            # trainer.py:242 divides in place
+    loss.backward()
+    for k, p in m.named_parameters():
+        g_ref = fx['ref_grads_fp64'][k]
+        g = torch.zeros_like(g_ref) if p.grad is None else p.grad.cpu()
+        if g_ref.norm() == 0:
+            assert g.norm() == 0, k
+        else:
+            assert rel_err(g, g_ref) < GRAD_TOL, (k, rel_err(g, g_ref))
+
+
+def _assemble(draws, t_max, direction):
+    order = list(range(t_max - 1, -1, -1)) if direction == 'bwd' else list(range(t_max))
+    k, b, z = draws[0].shape
+    eps = torch.empty(t_max, b, k, z)
+    for i, t in enumerate(order):
+        eps[t] = draws[i].permute(1, 0, 2)
+    return eps.cuda()
+
+
+@pytest.mark.parametrize('name', ['spirals_ragged', 'gauss3_ffilter', 'bsmooth_full'])
+def test_forward_modes_match_reference_golden(name):
+    fx = load_golden(name)
+    m = build(fx).eval()
+    t_max = max(fx['lengths'])
+    for key, ref in fx['ref_forward_fp32'].items():
+        mode, sample, kf = key.split('/')
+        sample, kf = bool(int(sample)), int(kf)
+        draws = list(ref['draws'])
+        flt_dir = 'fwd' if mode in ('ffilter', 'bsmooth') else 'bwd'
+        eps_flt = eps_smt = None
+        if sample or kf > 1:
+            eps_flt = _assemble(draws[:t_max], t_max, flt_dir)
+            draws = draws[t_max:]
+        if mode in ('fsmooth', 'bsmooth') and sample:
+            eps_smt = _assemble(draws[:t_max], t_max, 'fwd' if mode == 'fsmooth' else 'bwd')
+        with torch.no_grad():
+            infer, prior, recon = m(cuda(fx['inputs']), lengths=fx['lengths'], mode=mode, sample=sample,
+                                    flt_particles=kf, smt_particles=1, noise=(eps_flt, eps_smt))
+        for a, b in zip(list(infer) + list(prior), ref['infer'] + ref['prior']):
+            assert torch.allclose(a.cpu(), b, rtol=2e-4, atol=2e-5, equal_nan=True), key
+        for mod in fx['modalities']:
+            for a, b in zip(recon[mod], ref['recon'][mod]):
+                assert torch.allclose(a.cpu(), b, rtol=2e-4, atol=2e-5, equal_nan=True), key
+
+
+def test_masks_bit_exact():
+    fx = load_golden('spirals_half_missing')
+    m = build(fx).eval()
+    with torch.no_grad():
+        _, _, masks = m.encode(cuda(fx['inputs']))
+    for i, mod in enumerate(fx['modalities']):
+        assert torch.equal(masks[i].cpu(), ~torch.isnan(fx['inputs'][mod]).any(dim=-1))
+
+
+def test_composed_forward_is_differentiable_and_matches_oracle():
+    """forward() -> loss() -> backward() through the op-level autograd Functions."""
+    fx = load_golden('gauss3_ffilter')
+    m = build(fx).train()
+    t_max, b_dim, z = max(fx['lengths']), len(fx['lengths']), fx['z_dim']
+    g = torch.Generator().manual_seed(5)
+    k = 6
+    eps_flt = torch.randn(t_max, b_dim, k, z, generator=g)
+    eps_smt = torch.randn(t_max, b_dim, 1, z, generator=g)
+    infer, prior, recon = m(cuda(fx['inputs']), lengths=fx['lengths'], mode='fsmooth',
+                            flt_particles=k, noise=(eps_flt.cuda(), eps_smt.cuda()))
+    loss = m.loss(cuda(fx['targets']), infer, prior, recon, fx['mask'].cuda(), 0.7, fx['rec_mults'])
+    loss.backward()
+    params = {kk: v.clone().double().requires_grad_(True) for kk, v in fx['state_dict'].items()}
+    tape = [eps_flt[t].permute(1, 0, 2).contiguous() for t in range(t_max - 1, -1, -1)] + \
+           [eps_smt[t].permute(1, 0, 2).contiguous() for t in range(t_max)]
+    orc = bo.OracleDMM(fx['modalities'], fx['dims'], params, h_dim=fx['h_dim'], z_dim=z,
+                       min_std=fx['min_std'], draw=bo.NoiseTape(tape))
+    cast = lambda d: {kk: v.double() for kk, v in d.items()}
+    inf_o, pri_o, rec_o = orc.forward(cast(fx['inputs']), fx['lengths'], mode='fsmooth', flt_particles=k)
+    ref = orc.loss(cast(fx['targets']), inf_o, pri_o, rec_o, fx['mask'], 0.7, fx['rec_mults'])
+    ref.backward()
+    assert abs(loss.item() - ref.item()) / abs(ref.item()) < ELBO_TOL
+    for kk, p in m.named_parameters():
+        g_ref = params[kk].grad
+        if g_ref is None or g_ref.norm() == 0:
+            assert p.grad is None or p.grad.norm() == 0, kk
+        else:
+            assert rel_err(p.grad.cpu(), g_ref) < GRAD_TOL, (kk, rel_err(p.grad.cpu(), g_ref))
+
+
+def test_losses_match_formulas():
+    g = torch.Generator().manual_seed(0)
+    m1, m2 = torch.randn(7, 5, 4, generator=g), torch.randn(7, 5, 4, generator=g)
+    s1, s2 = torch.rand(7, 5, 4, generator=g) + 0.1, torch.rand(7, 5, 4, generator=g) + 0.1
+    mask = torch.rand(7, 5, 1, generator=g) > 0.3
+    x = torch.randn(7, 5, 4, generator=g)
+    x[torch.rand(7, 5, 4, generator=g) < 0.2] = float('nan')
+    cpu = [t.clone().double().requires_grad_(True) for t in (m1, s1, m2, s2)]
+    gpu = [t.clone().cuda().requires_grad_(True) for t in (m1, s1, m2, s2)]
+    ref = bo.kld_gauss(*cpu, mask) + bo.nll_gauss(cpu[0], cpu[1], x.double(), mask)
+    out = models.losses.kld_gauss(*gpu, mask.cuda()) + \
+        models.losses.nll_gauss(gpu[0], gpu[1], x.cuda(), mask.cuda())
+    ref.backward()
+    out.backward()
+    assert abs(out.item() - ref.item()) / abs(ref.item()) < 1e-5
+    for a, b in zip(gpu, cpu):
+        assert rel_err(a.grad.cpu(), b.grad) < 1e-5
+
+
+def test_trainer_contract_adam_steps():
+    """The loop of trainer.py:225-252: step -> /= sum(lengths) -> backward -> clip ->
+    Adam.step -> zero_grad; loss must go down and parameters must stay aliased to
+    the flat buffer the kernels read."""
+    fx = load_golden('spirals_ragged')
+    m = build(fx).train()
+    m.noise_seed = 123
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    inputs, targets, mask = cuda(fx['inputs']), cuda(fx['targets']), fx['mask'].cuda()
+    hist = []
+    for _ in range(25):
+        b_loss = m.step(inputs, mask, 1.0, fx['rec_mults'], targets=targets, lengths=fx['lengths'])
+        hist.append(b_loss.item())
+        b_loss /= sum(fx['lengths'])
+        b_loss.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 10.0)
+        opt.step()
+        opt.zero_grad()
+    assert hist[-1] < hist[0]
+    assert m.fused_step_available and m.last_launches > 0
+    sd = m.state_dict()
+    assert set(sd.keys()) == set(fx['state_dict'].keys())
