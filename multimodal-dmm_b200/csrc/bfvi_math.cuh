@@ -43,6 +43,8 @@ struct GtfLayout {
 __device__ __forceinline__ float softplus_f(float x) {      // torch Softplus(beta=1, threshold=20)
   return x > 20.f ? x : log1pf(expf(x));
 }
+// NaN-propagating ReLU like torch.relu (fmaxf would swallow a NaN)
+__device__ __forceinline__ float relu_f(float x) { return x < 0.f ? 0.f : x; }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
 __device__ __forceinline__ float softplus_grad(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
 __device__ __forceinline__ float sign_f(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
@@ -104,12 +106,12 @@ __device__ __forceinline__ void gtf_forward(const float* __restrict__ W, float m
   using L = GtfLayout<Z, H>;
   matvec<H, Z>(W + L::G0W, W + L::G0B, z, a.h1);
 #pragma unroll
-  for (int h = 0; h < H; ++h) a.h1[h] = fmaxf(a.h1[h], 0.f);
+  for (int h = 0; h < H; ++h) a.h1[h] = relu_f(a.h1[h]);
   matvec<Z, H>(W + L::G2W, W + L::G2B, a.h1, a.g);
   matvec<Z, Z>(W + L::LW, W + L::LB, z, a.lin);
   matvec<H, Z>(W + L::N0W, W + L::N0B, z, a.h3);
 #pragma unroll
-  for (int h = 0; h < H; ++h) a.h3[h] = fmaxf(a.h3[h], 0.f);
+  for (int h = 0; h < H; ++h) a.h3[h] = relu_f(a.h3[h]);
   matvec<Z, H>(W + L::N2W, W + L::N2B, a.h3, a.nl);
   matvec<Z, Z>(W + L::SW, W + L::SB, a.nl, a.as);
 #pragma unroll

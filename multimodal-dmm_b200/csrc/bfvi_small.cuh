@@ -78,7 +78,7 @@ __device__ __forceinline__ void poe_step_forward(const bfvi_filter_args& a, unsi
   for (int i = 0; i < Z; ++i) {
     const float tp = poe_prec(ps[i]);
     S[i] = tp;
-    N[i] = pm[i] * tp;
+    N[i] = __fmul_rn(pm[i], tp);
   }
   for (int e = 0; e < a.n_experts; ++e) {
     if (!((bits >> e) & 1u)) continue;
@@ -94,9 +94,12 @@ __device__ __forceinline__ void poe_step_forward(const bfvi_filter_args& a, unsi
       float mean, std;
       if (ex.kind == BFVI_EXPERT_INV_PRIOR) { mean = gm[i]; std = -gs[i]; }   // models/dmm.py:476-477
       else { mean = pmean[i]; std = pstd[i]; }
+      // products are rounded before they are summed (no FMA contraction), like the
+      // reference's `sum(mean * T)`: when the inverse-prior expert cancels the prior
+      // exactly (0/0 -> NaN -> 0, models/dgts.py:48-49) the cancellation must be exact
       const float te = poe_prec(std) * w;
-      S[i] += te;
-      N[i] = fmaf(mean * w, te, N[i]);
+      S[i] = __fadd_rn(S[i], te);
+      N[i] = __fadd_rn(N[i], __fmul_rn(mean * w, te));
     }
   }
 #pragma unroll
@@ -774,7 +777,7 @@ __device__ __forceinline__ bool mlp_hidden(const float* sW, const MlpOffsets& o,
     for (int j = 0; j < H; ++j) h[j] = fmaf(sW[o.w1 + j * n_in + i], xi, h[j]);
   }
 #pragma unroll
-  for (int j = 0; j < H; ++j) h[j] = fmaxf(h[j], 0.f);
+  for (int j = 0; j < H; ++j) h[j] = relu_f(h[j]);
   return any_nan;
 }
 template <int H>

@@ -31,6 +31,11 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def args_need_grad(keep):
+    """`keep` carries the caller's grad mode as its first element."""
+    return keep[0]
+
+
 def _aligned_empty(nbytes, device, align=256):
     buf = torch.empty(nbytes + align, dtype=torch.uint8, device=device)
     off = (-buf.data_ptr()) % align
@@ -44,9 +49,10 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, args, keep, *params):
         lib = _lib.load()
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # grad mode is always off inside Function.forward: the caller decides
+        need_grad = bool(args_need_grad(keep)) and any(p.requires_grad for p in params)
         flat_grad = torch.empty_like(model._flat) if need_grad else None
-        loss = torch.empty(1, dtype=torch.float32, device=model._flat.device)
+        loss = torch.empty((), dtype=torch.float32, device=model._flat.device)
         nbytes = C.c_size_t(0)
         lib.call('bfvi_step_workspace', C.byref(model._cmodel), C.byref(args), C.byref(nbytes))
         ws = model._workspace(nbytes.value)
@@ -56,7 +62,7 @@ class _StepFn(torch.autograd.Function):
                  _lib.ptr(loss), C.byref(launches), _stream())
         model.last_launches = launches.value
         ctx.model, ctx.flat_grad = model, flat_grad
-        return loss.reshape(())
+        return loss
 
     @staticmethod
     def backward(ctx, g):
@@ -507,7 +513,7 @@ class MultiDMM(MultiDGTS):
         t_max, b_dim = first.shape[:2]
         dev = self._flat.device
         a = _lib.StepArgs()
-        keep = []
+        keep = [torch.is_grad_enabled()]
 
         def dev_f32(t):
             if not t.is_cuda:

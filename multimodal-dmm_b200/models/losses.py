@@ -45,7 +45,7 @@ class _Kld(torch.autograd.Function):
                  _lib.ptr(out), _stream())
         ctx.save_for_backward(*t)
         ctx.rmask, ctx.z_dim, ctx.shapes = rmask, z_dim, [x.shape for x in (m1, s1, m2, s2)]
-        return out.to(torch.float32).reshape(())
+        return out.sum().to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):
@@ -82,7 +82,7 @@ class _NllGauss(torch.autograd.Function):
                  _lib.ptr(out), _stream())
         ctx.save_for_backward(*t)
         ctx.rmask, ctx.rows, ctx.shapes = rmask, rows, (mean.shape, std.shape)
-        return out.to(torch.float32).reshape(())
+        return out.sum().to(torch.float32)
 
     @staticmethod
     def backward(ctx, g):

@@ -59,6 +59,7 @@ def test_forward_modes_match_reference_golden(name):
     fx = load_golden(name)
     m = build(fx).eval()
     t_max = max(fx['lengths'])
+    failures = []
     for key, ref in fx['ref_forward_fp32'].items():
         mode, sample, kf = key.split('/')
         sample, kf = bool(int(sample)), int(kf)
@@ -73,11 +74,18 @@ def test_forward_modes_match_reference_golden(name):
         with torch.no_grad():
             infer, prior, recon = m(cuda(fx['inputs']), lengths=fx['lengths'], mode=mode, sample=sample,
                                     flt_particles=kf, smt_particles=1, noise=(eps_flt, eps_smt))
-        for a, b in zip(list(infer) + list(prior), ref['infer'] + ref['prior']):
-            assert torch.allclose(a.cpu(), b, rtol=2e-4, atol=2e-5, equal_nan=True), key
+        names = ['infer_mean', 'infer_std', 'prior_mean', 'prior_std']
+        pairs = list(zip(names, list(infer) + list(prior), ref['infer'] + ref['prior']))
         for mod in fx['modalities']:
-            for a, b in zip(recon[mod], ref['recon'][mod]):
-                assert torch.allclose(a.cpu(), b, rtol=2e-4, atol=2e-5, equal_nan=True), key
+            pairs += [('recon_' + mod, a, b) for a, b in zip(recon[mod], ref['recon'][mod])]
+        for nm, a, b in pairs:
+            a = a.cpu()
+            bad = ~torch.isclose(a, b, rtol=2e-4, atol=2e-5, equal_nan=True)
+            if bad.any():
+                idx = bad.nonzero()[:4].tolist()
+                failures.append((key, nm, int(bad.sum()), idx, [a[tuple(i)].item() for i in idx],
+                                 [b[tuple(i)].item() for i in idx]))
+    assert not failures, '\n'.join(str(f) for f in failures[:6])
 
 
 def test_masks_bit_exact():
