@@ -249,6 +249,23 @@ int bfvi_step_fwd_bwd(const bfvi_model* model, const float* params, float* grads
                       size_t workspace_bytes, float* loss_out, int32_t* launches,
                       void* stream);
 
+/* Same as bfvi_step_fwd_bwd, but brackets every phase of the step with CUDA events
+ * on `stream`, SYNCHRONISES, and writes the per-phase device time in milliseconds to
+ * the host array phase_ms[BFVI_N_PHASES] (measurement aid for bench.py's roofline). */
+enum {
+  BFVI_PHASE_MATCH = 0, BFVI_PHASE_ENCODE_FWD, BFVI_PHASE_FILTER_F_FWD,
+  BFVI_PHASE_FILTER_S_FLT_FWD, BFVI_PHASE_FILTER_S_SMT_FWD, BFVI_PHASE_DECODE_NLL,
+  BFVI_PHASE_FILTER_S_SMT_BWD, BFVI_PHASE_FILTER_S_FLT_BWD, BFVI_PHASE_FILTER_F_BWD,
+  BFVI_PHASE_ENCODE_BWD, BFVI_PHASE_FINALIZE, BFVI_N_PHASES
+};
+int bfvi_step_profile(const bfvi_model* model, const float* params, float* grads,
+                      const bfvi_step_args* args, void* workspace, size_t workspace_bytes,
+                      float* loss_out, float* phase_ms, void* stream);
+
+/* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
+ * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */
+int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream);
+
 /* Materialise the Philox stream (same generator the kernels use) as an external
  * noise tensor (S, T, B, K, Z) so the oracle can be run on identical draws. */
 int bfvi_dump_noise(uint64_t seed, uint32_t stream_id, uint32_t b_offset, int32_t S,

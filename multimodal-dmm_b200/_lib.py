@@ -15,6 +15,8 @@ DIST_CODES = {'Normal': 0, 'Bernoulli': 1, 'Categorical': 2}
 DIR_FWD, DIR_BWD = 0, 1
 MODE_CODES = {'bfilter': 0, 'ffilter': 1, 'fsmooth': 2, 'bsmooth': 3}
 EXPERT_TENSOR, EXPERT_INV_PRIOR = 0, 1
+PHASES = ('match', 'encode_fwd', 'filter_f_fwd', 'filter_s_flt_fwd', 'filter_s_smt_fwd', 'decode_nll',
+          'filter_s_smt_bwd', 'filter_s_flt_bwd', 'filter_f_bwd', 'encode_bwd', 'finalize')
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libbfvi_b200.so')
@@ -120,6 +122,10 @@ SYMBOLS = {
     'bfvi_step_fwd_bwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(StepArgs),
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32),
                                     C.c_void_p]),
+    'bfvi_step_profile': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(StepArgs),
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float),
+                                    C.c_void_p]),
+    'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_dump_noise': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }

@@ -491,6 +491,14 @@ int bfvi_dump_noise(uint64_t seed, uint32_t stream_id, uint32_t b_offset, int32_
   return BFVI_OK;
 }
 
+int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream) {
+  if (!out || iters < 1 || blocks < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::ffma_peak_kernel;
+  BFVI_LAUNCH(k, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, out, (int)iters);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
 static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
   if (int rc = check_model(m)) return rc;
   if (a == nullptr) return fail(BFVI_ERR_ARG, "step args null");
@@ -515,9 +523,20 @@ int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* by
   return BFVI_OK;
 }
 
-int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
-                      void* workspace, size_t workspace_bytes, float* loss_out, int32_t* launches,
-                      void* stream) {
+// Marks the start of a phase on the stream when a profile is being recorded.
+struct PhaseMarks {
+  cudaEvent_t ev[BFVI_N_PHASES + 1];
+  int used[BFVI_N_PHASES + 1];
+  bool on;
+  cudaStream_t st;
+  void begin(int phase) {
+    if (on && !used[phase]) { cudaEventRecord(ev[phase], st); used[phase] = 1; }
+  }
+};
+
+static int step_impl(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
+                     void* workspace, size_t workspace_bytes, float* loss_out, int32_t* launches,
+                     void* stream, PhaseMarks& pm) {
   if (int rc = check_step(m, a)) return rc;
   if (!params || !workspace || !loss_out) return fail(BFVI_ERR_ARG, "null argument");
   if (!a->seq_mask) return fail(BFVI_ERR_ARG, "seq_mask null");
@@ -556,6 +575,7 @@ int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, co
   const int S = pl.S;
 
   // ---- prior-matching term (models/dmm.py:540-545) ------------------------------
+  pm.begin(BFVI_PHASE_MATCH);
   if (a->match_mult > 0.f) {
     if (external && !a->eps_match) return fail(BFVI_ERR_ARG, "eps_match missing");
     bfvi::MatchParams mp;
@@ -586,6 +606,7 @@ int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, co
 
   if (S > 0 && (a->f_mult != 0.f || a->s_mult != 0.f)) {
     // ---- encode every modality once (models/dmm.py:165-173) ----------------------
+    pm.begin(BFVI_PHASE_ENCODE_FWD);
     for (int i = 0; i < M; ++i) {
       if (int rc = bfvi_encode_fwd(m, params, i, a->inputs[i], tb, obs_mean + (size_t)i * pl.n_tbz,
                                    obs_std + (size_t)i * pl.n_tbz, obs_mask + (size_t)i * tb, stream))
@@ -661,12 +682,16 @@ int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, co
     }
 
     const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
+    pm.begin(BFVI_PHASE_FILTER_F_FWD);
     if (do_f) { if (int rc = bfvi_filter_fwd(m, params, &fa, stream)) return rc; ++n_launch; }
+    pm.begin(BFVI_PHASE_FILTER_S_FLT_FWD);
     if (do_s) {
       if (int rc = bfvi_filter_fwd(m, params, &fb, stream)) return rc; ++n_launch;
+      pm.begin(BFVI_PHASE_FILTER_S_SMT_FWD);
       if (int rc = bfvi_filter_fwd(m, params, &fc, stream)) return rc; ++n_launch;
     }
     // ---- decoders + NLL (+ their backward) on the samples of passes A and C --------
+    pm.begin(BFVI_PHASE_DECODE_NLL);
     for (int pass = 0; pass < 2; ++pass) {
       if ((pass == 0 && !do_f) || (pass == 1 && !do_s)) continue;
       const float mult = pass == 0 ? a->f_mult : a->s_mult;
@@ -686,14 +711,18 @@ int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, co
     if (with_grad) {
       if (do_s) {
         fc.d_samples = C(5);
+        pm.begin(BFVI_PHASE_FILTER_S_SMT_BWD);
         if (int rc = bfvi_filter_bwd(m, params, grads, &fc, stream)) return rc; ++n_launch;
         fb.d_prior_mean = Bf(4); fb.d_prior_std = Bf(5);
+        pm.begin(BFVI_PHASE_FILTER_S_FLT_BWD);
         if (int rc = bfvi_filter_bwd(m, params, grads, &fb, stream)) return rc; ++n_launch;
       }
       if (do_f) {
         fa.d_samples = A(5);
+        pm.begin(BFVI_PHASE_FILTER_F_BWD);
         if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream)) return rc; ++n_launch;
       }
+      pm.begin(BFVI_PHASE_ENCODE_BWD);
       for (int i = 0; i < M; ++i) {
         if (int rc = bfvi_encode_bwd(m, params, grads, i, a->inputs[i], tb, dobs_mean + (size_t)i * pl.n_tbz,
                                      dobs_std + (size_t)i * pl.n_tbz, stream))
@@ -702,12 +731,47 @@ int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, co
       }
     }
   }
+  pm.begin(BFVI_PHASE_FINALIZE);
   auto k = bfvi::finalize_loss_kernel;
   BFVI_LAUNCH(k, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
   BFVI_CHECK_CUDA();
   ++n_launch;
   if (launches) *launches = n_launch;
   return BFVI_OK;
+}
+
+int bfvi_step_fwd_bwd(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
+                      void* workspace, size_t workspace_bytes, float* loss_out, int32_t* launches,
+                      void* stream) {
+  PhaseMarks pm;
+  pm.on = false;
+  return step_impl(m, params, grads, a, workspace, workspace_bytes, loss_out, launches, stream, pm);
+}
+
+int bfvi_step_profile(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
+                      void* workspace, size_t workspace_bytes, float* loss_out, float* phase_ms,
+                      void* stream) {
+  if (!phase_ms) return fail(BFVI_ERR_ARG, "phase_ms null");
+  PhaseMarks pm;
+  pm.on = true;
+  pm.st = (cudaStream_t)stream;
+  for (int i = 0; i <= BFVI_N_PHASES; ++i) { cudaEventCreate(&pm.ev[i]); pm.used[i] = 0; }
+  int rc = step_impl(m, params, grads, a, workspace, workspace_bytes, loss_out, nullptr, stream, pm);
+  if (rc == BFVI_OK) {
+    cudaEventRecord(pm.ev[BFVI_N_PHASES], pm.st);
+    cudaEventSynchronize(pm.ev[BFVI_N_PHASES]);
+    // phase i lasts from its marker to the next marker that was recorded
+    for (int i = 0; i < BFVI_N_PHASES; ++i) {
+      phase_ms[i] = 0.f;
+      if (!pm.used[i]) continue;
+      int j = i + 1;
+      while (j < BFVI_N_PHASES && !pm.used[j]) ++j;
+      cudaEventElapsedTime(&phase_ms[i], pm.ev[i], pm.ev[j]);
+    }
+    if (cudaGetLastError() != cudaSuccess) rc = fail(BFVI_ERR_CUDA, "event timing failed");
+  }
+  for (int i = 0; i <= BFVI_N_PHASES; ++i) cudaEventDestroy(pm.ev[i]);
+  return rc;
 }
 
 }  // extern "C"

@@ -1012,4 +1012,21 @@ dump_noise_kernel(uint64_t seed, unsigned stream_id, unsigned b_offset, int S, i
   }
 }
 
+// FP32 FFMA peak probe for the roofline denominator of the small-dim path: every
+// thread runs 16 independent FMA chains (register operands only).
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 1.0000001f, c = 1e-7f;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  if (s == 123.456f) out[0] = s;       // keeps the chains alive, practically never true
+}
+
 }  // namespace bfvi
