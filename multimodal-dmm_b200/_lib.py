@@ -19,7 +19,8 @@ PHASES = ('match', 'encode_fwd', 'filter_f_fwd', 'filter_s_flt_fwd', 'filter_s_s
           'filter_s_smt_bwd', 'filter_s_flt_bwd', 'filter_f_bwd', 'encode_bwd', 'finalize')
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbfvi_b200.so')
+# BFVI_LIB_PATH: tuning aid (tools/variants.py builds differently-tiled variants of the same library)
+LIB_PATH = os.environ.get('BFVI_LIB_PATH') or os.path.join(_HERE, 'libbfvi_b200.so')
 
 
 class Model(C.Structure):

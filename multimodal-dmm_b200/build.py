@@ -21,8 +21,14 @@ def up_to_date():
         os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources())
 
 
-def build(force=False, verbose=False):
-    """Compiles every CUDA source into one shared library next to this file."""
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compiles every CUDA source into one shared library next to this file.
+    `defines` / `out` build a tuning variant (tools/variants.py) beside the product."""
+    if out is not None:
+        nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+        subprocess.run([nvcc] + NVCC_FLAGS + ['-D%s' % d for d in defines] +
+                       [os.path.join(CSRC, 'bfvi_api.cu'), '-o', out], check=True)
+        return out
     if not force and up_to_date():
         return OUT
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'

@@ -4,6 +4,7 @@
 // on the caller's stream.  No device allocation, no global mutable state.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -112,38 +113,76 @@ int layout_matches(const bfvi_gtf_layout& l) {
          l.end - b == L::SIZE;
 }
 
+// Lane-group geometry for K particles with R rows per thread (bfvi_chain.cuh): among
+// the lane counts whose utilisation is within 10 % of the best, take the smallest
+// that still yields enough warp tasks to fill the machine, else the most parallel.
+void choose_lanes(int K, int R, int64_t chains, int* lanes, int* rounds) {
+  double best = 0.0;
+  double util[33];
+  for (int L = 1; L <= 32; ++L) {
+    const int cpw = 32 / L, rd = (K + L * R - 1) / (L * R);
+    util[L] = (double)cpw * K / (32.0 * R * rd);
+    if (util[L] > best) best = util[L];
+  }
+  const int sms = num_sms();
+  const int64_t want = (int64_t)(sms > 0 ? sms : 1) * 16;
+  int pick = 0;
+  if (const char* env = getenv("BFVI_LANES")) {          // test / tuning knob
+    const int v = atoi(env);
+    if (v >= 1 && v <= 32 && K > 1) pick = v;
+  }
+  for (int L = 1; L <= 32 && !pick; ++L)
+    if (util[L] >= 0.9 * best && (chains + 32 / L - 1) / (32 / L) >= want) pick = L;
+  if (!pick)
+    for (int L = 32; L >= 1 && !pick; --L)
+      if (util[L] >= 0.9 * best) pick = L;
+  *lanes = pick;
+  *rounds = (K + pick * R - 1) / (pick * R);
+}
+
+int task_grid(int64_t chains, int lanes, int warps_per_block) {
+  const int cpw = 32 / lanes;
+  const int64_t tasks = (chains + cpw - 1) / cpw;
+  int64_t blocks = (tasks + warps_per_block - 1) / warps_per_block;
+  const int64_t cap = (int64_t)(num_sms() > 0 ? num_sms() : 1) * 32;
+  if (blocks < 1) blocks = 1;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
 template <int Z, int H>
-int launch_filter_fwd(const bfvi::FilterParams& fp, cudaStream_t st) {
+int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
   const int64_t chains = (int64_t)a.S * a.B;
+  const int wpb = bfvi::kChainFwdThreads / 32;
   if (a.n_particles > 1) {
-    auto k = bfvi::filter_fwd_kernel<Z, H, true>;
-    const int wpb = bfvi::kFilterFwdThreads / 32;
-    BFVI_LAUNCH(k, dim3(grid_for(chains, wpb, 16)), dim3(bfvi::kFilterFwdThreads), 0, st, fp);
+    constexpr int R = 5;
+    choose_lanes(a.n_particles, R, chains, &fp.lanes, &fp.rounds);
+    auto k = bfvi::chain_fwd_kernel<Z, H, R>;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, wpb)), dim3(bfvi::kChainFwdThreads), 0, st, fp);
   } else {
-    auto k = bfvi::filter_fwd_kernel<Z, H, false>;
-    const int tpb = 64;     // few sequences per CTA: spread K == 1 chains over all SMs
-    BFVI_LAUNCH(k, dim3(grid_for(chains, tpb, 16)), dim3(tpb), 0, st, fp);
+    fp.lanes = 1; fp.rounds = 1;
+    auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, 1, wpb)), dim3(bfvi::kChainFwdThreads), 0, st, fp);
   }
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
 
 template <int Z, int H>
-int launch_filter_bwd(const bfvi::FilterParams& fp, cudaStream_t st) {
+int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
   const int64_t chains = (int64_t)a.S * a.B;
-  const size_t smem = bfvi::filter_bwd_smem_bytes<Z, H>();
-  const int threads = bfvi::kFilterBwdWarps * 32;
-  if (a.n_particles > 1) {
-    auto k = bfvi::filter_bwd_kernel<Z, H, true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    BFVI_LAUNCH(k, dim3(grid_for(chains, bfvi::kFilterBwdWarps, 2)), dim3(threads), smem, st, fp);
-  } else {
-    auto k = bfvi::filter_bwd_kernel<Z, H, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    BFVI_LAUNCH(k, dim3(grid_for(chains, threads, 2)), dim3(threads), smem, st, fp);
-  }
+  const size_t smem = bfvi::chain_bwd_smem_bytes<Z, H>();
+  const int threads = bfvi::kChainBwdWarps * 32;
+  const bfvi::WgSpec spec = bfvi::GtfPanels<Z, H>::spec();
+  if (bfvi::wg_rounds<bfvi::GtfPanels<Z, H>::TD, bfvi::kTX>(spec) != 1)
+    return fail(BFVI_ERR_UNSUPPORTED, "internal: weight-gradient tiling needs one round");
+  int rounds = 1;
+  choose_lanes(a.n_particles, 1, chains, &fp.lanes, &rounds);
+  fp.slices = (a.n_particles + fp.lanes - 1) / fp.lanes;
+  auto k = bfvi::chain_bwd_kernel<Z, H>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, bfvi::kChainBwdWarps)), dim3(threads), smem, st, fp);
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
@@ -245,6 +284,7 @@ bfvi::FilterParams make_filter_params(const bfvi_model* m, const bfvi_layout& la
   fp.g_z0_mean = grads ? grads + lay.z0_mean : nullptr;
   fp.g_z0_log_std = grads ? grads + lay.z0_log_std : nullptr;
   fp.min_std = m->min_std;
+  fp.lanes = 1; fp.rounds = 1; fp.slices = 1;
   return fp;
 }
 

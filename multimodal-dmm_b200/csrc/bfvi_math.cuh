@@ -1,7 +1,13 @@
 // bfvi_math.cuh — per-row device math of the BFVI step (forward and hand-derived
-// backward).  Everything here is register-level code on compile-time (Z, H) so the
-// loops unroll completely; weights are read from a shared-memory copy of the flat
-// parameter block as 128-bit broadcast loads.
+// backward) for the register-resident small-dim path.  Everything here is
+// register-level code on compile-time (Z, H) so the loops unroll completely.
+//
+// The gated transition is evaluated "unit-streaming": for every hidden unit the
+// pre-activation (a dot product with z), its ReLU and the unit's contribution to
+// the Z outputs are computed back to back, so no H-sized activation array ever
+// lives in registers (the v0 kernels spilled 1.5-2 KB per thread on exactly those
+// arrays).  Weights are read from a re-packed, unit-major shared-memory copy
+// (GtfPack) with 128-bit broadcast loads; R rows per thread share each load.
 //
 // Reference formulas (paths relative to the reference repository):
 //   GaussianGTF           models/common.py:43-68
@@ -39,162 +45,306 @@ struct GtfLayout {
   static constexpr int SIZE = SB + pad4(Z);
 };
 
+// Unit-major shared-memory packing of one GTF:
+//   gate unit h   : [ b0[h], W0[h][0..Z), W2[0..Z)[h] ]   (U floats, 16-byte aligned)
+//   nonlin unit h : same for the z_nonlin branch
+//   lin row o     : [ b[o], W[o][0..Z) ]                  (RW floats)
+//   std row o     : same for z_to_std
+//   B2G / B2N     : output biases of z_to_gate.2 / z_nonlin.2
+template <int Z, int H>
+struct GtfPack {
+  static constexpr int U = pad4(1 + 2 * Z);
+  static constexpr int RW = pad4(1 + Z);
+  static constexpr int GATE = 0;
+  static constexpr int NONLIN = GATE + H * U;
+  static constexpr int LIN = NONLIN + H * U;
+  static constexpr int STD = LIN + Z * RW;
+  static constexpr int B2G = STD + Z * RW;
+  static constexpr int B2N = B2G + pad4(Z);
+  static constexpr int SIZE = B2N + pad4(Z);
+};
+
+// cooperative re-pack global flat GTF block -> shared GtfPack (all threads of the CTA)
+template <int Z, int H>
+__device__ inline void gtf_pack_load(const float* __restrict__ w, float* __restrict__ sP) {
+  using L = GtfLayout<Z, H>;
+  using P = GtfPack<Z, H>;
+  for (int i = threadIdx.x; i < P::SIZE; i += blockDim.x) {
+    float v = 0.f;
+    if (i < P::LIN) {
+      const int br = i >= P::NONLIN;                      // 0 gate, 1 nonlin
+      const int j = i - (br ? P::NONLIN : P::GATE);
+      const int h = j / P::U, c = j % P::U;
+      const int w0 = br ? L::N0W : L::G0W, b0 = br ? L::N0B : L::G0B, w2 = br ? L::N2W : L::G2W;
+      if (c == 0) v = w[b0 + h];
+      else if (c <= Z) v = w[w0 + h * Z + (c - 1)];
+      else if (c <= 2 * Z) v = w[w2 + (c - 1 - Z) * H + h];
+    } else if (i < P::B2G) {
+      const int st = i >= P::STD;
+      const int j = i - (st ? P::STD : P::LIN);
+      const int o = j / P::RW, c = j % P::RW;
+      const int ww = st ? L::SW : L::LW, bb = st ? L::SB : L::LB;
+      if (c == 0) v = w[bb + o];
+      else if (c <= Z) v = w[ww + o * Z + (c - 1)];
+    } else if (i < P::B2N) {
+      const int o = i - P::B2G;
+      if (o < Z) v = w[L::G2B + o];
+    } else {
+      const int o = i - P::B2N;
+      if (o < Z) v = w[L::N2B + o];
+    }
+    sP[i] = v;
+  }
+}
+
+// N floats from a 16-byte aligned shared address with 128-bit loads (N % 4 == 0)
+template <int N>
+__device__ __forceinline__ void lds_vec(const float* __restrict__ p, float (&v)[N]) {
+  static_assert(N % 4 == 0, "vector loads need a multiple of 4 floats");
+  const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    const float4 t = p4[q];
+    v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+  }
+}
+
+// ---------------------------------------------------------------- fast scalar ops
+// Approximate reciprocal / division / sqrt for WELL-CONDITIONED per-particle math
+// (about 2 ulp).  The product-of-experts step keeps IEEE-rounded operations: its
+// inverse-prior expert cancels precisions and amplifies every rounding error.
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_sqrt(float x) {
+#ifdef BFVI_EMU
+  return sqrtf(x);
+#else
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+
 // ---------------------------------------------------------------- activations
-__device__ __forceinline__ float softplus_f(float x) {      // torch Softplus(beta=1, threshold=20)
-  return x > 20.f ? x : log1pf(expf(x));
+// torch Softplus(beta=1, threshold=20) = max(x,0) + log1p(exp(-|x|)).  log1p(u) for
+// u in (0,1] is evaluated as 2*atanh(s), s = u/(2+u) <= 1/3, with the odd series up
+// to s^15: relative error < 1e-7 over the whole range (MUFU __logf has an ABSOLUTE
+// error of 2^-21, i.e. 1e-5 relative for small results, which the reference's
+// cancelling product of experts amplifies beyond the parity tolerance).
+__device__ __forceinline__ float log1p_unit(float u) {
+  const float s = fast_div(u, 2.f + u), q = s * s;
+  float p = 1.f / 15.f;
+  p = fmaf(p, q, 1.f / 13.f);
+  p = fmaf(p, q, 1.f / 11.f);
+  p = fmaf(p, q, 1.f / 9.f);
+  p = fmaf(p, q, 1.f / 7.f);
+  p = fmaf(p, q, 1.f / 5.f);
+  p = fmaf(p, q, 1.f / 3.f);
+  p = fmaf(p, q, 1.f);
+  return 2.f * s * p;
+}
+__device__ __forceinline__ float softplus_f(float x) {
+  const float l = log1p_unit(__expf(-fabsf(x)));
+  return x > 20.f ? x : (x > 0.f ? x + l : l);
 }
 // NaN-propagating ReLU like torch.relu (fmaxf would swallow a NaN)
 __device__ __forceinline__ float relu_f(float x) { return x < 0.f ? 0.f : x; }
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_div(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float softplus_grad(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
 __device__ __forceinline__ float sign_f(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
-// y[o] = b[o] + sum_i W[o][i] x[i]; W row-major (OUT, IN) at a 16-byte aligned
-// shared-memory address.  The flat walk over W lets 128-bit loads serve any IN.
-template <int OUT, int IN>
-__device__ __forceinline__ void matvec(const float* __restrict__ W, const float* __restrict__ b,
-                                       const float (&x)[IN], float (&y)[OUT]) {
+// ------------------------------------------------------------------ GTF forward
+// R rows per thread; q'(z_next | z) mean / std (models/common.py:62-68) of row r,
+// component o are handed to `epi(r, o, mean, std)` as soon as they are complete.
+template <int Z, int H, int R, typename Epi>
+__device__ __forceinline__ void gtf_rows_forward(const float* __restrict__ sP, float min_std,
+                                                 const float (&z)[R][Z], Epi&& epi) {
+  using P = GtfPack<Z, H>;
+  float g[R][Z], nl[R][Z];
 #pragma unroll
-  for (int o = 0; o < OUT; ++o) y[o] = b[o];
-  constexpr int N = OUT * IN;
-  const float4* W4 = reinterpret_cast<const float4*>(W);
+  for (int o = 0; o < Z; ++o) {
+    const float bg = sP[P::B2G + o], bn = sP[P::B2N + o];
 #pragma unroll
-  for (int q = 0; q < (N + 3) / 4; ++q) {
-    const float4 w = W4[q];
-    const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = 4 * q + j;
-      if (idx < N) y[idx / IN] = fmaf(wv[j], x[idx % IN], y[idx / IN]);
-    }
+    for (int r = 0; r < R; ++r) { g[r][o] = bg; nl[r][o] = bn; }
   }
-}
-
-// dx[i] += sum_o W[o][i] dy[o]  (transposed product, same flat walk)
-template <int OUT, int IN>
-__device__ __forceinline__ void matvec_t_acc(const float* __restrict__ W, const float (&dy)[OUT],
-                                             float (&dx)[IN]) {
-  constexpr int N = OUT * IN;
-  const float4* W4 = reinterpret_cast<const float4*>(W);
-#pragma unroll
-  for (int q = 0; q < (N + 3) / 4; ++q) {
-    const float4 w = W4[q];
-    const float wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int idx = 4 * q + j;
-      if (idx < N) dx[idx % IN] = fmaf(wv[j], dy[idx / IN], dx[idx % IN]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------ GTF
-template <int Z, int H>
-struct GtfAct {       // activations kept for the backward pass
-  float h1[H];        // relu(gate hidden)
-  float h3[H];        // relu(nonlin hidden)
-  float g[Z];         // gate
-  float lin[Z];
-  float nl[Z];
-  float as[Z];        // pre-softplus std
-};
-
-template <int Z, int H>
-__device__ __forceinline__ void gtf_forward(const float* __restrict__ W, float min_std,
-                                            const float (&z)[Z], GtfAct<Z, H>& a,
-                                            float (&qm)[Z], float (&qs)[Z]) {
-  using L = GtfLayout<Z, H>;
-  matvec<H, Z>(W + L::G0W, W + L::G0B, z, a.h1);
-#pragma unroll
-  for (int h = 0; h < H; ++h) a.h1[h] = relu_f(a.h1[h]);
-  matvec<Z, H>(W + L::G2W, W + L::G2B, a.h1, a.g);
-  matvec<Z, Z>(W + L::LW, W + L::LB, z, a.lin);
-  matvec<H, Z>(W + L::N0W, W + L::N0B, z, a.h3);
-#pragma unroll
-  for (int h = 0; h < H; ++h) a.h3[h] = relu_f(a.h3[h]);
-  matvec<Z, H>(W + L::N2W, W + L::N2B, a.h3, a.nl);
-  matvec<Z, Z>(W + L::SW, W + L::SB, a.nl, a.as);
-#pragma unroll
-  for (int i = 0; i < Z; ++i) {
-    a.g[i] = sigmoid_f(a.g[i]);
-    qs[i] = softplus_f(a.as[i]) + min_std;
-    qm[i] = (1.f - a.g[i]) * a.lin[i] + a.g[i] * a.nl[i];
-  }
-}
-
-// Gradients at every pre-activation (what the weight-gradient panels need) and dz.
-template <int Z, int H>
-struct GtfGrad {
-  float d_a1[H];   // gate hidden pre-relu
-  float d_a3[H];   // nonlin hidden pre-relu
-  float d_lin[Z];
-  float d_ag[Z];   // gate pre-sigmoid
-  float d_nl[Z];
-  float d_as[Z];   // std pre-softplus
-};
-
-template <int Z, int H>
-__device__ __forceinline__ void gtf_backward(const float* __restrict__ W, const GtfAct<Z, H>& a,
-                                             const float (&d_qm)[Z], const float (&d_qs)[Z],
-                                             GtfGrad<Z, H>& g, float (&dz)[Z]) {
-  using L = GtfLayout<Z, H>;
-#pragma unroll
-  for (int i = 0; i < Z; ++i) {
-    g.d_as[i] = d_qs[i] * softplus_grad(a.as[i]);
-    g.d_nl[i] = d_qm[i] * a.g[i];
-    g.d_ag[i] = d_qm[i] * (a.nl[i] - a.lin[i]) * a.g[i] * (1.f - a.g[i]);
-    g.d_lin[i] = d_qm[i] * (1.f - a.g[i]);
-    dz[i] = 0.f;
-  }
-  matvec_t_acc<Z, Z>(W + L::SW, g.d_as, g.d_nl);           // nl feeds the std head too
-#pragma unroll
-  for (int h = 0; h < H; ++h) { g.d_a1[h] = 0.f; g.d_a3[h] = 0.f; }
-  matvec_t_acc<Z, H>(W + L::N2W, g.d_nl, g.d_a3);
-  matvec_t_acc<Z, H>(W + L::G2W, g.d_ag, g.d_a1);
-#pragma unroll
+#pragma unroll 2
   for (int h = 0; h < H; ++h) {
-    g.d_a3[h] = a.h3[h] > 0.f ? g.d_a3[h] : 0.f;
-    g.d_a1[h] = a.h1[h] > 0.f ? g.d_a1[h] : 0.f;
+    float wg[P::U], wn[P::U];
+    lds_vec<P::U>(sP + P::GATE + h * P::U, wg);
+    lds_vec<P::U>(sP + P::NONLIN + h * P::U, wn);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float a = wg[0], c = wn[0];
+#pragma unroll
+      for (int i = 0; i < Z; ++i) { a = fmaf(wg[1 + i], z[r][i], a); c = fmaf(wn[1 + i], z[r][i], c); }
+      a = relu_f(a); c = relu_f(c);
+#pragma unroll
+      for (int o = 0; o < Z; ++o) {
+        g[r][o] = fmaf(wg[1 + Z + o], a, g[r][o]);
+        nl[r][o] = fmaf(wn[1 + Z + o], c, nl[r][o]);
+      }
+    }
   }
-  matvec_t_acc<H, Z>(W + L::G0W, g.d_a1, dz);
-  matvec_t_acc<H, Z>(W + L::N0W, g.d_a3, dz);
-  matvec_t_acc<Z, Z>(W + L::LW, g.d_lin, dz);
+#pragma unroll
+  for (int o = 0; o < Z; ++o) {
+    float wl[P::RW], ws[P::RW];
+    lds_vec<P::RW>(sP + P::LIN + o * P::RW, wl);
+    lds_vec<P::RW>(sP + P::STD + o * P::RW, ws);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float lin = wl[0], as = ws[0];
+#pragma unroll
+      for (int i = 0; i < Z; ++i) { lin = fmaf(wl[1 + i], z[r][i], lin); as = fmaf(ws[1 + i], nl[r][i], as); }
+      const float gate = sigmoid_f(g[r][o]);
+      epi(r, o, fmaf(gate, nl[r][o] - lin, lin), softplus_f(as) + min_std);   // (1-g)*lin + g*nl
+    }
+  }
+}
+
+// one row, keeping what the backward pass needs: gate (post-sigmoid), lin, nl and
+// the pre-softplus std
+template <int Z, int H>
+__device__ __forceinline__ void gtf_row_forward_full(const float* __restrict__ sP, const float (&z)[Z],
+                                                     float (&g)[Z], float (&lin)[Z], float (&nl)[Z],
+                                                     float (&as)[Z]) {
+  using P = GtfPack<Z, H>;
+#pragma unroll
+  for (int o = 0; o < Z; ++o) { g[o] = sP[P::B2G + o]; nl[o] = sP[P::B2N + o]; }
+#pragma unroll 4
+  for (int h = 0; h < H; ++h) {
+    float wg[P::U], wn[P::U];
+    lds_vec<P::U>(sP + P::GATE + h * P::U, wg);
+    lds_vec<P::U>(sP + P::NONLIN + h * P::U, wn);
+    float a = wg[0], c = wn[0];
+#pragma unroll
+    for (int i = 0; i < Z; ++i) { a = fmaf(wg[1 + i], z[i], a); c = fmaf(wn[1 + i], z[i], c); }
+    a = relu_f(a); c = relu_f(c);
+#pragma unroll
+    for (int o = 0; o < Z; ++o) { g[o] = fmaf(wg[1 + Z + o], a, g[o]); nl[o] = fmaf(wn[1 + Z + o], c, nl[o]); }
+  }
+#pragma unroll
+  for (int o = 0; o < Z; ++o) {
+    float wl[P::RW], ws[P::RW];
+    lds_vec<P::RW>(sP + P::LIN + o * P::RW, wl);
+    lds_vec<P::RW>(sP + P::STD + o * P::RW, ws);
+    float l = wl[0], s = ws[0];
+#pragma unroll
+    for (int i = 0; i < Z; ++i) { l = fmaf(wl[1 + i], z[i], l); s = fmaf(ws[1 + i], nl[i], s); }
+    lin[o] = l; as[o] = s;
+    g[o] = sigmoid_f(g[o]);
+  }
+}
+
+// Panel columns of the weight-gradient staging area (bfvi_wgrad.cuh): X holds the
+// layer inputs [1, z] [1, h1] [1, h3] [1, nl]; D the pre-activation gradients.
+template <int Z, int H>
+struct GtfCols {
+  static constexpr int XZ = 0, XH1 = 1 + Z, XH3 = XH1 + 1 + H, XNL = XH3 + 1 + H, NXC = XNL + 1 + Z;
+  static constexpr int DA1 = 0, DA3 = H, DLIN = 2 * H, DAG = 2 * H + Z, DNL = 2 * H + 2 * Z,
+                       DAS = 2 * H + 3 * Z, NDC = 2 * H + 4 * Z;
+};
+
+// Backward of one row given d_qm / d_qs.  Hidden activations are recomputed per
+// unit; the row's layer inputs and pre-activation gradients are written straight
+// into this lane's slot of the staging panels (column * RS + lane), zeroed when the
+// row is padding.  Returns dz.
+template <int Z, int H, int RS>
+__device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__ sP, const float (&z)[Z],
+                                                       const float (&g)[Z], const float (&lin)[Z],
+                                                       const float (&nl)[Z], const float (&as)[Z],
+                                                       const float (&d_qm)[Z], const float (&d_qs)[Z],
+                                                       float (&dz)[Z], float* __restrict__ Xp,
+                                                       float* __restrict__ Dp, int lane, bool valid) {
+  using P = GtfPack<Z, H>;
+  using C = GtfCols<Z, H>;
+  const float vm = valid ? 1.f : 0.f;
+  float d_as[Z], d_nl[Z], d_ag[Z], d_lin[Z];
+#pragma unroll
+  for (int o = 0; o < Z; ++o) {
+    d_as[o] = d_qs[o] * softplus_grad(as[o]) * vm;
+    d_nl[o] = d_qm[o] * g[o] * vm;
+    d_ag[o] = d_qm[o] * (nl[o] - lin[o]) * g[o] * (1.f - g[o]) * vm;
+    d_lin[o] = d_qm[o] * (1.f - g[o]) * vm;
+    dz[o] = 0.f;
+  }
+#pragma unroll
+  for (int o = 0; o < Z; ++o) {
+    float wl[P::RW], ws[P::RW];
+    lds_vec<P::RW>(sP + P::LIN + o * P::RW, wl);
+    lds_vec<P::RW>(sP + P::STD + o * P::RW, ws);
+#pragma unroll
+    for (int i = 0; i < Z; ++i) {
+      d_nl[i] = fmaf(ws[1 + i], d_as[o], d_nl[i]);       // nl feeds the std head too
+      dz[i] = fmaf(wl[1 + i], d_lin[o], dz[i]);
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < Z; ++o) {
+    Xp[(C::XZ + 1 + o) * RS + lane] = z[o] * vm;
+    Xp[(C::XNL + 1 + o) * RS + lane] = nl[o] * vm;
+    Dp[(C::DLIN + o) * RS + lane] = d_lin[o];
+    Dp[(C::DAG + o) * RS + lane] = d_ag[o];
+    Dp[(C::DNL + o) * RS + lane] = d_nl[o];
+    Dp[(C::DAS + o) * RS + lane] = d_as[o];
+  }
+#pragma unroll 4
+  for (int h = 0; h < H; ++h) {
+    float wg[P::U], wn[P::U];
+    lds_vec<P::U>(sP + P::GATE + h * P::U, wg);
+    lds_vec<P::U>(sP + P::NONLIN + h * P::U, wn);
+    float a = wg[0], c = wn[0], da = 0.f, dc = 0.f;
+#pragma unroll
+    for (int i = 0; i < Z; ++i) { a = fmaf(wg[1 + i], z[i], a); c = fmaf(wn[1 + i], z[i], c); }
+#pragma unroll
+    for (int o = 0; o < Z; ++o) { da = fmaf(wg[1 + Z + o], d_ag[o], da); dc = fmaf(wn[1 + Z + o], d_nl[o], dc); }
+    da = a > 0.f ? da : 0.f;
+    dc = c > 0.f ? dc : 0.f;
+#pragma unroll
+    for (int i = 0; i < Z; ++i) { dz[i] = fmaf(wg[1 + i], da, dz[i]); dz[i] = fmaf(wn[1 + i], dc, dz[i]); }
+    Xp[(C::XH1 + 1 + h) * RS + lane] = relu_f(a) * vm;
+    Xp[(C::XH3 + 1 + h) * RS + lane] = relu_f(c) * vm;
+    Dp[(C::DA1 + h) * RS + lane] = da;
+    Dp[(C::DA3 + h) * RS + lane] = dc;
+  }
 }
 
 // ------------------------------------------------ product / mixture of experts
-// precision with the sign trick of models/dgts.py:40-42
+// precision with the sign trick of models/dgts.py:40-42, IEEE-rounded operations in
+// the reference's order (1/var, then * sign)
 __device__ __forceinline__ float poe_prec(float std) {
-  return 1.f / (std * std + kPoeEps) * sign_f(std);
+  return __fmul_rn(__fdiv_rn(1.f, __fadd_rn(__fmul_rn(std, std), kPoeEps)), sign_f(std));
 }
 // d prec / d std
 __device__ __forceinline__ float poe_prec_grad(float std, float prec) {
   return -2.f * std * prec / (std * std + kPoeEps);
 }
 
-// p(z|z_prev) = p(z) * q'(z|z_prev)   (models/dmm.py:239-245), one component
+// p(z|z_prev) = p(z) * q'(z|z_prev)   (models/dmm.py:239-245), one component, both
+// stds positive (global prior and a GTF output).  Same value as the reference's
+// sum of precisions, written with ONE division: with vg = gs^2+eps, vq = qs^2+eps,
+//   mean = (gm*vq + qm*vg) / (vg+vq),   var = vg*vq / (vg+vq).
 __device__ __forceinline__ void poe2_forward(float gm, float gs, float qm, float qs,
                                              float& pm, float& ps) {
-  const float tg = poe_prec(gs), tq = poe_prec(qs);
-  const float s = tg + tq;
-  float m = (gm * tg + qm * tq) / s;
-  pm = (m != m) ? 0.f : m;
-  ps = sqrtf(1.f / s);
+  const float vg = fmaf(gs, gs, kPoeEps), vq = fmaf(qs, qs, kPoeEps);
+  const float r = fast_div(1.f, vg + vq);
+  const float m = (gm * vq + qm * vg) * r;
+  pm = (m != m) ? 0.f : m;                    // product_mean[isnan] = 0, models/dgts.py:49
+  ps = fast_sqrt(vg * vq * r);
 }
 __device__ __forceinline__ void poe2_backward(float gm, float gs, float qm, float qs, float pm,
                                               float ps, float d_pm, float d_ps, float& d_gm,
                                               float& d_gs, float& d_qm, float& d_qs) {
-  const float tg = poe_prec(gs), tq = poe_prec(qs);
-  const float s = tg + tq;
-  const float d_n = d_pm / s;
-  const float d_s = -d_pm * pm / s - 0.5f * d_ps * ps / s;
-  d_gm = d_n * tg;
-  d_qm = d_n * tq;
-  d_gs = (d_n * gm + d_s) * poe_prec_grad(gs, tg);
-  d_qs = (d_n * qm + d_s) * poe_prec_grad(qs, tq);
+  const float vg = fmaf(gs, gs, kPoeEps), vq = fmaf(qs, qs, kPoeEps);
+  const float r = fast_div(1.f, vg + vq);
+  const float wg = vq * r, wq = vg * r;             // weights of gm / qm in the mean
+  const float d_var = fast_div(0.5f * d_ps, ps);
+  d_gm = d_pm * wg;
+  d_qm = d_pm * wq;
+  d_gs = (d_pm * (qm - pm) * r + d_var * wg * wg) * 2.f * gs;
+  d_qs = (d_pm * (gm - pm) * r + d_var * wq * wq) * 2.f * qs;
 }
 
 // ------------------------------------------------------------------ losses
-// one element of losses.kld_gauss (before the 0.5 factor is applied: included here)
+// one element of losses.kld_gauss (the 0.5 factor included)
 __device__ __forceinline__ float kld_elem(float m1, float s1, float m2, float s2) {
   const float dm = m1 - m2;
   return 0.5f * (2.f * logf(s2) - 2.f * logf(s1) + (s1 * s1 + dm * dm) / (s2 * s2) - 1.f);
@@ -223,6 +373,14 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// Sum over the L consecutive lanes [base, base+L) of a lane group, in lane order so
+// that every lane of the group gets the bit-identical result.  All 32 lanes call it.
+__device__ __forceinline__ float group_sum(float v, int base, int L) {
+  float s = __shfl_sync(0xffffffffu, v, base);
+  for (int j = 1; j < L; ++j) s += __shfl_sync(0xffffffffu, v, base + j);
+  return s;
 }
 
 }  // namespace bfvi

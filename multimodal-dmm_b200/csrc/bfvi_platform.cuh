@@ -17,3 +17,19 @@
   extern __shared__ __align__(16) unsigned char bfvi_dyn_smem_raw[]; \
   type* name = reinterpret_cast<type*>(bfvi_dyn_smem_raw)
 #endif
+
+namespace bfvi {
+// An integer zero the compiler cannot see through.  Adding it to the base of the
+// shared-memory weight block inside the time loop stops loop-invariant hoisting of
+// the ~130 weight loads of one GTF evaluation (which would otherwise be "kept in
+// registers" across iterations, i.e. spilled to local memory).
+__device__ __forceinline__ int opaque_zero() {
+#ifdef BFVI_EMU
+  return 0;
+#else
+  int z;
+  asm volatile("mov.u32 %0, 0;" : "=r"(z));
+  return z;
+#endif
+}
+}  // namespace bfvi

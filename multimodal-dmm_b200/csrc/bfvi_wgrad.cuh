@@ -119,6 +119,49 @@ __device__ __forceinline__ void wg_accumulate(const float* __restrict__ Dp, cons
   }
 }
 
+// Register-tile variant for kernels whose task list fits ONE round (<= 32 tiles):
+// the lane keeps its TD x TX tile in registers across several staged row slices
+// (wg_tile_fma) and folds it into the per-warp accumulator G once (wg_tile_flush).
+template <int TD, int TX>
+__device__ __forceinline__ void wg_tile_fma(float (&acc)[TD][TX], const float* __restrict__ Dp,
+                                            const float* __restrict__ Xp, const int4 t) {
+  const float* dcol[TD];
+  const float* xcol[TX];
+#pragma unroll
+  for (int i = 0; i < TD; ++i) dcol[i] = Dp + (t.x + min(i, t.y - 1)) * kRS;
+#pragma unroll
+  for (int j = 0; j < TX; ++j) xcol[j] = Xp + (t.z + min(j, t.w - 1)) * kRS;
+#pragma unroll 2
+  for (int q = 0; q < 8; ++q) {
+    float4 dv[TD], xv[TX];
+#pragma unroll
+    for (int i = 0; i < TD; ++i) dv[i] = reinterpret_cast<const float4*>(dcol[i])[q];
+#pragma unroll
+    for (int j = 0; j < TX; ++j) xv[j] = reinterpret_cast<const float4*>(xcol[j])[q];
+#pragma unroll
+    for (int i = 0; i < TD; ++i)
+#pragma unroll
+      for (int j = 0; j < TX; ++j) {
+        acc[i][j] = fmaf(dv[i].x, xv[j].x, acc[i][j]);
+        acc[i][j] = fmaf(dv[i].y, xv[j].y, acc[i][j]);
+        acc[i][j] = fmaf(dv[i].z, xv[j].z, acc[i][j]);
+        acc[i][j] = fmaf(dv[i].w, xv[j].w, acc[i][j]);
+      }
+  }
+}
+template <int TD, int TX>
+__device__ __forceinline__ void wg_tile_flush(float (&acc)[TD][TX], const int* __restrict__ oidx,
+                                              float* __restrict__ G, int lane) {
+  const int* oi = oidx + lane;
+#pragma unroll
+  for (int i = 0; i < TD; ++i)
+#pragma unroll
+    for (int j = 0; j < TX; ++j) {
+      G[oi[(i * TX + j) * 32]] += acc[i][j];
+      acc[i][j] = 0.f;
+    }
+}
+
 // Block-level flush: sum the per-warp accumulators and add them to the global
 // gradient block with one atomic per parameter per CTA.
 __device__ inline void wg_flush(const float* __restrict__ G_all, int g_stride, int n_warps, int n_out,

@@ -254,6 +254,7 @@ template <typename T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline float __frcp_rn(float x) { return 1.0f / x; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float __fsqrt_rn(float x) { return sqrtf(x); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }

@@ -28,3 +28,18 @@ def test_step_loss_and_grads(lib, name):
             assert g.norm() == 0, k
         else:
             assert rel_err(g, g_ref) < 1e-3, (k, rel_err(g, g_ref))
+
+
+@pytest.mark.parametrize('lanes', ['1', '3', '8', '32'])
+def test_lane_group_geometries_agree(lib, lanes, monkeypatch):
+    """Every lanes-per-chain mapping of the particle kernels (bfvi_chain.cuh) must give
+    the same step: exercised through the BFVI_LANES tuning knob."""
+    fx = load_golden('spirals_ragged')
+    monkeypatch.setenv('BFVI_LANES', lanes)
+    loss, grads, _ = helpers.run_step(lib, fx, 'cpu')
+    ref = fx['ref_loss_fp64']
+    assert abs(loss - ref) / abs(ref) < 1e-4, (loss, ref)
+    n = float(sum(fx['lengths']))
+    for k, g_ref in fx['ref_grads_fp64'].items():
+        if g_ref.norm() > 0:
+            assert rel_err(grads[k] / n, g_ref) < 1e-3, (k, rel_err(grads[k] / n, g_ref))
