@@ -290,6 +290,29 @@ bfvi::FilterParams make_filter_params(const bfvi_model* m, const bfvi_layout& la
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A lazily created non-blocking side stream + fork/join events per (host thread,
+// device): the f_mode filtering ELBO of a step (pass A) is independent of the s_mode
+// passes (B, C), is latency-bound, and overlaps them on the side stream.
+struct SideStream {
+  cudaStream_t stream;
+  cudaEvent_t fork, join;
+  bool ok;
+};
+SideStream* side_stream() {
+  static thread_local SideStream cache[64];
+  static thread_local bool made[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!made[dev]) {
+    made[dev] = true;
+    SideStream& c = cache[dev];
+    c.ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
+  }
+  return cache[dev].ok ? &cache[dev] : nullptr;
+}
+
 struct StepPlan {
   int S;
   unsigned set_bits[BFVI_MAX_SETS];     // modalities in each input set
@@ -722,18 +745,8 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     }
 
     const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
-    pm.begin(BFVI_PHASE_FILTER_F_FWD);
-    if (do_f) { if (int rc = bfvi_filter_fwd(m, params, &fa, stream)) return rc; ++n_launch; }
-    pm.begin(BFVI_PHASE_FILTER_S_FLT_FWD);
-    if (do_s) {
-      if (int rc = bfvi_filter_fwd(m, params, &fb, stream)) return rc; ++n_launch;
-      pm.begin(BFVI_PHASE_FILTER_S_SMT_FWD);
-      if (int rc = bfvi_filter_fwd(m, params, &fc, stream)) return rc; ++n_launch;
-    }
-    // ---- decoders + NLL (+ their backward) on the samples of passes A and C --------
-    pm.begin(BFVI_PHASE_DECODE_NLL);
-    for (int pass = 0; pass < 2; ++pass) {
-      if ((pass == 0 && !do_f) || (pass == 1 && !do_s)) continue;
+    // decoders + NLL (+ their backward) on the samples of one pass
+    auto decode_pass = [&](int pass, void* strm) -> int {
       const float mult = pass == 0 ? a->f_mult : a->s_mult;
       float* samp = pass == 0 ? A(4) : C(4);
       float* dsamp = with_grad ? (pass == 0 ? A(5) : C(5)) : nullptr;
@@ -742,11 +755,41 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
           if (!((pl.set_bits[s] >> i) & 1u) || a->rec_mults[i] == 0.f) continue;
           if (int rc = bfvi_decode_nll(m, params, grads, i, samp + (size_t)s * pl.n_tbz, a->targets[i],
                                        a->seq_mask, tb, mult * a->rec_mults[i], acc,
-                                       dsamp ? dsamp + (size_t)s * pl.n_tbz : nullptr, stream))
+                                       dsamp ? dsamp + (size_t)s * pl.n_tbz : nullptr, strm))
             return rc;
           ++n_launch;
         }
+      return BFVI_OK;
+    };
+    // Pass A (f_mode ELBO) shares nothing but atomically accumulated outputs with
+    // passes B / C: when both run, A goes to the side stream (not while profiling
+    // phases, where every phase must be alone on the timed stream).
+    SideStream* side = (do_f && do_s && !pm.on) ? side_stream() : nullptr;
+    void* stream_a = stream;
+    if (side != nullptr) {
+      cudaEventRecord(side->fork, st);
+      cudaStreamWaitEvent(side->stream, side->fork, 0);
+      stream_a = (void*)side->stream;
     }
+    pm.begin(BFVI_PHASE_FILTER_F_FWD);
+    if (do_f) { if (int rc = bfvi_filter_fwd(m, params, &fa, stream_a)) return rc; ++n_launch; }
+    if (do_f && side != nullptr) {               // the whole A pipeline runs beside B / C
+      if (int rc = decode_pass(0, stream_a)) return rc;
+      if (with_grad) {
+        fa.d_samples = A(5);
+        if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream_a)) return rc; ++n_launch;
+      }
+      cudaEventRecord(side->join, side->stream);
+    }
+    pm.begin(BFVI_PHASE_FILTER_S_FLT_FWD);
+    if (do_s) {
+      if (int rc = bfvi_filter_fwd(m, params, &fb, stream)) return rc; ++n_launch;
+      pm.begin(BFVI_PHASE_FILTER_S_SMT_FWD);
+      if (int rc = bfvi_filter_fwd(m, params, &fc, stream)) return rc; ++n_launch;
+    }
+    pm.begin(BFVI_PHASE_DECODE_NLL);
+    if (do_f && side == nullptr) { if (int rc = decode_pass(0, stream)) return rc; }
+    if (do_s) { if (int rc = decode_pass(1, stream)) return rc; }
     // ---- backward through the three passes and the encoders ------------------------
     if (with_grad) {
       if (do_s) {
@@ -757,11 +800,14 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
         pm.begin(BFVI_PHASE_FILTER_S_FLT_BWD);
         if (int rc = bfvi_filter_bwd(m, params, grads, &fb, stream)) return rc; ++n_launch;
       }
-      if (do_f) {
+      if (do_f && side == nullptr) {
         fa.d_samples = A(5);
         pm.begin(BFVI_PHASE_FILTER_F_BWD);
         if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream)) return rc; ++n_launch;
       }
+    }
+    if (side != nullptr) cudaStreamWaitEvent(st, side->join, 0);
+    if (with_grad) {
       pm.begin(BFVI_PHASE_ENCODE_BWD);
       for (int i = 0; i < M; ++i) {
         if (int rc = bfvi_encode_bwd(m, params, grads, i, a->inputs[i], tb, dobs_mean + (size_t)i * pl.n_tbz,
@@ -770,6 +816,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
         ++n_launch;
       }
     }
+    BFVI_CHECK_CUDA();
   }
   pm.begin(BFVI_PHASE_FINALIZE);
   auto k = bfvi::finalize_loss_kernel;

@@ -31,7 +31,7 @@ constexpr int kTX = 4;                       // weight-gradient tile width
 #define BFVI_FWD_THREADS 128
 #endif
 #ifndef BFVI_FWD_MINB
-#define BFVI_FWD_MINB 3          // resident CTAs per SM the R = 5 forward kernel is compiled for
+#define BFVI_FWD_MINB 4          // resident CTAs per SM the R = 5 forward kernel is compiled for
 #endif
 #ifndef BFVI_BWD_WARPS
 #define BFVI_BWD_WARPS 4
@@ -282,11 +282,14 @@ chain_fwd_kernel(const __grid_constant__ FilterParams p) {
 #pragma unroll
           for (int j = 0; j < Z; ++j) { pm[j] = sm[j]; ps[j] = sv[j]; }
         } else {
+          float mom[3 * Z];
+#pragma unroll
+          for (int j = 0; j < Z; ++j) { mom[j] = sm[j]; mom[Z + j] = sv[j]; mom[2 * Z + j] = sq[j]; }
+          group_sum_vec<3 * Z>(mom, lg.base, L);
 #pragma unroll
           for (int j = 0; j < Z; ++j) {                     // models/dgts.py:78-83
-            const float m = group_sum(sm[j], lg.base, L) * inv_k;
-            const float v = group_sum(sv[j], lg.base, L) * inv_k +
-                            (group_sum(sq[j], lg.base, L) * inv_k - m * m);
+            const float m = mom[j] * inv_k;
+            const float v = mom[Z + j] * inv_k + (mom[2 * Z + j] * inv_k - m * m);
             pm[j] = m; ps[j] = sqrtf(v);
           }
         }
@@ -403,7 +406,8 @@ __device__ __forceinline__ void transition_slice_backward(
     float* __restrict__ Xp, float* __restrict__ Dp, int lane,
     float (&acc)[GtfPanels<Z, H>::TD][kTX], const int4 task) {
   float g[Z], lin[Z], nl[Z], as[Z], d_qm[Z], d_qs[Z];
-  gtf_row_forward_full<Z, H>(sP, z, g, lin, nl, as);
+  __syncwarp();                        // the previous slice's tile reads are done
+  gtf_row_forward_stage<Z, H>(sP, z, g, lin, nl, as, Xp, lane);
 #pragma unroll
   for (int j = 0; j < Z; ++j) {
     const float qs = softplus_f(as[j]) + min_std;
@@ -415,8 +419,7 @@ __device__ __forceinline__ void transition_slice_backward(
     poe2_backward(sGm[j], sGs[j], qm, qs, m_k, s_k, d_mk, d_sk, g_gm, g_gs, d_qm[j], d_qs[j]);
     if (valid) { d_gm[j] += g_gm; d_gs[j] += g_gs; }
   }
-  __syncwarp();                        // the previous slice's tile reads are done
-  gtf_row_backward_stage<Z, H, kRS>(sP, z, g, lin, nl, as, d_qm, d_qs, dz, Xp, Dp, lane, valid);
+  gtf_row_backward_stage<Z, H>(sP, g, lin, nl, as, d_qm, d_qs, dz, Xp, Dp, lane, valid);
   __syncwarp();
   wg_tile_fma<GtfPanels<Z, H>::TD, kTX>(acc, Dp, Xp, task);
 }
@@ -453,10 +456,10 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
   for (int i = lane; i < L_::SIZE + 32; i += 32) G[i] = 0.f;
   for (int i = lane; i < (C::NXC + C::NDC) * kRS; i += 32) Xp[i] = 0.f;
   __syncwarp();
-  Xp[(C::XZ) * kRS + lane] = 1.f;
-  Xp[(C::XH1) * kRS + lane] = 1.f;
-  Xp[(C::XH3) * kRS + lane] = 1.f;
-  Xp[(C::XNL) * kRS + lane] = 1.f;
+  Xp[panel_at(C::XZ, lane)] = 1.f;
+  Xp[panel_at(C::XH1, lane)] = 1.f;
+  Xp[panel_at(C::XH3, lane)] = 1.f;
+  Xp[panel_at(C::XNL, lane)] = 1.f;
   __syncthreads();
   const int4 task = reinterpret_cast<const int4*>(tasks)[lane];
   float acc[TD][kTX];
@@ -589,11 +592,12 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
         }
       }
       if (L > 1) {
+        float cc[2 * Z];
 #pragma unroll
-        for (int j = 0; j < Z; ++j) {
-          c_mu[j] = group_sum(c_mu[j], lg.base, L);
-          c_sd[j] = group_sum(c_sd[j], lg.base, L);
-        }
+        for (int j = 0; j < Z; ++j) { cc[j] = c_mu[j]; cc[Z + j] = c_sd[j]; }
+        group_sum_vec<2 * Z>(cc, lg.base, L);
+#pragma unroll
+        for (int j = 0; j < Z; ++j) { c_mu[j] = cc[j]; c_sd[j] = cc[Z + j]; }
       }
       have_eps_cur = sampled_prev;
     }
@@ -674,8 +678,8 @@ __global__ void __launch_bounds__(32) match_kernel(const __grid_constant__ Match
   for (int i = lane; i < L_::SIZE + 32; i += 32) G[i] = 0.f;
   for (int i = lane; i < (C::NXC + C::NDC) * kRS; i += 32) Xp[i] = 0.f;
   __syncwarp();
-  Xp[(C::XZ) * kRS + lane] = 1.f; Xp[(C::XH1) * kRS + lane] = 1.f;
-  Xp[(C::XH3) * kRS + lane] = 1.f; Xp[(C::XNL) * kRS + lane] = 1.f;
+  Xp[panel_at(C::XZ, lane)] = 1.f; Xp[panel_at(C::XH1, lane)] = 1.f;
+  Xp[panel_at(C::XH3, lane)] = 1.f; Xp[panel_at(C::XNL, lane)] = 1.f;
   __syncthreads();
   const int4 task = reinterpret_cast<const int4*>(tasks)[lane];
   const int K = p.K;

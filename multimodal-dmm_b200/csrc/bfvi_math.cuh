@@ -17,6 +17,7 @@
 //   kld_gauss / nll_gauss models/losses.py:14-21, 68-89
 #pragma once
 #include "bfvi_platform.cuh"
+#include "bfvi_wgrad.cuh"
 
 namespace bfvi {
 
@@ -110,28 +111,36 @@ __device__ __forceinline__ void lds_vec(const float* __restrict__ p, float (&v)[
 }
 
 // ---------------------------------------------------------------- fast scalar ops
-// Approximate reciprocal / division / sqrt for WELL-CONDITIONED per-particle math
-// (about 2 ulp).  The product-of-experts step keeps IEEE-rounded operations: its
-// inverse-prior expert cancels precisions and amplifies every rounding error.
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float fast_sqrt(float x) {
+// Single-instruction MUFU approximations (about 1-2 ulp, denormals flushed) for the
+// WELL-CONDITIONED per-particle math.  The product-of-experts step keeps IEEE-rounded
+// operations: its inverse-prior expert cancels precisions and amplifies every
+// rounding error.
 #ifdef BFVI_EMU
-  return sqrtf(x);
+__device__ __forceinline__ float fast_rcp(float x) { return 1.f / x; }
+__device__ __forceinline__ float fast_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float fast_ex2(float x) { return exp2f(x); }
+__device__ __forceinline__ float fast_lg2(float x) { return log2f(x); }
+// NaN-propagating max like torch.relu (fmaxf would swallow a NaN)
+__device__ __forceinline__ float max_nan(float a, float b) { return (a != a || b != b) ? NAN : (a > b ? a : b); }
 #else
-  float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float max_nan(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 #endif
-}
+__device__ __forceinline__ float fast_div(float a, float b) { return a * fast_rcp(b); }
+constexpr float kLog2e = 1.4426950408889634f;
 
 // ---------------------------------------------------------------- activations
-// torch Softplus(beta=1, threshold=20) = max(x,0) + log1p(exp(-|x|)).  log1p(u) for
-// u in (0,1] is evaluated as 2*atanh(s), s = u/(2+u) <= 1/3, with the odd series up
-// to s^15: relative error < 1e-7 over the whole range (MUFU __logf has an ABSOLUTE
-// error of 2^-21, i.e. 1e-5 relative for small results, which the reference's
+// torch Softplus(beta=1, threshold=20) = max(x,0) + log1p(exp(-|x|)) (above the
+// threshold the log term is below half an ulp of x, so no select is needed).
+// log1p(u) for u in (0,1] is evaluated as 2*atanh(s), s = u/(2+u) <= 1/3, with the odd
+// series up to s^15: relative error < 1e-7 over the whole range (MUFU lg2 has an
+// ABSOLUTE error of 2^-22, i.e. 1e-5 relative for small results, which the reference's
 // cancelling product of experts amplifies beyond the parity tolerance).
 __device__ __forceinline__ float log1p_unit(float u) {
-  const float s = fast_div(u, 2.f + u), q = s * s;
+  const float s = u * fast_rcp(2.f + u), q = s * s;
   float p = 1.f / 15.f;
   p = fmaf(p, q, 1.f / 13.f);
   p = fmaf(p, q, 1.f / 11.f);
@@ -140,16 +149,15 @@ __device__ __forceinline__ float log1p_unit(float u) {
   p = fmaf(p, q, 1.f / 5.f);
   p = fmaf(p, q, 1.f / 3.f);
   p = fmaf(p, q, 1.f);
-  return 2.f * s * p;
+  return (s + s) * p;
 }
 __device__ __forceinline__ float softplus_f(float x) {
-  const float l = log1p_unit(__expf(-fabsf(x)));
-  return x > 20.f ? x : (x > 0.f ? x + l : l);
+  return max_nan(x, 0.f) + log1p_unit(fast_ex2(-fabsf(x) * kLog2e));
 }
-// NaN-propagating ReLU like torch.relu (fmaxf would swallow a NaN)
-__device__ __forceinline__ float relu_f(float x) { return x < 0.f ? 0.f : x; }
-__device__ __forceinline__ float sigmoid_f(float x) { return fast_div(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float softplus_grad(float x) { return x > 20.f ? 1.f : sigmoid_f(x); }
+__device__ __forceinline__ float relu_f(float x) { return max_nan(x, 0.f); }
+__device__ __forceinline__ float sigmoid_f(float x) { return fast_rcp(1.f + fast_ex2(-x * kLog2e)); }
+// d softplus / dx (equals 1 to fp32 precision above torch's threshold of 20)
+__device__ __forceinline__ float softplus_grad(float x) { return sigmoid_f(x); }
 __device__ __forceinline__ float sign_f(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 
 // ------------------------------------------------------------------ GTF forward
@@ -200,13 +208,25 @@ __device__ __forceinline__ void gtf_rows_forward(const float* __restrict__ sP, f
   }
 }
 
-// one row, keeping what the backward pass needs: gate (post-sigmoid), lin, nl and
-// the pre-softplus std
+// Panel columns of the weight-gradient staging area (bfvi_wgrad.cuh): X holds the
+// layer inputs [1, z] [1, h1] [1, h3] [1, nl]; D the pre-activation gradients.
 template <int Z, int H>
-__device__ __forceinline__ void gtf_row_forward_full(const float* __restrict__ sP, const float (&z)[Z],
-                                                     float (&g)[Z], float (&lin)[Z], float (&nl)[Z],
-                                                     float (&as)[Z]) {
+struct GtfCols {
+  static constexpr int XZ = 0, XH1 = 1 + Z, XH3 = XH1 + 1 + H, XNL = XH3 + 1 + H, NXC = XNL + 1 + Z;
+  static constexpr int DA1 = 0, DA3 = H, DLIN = 2 * H, DAG = 2 * H + Z, DNL = 2 * H + 2 * Z,
+                       DAS = 2 * H + 3 * Z, NDC = 2 * H + 4 * Z;
+};
+
+// One row forward for the backward pass: returns gate (post-sigmoid), lin, nl and
+// the pre-softplus std, and writes the hidden activations relu(a1), relu(a3) straight
+// into this lane's slot of the X staging panel (panel_at(column, lane)), where the
+// weight-gradient tiles AND the backward unit loop below read them back.
+template <int Z, int H>
+__device__ __forceinline__ void gtf_row_forward_stage(const float* __restrict__ sP, const float (&z)[Z],
+                                                      float (&g)[Z], float (&lin)[Z], float (&nl)[Z],
+                                                      float (&as)[Z], float* __restrict__ Xp, int lane) {
   using P = GtfPack<Z, H>;
+  using C = GtfCols<Z, H>;
 #pragma unroll
   for (int o = 0; o < Z; ++o) { g[o] = sP[P::B2G + o]; nl[o] = sP[P::B2N + o]; }
 #pragma unroll 4
@@ -218,6 +238,8 @@ __device__ __forceinline__ void gtf_row_forward_full(const float* __restrict__ s
 #pragma unroll
     for (int i = 0; i < Z; ++i) { a = fmaf(wg[1 + i], z[i], a); c = fmaf(wn[1 + i], z[i], c); }
     a = relu_f(a); c = relu_f(c);
+    Xp[panel_at(C::XH1 + 1 + h, lane)] = a;
+    Xp[panel_at(C::XH3 + 1 + h, lane)] = c;
 #pragma unroll
     for (int o = 0; o < Z; ++o) { g[o] = fmaf(wg[1 + Z + o], a, g[o]); nl[o] = fmaf(wn[1 + Z + o], c, nl[o]); }
   }
@@ -231,39 +253,33 @@ __device__ __forceinline__ void gtf_row_forward_full(const float* __restrict__ s
     for (int i = 0; i < Z; ++i) { l = fmaf(wl[1 + i], z[i], l); s = fmaf(ws[1 + i], nl[i], s); }
     lin[o] = l; as[o] = s;
     g[o] = sigmoid_f(g[o]);
+    Xp[panel_at(C::XZ + 1 + o, lane)] = z[o];
+    Xp[panel_at(C::XNL + 1 + o, lane)] = nl[o];
   }
 }
 
-// Panel columns of the weight-gradient staging area (bfvi_wgrad.cuh): X holds the
-// layer inputs [1, z] [1, h1] [1, h3] [1, nl]; D the pre-activation gradients.
+// Backward of one row given d_qm / d_qs.  Hidden activations come back from the X
+// panel (gtf_row_forward_stage); the pre-activation gradients go to the D panel,
+// all zero when the row is padding (so the X entries of padding rows, copies of a
+// real row, contribute nothing).  Returns dz.
 template <int Z, int H>
-struct GtfCols {
-  static constexpr int XZ = 0, XH1 = 1 + Z, XH3 = XH1 + 1 + H, XNL = XH3 + 1 + H, NXC = XNL + 1 + Z;
-  static constexpr int DA1 = 0, DA3 = H, DLIN = 2 * H, DAG = 2 * H + Z, DNL = 2 * H + 2 * Z,
-                       DAS = 2 * H + 3 * Z, NDC = 2 * H + 4 * Z;
-};
-
-// Backward of one row given d_qm / d_qs.  Hidden activations are recomputed per
-// unit; the row's layer inputs and pre-activation gradients are written straight
-// into this lane's slot of the staging panels (column * RS + lane), zeroed when the
-// row is padding.  Returns dz.
-template <int Z, int H, int RS>
-__device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__ sP, const float (&z)[Z],
-                                                       const float (&g)[Z], const float (&lin)[Z],
-                                                       const float (&nl)[Z], const float (&as)[Z],
-                                                       const float (&d_qm)[Z], const float (&d_qs)[Z],
-                                                       float (&dz)[Z], float* __restrict__ Xp,
-                                                       float* __restrict__ Dp, int lane, bool valid) {
+__device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__ sP, const float (&g)[Z],
+                                                       const float (&lin)[Z], const float (&nl)[Z],
+                                                       const float (&as)[Z], const float (&d_qm)[Z],
+                                                       const float (&d_qs)[Z], float (&dz)[Z],
+                                                       const float* __restrict__ Xp, float* __restrict__ Dp,
+                                                       int lane, bool valid) {
   using P = GtfPack<Z, H>;
   using C = GtfCols<Z, H>;
   const float vm = valid ? 1.f : 0.f;
   float d_as[Z], d_nl[Z], d_ag[Z], d_lin[Z];
 #pragma unroll
   for (int o = 0; o < Z; ++o) {
-    d_as[o] = d_qs[o] * softplus_grad(as[o]) * vm;
-    d_nl[o] = d_qm[o] * g[o] * vm;
-    d_ag[o] = d_qm[o] * (nl[o] - lin[o]) * g[o] * (1.f - g[o]) * vm;
-    d_lin[o] = d_qm[o] * (1.f - g[o]) * vm;
+    const float dq = d_qm[o] * vm;
+    d_as[o] = d_qs[o] * vm * softplus_grad(as[o]);
+    d_nl[o] = dq * g[o];
+    d_lin[o] = dq - d_nl[o];                               // dq * (1 - g)
+    d_ag[o] = d_lin[o] * g[o] * (nl[o] - lin[o]);          // dq * (nl - lin) * g * (1 - g)
     dz[o] = 0.f;
   }
 #pragma unroll
@@ -279,31 +295,26 @@ __device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__
   }
 #pragma unroll
   for (int o = 0; o < Z; ++o) {
-    Xp[(C::XZ + 1 + o) * RS + lane] = z[o] * vm;
-    Xp[(C::XNL + 1 + o) * RS + lane] = nl[o] * vm;
-    Dp[(C::DLIN + o) * RS + lane] = d_lin[o];
-    Dp[(C::DAG + o) * RS + lane] = d_ag[o];
-    Dp[(C::DNL + o) * RS + lane] = d_nl[o];
-    Dp[(C::DAS + o) * RS + lane] = d_as[o];
+    Dp[panel_at(C::DLIN + o, lane)] = d_lin[o];
+    Dp[panel_at(C::DAG + o, lane)] = d_ag[o];
+    Dp[panel_at(C::DNL + o, lane)] = d_nl[o];
+    Dp[panel_at(C::DAS + o, lane)] = d_as[o];
   }
 #pragma unroll 4
   for (int h = 0; h < H; ++h) {
     float wg[P::U], wn[P::U];
     lds_vec<P::U>(sP + P::GATE + h * P::U, wg);
     lds_vec<P::U>(sP + P::NONLIN + h * P::U, wn);
-    float a = wg[0], c = wn[0], da = 0.f, dc = 0.f;
-#pragma unroll
-    for (int i = 0; i < Z; ++i) { a = fmaf(wg[1 + i], z[i], a); c = fmaf(wn[1 + i], z[i], c); }
+    const float h1 = Xp[panel_at(C::XH1 + 1 + h, lane)], h3 = Xp[panel_at(C::XH3 + 1 + h, lane)];
+    float da = 0.f, dc = 0.f;
 #pragma unroll
     for (int o = 0; o < Z; ++o) { da = fmaf(wg[1 + Z + o], d_ag[o], da); dc = fmaf(wn[1 + Z + o], d_nl[o], dc); }
-    da = a > 0.f ? da : 0.f;
-    dc = c > 0.f ? dc : 0.f;
+    da = h1 > 0.f ? da : 0.f;
+    dc = h3 > 0.f ? dc : 0.f;
 #pragma unroll
     for (int i = 0; i < Z; ++i) { dz[i] = fmaf(wg[1 + i], da, dz[i]); dz[i] = fmaf(wn[1 + i], dc, dz[i]); }
-    Xp[(C::XH1 + 1 + h) * RS + lane] = relu_f(a) * vm;
-    Xp[(C::XH3 + 1 + h) * RS + lane] = relu_f(c) * vm;
-    Dp[(C::DA1 + h) * RS + lane] = da;
-    Dp[(C::DA3 + h) * RS + lane] = dc;
+    Dp[panel_at(C::DA1 + h, lane)] = da;
+    Dp[panel_at(C::DA3 + h, lane)] = dc;
   }
 }
 
@@ -325,7 +336,7 @@ __device__ __forceinline__ float poe_prec_grad(float std, float prec) {
 __device__ __forceinline__ void poe2_forward(float gm, float gs, float qm, float qs,
                                              float& pm, float& ps) {
   const float vg = fmaf(gs, gs, kPoeEps), vq = fmaf(qs, qs, kPoeEps);
-  const float r = fast_div(1.f, vg + vq);
+  const float r = fast_rcp(vg + vq);
   const float m = (gm * vq + qm * vg) * r;
   pm = (m != m) ? 0.f : m;                    // product_mean[isnan] = 0, models/dgts.py:49
   ps = fast_sqrt(vg * vq * r);
@@ -334,9 +345,9 @@ __device__ __forceinline__ void poe2_backward(float gm, float gs, float qm, floa
                                               float ps, float d_pm, float d_ps, float& d_gm,
                                               float& d_gs, float& d_qm, float& d_qs) {
   const float vg = fmaf(gs, gs, kPoeEps), vq = fmaf(qs, qs, kPoeEps);
-  const float r = fast_div(1.f, vg + vq);
+  const float r = fast_rcp(vg + vq);
   const float wg = vq * r, wq = vg * r;             // weights of gm / qm in the mean
-  const float d_var = fast_div(0.5f * d_ps, ps);
+  const float d_var = 0.5f * d_ps * fast_rcp(ps);
   d_gm = d_pm * wg;
   d_qm = d_pm * wq;
   d_gs = (d_pm * (qm - pm) * r + d_var * wg * wg) * 2.f * gs;
@@ -381,6 +392,20 @@ __device__ __forceinline__ float group_sum(float v, int base, int L) {
   float s = __shfl_sync(0xffffffffu, v, base);
   for (int j = 1; j < L; ++j) s += __shfl_sync(0xffffffffu, v, base + j);
   return s;
+}
+
+// the same for N values at once (one shuffle loop instead of N)
+template <int N>
+__device__ __forceinline__ void group_sum_vec(float (&v)[N], int base, int L) {
+  float s[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) s[i] = __shfl_sync(0xffffffffu, v[i], base);
+  for (int j = 1; j < L; ++j) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) s[i] += __shfl_sync(0xffffffffu, v[i], base + j);
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = s[i];
 }
 
 }  // namespace bfvi

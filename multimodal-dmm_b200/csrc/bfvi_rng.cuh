@@ -7,7 +7,7 @@
 // backward pass can regenerate it instead of storing it.  bfvi_dump_noise runs the
 // SAME function to hand the identical stream to the oracle.
 #pragma once
-#include "bfvi_platform.cuh"
+#include "bfvi_math.cuh"
 
 namespace bfvi {
 
@@ -33,8 +33,9 @@ __device__ __forceinline__ void normal4(uint64_t seed, unsigned stream_id, unsig
                                         unsigned b, unsigned k, unsigned chunk, float (&out)[4]) {
   const uint4 r = philox4x32_10(make_uint4(b, k | (chunk << 24), t, s | (stream_id << 16)),
                                 uint2{(unsigned)seed, (unsigned)(seed >> 32)});
-  const float r0 = sqrtf(__fmul_rn(-2.f, __logf(u01(r.x))));
-  const float r1 = sqrtf(__fmul_rn(-2.f, __logf(u01(r.z))));
+  // Box-Muller radius sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u) on the MUFU path
+  const float r0 = fast_sqrt(-1.3862943611198906f * fast_lg2(u01(r.x)));
+  const float r1 = fast_sqrt(-1.3862943611198906f * fast_lg2(u01(r.z)));
   float s0, c0, s1, c1;
   __sincosf(__fmul_rn(6.283185307179586f, u01(r.y)), &s0, &c0);
   __sincosf(__fmul_rn(6.283185307179586f, u01(r.w)), &s1, &c1);

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(kMlpWarps * 32) mlp_bwd_kernel(const __grid_co
   if (with_grad) {
     wg_build_tables<kMlpTD, kTX>(spec, tasks, oidx, rounds, p.off.size);
     for (int i = lane; i < p.off.size + 32; i += 32) G[i] = 0.f;
-    Xp[0 * kRS + lane] = 1.f;
-    Xp[pn.xh() * kRS + lane] = 1.f;
+    Xp[panel_at(0, lane)] = 1.f;
+    Xp[panel_at(pn.xh(), lane)] = 1.f;
   }
   __syncthreads();
 
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(kMlpWarps * 32) mlp_bwd_kernel(const __grid_co
         }
       }
       if (with_grad) {
-        Dp[(pn.dm() + o) * kRS + lane] = d_m;
-        Dp[(pn.ds() + o) * kRS + lane] = d_p;
+        Dp[panel_at(pn.dm() + o, lane)] = d_m;
+        Dp[panel_at(pn.ds() + o, lane)] = d_p;
       }
 #pragma unroll
       for (int j = 0; j < H; ++j)
@@ -190,13 +190,13 @@ __global__ void __launch_bounds__(kMlpWarps * 32) mlp_bwd_kernel(const __grid_co
     if (with_grad) {
 #pragma unroll
       for (int j = 0; j < H; ++j) {
-        Dp[(pn.da() + j) * kRS + lane] = ok ? dh[j] : 0.f;
-        Xp[(pn.xh() + 1 + j) * kRS + lane] = ok ? h[j] : 0.f;
+        Dp[panel_at(pn.da() + j, lane)] = ok ? dh[j] : 0.f;
+        Xp[panel_at(pn.xh() + 1 + j, lane)] = ok ? h[j] : 0.f;
       }
       for (int i = 0; i < p.n_in; ++i) {
         float xi = xrow[i];
         if (xi != xi) xi = 0.f;
-        Xp[(1 + i) * kRS + lane] = ok ? xi : 0.f;
+        Xp[panel_at(1 + i, lane)] = ok ? xi : 0.f;
       }
       __syncwarp();
       wg_accumulate<kMlpTD, kTX>(Dp, Xp, tasks, oidx, rounds, G, lane);
