@@ -152,7 +152,7 @@ int task_grid(int64_t chains, int lanes, int warps_per_block) {
 template <int Z, int H>
 int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
-  const int64_t chains = (int64_t)a.S * a.B;
+  const int64_t chains = (int64_t)a.S * (fp.bc > 0 ? fp.bc : a.B);
   const int wpb = bfvi::kChainFwdThreads / 32;
   if (a.n_particles > 1) {
     constexpr int R = 5;
@@ -162,7 +162,8 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   } else {
     fp.lanes = 1; fp.rounds = 1;
     auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
-    BFVI_LAUNCH(k, dim3(task_grid(chains, 1, wpb)), dim3(bfvi::kChainFwdThreads), 0, st, fp);
+    // latency-bound single-particle pass: 2-warp CTAs spread the few warps over all SMs
+    BFVI_LAUNCH(k, dim3(task_grid(chains, 1, 2)), dim3(64), 0, st, fp);
   }
   BFVI_CHECK_CUDA();
   return BFVI_OK;
@@ -171,9 +172,11 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
 template <int Z, int H>
 int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
-  const int64_t chains = (int64_t)a.S * a.B;
-  const size_t smem = bfvi::chain_bwd_smem_bytes<Z, H>();
-  const int threads = bfvi::kChainBwdWarps * 32;
+  const int64_t chains = (int64_t)a.S * (fp.bc > 0 ? fp.bc : a.B);
+  // single-particle passes are latency-bound with few warps: 2-warp CTAs reach all SMs
+  const int warps = a.n_particles > 1 ? bfvi::kChainBwdWarps : 2;
+  const size_t smem = bfvi::chain_bwd_smem_bytes<Z, H>(warps);
+  const int threads = warps * 32;
   const bfvi::WgSpec spec = bfvi::GtfPanels<Z, H>::spec();
   if (bfvi::wg_rounds<bfvi::GtfPanels<Z, H>::TD, bfvi::kTX>(spec) != 1)
     return fail(BFVI_ERR_UNSUPPORTED, "internal: weight-gradient tiling needs one round");
@@ -182,7 +185,7 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   fp.slices = (a.n_particles + fp.lanes - 1) / fp.lanes;
   auto k = bfvi::chain_bwd_kernel<Z, H>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, bfvi::kChainBwdWarps)), dim3(threads), smem, st, fp);
+  BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
@@ -285,30 +288,36 @@ bfvi::FilterParams make_filter_params(const bfvi_model* m, const bfvi_layout& la
   fp.g_z0_log_std = grads ? grads + lay.z0_log_std : nullptr;
   fp.min_std = m->min_std;
   fp.lanes = 1; fp.rounds = 1; fp.slices = 1;
+  fp.b0 = 0; fp.bc = 0;
   return fp;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// A lazily created non-blocking side stream + fork/join events per (host thread,
-// device): the f_mode filtering ELBO of a step (pass A) is independent of the s_mode
-// passes (B, C), is latency-bound, and overlaps them on the side stream.
-struct SideStream {
-  cudaStream_t stream;
-  cudaEvent_t fork, join;
+// Lazily created non-blocking side streams + fork/join events per (host thread,
+// device).  Inside one step the f_mode filtering ELBO (pass A) is independent of the
+// s_mode passes (B, C), and the batch chunks of B / C are independent of each other:
+// the latency-bound single-particle kernels of one branch overlap the throughput-bound
+// particle kernels of another.  Everything forks from and joins back into the caller's
+// stream, so the call stays asynchronous and stream-ordered for the caller.
+constexpr int kSideStreams = 4;
+struct SideStreams {
+  cudaStream_t stream[kSideStreams];
+  cudaEvent_t fork, join[kSideStreams];
   bool ok;
 };
-SideStream* side_stream() {
-  static thread_local SideStream cache[64];
+SideStreams* side_streams() {
+  static thread_local SideStreams cache[64];
   static thread_local bool made[64];
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!made[dev]) {
     made[dev] = true;
-    SideStream& c = cache[dev];
-    c.ok = cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) == cudaSuccess &&
-           cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess &&
-           cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) == cudaSuccess;
+    SideStreams& c = cache[dev];
+    c.ok = cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < kSideStreams && c.ok; ++i)
+      c.ok = cudaStreamCreateWithFlags(&c.stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c.join[i], cudaEventDisableTiming) == cudaSuccess;
   }
   return cache[dev].ok ? &cache[dev] : nullptr;
 }
@@ -356,6 +365,32 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   for (int i = 0; i < 4; ++i) pl->off_b[i] = carve(fS);
   for (int i = 0; i < 5; ++i) pl->off_c[i] = carve(fS);
   pl->total = cur;
+}
+
+// batch chunk [b0, b0 + bc) of the (T, B) problem; bc = 0 means the whole batch
+struct Chunk { int b0, bc; };
+
+int decode_nll_impl(const bfvi_model* m, const bfvi_layout& lay, const float* params, float* grads, int32_t mod,
+                    const float* z, const float* target, const uint8_t* row_mask, int T, int B, Chunk ck,
+                    float weight, double* loss_acc, float* d_z, cudaStream_t st) {
+  bfvi::MlpParams mp;
+  memset(&mp, 0, sizeof(mp));
+  mp.w = params + lay.dec[mod].begin;
+  mp.g = grads ? grads + lay.dec[mod].begin : nullptr;
+  mp.off = mlp_offsets(lay.dec[mod]);
+  mp.n_in = m->z_dim; mp.n_out = m->dims[mod];
+  mp.n_rows = (int64_t)T * (ck.bc > 0 ? ck.bc : B);
+  mp.B = B; mp.b0 = ck.b0; mp.bc = ck.bc;
+  mp.x = z; mp.target = target; mp.row_mask = row_mask; mp.weight = weight;
+  mp.loss_acc = loss_acc; mp.d_x = d_z;
+  return launch_mlp_bwd(m->h_dim, true, mp, st);
+}
+
+int filter_impl(const bfvi_model* m, const bfvi_layout& lay, const float* params, float* grads,
+                const bfvi_filter_args* a, Chunk ck, bool backward, cudaStream_t st) {
+  bfvi::FilterParams fp = make_filter_params(m, lay, params, grads, a);
+  fp.b0 = ck.b0; fp.bc = ck.bc;
+  return dispatch_filter(m, lay, backward, fp, st);
 }
 
 }  // namespace
@@ -745,68 +780,109 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     }
 
     const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
-    // decoders + NLL (+ their backward) on the samples of one pass
-    auto decode_pass = [&](int pass, void* strm) -> int {
+    // decoders + NLL (+ their backward) on the samples of one pass, one batch chunk
+    auto decode_pass = [&](int pass, Chunk ck, cudaStream_t strm) -> int {
       const float mult = pass == 0 ? a->f_mult : a->s_mult;
       float* samp = pass == 0 ? A(4) : C(4);
       float* dsamp = with_grad ? (pass == 0 ? A(5) : C(5)) : nullptr;
       for (int s = 0; s < S; ++s)
         for (int i = 0; i < M; ++i) {
           if (!((pl.set_bits[s] >> i) & 1u) || a->rec_mults[i] == 0.f) continue;
-          if (int rc = bfvi_decode_nll(m, params, grads, i, samp + (size_t)s * pl.n_tbz, a->targets[i],
-                                       a->seq_mask, tb, mult * a->rec_mults[i], acc,
+          if (int rc = decode_nll_impl(m, lay, params, grads, i, samp + (size_t)s * pl.n_tbz, a->targets[i],
+                                       a->seq_mask, T, B, ck, mult * a->rec_mults[i], acc,
                                        dsamp ? dsamp + (size_t)s * pl.n_tbz : nullptr, strm))
             return rc;
           ++n_launch;
         }
       return BFVI_OK;
     };
-    // Pass A (f_mode ELBO) shares nothing but atomically accumulated outputs with
-    // passes B / C: when both run, A goes to the side stream (not while profiling
-    // phases, where every phase must be alone on the timed stream).
-    SideStream* side = (do_f && do_s && !pm.on) ? side_stream() : nullptr;
-    void* stream_a = stream;
-    if (side != nullptr) {
-      cudaEventRecord(side->fork, st);
-      cudaStreamWaitEvent(side->stream, side->fork, 0);
-      stream_a = (void*)side->stream;
-    }
-    pm.begin(BFVI_PHASE_FILTER_F_FWD);
-    if (do_f) { if (int rc = bfvi_filter_fwd(m, params, &fa, stream_a)) return rc; ++n_launch; }
-    if (do_f && side != nullptr) {               // the whole A pipeline runs beside B / C
-      if (int rc = decode_pass(0, stream_a)) return rc;
-      if (with_grad) {
-        fa.d_samples = A(5);
-        if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream_a)) return rc; ++n_launch;
+    fa.d_samples = with_grad ? A(5) : nullptr;
+    fc.d_samples = with_grad ? C(5) : nullptr;
+    fb.d_prior_mean = with_grad ? Bf(4) : nullptr;
+    fb.d_prior_std = with_grad ? Bf(5) : nullptr;
+    const Chunk all{0, 0};
+
+    // ---- stream plan ------------------------------------------------------------------
+    // Pass A and every batch chunk of passes B / C are independent branches.  While a
+    // phase profile is recorded everything stays on the caller's stream, one phase at a
+    // time; otherwise branches fork onto side streams and join before the encoders'
+    // backward.
+    int n_chunks = 1;
+    SideStreams* side = pm.on ? nullptr : side_streams();
+    if (side != nullptr && do_s) {
+      n_chunks = B >= 1024 ? 2 : 1;
+      if (const char* env = getenv("BFVI_CHUNKS")) {       // tuning knob
+        const int v = atoi(env);
+        if (v >= 1 && v <= kSideStreams) n_chunks = v;
       }
-      cudaEventRecord(side->join, side->stream);
+      if (n_chunks > B) n_chunks = B;
     }
-    pm.begin(BFVI_PHASE_FILTER_S_FLT_FWD);
+    const bool fork_a = side != nullptr && do_f && do_s;
+    const bool forked = fork_a || n_chunks > 1;
+    if (forked) {
+      cudaEventRecord(side->fork, st);
+      for (int i = 0; i < kSideStreams; ++i) cudaStreamWaitEvent(side->stream[i], side->fork, 0);
+    }
+    // chunk c of B / C runs on the caller's stream (c = 0) or side stream c; pass A on
+    // side stream 0 when it is forked
+    auto chunk_stream = [&](int c) { return c == 0 ? st : side->stream[c]; };
+    auto chunk_of = [&](int c) {
+      if (n_chunks == 1) return all;
+      const int per = (B + n_chunks - 1) / n_chunks, b0 = c * per;
+      return Chunk{b0, (b0 + per <= B ? per : B - b0)};
+    };
+    cudaStream_t st_a = fork_a ? side->stream[0] : st;
+
+    pm.begin(BFVI_PHASE_FILTER_F_FWD);
+    if (do_f) { if (int rc = filter_impl(m, lay, params, nullptr, &fa, all, false, st_a)) return rc; ++n_launch; }
+    if (do_f && fork_a) {                        // the whole A pipeline runs beside B / C
+      if (int rc = decode_pass(0, all, st_a)) return rc;
+      if (with_grad) { if (int rc = filter_impl(m, lay, params, grads, &fa, all, true, st_a)) return rc; ++n_launch; }
+    }
     if (do_s) {
-      if (int rc = bfvi_filter_fwd(m, params, &fb, stream)) return rc; ++n_launch;
+      pm.begin(BFVI_PHASE_FILTER_S_FLT_FWD);
+      for (int c = 0; c < n_chunks; ++c) {
+        if (int rc = filter_impl(m, lay, params, nullptr, &fb, chunk_of(c), false, chunk_stream(c))) return rc;
+        ++n_launch;
+      }
       pm.begin(BFVI_PHASE_FILTER_S_SMT_FWD);
-      if (int rc = bfvi_filter_fwd(m, params, &fc, stream)) return rc; ++n_launch;
+      for (int c = 0; c < n_chunks; ++c) {
+        if (int rc = filter_impl(m, lay, params, nullptr, &fc, chunk_of(c), false, chunk_stream(c))) return rc;
+        ++n_launch;
+      }
     }
     pm.begin(BFVI_PHASE_DECODE_NLL);
-    if (do_f && side == nullptr) { if (int rc = decode_pass(0, stream)) return rc; }
-    if (do_s) { if (int rc = decode_pass(1, stream)) return rc; }
+    if (do_f && !fork_a) { if (int rc = decode_pass(0, all, st)) return rc; }
+    if (do_s)
+      for (int c = 0; c < n_chunks; ++c)
+        if (int rc = decode_pass(1, chunk_of(c), chunk_stream(c))) return rc;
     // ---- backward through the three passes and the encoders ------------------------
     if (with_grad) {
       if (do_s) {
-        fc.d_samples = C(5);
         pm.begin(BFVI_PHASE_FILTER_S_SMT_BWD);
-        if (int rc = bfvi_filter_bwd(m, params, grads, &fc, stream)) return rc; ++n_launch;
-        fb.d_prior_mean = Bf(4); fb.d_prior_std = Bf(5);
+        for (int c = 0; c < n_chunks; ++c) {
+          if (int rc = filter_impl(m, lay, params, grads, &fc, chunk_of(c), true, chunk_stream(c))) return rc;
+          ++n_launch;
+        }
         pm.begin(BFVI_PHASE_FILTER_S_FLT_BWD);
-        if (int rc = bfvi_filter_bwd(m, params, grads, &fb, stream)) return rc; ++n_launch;
+        for (int c = 0; c < n_chunks; ++c) {
+          if (int rc = filter_impl(m, lay, params, grads, &fb, chunk_of(c), true, chunk_stream(c))) return rc;
+          ++n_launch;
+        }
       }
-      if (do_f && side == nullptr) {
-        fa.d_samples = A(5);
+      if (do_f && !fork_a) {
         pm.begin(BFVI_PHASE_FILTER_F_BWD);
-        if (int rc = bfvi_filter_bwd(m, params, grads, &fa, stream)) return rc; ++n_launch;
+        if (int rc = filter_impl(m, lay, params, grads, &fa, all, true, st)) return rc; ++n_launch;
       }
     }
-    if (side != nullptr) cudaStreamWaitEvent(st, side->join, 0);
+    if (forked) {
+      for (int i = 0; i < kSideStreams; ++i) {
+        const bool used = (i == 0 && fork_a) || (i > 0 && i < n_chunks);
+        if (!used) continue;
+        cudaEventRecord(side->join[i], side->stream[i]);
+        cudaStreamWaitEvent(st, side->join[i], 0);
+      }
+    }
     if (with_grad) {
       pm.begin(BFVI_PHASE_ENCODE_BWD);
       for (int i = 0; i < M; ++i) {

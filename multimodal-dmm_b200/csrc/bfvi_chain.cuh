@@ -54,6 +54,7 @@ struct FilterParams {
   int lanes;                 // L: lanes per chain (1..32)
   int rounds;                // forward: ceil(K / (L * R))
   int slices;                // backward: ceil(K / L)
+  int b0, bc;                // batch chunk [b0, b0 + bc) served by this launch (bc = 0: all of B)
 };
 
 // -------------------------------------------------------------------------
@@ -174,6 +175,23 @@ __device__ __forceinline__ void poe_step_backward(const bfvi_filter_args& a, uns
   }
 }
 
+// Warm L1 with everything the product of experts of (s, t, b) will read, one time
+// step ahead of its use: the single-particle passes are latency-bound and their
+// expert loads sit on the critical path of every step.
+template <int Z>
+__device__ __forceinline__ void poe_step_prefetch(const bfvi_filter_args& a, unsigned bits, int s, int t,
+                                                  int b) {
+  for (int e = 0; e < a.n_experts; ++e) {
+    if (!((bits >> e) & 1u)) continue;
+    const bfvi_expert& ex = a.experts[e];
+    if (ex.kind != BFVI_EXPERT_TENSOR) continue;
+    if (ex.mask != nullptr) prefetch_l1(ex.mask + s * ex.mstride_s + t * ex.mstride_t + b * ex.mstride_b);
+    const int64_t off = s * ex.stride_s + t * ex.stride_t + b * ex.stride_b;
+    prefetch_l1(ex.mean + off); prefetch_l1(ex.mean + off + Z - 1);
+    prefetch_l1(ex.std + off); prefetch_l1(ex.std + off + Z - 1);
+  }
+}
+
 // lane-group geometry of one warp
 struct LaneGroup {
   int L, cpw, cig, lig, base;
@@ -209,7 +227,8 @@ chain_fwd_kernel(const __grid_constant__ FilterParams p) {
   const LaneGroup lg(p.lanes);
   const int L = lg.L, rounds = p.rounds;
   const int T = a.T, B = a.B, K = a.n_particles;
-  const int n_chains = a.S * B;
+  const int Bc = p.bc > 0 ? p.bc : B;
+  const int n_chains = a.S * Bc;
   const int n_tasks = (n_chains + lg.cpw - 1) / lg.cpw;
   const int wpb = blockDim.x >> 5;
   const float inv_k = 1.f / (float)K;
@@ -219,7 +238,7 @@ chain_fwd_kernel(const __grid_constant__ FilterParams p) {
     const int chain_raw = task * lg.cpw + lg.cig;
     const bool chain_ok = lg.on && chain_raw < n_chains;
     const int chain = chain_raw < n_chains ? chain_raw : n_chains - 1;
-    const int s = chain / B, b = chain % B;
+    const int s = chain / Bc, b = p.b0 + chain % Bc;
     const unsigned bits = a.set_expert_bits[s];
     const bool writer = chain_ok && lg.lig == 0;
     float mu_p[Z], sd_p[Z];
@@ -234,6 +253,7 @@ chain_fwd_kernel(const __grid_constant__ FilterParams p) {
 
     for (int i = 0; i < T; ++i) {
       const int t = pass_time(i, T, a.direction);
+      if (R == 1 && i + 1 < T) poe_step_prefetch<Z>(a, bits, s, pass_time(i + 1, T, a.direction), b);
       float pm[Z], ps[Z];
       if (i == 0) {
 #pragma unroll
@@ -305,7 +325,7 @@ chain_fwd_kernel(const __grid_constant__ FilterParams p) {
         }
         if (a.kl_weight != 0.f && (a.seq_mask == nullptr || a.seq_mask[t * B + b])) {
 #pragma unroll
-          for (int j = 0; j < Z; ++j) kl_sum += kld_elem(mu[j], sd[j], pm[j], ps[j]);
+          for (int j = 0; j < Z; ++j) kl_sum += kld_elem_fast(mu[j], sd[j], pm[j], ps[j]);
         }
       }
       // ---- particles of this step: next step's GTF input and the `samples` output ----
@@ -404,7 +424,7 @@ __device__ __forceinline__ void transition_slice_backward(
     float min_std, float inv_k, const float (&z)[Z], const float (&pm)[Z], const float (&d_pm)[Z],
     const float (&d_v)[Z], bool valid, float (&d_gm)[Z], float (&d_gs)[Z], float (&dz)[Z],
     float* __restrict__ Xp, float* __restrict__ Dp, int lane,
-    float (&acc)[GtfPanels<Z, H>::TD][kTX], const int4 task) {
+    float2 (&acc)[GtfPanels<Z, H>::TD][kTX], const int4 task) {
   float g[Z], lin[Z], nl[Z], as[Z], d_qm[Z], d_qs[Z];
   __syncwarp();                        // the previous slice's tile reads are done
   gtf_row_forward_stage<Z, H>(sP, z, g, lin, nl, as, Xp, lane);
@@ -462,16 +482,17 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
   Xp[panel_at(C::XNL, lane)] = 1.f;
   __syncthreads();
   const int4 task = reinterpret_cast<const int4*>(tasks)[lane];
-  float acc[TD][kTX];
+  float2 acc[TD][kTX];
 #pragma unroll
   for (int i = 0; i < TD; ++i)
 #pragma unroll
-    for (int j = 0; j < kTX; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < kTX; ++j) acc[i][j] = float2{0.f, 0.f};
 
   const LaneGroup lg(p.lanes);
   const int L = lg.L, slices = p.slices;
   const int T = a.T, B = a.B, K = a.n_particles;
-  const int n_chains = a.S * B;
+  const int Bc = p.bc > 0 ? p.bc : B;
+  const int n_chains = a.S * Bc;
   const int n_tasks = (n_chains + lg.cpw - 1) / lg.cpw;
   const float inv_k = 1.f / (float)K;
   float d_gm[Z], d_gs[Z];                 // global-prior gradient, per thread
@@ -483,7 +504,7 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
     const int chain_raw = wt * lg.cpw + lg.cig;
     const bool chain_ok = lg.on && chain_raw < n_chains;
     const int chain = chain_raw < n_chains ? chain_raw : n_chains - 1;
-    const int s = chain / B, b = chain % B;
+    const int s = chain / Bc, b = p.b0 + chain % Bc;
     const unsigned bits = a.set_expert_bits[s];
     const bool emit = chain_ok && lg.lig == 0;        // one writer per chain
     float c_mu[Z], c_sd[Z], eps_cur[Z];
@@ -491,13 +512,33 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
     for (int j = 0; j < Z; ++j) c_mu[j] = c_sd[j] = eps_cur[j] = 0.f;
     bool have_eps_cur = false;
 
+    float mu_c[Z], sd_c[Z];               // infer (mean, std) of the step being processed
+    {
+      const int64_t o0 = (((int64_t)s * T + pass_time(T - 1, T, a.direction)) * B + b) * Z;
+#pragma unroll
+      for (int j = 0; j < Z; ++j) { mu_c[j] = a.infer_mean[o0 + j]; sd_c[j] = a.infer_std[o0 + j]; }
+    }
     for (int i = T - 1; i >= 0; --i) {
       const int t = pass_time(i, T, a.direction);
       const int64_t o = (((int64_t)s * T + t) * B + b) * Z;
+      if (K == 1 && i > 0) {              // warm L1 for the next (earlier) step of this chain
+        const int tn = pass_time(i - 1, T, a.direction);
+        const int64_t on = (((int64_t)s * T + tn) * B + b) * Z;
+        prefetch_l1(a.prior_mean + on); prefetch_l1(a.prior_mean + on + Z - 1);
+        prefetch_l1(a.prior_std + on); prefetch_l1(a.prior_std + on + Z - 1);
+        if (a.d_samples) { prefetch_l1(a.d_samples + on); prefetch_l1(a.d_samples + on + Z - 1); }
+        if (a.d_prior_mean) { prefetch_l1(a.d_prior_mean + on); prefetch_l1(a.d_prior_std + on); }
+        if (i > 1) {
+          const int64_t o2 = (((int64_t)s * T + pass_time(i - 2, T, a.direction)) * B + b) * Z;
+          prefetch_l1(a.infer_mean + o2); prefetch_l1(a.infer_mean + o2 + Z - 1);
+          prefetch_l1(a.infer_std + o2); prefetch_l1(a.infer_std + o2 + Z - 1);
+        }
+        poe_step_prefetch<Z>(a, bits, s, tn, b);
+      }
       float mu[Z], sd[Z], pm[Z], ps[Z], d_mu[Z], d_sd[Z], d_pm[Z], d_ps[Z];
 #pragma unroll
       for (int j = 0; j < Z; ++j) {
-        mu[j] = a.infer_mean[o + j]; sd[j] = a.infer_std[o + j];
+        mu[j] = mu_c[j]; sd[j] = sd_c[j];
         pm[j] = a.prior_mean[o + j]; ps[j] = a.prior_std[o + j];
         d_mu[j] = c_mu[j] + (a.d_infer_mean ? a.d_infer_mean[o + j] : 0.f);
         d_sd[j] = c_sd[j] + (a.d_infer_std ? a.d_infer_std[o + j] : 0.f);
@@ -563,6 +604,7 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
 #pragma unroll
       for (int j = 0; j < Z; ++j) {
         mu_p[j] = a.infer_mean[op + j]; sd_p[j] = a.infer_std[op + j];
+        mu_c[j] = mu_p[j]; sd_c[j] = sd_p[j];
         d_v[j] = d_ps[j] * 0.5f / ps[j];
         c_mu[j] = c_sd[j] = 0.f;
       }
@@ -626,10 +668,10 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
 }
 
 template <int Z, int H>
-inline size_t chain_bwd_smem_bytes() {
+inline size_t chain_bwd_smem_bytes(int warps) {
   using PN = GtfPanels<Z, H>;
   const WgSpec spec = PN::spec();
-  return sizeof(float) * ((size_t)kChainBwdWarps * PN::WARP_FLOATS) +
+  return sizeof(float) * ((size_t)warps * PN::WARP_FLOATS) +
          sizeof(int) * (size_t)wg_table_ints<PN::TD, kTX>(spec);
 }
 
@@ -726,11 +768,11 @@ __global__ void __launch_bounds__(32) match_kernel(const __grid_constant__ Match
     d_gs[j] = lane == 0 ? g2 : 0.f;
     d_v[j] = d_ns * 0.5f / ns[j];
   }
-  float acc[TD][kTX];
+  float2 acc[TD][kTX];
 #pragma unroll
   for (int i = 0; i < TD; ++i)
 #pragma unroll
-    for (int j = 0; j < kTX; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < kTX; ++j) acc[i][j] = float2{0.f, 0.f};
   for (int sl = 0; sl < n_sl; ++sl) {
     const int k = sl * 32 + lane;
     const bool valid = k < K;

@@ -45,7 +45,13 @@ struct MlpParams {
   float weight;
   double* loss_acc;
   float* d_x;             // (n_rows, n_in), += (nullable)
+  // batch chunking of (T, B) rows: row r' of the launch is (t = r' / bc, b = b0 + r' % bc)
+  // of the full tensor, i.e. row t * B + b; bc = 0 means the identity
+  int B, b0, bc;
 };
+__device__ __forceinline__ int64_t mlp_row(const MlpParams& p, int64_t r) {
+  return p.bc > 0 ? (r / p.bc) * p.B + p.b0 + r % p.bc : r;
+}
 
 // hidden layer: h = relu(W1 x + b1); x read from global with NaN -> 0 when `nan_to_zero`
 template <int H>
@@ -141,7 +147,7 @@ __global__ void __launch_bounds__(kMlpWarps * 32) mlp_bwd_kernel(const __grid_co
   for (int64_t base = gwarp * 32; base < p.n_rows; base += total_warps * 32) {
     const int64_t r_raw = base + lane;
     const bool ok = r_raw < p.n_rows;
-    const int64_t r = ok ? r_raw : p.n_rows - 1;
+    const int64_t r = mlp_row(p, ok ? r_raw : p.n_rows - 1);
     const float* xrow = p.x + r * p.n_in;
     float h[H], dh[H];
     mlp_hidden<H>(sW, p.off, xrow, p.n_in, !DECODER, h);

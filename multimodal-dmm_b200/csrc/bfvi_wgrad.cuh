@@ -13,15 +13,12 @@
 
 namespace bfvi {
 
-constexpr int kRS = 32;   // panel column stride in floats: exactly the 32 rows of a slice
+constexpr int kRS = 36;   // panel column stride in floats: 32 rows + 4 pad (keeps float4 alignment
+                          // and spreads the tile loads of 8 lanes on 8 columns over 8 bank groups)
 
-// Element (col, row) of a panel.  The 8 row-quads of a column are XOR-swizzled with the
-// column index, so the 128-bit tile loads of 8 lanes on 8 consecutive columns hit 8
-// different bank groups without padding the columns (padding to 36 floats cost 11 % of
-// the shared memory that bounds the resident warps of the backward kernels).
-__host__ __device__ __forceinline__ int panel_at(int col, int row) {
-  return col * kRS + ((((row >> 2) ^ col) & 7) << 2) + (row & 3);
-}
+// element (col, row) of a panel (an XOR swizzle without padding was tried: it saves 11 %
+// of the shared memory but costs two integer instructions per tile load)
+__host__ __device__ __forceinline__ int panel_at(int col, int row) { return col * kRS + row; }
 
 struct WgBlock {          // one Linear layer: dW (nd x (nx-1)) and db (nd)
   int d0, nd;             // D-panel columns (pre-activation gradients)
@@ -98,24 +95,23 @@ __device__ __forceinline__ void wg_accumulate(const float* __restrict__ Dp, cons
       for (int j = 0; j < TX; ++j) acc[i][j] = 0.f;
     const float4* dcol[TD];
     const float4* xcol[TX];
-    int dsw[TD], xsw[TX];
-#pragma unroll
+  #pragma unroll
     for (int i = 0; i < TD; ++i) {
       const int c = t.x + min(i, t.y - 1);
-      dcol[i] = reinterpret_cast<const float4*>(Dp + c * kRS); dsw[i] = c & 7;
+      dcol[i] = reinterpret_cast<const float4*>(Dp + c * kRS);
     }
 #pragma unroll
     for (int j = 0; j < TX; ++j) {
       const int c = t.z + min(j, t.w - 1);
-      xcol[j] = reinterpret_cast<const float4*>(Xp + c * kRS); xsw[j] = c & 7;
+      xcol[j] = reinterpret_cast<const float4*>(Xp + c * kRS);
     }
 #pragma unroll 2
     for (int q = 0; q < 8; ++q) {
       float4 dv[TD], xv[TX];
 #pragma unroll
-      for (int i = 0; i < TD; ++i) dv[i] = dcol[i][q ^ dsw[i]];
+      for (int i = 0; i < TD; ++i) dv[i] = dcol[i][q];
 #pragma unroll
-      for (int j = 0; j < TX; ++j) xv[j] = xcol[j][q ^ xsw[j]];
+      for (int j = 0; j < TX; ++j) xv[j] = xcol[j][q];
 #pragma unroll
       for (int i = 0; i < TD; ++i)
 #pragma unroll
@@ -137,50 +133,51 @@ __device__ __forceinline__ void wg_accumulate(const float* __restrict__ Dp, cons
 // Register-tile variant for kernels whose task list fits ONE round (<= 32 tiles):
 // the lane keeps its TD x TX tile in registers across several staged row slices
 // (wg_tile_fma) and folds it into the per-warp accumulator G once (wg_tile_flush).
+// Each accumulator is a float2 {even rows, odd rows}: the products of one 128-bit
+// panel load pair up as two packed FFMA2 (sm_100 fma.rn.f32x2) instead of four FFMA,
+// halving the issue slots of the rank-32 update.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#ifdef BFVI_EMU
+  return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#else
+  return __ffma2_rn(a, b, c);
+#endif
+}
 template <int TD, int TX>
-__device__ __forceinline__ void wg_tile_fma(float (&acc)[TD][TX], const float* __restrict__ Dp,
+__device__ __forceinline__ void wg_tile_fma(float2 (&acc)[TD][TX], const float* __restrict__ Dp,
                                             const float* __restrict__ Xp, const int4 t) {
   const float4* dcol[TD];
   const float4* xcol[TX];
-  int dsw[TD], xsw[TX];
 #pragma unroll
-  for (int i = 0; i < TD; ++i) {
-    const int c = t.x + min(i, t.y - 1);
-    dcol[i] = reinterpret_cast<const float4*>(Dp + c * kRS); dsw[i] = c & 7;
-  }
+  for (int i = 0; i < TD; ++i) dcol[i] = reinterpret_cast<const float4*>(Dp + (t.x + min(i, t.y - 1)) * kRS);
 #pragma unroll
-  for (int j = 0; j < TX; ++j) {
-    const int c = t.z + min(j, t.w - 1);
-    xcol[j] = reinterpret_cast<const float4*>(Xp + c * kRS); xsw[j] = c & 7;
-  }
+  for (int j = 0; j < TX; ++j) xcol[j] = reinterpret_cast<const float4*>(Xp + (t.z + min(j, t.w - 1)) * kRS);
 #pragma unroll 2
   for (int q = 0; q < 8; ++q) {
     float4 dv[TD], xv[TX];
 #pragma unroll
-    for (int i = 0; i < TD; ++i) dv[i] = dcol[i][q ^ dsw[i]];
+    for (int i = 0; i < TD; ++i) dv[i] = dcol[i][q];
 #pragma unroll
-    for (int j = 0; j < TX; ++j) xv[j] = xcol[j][q ^ xsw[j]];
+    for (int j = 0; j < TX; ++j) xv[j] = xcol[j][q];
 #pragma unroll
     for (int i = 0; i < TD; ++i)
 #pragma unroll
       for (int j = 0; j < TX; ++j) {
-        acc[i][j] = fmaf(dv[i].x, xv[j].x, acc[i][j]);
-        acc[i][j] = fmaf(dv[i].y, xv[j].y, acc[i][j]);
-        acc[i][j] = fmaf(dv[i].z, xv[j].z, acc[i][j]);
-        acc[i][j] = fmaf(dv[i].w, xv[j].w, acc[i][j]);
+        acc[i][j] = ffma2(float2{dv[i].x, dv[i].y}, float2{xv[j].x, xv[j].y}, acc[i][j]);
+        acc[i][j] = ffma2(float2{dv[i].z, dv[i].w}, float2{xv[j].z, xv[j].w}, acc[i][j]);
       }
   }
 }
 template <int TD, int TX>
-__device__ __forceinline__ void wg_tile_flush(float (&acc)[TD][TX], const int* __restrict__ oidx,
+__device__ __forceinline__ void wg_tile_flush(float2 (&acc)[TD][TX], const int* __restrict__ oidx,
                                               float* __restrict__ G, int lane) {
   const int* oi = oidx + lane;
 #pragma unroll
   for (int i = 0; i < TD; ++i)
 #pragma unroll
     for (int j = 0; j < TX; ++j) {
-      G[oi[(i * TX + j) * 32]] += acc[i][j];
-      acc[i][j] = 0.f;
+      G[oi[(i * TX + j) * 32]] += acc[i][j].x + acc[i][j].y;
+      acc[i][j] = float2{0.f, 0.f};
     }
 }
 

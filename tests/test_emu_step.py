@@ -43,3 +43,18 @@ def test_lane_group_geometries_agree(lib, lanes, monkeypatch):
     for k, g_ref in fx['ref_grads_fp64'].items():
         if g_ref.norm() > 0:
             assert rel_err(grads[k] / n, g_ref) < 1e-3, (k, rel_err(grads[k] / n, g_ref))
+
+
+@pytest.mark.parametrize('chunks', ['2', '3'])
+def test_batch_chunked_step_agrees(lib, chunks, monkeypatch):
+    """bfvi_step_fwd_bwd splits the batch into chunks on side streams (BFVI_CHUNKS knob):
+    the chunked step must equal the whole-batch step."""
+    fx = load_golden('spirals_half_missing')
+    monkeypatch.setenv('BFVI_CHUNKS', chunks)
+    loss, grads, _ = helpers.run_step(lib, fx, 'cpu')
+    ref = fx['ref_loss_fp64']
+    assert abs(loss - ref) / abs(ref) < 1e-4, (loss, ref)
+    n = float(sum(fx['lengths']))
+    for k, g_ref in fx['ref_grads_fp64'].items():
+        if g_ref.norm() > 0:
+            assert rel_err(grads[k] / n, g_ref) < 1e-3, (k, rel_err(grads[k] / n, g_ref))
