@@ -325,8 +325,16 @@ def main():
         except Exception:
             pass
         hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+        traffic = None
+        try:       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full)
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel.json')))
+            if dom == 'filter_s_flt_bwd' and b_dim == B_PER_GPU:
+                traffic = prof['dram_bytes_read'] + prof['dram_bytes_write']
+        except Exception:
+            pass
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': bytes_alg / dur / 1e9, 'peak': hbm_peak,
-                    'unit': 'GB/s', 'frac': bytes_alg / dur / 1e9 / hbm_peak, 'traffic': None,
+                    'unit': 'GB/s', 'frac': bytes_alg / dur / 1e9 / hbm_peak, 'traffic': traffic,
+                    'algorithmic_bytes': bytes_alg,
                     'peak_source': 'measured' if peaks else 'fallback',
                     'note': 'kernel is FP32-FFMA bound (Z=5,H=20 cannot feed tcgen05); see roofline_fp32'}
         # FP32 FFMA peak measured live (register-only FMA chains on every SM)

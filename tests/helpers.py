@@ -50,7 +50,7 @@ def unpack(lib, model, modalities, dists, flat, like):
     return out
 
 
-def step_args(fx, device, noise=None, seed=0, kwargs=None):
+def step_args(fx, device, noise=None, seed=0, kwargs=None, b_offset=0):
     """Builds bfvi_step_args for a golden fixture; returns (args, keepalive)."""
     kw = dict(fx['step_kwargs'])
     kw.update(kwargs or {})
@@ -77,7 +77,7 @@ def step_args(fx, device, noise=None, seed=0, kwargs=None):
     a.train_particles = int(kw.get('train_particles', 25))
     a.match_particles = int(kw.get('match_particles', 50))
     a.sample, a.sample_init = int(kw.get('sample', True)), int(kw.get('sample_init', False))
-    a.seed, a.b_offset, a.match_count = seed, 0, -1.0
+    a.seed, a.b_offset, a.match_count = seed, b_offset, -1.0
     if noise is not None:
         for name, field in (('match', 'eps_match'), ('filt', 'eps_filt'), ('sflt', 'eps_sflt'),
                             ('ssmt', 'eps_ssmt')):
@@ -87,13 +87,14 @@ def step_args(fx, device, noise=None, seed=0, kwargs=None):
     return a, keep
 
 
-def run_step(lib, fx, device, with_grad=True, noise='fixture', seed=0, kwargs=None):
+def run_step(lib, fx, device, with_grad=True, noise='fixture', seed=0, kwargs=None, b_offset=0,
+             return_flat=False):
     """Calls bfvi_step_fwd_bwd; returns (loss float, {param: grad of the summed loss})."""
     model, dists = fixture_model(fx)
     mods = fx['modalities']
     flat, lay = pack_params(lib, model, mods, dists, fx['state_dict'], device)
     nz = fx['noise'] if noise == 'fixture' else noise
-    a, keep = step_args(fx, device, nz, seed, kwargs)
+    a, keep = step_args(fx, device, nz, seed, kwargs, b_offset)
     nbytes = C.c_size_t(0)
     lib.call('bfvi_step_workspace', C.byref(model), C.byref(a), C.byref(nbytes))
     ws = aligned_empty(nbytes.value, device)
@@ -107,5 +108,7 @@ def run_step(lib, fx, device, with_grad=True, noise='fixture', seed=0, kwargs=No
              _lib.ptr(ws), C.c_size_t(nbytes.value), _lib.ptr(loss), C.byref(launches), stream)
     if device != 'cpu':
         torch.cuda.synchronize()
+    if return_flat:
+        return loss.item(), grads, launches.value
     g = unpack(lib, model, mods, dists, grads, fx['state_dict']) if with_grad else None
     return loss.item(), g, launches.value
