@@ -262,6 +262,15 @@ int bfvi_step_profile(const bfvi_model* model, const float* params, float* grads
                       const bfvi_step_args* args, void* workspace, size_t workspace_bytes,
                       float* loss_out, float* phase_ms, void* stream);
 
+/* y = act(x W^T + b) on the tcgen05 tensor cores (TF32 operands, rounded to nearest
+ * while staged; FP32 accumulation in tensor memory): the dense layers of GaussianMLP /
+ * GaussianGTF at large batch (models/common.py:38-41, 62-68).  x (n_rows, n_in) row-major
+ * with leading dimension ldx; w (n_out, n_in) in nn.Linear layout, leading dimension ldw;
+ * bias (n_out) nullable; y (n_rows, n_out), leading dimension ldy.  act: 0 none, 1 ReLU. */
+int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
+                     float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out,
+                     int32_t act, void* stream);
+
 /* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
  * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream);

@@ -126,6 +126,8 @@ SYMBOLS = {
     'bfvi_step_profile': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(StepArgs),
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float),
                                     C.c_void_p]),
+    'bfvi_linear_tf32': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                   C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_dump_noise': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

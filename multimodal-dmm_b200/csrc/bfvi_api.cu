@@ -9,6 +9,7 @@
 #include <string>
 
 #include "bfvi_small.cuh"
+#include "bfvi_tc.cuh"
 
 namespace {
 
@@ -367,6 +368,22 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   pl->total = cur;
 }
 
+template <int BN>
+int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
+#ifdef BFVI_EMU
+  (void)st;
+  bfvi::tc::gemm_reference_emu(gp);
+#else
+  auto k = bfvi::tc::gemm_tf32_kernel<BN>;
+  const size_t smem = bfvi::tc::gemm_smem_bytes<BN>();
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN));
+  k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
+#endif
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
 // batch chunk [b0, b0 + bc) of the (T, B) problem; bc = 0 means the whole batch
 struct Chunk { int b0, bc; };
 
@@ -587,6 +604,22 @@ int bfvi_dump_noise(uint64_t seed, uint32_t stream_id, uint32_t b_offset, int32_
               (unsigned)stream_id, (unsigned)b_offset, (int)S, (int)T, (int)B, (int)K, (int)Z, out);
   BFVI_CHECK_CUDA();
   return BFVI_OK;
+}
+
+int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y,
+                     int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out, int32_t act, void* stream) {
+  if (!x || !w || !y || n_rows < 1 || n_in < 1 || n_out < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (ldx < n_in || ldw < n_in || ldy < n_out) return fail(BFVI_ERR_ARG, "leading dimension too small");
+  if (act != 0 && act != 1) return fail(BFVI_ERR_ARG, "unknown activation %d", act);
+  if ((n_rows + bfvi::tc::kBM - 1) / bfvi::tc::kBM > 0x7fffffff) return fail(BFVI_ERR_ARG, "too many rows");
+  bfvi::tc::GemmParams gp;
+  gp.A = x; gp.lda = ldx; gp.W = w; gp.ldw = ldw; gp.bias = bias; gp.C = y; gp.ldc = ldy;
+  gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_out <= 32) return launch_gemm_tf32<32>(gp, st);
+  if (n_out <= 64) return launch_gemm_tf32<64>(gp, st);
+  if (n_out <= 128) return launch_gemm_tf32<128>(gp, st);
+  return launch_gemm_tf32<256>(gp, st);
 }
 
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream) {

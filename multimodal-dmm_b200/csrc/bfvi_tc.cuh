@@ -1,0 +1,277 @@
+// bfvi_tc.cuh — tcgen05 (5th-generation tensor core) building blocks for the large-dim
+// kernel family: a TF32 GEMM tile kernel with a fused bias / activation epilogue,
+//
+//     C[M, N] = act( A[M, K] · W[N, K]^T + bias[N] ),
+//
+// which is exactly an nn.Linear (weights stay in PyTorch's (out, in) row-major layout,
+// i.e. the K-major B operand of the MMA — no transposition anywhere).  Dense
+// contractions of the BFVI step at large batch — GaussianMLP encoder / decoder layers
+// (models/common.py:38-41) and the six GaussianGTF layers evaluated for all particles of
+// a time step (models/common.py:62-68) — run through it.
+//
+// Precision: kind::tf32 with an FP32 accumulator in TMEM.  Operands are rounded to TF32
+// with round-to-nearest (cvt.rna) while they are staged into shared memory; letting the
+// MMA truncate raw FP32 bits would bias every product low by ~2^-11 and break the 1e-4
+// ELBO tolerance (rounded TF32 meets 1e-4 / 1e-3, plain BF16 does not).
+//
+// Data path of one CTA (128 threads, one 128 x BN output tile, cta_group::1):
+//   global --ld.global.v4--> registers --cvt.rna.tf32--> shared memory in the canonical
+//   K-major no-swizzle UMMA layout, double buffered over K chunks of 32 floats;
+//   one elected thread issues tcgen05.mma (M=128, N=BN, K=8 per instruction) and
+//   tcgen05.commit to an mbarrier per stage; the accumulator is read back with
+//   tcgen05.ld (32 lanes x 32 columns per warp) for the epilogue.
+//
+// Shared-memory operand layout: element (row r, float k) of a [ROWS x 32] chunk lives at
+// byte (k/4) * ROWS*16 + r*16 + (k%4)*4 — an array [k/4][r] of 16-byte vectors.  In UMMA
+// terms: 8-row x 16-byte core matrices, contiguous along rows (SBO = 128 B), K chunks
+// ROWS*16 B apart (LBO).  A warp storing 32 consecutive rows writes 512 contiguous bytes.
+#pragma once
+#include "bfvi_platform.cuh"
+
+namespace bfvi {
+namespace tc {
+
+constexpr int kBM = 128;          // rows per CTA tile (UMMA M)
+constexpr int kBK = 32;           // floats of K per shared-memory stage (4 MMA k-steps)
+constexpr int kThreads = 128;
+
+enum { ACT_NONE = 0, ACT_RELU = 1 };
+
+struct GemmParams {
+  const float* A; int64_t lda;      // [M, K] row-major
+  const float* W; int64_t ldw;      // [N, K] row-major (nn.Linear weight)
+  const float* bias;                // [N] or null
+  float* C; int64_t ldc;            // [M, N] row-major
+  int64_t M;
+  int N, K;
+  int act;
+};
+
+#ifndef BFVI_EMU
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bits:
+// start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout_type=0 [61,64))
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor for kind::tf32, FP32 accumulate, both operands K-major
+// (cute::UMMA::InstrDescriptor: c_format=F32 [4,6), a/b_format=TF32 [7,10)/[10,13),
+//  N>>3 [17,23), M>>4 [24,29))
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+__device__ __forceinline__ void umma_commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+      smem_u32(mbar)));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}\n" ::"r"(smem_u32(mbar)),
+      "r"(parity));
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {       // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {          // same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+// 32 lanes x 32 consecutive fp32 columns: thread (lane) gets its row's 32 values
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+        "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+        "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// one [ROWS x 32] K-chunk of a row-major matrix -> registers (zero outside the matrix)
+// thread t owns 16-byte vectors v = t, t + 128, ... of the chunk; vector v = (row v % ROWS, k4 v / ROWS)
+template <int ROWS>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t n_rows,
+                                           int k0, int K, bool vec_ok, float4 (&reg)[ROWS * 8 / kThreads]) {
+  constexpr int NV = ROWS * 8 / kThreads;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * kThreads;
+    const int r = v % ROWS, k = k0 + (v / ROWS) * 4;
+    const int64_t row = row0 + r;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < n_rows && k < K) {
+      const float* src = P + row * ld + k;
+      if (vec_ok && k + 3 < K) {
+        x = *reinterpret_cast<const float4*>(src);
+      } else {
+        x.x = src[0];
+        if (k + 1 < K) x.y = src[1];
+        if (k + 2 < K) x.z = src[2];
+        if (k + 3 < K) x.w = src[3];
+      }
+    }
+    reg[i] = x;
+  }
+}
+template <int ROWS>
+__device__ __forceinline__ void store_chunk(float* __restrict__ s, const float4 (&reg)[ROWS * 8 / kThreads]) {
+  constexpr int NV = ROWS * 8 / kThreads;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int v = threadIdx.x + i * kThreads;          // [k4][row] vector index == canonical layout
+    float4 x = reg[i];
+    x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
+    reinterpret_cast<float4*>(s)[v] = x;
+  }
+}
+
+// C tile = act(A W^T + bias); BN in {32, 64, 128, 256}
+template <int BN>
+__global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(128) unsigned char tc_smem_raw[];
+  float* sA[2];
+  float* sW[2];
+  sA[0] = reinterpret_cast<float*>(tc_smem_raw);
+  sA[1] = sA[0] + kBM * kBK;
+  sW[0] = sA[1] + kBM * kBK;
+  sW[1] = sW[0] + BN * kBK;
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kBM;
+  const int col0 = blockIdx.y * BN;
+  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, kCols);
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
+  const bool w_vec = (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
+  const int n_chunks = (p.K + kBK - 1) / kBK;
+  const uint32_t idesc = umma_idesc_tf32(kBM, BN);
+  float4 ra[kBM * 8 / kThreads], rw[BN * 8 / kThreads];
+
+  load_chunk<kBM>(p.A, p.lda, row0, p.M, 0, p.K, a_vec, ra);
+  load_chunk<BN>(p.W, p.ldw, col0, p.N, 0, p.K, w_vec, rw);
+  store_chunk<kBM>(sA[0], ra);
+  store_chunk<BN>(sW[0], rw);
+  fence_async_smem();
+  __syncthreads();
+
+  uint32_t phase[2] = {0u, 0u};
+  for (int i = 0; i < n_chunks; ++i) {
+    const int s = i & 1;
+    if (i + 1 < n_chunks) {                       // global loads of the next chunk fly during the MMAs
+      load_chunk<kBM>(p.A, p.lda, row0, p.M, (i + 1) * kBK, p.K, a_vec, ra);
+      load_chunk<BN>(p.W, p.ldw, col0, p.N, (i + 1) * kBK, p.K, w_vec, rw);
+    }
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sA[s]), w0 = smem_u32(sW[s]);
+#pragma unroll
+      for (int j = 0; j < kBK / 8; ++j) {         // one MMA consumes K = 8 floats = two 16-byte K vectors
+        const uint64_t da = umma_desc(a0 + j * 2 * kBM * 16, kBM * 16, 128);
+        const uint64_t dw = umma_desc(w0 + j * 2 * BN * 16, BN * 16, 128);
+        umma_tf32(tmem_d, da, dw, idesc, (i > 0 || j > 0) ? 1u : 0u);
+      }
+      umma_commit(&mbar[s]);                      // arrives when these MMAs have read their operands
+    }
+    if (i + 1 < n_chunks) {
+      if (i >= 1) { mbar_wait(&mbar[s ^ 1], phase[s ^ 1]); phase[s ^ 1] ^= 1u; }   // chunk i-1 done with its stage
+      store_chunk<kBM>(sA[s ^ 1], ra);
+      store_chunk<BN>(sW[s ^ 1], rw);
+      fence_async_smem();
+      __syncthreads();
+    }
+  }
+  // drain: the last one or two commits
+  if (n_chunks >= 2) { const int s = (n_chunks - 2) & 1; mbar_wait(&mbar[s], phase[s]); phase[s] ^= 1u; }
+  { const int s = (n_chunks - 1) & 1; mbar_wait(&mbar[s], phase[s]); phase[s] ^= 1u; }
+  tc_fence_after();
+
+  // epilogue: warp w owns accumulator rows (TMEM lanes) 32w .. 32w+31
+  const int64_t row = row0 + warp * 32 + lane;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 32) {
+    float v[32];
+    tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
+    if (row < p.M) {
+      float* dst = p.C + row * p.ldc + col0 + c;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + c + j;
+        if (col < p.N) {
+          float x = v[j] + (p.bias != nullptr ? p.bias[col] : 0.f);
+          if (p.act == ACT_RELU) x = x < 0.f ? 0.f : x;
+          dst[j] = x;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, kCols);
+}
+#endif  // !BFVI_EMU
+
+// CPU stand-in used only by the SIMT-emulator test build (exact fp32, no TF32 rounding)
+#ifdef BFVI_EMU
+inline void gemm_reference_emu(const GemmParams& p) {
+  for (int64_t m = 0; m < p.M; ++m)
+    for (int n = 0; n < p.N; ++n) {
+      float acc = p.bias ? p.bias[n] : 0.f;
+      for (int k = 0; k < p.K; ++k) acc = fmaf(p.A[m * p.lda + k], p.W[(int64_t)n * p.ldw + k], acc);
+      if (p.act == ACT_RELU) acc = acc < 0.f ? 0.f : acc;
+      p.C[m * p.ldc + n] = acc;
+    }
+}
+#endif
+
+template <int BN>
+inline size_t gemm_smem_bytes() { return sizeof(float) * 2 * (size_t)(kBM + BN) * kBK; }
+
+}  // namespace tc
+}  // namespace bfvi

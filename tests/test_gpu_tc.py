@@ -1,0 +1,63 @@
+"""tcgen05 TF32 linear layer (bfvi_linear_tf32) against a float64 reference on the
+TF32-rounded operands (tight) and against plain fp32 torch (TF32 tolerance)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from multimodal_dmm_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def round_tf32(x):
+    """Round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32."""
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x1000) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def run(lib, x, w, b, act, ldx=None, ldy=None):
+    n_rows, n_in = x.shape
+    n_out = w.shape[0]
+    ldx = ldx or n_in
+    ldy = ldy or n_out
+    xs = torch.zeros(n_rows, ldx, device='cuda')
+    xs[:, :n_in] = x
+    y = torch.full((n_rows, ldy), float('nan'), device='cuda')
+    lib.call('bfvi_linear_tf32', _lib.ptr(xs), ldx, _lib.ptr(w), w.stride(0), _lib.ptr(b), _lib.ptr(y), ldy,
+             n_rows, n_in, n_out, act, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize('shape', [(128, 64, 64), (300, 16, 512), (1000, 512, 64), (257, 20, 40),
+                                   (5000, 256, 256), (33, 7, 3), (4096, 64, 512), (129, 512, 16)])
+@pytest.mark.parametrize('act', [0, 1])
+def test_linear_tf32_matches_reference(shape, act):
+    lib = _lib.load()
+    m, k, n = shape
+    g = torch.Generator(device='cuda').manual_seed(m * 31 + k * 7 + n)
+    x = torch.randn(m, k, device='cuda', generator=g)
+    w = torch.randn(n, k, device='cuda', generator=g) / k ** 0.5
+    b = torch.randn(n, device='cuda', generator=g)
+    pad = 4 if k % 4 else 0
+    y = run(lib, x, w, b, act, ldx=k + pad, ldy=n + 3)
+    assert torch.isnan(y[:, n:]).all()                       # nothing written outside (n_rows, n_out)
+    y = y[:, :n]
+    ref = round_tf32(x).double() @ round_tf32(w).double().t() + b.double()
+    ref32 = x @ w.t() + b
+    if act:
+        ref, ref32 = ref.clamp_min(0), ref32.clamp_min(0)
+    scale = ref.abs().max().item()
+    assert (y.double() - ref).abs().max().item() < 2e-5 * scale, (y.double() - ref).abs().max().item()
+    assert (y - ref32).abs().max().item() < 5e-3 * scale
+
+
+def test_linear_tf32_argument_errors():
+    lib = _lib.load()
+    x = torch.zeros(4, 4, device='cuda')
+    with pytest.raises(_lib.BfviError):
+        lib.call('bfvi_linear_tf32', _lib.ptr(x), 2, _lib.ptr(x), 4, None, _lib.ptr(x), 4, 4, 4, 4, 0, None)
+    with pytest.raises(_lib.BfviError):
+        lib.call('bfvi_linear_tf32', _lib.ptr(x), 4, _lib.ptr(x), 4, None, _lib.ptr(x), 4, 4, 4, 4, 7, None)
