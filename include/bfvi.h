@@ -180,8 +180,10 @@ const char* bfvi_last_error(void);
 /* Flat parameter layout for a model (all-default MLP encoders/decoders). */
 int bfvi_param_layout(const bfvi_model* model, bfvi_layout* out);
 
-/* Which kernel family serves this model: 1 = register-resident small-dim path,
- * 2 = generic path, 0 = unsupported. */
+/* Which kernel family serves this model: 1 = register-resident small-dim family (every
+ * entry point, training included), 2 = tcgen05 large-dim family (bfvi_forward only this
+ * release: inference / evaluation; training entry points return BFVI_ERR_UNSUPPORTED),
+ * 0 = invalid model. */
 int bfvi_kernel_family(const bfvi_model* model);
 
 /* MultiDMM.encode for one default Gaussian-MLP encoder (models/dmm.py:165-173 +
@@ -262,11 +264,40 @@ int bfvi_step_profile(const bfvi_model* model, const float* params, float* grads
                       const bfvi_step_args* args, void* workspace, size_t workspace_bytes,
                       float* loss_out, float* phase_ms, void* stream);
 
+/* MultiDMM.forward (models/dmm.py:420-494) for an all-default Gaussian model of ANY
+ * (z_dim, h_dim): encode -> filtering pass -> (smoothing pass) -> decode, the inference /
+ * evaluation path of Trainer.evaluate (trainer.py:294-296).  This is the entry point of
+ * the large-dim kernel family: every Linear layer is a tcgen05 GEMM over all rows
+ * (sequences x particles) of a time step, the per-component math between them runs in
+ * fused elementwise kernels, the time loop is a stream-ordered launch sequence. */
+typedef struct bfvi_forward_args {
+  int32_t T, B;
+  const float* inputs[BFVI_MAX_MODS];  /* (T,B,D_m), NaN = missing; NULL = modality not given */
+  int32_t mode;                        /* BFVI_MODE_* */
+  int32_t sample, sample_init;
+  int32_t flt_particles, smt_particles;
+  const float* eps_flt;                /* (T,B,flt_particles,Z) injected noise or NULL (Philox) */
+  const float* eps_smt;                /* (T,B,smt_particles,Z) */
+  uint64_t seed;
+  uint32_t b_offset;
+  int32_t precision;                   /* 0 = error-compensated 3xTF32 (default), 1 = TF32 */
+  float* infer_mean; float* infer_std; /* outputs (T,B,Z) */
+  float* prior_mean; float* prior_std;
+  float* recon_mean[BFVI_MAX_MODS];    /* outputs (T,B,D_m), nullable per modality */
+  float* recon_std[BFVI_MAX_MODS];
+} bfvi_forward_args;
+
+int bfvi_forward_workspace(const bfvi_model* model, const bfvi_forward_args* args, size_t* bytes);
+int bfvi_forward(const bfvi_model* model, const float* params, const bfvi_forward_args* args,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
 /* y = act(x W^T + b) on the tcgen05 tensor cores (TF32 operands, rounded to nearest
  * while staged; FP32 accumulation in tensor memory): the dense layers of GaussianMLP /
  * GaussianGTF at large batch (models/common.py:38-41, 62-68).  x (n_rows, n_in) row-major
  * with leading dimension ldx; w (n_out, n_in) in nn.Linear layout, leading dimension ldw;
- * bias (n_out) nullable; y (n_rows, n_out), leading dimension ldy.  act: 0 none, 1 ReLU. */
+ * bias (n_out) nullable; y (n_rows, n_out), leading dimension ldy.  act: 0 none, 1 ReLU;
+ * | 16 selects single-pass TF32 instead of the default error-compensated 3xTF32
+ * (a_hi w_hi + a_lo w_hi + a_hi w_lo in one accumulator: FP32-class accuracy). */
 int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias,
                      float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out,
                      int32_t act, void* stream);

@@ -90,6 +90,18 @@ class StepArgs(C.Structure):
                 ('seed', C.c_uint64), ('b_offset', C.c_uint32), ('match_count', C.c_float)]
 
 
+class ForwardArgs(C.Structure):
+    _fields_ = [('T', C.c_int32), ('B', C.c_int32),
+                ('inputs', C.c_void_p * MAX_MODS),
+                ('mode', C.c_int32), ('sample', C.c_int32), ('sample_init', C.c_int32),
+                ('flt_particles', C.c_int32), ('smt_particles', C.c_int32),
+                ('eps_flt', C.c_void_p), ('eps_smt', C.c_void_p),
+                ('seed', C.c_uint64), ('b_offset', C.c_uint32), ('precision', C.c_int32),
+                ('infer_mean', C.c_void_p), ('infer_std', C.c_void_p),
+                ('prior_mean', C.c_void_p), ('prior_std', C.c_void_p),
+                ('recon_mean', C.c_void_p * MAX_MODS), ('recon_std', C.c_void_p * MAX_MODS)]
+
+
 class BfviError(RuntimeError):
     pass
 
@@ -126,6 +138,9 @@ SYMBOLS = {
     'bfvi_step_profile': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(StepArgs),
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float),
                                     C.c_void_p]),
+    'bfvi_forward_workspace': (C.c_int, [C.POINTER(Model), C.POINTER(ForwardArgs), C.POINTER(C.c_size_t)]),
+    'bfvi_forward': (C.c_int, [C.POINTER(Model), C.c_void_p, C.POINTER(ForwardArgs), C.c_void_p, C.c_size_t,
+                               C.c_void_p]),
     'bfvi_linear_tf32': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                    C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

@@ -10,6 +10,7 @@
 
 #include "bfvi_small.cuh"
 #include "bfvi_tc.cuh"
+#include "bfvi_generic.cuh"
 
 namespace {
 
@@ -368,20 +369,38 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   pl->total = cur;
 }
 
-template <int BN>
+template <int BN, bool SPLIT>
 int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
 #ifdef BFVI_EMU
   (void)st;
   bfvi::tc::gemm_reference_emu(gp);
 #else
-  auto k = bfvi::tc::gemm_tf32_kernel<BN>;
-  const size_t smem = bfvi::tc::gemm_smem_bytes<BN>();
+  auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
+  const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN));
   k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
 #endif
   BFVI_CHECK_CUDA();
   return BFVI_OK;
+}
+
+// y = act(x W^T + b) on tcgen05; prec: PREC_TF32X3 (error-compensated) or PREC_TF32
+int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy,
+              int64_t n_rows, int n_in, int n_out, int act, int prec, cudaStream_t st) {
+  bfvi::tc::GemmParams gp;
+  gp.A = x; gp.lda = ldx; gp.W = w; gp.ldw = ldw; gp.bias = bias; gp.C = y; gp.ldc = ldy;
+  gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
+  if (prec == bfvi::tc::PREC_TF32) {
+    if (n_out <= 32) return launch_gemm_tf32<32, false>(gp, st);
+    if (n_out <= 64) return launch_gemm_tf32<64, false>(gp, st);
+    if (n_out <= 128) return launch_gemm_tf32<128, false>(gp, st);
+    return launch_gemm_tf32<256, false>(gp, st);
+  }
+  if (n_out <= 32) return launch_gemm_tf32<32, true>(gp, st);
+  if (n_out <= 64) return launch_gemm_tf32<64, true>(gp, st);
+  if (n_out <= 128) return launch_gemm_tf32<128, true>(gp, st);
+  return launch_gemm_tf32<256, true>(gp, st);
 }
 
 // batch chunk [b0, b0 + bc) of the (T, B) problem; bc = 0 means the whole batch
@@ -437,7 +456,7 @@ int bfvi_param_layout(const bfvi_model* m, bfvi_layout* out) {
 
 int bfvi_kernel_family(const bfvi_model* m) {
   if (check_model(m)) return 0;
-  return small_supported(m->z_dim, m->h_dim) ? 1 : 0;
+  return small_supported(m->z_dim, m->h_dim) ? 1 : 2;
 }
 
 int bfvi_encode_fwd(const bfvi_model* m, const float* params, int32_t mod, const float* x,
@@ -610,16 +629,9 @@ int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, c
                      int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out, int32_t act, void* stream) {
   if (!x || !w || !y || n_rows < 1 || n_in < 1 || n_out < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
   if (ldx < n_in || ldw < n_in || ldy < n_out) return fail(BFVI_ERR_ARG, "leading dimension too small");
-  if (act != 0 && act != 1) return fail(BFVI_ERR_ARG, "unknown activation %d", act);
+  if ((act & ~0x11) != 0) return fail(BFVI_ERR_ARG, "unknown activation / precision flags %d", act);
   if ((n_rows + bfvi::tc::kBM - 1) / bfvi::tc::kBM > 0x7fffffff) return fail(BFVI_ERR_ARG, "too many rows");
-  bfvi::tc::GemmParams gp;
-  gp.A = x; gp.lda = ldx; gp.W = w; gp.ldw = ldw; gp.bias = bias; gp.C = y; gp.ldc = ldy;
-  gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (n_out <= 32) return launch_gemm_tf32<32>(gp, st);
-  if (n_out <= 64) return launch_gemm_tf32<64>(gp, st);
-  if (n_out <= 128) return launch_gemm_tf32<128>(gp, st);
-  return launch_gemm_tf32<256>(gp, st);
+  return linear_tc(x, ldx, w, ldw, bias, y, ldy, n_rows, n_in, n_out, act & 1, (act >> 4) & 1, (cudaStream_t)stream);
 }
 
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream) {
@@ -968,6 +980,205 @@ int bfvi_step_profile(const bfvi_model* m, const float* params, float* grads, co
   }
   for (int i = 0; i <= BFVI_N_PHASES; ++i) cudaEventDestroy(pm.ev[i]);
   return rc;
+}
+
+// ---------------------------------------------------------------------------
+// large-dim family: MultiDMM.forward as a launch sequence of tcgen05 GEMMs and fused
+// elementwise kernels
+// ---------------------------------------------------------------------------
+struct ForwardPlan {
+  int n_present, k_max, d_max;
+  size_t tb, tbz;
+  size_t off_obs_mean, off_obs_std, off_obs_mask, off_x0, off_h, off_flt[4], off_samples;
+  size_t off_zrows, off_hrows, off_g, off_nl, off_lin, off_as;
+  size_t total;
+};
+
+static int plan_forward(const bfvi_model* m, const bfvi_forward_args* a, ForwardPlan* pl) {
+  if (int rc = check_model(m)) return rc;
+  if (a == nullptr) return fail(BFVI_ERR_ARG, "forward args null");
+  if (a->T < 1 || a->B < 1) return fail(BFVI_ERR_ARG, "bad T/B");
+  if (a->mode < BFVI_MODE_BFILTER || a->mode > BFVI_MODE_BSMOOTH) return fail(BFVI_ERR_ARG, "bad mode");
+  if (a->flt_particles < 1 || a->smt_particles < 1) return fail(BFVI_ERR_ARG, "particle counts must be >= 1");
+  if (a->precision != 0 && a->precision != 1) return fail(BFVI_ERR_ARG, "bad precision");
+  for (int i = 0; i < m->n_mods; ++i)
+    if (m->dists[i] != BFVI_DIST_NORMAL)
+      return fail(BFVI_ERR_UNSUPPORTED, "bfvi_forward covers Normal modalities; compose the ops for others");
+  pl->n_present = 0; pl->d_max = 1;
+  for (int i = 0; i < m->n_mods; ++i) {
+    if (a->inputs[i]) ++pl->n_present;
+    if (m->dims[i] > pl->d_max) pl->d_max = m->dims[i];
+  }
+  if (pl->n_present == 0) return fail(BFVI_ERR_ARG, "at least one modality must be given");
+  pl->k_max = a->flt_particles > a->smt_particles ? a->flt_particles : a->smt_particles;
+  pl->tb = (size_t)a->T * a->B;
+  pl->tbz = pl->tb * m->z_dim;
+  const size_t rows = (size_t)a->B * pl->k_max;
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  pl->off_obs_mean = carve(sizeof(float) * pl->tbz * pl->n_present);
+  pl->off_obs_std = carve(sizeof(float) * pl->tbz * pl->n_present);
+  pl->off_obs_mask = carve(pl->tb * pl->n_present);
+  pl->off_x0 = carve(sizeof(float) * pl->tb * pl->d_max);
+  pl->off_h = carve(sizeof(float) * pl->tb * m->h_dim);
+  for (int i = 0; i < 4; ++i) pl->off_flt[i] = carve(sizeof(float) * pl->tbz);
+  pl->off_samples = carve(sizeof(float) * pl->tbz);
+  pl->off_zrows = carve(sizeof(float) * rows * m->z_dim);
+  pl->off_hrows = carve(sizeof(float) * rows * m->h_dim);
+  pl->off_g = carve(sizeof(float) * rows * m->z_dim);
+  pl->off_nl = carve(sizeof(float) * rows * m->z_dim);
+  pl->off_lin = carve(sizeof(float) * rows * m->z_dim);
+  pl->off_as = carve(sizeof(float) * rows * m->z_dim);
+  pl->total = cur;
+  return BFVI_OK;
+}
+
+int bfvi_forward_workspace(const bfvi_model* m, const bfvi_forward_args* a, size_t* bytes) {
+  ForwardPlan pl;
+  if (int rc = plan_forward(m, a, &pl)) return rc;
+  if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
+  *bytes = pl.total;
+  return BFVI_OK;
+}
+
+int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_args* a, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  ForwardPlan pl;
+  if (int rc = plan_forward(m, a, &pl)) return rc;
+  if (!params || !workspace) return fail(BFVI_ERR_ARG, "null argument");
+  if (!a->infer_mean || !a->infer_std || !a->prior_mean || !a->prior_std) return fail(BFVI_ERR_ARG, "outputs null");
+  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, T = a->T, B = a->B, prec = a->precision;
+  const int64_t tb = (int64_t)pl.tb;
+  float* obs_mean = (float*)(ws + pl.off_obs_mean);
+  float* obs_std = (float*)(ws + pl.off_obs_std);
+  uint8_t* obs_mask = (uint8_t*)(ws + pl.off_obs_mask);
+  float* x0 = (float*)(ws + pl.off_x0);
+  float* hbuf = (float*)(ws + pl.off_h);
+  float* samples = (float*)(ws + pl.off_samples);
+  float* zrows = (float*)(ws + pl.off_zrows);
+  float* hrows = (float*)(ws + pl.off_hrows);
+  float* gbuf = (float*)(ws + pl.off_g);
+  float* nlbuf = (float*)(ws + pl.off_nl);
+  float* linbuf = (float*)(ws + pl.off_lin);
+  float* asbuf = (float*)(ws + pl.off_as);
+  auto ew_grid = [&](int64_t n, int per) { return dim3((unsigned)grid_for(n, per, 16)); };
+
+  // ---- encode every given modality (models/dmm.py:160-173) ------------------------------
+  int slot = 0;
+  for (int i = 0; i < M; ++i) {
+    if (!a->inputs[i]) continue;
+    const bfvi_mlp_layout& l = lay.enc[i];
+    const int D = m->dims[i];
+    float* mean = obs_mean + (size_t)slot * pl.tbz;
+    float* std = obs_std + (size_t)slot * pl.tbz;
+    auto kp = bfvi::gen::prep_rows_kernel;
+    BFVI_LAUNCH(kp, ew_grid(tb, 256), dim3(256), 0, st, a->inputs[i], tb, D, x0, obs_mask + (size_t)slot * pl.tb);
+    if (int rc = linear_tc(x0, D, params + l.in_to_h_w, D, params + l.in_to_h_b, hbuf, H, tb, D, H, 1, prec, st)) return rc;
+    if (int rc = linear_tc(hbuf, H, params + l.mean_w, H, params + l.mean_b, mean, Z, tb, H, Z, 0, prec, st)) return rc;
+    if (int rc = linear_tc(hbuf, H, params + l.std_w, H, params + l.std_b, std, Z, tb, H, Z, 0, prec, st)) return rc;
+    auto ks = bfvi::gen::softplus_kernel;
+    BFVI_LAUNCH(ks, ew_grid(tb * Z, 256), dim3(256), 0, st, std, tb * Z, bfvi::kMlpMinStd);
+    ++slot;
+  }
+  BFVI_CHECK_CUDA();
+
+  // ---- one filtering pass: T steps, each = 6 GEMMs over (B*K) rows + one fused kernel ----
+  auto run_pass = [&](bfvi_filter_args& f) -> int {
+    const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
+    const int64_t rows = (int64_t)B * f.n_particles;
+    for (int i = 0; i < T; ++i) {
+      if (i > 0) {
+        if (int rc = linear_tc(zrows, Z, params + g.gate0_w, Z, params + g.gate0_b, hrows, H, rows, Z, H, 1, prec, st)) return rc;
+        if (int rc = linear_tc(hrows, H, params + g.gate2_w, H, params + g.gate2_b, gbuf, Z, rows, H, Z, 0, prec, st)) return rc;
+        if (int rc = linear_tc(zrows, Z, params + g.nonlin0_w, Z, params + g.nonlin0_b, hrows, H, rows, Z, H, 1, prec, st)) return rc;
+        if (int rc = linear_tc(hrows, H, params + g.nonlin2_w, H, params + g.nonlin2_b, nlbuf, Z, rows, H, Z, 0, prec, st)) return rc;
+        if (int rc = linear_tc(zrows, Z, params + g.lin_w, Z, params + g.lin_b, linbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
+        if (int rc = linear_tc(nlbuf, Z, params + g.std_w, Z, params + g.std_b, asbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
+      }
+      bfvi::gen::StepParams sp;
+      sp.a = f;
+      sp.z0_mean = params + lay.z0_mean; sp.z0_log_std = params + lay.z0_log_std;
+      sp.min_std = m->min_std; sp.Z = Z; sp.i = i;
+      sp.g = gbuf; sp.nl = nlbuf; sp.lin = linbuf; sp.as = asbuf;
+      sp.zrows = zrows;
+      auto k = bfvi::gen::step_kernel;
+      BFVI_LAUNCH(k, ew_grid((int64_t)B * Z, 128), dim3(128), 0, st, sp);
+    }
+    BFVI_CHECK_CUDA();
+    return BFVI_OK;
+  };
+  auto obs_experts = [&](bfvi_filter_args& f) {
+    memset(&f, 0, sizeof(f));
+    f.T = T; f.B = B; f.S = 1;
+    for (int e = 0; e < pl.n_present; ++e) {
+      bfvi_expert& ex = f.experts[e];
+      ex.mean = obs_mean + (size_t)e * pl.tbz; ex.std = obs_std + (size_t)e * pl.tbz;
+      ex.mask = obs_mask + (size_t)e * pl.tb;
+      ex.stride_t = (int64_t)B * Z; ex.stride_b = Z; ex.mstride_t = B; ex.mstride_b = 1;
+      ex.kind = BFVI_EXPERT_TENSOR;
+    }
+    f.n_experts = pl.n_present;
+    f.sample = a->sample;
+    f.noise.seed = a->seed; f.noise.b_offset = a->b_offset;
+  };
+  const bool smooth = a->mode == BFVI_MODE_FSMOOTH || a->mode == BFVI_MODE_BSMOOTH;
+  // filtering pass (models/dmm.py:462-470): forward for ffilter / bsmooth, backward otherwise
+  bfvi_filter_args f1;
+  obs_experts(f1);
+  f1.set_expert_bits[0] = (1u << pl.n_present) - 1u;
+  f1.direction = (a->mode == BFVI_MODE_FFILTER || a->mode == BFVI_MODE_BSMOOTH) ? BFVI_DIR_FWD : BFVI_DIR_BWD;
+  f1.n_particles = a->flt_particles;
+  f1.sample_init = smooth ? 0 : a->sample_init;
+  f1.noise.eps = a->eps_flt; f1.noise.stream_id = 7;
+  if (smooth) {
+    f1.infer_mean = (float*)(ws + pl.off_flt[0]); f1.infer_std = (float*)(ws + pl.off_flt[1]);
+    f1.prior_mean = (float*)(ws + pl.off_flt[2]); f1.prior_std = (float*)(ws + pl.off_flt[3]);
+  } else {
+    f1.infer_mean = a->infer_mean; f1.infer_std = a->infer_std;
+    f1.prior_mean = a->prior_mean; f1.prior_std = a->prior_std;
+  }
+  f1.samples = samples;
+  if (int rc = run_pass(f1)) return rc;
+  if (smooth) {                                   // smoothing pass (models/dmm.py:473-489)
+    bfvi_filter_args f2;
+    obs_experts(f2);
+    const int P = pl.n_present;
+    bfvi_expert& fe = f2.experts[P];
+    fe.mean = f1.prior_mean; fe.std = f1.prior_std; fe.mask = nullptr;
+    fe.stride_t = (int64_t)B * Z; fe.stride_b = Z;
+    fe.kind = BFVI_EXPERT_TENSOR; fe.zero_mask_last_t = 1;          // flt_mask[-1] = 0
+    f2.experts[P + 1].kind = BFVI_EXPERT_INV_PRIOR;
+    f2.n_experts = P + 2;
+    f2.set_expert_bits[0] = (1u << (P + 2)) - 1u;
+    f2.direction = a->mode == BFVI_MODE_FSMOOTH ? BFVI_DIR_FWD : BFVI_DIR_BWD;
+    f2.n_particles = a->smt_particles;
+    f2.sample_init = a->sample_init;
+    f2.noise.eps = a->eps_smt; f2.noise.stream_id = 8;
+    f2.infer_mean = a->infer_mean; f2.infer_std = a->infer_std;
+    f2.prior_mean = a->prior_mean; f2.prior_std = a->prior_std;
+    f2.samples = samples;
+    if (int rc = run_pass(f2)) return rc;
+  }
+
+  // ---- decode every modality from the pass's samples (models/dmm.py:192-212) -------------
+  for (int i = 0; i < M; ++i) {
+    if (!a->recon_mean[i] || !a->recon_std[i]) continue;
+    const bfvi_mlp_layout& l = lay.dec[i];
+    const int D = m->dims[i];
+    if (int rc = linear_tc(samples, Z, params + l.in_to_h_w, Z, params + l.in_to_h_b, hbuf, H, tb, Z, H, 1, prec, st)) return rc;
+    if (int rc = linear_tc(hbuf, H, params + l.mean_w, H, params + l.mean_b, a->recon_mean[i], D, tb, H, D, 0, prec, st)) return rc;
+    if (int rc = linear_tc(hbuf, H, params + l.std_w, H, params + l.std_b, a->recon_std[i], D, tb, H, D, 0, prec, st)) return rc;
+    auto ks = bfvi::gen::softplus_kernel;
+    BFVI_LAUNCH(ks, ew_grid(tb * D, 256), dim3(256), 0, st, a->recon_std[i], tb * D, bfvi::kMlpMinStd);
+  }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
 }
 
 }  // extern "C"

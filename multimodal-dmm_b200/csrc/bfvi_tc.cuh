@@ -46,6 +46,7 @@ struct GemmParams {
   int N, K;
   int act;
 };
+enum { PREC_TF32X3 = 0, PREC_TF32 = 1 };   // operand precision of the large-dim family
 
 #ifndef BFVI_EMU
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -147,28 +148,47 @@ __device__ __forceinline__ void load_chunk(const float* __restrict__ P, int64_t 
     reg[i] = x;
   }
 }
+// registers -> shared memory; `lo` (nullable) receives the TF32-rounded residual x - hi
+// for the error-compensated 3xTF32 product
 template <int ROWS>
-__device__ __forceinline__ void store_chunk(float* __restrict__ s, const float4 (&reg)[ROWS * 8 / kThreads]) {
+__device__ __forceinline__ void store_chunk(float* __restrict__ hi, float* __restrict__ lo,
+                                            const float4 (&reg)[ROWS * 8 / kThreads]) {
   constexpr int NV = ROWS * 8 / kThreads;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = threadIdx.x + i * kThreads;          // [k4][row] vector index == canonical layout
-    float4 x = reg[i];
-    x.x = to_tf32(x.x); x.y = to_tf32(x.y); x.z = to_tf32(x.z); x.w = to_tf32(x.w);
-    reinterpret_cast<float4*>(s)[v] = x;
+    const float4 x = reg[i];
+    float4 h;
+    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    reinterpret_cast<float4*>(hi)[v] = h;
+    if (lo != nullptr) {
+      float4 l;
+      l.x = to_tf32(x.x - h.x); l.y = to_tf32(x.y - h.y); l.z = to_tf32(x.z - h.z); l.w = to_tf32(x.w - h.w);
+      reinterpret_cast<float4*>(lo)[v] = l;
+    }
   }
 }
 
-// C tile = act(A W^T + bias); BN in {32, 64, 128, 256}
-template <int BN>
+// C tile = act(A W^T + bias); BN in {32, 64, 128, 256}.  SPLIT: error-compensated 3xTF32
+// (A_hi W_hi + A_lo W_hi + A_hi W_lo, all into the same TMEM accumulator): FP32-class
+// accuracy at three MMAs per k-step, for the parity mode of the large-dim family.
+template <int BN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(128) unsigned char tc_smem_raw[];
   float* sA[2];
   float* sW[2];
+  float* sAl[2] = {nullptr, nullptr};
+  float* sWl[2] = {nullptr, nullptr};
   sA[0] = reinterpret_cast<float*>(tc_smem_raw);
   sA[1] = sA[0] + kBM * kBK;
   sW[0] = sA[1] + kBM * kBK;
   sW[1] = sW[0] + BN * kBK;
+  if (SPLIT) {
+    sAl[0] = sW[1] + BN * kBK;
+    sAl[1] = sAl[0] + kBM * kBK;
+    sWl[0] = sAl[1] + kBM * kBK;
+    sWl[1] = sWl[0] + BN * kBK;
+  }
   __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
 
@@ -196,8 +216,8 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 
   load_chunk<kBM>(p.A, p.lda, row0, p.M, 0, p.K, a_vec, ra);
   load_chunk<BN>(p.W, p.ldw, col0, p.N, 0, p.K, w_vec, rw);
-  store_chunk<kBM>(sA[0], ra);
-  store_chunk<BN>(sW[0], rw);
+  store_chunk<kBM>(sA[0], sAl[0], ra);
+  store_chunk<BN>(sW[0], sWl[0], rw);
   fence_async_smem();
   __syncthreads();
 
@@ -216,13 +236,19 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
         const uint64_t da = umma_desc(a0 + j * 2 * kBM * 16, kBM * 16, 128);
         const uint64_t dw = umma_desc(w0 + j * 2 * BN * 16, BN * 16, 128);
         umma_tf32(tmem_d, da, dw, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        if (SPLIT) {
+          const uint64_t dal = umma_desc(smem_u32(sAl[s]) + j * 2 * kBM * 16, kBM * 16, 128);
+          const uint64_t dwl = umma_desc(smem_u32(sWl[s]) + j * 2 * BN * 16, BN * 16, 128);
+          umma_tf32(tmem_d, dal, dw, idesc, 1u);
+          umma_tf32(tmem_d, da, dwl, idesc, 1u);
+        }
       }
       umma_commit(&mbar[s]);                      // arrives when these MMAs have read their operands
     }
     if (i + 1 < n_chunks) {
       if (i >= 1) { mbar_wait(&mbar[s ^ 1], phase[s ^ 1]); phase[s ^ 1] ^= 1u; }   // chunk i-1 done with its stage
-      store_chunk<kBM>(sA[s ^ 1], ra);
-      store_chunk<BN>(sW[s ^ 1], rw);
+      store_chunk<kBM>(sA[s ^ 1], sAl[s ^ 1], ra);
+      store_chunk<BN>(sW[s ^ 1], sWl[s ^ 1], rw);
       fence_async_smem();
       __syncthreads();
     }
@@ -270,8 +296,8 @@ inline void gemm_reference_emu(const GemmParams& p) {
 }
 #endif
 
-template <int BN>
-inline size_t gemm_smem_bytes() { return sizeof(float) * 2 * (size_t)(kBM + BN) * kBK; }
+template <int BN, bool SPLIT>
+inline size_t gemm_smem_bytes() { return sizeof(float) * (SPLIT ? 4 : 2) * (size_t)(kBM + BN) * kBK; }
 
 }  // namespace tc
 }  // namespace bfvi

@@ -419,7 +419,8 @@ class MultiDMM(MultiDGTS):
         N(0,1) draws as a (T, B, K, Z) tensor; default is the in-kernel generator."""
         self._ensure_flat()
         if self._family != 1:
-            raise _lib.BfviError('no filter kernel for z_dim=%d h_dim=%d yet' % (self.z_dim, self.h_dim))
+            raise _lib.BfviError('z_filter as a stand-alone op exists for the small-dim family only '
+                                 '(z_dim=%d h_dim=%d is served by forward())' % (self.z_dim, self.h_dim))
         cfg = dict(direction=direction, sample=sample, n_particles=n_particles,
                    sample_init=sample_init, seed=self._next_seed())
         if eps is not None:
@@ -447,6 +448,9 @@ class MultiDMM(MultiDGTS):
         smt_particles = kwargs.get('smt_particles', 1)
         eps_flt, eps_smt = kwargs.get('noise', (None, None))
         t_max, b_dim = max(lengths), len(lengths)
+        if self._family == 2:
+            return self._forward_large(inputs, t_max, b_dim, mode, sample, sample_init, flt_particles,
+                                       smt_particles, eps_flt, eps_smt, kwargs.get('precision', 'tf32x3'))
 
         obs_mean, obs_std, obs_mask = self.encode(inputs)
         direction = 'fwd' if mode in ('ffilter', 'bsmooth') else 'bwd'
@@ -467,6 +471,57 @@ class MultiDMM(MultiDGTS):
                 sample_init=sample_init, eps=eps_smt)
         recon = self.decode(z_samples)
         return infer, prior, recon
+
+    def _forward_large(self, inputs, t_max, b_dim, mode, sample, sample_init, flt_particles,
+                       smt_particles, eps_flt, eps_smt, precision):
+        """forward() of the large-dim kernel family: ONE C call (bfvi_forward) that runs every
+        Linear layer as a tcgen05 GEMM.  Inference / evaluation only in this release."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise _lib.BfviError(
+                'z_dim=%d, h_dim=%d is served by the tcgen05 large-dim family, which implements '
+                'forward() / evaluation only in this release: call it under torch.no_grad() '
+                '(training kernels exist for the small-dim family only; there is no fallback)'
+                % (self.z_dim, self.h_dim))
+        if not all(self._default_enc(m) and self._default_dec(m) for m in self.modalities):
+            raise _lib.BfviError('the large-dim family covers default Gaussian encoders / decoders only')
+        lib = _lib.load()
+        dev = self._flat.device
+        a = _lib.ForwardArgs()
+        keep = []
+        a.T, a.B = t_max, b_dim
+        for i, m in enumerate(self.modalities):
+            if m in inputs:
+                x = inputs[m]
+                if not x.is_cuda:
+                    raise _lib.BfviError('forward() inputs must be CUDA tensors')
+                x = x.detach().reshape(t_max, b_dim, -1).contiguous().float()
+                keep.append(x)
+                a.inputs[i] = x.data_ptr()
+        a.mode = _lib.MODE_CODES[mode]
+        a.sample, a.sample_init = int(bool(sample)), int(bool(sample_init))
+        a.flt_particles, a.smt_particles = int(flt_particles), int(smt_particles)
+        for t, field in ((eps_flt, 'eps_flt'), (eps_smt, 'eps_smt')):
+            if t is not None:
+                t = t.detach().to(dev).contiguous().float()
+                keep.append(t)
+                setattr(a, field, t.data_ptr())
+        a.seed, a.b_offset = self._next_seed(), int(getattr(self, 'b_offset', 0))
+        a.precision = {'tf32x3': 0, 'tf32': 1}[precision]
+        outs = [torch.empty(t_max, b_dim, self.z_dim, device=dev) for _ in range(4)]
+        a.infer_mean, a.infer_std, a.prior_mean, a.prior_std = [t.data_ptr() for t in outs]
+        recon = {}
+        for i, m in enumerate(self.modalities):
+            d = self._mods_flat()[i]
+            mean, std = torch.empty(t_max, b_dim, d, device=dev), torch.empty(t_max, b_dim, d, device=dev)
+            a.recon_mean[i], a.recon_std[i] = mean.data_ptr(), std.data_ptr()
+            shape = (t_max, b_dim) + tuple(np.atleast_1d(self.dims[m]).tolist())
+            recon[m] = (mean.view(shape), std.view(shape))
+        nbytes = C.c_size_t(0)
+        lib.call('bfvi_forward_workspace', C.byref(self._cmodel), C.byref(a), C.byref(nbytes))
+        ws = self._workspace(nbytes.value)
+        lib.call('bfvi_forward', C.byref(self._cmodel), _lib.ptr(self._flat), C.byref(a), _lib.ptr(ws),
+                 C.c_size_t(nbytes.value), _stream())
+        return (outs[0], outs[1]), (outs[2], outs[3]), recon
 
     def kld_prior(self, n_particles, direction='fwd'):
         """KL(p(z) || E_k p(z_next | z_k)) (models/dmm.py:496-501)."""

@@ -47,7 +47,7 @@ def test_cabi_library_exports_every_declared_symbol():
     lib = _lib.Library(path)                # resolves every entry of _lib.SYMBOLS
     header = open(os.path.join(ROOT, 'include', 'bfvi.h')).read()
     import re
-    declared = set(re.findall(r'\b(bfvi_[a-z_]+)\s*\(', header))
+    declared = set(re.findall(r'\b(bfvi_[a-z0-9_]+)\s*\(', header))
     assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
     for name in declared:
         assert hasattr(lib.dll, name)
@@ -68,7 +68,7 @@ def test_layout_and_argument_errors():
     with pytest.raises(_lib.BfviError):
         lib.layout(bad)
     big = _lib.make_model([4], ['Normal'], 999, 999, 1e-3)
-    assert lib.dll.bfvi_kernel_family(C.byref(big)) == 0            # unsupported, not a crash
+    assert lib.dll.bfvi_kernel_family(C.byref(big)) == 2            # tcgen05 family: forward only
     a = _lib.StepArgs()
     a.T, a.B = 4, 4
     n = C.c_size_t(0)
