@@ -302,6 +302,15 @@ int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, c
                      float* y, int64_t ldy, int64_t n_rows, int32_t n_in, int32_t n_out,
                      int32_t act, void* stream);
 
+/* Weight gradient of a Linear layer on the tcgen05 tensor cores: dw (n_out, n_in) (+)= dy^T x,
+ * given the TRANSPOSED activations dy_t (n_out, n_rows) and x_t (n_in, n_rows) (the contraction
+ * runs over the rows, which makes both operands K-major; the producing kernels of this library
+ * write the transposed copies themselves).  accumulate != 0 adds into dw.  flags: 16 =
+ * single-pass TF32 (default error-compensated 3xTF32). */
+int bfvi_wgrad_tf32(const float* dy_t, int64_t lddy, const float* x_t, int64_t ldx, float* dw, int64_t lddw,
+                    int64_t n_rows, int32_t n_out, int32_t n_in, int32_t accumulate, int32_t flags,
+                    void* stream);
+
 /* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
  * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream);

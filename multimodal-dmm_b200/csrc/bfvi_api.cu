@@ -95,6 +95,9 @@ int grid_for(int64_t work_items, int per_block, int blocks_per_sm) {
 // ---- (Z, H) dispatch for the register-resident family -------------------------
 #define BFVI_SMALL_DIMS(X) X(5, 20) X(4, 8) X(3, 6) X(6, 12)
 
+// 1 = register-resident small-dim family, 2 = tcgen05 large-dim family.  BFVI_FAMILY=2 forces the
+// large-dim family on small models (test knob: the golden fixtures then exercise it end to end).
+int family_of(int Z, int H);
 bool small_supported(int Z, int H) {
 #define X(z, h) if (Z == z && H == h) return true;
   BFVI_SMALL_DIMS(X)
@@ -103,6 +106,12 @@ bool small_supported(int Z, int H) {
 }
 
 #define BFVI_MLP_H(X) X(20) X(8) X(6) X(12)
+
+int family_of(int Z, int H) {
+  if (!small_supported(Z, H)) return 2;
+  const char* env = getenv("BFVI_FAMILY");
+  return (env != nullptr && atoi(env) == 2) ? 2 : 1;
+}
 
 template <int Z, int H>
 int layout_matches(const bfvi_gtf_layout& l) {
@@ -385,22 +394,518 @@ int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
   return BFVI_OK;
 }
 
+template <bool SPLIT>
+int dispatch_gemm_bn(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
+  if (gp.N <= 32) return launch_gemm_tf32<32, SPLIT>(gp, st);
+  if (gp.N <= 64) return launch_gemm_tf32<64, SPLIT>(gp, st);
+  if (gp.N <= 128) return launch_gemm_tf32<128, SPLIT>(gp, st);
+  return launch_gemm_tf32<256, SPLIT>(gp, st);
+}
+
+int gemm_tc(const bfvi::tc::GemmParams& gp, int prec, cudaStream_t st) {
+  return prec == bfvi::tc::PREC_TF32 ? dispatch_gemm_bn<false>(gp, st) : dispatch_gemm_bn<true>(gp, st);
+}
+
 // y = act(x W^T + b) on tcgen05; prec: PREC_TF32X3 (error-compensated) or PREC_TF32
 int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy,
               int64_t n_rows, int n_in, int n_out, int act, int prec, cudaStream_t st) {
   bfvi::tc::GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
   gp.A = x; gp.lda = ldx; gp.W = w; gp.ldw = ldw; gp.bias = bias; gp.C = y; gp.ldc = ldy;
   gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
-  if (prec == bfvi::tc::PREC_TF32) {
-    if (n_out <= 32) return launch_gemm_tf32<32, false>(gp, st);
-    if (n_out <= 64) return launch_gemm_tf32<64, false>(gp, st);
-    if (n_out <= 128) return launch_gemm_tf32<128, false>(gp, st);
-    return launch_gemm_tf32<256, false>(gp, st);
+  return gemm_tc(gp, prec, st);
+}
+
+// ===========================================================================================
+// large-dim family: the whole MultiDMM.step + backward as a stream-ordered launch sequence of
+// tcgen05 GEMMs (every Linear layer: forward, input gradient, weight gradient) and fused
+// elementwise kernels (bfvi_generic.cuh).  Same passes, chain sets and workspace roles as the
+// small-dim step_impl below; rows of a GEMM = chains x particles of ONE time step.
+// ===========================================================================================
+struct LargePlan {
+  int S, k_b;
+  unsigned set_bits[BFVI_MAX_SETS];
+  size_t tb, tbz, C, R, d_max;
+  size_t zero_begin, zero_end, total;
+  size_t acc, count, dobs_mean, dobs_std, a_dsamp, c_dsamp, b_dpm, b_dps;        // zeroed
+  size_t paramsT, x0[BFVI_MAX_MODS], x0T[BFVI_MAX_MODS], mask, henc, hencT, obs_mean, obs_stdpre, obs_std;
+  size_t pa[6], pb[4], pc[6];                       // infer m/s, prior m/s, samples, samplesT
+  size_t zrows, zrowsT, h1, h1T, h3, h3T, dh1, dh1T, dh3, dh3T;
+  size_t g, nl, nlT, lin, as, d_as, d_asT, d_g, d_gT, d_lin, d_linT, d_nl, d_nlT, dz;
+  size_t c_mu, c_sd, d_pm, d_v, zvec;
+  size_t hdec, hdecT, dhd, dhdT, dmean, dstd, dmeanT, dstdT;
+};
+
+int plan_large(const bfvi_model* m, const bfvi_step_args* a, LargePlan* pl) {
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim;
+  int S = 0;
+  if (M > 1) pl->set_bits[S++] = (M >= 32) ? 0xffffffffu : ((1u << M) - 1u);
+  if (a->uni_loss)
+    for (int i = 0; i < M; ++i) pl->set_bits[S++] = 1u << i;
+  pl->S = S;
+  pl->k_b = a->train_particles;
+  pl->tb = (size_t)a->T * a->B;
+  pl->tbz = pl->tb * Z;
+  pl->C = (size_t)(S > 0 ? S : 1) * a->B;
+  size_t R = pl->C * (size_t)a->train_particles;
+  if ((size_t)a->match_particles > R) R = a->match_particles;
+  pl->R = R;
+  pl->d_max = Z;                     // head scratch serves decoders (D_m wide) and encoders (Z wide)
+  for (int i = 0; i < M; ++i) if ((size_t)m->dims[i] > pl->d_max) pl->d_max = m->dims[i];
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  const size_t f = sizeof(float), fS = f * pl->tbz * (S > 0 ? S : 1);
+  pl->zero_begin = cur;
+  pl->acc = carve(sizeof(double)); pl->count = carve(f);
+  pl->dobs_mean = carve(f * pl->tbz * M); pl->dobs_std = carve(f * pl->tbz * M);
+  pl->a_dsamp = carve(fS); pl->c_dsamp = carve(fS); pl->b_dpm = carve(fS); pl->b_dps = carve(fS);
+  pl->zero_end = cur;
+  pl->paramsT = carve(f * lay.total);
+  for (int i = 0; i < M; ++i) { pl->x0[i] = carve(f * pl->tb * m->dims[i]); pl->x0T[i] = carve(f * pl->tb * m->dims[i]); }
+  pl->mask = carve(pl->tb * M);
+  pl->henc = carve(f * pl->tb * H * M); pl->hencT = carve(f * pl->tb * H * M);
+  pl->obs_mean = carve(f * pl->tbz * M); pl->obs_stdpre = carve(f * pl->tbz * M); pl->obs_std = carve(f * pl->tbz * M);
+  for (int i = 0; i < 6; ++i) pl->pa[i] = carve(fS);
+  for (int i = 0; i < 4; ++i) pl->pb[i] = carve(fS);
+  for (int i = 0; i < 6; ++i) pl->pc[i] = carve(fS);
+  const size_t rz = f * R * Z, rh = f * R * H;
+  pl->zrows = carve(rz); pl->zrowsT = carve(rz);
+  pl->h1 = carve(rh); pl->h1T = carve(rh); pl->h3 = carve(rh); pl->h3T = carve(rh);
+  pl->dh1 = carve(rh); pl->dh1T = carve(rh); pl->dh3 = carve(rh); pl->dh3T = carve(rh);
+  size_t* zbufs[] = {&pl->g, &pl->nl, &pl->nlT, &pl->lin, &pl->as, &pl->d_as, &pl->d_asT, &pl->d_g, &pl->d_gT,
+                     &pl->d_lin, &pl->d_linT, &pl->d_nl, &pl->d_nlT, &pl->dz};
+  for (size_t* z : zbufs) *z = carve(rz);
+  pl->c_mu = carve(f * pl->C * Z); pl->c_sd = carve(f * pl->C * Z);
+  pl->d_pm = carve(f * pl->C * Z); pl->d_v = carve(f * pl->C * Z);
+  pl->zvec = carve(f * Z * 4);
+  pl->hdec = carve(f * pl->tb * H); pl->hdecT = carve(f * pl->tb * H);
+  pl->dhd = carve(f * pl->tb * H); pl->dhdT = carve(f * pl->tb * H);
+  pl->dmean = carve(f * pl->tb * pl->d_max); pl->dstd = carve(f * pl->tb * pl->d_max);
+  pl->dmeanT = carve(f * pl->tb * pl->d_max); pl->dstdT = carve(f * pl->tb * pl->d_max);
+  pl->total = cur;
+  return BFVI_OK;
+}
+
+// fills mu[z] = z0_mean, sd[z] = exp(z0_log_std) + min_std (the "infer" of the prior-matching chain)
+__global__ void prior_fill_kernel(const float* z0_mean, const float* z0_log_std, float min_std, int Z, float* mu,
+                                  float* sd) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Z) { mu[i] = z0_mean[i]; sd[i] = expf(z0_log_std[i]) + min_std; }
+}
+// z_k = gm + eps_k gs: gradient of the propagated particles back to the global prior
+__global__ void match_tail_kernel(const float* c_mu, const float* c_sd, const float* z0_log_std, int Z,
+                                  float* g_z0_mean, float* g_z0_log_std) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Z) { atomicAdd(g_z0_mean + i, c_mu[i]); atomicAdd(g_z0_log_std + i, c_sd[i] * expf(z0_log_std[i])); }
+}
+
+int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a, void* workspace,
+               size_t workspace_bytes, float* loss_out, int32_t* launches, cudaStream_t st) {
+  LargePlan pl;
+  plan_large(m, a, &pl);
+  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  char* ws = (char*)workspace;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, T = a->T, B = a->B, S = pl.S;
+  const bool with_grad = grads != nullptr;
+  const int prec = bfvi::tc::PREC_TF32X3;
+  const int64_t tb = (int64_t)pl.tb;
+  int n_launch = 0;
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  float* paramsT = F(pl.paramsT);
+  double* acc = (double*)(ws + pl.acc);
+  float* count = F(pl.count);
+  auto ew_grid = [&](int64_t n, int per) { return dim3((unsigned)grid_for(n, per, 16)); };
+
+  cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
+  if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
+  BFVI_CHECK_CUDA();
+
+  // ---- GEMM helpers ---------------------------------------------------------------------
+  auto gemm = [&](const bfvi::tc::GemmParams& gp) -> int { ++n_launch; return gemm_tc(gp, prec, st); };
+  // y = act(x W^T + b), optional transposed copy yT
+  auto lin = [&](const float* x, int64_t ldx, int64_t w_off, int64_t b_off, float* y, float* yT, int64_t rows,
+                 int n_in, int n_out, int act) -> int {
+    bfvi::tc::GemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.A = x; gp.lda = ldx; gp.W = params + w_off; gp.ldw = n_in; gp.bias = params + b_off;
+    gp.C = y; gp.ldc = n_out; gp.M = rows; gp.N = n_out; gp.K = n_in; gp.act = act;
+    gp.Ct = yT; gp.ldct = rows;
+    return gemm(gp);
+  };
+  // dx (+)= dy W  (W stored (n_out, n_in); its transposed copy is the K-major B operand)
+  auto dgrad = [&](const float* dy, int64_t w_off, float* dx, float* dxT, int64_t rows, int n_out, int n_in,
+                   bool accumulate, const float* relu_aux, float* bias_grad) -> int {
+    bfvi::tc::GemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.A = dy; gp.lda = n_out; gp.W = paramsT + w_off; gp.ldw = n_out;
+    gp.C = dx; gp.ldc = n_in; gp.M = rows; gp.N = n_in; gp.K = n_out;
+    gp.accumulate = accumulate ? 1 : 0; gp.mask_aux = relu_aux; gp.ldaux = n_in;
+    gp.Ct = dxT; gp.ldct = rows; gp.colsum = bias_grad;
+    return gemm(gp);
+  };
+  // dW (n_out, n_in) += dy^T x from the transposed copies
+  auto wgrad = [&](const float* dyT, const float* xT, int64_t rows, int n_out, int n_in, int64_t w_off) -> int {
+    bfvi::tc::GemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.A = dyT; gp.lda = rows; gp.W = xT; gp.ldw = rows;
+    gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_out; gp.N = n_in; gp.K = rows; gp.accumulate = 1;
+    return gemm(gp);
+  };
+  auto transpose = [&](const float* in, int64_t rows, int cols, float* out) {
+    auto k = bfvi::gen::transpose_kernel;
+    BFVI_LAUNCH(k, dim3((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), dim3(256), 0, st, in, rows, cols, out);
+    ++n_launch;
+  };
+
+  // ---- transposed weights (input-gradient GEMMs) ------------------------------------------
+  if (with_grad) {
+    auto tw = [&](int64_t w_off, int n_out, int n_in) { transpose(params + w_off, n_out, n_in, paramsT + w_off); };
+    for (int i = 0; i < M; ++i) {
+      tw(lay.enc[i].in_to_h_w, H, m->dims[i]); tw(lay.enc[i].mean_w, Z, H); tw(lay.enc[i].std_w, Z, H);
+      tw(lay.dec[i].in_to_h_w, H, Z); tw(lay.dec[i].mean_w, m->dims[i], H); tw(lay.dec[i].std_w, m->dims[i], H);
+    }
+    for (int d = 0; d < 2; ++d) {
+      const bfvi_gtf_layout& g = lay.trans[d];
+      tw(g.gate0_w, H, Z); tw(g.gate2_w, Z, H); tw(g.lin_w, Z, Z);
+      tw(g.nonlin0_w, H, Z); tw(g.nonlin2_w, Z, H); tw(g.std_w, Z, Z);
+    }
+    BFVI_CHECK_CUDA();
   }
-  if (n_out <= 32) return launch_gemm_tf32<32, true>(gp, st);
-  if (n_out <= 64) return launch_gemm_tf32<64, true>(gp, st);
-  if (n_out <= 128) return launch_gemm_tf32<128, true>(gp, st);
-  return launch_gemm_tf32<256, true>(gp, st);
+
+  // ---- one transition: 6 forward GEMMs over `rows` particles --------------------------------
+  auto trans_fwd = [&](const bfvi_gtf_layout& g, int64_t rows, bool keep) -> int {
+    float* h3 = keep ? F(pl.h3) : F(pl.h1);
+    if (int rc = lin(F(pl.zrows), Z, g.gate0_w, g.gate0_b, F(pl.h1), keep ? F(pl.h1T) : nullptr, rows, Z, H, 1)) return rc;
+    if (int rc = lin(F(pl.h1), H, g.gate2_w, g.gate2_b, F(pl.g), nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = lin(F(pl.zrows), Z, g.nonlin0_w, g.nonlin0_b, h3, keep ? F(pl.h3T) : nullptr, rows, Z, H, 1)) return rc;
+    if (int rc = lin(h3, H, g.nonlin2_w, g.nonlin2_b, F(pl.nl), keep ? F(pl.nlT) : nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = lin(F(pl.zrows), Z, g.lin_w, g.lin_b, F(pl.lin), nullptr, rows, Z, Z, 0)) return rc;
+    return lin(F(pl.nl), Z, g.std_w, g.std_b, F(pl.as), nullptr, rows, Z, Z, 0);
+  };
+  // backward of one transition given d_as / d_g / d_lin / d_nl(partial) rows: input gradient dz
+  // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums)
+  auto trans_bwd = [&](const bfvi_gtf_layout& g, int64_t rows) -> int {
+    if (int rc = dgrad(F(pl.d_as), g.std_w, F(pl.d_nl), F(pl.d_nlT), rows, Z, Z, true, nullptr, grads + g.nonlin2_b)) return rc;
+    if (int rc = dgrad(F(pl.d_nl), g.nonlin2_w, F(pl.dh3), F(pl.dh3T), rows, Z, H, false, F(pl.h3), grads + g.nonlin0_b)) return rc;
+    if (int rc = dgrad(F(pl.d_g), g.gate2_w, F(pl.dh1), F(pl.dh1T), rows, Z, H, false, F(pl.h1), grads + g.gate0_b)) return rc;
+    if (int rc = dgrad(F(pl.d_lin), g.lin_w, F(pl.dz), nullptr, rows, Z, Z, false, nullptr, nullptr)) return rc;
+    if (int rc = dgrad(F(pl.dh1), g.gate0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    if (int rc = dgrad(F(pl.dh3), g.nonlin0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    if (int rc = wgrad(F(pl.dh1T), F(pl.zrowsT), rows, H, Z, g.gate0_w)) return rc;
+    if (int rc = wgrad(F(pl.dh3T), F(pl.zrowsT), rows, H, Z, g.nonlin0_w)) return rc;
+    if (int rc = wgrad(F(pl.d_linT), F(pl.zrowsT), rows, Z, Z, g.lin_w)) return rc;
+    if (int rc = wgrad(F(pl.d_gT), F(pl.h1T), rows, Z, H, g.gate2_w)) return rc;
+    if (int rc = wgrad(F(pl.d_nlT), F(pl.h3T), rows, Z, H, g.nonlin2_w)) return rc;
+    return wgrad(F(pl.d_asT), F(pl.nlT), rows, Z, Z, g.std_w);
+  };
+  auto step_params = [&](const bfvi_filter_args& f, int i) {
+    bfvi::gen::StepParams sp;
+    memset(&sp, 0, sizeof(sp));
+    const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
+    sp.a = f;
+    sp.z0_mean = params + lay.z0_mean; sp.z0_log_std = params + lay.z0_log_std;
+    sp.g_z0_mean = grads ? grads + lay.z0_mean : nullptr; sp.g_z0_log_std = grads ? grads + lay.z0_log_std : nullptr;
+    sp.min_std = m->min_std; sp.Z = Z; sp.i = i; sp.R = (int64_t)f.S * f.B * f.n_particles;
+    sp.g = F(pl.g); sp.nl = F(pl.nl); sp.lin = F(pl.lin); sp.as = F(pl.as);
+    sp.zrows = F(pl.zrows); sp.zrowsT = F(pl.zrowsT);
+    sp.c_mu = F(pl.c_mu); sp.c_sd = F(pl.c_sd); sp.d_pm = F(pl.d_pm); sp.d_v = F(pl.d_v);
+    sp.d_as = F(pl.d_as); sp.d_asT = F(pl.d_asT); sp.d_g = F(pl.d_g); sp.d_gT = F(pl.d_gT);
+    sp.d_lin = F(pl.d_lin); sp.d_linT = F(pl.d_linT); sp.d_nl = F(pl.d_nl); sp.d_nlT = F(pl.d_nlT);
+    if (grads) {
+      sp.gb_std = grads + g.std_b; sp.gb_gate2 = grads + g.gate2_b;
+      sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
+    }
+    sp.dz = F(pl.dz);
+    return sp;
+  };
+  auto pass_fwd = [&](const bfvi_filter_args& f, float* samplesT) -> int {
+    const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
+    const int64_t chains = (int64_t)f.S * B, rows = chains * f.n_particles;
+    for (int i = 0; i < T; ++i) {
+      if (i > 0) { if (int rc = trans_fwd(g, rows, false)) return rc; }
+      bfvi::gen::StepParams sp = step_params(f, i);
+      sp.zrowsT = nullptr; sp.samplesT = samplesT;
+      auto k = bfvi::gen::step_kernel;
+      BFVI_LAUNCH(k, ew_grid(chains * Z, 128), dim3(128), 0, st, sp);
+      ++n_launch;
+    }
+    BFVI_CHECK_CUDA();
+    return BFVI_OK;
+  };
+  auto pass_bwd = [&](const bfvi_filter_args& f) -> int {
+    const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
+    const int64_t chains = (int64_t)f.S * B, rows = chains * f.n_particles;
+    cudaMemsetAsync(F(pl.c_mu), 0, sizeof(float) * chains * Z, st);
+    cudaMemsetAsync(F(pl.c_sd), 0, sizeof(float) * chains * Z, st);
+    for (int i = T - 1; i >= 0; --i) {
+      bfvi::gen::StepParams sp = step_params(f, i);
+      auto kh = bfvi::gen::bwd_head_kernel;
+      BFVI_LAUNCH(kh, ew_grid(chains * Z, 128), dim3(128), 0, st, sp);
+      ++n_launch;
+      if (i == 0) break;
+      auto ks = bfvi::gen::sample_rows_kernel;                 // particles of step i-1
+      BFVI_LAUNCH(ks, ew_grid(rows * Z, 256), dim3(256), 0, st, sp, i - 1);
+      ++n_launch;
+      if (int rc = trans_fwd(g, rows, true)) return rc;
+      auto kr = bfvi::gen::bwd_rows_kernel;
+      BFVI_LAUNCH(kr, dim3((unsigned)((rows + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                           (unsigned)((Z + 127) / 128)), dim3(128), 0, st, sp);
+      ++n_launch;
+      if (int rc = trans_bwd(g, rows)) return rc;
+      auto kc = bfvi::gen::bwd_carry_kernel;
+      BFVI_LAUNCH(kc, ew_grid(chains * Z, 128), dim3(128), 0, st, sp, i - 1);
+      ++n_launch;
+    }
+    BFVI_CHECK_CUDA();
+    return BFVI_OK;
+  };
+
+  const bool external = a->eps_filt != nullptr || a->eps_sflt != nullptr || a->eps_ssmt != nullptr ||
+                        a->eps_match != nullptr;
+  // ---- prior-matching term (models/dmm.py:540-545) -----------------------------------------
+  if (a->match_mult > 0.f) {
+    if (external && !a->eps_match) return fail(BFVI_ERR_ARG, "eps_match missing");
+    const float* cnt = nullptr;
+    float coef = a->match_mult * a->kld_mult;
+    if (a->match_count < 0.f) {
+      auto k = bfvi::count_mask_kernel;
+      BFVI_LAUNCH(k, dim3(grid_for(tb, 256, 4)), dim3(256), 0, st, a->seq_mask, tb, count);
+      ++n_launch;
+      cnt = count;
+    } else {
+      coef *= a->match_count;
+    }
+    const int Km = a->match_particles;
+    float* zvec = F(pl.zvec);                       // [mu | sd | pm | unused] x Z
+    auto kf = prior_fill_kernel;
+    BFVI_LAUNCH(kf, dim3((Z + 127) / 128), dim3(128), 0, st, params + lay.z0_mean, params + lay.z0_log_std,
+                m->min_std, Z, zvec, zvec + Z);
+    ++n_launch;
+    for (int dir = 0; dir < 2; ++dir) {
+      bfvi_filter_args f;
+      memset(&f, 0, sizeof(f));
+      f.T = 1; f.B = 1; f.S = 1; f.n_particles = Km; f.sample = 1; f.direction = BFVI_DIR_FWD;
+      f.noise.eps = a->eps_match ? a->eps_match + (size_t)dir * Km * Z : nullptr;
+      f.noise.seed = a->seed; f.noise.stream_id = 100u + dir;
+      f.infer_mean = zvec; f.infer_std = zvec + Z; f.prior_mean = zvec + 2 * Z; f.prior_std = zvec + 3 * Z;
+      bfvi::gen::StepParams sp = step_params(f, 0);
+      const bfvi_gtf_layout& g = lay.trans[dir];
+      if (grads) {
+        sp.gb_std = grads + g.std_b; sp.gb_gate2 = grads + g.gate2_b;
+        sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
+      }
+      auto ks = bfvi::gen::sample_rows_kernel;
+      BFVI_LAUNCH(ks, ew_grid((int64_t)Km * Z, 256), dim3(256), 0, st, sp, 0);
+      ++n_launch;
+      if (int rc = trans_fwd(g, Km, with_grad)) return rc;
+      bfvi::gen::MatchHeadParams mh;
+      memset(&mh, 0, sizeof(mh));
+      mh.z0_mean = sp.z0_mean; mh.z0_log_std = sp.z0_log_std; mh.g_z0_mean = sp.g_z0_mean; mh.g_z0_log_std = sp.g_z0_log_std;
+      mh.g = F(pl.g); mh.nl = F(pl.nl); mh.lin = F(pl.lin); mh.as = F(pl.as);
+      mh.pm = zvec + 2 * Z; mh.d_pm = F(pl.d_pm); mh.d_v = F(pl.d_v);
+      mh.min_std = m->min_std; mh.coef_static = coef; mh.count = cnt; mh.loss_acc = acc;
+      mh.K = Km; mh.Z = Z; mh.with_grad = with_grad ? 1 : 0;
+      auto km = bfvi::gen::match_head_kernel;
+      BFVI_LAUNCH(km, dim3((Z + 127) / 128), dim3(128), 0, st, mh);
+      ++n_launch;
+      if (with_grad) {
+        auto kr = bfvi::gen::bwd_rows_kernel;
+        BFVI_LAUNCH(kr, dim3((unsigned)((Km + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                             (unsigned)((Z + 127) / 128)), dim3(128), 0, st, sp);
+        ++n_launch;
+        if (int rc = trans_bwd(g, Km)) return rc;
+        auto kc = bfvi::gen::bwd_carry_kernel;
+        BFVI_LAUNCH(kc, dim3((Z + 127) / 128), dim3(128), 0, st, sp, 0);
+        auto kt = match_tail_kernel;
+        BFVI_LAUNCH(kt, dim3((Z + 127) / 128), dim3(128), 0, st, (const float*)F(pl.c_mu), (const float*)F(pl.c_sd),
+                    params + lay.z0_log_std, Z, grads + lay.z0_mean, grads + lay.z0_log_std);
+        n_launch += 2;
+      }
+    }
+    BFVI_CHECK_CUDA();
+  }
+
+  if (S > 0 && (a->f_mult != 0.f || a->s_mult != 0.f)) {
+    float* obs_mean = F(pl.obs_mean); float* obs_stdpre = F(pl.obs_stdpre); float* obs_std = F(pl.obs_std);
+    uint8_t* obs_mask = (uint8_t*)(ws + pl.mask);
+    float* dobs_mean = F(pl.dobs_mean); float* dobs_std = F(pl.dobs_std);
+    // ---- encoders (models/dmm.py:165-173) ---------------------------------------------------
+    for (int i = 0; i < M; ++i) {
+      const bfvi_mlp_layout& l = lay.enc[i];
+      const int D = m->dims[i];
+      float* henc = F(pl.henc) + (size_t)i * pl.tb * H;
+      float* hencT = F(pl.hencT) + (size_t)i * pl.tb * H;
+      auto kp = bfvi::gen::prep_rows_kernel;
+      BFVI_LAUNCH(kp, ew_grid(tb, 256), dim3(256), 0, st, a->inputs[i], tb, D, F(pl.x0[i]), obs_mask + (size_t)i * pl.tb);
+      ++n_launch;
+      if (with_grad) transpose(F(pl.x0[i]), tb, D, F(pl.x0T[i]));
+      if (int rc = lin(F(pl.x0[i]), D, l.in_to_h_w, l.in_to_h_b, henc, with_grad ? hencT : nullptr, tb, D, H, 1)) return rc;
+      if (int rc = lin(henc, H, l.mean_w, l.mean_b, obs_mean + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
+      if (int rc = lin(henc, H, l.std_w, l.std_b, obs_stdpre + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
+      cudaMemcpyAsync(obs_std + (size_t)i * pl.tbz, obs_stdpre + (size_t)i * pl.tbz, sizeof(float) * pl.tbz,
+                      cudaMemcpyDeviceToDevice, st);
+      auto ks = bfvi::gen::softplus_kernel;
+      BFVI_LAUNCH(ks, ew_grid(tb * Z, 256), dim3(256), 0, st, obs_std + (size_t)i * pl.tbz, tb * Z, bfvi::kMlpMinStd);
+      ++n_launch;
+    }
+    BFVI_CHECK_CUDA();
+    auto obs_expert = [&](int i) {
+      bfvi_expert e;
+      memset(&e, 0, sizeof(e));
+      e.mean = obs_mean + (size_t)i * pl.tbz; e.std = obs_std + (size_t)i * pl.tbz;
+      e.mask = obs_mask + (size_t)i * pl.tb;
+      e.stride_s = 0; e.stride_t = (int64_t)B * Z; e.stride_b = Z;
+      e.mstride_s = 0; e.mstride_t = B; e.mstride_b = 1;
+      e.d_mean = with_grad ? dobs_mean + (size_t)i * pl.tbz : nullptr;
+      e.d_std = with_grad ? dobs_std + (size_t)i * pl.tbz : nullptr;
+      e.kind = BFVI_EXPERT_TENSOR;
+      return e;
+    };
+    auto base_args = [&]() {
+      bfvi_filter_args f;
+      memset(&f, 0, sizeof(f));
+      f.T = T; f.B = B; f.S = S;
+      f.n_experts = M;
+      for (int i = 0; i < M; ++i) f.experts[i] = obs_expert(i);
+      for (int s = 0; s < S; ++s) f.set_expert_bits[s] = pl.set_bits[s];
+      f.sample = a->sample; f.sample_init = a->sample_init;
+      f.noise.seed = a->seed; f.noise.b_offset = a->b_offset;
+      f.seq_mask = a->seq_mask;
+      f.loss_acc = acc;
+      return f;
+    };
+    bfvi_filter_args fa = base_args();
+    fa.direction = a->f_mode == BFVI_MODE_BFILTER ? BFVI_DIR_BWD : BFVI_DIR_FWD;
+    fa.n_particles = 1;
+    fa.noise.eps = a->eps_filt; fa.noise.stream_id = 1;
+    fa.infer_mean = F(pl.pa[0]); fa.infer_std = F(pl.pa[1]); fa.prior_mean = F(pl.pa[2]); fa.prior_std = F(pl.pa[3]);
+    fa.samples = F(pl.pa[4]);
+    fa.kl_weight = a->f_mult * a->kld_mult;
+    bfvi_filter_args fb = base_args();
+    fb.direction = a->s_mode == BFVI_MODE_FSMOOTH ? BFVI_DIR_BWD : BFVI_DIR_FWD;
+    fb.n_particles = a->train_particles;
+    fb.sample_init = 0;
+    fb.noise.eps = a->eps_sflt; fb.noise.stream_id = 2;
+    fb.infer_mean = F(pl.pb[0]); fb.infer_std = F(pl.pb[1]); fb.prior_mean = F(pl.pb[2]); fb.prior_std = F(pl.pb[3]);
+    fb.samples = nullptr; fb.kl_weight = 0.f; fb.loss_acc = nullptr;
+    bfvi_filter_args fc = base_args();
+    fc.direction = a->s_mode == BFVI_MODE_FSMOOTH ? BFVI_DIR_FWD : BFVI_DIR_BWD;
+    fc.n_particles = 1;
+    fc.noise.eps = a->eps_ssmt; fc.noise.stream_id = 3;
+    {
+      bfvi_expert e;
+      memset(&e, 0, sizeof(e));
+      e.mean = F(pl.pb[2]); e.std = F(pl.pb[3]); e.mask = nullptr;
+      e.stride_s = (int64_t)pl.tbz; e.stride_t = (int64_t)B * Z; e.stride_b = Z;
+      e.d_mean = with_grad ? F(pl.b_dpm) : nullptr; e.d_std = with_grad ? F(pl.b_dps) : nullptr;
+      e.kind = BFVI_EXPERT_TENSOR; e.zero_mask_last_t = 1;
+      fc.experts[M] = e;
+      memset(&e, 0, sizeof(e));
+      e.kind = BFVI_EXPERT_INV_PRIOR;
+      fc.experts[M + 1] = e;
+      fc.n_experts = M + 2;
+      for (int s = 0; s < S; ++s) fc.set_expert_bits[s] = pl.set_bits[s] | (1u << M) | (1u << (M + 1));
+    }
+    fc.infer_mean = F(pl.pc[0]); fc.infer_std = F(pl.pc[1]); fc.prior_mean = F(pl.pc[2]); fc.prior_std = F(pl.pc[3]);
+    fc.samples = F(pl.pc[4]);
+    fc.kl_weight = a->s_mult * a->kld_mult;
+    if (external) {
+      if (a->f_mult != 0.f && !fa.noise.eps && (a->sample || a->sample_init)) return fail(BFVI_ERR_ARG, "eps_filt missing");
+      if (a->s_mult != 0.f && !fb.noise.eps) return fail(BFVI_ERR_ARG, "eps_sflt missing");
+      if (a->s_mult != 0.f && !fc.noise.eps && (a->sample || a->sample_init)) return fail(BFVI_ERR_ARG, "eps_ssmt missing");
+    }
+    const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
+    if (do_f) { if (int rc = pass_fwd(fa, with_grad ? F(pl.pa[5]) : nullptr)) return rc; }
+    if (do_s) {
+      if (int rc = pass_fwd(fb, nullptr)) return rc;
+      if (int rc = pass_fwd(fc, with_grad ? F(pl.pc[5]) : nullptr)) return rc;
+    }
+    // ---- decoders + NLL, forward and backward (models/dmm.py:207-211, models/losses.py:68-89) ----
+    for (int pass = 0; pass < 2; ++pass) {
+      if ((pass == 0 && !do_f) || (pass == 1 && !do_s)) continue;
+      const float mult = pass == 0 ? a->f_mult : a->s_mult;
+      float* samp = pass == 0 ? F(pl.pa[4]) : F(pl.pc[4]);
+      float* sampT = pass == 0 ? F(pl.pa[5]) : F(pl.pc[5]);
+      float* dsamp = pass == 0 ? F(pl.a_dsamp) : F(pl.c_dsamp);
+      for (int s = 0; s < S; ++s)
+        for (int i = 0; i < M; ++i) {
+          if (!((pl.set_bits[s] >> i) & 1u) || a->rec_mults[i] == 0.f) continue;
+          const bfvi_mlp_layout& l = lay.dec[i];
+          const int D = m->dims[i];
+          const float* zs = samp + (size_t)s * pl.tbz;
+          if (int rc = lin(zs, Z, l.in_to_h_w, l.in_to_h_b, F(pl.hdec), with_grad ? F(pl.hdecT) : nullptr, tb, Z, H, 1)) return rc;
+          if (int rc = lin(F(pl.hdec), H, l.mean_w, l.mean_b, F(pl.dmean), nullptr, tb, H, D, 0)) return rc;
+          if (int rc = lin(F(pl.hdec), H, l.std_w, l.std_b, F(pl.dstd), nullptr, tb, H, D, 0)) return rc;
+          bfvi::gen::HeadParams hp;
+          memset(&hp, 0, sizeof(hp));
+          hp.mean = F(pl.dmean); hp.stdpre = F(pl.dstd); hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
+          hp.target = a->targets[i]; hp.row_mask = a->seq_mask;
+          hp.gb_mean = with_grad ? grads + l.mean_b : F(pl.dz); hp.gb_std = with_grad ? grads + l.std_b : F(pl.dz);
+          hp.n_rows = tb; hp.D = D; hp.weight = mult * a->rec_mults[i]; hp.loss_acc = acc;
+          auto kh = bfvi::gen::head_kernel;
+          BFVI_LAUNCH(kh, dim3((unsigned)((tb + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                               (unsigned)((D + 127) / 128)), dim3(128), 0, st, hp);
+          ++n_launch;
+          if (!with_grad) continue;
+          if (int rc = dgrad(F(pl.dmean), l.mean_w, F(pl.dhd), nullptr, tb, D, H, false, F(pl.hdec), grads + l.in_to_h_b)) return rc;
+          if (int rc = dgrad(F(pl.dstd), l.std_w, F(pl.dhd), F(pl.dhdT), tb, D, H, true, F(pl.hdec), grads + l.in_to_h_b)) return rc;
+          if (int rc = dgrad(F(pl.dhd), l.in_to_h_w, dsamp + (size_t)s * pl.tbz, nullptr, tb, H, Z, true, nullptr, nullptr)) return rc;
+          if (int rc = wgrad(F(pl.dmeanT), F(pl.hdecT), tb, D, H, l.mean_w)) return rc;
+          if (int rc = wgrad(F(pl.dstdT), F(pl.hdecT), tb, D, H, l.std_w)) return rc;
+          if (int rc = wgrad(F(pl.dhdT), sampT + (size_t)s * pl.tbz, tb, H, Z, l.in_to_h_w)) return rc;
+        }
+    }
+    BFVI_CHECK_CUDA();
+    // ---- backward through the three passes and the encoders ----------------------------------
+    if (with_grad) {
+      if (do_s) {
+        fc.d_samples = F(pl.c_dsamp);
+        if (int rc = pass_bwd(fc)) return rc;
+        fb.d_prior_mean = F(pl.b_dpm); fb.d_prior_std = F(pl.b_dps);
+        if (int rc = pass_bwd(fb)) return rc;
+      }
+      if (do_f) {
+        fa.d_samples = F(pl.a_dsamp);
+        if (int rc = pass_bwd(fa)) return rc;
+      }
+      for (int i = 0; i < M; ++i) {
+        const bfvi_mlp_layout& l = lay.enc[i];
+        const int D = m->dims[i];
+        float* henc = F(pl.henc) + (size_t)i * pl.tb * H;
+        float* hencT = F(pl.hencT) + (size_t)i * pl.tb * H;
+        // d_mean / d_stdpre live in the obs_mean / obs_stdpre slots from here on (their values are spent)
+        float* dm = obs_mean + (size_t)i * pl.tbz;
+        float* dsp = obs_stdpre + (size_t)i * pl.tbz;
+        bfvi::gen::HeadParams hp;
+        memset(&hp, 0, sizeof(hp));
+        hp.mean = dm; hp.stdpre = dsp; hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
+        hp.d_mean_in = dobs_mean + (size_t)i * pl.tbz; hp.d_std_in = dobs_std + (size_t)i * pl.tbz;
+        hp.gb_mean = grads + l.mean_b; hp.gb_std = grads + l.std_b;
+        hp.n_rows = tb; hp.D = Z; hp.weight = 1.f;
+        auto kh = bfvi::gen::head_kernel;
+        BFVI_LAUNCH(kh, dim3((unsigned)((tb + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                             (unsigned)((Z + 127) / 128)), dim3(128), 0, st, hp);
+        ++n_launch;
+        if (int rc = dgrad(dm, l.mean_w, F(pl.dhd), nullptr, tb, Z, H, false, henc, grads + l.in_to_h_b)) return rc;
+        if (int rc = dgrad(dsp, l.std_w, F(pl.dhd), F(pl.dhdT), tb, Z, H, true, henc, grads + l.in_to_h_b)) return rc;
+        if (int rc = wgrad(F(pl.dmeanT), hencT, tb, Z, H, l.mean_w)) return rc;
+        if (int rc = wgrad(F(pl.dstdT), hencT, tb, Z, H, l.std_w)) return rc;
+        if (int rc = wgrad(F(pl.dhdT), F(pl.x0T[i]), tb, H, D, l.in_to_h_w)) return rc;
+      }
+      BFVI_CHECK_CUDA();
+    }
+  }
+  auto kfin = bfvi::finalize_loss_kernel;
+  BFVI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
+  BFVI_CHECK_CUDA();
+  ++n_launch;
+  if (launches) *launches = n_launch;
+  return BFVI_OK;
 }
 
 // batch chunk [b0, b0 + bc) of the (T, B) problem; bc = 0 means the whole batch
@@ -456,7 +961,7 @@ int bfvi_param_layout(const bfvi_model* m, bfvi_layout* out) {
 
 int bfvi_kernel_family(const bfvi_model* m) {
   if (check_model(m)) return 0;
-  return small_supported(m->z_dim, m->h_dim) ? 1 : 2;
+  return family_of(m->z_dim, m->h_dim);
 }
 
 int bfvi_encode_fwd(const bfvi_model* m, const float* params, int32_t mod, const float* x,
@@ -634,6 +1139,18 @@ int bfvi_linear_tf32(const float* x, int64_t ldx, const float* w, int64_t ldw, c
   return linear_tc(x, ldx, w, ldw, bias, y, ldy, n_rows, n_in, n_out, act & 1, (act >> 4) & 1, (cudaStream_t)stream);
 }
 
+int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, float* dw, int64_t lddw,
+                    int64_t n_rows, int32_t n_out, int32_t n_in, int32_t accumulate, int32_t flags,
+                    void* stream) {
+  if (!dy || !x || !dw || n_rows < 1 || n_in < 1 || n_out < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (lddy < n_rows || ldx < n_rows || lddw < n_in) return fail(BFVI_ERR_ARG, "leading dimension too small");
+  bfvi::tc::GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.A = dy; gp.lda = lddy; gp.W = x; gp.ldw = ldx; gp.C = dw; gp.ldc = lddw;
+  gp.M = n_out; gp.N = n_in; gp.K = n_rows; gp.accumulate = accumulate ? 1 : 0;
+  return gemm_tc(gp, (flags >> 4) & 1, (cudaStream_t)stream);
+}
+
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream) {
   if (!out || iters < 1 || blocks < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
   auto k = bfvi::ffma_peak_kernel;
@@ -646,8 +1163,6 @@ static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
   if (int rc = check_model(m)) return rc;
   if (a == nullptr) return fail(BFVI_ERR_ARG, "step args null");
   if (a->T < 1 || a->B < 1) return fail(BFVI_ERR_ARG, "bad T/B");
-  if (!small_supported(m->z_dim, m->h_dim))
-    return fail(BFVI_ERR_UNSUPPORTED, "no fused step kernels for z_dim=%d h_dim=%d", m->z_dim, m->h_dim);
   for (int i = 0; i < m->n_mods; ++i)
     if (m->dists[i] != BFVI_DIST_NORMAL)
       return fail(BFVI_ERR_UNSUPPORTED, "fused step covers Normal modalities; compose the ops for others");
@@ -660,6 +1175,12 @@ static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
 int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* bytes) {
   if (int rc = check_step(m, a)) return rc;
   if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
+  if (family_of(m->z_dim, m->h_dim) == 2) {
+    LargePlan lp;
+    plan_large(m, a, &lp);
+    *bytes = lp.total;
+    return BFVI_OK;
+  }
   StepPlan pl;
   plan_step(m, a, true, &pl);
   *bytes = pl.total;
@@ -686,6 +1207,10 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
   const int M = m->n_mods, Z = m->z_dim, T = a->T, B = a->B;
   for (int i = 0; i < M; ++i)
     if (!a->inputs[i] || !a->targets[i]) return fail(BFVI_ERR_ARG, "inputs/targets[%d] null", i);
+  if (family_of(m->z_dim, m->h_dim) == 2) {
+    if (pm.on) return fail(BFVI_ERR_UNSUPPORTED, "phase profile exists for the small-dim family only");
+    return step_large(m, params, grads, a, workspace, workspace_bytes, loss_out, launches, (cudaStream_t)stream);
+  }
   const bool with_grad = grads != nullptr;
   StepPlan pl;
   plan_step(m, a, with_grad, &pl);
@@ -1102,9 +1627,10 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
         if (int rc = linear_tc(nlbuf, Z, params + g.std_w, Z, params + g.std_b, asbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
       }
       bfvi::gen::StepParams sp;
+      memset(&sp, 0, sizeof(sp));
       sp.a = f;
       sp.z0_mean = params + lay.z0_mean; sp.z0_log_std = params + lay.z0_log_std;
-      sp.min_std = m->min_std; sp.Z = Z; sp.i = i;
+      sp.min_std = m->min_std; sp.Z = Z; sp.i = i; sp.R = rows;
       sp.g = gbuf; sp.nl = nlbuf; sp.lin = linbuf; sp.as = asbuf;
       sp.zrows = zrows;
       auto k = bfvi::gen::step_kernel;

@@ -57,55 +57,83 @@ __global__ void __launch_bounds__(256) softplus_kernel(float* __restrict__ a, in
 }
 
 struct StepParams {
-  bfvi_filter_args a;          // S = 1; experts / outputs / noise of the pass
+  bfvi_filter_args a;          // experts / outputs / noise of the pass (S chain sets)
   const float* z0_mean;
   const float* z0_log_std;
+  float* g_z0_mean;            // gradient slots of the global prior (backward)
+  float* g_z0_log_std;
   float min_std;
   int Z;
   int i;                       // step index of the pass (0 = first), t = pass_time(i)
-  // GTF heads of this step's transition, rows (b, k): pre-sigmoid gate, nonlinear, linear,
-  // pre-softplus std; null when i == 0
+  int64_t R;                   // rows = S * B * K
+  // GTF heads of this step's transition, rows (chain, k): pre-sigmoid gate, nonlinear,
+  // linear, pre-softplus std (valid when i > 0)
   const float* g; const float* nl; const float* lin; const float* as;
-  float* zrows;                // (B, K, Z) particles of step i for the next transition (nullable)
+  float* zrows;                // (R, Z) particles of step i for the next transition (nullable)
+  float* zrowsT;               // (Z, R) transposed copy for the weight-gradient GEMMs (nullable)
+  float* samplesT;             // (S, Z, T*B) transposed copy of `samples` (nullable)
+  // ---- backward ----
+  float* c_mu; float* c_sd;    // (C, Z) gradient flowing into infer(i) from the later step
+  float* d_pm; float* d_v;     // (C, Z) gradient at the prior mean, 0.5 * d_ps / ps
+  float* d_as; float* d_asT;   // (R, Z) / (Z, R) pre-activation gradients of the four GTF heads
+  float* d_g; float* d_gT;
+  float* d_lin; float* d_linT;
+  float* d_nl; float* d_nlT;
+  float* gb_std; float* gb_gate2; float* gb_lin; float* gb_nonlin2;   // bias gradient slots (Z each)
+  const float* dz;             // (R, Z) gradient at the particles of the previous step
 };
 
 __device__ __forceinline__ int gen_pass_time(int i, int T, int direction) {
   return direction == BFVI_DIR_BWD ? T - 1 - i : i;
 }
+__device__ __forceinline__ bool gen_samples(const bfvi_filter_args& a, int i) {
+  return a.sample || a.n_particles > 1 || (i == 0 && a.sample_init);      // models/dmm.py:398
+}
 
-// particles of the PREVIOUS step -> GEMM input rows (used when the step kernel did not
-// already write them, i.e. never in the current pipeline; kept for the op-level API)
-__global__ void __launch_bounds__(256) sample_rows_kernel(StepParams p, int t_src, int sampled) {
+// particles of step i_src -> GEMM input rows (+ transposed copy); the backward pass uses it
+// to regenerate what the forward step kernel wrote
+__global__ void __launch_bounds__(256) sample_rows_kernel(const __grid_constant__ StepParams p, int i_src) {
   const bfvi_filter_args& a = p.a;
-  const int Z = p.Z, K = a.n_particles;
-  const int64_t n = (int64_t)a.B * K * Z;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
+  const int t = gen_pass_time(i_src, T, a.direction);
+  const bool sampled = gen_samples(a, i_src);
+  const int64_t n = p.R * Z;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int zi = (int)(idx % Z), k = (int)((idx / Z) % K), b = (int)(idx / ((int64_t)Z * K));
-    const int64_t o = ((int64_t)t_src * a.B + b) * Z + zi;
+    const int zi = (int)(idx % Z);
+    const int64_t r = idx / Z;
+    const int k = (int)(r % K);
+    const int64_t c = r / K;
+    const int s = (int)(c / B), b = (int)(c % B);
+    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
     const float mu = a.infer_mean[o], sd = a.infer_std[o];
-    p.zrows[idx] = sampled ? fmaf(eps_at(a.noise, 0, t_src, b, k, zi, a.T, a.B, K, Z), sd, mu) : mu;
+    const float z = sampled ? fmaf(eps_at(a.noise, s, t, b, k, zi, T, B, K, Z), sd, mu) : mu;
+    p.zrows[idx] = z;
+    if (p.zrowsT != nullptr) p.zrowsT[(int64_t)zi * p.R + r] = z;
   }
 }
 
-// one filtering step for every (b, zi)
+// one filtering step for every (chain, zi)
 __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepParams p) {
   const bfvi_filter_args& a = p.a;
   const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
   const int t = gen_pass_time(p.i, T, a.direction);
-  const unsigned bits = a.set_expert_bits[0];
   const float inv_k = 1.f / (float)K;
+  const int64_t n_chains = (int64_t)a.S * B;
   float kl_sum = 0.f;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)B * Z;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chains * Z;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int zi = (int)(idx % Z), b = (int)(idx / Z);
+    const int zi = (int)(idx % Z);
+    const int64_t c = idx / Z;
+    const int s = (int)(c / B), b = (int)(c % B);
+    const unsigned bits = a.set_expert_bits[s];
     const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;      // models/dmm.py:126-127
     float pm, ps;
     if (p.i == 0) { pm = gm; ps = gs; }
     else {
       float sm = 0.f, sv = 0.f, sq = 0.f;
       for (int k = 0; k < K; ++k) {
-        const int64_t r = ((int64_t)b * K + k) * Z + zi;
+        const int64_t r = (c * K + k) * Z + zi;
         const float gate = sigmoid_f(p.g[r]);
         const float nl = p.nl[r], lin = p.lin[r];
         const float qm = fmaf(gate, nl - lin, lin);
@@ -128,13 +156,13 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepP
       if (!((bits >> e) & 1u)) continue;
       const bfvi_expert& ex = a.experts[e];
       bool m = true;
-      if (ex.mask != nullptr) m = ex.mask[t * ex.mstride_t + b * ex.mstride_b] != 0;
+      if (ex.mask != nullptr) m = ex.mask[s * ex.mstride_s + t * ex.mstride_t + b * ex.mstride_b] != 0;
       if (ex.zero_mask_last_t && t == T - 1) m = false;
       const float w = m ? 1.f : 0.f;
       float mean, std;
       if (ex.kind == BFVI_EXPERT_INV_PRIOR) { mean = gm; std = -gs; }
       else {
-        const int64_t off = t * ex.stride_t + b * ex.stride_b + zi;
+        const int64_t off = s * ex.stride_s + t * ex.stride_t + b * ex.stride_b + zi;
         mean = ex.mean[off]; std = ex.std[off];
       }
       const float te = __fmul_rn(poe_prec(std), w);
@@ -144,22 +172,278 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepP
     const float mq = __fdiv_rn(N, S);
     const float mu = (mq != mq) ? 0.f : mq;
     const float sd = __fsqrt_rn(__fdiv_rn(1.f, S));
-    const int64_t o = ((int64_t)t * B + b) * Z + zi;
+    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
     a.infer_mean[o] = mu; a.infer_std[o] = sd;
     a.prior_mean[o] = pm; a.prior_std[o] = ps;
     if (a.kl_weight != 0.f && (a.seq_mask == nullptr || a.seq_mask[t * B + b]))
       kl_sum += kld_elem_fast(mu, sd, pm, ps);
     // particles of this step: input rows of the next transition and the `samples` output
-    const bool sampled = a.sample || K > 1 || (p.i == 0 && a.sample_init);          // models/dmm.py:398
+    const bool sampled = gen_samples(a, p.i);
     float se = 0.f;
     for (int k = 0; k < K; ++k) {
-      const float z = sampled ? fmaf(eps_at(a.noise, 0, t, b, k, zi, T, B, K, Z), sd, mu) : mu;
-      if (p.zrows != nullptr) p.zrows[((int64_t)b * K + k) * Z + zi] = z;
+      const float z = sampled ? fmaf(eps_at(a.noise, s, t, b, k, zi, T, B, K, Z), sd, mu) : mu;
+      if (p.zrows != nullptr) p.zrows[(c * K + k) * Z + zi] = z;
       se += z;
     }
-    if (a.samples != nullptr) a.samples[o] = se * inv_k;
+    if (a.samples != nullptr) {
+      a.samples[o] = se * inv_k;
+      if (p.samplesT != nullptr) p.samplesT[((int64_t)s * Z + zi) * ((int64_t)T * B) + (int64_t)t * B + b] = se * inv_k;
+    }
   }
   if (a.loss_acc != nullptr && a.kl_weight != 0.f) block_reduce_add_double(kl_sum * a.kl_weight, a.loss_acc);
+}
+
+// ---------------------------------------------------------------------------------------
+// backward of one step, part 1 — everything per (chain, zi) ABOVE the transition: upstream
+// gradients, the fused KL term, the product of experts.  Writes d_pm / d_v for the particle
+// kernel (bwd_rows_kernel); expert gradients are scattered with atomics.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bwd_head_kernel(const __grid_constant__ StepParams p) {
+  const bfvi_filter_args& a = p.a;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
+  const int t = gen_pass_time(p.i, T, a.direction);
+  const int64_t n_chains = (int64_t)a.S * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chains * Z;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int zi = (int)(idx % Z);
+    const int64_t c = idx / Z;
+    const int s = (int)(c / B), b = (int)(c % B);
+    const unsigned bits = a.set_expert_bits[s];
+    const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
+    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
+    const float mu = a.infer_mean[o], sd = a.infer_std[o], pm = a.prior_mean[o], ps = a.prior_std[o];
+    float d_mu = p.c_mu[idx] + (a.d_infer_mean ? a.d_infer_mean[o] : 0.f);
+    float d_sd = p.c_sd[idx] + (a.d_infer_std ? a.d_infer_std[o] : 0.f);
+    float d_pm = a.d_prior_mean ? a.d_prior_mean[o] : 0.f;
+    float d_ps = a.d_prior_std ? a.d_prior_std[o] : 0.f;
+    float d_gm = 0.f, d_gs = 0.f;
+    if (a.d_samples != nullptr) {                         // samples = mean_k (mu + eps_k sd)
+      const float ds = a.d_samples[o];
+      d_mu += ds;
+      if (gen_samples(a, p.i)) {
+        float me = 0.f;
+        for (int k = 0; k < K; ++k) me += eps_at(a.noise, s, t, b, k, zi, T, B, K, Z);
+        d_sd = fmaf(ds, me / (float)K, d_sd);
+      }
+    }
+    if (a.kl_weight != 0.f && (a.seq_mask == nullptr || a.seq_mask[t * B + b])) {
+      float g1, g2, g3, g4;
+      kld_elem_grad(mu, sd, pm, ps, a.kl_weight, g1, g2, g3, g4);
+      d_mu += g1; d_sd += g2; d_pm += g3; d_ps += g4;
+    }
+    // product of experts backward (models/dgts.py:40-51)
+    const float inv_s = sd * sd;
+    const float d_n = d_mu * inv_s;
+    const float d_s = -d_mu * mu * inv_s - 0.5f * d_sd * sd * inv_s;
+    {
+      const float tp = poe_prec(ps);
+      d_pm += d_n * tp;
+      d_ps += (d_n * pm + d_s) * poe_prec_grad(ps, tp);
+    }
+    for (int e = 0; e < a.n_experts; ++e) {
+      if (!((bits >> e) & 1u)) continue;
+      const bfvi_expert& ex = a.experts[e];
+      bool m = true;
+      if (ex.mask != nullptr) m = ex.mask[s * ex.mstride_s + t * ex.mstride_t + b * ex.mstride_b] != 0;
+      if (ex.zero_mask_last_t && t == T - 1) m = false;
+      if (!m) continue;
+      if (ex.kind == BFVI_EXPERT_INV_PRIOR) {
+        const float std = -gs, te = poe_prec(std);
+        d_gm += d_n * te;
+        d_gs -= (d_n * gm + d_s) * poe_prec_grad(std, te);
+      } else if (ex.d_mean != nullptr) {
+        const int64_t off = s * ex.stride_s + t * ex.stride_t + b * ex.stride_b + zi;
+        const float mean = ex.mean[off], std = ex.std[off], te = poe_prec(std);
+        atomicAdd(ex.d_mean + off, d_n * te);
+        atomicAdd(ex.d_std + off, (d_n * mean + d_s) * poe_prec_grad(std, te));
+      }
+    }
+    if (p.i == 0) { d_gm += d_pm; d_gs += d_ps; }          // the first prior is the global prior
+    else { p.d_pm[idx] = d_pm; p.d_v[idx] = d_ps * 0.5f / ps; }
+    if (d_gm != 0.f) atomicAdd(p.g_z0_mean + zi, d_gm);
+    if (d_gs != 0.f) atomicAdd(p.g_z0_log_std + zi, d_gs * expf(p.z0_log_std[zi]));
+  }
+}
+
+// backward of one step, part 2 — per particle row: mixture moment matching, the product
+// with the global prior and the four GTF heads (gate sigmoid, mean mix, softplus std).
+// Thread = one latent component zi walking a chunk of rows (coalesced along zi); writes the
+// pre-activation gradients and their transposed copies, accumulates bias gradients.
+constexpr int kRowsPerBlock = 32;
+__global__ void __launch_bounds__(128) bwd_rows_kernel(const __grid_constant__ StepParams p) {
+  const bfvi_filter_args& a = p.a;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
+  const int zi = blockIdx.y * blockDim.x + threadIdx.x;
+  if (zi >= Z) return;
+  const int t = gen_pass_time(p.i, T, a.direction);
+  const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
+  const float inv_k = 1.f / (float)K;
+  float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * kRowsPerBlock;
+  const int64_t r1 = r0 + kRowsPerBlock < p.R ? r0 + kRowsPerBlock : p.R;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int64_t c = r / K;
+    const int s = (int)(c / B), b = (int)(c % B);
+    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
+    const float pm = a.prior_mean[o];
+    const float d_pm = p.d_pm[c * Z + zi], d_v = p.d_v[c * Z + zi];
+    const int64_t q = r * Z + zi;
+    const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q], as = p.as[q];
+    const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(as) + p.min_std;
+    float m_k, s_k, g_gm, g_gs, d_qm, d_qs;
+    poe2_forward(gm, gs, qm, qs, m_k, s_k);
+    const float d_mk = (d_pm + 2.f * d_v * (m_k - pm)) * inv_k;      // models/dgts.py:78-83
+    const float d_sk = 2.f * d_v * s_k * inv_k;
+    poe2_backward(gm, gs, qm, qs, m_k, s_k, d_mk, d_sk, g_gm, g_gs, d_qm, d_qs);
+    d_gm += g_gm; d_gs += g_gs;
+    const float d_as = d_qs * softplus_grad(as);
+    const float d_nl = d_qm * gate;
+    const float d_lin = d_qm - d_nl;                                   // d_qm * (1 - gate)
+    const float d_g = d_lin * gate * (nl - lin);                       // through the sigmoid
+    p.d_as[q] = d_as; p.d_g[q] = d_g; p.d_lin[q] = d_lin; p.d_nl[q] = d_nl;
+    const int64_t qt = (int64_t)zi * p.R + r;
+    p.d_asT[qt] = d_as; p.d_gT[qt] = d_g; p.d_linT[qt] = d_lin;
+    b_s += d_as; b_g += d_g; b_l += d_lin; b_n += d_nl;
+  }
+  atomicAdd(p.gb_std + zi, b_s); atomicAdd(p.gb_gate2 + zi, b_g);
+  atomicAdd(p.gb_lin + zi, b_l); atomicAdd(p.gb_nonlin2 + zi, b_n);
+  if (d_gm != 0.f) atomicAdd(p.g_z0_mean + zi, d_gm);
+  if (d_gs != 0.f) atomicAdd(p.g_z0_log_std + zi, d_gs * expf(p.z0_log_std[zi]));
+}
+
+// backward of one step, part 3 — particles of the previous step back to its (mu, sd):
+// c_mu = sum_k dz, c_sd = sum_k dz * eps   (z = mu + eps * sd)
+__global__ void __launch_bounds__(128) bwd_carry_kernel(const __grid_constant__ StepParams p, int i_prev) {
+  const bfvi_filter_args& a = p.a;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
+  const int t = gen_pass_time(i_prev, T, a.direction);
+  const bool sampled = gen_samples(a, i_prev);
+  const int64_t n_chains = (int64_t)a.S * B;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chains * Z;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int zi = (int)(idx % Z);
+    const int64_t c = idx / Z;
+    const int s = (int)(c / B), b = (int)(c % B);
+    float cm = 0.f, cs = 0.f;
+    for (int k = 0; k < K; ++k) {
+      const float d = p.dz[(c * K + k) * Z + zi];
+      cm += d;
+      if (sampled) cs = fmaf(d, eps_at(a.noise, s, t, b, k, zi, T, B, K, Z), cs);
+    }
+    p.c_mu[idx] = cm; p.c_sd[idx] = cs;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// GaussianMLP heads
+// ---------------------------------------------------------------------------------------
+// decoder: Gaussian NLL forward + backward at the heads (models/losses.py:68-89).  In place:
+// mean -> d_mean, stdpre -> d_stdpre (gradient at the pre-softplus std), transposed copies
+// for the weight gradients, bias gradients.  Thread = one feature d walking a chunk of rows.
+struct HeadParams {
+  float* mean; float* stdpre;        // (n_rows, D) in: values; out: gradients
+  float* meanT; float* stdpreT;      // (D, n_rows) transposed gradients
+  const float* target;               // decoder: (n_rows, D), NaN = unobserved
+  const uint8_t* row_mask;           // decoder: (n_rows) nullable
+  const float* d_mean_in; const float* d_std_in;   // encoder: upstream gradients (n_rows, D)
+  float* gb_mean; float* gb_std;     // bias gradient slots (D each)
+  int64_t n_rows;
+  int D;
+  float weight;
+  double* loss_acc;
+};
+__global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ HeadParams p) {
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  float loss = 0.f, b_m = 0.f, b_s = 0.f;
+  if (d < p.D) {
+    const int64_t r0 = (int64_t)blockIdx.x * kRowsPerBlock;
+    const int64_t r1 = r0 + kRowsPerBlock < p.n_rows ? r0 + kRowsPerBlock : p.n_rows;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t q = r * p.D + d;
+      const float a_s = p.stdpre[q];
+      float d_m = 0.f, d_p = 0.f;
+      if (p.target != nullptr) {                      // decoder + NLL
+        const float xt = p.target[q];
+        if (xt == xt && (p.row_mask == nullptr || p.row_mask[r] != 0)) {
+          const float mean = p.mean[q], std = softplus_f(a_s) + kMlpMinStd;
+          loss += nll_gauss_elem(mean, std, xt);
+          float g_std;
+          nll_gauss_elem_grad(mean, std, xt, p.weight, d_m, g_std);
+          d_p = g_std * softplus_grad(a_s);
+        }
+      } else {                                        // encoder: chain rule through the softplus
+        d_m = p.d_mean_in[q];
+        d_p = p.d_std_in[q] * softplus_grad(a_s);
+      }
+      p.mean[q] = d_m; p.stdpre[q] = d_p;
+      p.meanT[(int64_t)d * p.n_rows + r] = d_m; p.stdpreT[(int64_t)d * p.n_rows + r] = d_p;
+      b_m += d_m; b_s += d_p;
+    }
+    atomicAdd(p.gb_mean + d, b_m); atomicAdd(p.gb_std + d, b_s);
+  }
+  if (p.loss_acc != nullptr) block_reduce_add_double(loss * p.weight, p.loss_acc);
+}
+
+// plain 2-D transpose (rows x cols) -> (cols x rows), used for per-step weight transposes
+// and the encoder inputs
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t rows, int cols,
+                                                        float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t r = r0 + tx;
+    if (r < rows && c < cols) out[(int64_t)c * rows + r] = tile[tx][j];
+  }
+}
+
+// prior-matching term (models/dmm.py:496-501,541-545), one direction: moments of the K
+// propagated particles of the global prior, KL(global || next), and its gradient wired into
+// the same d_pm / d_v slots bwd_rows_kernel reads (a single chain, no experts)
+struct MatchHeadParams {
+  const float* z0_mean; const float* z0_log_std; float* g_z0_mean; float* g_z0_log_std;
+  const float* g; const float* nl; const float* lin; const float* as;   // (K, Z) GTF heads
+  float* pm; float* d_pm; float* d_v;                                    // (Z)
+  float min_std, coef_static;
+  const float* count;      // device scalar mask.sum() (nullable)
+  double* loss_acc;
+  int K, Z, with_grad;
+};
+__global__ void __launch_bounds__(128) match_head_kernel(const __grid_constant__ MatchHeadParams p) {
+  const int zi = blockIdx.x * blockDim.x + threadIdx.x;
+  float kl = 0.f;
+  if (zi < p.Z) {
+    const float coef = p.coef_static * (p.count != nullptr ? p.count[0] : 1.f);
+    const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
+    float sm = 0.f, sv = 0.f, sq = 0.f;
+    for (int k = 0; k < p.K; ++k) {
+      const int64_t q = (int64_t)k * p.Z + zi;
+      const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q];
+      const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(p.as[q]) + p.min_std;
+      float m_k, s_k;
+      poe2_forward(gm, gs, qm, qs, m_k, s_k);
+      sm += m_k; sv = fmaf(s_k, s_k, sv); sq = fmaf(m_k, m_k, sq);
+    }
+    const float inv_k = 1.f / (float)p.K;
+    const float nm = sm * inv_k, ns = sqrtf(sv * inv_k + (sq * inv_k - nm * nm));
+    kl = coef * kld_elem(gm, gs, nm, ns);
+    if (p.with_grad) {
+      float g1, g2, d_nm, d_ns;
+      kld_elem_grad(gm, gs, nm, ns, coef, g1, g2, d_nm, d_ns);
+      p.pm[zi] = nm; p.d_pm[zi] = d_nm; p.d_v[zi] = d_ns * 0.5f / ns;
+      atomicAdd(p.g_z0_mean + zi, g1);
+      atomicAdd(p.g_z0_log_std + zi, g2 * expf(p.z0_log_std[zi]));
+    }
+  }
+  if (p.loss_acc != nullptr) block_reduce_add_double(kl, p.loss_acc);
 }
 
 }  // namespace gen

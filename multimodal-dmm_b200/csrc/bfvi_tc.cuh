@@ -38,13 +38,22 @@ constexpr int kThreads = 128;
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
 struct GemmParams {
-  const float* A; int64_t lda;      // [M, K] row-major
-  const float* W; int64_t ldw;      // [N, K] row-major (nn.Linear weight)
-  const float* bias;                // [N] or null
+  // C[M,N] = A[M,K] · W[N,K]^T: both operands K-major.  Forward and input-gradient layers use
+  // it directly; a weight gradient dW = dY^T X is the same form on the TRANSPOSED copies
+  // dY^T [out, rows], X^T [in, rows] that the producing kernels write next to dY and X.
+  const float* A; int64_t lda;
+  const float* W; int64_t ldw;
+  const float* bias;                // [N] or null, added before the activation
   float* C; int64_t ldc;            // [M, N] row-major
   int64_t M;
-  int N, K;
-  int act;
+  int N;
+  int64_t K;
+  int act;                          // ACT_*
+  int accumulate;                   // C += result instead of C = result
+  float* Ct; int64_t ldct;          // optional transposed copy of the result: Ct[n][m]  (nullable)
+  const float* mask_aux;            // epilogue: result *= (mask_aux[m][n] > 0)  (ReLU backward), nullable
+  int64_t ldaux;
+  float* colsum;                    // epilogue: colsum[n] += sum_m result[m][n] (bias gradients), nullable
 };
 enum { PREC_TF32X3 = 0, PREC_TF32 = 1 };   // operand precision of the large-dim family
 
@@ -126,12 +135,14 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // thread t owns 16-byte vectors v = t, t + 128, ... of the chunk; vector v = (row v % ROWS, k4 v / ROWS)
 template <int ROWS>
 __device__ __forceinline__ void load_chunk(const float* __restrict__ P, int64_t ld, int64_t row0, int64_t n_rows,
-                                           int k0, int K, bool vec_ok, float4 (&reg)[ROWS * 8 / kThreads]) {
+                                           int64_t k0, int64_t K, bool vec_ok,
+                                           float4 (&reg)[ROWS * 8 / kThreads]) {
   constexpr int NV = ROWS * 8 / kThreads;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int v = threadIdx.x + i * kThreads;
-    const int r = v % ROWS, k = k0 + (v / ROWS) * 4;
+    const int r = v % ROWS;
+    const int64_t k = k0 + (v / ROWS) * 4;
     const int64_t row = row0 + r;
     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < n_rows && k < K) {
@@ -210,35 +221,40 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 
   const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
   const bool w_vec = (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
-  const int n_chunks = (p.K + kBK - 1) / kBK;
+  const int n_chunks = (int)((p.K + kBK - 1) / kBK);
   const uint32_t idesc = umma_idesc_tf32(kBM, BN);
   float4 ra[kBM * 8 / kThreads], rw[BN * 8 / kThreads];
+  auto load_ab = [&](int chunk) {
+    load_chunk<kBM>(p.A, p.lda, row0, p.M, (int64_t)chunk * kBK, p.K, a_vec, ra);
+    load_chunk<BN>(p.W, p.ldw, col0, p.N, (int64_t)chunk * kBK, p.K, w_vec, rw);
+  };
+  auto store_ab = [&](int s) {
+    store_chunk<kBM>(sA[s], sAl[s], ra);
+    store_chunk<BN>(sW[s], sWl[s], rw);
+  };
+  // per MMA k-step (8 floats of K) the operands advance by two 16-byte K vectors of ROWS rows
+  constexpr uint32_t kStepA = 2 * kBM * 16, kStepW = 2 * BN * 16, kLboA = kBM * 16, kLboW = BN * 16;
 
-  load_chunk<kBM>(p.A, p.lda, row0, p.M, 0, p.K, a_vec, ra);
-  load_chunk<BN>(p.W, p.ldw, col0, p.N, 0, p.K, w_vec, rw);
-  store_chunk<kBM>(sA[0], sAl[0], ra);
-  store_chunk<BN>(sW[0], sWl[0], rw);
+  load_ab(0);
+  store_ab(0);
   fence_async_smem();
   __syncthreads();
 
   uint32_t phase[2] = {0u, 0u};
   for (int i = 0; i < n_chunks; ++i) {
     const int s = i & 1;
-    if (i + 1 < n_chunks) {                       // global loads of the next chunk fly during the MMAs
-      load_chunk<kBM>(p.A, p.lda, row0, p.M, (i + 1) * kBK, p.K, a_vec, ra);
-      load_chunk<BN>(p.W, p.ldw, col0, p.N, (i + 1) * kBK, p.K, w_vec, rw);
-    }
+    if (i + 1 < n_chunks) load_ab(i + 1);         // global loads of the next chunk fly during the MMAs
     if (threadIdx.x == 0) {
       tc_fence_after();
       const uint32_t a0 = smem_u32(sA[s]), w0 = smem_u32(sW[s]);
 #pragma unroll
       for (int j = 0; j < kBK / 8; ++j) {         // one MMA consumes K = 8 floats = two 16-byte K vectors
-        const uint64_t da = umma_desc(a0 + j * 2 * kBM * 16, kBM * 16, 128);
-        const uint64_t dw = umma_desc(w0 + j * 2 * BN * 16, BN * 16, 128);
+        const uint64_t da = umma_desc(a0 + j * kStepA, kLboA, 128);
+        const uint64_t dw = umma_desc(w0 + j * kStepW, kLboW, 128);
         umma_tf32(tmem_d, da, dw, idesc, (i > 0 || j > 0) ? 1u : 0u);
         if (SPLIT) {
-          const uint64_t dal = umma_desc(smem_u32(sAl[s]) + j * 2 * kBM * 16, kBM * 16, 128);
-          const uint64_t dwl = umma_desc(smem_u32(sWl[s]) + j * 2 * BN * 16, BN * 16, 128);
+          const uint64_t dal = umma_desc(smem_u32(sAl[s]) + j * kStepA, kLboA, 128);
+          const uint64_t dwl = umma_desc(smem_u32(sWl[s]) + j * kStepW, kLboW, 128);
           umma_tf32(tmem_d, dal, dw, idesc, 1u);
           umma_tf32(tmem_d, da, dwl, idesc, 1u);
         }
@@ -247,8 +263,7 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
     }
     if (i + 1 < n_chunks) {
       if (i >= 1) { mbar_wait(&mbar[s ^ 1], phase[s ^ 1]); phase[s ^ 1] ^= 1u; }   // chunk i-1 done with its stage
-      store_chunk<kBM>(sA[s ^ 1], sAl[s ^ 1], ra);
-      store_chunk<BN>(sW[s ^ 1], sWl[s ^ 1], rw);
+      store_ab(s ^ 1);
       fence_async_smem();
       __syncthreads();
     }
@@ -260,20 +275,30 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 
   // epilogue: warp w owns accumulator rows (TMEM lanes) 32w .. 32w+31
   const int64_t row = row0 + warp * 32 + lane;
+  const bool row_ok = row < p.M;
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
+    if (col0 + c >= p.N) break;
     float v[32];
     tmem_ld32(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-    if (row < p.M) {
-      float* dst = p.C + row * p.ldc + col0 + c;
+    float* dst = p.C + row * p.ldc + col0 + c;
+    const float* aux = p.mask_aux != nullptr ? p.mask_aux + row * p.ldaux + col0 + c : nullptr;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = col0 + c + j;
-        if (col < p.N) {
-          float x = v[j] + (p.bias != nullptr ? p.bias[col] : 0.f);
-          if (p.act == ACT_RELU) x = x < 0.f ? 0.f : x;
-          dst[j] = x;
-        }
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + c + j;
+      float x = 0.f;
+      if (row_ok && col < p.N) {
+        x = v[j] + (p.bias != nullptr ? p.bias[col] : 0.f);
+        if (p.act == ACT_RELU) x = x < 0.f ? 0.f : x;
+        if (aux != nullptr) x = aux[j] > 0.f ? x : 0.f;
+        const float y = p.accumulate ? dst[j] + x : x;
+        dst[j] = y;
+        if (p.Ct != nullptr) p.Ct[(int64_t)col * p.ldct + row] = y;     // lanes = consecutive rows: coalesced
+      }
+      if (p.colsum != nullptr) {                  // column sums of THIS product over the tile's rows (bias gradients)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && col < p.N) atomicAdd(p.colsum + col, x);
       }
     }
   }
@@ -286,13 +311,21 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 // CPU stand-in used only by the SIMT-emulator test build (exact fp32, no TF32 rounding)
 #ifdef BFVI_EMU
 inline void gemm_reference_emu(const GemmParams& p) {
-  for (int64_t m = 0; m < p.M; ++m)
-    for (int n = 0; n < p.N; ++n) {
-      float acc = p.bias ? p.bias[n] : 0.f;
-      for (int k = 0; k < p.K; ++k) acc = fmaf(p.A[m * p.lda + k], p.W[(int64_t)n * p.ldw + k], acc);
+  for (int n = 0; n < p.N; ++n) {
+    float cs = 0.f;
+    for (int64_t m = 0; m < p.M; ++m) {
+      float acc = 0.f;
+      for (int64_t k = 0; k < p.K; ++k) acc = fmaf(p.A[m * p.lda + k], p.W[(int64_t)n * p.ldw + k], acc);
+      acc += p.bias ? p.bias[n] : 0.f;
       if (p.act == ACT_RELU) acc = acc < 0.f ? 0.f : acc;
+      if (p.mask_aux != nullptr) acc = p.mask_aux[m * p.ldaux + n] > 0.f ? acc : 0.f;
+      cs += acc;
+      acc = p.accumulate ? p.C[m * p.ldc + n] + acc : acc;
       p.C[m * p.ldc + n] = acc;
+      if (p.Ct != nullptr) p.Ct[(int64_t)n * p.ldct + m] = acc;
     }
+    if (p.colsum != nullptr) p.colsum[n] += cs;
+  }
 }
 #endif
 

@@ -288,8 +288,8 @@ class MultiDMM(MultiDGTS):
     @property
     def fused_step_available(self):
         self._ensure_flat()
-        return (self._family == 1 and all(self._default_enc(m) and self._default_dec(m)
-                                          for m in self.modalities))
+        return (self._family in (1, 2) and all(self._default_enc(m) and self._default_dec(m)
+                                               for m in self.modalities))
 
     # ------------------------------------------------------------- reference API
     def prior(self, shape):

@@ -36,3 +36,27 @@ def test_forward_with_a_dropped_modality(lib):
     assert set(ours[2]) == {'m0', 'm1', 'm2'}                 # every decoder runs, models/dmm.py:207
     bad = helpers.compare_forward(ours, ref, rtol=2e-4, atol=2e-5)
     assert not bad, bad
+
+
+from conftest import golden_names, load_golden, rel_err
+
+SMALL = [n for n in golden_names() if n != 'medium_dims']
+
+
+@pytest.mark.parametrize('name', SMALL)
+def test_training_step_of_the_large_family_on_golden_fixtures(lib, name, monkeypatch):
+    """BFVI_FAMILY=2 routes the small golden models through the large-dim launch sequence
+    (GEMMs + elementwise kernels): loss and every parameter gradient must match the reference."""
+    monkeypatch.setenv('BFVI_FAMILY', '2')
+    fx = load_golden(name)
+    loss, grads, launches = helpers.run_step(lib, fx, 'cpu')
+    assert launches > 0
+    ref = fx['ref_loss_fp64']
+    assert abs(loss - ref) / abs(ref) < 1e-4, (loss, ref)
+    n = float(sum(fx['lengths']))
+    for k, g_ref in fx['ref_grads_fp64'].items():
+        g = grads[k] / n
+        if g_ref.norm() == 0:
+            assert g.norm() == 0, k
+        else:
+            assert rel_err(g, g_ref) < 1e-3, (k, rel_err(g, g_ref))

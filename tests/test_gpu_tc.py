@@ -63,3 +63,31 @@ def test_linear_tf32_argument_errors():
         lib.call('bfvi_linear_tf32', _lib.ptr(x), 2, _lib.ptr(x), 4, None, _lib.ptr(x), 4, 4, 4, 4, 0, None)
     with pytest.raises(_lib.BfviError):
         lib.call('bfvi_linear_tf32', _lib.ptr(x), 4, _lib.ptr(x), 4, None, _lib.ptr(x), 4, 4, 4, 4, 7, None)
+
+
+@pytest.mark.parametrize('shape', [(256, 64, 64), (1000, 512, 64), (77, 20, 40), (4096, 64, 512), (333, 16, 512),
+                                   (50, 5, 3)])
+def test_wgrad_tf32_matches_reference(shape):
+    """dW (+)= dY^T X from the transposed copies (contraction over the rows)."""
+    lib = _lib.load()
+    rows, n_out, n_in = shape
+    g = torch.Generator(device='cuda').manual_seed(rows + n_out)
+    dy = torch.randn(rows, n_out, device='cuda', generator=g)
+    x = torch.randn(rows, n_in, device='cuda', generator=g)
+    dw0 = torch.randn(n_out, n_in, device='cuda', generator=g)
+    dy_t, x_t = dy.t().contiguous(), x.t().contiguous()
+    exact = dy.double().t() @ x.double()
+    scale = exact.abs().max().item()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for flags, tol in ((0, 3e-6 + 2e-8 * rows), (16, 5e-3)):      # tensor-core accumulation error grows with K
+        dw = dw0.clone()
+        lib.call('bfvi_wgrad_tf32', _lib.ptr(dy_t), rows, _lib.ptr(x_t), rows, _lib.ptr(dw), n_in, rows, n_out,
+                 n_in, 1, flags, st)
+        torch.cuda.synchronize()
+        err = (dw.double() - dw0.double() - exact).abs().max().item()
+        assert err < tol * scale, (flags, err, scale)
+        dw2 = torch.full_like(dw0, float('nan'))
+        lib.call('bfvi_wgrad_tf32', _lib.ptr(dy_t), rows, _lib.ptr(x_t), rows, _lib.ptr(dw2), n_in, rows, n_out,
+                 n_in, 0, flags, st)
+        torch.cuda.synchronize()
+        assert (dw2.double() - exact).abs().max().item() < tol * scale
