@@ -387,7 +387,8 @@ int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
   auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
   const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN));
+  const unsigned gz = gp.k_split > 0 ? (unsigned)((gp.K + gp.k_split - 1) / gp.k_split) : 1u;
+  const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN), gz);
   k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
 #endif
   BFVI_CHECK_CUDA();
@@ -404,6 +405,21 @@ int dispatch_gemm_bn(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
 
 int gemm_tc(const bfvi::tc::GemmParams& gp, int prec, cudaStream_t st) {
   return prec == bfvi::tc::PREC_TF32 ? dispatch_gemm_bn<false>(gp, st) : dispatch_gemm_bn<true>(gp, st);
+}
+
+// Split of the (long) contraction over the rows of a weight-gradient GEMM: the output has only a
+// few 128 x BN tiles, so K is cut into enough slices to put ~2 CTAs on every SM (slices are a
+// multiple of the 32-float stage and at least 256 long).
+int64_t wgrad_k_split(int64_t rows, int n_out, int n_in) {
+  const int bn = n_in <= 32 ? 32 : n_in <= 64 ? 64 : n_in <= 128 ? 128 : 256;
+  const int64_t tiles = ((n_out + 127) / 128) * (int64_t)((n_in + bn - 1) / bn);
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  int64_t slices = (2 * sms + tiles - 1) / tiles;
+  if (slices < 1) slices = 1;
+  int64_t len = (rows + slices - 1) / slices;
+  len = (len + 31) / 32 * 32;
+  if (len < 256) len = 256;
+  return len >= rows ? 0 : len;
 }
 
 // y = act(x W^T + b) on tcgen05; prec: PREC_TF32X3 (error-compensated) or PREC_TF32
@@ -554,6 +570,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     memset(&gp, 0, sizeof(gp));
     gp.A = dyT; gp.lda = rows; gp.W = xT; gp.ldw = rows;
     gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_out; gp.N = n_in; gp.K = rows; gp.accumulate = 1;
+    gp.k_split = wgrad_k_split(rows, n_out, n_in);
     return gemm(gp);
   };
   auto transpose = [&](const float* in, int64_t rows, int cols, float* out) {
@@ -1148,6 +1165,7 @@ int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
   memset(&gp, 0, sizeof(gp));
   gp.A = dy; gp.lda = lddy; gp.W = x; gp.ldw = ldx; gp.C = dw; gp.ldc = lddw;
   gp.M = n_out; gp.N = n_in; gp.K = n_rows; gp.accumulate = accumulate ? 1 : 0;
+  if (accumulate) gp.k_split = wgrad_k_split(n_rows, n_out, n_in);
   return gemm_tc(gp, (flags >> 4) & 1, (cudaStream_t)stream);
 }
 

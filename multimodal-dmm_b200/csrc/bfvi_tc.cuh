@@ -51,6 +51,9 @@ struct GemmParams {
   int act;                          // ACT_*
   int accumulate;                   // C += result instead of C = result
   float* Ct; int64_t ldct;          // optional transposed copy of the result: Ct[n][m]  (nullable)
+  int64_t k_split;                  // > 0: blockIdx.z owns K range [z * k_split, (z+1) * k_split) and ADDS its
+                                    // partial tile into C with atomics (weight gradients: few output tiles,
+                                    // long contraction over the rows); requires accumulate semantics
   const float* mask_aux;            // epilogue: result *= (mask_aux[m][n] > 0)  (ReLU backward), nullable
   int64_t ldaux;
   float* colsum;                    // epilogue: colsum[n] += sum_m result[m][n] (bias gradients), nullable
@@ -221,12 +224,14 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 
   const bool a_vec = (p.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.A) & 15) == 0);
   const bool w_vec = (p.ldw % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
-  const int n_chunks = (int)((p.K + kBK - 1) / kBK);
+  const int64_t k_begin = p.k_split > 0 ? (int64_t)blockIdx.z * p.k_split : 0;
+  const int64_t k_end = p.k_split > 0 ? (k_begin + p.k_split < p.K ? k_begin + p.k_split : p.K) : p.K;
+  const int n_chunks = (int)((k_end - k_begin + kBK - 1) / kBK);
   const uint32_t idesc = umma_idesc_tf32(kBM, BN);
   float4 ra[kBM * 8 / kThreads], rw[BN * 8 / kThreads];
   auto load_ab = [&](int chunk) {
-    load_chunk<kBM>(p.A, p.lda, row0, p.M, (int64_t)chunk * kBK, p.K, a_vec, ra);
-    load_chunk<BN>(p.W, p.ldw, col0, p.N, (int64_t)chunk * kBK, p.K, w_vec, rw);
+    load_chunk<kBM>(p.A, p.lda, row0, p.M, k_begin + (int64_t)chunk * kBK, k_end, a_vec, ra);
+    load_chunk<BN>(p.W, p.ldw, col0, p.N, k_begin + (int64_t)chunk * kBK, k_end, w_vec, rw);
   };
   auto store_ab = [&](int s) {
     store_chunk<kBM>(sA[s], sAl[s], ra);
@@ -291,9 +296,13 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
         x = v[j] + (p.bias != nullptr ? p.bias[col] : 0.f);
         if (p.act == ACT_RELU) x = x < 0.f ? 0.f : x;
         if (aux != nullptr) x = aux[j] > 0.f ? x : 0.f;
-        const float y = p.accumulate ? dst[j] + x : x;
-        dst[j] = y;
-        if (p.Ct != nullptr) p.Ct[(int64_t)col * p.ldct + row] = y;     // lanes = consecutive rows: coalesced
+        if (p.k_split > 0) {
+          atomicAdd(dst + j, x);                                          // split-K partial tile
+        } else {
+          const float y = p.accumulate ? dst[j] + x : x;
+          dst[j] = y;
+          if (p.Ct != nullptr) p.Ct[(int64_t)col * p.ldct + row] = y;   // lanes = consecutive rows: coalesced
+        }
       }
       if (p.colsum != nullptr) {                  // column sums of THIS product over the tile's rows (bias gradients)
 #pragma unroll
