@@ -88,6 +88,11 @@ def make_c2_batch(b_dim, t_max=T_MAX, seed=1):
     return inputs, targets, mask, lengths
 
 
+def workload_name(b_dim):
+    return ('C2: spirals BFVI step, M=2 D=1 Z=5 H=20, T=%d, B=%d per GPU, 50%% uniform missing + 10%% burst, '
+            'K=%d, K_match=%d' % (T_MAX, b_dim, K_TRAIN, K_MATCH))
+
+
 REC_MULTS = {m: 1.0 for m in MODS}          # (1/D)/M * 1/(1-0.5), spirals.py:64-73
 KLD_MULT = 1.0
 
@@ -176,7 +181,8 @@ def run_reference(args):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
         'data': 'synthetic',
-        'config': {'workload': 'C2 spirals BFVI, 50%% missing, T=100 (reference CPU sample B=%d)' % b_dim},
+        'config': {'workload': workload_name(B_PER_GPU), 'global_batch': B_PER_GPU * args.gpus, 'seq_len': T_MAX,
+                   'parallelism': 'cpu', 'reference_sample_batch': b_dim},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
@@ -366,9 +372,7 @@ def main():
             'metric': METRIC, 'value': seq_ts_global / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': 'C2: spirals BFVI step, M=2 D=1 Z=5 H=20, T=%d, B=%d per GPU, 50%% '
-                                   'uniform missing + 10%% burst, K=%d, K_match=%d, in-kernel Philox noise'
-                                   % (T_MAX, b_dim, K_TRAIN, K_MATCH),
+            'config': {'workload': workload_name(b_dim),
                        'global_batch': b_dim * world, 'seq_len': T_MAX,
                        'parallelism': 'dp%d' % world,
                        'l2': '256 MiB flush write between timed steps; the step itself streams a '
