@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BFVI_VERSION 100 /* 0.1.0 */
+#define BFVI_VERSION 110 /* 0.1.1: large-dim (tcgen05) family entry points */
 
 #define BFVI_MAX_MODS 16
 #define BFVI_MAX_SETS (BFVI_MAX_MODS + 1)
@@ -147,6 +147,10 @@ typedef struct bfvi_filter_args {
   const float* d_infer_mean; const float* d_infer_std;
   const float* d_prior_mean; const float* d_prior_std;
   const float* d_samples;
+  /* scratch of the large-dim (tcgen05) family, bfvi_filter_workspace() bytes, 256-byte
+   * aligned device memory; unused (may be NULL) for the small-dim family */
+  void* workspace;
+  size_t workspace_bytes;
 } bfvi_filter_args;
 
 /* Arguments of one MultiDMM.step (models/dmm.py:503-554) as driven by
@@ -217,6 +221,7 @@ int bfvi_decode_nll(const bfvi_model* model, const float* params, float* grads,
  * forward outputs in `args` plus the upstream gradients; it accumulates the
  * transition / prior gradients into `grads` and expert gradients into
  * experts[e].d_mean / d_std. */
+int bfvi_filter_workspace(const bfvi_model* model, const bfvi_filter_args* args, size_t* bytes);
 int bfvi_filter_fwd(const bfvi_model* model, const float* params,
                     const bfvi_filter_args* args, void* stream);
 int bfvi_filter_bwd(const bfvi_model* model, const float* params, float* grads,

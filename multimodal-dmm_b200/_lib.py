@@ -73,7 +73,8 @@ class FilterArgs(C.Structure):
                 ('seq_mask', C.c_void_p), ('kl_weight', C.c_float), ('loss_acc', C.c_void_p),
                 ('d_infer_mean', C.c_void_p), ('d_infer_std', C.c_void_p),
                 ('d_prior_mean', C.c_void_p), ('d_prior_std', C.c_void_p),
-                ('d_samples', C.c_void_p)]
+                ('d_samples', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 
 
 class StepArgs(C.Structure):
@@ -123,6 +124,7 @@ SYMBOLS = {
     'bfvi_decode_nll': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    'bfvi_filter_workspace': (C.c_int, [C.POINTER(Model), C.POINTER(FilterArgs), C.POINTER(C.c_size_t)]),
     'bfvi_filter_fwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.POINTER(FilterArgs), C.c_void_p]),
     'bfvi_filter_bwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(FilterArgs),
                                   C.c_void_p]),

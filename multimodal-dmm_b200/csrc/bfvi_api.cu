@@ -452,19 +452,26 @@ struct LargePlan {
   size_t hdec, hdecT, dhd, dhdT, dmean, dstd, dmeanT, dstdT;
 };
 
-int plan_large(const bfvi_model* m, const bfvi_step_args* a, LargePlan* pl) {
+// `fonly` != null plans the workspace of a stand-alone z_filter call (bfvi_filter_fwd / _bwd of the
+// large-dim family): only the per-step row scratch, the chain scratch and the transposed weights.
+int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_args* fonly, LargePlan* pl) {
   const int M = m->n_mods, Z = m->z_dim, H = m->h_dim;
+  const int T = fonly ? fonly->T : a->T, B = fonly ? fonly->B : a->B;
   int S = 0;
-  if (M > 1) pl->set_bits[S++] = (M >= 32) ? 0xffffffffu : ((1u << M) - 1u);
-  if (a->uni_loss)
-    for (int i = 0; i < M; ++i) pl->set_bits[S++] = 1u << i;
+  if (fonly) {
+    S = fonly->S;
+  } else {
+    if (M > 1) pl->set_bits[S++] = (M >= 32) ? 0xffffffffu : ((1u << M) - 1u);
+    if (a->uni_loss)
+      for (int i = 0; i < M; ++i) pl->set_bits[S++] = 1u << i;
+  }
   pl->S = S;
-  pl->k_b = a->train_particles;
-  pl->tb = (size_t)a->T * a->B;
+  pl->k_b = fonly ? fonly->n_particles : a->train_particles;
+  pl->tb = fonly ? 0 : (size_t)T * B;
   pl->tbz = pl->tb * Z;
-  pl->C = (size_t)(S > 0 ? S : 1) * a->B;
-  size_t R = pl->C * (size_t)a->train_particles;
-  if ((size_t)a->match_particles > R) R = a->match_particles;
+  pl->C = (size_t)(S > 0 ? S : 1) * B;
+  size_t R = pl->C * (size_t)pl->k_b;
+  if (!fonly && (size_t)a->match_particles > R) R = a->match_particles;
   pl->R = R;
   pl->d_max = Z;                     // head scratch serves decoders (D_m wide) and encoders (Z wide)
   for (int i = 0; i < M; ++i) if ((size_t)m->dims[i] > pl->d_max) pl->d_max = m->dims[i];
@@ -473,12 +480,14 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, LargePlan* pl) {
   size_t cur = 0;
   auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
   const size_t f = sizeof(float), fS = f * pl->tbz * (S > 0 ? S : 1);
+  const size_t Mx = fonly ? 0 : M;                    // no encoder / decoder scratch for a lone filter
   pl->zero_begin = cur;
   pl->acc = carve(sizeof(double)); pl->count = carve(f);
   pl->dobs_mean = carve(f * pl->tbz * M); pl->dobs_std = carve(f * pl->tbz * M);
   pl->a_dsamp = carve(fS); pl->c_dsamp = carve(fS); pl->b_dpm = carve(fS); pl->b_dps = carve(fS);
   pl->zero_end = cur;
   pl->paramsT = carve(f * lay.total);
+  (void)Mx;
   for (int i = 0; i < M; ++i) { pl->x0[i] = carve(f * pl->tb * m->dims[i]); pl->x0T[i] = carve(f * pl->tb * m->dims[i]); }
   pl->mask = carve(pl->tb * M);
   pl->henc = carve(f * pl->tb * H * M); pl->hencT = carve(f * pl->tb * H * M);
@@ -517,17 +526,20 @@ __global__ void match_tail_kernel(const float* c_mu, const float* c_sd, const fl
   if (i < Z) { atomicAdd(g_z0_mean + i, c_mu[i]); atomicAdd(g_z0_log_std + i, c_sd[i] * expf(z0_log_std[i])); }
 }
 
-int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a, void* workspace,
-               size_t workspace_bytes, float* loss_out, int32_t* launches, cudaStream_t st) {
+// fonly != null: run only z_filter forward (fonly_backward = false) or backward on `fonly`
+int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
+               const bfvi_filter_args* fonly, bool fonly_backward, void* workspace, size_t workspace_bytes,
+               float* loss_out, int32_t* launches, cudaStream_t st) {
   LargePlan pl;
-  plan_large(m, a, &pl);
+  plan_large(m, a, fonly, &pl);
   if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
   if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
   char* ws = (char*)workspace;
   bfvi_layout lay;
   bfvi_param_layout(m, &lay);
-  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, T = a->T, B = a->B, S = pl.S;
-  const bool with_grad = grads != nullptr;
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, S = pl.S;
+  const int T = fonly ? fonly->T : a->T, B = fonly ? fonly->B : a->B;
+  const bool with_grad = fonly ? fonly_backward : grads != nullptr;
   const int prec = bfvi::tc::PREC_TF32X3;
   const int64_t tb = (int64_t)pl.tb;
   int n_launch = 0;
@@ -537,8 +549,10 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   float* count = F(pl.count);
   auto ew_grid = [&](int64_t n, int per) { return dim3((unsigned)grid_for(n, per, 16)); };
 
-  cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
-  if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
+  if (!fonly) {                      // a lone filter ACCUMULATES into the caller's (zeroed) gradient buffers
+    cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
+    if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
+  }
   BFVI_CHECK_CUDA();
 
   // ---- GEMM helpers ---------------------------------------------------------------------
@@ -582,7 +596,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   // ---- transposed weights (input-gradient GEMMs) ------------------------------------------
   if (with_grad) {
     auto tw = [&](int64_t w_off, int n_out, int n_in) { transpose(params + w_off, n_out, n_in, paramsT + w_off); };
-    for (int i = 0; i < M; ++i) {
+    for (int i = 0; i < (fonly ? 0 : M); ++i) {
       tw(lay.enc[i].in_to_h_w, H, m->dims[i]); tw(lay.enc[i].mean_w, Z, H); tw(lay.enc[i].std_w, Z, H);
       tw(lay.dec[i].in_to_h_w, H, Z); tw(lay.dec[i].mean_w, m->dims[i], H); tw(lay.dec[i].std_w, m->dims[i], H);
     }
@@ -682,6 +696,11 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     return BFVI_OK;
   };
 
+  if (fonly) {                       // stand-alone MultiDMM.z_filter (models/dmm.py:319-412)
+    if (int rc = fonly_backward ? pass_bwd(*fonly) : pass_fwd(*fonly, nullptr)) return rc;
+    if (launches) *launches = n_launch;
+    return BFVI_OK;
+  }
   const bool external = a->eps_filt != nullptr || a->eps_sflt != nullptr || a->eps_ssmt != nullptr ||
                         a->eps_match != nullptr;
   // ---- prior-matching term (models/dmm.py:540-545) -----------------------------------------
@@ -1072,10 +1091,31 @@ int bfvi_decode_nll(const bfvi_model* m, const float* params, float* grads, int3
   return launch_mlp_bwd(m->h_dim, true, mp, (cudaStream_t)stream);
 }
 
+int bfvi_filter_workspace(const bfvi_model* m, const bfvi_filter_args* a, size_t* bytes) {
+  if (int rc = check_model(m)) return rc;
+  if (int rc = check_filter_args(m, a)) return rc;
+  if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
+  *bytes = 0;
+  if (family_of(m->z_dim, m->h_dim) == 2) {
+    LargePlan pl;
+    plan_large(m, nullptr, a, &pl);
+    *bytes = pl.total;
+  }
+  return BFVI_OK;
+}
+
+static int filter_large(const bfvi_model* m, const float* params, float* grads, const bfvi_filter_args* a,
+                        bool backward, void* stream) {
+  if (!a->workspace) return fail(BFVI_ERR_WORKSPACE, "the large-dim family needs args->workspace (bfvi_filter_workspace)");
+  return step_large(m, params, grads, nullptr, a, backward, a->workspace, a->workspace_bytes, nullptr, nullptr,
+                    (cudaStream_t)stream);
+}
+
 int bfvi_filter_fwd(const bfvi_model* m, const float* params, const bfvi_filter_args* a, void* stream) {
   if (int rc = check_model(m)) return rc;
   if (int rc = check_filter_args(m, a)) return rc;
   if (!params) return fail(BFVI_ERR_ARG, "params null");
+  if (family_of(m->z_dim, m->h_dim) == 2) return filter_large(m, params, nullptr, a, false, stream);
   bfvi_layout lay;
   bfvi_param_layout(m, &lay);
   return dispatch_filter(m, lay, false, make_filter_params(m, lay, params, nullptr, a), (cudaStream_t)stream);
@@ -1086,6 +1126,7 @@ int bfvi_filter_bwd(const bfvi_model* m, const float* params, float* grads, cons
   if (int rc = check_model(m)) return rc;
   if (int rc = check_filter_args(m, a)) return rc;
   if (!params || !grads) return fail(BFVI_ERR_ARG, "params/grads null");
+  if (family_of(m->z_dim, m->h_dim) == 2) return filter_large(m, params, grads, a, true, stream);
   bfvi_layout lay;
   bfvi_param_layout(m, &lay);
   return dispatch_filter(m, lay, true, make_filter_params(m, lay, params, grads, a), (cudaStream_t)stream);
@@ -1195,7 +1236,7 @@ int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* by
   if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
   if (family_of(m->z_dim, m->h_dim) == 2) {
     LargePlan lp;
-    plan_large(m, a, &lp);
+    plan_large(m, a, nullptr, &lp);
     *bytes = lp.total;
     return BFVI_OK;
   }
@@ -1227,7 +1268,8 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     if (!a->inputs[i] || !a->targets[i]) return fail(BFVI_ERR_ARG, "inputs/targets[%d] null", i);
   if (family_of(m->z_dim, m->h_dim) == 2) {
     if (pm.on) return fail(BFVI_ERR_UNSUPPORTED, "phase profile exists for the small-dim family only");
-    return step_large(m, params, grads, a, workspace, workspace_bytes, loss_out, launches, (cudaStream_t)stream);
+    return step_large(m, params, grads, a, nullptr, false, workspace, workspace_bytes, loss_out, launches,
+                      (cudaStream_t)stream);
   }
   const bool with_grad = grads != nullptr;
   StepPlan pl;

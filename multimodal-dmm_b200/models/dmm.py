@@ -136,8 +136,10 @@ class _FilterFn(torch.autograd.Function):
         n_exp, t_max, b_dim, z = z_mean.shape
         outs = [torch.empty(t_max, b_dim, z, device=z_mean.device) for _ in range(5)]
         args = model._filter_args(cfg, z_mean, z_std, masks, eps, outs)
+        keep_ws = model._filter_workspace(lib, args)
         lib.call('bfvi_filter_fwd', C.byref(model._cmodel), _lib.ptr(model._flat), C.byref(args),
                  _stream())
+        del keep_ws
         ctx.model, ctx.cfg, ctx.eps = model, cfg, eps
         ctx.save_for_backward(z_mean, z_std, masks, *outs)
         return tuple(outs)
@@ -152,8 +154,10 @@ class _FilterFn(torch.autograd.Function):
         d_mean, d_std = torch.zeros_like(z_mean), torch.zeros_like(z_std)
         d_outs = [None if d is None else d.contiguous().float() for d in d_outs]
         args = model._filter_args(ctx.cfg, z_mean, z_std, masks, ctx.eps, outs, d_mean, d_std, d_outs)
+        keep_ws = model._filter_workspace(lib, args)
         lib.call('bfvi_filter_bwd', C.byref(model._cmodel), _lib.ptr(model._flat), _lib.ptr(flat_grad),
                  C.byref(args), _stream())
+        del keep_ws
         return (None, None, d_mean, d_std, None, None) + model._views(flat_grad)
 
 
@@ -412,15 +416,22 @@ class MultiDMM(MultiDGTS):
                 setattr(a, n, None if d is None else d.data_ptr())
         return a
 
+    def _filter_workspace(self, lib, args):
+        """Scratch of the large-dim family for one z_filter call (0 bytes for the small-dim family)."""
+        nbytes = C.c_size_t(0)
+        lib.call('bfvi_filter_workspace', C.byref(self._cmodel), C.byref(args), C.byref(nbytes))
+        if nbytes.value == 0:
+            return None
+        ws = self._workspace(nbytes.value)
+        args.workspace, args.workspace_bytes = ws.data_ptr(), nbytes.value
+        return ws
+
     def z_filter(self, z_mean, z_std, z_masks, direction='fwd', sample=True, n_particles=1,
                  sample_init=False, eps=None):
         """Product-of-experts filtering along time (models/dmm.py:319-412).
         z_mean/z_std (E, T, B, Z), z_masks (E, T, B).  `eps` optionally injects the
         N(0,1) draws as a (T, B, K, Z) tensor; default is the in-kernel generator."""
         self._ensure_flat()
-        if self._family != 1:
-            raise _lib.BfviError('z_filter as a stand-alone op exists for the small-dim family only '
-                                 '(z_dim=%d h_dim=%d is served by forward())' % (self.z_dim, self.h_dim))
         cfg = dict(direction=direction, sample=sample, n_particles=n_particles,
                    sample_init=sample_init, seed=self._next_seed())
         if eps is not None:
@@ -448,9 +459,13 @@ class MultiDMM(MultiDGTS):
         smt_particles = kwargs.get('smt_particles', 1)
         eps_flt, eps_smt = kwargs.get('noise', (None, None))
         t_max, b_dim = max(lengths), len(lengths)
-        if self._family == 2:
+        all_default = all(self._default_enc(m) and self._default_dec(m) for m in self.modalities)
+        needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if self._family == 2 and all_default and not needs_graph:
+            # inference fast path: ONE C call, every Linear layer a tcgen05 GEMM
             return self._forward_large(inputs, t_max, b_dim, mode, sample, sample_init, flt_particles,
                                        smt_particles, eps_flt, eps_smt, kwargs.get('precision', 'tf32x3'))
+        # composed, differentiable path: encode -> z_filter (fused temporal core) -> decode
 
         obs_mean, obs_std, obs_mask = self.encode(inputs)
         direction = 'fwd' if mode in ('ffilter', 'bsmooth') else 'bwd'
@@ -474,16 +489,9 @@ class MultiDMM(MultiDGTS):
 
     def _forward_large(self, inputs, t_max, b_dim, mode, sample, sample_init, flt_particles,
                        smt_particles, eps_flt, eps_smt, precision):
-        """forward() of the large-dim kernel family: ONE C call (bfvi_forward) that runs every
-        Linear layer as a tcgen05 GEMM.  Inference / evaluation only in this release."""
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise _lib.BfviError(
-                'z_dim=%d, h_dim=%d is served by the tcgen05 large-dim family, which implements '
-                'forward() / evaluation only in this release: call it under torch.no_grad() '
-                '(training kernels exist for the small-dim family only; there is no fallback)'
-                % (self.z_dim, self.h_dim))
-        if not all(self._default_enc(m) and self._default_dec(m) for m in self.modalities):
-            raise _lib.BfviError('the large-dim family covers default Gaussian encoders / decoders only')
+        """Inference forward() of the large-dim kernel family for all-default Gaussian models: ONE C
+        call (bfvi_forward) that runs every Linear layer as a tcgen05 GEMM.  No autograd graph:
+        training goes through step(), and forward() under grad mode takes the composed path."""
         lib = _lib.load()
         dev = self._flat.device
         a = _lib.ForwardArgs()

@@ -60,3 +60,59 @@ def test_training_step_of_the_large_family_on_golden_fixtures(lib, name, monkeyp
             assert g.norm() == 0, k
         else:
             assert rel_err(g, g_ref) < 1e-3, (k, rel_err(g, g_ref))
+
+
+def _filter_call(lib, fam_env, monkeypatch, backward):
+    """bfvi_filter_fwd (+ _bwd) through the C ABI on a fixed random problem; returns tensors."""
+    import ctypes as C
+    from multimodal_dmm_b200 import _lib
+    import bfvi_oracle as bo
+    if fam_env:
+        monkeypatch.setenv('BFVI_FAMILY', fam_env)
+    else:
+        monkeypatch.delenv('BFVI_FAMILY', raising=False)
+    z, h, t_max, b_dim, k, n_exp = 5, 20, 5, 4, 3, 3
+    g = torch.Generator().manual_seed(9)
+    model = _lib.make_model([1], ['Normal'], z, h, 1e-3)
+    sd = bo.init_params(['a'], [1], h_dim=h, z_dim=z, seed=4, scale=1.5)
+    flat, lay = helpers.pack_params(lib, model, ['a'], ['Normal'], sd, 'cpu')
+    mean = torch.randn(n_exp, t_max, b_dim, z, generator=g)
+    std = torch.rand(n_exp, t_max, b_dim, z, generator=g) + 0.3
+    masks = (torch.rand(n_exp, t_max, b_dim, generator=g) > 0.3).to(torch.uint8)
+    eps = torch.randn(t_max, b_dim, k, z, generator=g)
+    outs = [torch.zeros(t_max, b_dim, z) for _ in range(5)]
+    d_outs = [torch.randn(t_max, b_dim, z, generator=g) for _ in range(5)]
+    d_mean, d_std = torch.zeros_like(mean), torch.zeros_like(std)
+    a = _lib.FilterArgs()
+    a.T, a.B, a.S, a.n_experts = t_max, b_dim, 1, n_exp
+    tbz, tb = t_max * b_dim * z, t_max * b_dim
+    for e in range(n_exp):
+        ex = a.experts[e]
+        ex.mean, ex.std, ex.mask = mean.data_ptr() + 4 * e * tbz, std.data_ptr() + 4 * e * tbz, masks.data_ptr() + e * tb
+        ex.stride_t, ex.stride_b, ex.mstride_t, ex.mstride_b = b_dim * z, z, b_dim, 1
+        ex.d_mean, ex.d_std = d_mean.data_ptr() + 4 * e * tbz, d_std.data_ptr() + 4 * e * tbz
+    a.set_expert_bits[0] = (1 << n_exp) - 1
+    a.direction, a.n_particles, a.sample, a.sample_init = _lib.DIR_BWD, k, 1, 0
+    a.noise.eps = eps.data_ptr()
+    a.infer_mean, a.infer_std, a.prior_mean, a.prior_std, a.samples = [t.data_ptr() for t in outs]
+    nbytes = C.c_size_t(0)
+    lib.call('bfvi_filter_workspace', C.byref(model), C.byref(a), C.byref(nbytes))
+    ws = helpers.aligned_empty(max(nbytes.value, 256), 'cpu')
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes.value
+    lib.call('bfvi_filter_fwd', C.byref(model), _lib.ptr(flat), C.byref(a), None)
+    grads = torch.zeros_like(flat)
+    if backward:
+        (a.d_infer_mean, a.d_infer_std, a.d_prior_mean, a.d_prior_std, a.d_samples) = [t.data_ptr() for t in d_outs]
+        lib.call('bfvi_filter_bwd', C.byref(model), _lib.ptr(flat), _lib.ptr(grads), C.byref(a), None)
+    return nbytes.value, outs, grads, d_mean, d_std
+
+
+def test_standalone_filter_of_both_families_agree(lib, monkeypatch):
+    """bfvi_filter_fwd / _bwd: the large-dim launch sequence (forced with BFVI_FAMILY=2) against
+    the small-dim chain kernels on the same experts, masks, noise and upstream gradients."""
+    n1, o1, g1, dm1, ds1 = _filter_call(lib, None, monkeypatch, True)
+    n2, o2, g2, dm2, ds2 = _filter_call(lib, '2', monkeypatch, True)
+    assert n1 == 0 and n2 > 0                         # only the large-dim family needs scratch
+    for a, b in zip(o1, o2):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    assert rel_err(g2, g1) < 1e-4 and rel_err(dm2, dm1) < 1e-4 and rel_err(ds2, ds1) < 1e-4

@@ -64,8 +64,15 @@ def test_python_api_forward_large():
     ref = helpers.oracle_forward(fx, 'fsmooth', True, 5, eps_flt, eps_smt, dtype=torch.float64)
     bad = helpers.compare_forward((infer, prior, recon), ref, rtol=5e-4, atol=5e-5)
     assert not bad, bad
-    with pytest.raises(_lib.BfviError):                      # forward() of this family carries no autograd graph:
-        m(inputs, lengths=fx['lengths'])                     # training goes through step()
+    # under grad mode forward() takes the composed, differentiable path (torch MLP modules around the
+    # fused z_filter op of the large-dim family): same values, and gradients flow
+    m.train()
+    infer_g, prior_g, recon_g = m(inputs, lengths=fx['lengths'], mode='fsmooth', flt_particles=5,
+                                  noise=(eps_flt.cuda(), eps_smt.cuda()))
+    bad = helpers.compare_forward((infer_g, prior_g, recon_g), ref, rtol=5e-4, atol=5e-5)
+    assert not bad, bad
+    torch.nan_to_num(infer_g[0]).sum().backward()
+    assert m.trans['fwd'].z_lin.weight.grad is not None and m.enc['m0'].h_to_mean.weight.grad is not None
 
 
 # ---------------------------------------------------------------------------------------
