@@ -316,6 +316,16 @@ int bfvi_wgrad_tf32(const float* dy_t, int64_t lddy, const float* x_t, int64_t l
                     int64_t n_rows, int32_t n_out, int32_t n_in, int32_t accumulate, int32_t flags,
                     void* stream);
 
+/* The optimiser step either side of the hot path (trainer.py:248-252), fused over the flat
+ * buffers: optional clip_grad_norm_ (max_norm > 0; total L2 norm over the whole flat gradient,
+ * coefficient max_norm / (norm + 1e-6) clamped to 1) followed by torch.optim.Adam (no amsgrad;
+ * weight_decay added to the gradient like torch).  `grad_scale` multiplies the gradient first
+ * (e.g. 1 / sum(lengths)).  `step` is the 1-based step count; `norm_scratch` is one device float.
+ * Two launches, no host synchronisation. */
+int bfvi_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                   float grad_scale, float max_norm, float* norm_scratch, void* stream);
+
 /* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
  * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream);

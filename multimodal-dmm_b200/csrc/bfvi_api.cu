@@ -2,6 +2,7 @@
 // dispatch on (z_dim, h_dim), workspace carving and the orchestration of one whole
 // MultiDMM.step (models/dmm.py:503-554) + backward as a fixed sequence of launches
 // on the caller's stream.  No device allocation, no global mutable state.
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -1208,6 +1209,31 @@ int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
   gp.M = n_out; gp.N = n_in; gp.K = n_rows; gp.accumulate = accumulate ? 1 : 0;
   if (accumulate) gp.k_split = wgrad_k_split(n_rows, n_out, n_in);
   return gemm_tc(gp, (flags >> 4) & 1, (cudaStream_t)stream);
+}
+
+int bfvi_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int32_t step, float grad_scale,
+                   float max_norm, float* norm_scratch, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || n < 1 || step < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (max_norm > 0.f && !norm_scratch) return fail(BFVI_ERR_ARG, "norm_scratch null");
+  cudaStream_t st = (cudaStream_t)stream;
+  bfvi::AdamParams ap;
+  ap.p = params; ap.g = grads; ap.m = exp_avg; ap.v = exp_avg_sq; ap.n = n;
+  ap.lr = lr; ap.beta1 = beta1; ap.beta2 = beta2; ap.eps = eps; ap.weight_decay = weight_decay;
+  ap.grad_scale = grad_scale; ap.max_norm = max_norm;
+  ap.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  ap.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  ap.sqnorm = nullptr;
+  if (max_norm > 0.f) {
+    cudaMemsetAsync(norm_scratch, 0, sizeof(float), st);
+    auto kn = bfvi::sqnorm_kernel;
+    BFVI_LAUNCH(kn, dim3(grid_for(n, 256, 4)), dim3(256), 0, st, grads, n, grad_scale, norm_scratch);
+    ap.sqnorm = norm_scratch;
+  }
+  auto k = bfvi::adam_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n, 256, 8)), dim3(256), 0, st, ap);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
 }
 
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream) {

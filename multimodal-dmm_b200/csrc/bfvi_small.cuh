@@ -278,6 +278,46 @@ __global__ void __launch_bounds__(256) count_mask_kernel(const uint8_t* mask, in
   }
 }
 
+// ---- fused optimiser step on the flat buffers (trainer.py:248-252) -----------------------
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float* __restrict__ g, int64_t n, float scale,
+                                                     float* __restrict__ out) {
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = g[i] * scale;
+    acc = fmaf(v, v, acc);
+  }
+  __shared__ float red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+  }
+}
+struct AdamParams {
+  float* p; const float* g; float* m; float* v;
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, max_norm, bc1, bc2_sqrt;
+  const float* sqnorm;         // squared gradient norm (null: no clipping)
+};
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams a) {
+  float coef = a.grad_scale;
+  if (a.sqnorm != nullptr) {   // torch.nn.utils.clip_grad_norm_
+    const float c = a.max_norm / (sqrtf(a.sqnorm[0]) + 1e-6f);
+    coef *= c < 1.f ? c : 1.f;
+  }
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = a.p[i];
+    const float g = fmaf(a.weight_decay, p, a.g[i] * coef);
+    const float m = fmaf(a.beta1, a.m[i], (1.f - a.beta1) * g);
+    const float v = fmaf(a.beta2, a.v[i], (1.f - a.beta2) * g * g);
+    a.m[i] = m; a.v[i] = v;
+    a.p[i] = p - (a.lr / a.bc1) * m / (sqrtf(v) / a.bc2_sqrt + a.eps);
+  }
+}
+
 __global__ void finalize_loss_kernel(const double* acc, float* out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = (float)acc[0];
 }

@@ -169,3 +169,35 @@ def test_trainer_contract_adam_steps():
     assert m.fused_step_available and m.last_launches > 0
     sd = m.state_dict()
     assert set(sd.keys()) == set(fx['state_dict'].keys())
+
+
+def test_flat_adam_trains_like_torch_adam():
+    """optim.FlatAdam (bfvi_adam_step: fused clip + Adam on the flat buffers) against
+    torch.optim.Adam + clip_grad_norm_ over the same steps, noise and data."""
+    from multimodal_dmm_b200 import optim
+    fx = load_golden('spirals_half_missing')
+    n = float(sum(fx['lengths']))
+
+    def train(use_flat):
+        m = build(fx).train()
+        m.noise_seed = 5
+        opt = optim.FlatAdam(m, lr=5e-3, weight_decay=1e-4, max_norm=1.0) if use_flat else \
+            torch.optim.Adam(m.parameters(), lr=5e-3, weight_decay=1e-4)
+        losses = []
+        for _ in range(4):
+            loss = m.step(cuda(fx['inputs']), fx['mask'].cuda(), fx['kld_mult'], fx['rec_mults'],
+                          targets=cuda(fx['targets']), lengths=fx['lengths'])
+            (loss / n).backward()
+            if not use_flat:
+                torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+            opt.step()
+            opt.zero_grad()
+            losses.append(loss.item())
+        return losses, {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    l_flat, s_flat = train(True)
+    l_ref, s_ref = train(False)
+    assert l_flat[-1] < l_flat[0]
+    for a, b in zip(l_flat, l_ref):
+        assert abs(a - b) <= 1e-4 * abs(b), (l_flat, l_ref)
+    for k in s_ref:
+        assert torch.allclose(s_flat[k], s_ref[k], rtol=1e-3, atol=1e-5), k
