@@ -152,6 +152,15 @@ void choose_lanes(int K, int R, int64_t chains, int* lanes, int* rounds) {
   *rounds = (K + pick * R - 1) / (pick * R);
 }
 
+// Few chains (small batches such as the reference's default spirals run, B = 100): the serial
+// time loop is latency-bound and a warp per chain with ONE particle per lane minimises the work
+// of a step; throughput mappings (5 particles per lane) only pay once the GPU is filled.
+bool latency_bound_pass(int64_t chains, int K) {
+  if (K <= 1 || getenv("BFVI_LANES") != nullptr) return false;
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  return chains <= (int64_t)sms * 16;
+}
+
 int task_grid(int64_t chains, int lanes, int warps_per_block) {
   const int cpw = 32 / lanes;
   const int64_t tasks = (chains + cpw - 1) / cpw;
@@ -166,16 +175,22 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
   const int64_t chains = (int64_t)a.S * (fp.bc > 0 ? fp.bc : a.B);
   const int wpb = bfvi::kChainFwdThreads / 32;
-  if (a.n_particles > 1) {
+  if (latency_bound_pass(chains, a.n_particles)) {
+    fp.lanes = a.n_particles < 32 ? a.n_particles : 32;
+    fp.rounds = (a.n_particles + fp.lanes - 1) / fp.lanes;
+    auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, 2)), dim3(64), 0, st, fp);
+  } else if (a.n_particles > 1) {
     constexpr int R = 5;
     choose_lanes(a.n_particles, R, chains, &fp.lanes, &fp.rounds);
     auto k = bfvi::chain_fwd_kernel<Z, H, R>;
     BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, wpb)), dim3(bfvi::kChainFwdThreads), 0, st, fp);
   } else {
-    fp.lanes = 1; fp.rounds = 1;
-    auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
-    // latency-bound single-particle pass: 2-warp CTAs spread the few warps over all SMs
-    BFVI_LAUNCH(k, dim3(task_grid(chains, 1, 2)), dim3(64), 0, st, fp);
+    // single particle: latency-bound; a chain is spread over Z lanes (bfvi_zsplit.cuh), 2-warp CTAs
+    // put the few warps on all SMs
+    fp.lanes = Z; fp.rounds = 1;
+    auto k = bfvi::zsplit_fwd_kernel<Z, H>;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, Z, 2)), dim3(bfvi::kZsplitThreads), 0, st, fp);
   }
   BFVI_CHECK_CUDA();
   return BFVI_OK;
@@ -185,15 +200,27 @@ template <int Z, int H>
 int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
   const int64_t chains = (int64_t)a.S * (fp.bc > 0 ? fp.bc : a.B);
+  // z-split single-particle kernel (bfvi_zsplit.cuh) while all its warps are resident at once
+  // (8 warps/SM at its register budget); beyond that the one-chain-per-lane kernel below does the
+  // same work with 5x fewer warps and wins
+  const bool zsplit_bwd = a.n_particles == 1 && (chains + 32 / Z - 1) / (32 / Z) <= (int64_t)(num_sms() > 0 ? num_sms() : 1) * 8;
+  if (zsplit_bwd || (a.n_particles == 1 && getenv("BFVI_ZSPLIT_BWD") != nullptr)) {
+    fp.lanes = Z; fp.slices = 1;
+    auto k = bfvi::zsplit_bwd_kernel<Z, H>;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, Z, 2)), dim3(bfvi::kZsplitThreads), 0, st, fp);
+    BFVI_CHECK_CUDA();
+    return BFVI_OK;
+  }
   // single-particle passes are latency-bound with few warps: 2-warp CTAs reach all SMs
-  const int warps = a.n_particles > 1 ? bfvi::kChainBwdWarps : 2;
+  const int warps = (a.n_particles > 1 && !latency_bound_pass(chains, a.n_particles)) ? bfvi::kChainBwdWarps : 2;
   const size_t smem = bfvi::chain_bwd_smem_bytes<Z, H>(warps);
   const int threads = warps * 32;
   const bfvi::WgSpec spec = bfvi::GtfPanels<Z, H>::spec();
   if (bfvi::wg_rounds<bfvi::GtfPanels<Z, H>::TD, bfvi::kTX>(spec) != 1)
     return fail(BFVI_ERR_UNSUPPORTED, "internal: weight-gradient tiling needs one round");
   int rounds = 1;
-  choose_lanes(a.n_particles, 1, chains, &fp.lanes, &rounds);
+  if (latency_bound_pass(chains, a.n_particles)) fp.lanes = a.n_particles < 32 ? a.n_particles : 32;
+  else choose_lanes(a.n_particles, 1, chains, &fp.lanes, &rounds);
   fp.slices = (a.n_particles + fp.lanes - 1) / fp.lanes;
   auto k = bfvi::chain_bwd_kernel<Z, H>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -18,6 +18,7 @@
 #include "bfvi_rng.cuh"
 #include "bfvi_wgrad.cuh"
 #include "bfvi_chain.cuh"
+#include "bfvi_zsplit.cuh"
 
 namespace bfvi {
 
