@@ -201,15 +201,21 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
   const int64_t chains = (int64_t)a.S * (fp.bc > 0 ? fp.bc : a.B);
   // z-split single-particle kernel (bfvi_zsplit.cuh) while all its warps are resident at once
-  // (8 warps/SM at its register budget); beyond that the one-chain-per-lane kernel below does the
-  // same work with 5x fewer warps and wins
-  const bool zsplit_bwd = a.n_particles == 1 && (chains + 32 / Z - 1) / (32 / Z) <= (int64_t)(num_sms() > 0 ? num_sms() : 1) * 8;
-  if (zsplit_bwd || (a.n_particles == 1 && getenv("BFVI_ZSPLIT_BWD") != nullptr)) {
-    fp.lanes = Z; fp.slices = 1;
-    auto k = bfvi::zsplit_bwd_kernel<Z, H>;
-    BFVI_LAUNCH(k, dim3(task_grid(chains, Z, 2)), dim3(bfvi::kZsplitThreads), 0, st, fp);
-    BFVI_CHECK_CUDA();
-    return BFVI_OK;
+  // (register accumulators: 8 warps/SM); beyond that the one-chain-per-lane kernel below does the
+  // same work with 5x fewer warps, leaves room for the other pass running beside it, and wins
+  if (a.n_particles == 1) {
+    const int64_t warps_needed = (chains + 32 / Z - 1) / (32 / Z);
+    const int64_t sms = num_sms() > 0 ? num_sms() : 1;
+    const char* force = getenv("BFVI_ZSPLIT_BWD");          // tuning knob: 0 off, 1 registers, 2 shared
+    const int mode = force ? atoi(force) : (warps_needed <= sms * 8 ? 1 : 0);
+    if (mode == 1 || mode == 2) {
+      fp.lanes = Z; fp.slices = 1;
+      const dim3 grid(task_grid(chains, Z, 2)), block(bfvi::kZsplitThreads);
+      if (mode == 1) { auto k = bfvi::zsplit_bwd_kernel<Z, H, false>; BFVI_LAUNCH(k, grid, block, 0, st, fp); }
+      else { auto k = bfvi::zsplit_bwd_kernel<Z, H, true>; BFVI_LAUNCH(k, grid, block, 0, st, fp); }
+      BFVI_CHECK_CUDA();
+      return BFVI_OK;
+    }
   }
   // single-particle passes are latency-bound with few warps: 2-warp CTAs reach all SMs
   const int warps = (a.n_particles > 1 && !latency_bound_pass(chains, a.n_particles)) ? bfvi::kChainBwdWarps : 2;

@@ -27,6 +27,8 @@
 namespace bfvi {
 
 constexpr int kZsplitThreads = 64;
+// (a one-step-ahead prefetch.global.L1 of the per-step operands was measured SLOWER here:
+//  forward 0.44 -> 0.49 ms at C2, 0.31 -> 0.39 ms at C1 — DESIGN.md "tried and measured")
 
 // partial[idx] for a runtime idx in [0, Z)
 template <int Z>
@@ -190,14 +192,55 @@ __global__ void __launch_bounds__(kZsplitThreads) zsplit_fwd_kernel(const __grid
 // =========================================================================
 // backward
 // =========================================================================
+// Per-lane weight-gradient accumulators: registers (lowest latency; 8 warps/SM at ~230
+// registers) or one shared-memory column per lane (element i of lane l at i*32 + l: conflict
+// free; 128 registers, 14 warps/SM, so twice as many chains are resident at once).  The
+// shared-memory form is a tuning variant (BFVI_ZSPLIT_BWD=2): at C2 it shortens the smoothing
+// backward 1.18 -> 0.97 ms stand-alone, but its 214 KB/SM of shared memory keeps the f_mode
+// backward pass (side stream) from running beside it and the STEP gets 0.5 ms slower.
+template <int N, bool SMEM>
+struct LaneAcc;
+template <int N>
+struct LaneAcc<N, false> {
+  float v[N];
+  __device__ __forceinline__ explicit LaneAcc(float*) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = 0.f;
+  }
+  __device__ __forceinline__ void fma(int i, float a, float b) { v[i] = fmaf(a, b, v[i]); }
+  __device__ __forceinline__ void add(int i, float a) { v[i] += a; }
+  __device__ __forceinline__ float get(int i) const { return v[i]; }
+};
+template <int N>
+struct LaneAcc<N, true> {
+  float* col;
+  __device__ __forceinline__ explicit LaneAcc(float* warp_base) : col(warp_base + (threadIdx.x & 31)) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) col[i * 32] = 0.f;
+  }
+  __device__ __forceinline__ void fma(int i, float a, float b) { col[i * 32] = fmaf(a, b, col[i * 32]); }
+  __device__ __forceinline__ void add(int i, float a) { col[i * 32] += a; }
+  __device__ __forceinline__ float get(int i) const { return col[i * 32]; }
+};
 template <int Z, int H>
-__global__ void __launch_bounds__(kZsplitThreads) zsplit_bwd_kernel(const __grid_constant__ FilterParams p) {
+struct ZAccLayout {
+  static constexpr int UPL = H / Z;
+  static constexpr int W0G = 0, W2G = W0G + UPL * Z, W0N = W2G + UPL * Z, W2N = W0N + UPL * Z,
+                       B0G = W2N + UPL * Z, B0N = B0G + UPL, WL = B0N + UPL, WS = WL + Z, BL = WS + Z, BS = BL + 1,
+                       B2G = BS + 1, B2N = B2G + 1, N = B2N + 1;
+};
+
+template <int Z, int H, bool ACC_SMEM>
+__global__ void __launch_bounds__(kZsplitThreads, ACC_SMEM ? 7 : 1)
+zsplit_bwd_kernel(const __grid_constant__ FilterParams p) {
   static_assert(H % Z == 0, "z-split needs H to be a multiple of Z");
   using P = GtfPack<Z, H>;
   using L_ = GtfLayout<Z, H>;
   constexpr int UPL = H / Z;
+  using A_ = ZAccLayout<Z, H>;
   __shared__ __align__(16) float sP[P::SIZE];
   __shared__ float sG[L_::SIZE + 2 * Z];            // CTA-level gradient accumulator (+ global prior)
+  __shared__ float sAcc[ACC_SMEM ? (kZsplitThreads / 32) * A_::N * 32 : 1];
   const bfvi_filter_args& a = p.a;
   gtf_pack_load<Z, H>(p.trans_w, sP);
   for (int i = threadIdx.x; i < L_::SIZE + 2 * Z; i += blockDim.x) sG[i] = 0.f;
@@ -211,17 +254,9 @@ __global__ void __launch_bounds__(kZsplitThreads) zsplit_bwd_kernel(const __grid
   const int n_tasks = (n_chains + zg.cpw - 1) / zg.cpw;
   const int wpb = blockDim.x >> 5;
 
-  // weight-gradient accumulators of this lane's units and rows (registers, whole kernel)
-  float aw0g[UPL][Z], ab0g[UPL], aw2g[UPL][Z], aw0n[UPL][Z], ab0n[UPL], aw2n[UPL][Z];
-  float awl[Z], abl = 0.f, aws[Z], abs_ = 0.f, ab2g = 0.f, ab2n = 0.f, d_gm = 0.f, d_gs = 0.f;
-#pragma unroll
-  for (int u = 0; u < UPL; ++u) {
-    ab0g[u] = ab0n[u] = 0.f;
-#pragma unroll
-    for (int i = 0; i < Z; ++i) aw0g[u][i] = aw2g[u][i] = aw0n[u][i] = aw2n[u][i] = 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < Z; ++i) awl[i] = aws[i] = 0.f;
+  // weight-gradient accumulators of this lane's units and rows, alive for the whole kernel
+  LaneAcc<A_::N, ACC_SMEM> acc(sAcc + (ACC_SMEM ? (threadIdx.x >> 5) * A_::N * 32 : 0));
+  float d_gm = 0.f, d_gs = 0.f;
 
   for (int task = blockIdx.x * wpb + (threadIdx.x >> 5); task < n_tasks; task += gridDim.x * wpb) {
     const int chain_raw = task * zg.cpw + zg.cig;
@@ -332,24 +367,24 @@ __global__ void __launch_bounds__(kZsplitThreads) zsplit_bwd_kernel(const __grid
         for (int o = 0; o < Z; ++o) { da = fmaf(wg[1 + Z + o], d_agv[o], da); dc = fmaf(wn[1 + Z + o], d_nlv[o], dc); }
         da = ag[u] > 0.f ? da : 0.f;
         dc = an[u] > 0.f ? dc : 0.f;
-        ab0g[u] += da; ab0n[u] += dc;
+        acc.add(A_::B0G + u, da); acc.add(A_::B0N + u, dc);
 #pragma unroll
         for (int i2 = 0; i2 < Z; ++i2) {
           pz[i2] = fmaf(wg[1 + i2], da, pz[i2]);
           pz[i2] = fmaf(wn[1 + i2], dc, pz[i2]);
-          aw0g[u][i2] = fmaf(da, zv[i2], aw0g[u][i2]);
-          aw0n[u][i2] = fmaf(dc, zv[i2], aw0n[u][i2]);
-          aw2g[u][i2] = fmaf(d_agv[i2], ag[u], aw2g[u][i2]);
-          aw2n[u][i2] = fmaf(d_nlv[i2], an[u], aw2n[u][i2]);
+          acc.fma(A_::W0G + u * Z + i2, da, zv[i2]);
+          acc.fma(A_::W0N + u * Z + i2, dc, zv[i2]);
+          acc.fma(A_::W2G + u * Z + i2, d_agv[i2], ag[u]);
+          acc.fma(A_::W2N + u * Z + i2, d_nlv[i2], an[u]);
         }
       }
       dz += reduce_scatter<Z>(pz, zg.base, j);
 #pragma unroll
       for (int i2 = 0; i2 < Z; ++i2) {
-        awl[i2] = fmaf(d_lin, zv[i2], awl[i2]);
-        aws[i2] = fmaf(d_as, nlv[i2], aws[i2]);
+        acc.fma(A_::WL + i2, d_lin, zv[i2]);
+        acc.fma(A_::WS + i2, d_as, nlv[i2]);
       }
-      abl += d_lin; abs_ += d_as; ab2g += d_ag; ab2n += d_nl;
+      acc.add(A_::BL, d_lin); acc.add(A_::BS, d_as); acc.add(A_::B2G, d_ag); acc.add(A_::B2N, d_nl);
       c_mu = dz; c_sd = dz * eps;
       eps_cur = eps; have_eps_cur = sampled_prev;
     }
@@ -359,17 +394,22 @@ __global__ void __launch_bounds__(kZsplitThreads) zsplit_bwd_kernel(const __grid
 #pragma unroll
     for (int u = 0; u < UPL; ++u) {
       const int h = j * UPL + u;
-      atomicAdd(&sG[L_::G0B + h], ab0g[u]); atomicAdd(&sG[L_::N0B + h], ab0n[u]);
+      atomicAdd(&sG[L_::G0B + h], acc.get(A_::B0G + u)); atomicAdd(&sG[L_::N0B + h], acc.get(A_::B0N + u));
 #pragma unroll
       for (int i = 0; i < Z; ++i) {
-        atomicAdd(&sG[L_::G0W + h * Z + i], aw0g[u][i]); atomicAdd(&sG[L_::N0W + h * Z + i], aw0n[u][i]);
-        atomicAdd(&sG[L_::G2W + i * H + h], aw2g[u][i]); atomicAdd(&sG[L_::N2W + i * H + h], aw2n[u][i]);
+        atomicAdd(&sG[L_::G0W + h * Z + i], acc.get(A_::W0G + u * Z + i));
+        atomicAdd(&sG[L_::N0W + h * Z + i], acc.get(A_::W0N + u * Z + i));
+        atomicAdd(&sG[L_::G2W + i * H + h], acc.get(A_::W2G + u * Z + i));
+        atomicAdd(&sG[L_::N2W + i * H + h], acc.get(A_::W2N + u * Z + i));
       }
     }
 #pragma unroll
-    for (int i = 0; i < Z; ++i) { atomicAdd(&sG[L_::LW + j * Z + i], awl[i]); atomicAdd(&sG[L_::SW + j * Z + i], aws[i]); }
-    atomicAdd(&sG[L_::LB + j], abl); atomicAdd(&sG[L_::SB + j], abs_);
-    atomicAdd(&sG[L_::G2B + j], ab2g); atomicAdd(&sG[L_::N2B + j], ab2n);
+    for (int i = 0; i < Z; ++i) {
+      atomicAdd(&sG[L_::LW + j * Z + i], acc.get(A_::WL + i));
+      atomicAdd(&sG[L_::SW + j * Z + i], acc.get(A_::WS + i));
+    }
+    atomicAdd(&sG[L_::LB + j], acc.get(A_::BL)); atomicAdd(&sG[L_::SB + j], acc.get(A_::BS));
+    atomicAdd(&sG[L_::G2B + j], acc.get(A_::B2G)); atomicAdd(&sG[L_::N2B + j], acc.get(A_::B2N));
     atomicAdd(&sG[L_::SIZE + j], d_gm); atomicAdd(&sG[L_::SIZE + Z + j], d_gs);
   }
   __syncthreads();
