@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BFVI_VERSION 110 /* 0.1.1: large-dim (tcgen05) family entry points */
+#define BFVI_VERSION 112 /* 0.1.1: large-dim (tcgen05) family, Bernoulli / categorical likelihoods */
 
 #define BFVI_MAX_MODS 16
 #define BFVI_MAX_SETS (BFVI_MAX_MODS + 1)
@@ -244,6 +244,55 @@ int bfvi_nll_gauss_fwd(const float* mean, const float* std, const float* x,
 int bfvi_nll_gauss_bwd(const float* mean, const float* std, const float* x,
                        const uint8_t* row_mask, int64_t n_rows, int32_t d, float g,
                        float* d_mean, float* d_std, void* stream);
+
+/* losses.nll_bernoulli (models/losses.py:23-42): binary cross-entropy summed over the
+ * observed (x not NaN) elements of the rows row_mask keeps; theta, x: (n_rows, d).
+ * Clamps as F.binary_cross_entropy: log terms >= -100, gradient denominator >= 1e-12. */
+int bfvi_nll_bernoulli_fwd(const float* theta, const float* x, const uint8_t* row_mask,
+                           int64_t n_rows, int32_t d, double* out, void* stream);
+int bfvi_nll_bernoulli_bwd(const float* theta, const float* x, const uint8_t* row_mask,
+                           int64_t n_rows, int32_t d, float g, float* d_theta, void* stream);
+
+/* losses.nll_categorical (models/losses.py:44-66): -sum over observed rows of
+ * probs[row, (long)x[row]] (the reference feeds probabilities, not log-probabilities,
+ * to F.nll_loss; kept).  probs: (n_rows, n_cat); x: (n_rows) float labels, NaN = missing. */
+int bfvi_nll_categorical_fwd(const float* probs, const float* x, const uint8_t* row_mask,
+                             int64_t n_rows, int32_t n_cat, double* out, void* stream);
+int bfvi_nll_categorical_bwd(const float* probs, const float* x, const uint8_t* row_mask,
+                             int64_t n_rows, int32_t n_cat, float g, float* d_probs, void* stream);
+
+/* ---- batch preparation either side of the step -------------------
+ * Time-first (T, B, D...) fp32 batches, missing = NaN, as datasets/multiseq.py builds them. */
+
+/* len_to_mask (datasets/multiseq.py:321-327): mask[t, b] = t < lengths[b], (T, B) uint8. */
+int bfvi_len_to_mask(const int32_t* lengths, int32_t T, int32_t B, uint8_t* mask, void* stream);
+
+/* pad_and_merge (datasets/multiseq.py:342-353): sequences packed back to back as rows of D
+ * floats; row_start (B + 1, device) = first packed row of each sequence.  out (T, B, D),
+ * NaN beyond each sequence's end. */
+int bfvi_pad_merge(const float* packed, const int64_t* row_start, int32_t T, int32_t B,
+                   int64_t D, float* out, void* stream);
+
+/* func_delete (datasets/multiseq.py:405-420): out = copy of x with rows (t, b) set to NaN.
+ * _rows: explicit (T, B) flags (any del_func; the host replays the reference's numpy draws).
+ * _spans: rows lo[b] <= t < hi[b] (burst_delete :428-434, del_segment :443-448), or with
+ *   invert = 1 every row of [0, lengths[b]) OUTSIDE the span (keep_segment :436-441);
+ *   lengths nullable = T. */
+int bfvi_delete_rows(const float* x, const uint8_t* del_mask, int32_t T, int32_t B, int64_t D,
+                     float* out, void* stream);
+int bfvi_delete_spans(const float* x, const int32_t* lo, const int32_t* hi,
+                      const int32_t* lengths, int32_t invert, int32_t T, int32_t B, int64_t D,
+                      float* out, void* stream);
+
+/* Device-side draw of the deleted rows (seeded Philox stream instead of numpy's global
+ * generator): BFVI_DELETE_UNIFORM = rand_delete (:422-426), exactly int(frac * length)
+ * steps of each sequence, uniformly without replacement; BFVI_DELETE_BURST = burst_delete
+ * (:428-434).  Writes (T, B) flags for bfvi_delete_rows.  stream_id separates modalities,
+ * b_offset = global index of local sequence 0 (data parallel). */
+enum { BFVI_DELETE_UNIFORM = 0, BFVI_DELETE_BURST = 1 };
+int bfvi_draw_deletions(const int32_t* lengths, int32_t T, int32_t B, double frac, int32_t mode,
+                        uint64_t seed, uint32_t stream_id, uint32_t b_offset, uint8_t* del_mask,
+                        void* stream);
 
 /* Whole MultiDMM.step + backward (models/dmm.py:503-554, trainer.py:237-243).
  * loss_out[0] (device fp32) = un-normalised summed loss; grads (nullable: forward

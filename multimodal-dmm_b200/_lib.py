@@ -133,6 +133,16 @@ SYMBOLS = {
     'bfvi_nll_gauss_fwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     'bfvi_nll_gauss_bwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_float]
                            + [C.c_void_p] * 3),
+    'bfvi_nll_bernoulli_fwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    'bfvi_nll_bernoulli_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    'bfvi_nll_categorical_fwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    'bfvi_nll_categorical_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
+    'bfvi_len_to_mask': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    'bfvi_pad_merge': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    'bfvi_delete_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    'bfvi_delete_spans': (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    'bfvi_draw_deletions': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_uint64, C.c_uint32,
+                                      C.c_uint32, C.c_void_p, C.c_void_p]),
     'bfvi_step_workspace': (C.c_int, [C.POINTER(Model), C.POINTER(StepArgs), C.POINTER(C.c_size_t)]),
     'bfvi_step_fwd_bwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.POINTER(StepArgs),
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32),

@@ -12,6 +12,7 @@
 #include "bfvi_small.cuh"
 #include "bfvi_tc.cuh"
 #include "bfvi_generic.cuh"
+#include "bfvi_data.cuh"
 
 namespace {
 
@@ -1209,6 +1210,119 @@ int bfvi_nll_gauss_bwd(const float* mean, const float* std, const float* x, cons
   auto k = bfvi::nll_gauss_kernel;
   BFVI_LAUNCH(k, dim3(grid_for(n_rows * d, 256, 8)), dim3(256), 0, (cudaStream_t)stream, mean, std, x, row_mask,
               n_rows, (int)d, (double*)nullptr, g, d_mean, d_std);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+namespace {
+int launch_bernoulli(const float* theta, const float* x, const uint8_t* row_mask, int64_t n_rows, int d,
+                     double* out, float g, float* d_theta, cudaStream_t st) {
+  const int64_t n = n_rows * d;
+  const bool vec = d % 4 == 0 && ((uintptr_t)theta % 16 == 0) && ((uintptr_t)x % 16 == 0) &&
+                   (d_theta == nullptr || (uintptr_t)d_theta % 16 == 0);
+  // 16 resident 256-thread CTAs per SM, 4 elements per thread and trip
+  const dim3 grid(grid_for((n + (vec ? 3 : 0)) / (vec ? 4 : 1), 256, 8)), block(256);
+  if (vec) { auto k = bfvi::nll_bernoulli_kernel<true>; BFVI_LAUNCH(k, grid, block, 0, st, theta, x, row_mask, n_rows, d, out, g, d_theta); }
+  else { auto k = bfvi::nll_bernoulli_kernel<false>; BFVI_LAUNCH(k, grid, block, 0, st, theta, x, row_mask, n_rows, d, out, g, d_theta); }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+}  // namespace
+
+int bfvi_nll_bernoulli_fwd(const float* theta, const float* x, const uint8_t* row_mask, int64_t n_rows,
+                           int32_t d, double* out, void* stream) {
+  if (!theta || !x || !out || n_rows < 1 || d < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  return launch_bernoulli(theta, x, row_mask, n_rows, d, out, 0.f, nullptr, st);
+}
+
+int bfvi_nll_bernoulli_bwd(const float* theta, const float* x, const uint8_t* row_mask, int64_t n_rows,
+                           int32_t d, float g, float* d_theta, void* stream) {
+  if (!theta || !x || !d_theta || n_rows < 1 || d < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  return launch_bernoulli(theta, x, row_mask, n_rows, d, nullptr, g, d_theta, (cudaStream_t)stream);
+}
+
+int bfvi_nll_categorical_fwd(const float* probs, const float* x, const uint8_t* row_mask, int64_t n_rows,
+                             int32_t n_cat, double* out, void* stream) {
+  if (!probs || !x || !out || n_rows < 1 || n_cat < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(out, 0, sizeof(double), st);
+  auto k = bfvi::nll_categorical_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows, 256, 8)), dim3(256), 0, st, probs, x, row_mask, n_rows, (int)n_cat, out, 0.f,
+              (float*)nullptr);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_nll_categorical_bwd(const float* probs, const float* x, const uint8_t* row_mask, int64_t n_rows,
+                             int32_t n_cat, float g, float* d_probs, void* stream) {
+  if (!probs || !x || !d_probs || n_rows < 1 || n_cat < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::nll_categorical_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for(n_rows, 256, 8)), dim3(256), 0, (cudaStream_t)stream, probs, x, row_mask, n_rows,
+              (int)n_cat, (double*)nullptr, g, d_probs);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+// ---- batch preparation (datasets/multiseq.py), bfvi_data.cuh ------------------------------------
+namespace {
+int launch_delete(bfvi::DeleteParams dp, cudaStream_t st) {
+  const int64_t n = (int64_t)dp.T * dp.B * dp.D;
+  const bool vec = dp.D % 4 == 0 && (uintptr_t)dp.x % 16 == 0 && (uintptr_t)dp.out % 16 == 0;
+  const dim3 grid(grid_for(vec ? n / 4 : n, 256, 8)), block(256);
+  if (vec) { auto k = bfvi::delete_rows_kernel<true>; BFVI_LAUNCH(k, grid, block, 0, st, dp); }
+  else { auto k = bfvi::delete_rows_kernel<false>; BFVI_LAUNCH(k, grid, block, 0, st, dp); }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+}  // namespace
+
+int bfvi_len_to_mask(const int32_t* lengths, int32_t T, int32_t B, uint8_t* mask, void* stream) {
+  if (!lengths || !mask || T < 1 || B < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  auto k = bfvi::len_to_mask_kernel;
+  BFVI_LAUNCH(k, dim3(grid_for((int64_t)T * B, 256, 8)), dim3(256), 0, (cudaStream_t)stream, lengths, (int)T, (int)B, mask);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_pad_merge(const float* packed, const int64_t* row_start, int32_t T, int32_t B, int64_t D, float* out,
+                   void* stream) {
+  if (!packed || !row_start || !out || T < 1 || B < 1 || D < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  const int64_t n = (int64_t)T * B * D;
+  const bool vec = D % 4 == 0 && (uintptr_t)packed % 16 == 0 && (uintptr_t)out % 16 == 0;
+  const dim3 grid(grid_for(vec ? n / 4 : n, 256, 8)), block(256);
+  if (vec) { auto k = bfvi::pad_merge_kernel<true>; BFVI_LAUNCH(k, grid, block, 0, (cudaStream_t)stream, packed, row_start, (int)T, (int)B, D, out); }
+  else { auto k = bfvi::pad_merge_kernel<false>; BFVI_LAUNCH(k, grid, block, 0, (cudaStream_t)stream, packed, row_start, (int)T, (int)B, D, out); }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_delete_rows(const float* x, const uint8_t* del_mask, int32_t T, int32_t B, int64_t D, float* out,
+                     void* stream) {
+  if (!x || !del_mask || !out || T < 1 || B < 1 || D < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi::DeleteParams dp{};
+  dp.x = x; dp.out = out; dp.T = T; dp.B = B; dp.D = D; dp.del_mask = del_mask;
+  return launch_delete(dp, (cudaStream_t)stream);
+}
+
+int bfvi_delete_spans(const float* x, const int32_t* lo, const int32_t* hi, const int32_t* lengths, int32_t invert,
+                      int32_t T, int32_t B, int64_t D, float* out, void* stream) {
+  if (!x || !lo || !hi || !out || T < 1 || B < 1 || D < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  bfvi::DeleteParams dp{};
+  dp.x = x; dp.out = out; dp.T = T; dp.B = B; dp.D = D; dp.lo = lo; dp.hi = hi; dp.lengths = lengths;
+  dp.invert = invert != 0;
+  return launch_delete(dp, (cudaStream_t)stream);
+}
+
+int bfvi_draw_deletions(const int32_t* lengths, int32_t T, int32_t B, double frac, int32_t mode, uint64_t seed,
+                        uint32_t stream_id, uint32_t b_offset, uint8_t* del_mask, void* stream) {
+  if (!del_mask || T < 1 || B < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (mode != BFVI_DELETE_UNIFORM && mode != BFVI_DELETE_BURST) return fail(BFVI_ERR_ARG, "unknown deletion mode %d", (int)mode);
+  if (!(frac >= 0.0 && frac <= 1.0)) return fail(BFVI_ERR_ARG, "deleted fraction %g outside [0, 1]", frac);
+  auto k = bfvi::draw_deletions_kernel;
+  BFVI_LAUNCH(k, dim3((B + 127) / 128), dim3(128), 0, (cudaStream_t)stream, lengths, (int)T, (int)B, frac, (int)mode, seed,
+              (unsigned)stream_id, (unsigned)b_offset, del_mask);
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }

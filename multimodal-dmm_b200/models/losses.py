@@ -1,13 +1,12 @@
 """Loss functions with the reference signatures (models/losses.py:14-89).
 
-kld_gauss and nll_gauss run as CUDA kernels (bfvi_kld_*, bfvi_nll_gauss_*) wrapped
-in autograd Functions; the Bernoulli / categorical likelihoods (Weizmann-shaped
-models only) are device-side tensor ops with the reference's exact semantics,
-including its quirk of feeding probabilities to nll_loss."""
+Every loss runs as a CUDA kernel of libbfvi_b200 (bfvi_kld_*, bfvi_nll_gauss_*,
+bfvi_nll_bernoulli_*, bfvi_nll_categorical_*) wrapped in an autograd Function, with
+the reference's exact semantics, including its quirk of feeding probabilities to
+nll_loss in the categorical likelihood."""
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
 
 from .. import _lib
 
@@ -113,24 +112,87 @@ def nll_gauss(mean, std, x, mask=None):
     return _NllGauss.apply(mean.expand(x.shape), std.expand(x.shape), x, rmask, rows)
 
 
-def _elem_mask(x, mask):
-    obs = ~torch.isnan(x)
+def _lead_mask(mask, x, what):
+    """Row mask over the leading (T, B) dims of x as flat uint8 (None = every row)."""
     if mask is None:
-        return obs
-    shape = list(mask.shape) + [1] * (x.dim() - mask.dim())
-    return obs & mask.bool().view(*shape)
+        return None, x.shape[:2]
+    m = mask
+    while m.dim() > 2 and m.shape[-1] == 1:
+        m = m.squeeze(-1)
+    rmask = _row_mask(m, x.shape[:m.dim()])
+    if rmask is False or m.dim() != 2:
+        raise _lib.BfviError('%s: mask %s does not broadcast over x %s' % (what, tuple(mask.shape), tuple(x.shape)))
+    return rmask, x.shape[:2]
+
+
+class _NllBernoulli(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, x, rmask, rows):
+        lib = _lib.load()
+        th, xv = theta.detach().contiguous().float(), x.detach().contiguous().float()
+        d = xv.numel() // rows
+        out = torch.zeros(1, dtype=torch.float64, device=th.device)
+        lib.call('bfvi_nll_bernoulli_fwd', _lib.ptr(th), _lib.ptr(xv), _lib.ptr(rmask), rows, d,
+                 _lib.ptr(out), _stream())
+        ctx.save_for_backward(th, xv)
+        ctx.rmask, ctx.rows, ctx.shape = rmask, rows, theta.shape
+        return out.sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        th, xv = ctx.saved_tensors
+        d_th = torch.empty_like(th)
+        lib.call('bfvi_nll_bernoulli_bwd', _lib.ptr(th), _lib.ptr(xv), _lib.ptr(ctx.rmask), ctx.rows,
+                 xv.numel() // ctx.rows, C.c_float(1.0), _lib.ptr(d_th), _stream())
+        return d_th.reshape(ctx.shape) * g, None, None, None
 
 
 def nll_bernoulli(theta, x, mask=None):
-    """models/losses.py:23-42."""
+    """Bernoulli NLL (binary cross-entropy, summed) over observed in-sequence elements,
+    models/losses.py:23-42; theta, x: (T, B, D, ...), mask: (T, B[, 1...])."""
     _require_cuda(theta, x, mask)
-    keep = _elem_mask(x, mask)
-    return F.binary_cross_entropy(theta.masked_select(keep), x.masked_select(keep), reduction='sum')
+    rmask, lead = _lead_mask(mask, x, 'nll_bernoulli')
+    rows = int(lead[0]) * int(lead[1])
+    if rows == 0 or x.numel() == 0:
+        return theta.sum() * 0.0
+    return _NllBernoulli.apply(theta.expand(x.shape), x, rmask, rows)
+
+
+class _NllCategorical(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, probs, x, rmask, rows):
+        lib = _lib.load()
+        pr, xv = probs.detach().contiguous().float(), x.detach().contiguous().float()
+        n_cat = pr.numel() // rows
+        out = torch.zeros(1, dtype=torch.float64, device=pr.device)
+        lib.call('bfvi_nll_categorical_fwd', _lib.ptr(pr), _lib.ptr(xv), _lib.ptr(rmask), rows, n_cat,
+                 _lib.ptr(out), _stream())
+        ctx.save_for_backward(pr, xv)
+        ctx.rmask, ctx.rows, ctx.n_cat, ctx.shape = rmask, rows, n_cat, probs.shape
+        return out.sum().to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        pr, xv = ctx.saved_tensors
+        d_pr = torch.empty_like(pr)
+        lib.call('bfvi_nll_categorical_bwd', _lib.ptr(pr), _lib.ptr(xv), _lib.ptr(ctx.rmask), ctx.rows,
+                 ctx.n_cat, C.c_float(1.0), _lib.ptr(d_pr), _stream())
+        return d_pr.reshape(ctx.shape) * g, None, None, None
 
 
 def nll_categorical(probs, x, mask=None):
-    """models/losses.py:44-66 (value is -sum p[label]; quirk preserved)."""
+    """Categorical NLL as the reference computes it, models/losses.py:44-66: F.nll_loss fed with
+    probabilities, i.e. -sum p[label] over observed in-sequence rows (quirk preserved).
+    probs: (T, B, K[, 1]), x: (T, B[, 1]) float labels (NaN = missing).  Like the reference, only a
+    scalar label per (t, b) is meaningful (its mask/probs broadcast fails for wider label tensors)."""
     _require_cuda(probs, x, mask)
-    keep = _elem_mask(x, mask)
-    cols = [probs[:, :, k:k + 1].masked_select(keep) for k in range(probs.shape[2])]
-    return F.nll_loss(torch.stack(cols, dim=-1), x.masked_select(keep).long(), reduction='sum')
+    rmask, lead = _lead_mask(mask, x, 'nll_categorical')
+    rows = int(lead[0]) * int(lead[1])
+    if rows == 0:
+        return probs.sum() * 0.0
+    if x.numel() != rows or probs.numel() % rows != 0 or probs.shape[:2] != x.shape[:2]:
+        raise _lib.BfviError('nll_categorical: one label per (t, b) expected; probs %s, x %s'
+                             % (tuple(probs.shape), tuple(x.shape)))
+    return _NllCategorical.apply(probs, x, rmask, rows)
