@@ -143,9 +143,10 @@ __device__ __forceinline__ void poe_step_backward(const bfvi_filter_args& a, uns
     const float inv_s = sd[i] * sd[i];          // 1 / sum of precisions
     d_n[i] = d_mu[i] * inv_s;
     d_s[i] = -d_mu[i] * mu[i] * inv_s - 0.5f * d_sd[i] * sd[i] * inv_s;
-    const float tp = poe_prec(ps[i]);
+    float tp, dtp;
+    poe_prec_bwd(ps[i], tp, dtp);
     d_pm[i] += d_n[i] * tp;
-    d_ps[i] += (d_n[i] * pm[i] + d_s[i]) * poe_prec_grad(ps[i], tp);
+    d_ps[i] += (d_n[i] * pm[i] + d_s[i]) * dtp;
   }
   for (int e = 0; e < a.n_experts; ++e) {
     if (!((bits >> e) & 1u)) continue;
@@ -158,18 +159,21 @@ __device__ __forceinline__ void poe_step_backward(const bfvi_filter_args& a, uns
     if (ex.kind == BFVI_EXPERT_INV_PRIOR) {
 #pragma unroll
       for (int i = 0; i < Z; ++i) {
-        const float std = -gs[i], te = poe_prec(std);
         if (emit) {
+          float te, dte;
+          poe_prec_bwd(-gs[i], te, dte);
           d_gm[i] += d_n[i] * te;
-          d_gs[i] -= (d_n[i] * gm[i] + d_s[i]) * poe_prec_grad(std, te);
+          d_gs[i] -= (d_n[i] * gm[i] + d_s[i]) * dte;
         }
       }
     } else if (ex.d_mean != nullptr && emit) {
 #pragma unroll
       for (int i = 0; i < Z; ++i) {
-        const float mean = ex.mean[off + i], std = ex.std[off + i], te = poe_prec(std);
+        const float mean = ex.mean[off + i];
+        float te, dte;
+        poe_prec_bwd(ex.std[off + i], te, dte);
         atomicAdd(ex.d_mean + off + i, d_n[i] * te);
-        atomicAdd(ex.d_std + off + i, (d_n[i] * mean + d_s[i]) * poe_prec_grad(std, te));
+        atomicAdd(ex.d_std + off + i, (d_n[i] * mean + d_s[i]) * dte);
       }
     }
   }
@@ -605,7 +609,7 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
       for (int j = 0; j < Z; ++j) {
         mu_p[j] = a.infer_mean[op + j]; sd_p[j] = a.infer_std[op + j];
         mu_c[j] = mu_p[j]; sd_c[j] = sd_p[j];
-        d_v[j] = d_ps[j] * 0.5f / ps[j];
+        d_v[j] = d_ps[j] * 0.5f * fast_rcp(ps[j]);
         c_mu[j] = c_sd[j] = 0.f;
       }
       const bool sampled_prev = pass_samples(a, i - 1);
@@ -766,7 +770,7 @@ __global__ void __launch_bounds__(32) match_kernel(const __grid_constant__ Match
     kld_elem_grad(sGm[j], sGs[j], nm[j], ns[j], coef, g1, g2, d_nm[j], d_ns);
     d_gm[j] = lane == 0 ? g1 : 0.f;
     d_gs[j] = lane == 0 ? g2 : 0.f;
-    d_v[j] = d_ns * 0.5f / ns[j];
+    d_v[j] = d_ns * 0.5f * fast_rcp(ns[j]);
   }
   float2 acc[TD][kTX];
 #pragma unroll

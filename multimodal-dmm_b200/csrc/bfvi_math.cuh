@@ -62,7 +62,11 @@ struct GtfPack {
   static constexpr int STD = LIN + Z * RW;
   static constexpr int B2G = STD + Z * RW;
   static constexpr int B2N = B2G + pad4(Z);
-  static constexpr int SIZE = B2N + pad4(Z);
+  // the two hidden branches interleaved: unit h, column c -> (gate, nonlin) adjacent, so one
+  // 128-bit load yields two register PAIRS for packed FFMA2 (bfvi_wgrad.cuh: ffma2)
+  static constexpr int U2 = 2 * U;
+  static constexpr int PAIR = B2N + pad4(Z);
+  static constexpr int SIZE = PAIR + H * U2;
 };
 
 // cooperative re-pack global flat GTF block -> shared GtfPack (all threads of the CTA)
@@ -90,9 +94,16 @@ __device__ inline void gtf_pack_load(const float* __restrict__ w, float* __restr
     } else if (i < P::B2N) {
       const int o = i - P::B2G;
       if (o < Z) v = w[L::G2B + o];
-    } else {
+    } else if (i < P::PAIR) {
       const int o = i - P::B2N;
       if (o < Z) v = w[L::N2B + o];
+    } else {
+      const int j = i - P::PAIR;
+      const int h = j / P::U2, c = (j % P::U2) >> 1, br = j & 1;
+      const int w0 = br ? L::N0W : L::G0W, b0 = br ? L::N0B : L::G0B, w2 = br ? L::N2W : L::G2W;
+      if (c == 0) v = w[b0 + h];
+      else if (c <= Z) v = w[w0 + h * Z + (c - 1)];
+      else if (c <= 2 * Z) v = w[w2 + (c - 1 - Z) * H + h];
     }
     sP[i] = v;
   }
@@ -172,6 +183,19 @@ __device__ __forceinline__ float sign_f(float x) { return x > 0.f ? 1.f : (x < 0
 // ------------------------------------------------------------------ GTF forward
 // R rows per thread; q'(z_next | z) mean / std (models/common.py:62-68) of row r,
 // component o are handed to `epi(r, o, mean, std)` as soon as they are complete.
+#ifndef BFVI_GTF_PAIR
+#define BFVI_GTF_PAIR 1          // packed-FFMA2 hidden layers in the backward kernel (A/B build knob)
+#endif
+__device__ __forceinline__ float2 ffma2_rn(float2 a, float2 b, float2 c) {
+#ifdef BFVI_EMU
+  return float2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)};
+#else
+  return __ffma2_rn(a, b, c);
+#endif
+}
+// (R rows per lane stay scalar FFMA: pairing the branches needs every z duplicated into a
+//  register pair, which spills at 128 registers; pairing only the second layer measured
+//  1 % SLOWER at C2 — the kernel is bound by dependent-issue latency, not FMA issue slots.)
 template <int Z, int H, int R, typename Epi>
 __device__ __forceinline__ void gtf_rows_forward(const float* __restrict__ sP, float min_std,
                                                  const float (&z)[R][Z], Epi&& epi) {
@@ -236,6 +260,27 @@ __device__ __forceinline__ void gtf_row_forward_stage(const float* __restrict__ 
                                                       float (&as)[Z], float* __restrict__ Xp, int lane) {
   using P = GtfPack<Z, H>;
   using C = GtfCols<Z, H>;
+#if BFVI_GTF_PAIR
+  // one row per lane: (gate, nonlin) register pairs through both hidden layers, FFMA2 throughout
+  float2 gn[Z], zz[Z];
+#pragma unroll
+  for (int o = 0; o < Z; ++o) { gn[o] = float2{sP[P::B2G + o], sP[P::B2N + o]}; zz[o] = float2{z[o], z[o]}; }
+#pragma unroll 4
+  for (int h = 0; h < H; ++h) {
+    float w[P::U2];
+    lds_vec<P::U2>(sP + P::PAIR + h * P::U2, w);
+    float2 ac{w[0], w[1]};
+#pragma unroll
+    for (int i = 0; i < Z; ++i) ac = ffma2_rn(float2{w[2 + 2 * i], w[3 + 2 * i]}, zz[i], ac);
+    ac.x = relu_f(ac.x); ac.y = relu_f(ac.y);
+    Xp[panel_at(C::XH1 + 1 + h, lane)] = ac.x;
+    Xp[panel_at(C::XH3 + 1 + h, lane)] = ac.y;
+#pragma unroll
+    for (int o = 0; o < Z; ++o) gn[o] = ffma2_rn(float2{w[2 + 2 * (Z + o)], w[3 + 2 * (Z + o)]}, ac, gn[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < Z; ++o) { g[o] = gn[o].x; nl[o] = gn[o].y; }
+#else
 #pragma unroll
   for (int o = 0; o < Z; ++o) { g[o] = sP[P::B2G + o]; nl[o] = sP[P::B2N + o]; }
 #pragma unroll 4
@@ -252,6 +297,7 @@ __device__ __forceinline__ void gtf_row_forward_stage(const float* __restrict__ 
 #pragma unroll
     for (int o = 0; o < Z; ++o) { g[o] = fmaf(wg[1 + Z + o], a, g[o]); nl[o] = fmaf(wn[1 + Z + o], c, nl[o]); }
   }
+#endif
 #pragma unroll
   for (int o = 0; o < Z; ++o) {
     float wl[P::RW], ws[P::RW];
@@ -309,6 +355,28 @@ __device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__
     Dp[panel_at(C::DNL + o, lane)] = d_nl[o];
     Dp[panel_at(C::DAS + o, lane)] = d_as[o];
   }
+#if BFVI_GTF_PAIR
+  float2 dd[Z], dzz[Z];                                    // (gate path, nonlin path) pairs
+#pragma unroll
+  for (int o = 0; o < Z; ++o) { dd[o] = float2{d_ag[o], d_nl[o]}; dzz[o] = float2{0.f, 0.f}; }
+#pragma unroll 4
+  for (int h = 0; h < H; ++h) {
+    float w[P::U2];
+    lds_vec<P::U2>(sP + P::PAIR + h * P::U2, w);
+    const float h1 = Xp[panel_at(C::XH1 + 1 + h, lane)], h3 = Xp[panel_at(C::XH3 + 1 + h, lane)];
+    float2 dac{0.f, 0.f};
+#pragma unroll
+    for (int o = 0; o < Z; ++o) dac = ffma2_rn(float2{w[2 + 2 * (Z + o)], w[3 + 2 * (Z + o)]}, dd[o], dac);
+    dac.x = h1 > 0.f ? dac.x : 0.f;
+    dac.y = h3 > 0.f ? dac.y : 0.f;
+#pragma unroll
+    for (int i = 0; i < Z; ++i) dzz[i] = ffma2_rn(float2{w[2 + 2 * i], w[3 + 2 * i]}, dac, dzz[i]);
+    Dp[panel_at(C::DA1 + h, lane)] = dac.x;
+    Dp[panel_at(C::DA3 + h, lane)] = dac.y;
+  }
+#pragma unroll
+  for (int i = 0; i < Z; ++i) dz[i] += dzz[i].x + dzz[i].y;
+#else
 #pragma unroll 4
   for (int h = 0; h < H; ++h) {
     float wg[P::U], wn[P::U];
@@ -325,6 +393,7 @@ __device__ __forceinline__ void gtf_row_backward_stage(const float* __restrict__
     Dp[panel_at(C::DA1 + h, lane)] = da;
     Dp[panel_at(C::DA3 + h, lane)] = dc;
   }
+#endif
 }
 
 // ------------------------------------------------ product / mixture of experts
@@ -336,6 +405,14 @@ __device__ __forceinline__ float poe_prec(float std) {
 // d prec / d std
 __device__ __forceinline__ float poe_prec_grad(float std, float prec) {
   return -2.f * std * prec / (std * std + kPoeEps);
+}
+// Backward-pass form of both: gradients only need the reciprocal to an ulp or two, so the MUFU
+// reciprocal replaces two IEEE divisions (whose slow paths were 7 % of the dominant kernel's
+// stall samples); the FORWARD keeps poe_prec, its values feed the inverse-prior cancellation.
+__device__ __forceinline__ void poe_prec_bwd(float std, float& prec, float& dprec) {
+  const float r = fast_rcp(fmaf(std, std, kPoeEps));
+  prec = r * sign_f(std);
+  dprec = -2.f * std * prec * r;
 }
 
 // p(z|z_prev) = p(z) * q'(z|z_prev)   (models/dmm.py:239-245), one component, both
@@ -377,11 +454,11 @@ __device__ __forceinline__ float kld_elem_fast(float m1, float s1, float m2, flo
 }
 __device__ __forceinline__ void kld_elem_grad(float m1, float s1, float m2, float s2, float c,
                                               float& d_m1, float& d_s1, float& d_m2, float& d_s2) {
-  const float dm = m1 - m2, iv = 1.f / (s2 * s2);
+  const float dm = m1 - m2, r2 = fast_rcp(s2), iv = r2 * r2;
   d_m1 = c * dm * iv;
   d_m2 = -d_m1;
-  d_s1 = c * (s1 * iv - 1.f / s1);
-  d_s2 = c * (1.f / s2 - (s1 * s1 + dm * dm) * iv / s2);
+  d_s1 = c * (s1 * iv - fast_rcp(s1));
+  d_s2 = c * (r2 - (s1 * s1 + dm * dm) * iv * r2);
 }
 __device__ __forceinline__ float nll_gauss_elem(float mean, float std, float x) {
   const float r = (x - mean) / std;

@@ -298,9 +298,10 @@ zsplit_bwd_kernel(const __grid_constant__ FilterParams p) {
         const float inv_s = sd * sd;
         const float d_n = d_mu * inv_s;
         const float d_s = -d_mu * mu * inv_s - 0.5f * d_sd * sd * inv_s;
-        const float tp = poe_prec(ps);
+        float tp, dtp;
+        poe_prec_bwd(ps, tp, dtp);
         d_pm += d_n * tp;
-        d_ps += (d_n * pm + d_s) * poe_prec_grad(ps, tp);
+        d_ps += (d_n * pm + d_s) * dtp;
         for (int e = 0; e < a.n_experts; ++e) {
           if (!((bits >> e) & 1u)) continue;
           const bfvi_expert& ex = a.experts[e];
@@ -309,14 +310,17 @@ zsplit_bwd_kernel(const __grid_constant__ FilterParams p) {
           if (ex.zero_mask_last_t && t == T - 1) m = false;
           if (!m) continue;
           if (ex.kind == BFVI_EXPERT_INV_PRIOR) {
-            const float std = -gs, te = poe_prec(std);
+            float te, dte;
+            poe_prec_bwd(-gs, te, dte);
             d_gm += vm * d_n * te;
-            d_gs -= vm * (d_n * gm + d_s) * poe_prec_grad(std, te);
+            d_gs -= vm * (d_n * gm + d_s) * dte;
           } else if (ex.d_mean != nullptr && ok) {
             const int64_t off = s * ex.stride_s + t * ex.stride_t + b * ex.stride_b + j;
-            const float mean = ex.mean[off], std = ex.std[off], te = poe_prec(std);
+            const float mean = ex.mean[off];
+            float te, dte;
+            poe_prec_bwd(ex.std[off], te, dte);
             atomicAdd(ex.d_mean + off, d_n * te);
-            atomicAdd(ex.d_std + off, (d_n * mean + d_s) * poe_prec_grad(std, te));
+            atomicAdd(ex.d_std + off, (d_n * mean + d_s) * dte);
           }
         }
       }
