@@ -171,6 +171,12 @@ int task_grid(int64_t chains, int lanes, int warps_per_block) {
   return (int)(blocks < cap ? blocks : cap);
 }
 
+size_t align_up(size_t v, size_t a);
+// scratch of the time-segmented backward filter: per-task flags + the (S, B, 2Z) gradient carry
+size_t seg_scratch_bytes(int S, int B, int Z) {
+  return align_up(sizeof(int) * (size_t)S * B, 256) + align_up(sizeof(float) * (size_t)S * B * 2 * Z, 256);
+}
+
 template <int Z, int H>
 int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
@@ -229,9 +235,66 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   if (latency_bound_pass(chains, a.n_particles)) fp.lanes = a.n_particles < 32 ? a.n_particles : 32;
   else choose_lanes(a.n_particles, 1, chains, &fp.lanes, &rounds);
   fp.slices = (a.n_particles + fp.lanes - 1) / fp.lanes;
-  auto k = bfvi::chain_bwd_kernel<Z, H>;
+  auto k1 = bfvi::chain_bwd_kernel<Z, H, false>;
+  auto k = bfvi::chain_bwd_kernel<Z, H, true>;
+  cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
+  // Time segmentation (chain_bwd_kernel): when the warp tasks do not fill a whole number of rounds
+  // of the resident warps, cut the time loop into the segment count that packs best.
+  const int cpw = 32 / fp.lanes;
+  const int64_t tasks = (chains + cpw - 1) / cpw;
+  int n_seg = 1;
+  int64_t resident_blocks = 0;
+  const size_t seg_need = seg_scratch_bytes(a.S, a.B, Z);
+  if (a.n_particles > 1 && warps == bfvi::kChainBwdWarps && a.workspace != nullptr && a.workspace_bytes >= seg_need) {
+#ifdef BFVI_EMU
+    resident_blocks = 2;                                   // exercises the multi-launch form on the CPU
+#else
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) == cudaSuccess)
+      resident_blocks = (int64_t)per_sm * (num_sms() > 0 ? num_sms() : 1);
+#endif
+    const int64_t slots = resident_blocks * warps;
+    if (slots > 0 && tasks > slots) {
+      double best = (double)((tasks + slots - 1) / slots);       // rounds, in units of a whole task
+      for (int sg = 2; sg <= 8 && sg <= a.T; ++sg) {
+        const double r = (double)((tasks * sg + slots - 1) / slots) / sg;
+        if (r < 0.95 * best) { best = r; n_seg = sg; }
+      }
+    }
+    if (const char* env = getenv("BFVI_BWD_SEGMENTS")) {         // tuning / test knob (1 = off)
+      const int v = atoi(env);
+      if (v >= 1 && v <= 16 && v <= a.T) n_seg = v;
+    }
+  }
+  if (n_seg == 1) {
+    BFVI_LAUNCH(k1, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
+    BFVI_CHECK_CUDA();
+    return BFVI_OK;
+  }
+  // scratch: per-task flags (S * B ints, this chunk's share) then the (S, B, 2Z) carry
+  int* flags = reinterpret_cast<int*>(a.workspace) + (size_t)a.S * fp.b0;
+  fp.seg_count = n_seg;
+  fp.seg_done = flags;
+  fp.seg_carry = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + align_up(sizeof(int) * (size_t)a.S * a.B, 256));
+#ifndef BFVI_EMU
+  const char* coop_env = getenv("BFVI_BWD_COOPERATIVE");         // 0: stream-ordered launches per segment
+  if (coop_env == nullptr || atoi(coop_env) != 0) {
+    // one cooperative launch (every warp resident, so the per-task flags cannot deadlock)
+    cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)tasks, st);
+    fp.seg_lo = 0; fp.seg_hi = n_seg;
+    int64_t blocks = (tasks * n_seg + warps - 1) / warps;
+    if (blocks > resident_blocks) blocks = resident_blocks;
+    void* args[] = {&fp};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)blocks), dim3(threads), args, smem, st);
+    if (e == cudaSuccess) { BFVI_CHECK_CUDA(); return BFVI_OK; }
+    cudaGetLastError();                                          // not launchable cooperatively here: fall through
+  }
+#endif
+  for (int sg = 0; sg < n_seg; ++sg) {                            // same work, ordered by the stream
+    fp.seg_lo = sg; fp.seg_hi = sg + 1;
+    BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
+  }
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
@@ -335,6 +398,7 @@ bfvi::FilterParams make_filter_params(const bfvi_model* m, const bfvi_layout& la
   fp.min_std = m->min_std;
   fp.lanes = 1; fp.rounds = 1; fp.slices = 1;
   fp.b0 = 0; fp.bc = 0;
+  fp.seg_count = 1; fp.seg_lo = 0; fp.seg_hi = 1; fp.seg_done = nullptr; fp.seg_carry = nullptr;
   return fp;
 }
 
@@ -376,6 +440,7 @@ struct StepPlan {
   size_t off_acc, off_count, off_obs_mean, off_obs_std, off_obs_mask, off_dobs_mean, off_dobs_std;
   size_t off_a[6], off_b[6], off_c[6];  // infer_m, infer_s, prior_m, prior_s, samples / d_prior_m, d_samples / d_prior_s
   size_t zero_begin, zero_end;          // region cleared at step start
+  size_t off_seg, seg_bytes;            // scratch of the time-segmented pass-B backward
   size_t total;
 };
 
@@ -410,6 +475,8 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   for (int i = 0; i < 5; ++i) pl->off_a[i] = carve(fS);
   for (int i = 0; i < 4; ++i) pl->off_b[i] = carve(fS);
   for (int i = 0; i < 5; ++i) pl->off_c[i] = carve(fS);
+  pl->seg_bytes = with_grad ? seg_scratch_bytes(S > 0 ? S : 1, a->B, m->z_dim) : 0;
+  pl->off_seg = carve(pl->seg_bytes);
   pl->total = cur;
 }
 
@@ -1136,6 +1203,8 @@ int bfvi_filter_workspace(const bfvi_model* m, const bfvi_filter_args* a, size_t
     LargePlan pl;
     plan_large(m, nullptr, a, &pl);
     *bytes = pl.total;
+  } else if (a->n_particles > 1) {
+    *bytes = seg_scratch_bytes(a->S, a->B, m->z_dim);     // optional: lets the backward pack its time segments
   }
   return BFVI_OK;
 }
@@ -1604,6 +1673,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     fc.d_samples = with_grad ? C(5) : nullptr;
     fb.d_prior_mean = with_grad ? Bf(4) : nullptr;
     fb.d_prior_std = with_grad ? Bf(5) : nullptr;
+    if (with_grad) { fb.workspace = ws + pl.off_seg; fb.workspace_bytes = pl.seg_bytes; }
     const Chunk all{0, 0};
 
     // ---- stream plan ------------------------------------------------------------------
@@ -1614,7 +1684,10 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     int n_chunks = 1;
     SideStreams* side = pm.on ? nullptr : side_streams();
     if (side != nullptr && do_s) {
-      n_chunks = B >= 1024 ? 2 : 1;
+      // two chunks overlap one chunk's latency-bound single-particle passes with the other's particle
+      // kernels, which pays once each chunk alone fills the GPU (measured on B200: B = 4096 and 8192 are
+      // 1 % faster unchunked, B = 16384 is 2.5 % faster in two chunks)
+      n_chunks = B >= 16384 ? 2 : 1;
       if (const char* env = getenv("BFVI_CHUNKS")) {       // tuning knob
         const int v = atoi(env);
         if (v >= 1 && v <= kSideStreams) n_chunks = v;

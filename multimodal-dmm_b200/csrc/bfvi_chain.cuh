@@ -55,6 +55,11 @@ struct FilterParams {
   int rounds;                // forward: ceil(K / (L * R))
   int slices;                // backward: ceil(K / L)
   int b0, bc;                // batch chunk [b0, b0 + bc) served by this launch (bc = 0: all of B)
+  // backward, K > 1: the time loop cut into seg_count segments that are scheduled as separate
+  // work items (task, segment) — see chain_bwd_kernel.  This launch serves [seg_lo, seg_hi).
+  int seg_count, seg_lo, seg_hi;
+  int* seg_done;             // per task: segments completed (several segments per launch only)
+  float* seg_carry;          // (S, B, 2Z): gradient carried into the next (earlier) segment
 };
 
 // -------------------------------------------------------------------------
@@ -448,7 +453,8 @@ __device__ __forceinline__ void transition_slice_backward(
   wg_tile_fma<GtfPanels<Z, H>::TD, kTX>(acc, Dp, Xp, task);
 }
 
-template <int Z, int H>
+// SEG = false compiles the time segmentation out (single-particle and small-batch launches).
+template <int Z, int H, bool SEG>
 __global__ void __launch_bounds__(kChainBwdWarps * 32, BFVI_BWD_MINB)
 chain_bwd_kernel(const __grid_constant__ FilterParams p) {
   using L_ = GtfLayout<Z, H>;
@@ -503,8 +509,21 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
 #pragma unroll
   for (int j = 0; j < Z; ++j) d_gm[j] = d_gs[j] = 0.f;
 
+  // Work items.  A warp task (32 / L chains, all T steps) is long — 2.6 ms at C2 — and a B200 holds
+  // 1184 such warps, so 2048 tasks take two full rounds with the second 27 % empty.  Cutting the
+  // time loop into segments makes the items short enough to pack the machine: item q = (segment,
+  // task), segment-major, dealt round-robin to the resident warps; (seg, task) starts from the
+  // gradient carry (c_mu, c_sd) that (seg - 1, task) left in seg_carry.  When one launch serves
+  // several segments (cooperative launch: every warp resident) the hand-over is a per-task flag.
+  const int n_seg = SEG && p.seg_count > 1 ? p.seg_count : 1;
+  const int seg_lo = SEG && n_seg > 1 ? p.seg_lo : 0, seg_n = SEG && n_seg > 1 ? p.seg_hi - p.seg_lo : 1;
+  const bool seg_flags = SEG && seg_n > 1;
+  const int n_items = n_tasks * seg_n;
   const int gwarp = blockIdx.x * n_warps + warp, total_warps = gridDim.x * n_warps;
-  for (int wt = gwarp; wt < n_tasks; wt += total_warps) {
+  for (int q = gwarp; q < n_items; q += total_warps) {
+    const int seg = seg_lo + q / n_tasks, wt = q - (q / n_tasks) * n_tasks;
+    const int i_hi = T - 1 - (int)(((int64_t)seg * T) / n_seg);
+    const int i_lo = seg + 1 < n_seg ? T - (int)(((int64_t)(seg + 1) * T) / n_seg) : 0;
     const int chain_raw = wt * lg.cpw + lg.cig;
     const bool chain_ok = lg.on && chain_raw < n_chains;
     const int chain = chain_raw < n_chains ? chain_raw : n_chains - 1;
@@ -515,14 +534,23 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
 #pragma unroll
     for (int j = 0; j < Z; ++j) c_mu[j] = c_sd[j] = eps_cur[j] = 0.f;
     bool have_eps_cur = false;
+    if (SEG && seg > 0) {
+      if (seg_flags) {
+        if (lane == 0) seg_wait(p.seg_done + wt, seg);
+        __syncwarp();
+      }
+      const float* cr = p.seg_carry + ((int64_t)s * B + b) * 2 * Z;
+#pragma unroll
+      for (int j = 0; j < Z; ++j) { c_mu[j] = ld_cg(cr + j); c_sd[j] = ld_cg(cr + Z + j); }
+    }
 
     float mu_c[Z], sd_c[Z];               // infer (mean, std) of the step being processed
     {
-      const int64_t o0 = (((int64_t)s * T + pass_time(T - 1, T, a.direction)) * B + b) * Z;
+      const int64_t o0 = (((int64_t)s * T + pass_time(i_hi, T, a.direction)) * B + b) * Z;
 #pragma unroll
       for (int j = 0; j < Z; ++j) { mu_c[j] = a.infer_mean[o0 + j]; sd_c[j] = a.infer_std[o0 + j]; }
     }
-    for (int i = T - 1; i >= 0; --i) {
+    for (int i = i_hi; i >= i_lo; --i) {
       const int t = pass_time(i, T, a.direction);
       const int64_t o = (((int64_t)s * T + t) * B + b) * Z;
       if (K == 1 && i > 0) {              // warm L1 for the next (earlier) step of this chain
@@ -648,6 +676,18 @@ chain_bwd_kernel(const __grid_constant__ FilterParams p) {
       have_eps_cur = sampled_prev;
     }
     wg_tile_flush<TD, kTX>(acc, oidx, G, lane);
+    if (SEG && seg + 1 < n_seg) {         // hand the gradient carry to the next (earlier) segment
+      if (emit) {
+        float* cw = p.seg_carry + ((int64_t)s * B + b) * 2 * Z;
+#pragma unroll
+        for (int j = 0; j < Z; ++j) { cw[j] = c_mu[j]; cw[Z + j] = c_sd[j]; }
+      }
+      if (seg_flags) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) seg_post(p.seg_done + wt, seg + 1);
+      }
+    }
   }
 
   // ---- flush: transition weights, global prior --------------------------------

@@ -19,6 +19,37 @@
 #endif
 
 namespace bfvi {
+// Inter-CTA hand-over inside ONE (cooperative, fully resident) launch: a producer warp publishes
+// "segments 0..v-1 of this task are done" with a release store, the consumer spins on an acquire
+// load; payload written before seg_post is read after seg_wait with ld_cg (L1 is not coherent).
+// The emulator never runs several segments in one launch (stream-ordered launches instead).
+__device__ __forceinline__ void seg_post(int* flag, int v) {
+#ifdef BFVI_EMU
+  *flag = v;
+#else
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void seg_wait(const int* flag, int want) {
+#ifdef BFVI_EMU
+  (void)flag; (void)want;
+#else
+  int v;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= want) break;
+    __nanosleep(256);
+  }
+#endif
+}
+__device__ __forceinline__ float ld_cg(const float* p) {
+#ifdef BFVI_EMU
+  return *p;
+#else
+  return __ldcg(p);
+#endif
+}
+
 // An integer zero the compiler cannot see through.  Adding it to the base of the
 // shared-memory weight block inside the time loop stops loop-invariant hoisting of
 // the ~130 weight loads of one GTF evaluation (which would otherwise be "kept in

@@ -58,3 +58,26 @@ def test_batch_chunked_step_agrees(lib, chunks, monkeypatch):
     for k, g_ref in fx['ref_grads_fp64'].items():
         if g_ref.norm() > 0:
             assert rel_err(grads[k] / n, g_ref) < 1e-3, (k, rel_err(grads[k] / n, g_ref))
+
+
+@pytest.mark.parametrize('segments,chunks', [('2', '1'), ('3', '1'), ('7', '1'), ('4', '2')])
+def test_time_segmented_backward_agrees(lib, segments, chunks, monkeypatch):
+    """The particle backward kernel cuts its time loop into segments that hand the gradient carry
+    over through scratch memory (BFVI_BWD_SEGMENTS knob; on the CPU one launch per segment): the
+    step must equal the unsegmented one to rounding, also combined with batch chunks."""
+    fx = load_golden('spirals_ragged')
+    monkeypatch.setenv('BFVI_LANES', '5')            # throughput mapping (the one that is segmented)
+    monkeypatch.setenv('BFVI_CHUNKS', chunks)
+    loss0, grads0, _ = helpers.run_step(lib, fx, 'cpu')
+    monkeypatch.setenv('BFVI_BWD_SEGMENTS', segments)
+    loss, grads, _ = helpers.run_step(lib, fx, 'cpu')
+    assert loss == loss0
+    for k, g0 in grads0.items():
+        if g0.norm() > 0:
+            assert rel_err(grads[k], g0) < 2e-6, (k, rel_err(grads[k], g0))
+    ref = fx['ref_loss_fp64']
+    assert abs(loss - ref) / abs(ref) < 1e-4
+    n = float(sum(fx['lengths']))
+    for k, g_ref in fx['ref_grads_fp64'].items():
+        if g_ref.norm() > 0:
+            assert rel_err(grads[k] / n, g_ref) < 1e-3, (k, rel_err(grads[k] / n, g_ref))

@@ -1,4 +1,6 @@
-for r in 1 2; do python tools/quick_time.py --steps 10 --tag rcp 2>&1 | tail -2; done
-python tools/quick_time.py --B 100 --tag c1 2>&1 | tail -2
-python -m pytest tests/test_gpu_step.py tests/test_gpu_model.py tests/test_gpu_random.py -x -q 2>&1 | tail -2
-ncu --set full --clock-control none --import-source on -k regex:chain_bwd_kernel -s 1 -c 1 -o gpurun_out/prof_r1_pair_bwd25 python tools/quick_time.py --steps 1 --warmup 0 > gpurun_out/ncu_pair.log 2>&1
+for i in 1 2; do timeout 120 python tools/quick_time.py --steps 10 --tag seg_auto 2>&1 | tail -2; done
+BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --tag seg_off 2>&1 | tail -2
+timeout 120 python tools/quick_time.py --steps 10 --B 8192 --tag B8k 2>&1 | tail -2 | head -1
+BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --B 8192 --tag B8k_off 2>&1 | tail -2 | head -1
+timeout 120 python tools/quick_time.py --steps 10 --B 2048 --tag B2k 2>&1 | tail -2 | head -1
+BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --B 2048 --tag B2k_off 2>&1 | tail -2 | head -1

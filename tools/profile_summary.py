@@ -42,9 +42,11 @@ for r in rows[2:]:
             print('  %-70s %s %s' % (w, r[hdr.index(w)], units[hdr.index(w)]))
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 open('/tmp/_src.csv', 'w').write(src)
-n = src.count('"Kernel Name"')
+n_sections = src.count('"Kernel Name"')
+n = len(rows) - 2                       # kernels in the report; the source export may repeat each one
+per = max(n_sections // max(n, 1), 1)
 for k in range(n):
     print('=' * 100)
     print('SASS opcode histogram, kernel #%d' % k)
-    print(subprocess.run([sys.executable, __file__.replace('profile_summary', 'sass_hist'), '/tmp/_src.csv', '24', str(k)],
+    print(subprocess.run([sys.executable, __file__.replace('profile_summary', 'sass_hist'), '/tmp/_src.csv', '24', str(k * per)],
                          capture_output=True, text=True).stdout)
