@@ -177,6 +177,66 @@ size_t seg_scratch_bytes(int S, int B, int Z) {
   return align_up(sizeof(int) * (size_t)S * B, 256) + align_up(sizeof(float) * (size_t)S * B * 2 * Z, 256);
 }
 
+// Segment count for the time-segmented particle kernels: `tasks` warp tasks on `slots` resident
+// warps take ceil(tasks / slots) rounds of a whole task; with sg segments the rounds shrink to
+// ceil(tasks * sg / slots) / sg.  Smallest sg within 1 % of the best, if that saves >= 5 %.
+int pick_segments(int64_t tasks, int64_t slots, int T, const char* env_name) {
+  int n_seg = 1;
+  if (slots > 0 && tasks > 0) {
+    const double base = (double)((tasks + slots - 1) / slots);
+    double best = base;
+    for (int sg = 2; sg <= 8 && sg <= T; ++sg) {
+      const double r = (double)((tasks * sg + slots - 1) / slots) / sg;
+      if (r < 0.99 * best) { best = r; n_seg = sg; }
+    }
+    if (best > 0.95 * base) n_seg = 1;
+  }
+  if (const char* env = getenv(env_name)) {                  // tuning / test knob (1 = off)
+    const int v = atoi(env);
+    if (v >= 1 && v <= 16 && v <= T) n_seg = v;
+  }
+  return n_seg;
+}
+
+// Launch a time-segmented kernel: one cooperative launch serving every segment (all warps resident,
+// per-task flags order the segments), else one stream-ordered launch per segment.
+template <typename Kernel>
+int launch_segmented(Kernel k, bfvi::FilterParams& fp, int n_seg, int64_t tasks, int warps, int64_t resident_blocks,
+                     dim3 plain_grid, int threads, size_t smem, cudaStream_t st) {
+#ifndef BFVI_EMU
+  const char* coop_env = getenv("BFVI_COOPERATIVE");           // 0: stream-ordered launches per segment
+  if ((coop_env == nullptr || atoi(coop_env) != 0) && resident_blocks > 0) {
+    cudaMemsetAsync(fp.seg_done, 0, sizeof(int) * (size_t)tasks, st);
+    fp.seg_lo = 0; fp.seg_hi = n_seg;
+    int64_t blocks = (tasks * n_seg + warps - 1) / warps;
+    if (blocks > resident_blocks) blocks = resident_blocks;
+    void* args[] = {&fp};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)blocks), dim3(threads), args, smem, st);
+    if (e == cudaSuccess) return BFVI_OK;
+    cudaGetLastError();                                        // not launchable cooperatively here: fall through
+  }
+#else
+  (void)tasks; (void)warps; (void)resident_blocks;
+#endif
+  for (int sg = 0; sg < n_seg; ++sg) {                          // same work, ordered by the stream
+    fp.seg_lo = sg; fp.seg_hi = sg + 1;
+    BFVI_LAUNCH(k, plain_grid, dim3(threads), smem, st, fp);
+  }
+  return BFVI_OK;
+}
+
+template <typename Kernel>
+int64_t resident_blocks_of(Kernel k, int threads, size_t smem) {
+#ifdef BFVI_EMU
+  (void)k; (void)threads; (void)smem;
+  return 2;                                                    // exercises the multi-launch form on the CPU
+#else
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) != cudaSuccess) return 0;
+  return (int64_t)per_sm * (num_sms() > 0 ? num_sms() : 1);
+#endif
+}
+
 template <int Z, int H>
 int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
   const bfvi_filter_args& a = fp.a;
@@ -188,6 +248,9 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
     auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
     BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, 2)), dim3(64), 0, st, fp);
   } else if (a.n_particles > 1) {
+    // (time segmentation as in the backward kernel was measured here and not kept: 2048 tasks fit
+    //  the 2368 resident warps in one round, the kernel is issue-bound rather than short of warps,
+    //  and a cooperative launch has to wait for pass A's kernels on the side stream: step +0.4 ms)
     constexpr int R = 5;
     choose_lanes(a.n_particles, R, chains, &fp.lanes, &fp.rounds);
     auto k = bfvi::chain_fwd_kernel<Z, H, R>;
@@ -243,58 +306,24 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
   // of the resident warps, cut the time loop into the segment count that packs best.
   const int cpw = 32 / fp.lanes;
   const int64_t tasks = (chains + cpw - 1) / cpw;
+  const dim3 grid(task_grid(chains, fp.lanes, warps));
   int n_seg = 1;
-  int64_t resident_blocks = 0;
-  const size_t seg_need = seg_scratch_bytes(a.S, a.B, Z);
-  if (a.n_particles > 1 && warps == bfvi::kChainBwdWarps && a.workspace != nullptr && a.workspace_bytes >= seg_need) {
-#ifdef BFVI_EMU
-    resident_blocks = 2;                                   // exercises the multi-launch form on the CPU
-#else
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem) == cudaSuccess)
-      resident_blocks = (int64_t)per_sm * (num_sms() > 0 ? num_sms() : 1);
-#endif
-    const int64_t slots = resident_blocks * warps;
-    if (slots > 0 && tasks > slots) {
-      double best = (double)((tasks + slots - 1) / slots);       // rounds, in units of a whole task
-      for (int sg = 2; sg <= 8 && sg <= a.T; ++sg) {
-        const double r = (double)((tasks * sg + slots - 1) / slots) / sg;
-        if (r < 0.95 * best) { best = r; n_seg = sg; }
-      }
-    }
-    if (const char* env = getenv("BFVI_BWD_SEGMENTS")) {         // tuning / test knob (1 = off)
-      const int v = atoi(env);
-      if (v >= 1 && v <= 16 && v <= a.T) n_seg = v;
-    }
+  int64_t resident = 0;
+  if (a.n_particles > 1 && warps == bfvi::kChainBwdWarps && a.workspace != nullptr &&
+      a.workspace_bytes >= seg_scratch_bytes(a.S, a.B, Z)) {
+    resident = resident_blocks_of(k, threads, smem);
+    n_seg = pick_segments(tasks, resident * warps, a.T, "BFVI_BWD_SEGMENTS");
   }
   if (n_seg == 1) {
-    BFVI_LAUNCH(k1, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
+    BFVI_LAUNCH(k1, grid, dim3(threads), smem, st, fp);
     BFVI_CHECK_CUDA();
     return BFVI_OK;
   }
   // scratch: per-task flags (S * B ints, this chunk's share) then the (S, B, 2Z) carry
-  int* flags = reinterpret_cast<int*>(a.workspace) + (size_t)a.S * fp.b0;
   fp.seg_count = n_seg;
-  fp.seg_done = flags;
+  fp.seg_done = reinterpret_cast<int*>(a.workspace) + (size_t)a.S * fp.b0;
   fp.seg_carry = reinterpret_cast<float*>(reinterpret_cast<char*>(a.workspace) + align_up(sizeof(int) * (size_t)a.S * a.B, 256));
-#ifndef BFVI_EMU
-  const char* coop_env = getenv("BFVI_BWD_COOPERATIVE");         // 0: stream-ordered launches per segment
-  if (coop_env == nullptr || atoi(coop_env) != 0) {
-    // one cooperative launch (every warp resident, so the per-task flags cannot deadlock)
-    cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)tasks, st);
-    fp.seg_lo = 0; fp.seg_hi = n_seg;
-    int64_t blocks = (tasks * n_seg + warps - 1) / warps;
-    if (blocks > resident_blocks) blocks = resident_blocks;
-    void* args[] = {&fp};
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)blocks), dim3(threads), args, smem, st);
-    if (e == cudaSuccess) { BFVI_CHECK_CUDA(); return BFVI_OK; }
-    cudaGetLastError();                                          // not launchable cooperatively here: fall through
-  }
-#endif
-  for (int sg = 0; sg < n_seg; ++sg) {                            // same work, ordered by the stream
-    fp.seg_lo = sg; fp.seg_hi = sg + 1;
-    BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, warps)), dim3(threads), smem, st, fp);
-  }
+  if (int rc = launch_segmented(k, fp, n_seg, tasks, warps, resident, grid, threads, smem, st)) return rc;
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
@@ -475,7 +504,7 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   for (int i = 0; i < 5; ++i) pl->off_a[i] = carve(fS);
   for (int i = 0; i < 4; ++i) pl->off_b[i] = carve(fS);
   for (int i = 0; i < 5; ++i) pl->off_c[i] = carve(fS);
-  pl->seg_bytes = with_grad ? seg_scratch_bytes(S > 0 ? S : 1, a->B, m->z_dim) : 0;
+  pl->seg_bytes = seg_scratch_bytes(S > 0 ? S : 1, a->B, m->z_dim);
   pl->off_seg = carve(pl->seg_bytes);
   pl->total = cur;
 }
@@ -1673,7 +1702,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     fc.d_samples = with_grad ? C(5) : nullptr;
     fb.d_prior_mean = with_grad ? Bf(4) : nullptr;
     fb.d_prior_std = with_grad ? Bf(5) : nullptr;
-    if (with_grad) { fb.workspace = ws + pl.off_seg; fb.workspace_bytes = pl.seg_bytes; }
+    fb.workspace = ws + pl.off_seg; fb.workspace_bytes = pl.seg_bytes;
     const Chunk all{0, 0};
 
     // ---- stream plan ------------------------------------------------------------------

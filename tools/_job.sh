@@ -1,6 +1,6 @@
 for i in 1 2; do timeout 120 python tools/quick_time.py --steps 10 --tag seg_auto 2>&1 | tail -2; done
-BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --tag seg_off 2>&1 | tail -2
-timeout 120 python tools/quick_time.py --steps 10 --B 8192 --tag B8k 2>&1 | tail -2 | head -1
-BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --B 8192 --tag B8k_off 2>&1 | tail -2 | head -1
-timeout 120 python tools/quick_time.py --steps 10 --B 2048 --tag B2k 2>&1 | tail -2 | head -1
-BFVI_BWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --B 2048 --tag B2k_off 2>&1 | tail -2 | head -1
+BFVI_FWD_SEGMENTS=1 timeout 120 python tools/quick_time.py --steps 10 --tag fwdseg_off 2>&1 | tail -2
+BFVI_FWD_SEGMENTS=4 timeout 120 python tools/quick_time.py --steps 10 --tag fwdseg4 2>&1 | tail -2
+BFVI_FWD_SEGMENTS=16 timeout 120 python tools/quick_time.py --steps 10 --tag fwdseg16 2>&1 | tail -2
+BFVI_COOPERATIVE=0 timeout 120 python tools/quick_time.py --steps 10 --tag multilaunch 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_gpu_step.py tests/test_gpu_model.py tests/test_gpu_random.py -x -q 2>&1 | tail -2
