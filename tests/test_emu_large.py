@@ -112,7 +112,7 @@ def test_standalone_filter_of_both_families_agree(lib, monkeypatch):
     the small-dim chain kernels on the same experts, masks, noise and upstream gradients."""
     n1, o1, g1, dm1, ds1 = _filter_call(lib, None, monkeypatch, True)
     n2, o2, g2, dm2, ds2 = _filter_call(lib, '2', monkeypatch, True)
-    assert n1 == 0 and n2 > 0                         # only the large-dim family needs scratch
+    assert n1 < 4096 < n2                             # small-dim: optional segment hand-over scratch only
     for a, b in zip(o1, o2):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
     assert rel_err(g2, g1) < 1e-4 and rel_err(dm2, dm1) < 1e-4 and rel_err(ds2, ds1) < 1e-4
