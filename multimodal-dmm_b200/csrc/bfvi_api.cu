@@ -515,12 +515,31 @@ int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
   (void)st;
   bfvi::tc::gemm_reference_emu(gp);
 #else
-  auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
-  const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static const bool v1 = [] { const char* e = getenv("BFVI_GEMM_V1"); return e && atoi(e) != 0; }();
   const unsigned gz = gp.k_split > 0 ? (unsigned)((gp.K + gp.k_split - 1) / gp.k_split) : 1u;
   const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN), gz);
-  k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
+  if (v1) {                          // round-1 kernel kept for A/B timing (tools/time_gemm.py)
+    auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
+    const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
+  } else {
+    // ring depth: as many 32-float chunks in flight as the contraction has, up to 4 stages / 200 kB;
+    // short contractions (K <= 64) take 2 stages so that two CTAs share an SM and one's epilogue
+    // overlaps the other's main loop
+    static const int cap = [] { const char* e = getenv("BFVI_GEMM_STAGES"); return e ? atoi(e) : bfvi::tc::kMaxStages; }();
+    const int64_t k_len = gp.k_split > 0 ? gp.k_split : gp.K;
+    const int64_t chunks = (k_len + bfvi::tc::kBK - 1) / bfvi::tc::kBK;
+    int stages = (int)(chunks < 2 ? 2 : chunks > bfvi::tc::kMaxStages ? bfvi::tc::kMaxStages : chunks);
+    const int fit = (int)((200u * 1024u) / bfvi::tc::gemm_v2_stage_bytes<BN, SPLIT>());
+    if (stages > fit) stages = fit;
+    if (stages > cap) stages = cap;
+    if (stages < 2) stages = 2;
+    auto k = bfvi::tc::gemm_tf32_v2_kernel<BN, SPLIT>;
+    const size_t smem = bfvi::tc::gemm_v2_smem_bytes<BN, SPLIT>(stages);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<grid, dim3(bfvi::tc::kThreadsV2host), smem, st>>>(gp, stages);
+  }
 #endif
   BFVI_CHECK_CUDA();
   return BFVI_OK;

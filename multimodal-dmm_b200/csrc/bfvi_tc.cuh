@@ -34,6 +34,7 @@ namespace tc {
 constexpr int kBM = 128;          // rows per CTA tile (UMMA M)
 constexpr int kBK = 32;           // floats of K per shared-memory stage (4 MMA k-steps)
 constexpr int kThreads = 128;
+constexpr int kThreadsV2host = 256;    // CTA size of the v2 tile kernel
 
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
@@ -315,6 +316,261 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_d, kCols);
 }
+
+// =====================================================================================
+// v2 of the tile kernel (the default): same contract and epilogue options as
+// gemm_tf32_kernel above, rebuilt around what the launch list of a C3-dims step showed
+// (profiles/r1_c3_launches_before.csv): 2.8 us per 32-float K chunk on the latency-bound
+// single-particle GEMMs and 13x the HBM time on the 57 600-row particle GEMMs, where the
+// row-per-thread epilogue wrote 32 different lines per store instruction.
+//
+//  * operands travel global -> shared memory with 16-byte cp.async (LDGSTS, zero-filling
+//    out-of-range rows / the K tail) into a ring of 2-4 stages, so 1-3 chunks are in flight
+//    while the current one is converted and multiplied;
+//  * shared-memory operand layout: K-major SWIZZLE_128B (a row's 32-float chunk is one
+//    128-byte line whose 16-byte vectors are XOR-permuted by row % 8; 8-row groups 1024 B
+//    apart) — eight lanes fetch one full global line and store one full shared line;
+//  * each thread rounds ITS vectors in place (hi = cvt.rna.tf32, lo = rna(x - hi) into the
+//    twin tile), so no barrier is needed between the copy and the conversion;
+//  * epilogue through a padded 32x33 shared patch per warp: TMEM rows -> patch, then
+//    lane = column: bias / ReLU / ReLU-mask / accumulate / split-K atomics / column sums
+//    all touch global memory as full 128-byte lines; the transposed copy leaves with
+//    lane = row, also as full lines.
+// =====================================================================================
+constexpr int kRowBytes = kBK * 4;            // 128 B: one swizzle-128B line per operand row and chunk
+constexpr int kMaxStages = 4;
+
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  // K-major SWIZZLE_128B: LBO unused (1), SBO = 1024 B between 8-row groups, version 1, layout type 2
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- per-thread view of one operand: the thread owns vectors (row r0 + 32 i, 16-byte column c4)
+// of every K chunk, with r0 = tid >> 3, c4 = tid & 7; (r & 7) does not depend on i, so the swizzled
+// offset is off0 + i * 32 rows.  Eight lanes cover one 128-byte global line and one shared line.
+constexpr int kThreadsV2 = 256;
+struct OperandView {
+  const float* src;        // &P[row0 + r0][k_begin + 4 c4]  (dereferenced only where valid)
+  const float* base;       // P (dummy source of zero-filled vectors)
+  int64_t row_step;        // 32 * ld
+  int valid;               // rows of this tile inside the matrix, minus r0: vector i is valid iff 32 i < valid
+  uint32_t off0;           // swizzled byte offset of vector (r0, c4)
+  bool vec;                // 16-byte aligned rows
+};
+__device__ __forceinline__ OperandView make_view(const float* P, int64_t ld, int64_t row0, int64_t n_rows, int tile_rows,
+                                                 int64_t k_begin) {
+  OperandView v;
+  const int r0 = threadIdx.x >> 3, c4 = threadIdx.x & 7;
+  v.src = P + (row0 + r0) * ld + k_begin + c4 * 4;
+  v.base = P;
+  v.row_step = 32 * ld;
+  const int64_t in = n_rows - row0 < tile_rows ? n_rows - row0 : tile_rows;
+  v.valid = (int)in - r0;
+  v.off0 = (uint32_t)(r0 * kRowBytes + ((c4 ^ (r0 & 7)) << 4));
+  v.vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
+  return v;
+}
+// asynchronous copy of K chunk `chunk` ([ROWS x 32] floats) into the swizzled tile at shared address `tile`
+template <int ROWS>
+__device__ __forceinline__ void load_tile_async(uint32_t tile, const OperandView& v, int chunk, int64_t k_left0) {
+  // k_left0 = floats between this thread's column of chunk 0 and the end of the contraction
+  const int64_t left = k_left0 - (int64_t)chunk * kBK;
+  const int kbytes = left >= 4 ? 16 : left > 0 ? (int)left * 4 : 0;
+  const float* src = v.src + (int64_t)chunk * kBK;
+  uint32_t dst = tile + v.off0;
+#pragma unroll
+  for (int i = 0; i < ROWS / 32; ++i) {
+    const bool in = 32 * i < v.valid && kbytes > 0;
+    if (v.vec) {
+      cp_async16(dst, in ? src : v.base, in ? kbytes : 0);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ine = in && e * 4 < kbytes;
+        cp_async4(dst + e * 4, ine ? src + e : v.base, ine ? 4 : 0);
+      }
+    }
+    src += v.row_step;
+    dst += 32 * kRowBytes;
+  }
+}
+// in-place rounding of the thread's own vectors: hi = rna_tf32(x); lo = x - hi is stored unrounded
+// (exact in fp32; the MMA reads its top 11 bits — 2^-21 of |x| at worst, below the dropped lo*lo term)
+template <int ROWS, bool SPLIT>
+__device__ __forceinline__ void convert_tile(unsigned char* hi, unsigned char* lo, uint32_t off0) {
+#pragma unroll
+  for (int i = 0; i < ROWS / 32; ++i) {
+    const uint32_t off = off0 + i * (32 * kRowBytes);
+    const float4 x = *reinterpret_cast<const float4*>(hi + off);
+    float4 h;
+    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+  }
+}
+
+template <int BN, bool SPLIT>
+struct TileCfg {
+  static constexpr int kABytes = kBM * kRowBytes;                    // 16 KB
+  static constexpr int kWBytes = BN * kRowBytes;                     // multiple of 1024 (BN >= 32)
+  static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kWBytes);
+  static constexpr int kPatchBytes = (kThreadsV2 / 32) * 32 * 33 * 4;   // epilogue staging, reuses the ring
+  static_assert(BN % 32 == 0, "tile width");
+  static_assert(2 * kStageBytes >= kPatchBytes, "epilogue patches must fit in two stages");
+};
+
+template <int BN, bool SPLIT>
+__global__ void __launch_bounds__(kThreadsV2) gemm_tf32_v2_kernel(const __grid_constant__ GemmParams p, int n_stages) {
+  using Cfg = TileCfg<BN, SPLIT>;
+  extern __shared__ unsigned char tc_smem_dyn[];
+  __shared__ __align__(8) uint64_t mbar[kMaxStages];
+  __shared__ uint32_t tmem_base_s;
+  // swizzle-128B tiles need 1024-byte aligned bases
+  unsigned char* smem = tc_smem_dyn + ((1024u - (smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
+  auto tileA = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+  auto tileW = [&](int s) { return tileA(s) + Cfg::kABytes; };
+  auto tileAl = [&](int s) { return tileW(s) + Cfg::kWBytes; };
+  auto tileWl = [&](int s) { return tileAl(s) + Cfg::kABytes; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kBM;
+  const int col0 = blockIdx.y * BN;
+  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+
+  if (warp == 0) tmem_alloc(&tmem_base_s, kCols);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) mbar_init(&mbar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+
+  const int64_t k_begin = p.k_split > 0 ? (int64_t)blockIdx.z * p.k_split : 0;
+  const int64_t k_end = p.k_split > 0 ? (k_begin + p.k_split < p.K ? k_begin + p.k_split : p.K) : p.K;
+  const int n_chunks = (int)((k_end - k_begin + kBK - 1) / kBK);
+  const uint32_t idesc = umma_idesc_tf32(kBM, BN);
+  const OperandView va = make_view(p.A, p.lda, row0, p.M, kBM, k_begin);
+  const OperandView vw = make_view(p.W, p.ldw, col0, p.N, BN, k_begin);
+  const int64_t k_left0 = k_end - k_begin - (threadIdx.x & 7) * 4;
+  auto issue_load = [&](int chunk, int s) {
+    load_tile_async<kBM>(smem_u32(tileA(s)), va, chunk, k_left0);
+    load_tile_async<BN>(smem_u32(tileW(s)), vw, chunk, k_left0);
+  };
+  // prologue: chunks 0 .. n_stages-2 in flight (one commit group per chunk, empty groups keep the count uniform)
+  for (int c = 0; c < n_stages - 1; ++c) {
+    if (c < n_chunks) issue_load(c, c);
+    cp_async_commit();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_s;
+
+  int s = 0;                                   // stage of chunk i
+  for (int i = 0; i < n_chunks; ++i) {
+    // chunk i is the oldest group but (n_stages - 2) younger ones: wait for it
+    if (n_stages == 2) cp_async_wait<0>(); else if (n_stages == 3) cp_async_wait<1>(); else cp_async_wait<2>();
+    convert_tile<kBM, SPLIT>(tileA(s), tileAl(s), va.off0);
+    convert_tile<BN, SPLIT>(tileW(s), tileWl(s), vw.off0);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(tileA(s)), w0 = smem_u32(tileW(s));
+      const uint32_t al0 = smem_u32(tileAl(s)), wl0 = smem_u32(tileWl(s));
+#pragma unroll
+      for (int j = 0; j < kBK / 8; ++j) {      // one MMA consumes 8 floats = 32 bytes of every row's line
+        const uint64_t da = umma_desc_sw128(a0 + j * 32), dw = umma_desc_sw128(w0 + j * 32);
+        umma_tf32(tmem_d, da, dw, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        if (SPLIT) {
+          umma_tf32(tmem_d, umma_desc_sw128(al0 + j * 32), dw, idesc, 1u);
+          umma_tf32(tmem_d, da, umma_desc_sw128(wl0 + j * 32), idesc, 1u);
+        }
+      }
+      umma_commit(&mbar[s]);                    // arrives when these MMAs have read their operands
+    }
+    // refill the stage chunk i-1 used with chunk i + n_stages - 1 once its MMAs are done
+    const int nxt = i + n_stages - 1;
+    if (nxt < n_chunks) {
+      const int sp = s == 0 ? n_stages - 1 : s - 1;
+      if (i >= 1) mbar_wait(&mbar[sp], (uint32_t)(((i - 1) / n_stages) & 1));
+      issue_load(nxt, sp);
+    }
+    cp_async_commit();
+    s = s + 1 == n_stages ? 0 : s + 1;
+  }
+  if (n_chunks > 0) {                           // the last commit covers every earlier MMA
+    const int last = n_chunks - 1;
+    mbar_wait(&mbar[last % n_stages], (uint32_t)((last / n_stages) & 1));
+  }
+  cp_async_wait<0>();
+  tc_fence_after();
+  __syncthreads();                              // every thread's copies have landed: the ring is free for the patches
+
+  // ---- epilogue: warps w and w + 4 own accumulator rows (TMEM lanes) 32 (w % 4) .., alternate 32-column blocks
+  float* patch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+  const int wq = warp & 3;
+  const int64_t wrow0 = row0 + wq * 32;
+  const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+#pragma unroll 1
+  for (int c = (warp >> 2) * 32; c < BN; c += 64) {
+    if (col0 + c >= p.N) break;
+    float v[32];
+    if (n_chunks > 0) {
+      tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];      // thread = row
+    __syncwarp();
+    const int col = col0 + c + lane;                                // lane = column from here on
+    const bool col_ok = col < p.N;
+    const int cols_valid = p.N - (col0 + c) < 32 ? p.N - (col0 + c) : 32;
+    const float bias = (p.bias != nullptr && col_ok) ? p.bias[col] : 0.f;
+    float csum = 0.f;
+    if (col_ok) {
+      float* dst = p.C + wrow0 * p.ldc + col;
+      const float* aux = p.mask_aux != nullptr ? p.mask_aux + wrow0 * p.ldaux + col : nullptr;
+      const bool relu = p.act == ACT_RELU, split = p.k_split > 0, acc = p.accumulate != 0;
+#pragma unroll 4
+      for (int rr = 0; rr < rows_valid; ++rr) {
+        float x = patch[rr * 33 + lane] + bias;
+        if (relu) x = x < 0.f ? 0.f : x;
+        if (aux != nullptr) { x = *aux > 0.f ? x : 0.f; aux += p.ldaux; }
+        csum += x;
+        if (split) {
+          atomicAdd(dst, x);                                        // split-K partial tile
+        } else {
+          if (acc) x += *dst;
+          *dst = x;
+        }
+        dst += p.ldc;
+        patch[rr * 33 + lane] = x;                                  // final value, for the transposed copy
+      }
+      if (p.colsum != nullptr) atomicAdd(p.colsum + col, csum);
+    }
+    __syncwarp();
+    if (p.Ct != nullptr && p.k_split == 0 && lane < rows_valid) {   // lane = row again: Ct[col][row], full lines
+      float* dt = p.Ct + (int64_t)(col0 + c) * p.ldct + wrow0 + lane;
+#pragma unroll 4
+      for (int j = 0; j < cols_valid; ++j) { *dt = patch[lane * 33 + j]; dt += p.ldct; }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_d, kCols);
+}
 #endif  // !BFVI_EMU
 
 // CPU stand-in used only by the SIMT-emulator test build (exact fp32, no TF32 rounding)
@@ -340,6 +596,11 @@ inline void gemm_reference_emu(const GemmParams& p) {
 
 template <int BN, bool SPLIT>
 inline size_t gemm_smem_bytes() { return sizeof(float) * (SPLIT ? 4 : 2) * (size_t)(kBM + BN) * kBK; }
+// v2: ring of `stages` stages (+ slack for the 1024-byte alignment of the swizzled tiles)
+template <int BN, bool SPLIT>
+inline size_t gemm_v2_stage_bytes() { return (size_t)(SPLIT ? 2 : 1) * (size_t)(kBM + BN) * kBK * sizeof(float); }
+template <int BN, bool SPLIT>
+inline size_t gemm_v2_smem_bytes(int stages) { return gemm_v2_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024; }
 
 }  // namespace tc
 }  // namespace bfvi
