@@ -509,54 +509,80 @@ void plan_step(const bfvi_model* m, const bfvi_step_args* a, bool with_grad, Ste
   pl->total = cur;
 }
 
+// One launch of the grouped persistent tile kernel over `n` independent problems (no problem may read
+// what another one of the group writes, and no two may accumulate into the same C without split-K atomics).
 template <int BN, bool SPLIT>
-int launch_gemm_tf32(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
+int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
 #ifdef BFVI_EMU
   (void)st;
-  bfvi::tc::gemm_reference_emu(gp);
+  for (int i = 0; i < n; ++i) bfvi::tc::gemm_reference_emu(gps[i]);
 #else
   static const bool v1 = [] { const char* e = getenv("BFVI_GEMM_V1"); return e && atoi(e) != 0; }();
-  const unsigned gz = gp.k_split > 0 ? (unsigned)((gp.K + gp.k_split - 1) / gp.k_split) : 1u;
-  const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN), gz);
   if (v1) {                          // round-1 kernel kept for A/B timing (tools/time_gemm.py)
-    auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
-    const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
+    for (int i = 0; i < n; ++i) {
+      const bfvi::tc::GemmParams& gp = gps[i];
+      const unsigned gz = gp.k_split > 0 ? (unsigned)((gp.K + gp.k_split - 1) / gp.k_split) : 1u;
+      const dim3 grid((unsigned)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM), (unsigned)((gp.N + BN - 1) / BN), gz);
+      auto k = bfvi::tc::gemm_tf32_kernel<BN, SPLIT>;
+      const size_t smem = bfvi::tc::gemm_smem_bytes<BN, SPLIT>();
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      k<<<grid, dim3(bfvi::tc::kThreads), smem, st>>>(gp);
+    }
   } else {
-    // ring depth: as many 32-float chunks in flight as the contraction has, up to 4 stages / 200 kB;
-    // short contractions (K <= 64) take 2 stages so that two CTAs share an SM and one's epilogue
-    // overlaps the other's main loop
     static const int cap = [] { const char* e = getenv("BFVI_GEMM_STAGES"); return e ? atoi(e) : bfvi::tc::kMaxStages; }();
-    const int64_t k_len = gp.k_split > 0 ? gp.k_split : gp.K;
-    const int64_t chunks = (k_len + bfvi::tc::kBK - 1) / bfvi::tc::kBK;
-    int stages = (int)(chunks < 2 ? 2 : chunks > bfvi::tc::kMaxStages ? bfvi::tc::kMaxStages : chunks);
-    const int fit = (int)((200u * 1024u) / bfvi::tc::gemm_v2_stage_bytes<BN, SPLIT>());
-    if (stages > fit) stages = fit;
+    static const int ctas_per_sm = [] { const char* e = getenv("BFVI_GEMM_CTAS"); return e ? atoi(e) : 1; }();
+    bfvi::tc::GemmGroup grp;
+    memset(&grp, 0, sizeof(grp));
+    bool vec = true;
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+      const bfvi::tc::GemmParams& gp = gps[i];
+      grp.g[i] = gp;
+      const int64_t k_len = gp.k_split > 0 ? gp.k_split : gp.K;
+      grp.chunks[i] = (int)((k_len + bfvi::tc::kBK - 1) / bfvi::tc::kBK);
+      grp.tiles_m[i] = (int)((gp.M + bfvi::tc::kBM - 1) / bfvi::tc::kBM);
+      grp.tiles_n[i] = (gp.N + BN - 1) / BN;
+      const int tz = gp.k_split > 0 ? (int)((gp.K + gp.k_split - 1) / gp.k_split) : 1;
+      total += grp.tiles_m[i] * grp.tiles_n[i] * tz;
+      grp.tile_end[i] = total;
+      vec = vec && gp.lda % 4 == 0 && gp.ldw % 4 == 0 && (((uintptr_t)gp.A | (uintptr_t)gp.W) & 15) == 0;
+    }
+    grp.n = n; grp.total = total;
+    // the operand ring runs across tile boundaries, so it is as deep as fits (4 stages / 200 kB)
+    const size_t budget = (ctas_per_sm > 1 ? 96u : 200u) * 1024u;
+    int stages = (int)(budget / bfvi::tc::gemm_v2_stage_bytes<BN, SPLIT>());
+    if (stages > bfvi::tc::kMaxStages) stages = bfvi::tc::kMaxStages;
     if (stages > cap) stages = cap;
     if (stages < 2) stages = 2;
-    auto k = bfvi::tc::gemm_tf32_v2_kernel<BN, SPLIT>;
-    const size_t smem = bfvi::tc::gemm_v2_smem_bytes<BN, SPLIT>(stages);
+    const size_t smem = bfvi::tc::gemm_p_smem_bytes<BN, SPLIT>(stages);
+    auto k = vec ? bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, true> : bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<grid, dim3(bfvi::tc::kThreadsV2host), smem, st>>>(gp, stages);
+    const int slots = (num_sms() > 0 ? num_sms() : 1) * (ctas_per_sm > 1 ? 2 : 1);
+    k<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem, st>>>(grp, stages);
   }
 #endif
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
 
+// tile width of a launch: 32 when every problem is at most 32 wide, else 64 (98 kB of operands per
+// 4-stage... ring stage pair; BFVI_GEMM_BN raises the cap for experiments)
 template <bool SPLIT>
-int dispatch_gemm_bn(const bfvi::tc::GemmParams& gp, cudaStream_t st) {
-  static const int cap = [] { const char* e = getenv("BFVI_GEMM_BN"); return e ? atoi(e) : 64; }();   // 64-wide tiles: 98 kB of operands per CTA, 2 CTAs/SM (measured +14..28 % on the C3 step vs 256)
-  if (gp.N <= 32 || cap <= 32) return launch_gemm_tf32<32, SPLIT>(gp, st);
-  if (gp.N <= 64 || cap <= 64) return launch_gemm_tf32<64, SPLIT>(gp, st);
-  if (gp.N <= 128 || cap <= 128) return launch_gemm_tf32<128, SPLIT>(gp, st);
-  return launch_gemm_tf32<256, SPLIT>(gp, st);
+int dispatch_gemm_bn(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
+  static const int cap = [] { const char* e = getenv("BFVI_GEMM_BN"); return e ? atoi(e) : 64; }();
+  int n_max = 0;
+  for (int i = 0; i < n; ++i) n_max = gps[i].N > n_max ? gps[i].N : n_max;
+  if (n_max <= 32 || cap <= 32) return launch_gemm_group<32, SPLIT>(gps, n, st);
+  if (n_max <= 64 || cap <= 64) return launch_gemm_group<64, SPLIT>(gps, n, st);
+  if (n_max <= 128 || cap <= 128) return launch_gemm_group<128, SPLIT>(gps, n, st);
+  return launch_gemm_group<256, SPLIT>(gps, n, st);
 }
 
-int gemm_tc(const bfvi::tc::GemmParams& gp, int prec, cudaStream_t st) {
-  return prec == bfvi::tc::PREC_TF32 ? dispatch_gemm_bn<false>(gp, st) : dispatch_gemm_bn<true>(gp, st);
+int gemm_group_tc(const bfvi::tc::GemmParams* gps, int n, int prec, cudaStream_t st) {
+  if (n <= 0) return BFVI_OK;
+  return prec == bfvi::tc::PREC_TF32 ? dispatch_gemm_bn<false>(gps, n, st) : dispatch_gemm_bn<true>(gps, n, st);
 }
+int gemm_tc(const bfvi::tc::GemmParams& gp, int prec, cudaStream_t st) { return gemm_group_tc(&gp, 1, prec, st); }
 
 // Split of the (long) contraction over the rows of a weight-gradient GEMM: the output has only a
 // few 128 x BN tiles, so K is cut into enough slices to put ~2 CTAs on every SM (slices are a
@@ -707,7 +733,24 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   BFVI_CHECK_CUDA();
 
   // ---- GEMM helpers ---------------------------------------------------------------------
-  auto gemm = [&](const bfvi::tc::GemmParams& gp) -> int { ++n_launch; return gemm_tc(gp, prec, st); };
+  // GEMMs queue into `pending`; flush() runs everything queued as ONE grouped launch.  The code below
+  // flushes wherever a later GEMM (or elementwise kernel) reads what a queued one writes, or two would
+  // accumulate into the same matrix.  BFVI_GEMM_GROUP=0: one launch per GEMM (A/B timing, bisecting).
+  static const bool grouping = [] { const char* e = getenv("BFVI_GEMM_GROUP"); return !e || atoi(e) != 0; }();
+  bfvi::tc::GemmParams pending[bfvi::tc::kMaxGroup];
+  int n_pending = 0;
+  auto flush = [&]() -> int {
+    if (n_pending == 0) return BFVI_OK;
+    ++n_launch;
+    const int rc = gemm_group_tc(pending, n_pending, prec, st);
+    n_pending = 0;
+    return rc;
+  };
+  auto gemm = [&](const bfvi::tc::GemmParams& gp) -> int {
+    pending[n_pending++] = gp;
+    if (!grouping || n_pending == bfvi::tc::kMaxGroup) return flush();
+    return BFVI_OK;
+  };
   // y = act(x W^T + b), optional transposed copy yT
   auto lin = [&](const float* x, int64_t ldx, int64_t w_off, int64_t b_off, float* y, float* yT, int64_t rows,
                  int n_in, int n_out, int act) -> int {
@@ -761,29 +804,39 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
 
   // ---- one transition: 6 forward GEMMs over `rows` particles --------------------------------
   auto trans_fwd = [&](const bfvi_gtf_layout& g, int64_t rows, bool keep) -> int {
-    float* h3 = keep ? F(pl.h3) : F(pl.h1);
+    // the three layers that read the particles; then the two that read the hidden layers; then the std head
     if (int rc = lin(F(pl.zrows), Z, g.gate0_w, g.gate0_b, F(pl.h1), keep ? F(pl.h1T) : nullptr, rows, Z, H, 1)) return rc;
-    if (int rc = lin(F(pl.h1), H, g.gate2_w, g.gate2_b, F(pl.g), nullptr, rows, H, Z, 0)) return rc;
-    if (int rc = lin(F(pl.zrows), Z, g.nonlin0_w, g.nonlin0_b, h3, keep ? F(pl.h3T) : nullptr, rows, Z, H, 1)) return rc;
-    if (int rc = lin(h3, H, g.nonlin2_w, g.nonlin2_b, F(pl.nl), keep ? F(pl.nlT) : nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = lin(F(pl.zrows), Z, g.nonlin0_w, g.nonlin0_b, F(pl.h3), keep ? F(pl.h3T) : nullptr, rows, Z, H, 1)) return rc;
     if (int rc = lin(F(pl.zrows), Z, g.lin_w, g.lin_b, F(pl.lin), nullptr, rows, Z, Z, 0)) return rc;
-    return lin(F(pl.nl), Z, g.std_w, g.std_b, F(pl.as), nullptr, rows, Z, Z, 0);
+    if (int rc = flush()) return rc;
+    if (int rc = lin(F(pl.h1), H, g.gate2_w, g.gate2_b, F(pl.g), nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = lin(F(pl.h3), H, g.nonlin2_w, g.nonlin2_b, F(pl.nl), keep ? F(pl.nlT) : nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = flush()) return rc;
+    if (int rc = lin(F(pl.nl), Z, g.std_w, g.std_b, F(pl.as), nullptr, rows, Z, Z, 0)) return rc;
+    return flush();
   };
   // backward of one transition given d_as / d_g / d_lin / d_nl(partial) rows: input gradient dz
-  // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums)
+  // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums),
+  // twelve GEMMs in three dependency levels
   auto trans_bwd = [&](const bfvi_gtf_layout& g, int64_t rows) -> int {
+    // level 1: everything that needs only the head gradients and the saved activations
     if (int rc = dgrad(F(pl.d_as), g.std_w, F(pl.d_nl), F(pl.d_nlT), rows, Z, Z, true, nullptr, grads + g.nonlin2_b)) return rc;
-    if (int rc = dgrad(F(pl.d_nl), g.nonlin2_w, F(pl.dh3), F(pl.dh3T), rows, Z, H, false, F(pl.h3), grads + g.nonlin0_b)) return rc;
     if (int rc = dgrad(F(pl.d_g), g.gate2_w, F(pl.dh1), F(pl.dh1T), rows, Z, H, false, F(pl.h1), grads + g.gate0_b)) return rc;
     if (int rc = dgrad(F(pl.d_lin), g.lin_w, F(pl.dz), nullptr, rows, Z, Z, false, nullptr, nullptr)) return rc;
-    if (int rc = dgrad(F(pl.dh1), g.gate0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
-    if (int rc = dgrad(F(pl.dh3), g.nonlin0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
-    if (int rc = wgrad(F(pl.dh1T), F(pl.zrowsT), rows, H, Z, g.gate0_w)) return rc;
-    if (int rc = wgrad(F(pl.dh3T), F(pl.zrowsT), rows, H, Z, g.nonlin0_w)) return rc;
     if (int rc = wgrad(F(pl.d_linT), F(pl.zrowsT), rows, Z, Z, g.lin_w)) return rc;
     if (int rc = wgrad(F(pl.d_gT), F(pl.h1T), rows, Z, H, g.gate2_w)) return rc;
+    if (int rc = wgrad(F(pl.d_asT), F(pl.nlT), rows, Z, Z, g.std_w)) return rc;
+    if (int rc = flush()) return rc;
+    // level 2: needs the complete d_nl (+ transposed copy) and dh1
+    if (int rc = dgrad(F(pl.d_nl), g.nonlin2_w, F(pl.dh3), F(pl.dh3T), rows, Z, H, false, F(pl.h3), grads + g.nonlin0_b)) return rc;
+    if (int rc = dgrad(F(pl.dh1), g.gate0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    if (int rc = wgrad(F(pl.dh1T), F(pl.zrowsT), rows, H, Z, g.gate0_w)) return rc;
     if (int rc = wgrad(F(pl.d_nlT), F(pl.h3T), rows, Z, H, g.nonlin2_w)) return rc;
-    return wgrad(F(pl.d_asT), F(pl.nlT), rows, Z, Z, g.std_w);
+    if (int rc = flush()) return rc;
+    // level 3: needs dh3; dz receives its third term
+    if (int rc = dgrad(F(pl.dh3), g.nonlin0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    if (int rc = wgrad(F(pl.dh3T), F(pl.zrowsT), rows, H, Z, g.nonlin0_w)) return rc;
+    return flush();
   };
   auto step_params = [&](const bfvi_filter_args& f, int i) {
     bfvi::gen::StepParams sp;
@@ -849,6 +902,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
 
   if (fonly) {                       // stand-alone MultiDMM.z_filter (models/dmm.py:319-412)
     if (int rc = fonly_backward ? pass_bwd(*fonly) : pass_fwd(*fonly, nullptr)) return rc;
+    if (int rc = flush()) return rc;
     if (launches) *launches = n_launch;
     return BFVI_OK;
   }
@@ -932,8 +986,10 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       ++n_launch;
       if (with_grad) transpose(F(pl.x0[i]), tb, D, F(pl.x0T[i]));
       if (int rc = lin(F(pl.x0[i]), D, l.in_to_h_w, l.in_to_h_b, henc, with_grad ? hencT : nullptr, tb, D, H, 1)) return rc;
+      if (int rc = flush()) return rc;
       if (int rc = lin(henc, H, l.mean_w, l.mean_b, obs_mean + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
       if (int rc = lin(henc, H, l.std_w, l.std_b, obs_stdpre + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
+      if (int rc = flush()) return rc;
       cudaMemcpyAsync(obs_std + (size_t)i * pl.tbz, obs_stdpre + (size_t)i * pl.tbz, sizeof(float) * pl.tbz,
                       cudaMemcpyDeviceToDevice, st);
       auto ks = bfvi::gen::softplus_kernel;
@@ -1026,8 +1082,10 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
           const int D = m->dims[i];
           const float* zs = samp + (size_t)s * pl.tbz;
           if (int rc = lin(zs, Z, l.in_to_h_w, l.in_to_h_b, F(pl.hdec), with_grad ? F(pl.hdecT) : nullptr, tb, Z, H, 1)) return rc;
+          if (int rc = flush()) return rc;
           if (int rc = lin(F(pl.hdec), H, l.mean_w, l.mean_b, F(pl.dmean), nullptr, tb, H, D, 0)) return rc;
           if (int rc = lin(F(pl.hdec), H, l.std_w, l.std_b, F(pl.dstd), nullptr, tb, H, D, 0)) return rc;
+          if (int rc = flush()) return rc;
           bfvi::gen::HeadParams hp;
           memset(&hp, 0, sizeof(hp));
           hp.mean = F(pl.dmean); hp.stdpre = F(pl.dstd); hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
@@ -1040,11 +1098,14 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
           ++n_launch;
           if (!with_grad) continue;
           if (int rc = dgrad(F(pl.dmean), l.mean_w, F(pl.dhd), nullptr, tb, D, H, false, F(pl.hdec), grads + l.in_to_h_b)) return rc;
-          if (int rc = dgrad(F(pl.dstd), l.std_w, F(pl.dhd), F(pl.dhdT), tb, D, H, true, F(pl.hdec), grads + l.in_to_h_b)) return rc;
-          if (int rc = dgrad(F(pl.dhd), l.in_to_h_w, dsamp + (size_t)s * pl.tbz, nullptr, tb, H, Z, true, nullptr, nullptr)) return rc;
           if (int rc = wgrad(F(pl.dmeanT), F(pl.hdecT), tb, D, H, l.mean_w)) return rc;
           if (int rc = wgrad(F(pl.dstdT), F(pl.hdecT), tb, D, H, l.std_w)) return rc;
+          if (int rc = flush()) return rc;
+          if (int rc = dgrad(F(pl.dstd), l.std_w, F(pl.dhd), F(pl.dhdT), tb, D, H, true, F(pl.hdec), grads + l.in_to_h_b)) return rc;
+          if (int rc = flush()) return rc;
+          if (int rc = dgrad(F(pl.dhd), l.in_to_h_w, dsamp + (size_t)s * pl.tbz, nullptr, tb, H, Z, true, nullptr, nullptr)) return rc;
           if (int rc = wgrad(F(pl.dhdT), sampT + (size_t)s * pl.tbz, tb, H, Z, l.in_to_h_w)) return rc;
+          if (int rc = flush()) return rc;
         }
     }
     BFVI_CHECK_CUDA();
@@ -1079,14 +1140,18 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
                              (unsigned)((Z + 127) / 128)), dim3(128), 0, st, hp);
         ++n_launch;
         if (int rc = dgrad(dm, l.mean_w, F(pl.dhd), nullptr, tb, Z, H, false, henc, grads + l.in_to_h_b)) return rc;
-        if (int rc = dgrad(dsp, l.std_w, F(pl.dhd), F(pl.dhdT), tb, Z, H, true, henc, grads + l.in_to_h_b)) return rc;
         if (int rc = wgrad(F(pl.dmeanT), hencT, tb, Z, H, l.mean_w)) return rc;
         if (int rc = wgrad(F(pl.dstdT), hencT, tb, Z, H, l.std_w)) return rc;
+        if (int rc = flush()) return rc;
+        if (int rc = dgrad(dsp, l.std_w, F(pl.dhd), F(pl.dhdT), tb, Z, H, true, henc, grads + l.in_to_h_b)) return rc;
+        if (int rc = flush()) return rc;
         if (int rc = wgrad(F(pl.dhdT), F(pl.x0T[i]), tb, H, D, l.in_to_h_w)) return rc;
+        if (int rc = flush()) return rc;
       }
       BFVI_CHECK_CUDA();
     }
   }
+  if (int rc = flush()) return rc;
   auto kfin = bfvi::finalize_loss_kernel;
   BFVI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
   BFVI_CHECK_CUDA();

@@ -34,7 +34,6 @@ namespace tc {
 constexpr int kBM = 128;          // rows per CTA tile (UMMA M)
 constexpr int kBK = 32;           // floats of K per shared-memory stage (4 MMA k-steps)
 constexpr int kThreads = 128;
-constexpr int kThreadsV2host = 256;    // CTA size of the v2 tile kernel
 
 enum { ACT_NONE = 0, ACT_RELU = 1 };
 
@@ -381,7 +380,8 @@ __device__ __forceinline__ OperandView make_view(const float* P, int64_t ld, int
   return v;
 }
 // asynchronous copy of K chunk `chunk` ([ROWS x 32] floats) into the swizzled tile at shared address `tile`
-template <int ROWS>
+// VEC: rows are 16-byte aligned (one LDGSTS.128 per vector), else four 4-byte copies
+template <int ROWS, bool VEC>
 __device__ __forceinline__ void load_tile_async(uint32_t tile, const OperandView& v, int chunk, int64_t k_left0) {
   // k_left0 = floats between this thread's column of chunk 0 and the end of the contraction
   const int64_t left = k_left0 - (int64_t)chunk * kBK;
@@ -391,7 +391,7 @@ __device__ __forceinline__ void load_tile_async(uint32_t tile, const OperandView
 #pragma unroll
   for (int i = 0; i < ROWS / 32; ++i) {
     const bool in = 32 * i < v.valid && kbytes > 0;
-    if (v.vec) {
+    if (VEC) {
       cp_async16(dst, in ? src : v.base, in ? kbytes : 0);
     } else {
 #pragma unroll
@@ -404,16 +404,22 @@ __device__ __forceinline__ void load_tile_async(uint32_t tile, const OperandView
     dst += 32 * kRowBytes;
   }
 }
-// in-place rounding of the thread's own vectors: hi = rna_tf32(x); lo = x - hi is stored unrounded
-// (exact in fp32; the MMA reads its top 11 bits — 2^-21 of |x| at worst, below the dropped lo*lo term)
+// Operand preparation by the thread that copied the vectors (no barrier in between):
+// hi = rn_tf32(x) in place (round-to-nearest-even, ONE F2FP.TF32.F32 instruction on sm_100; cvt.rna is a
+// four-instruction emulation, and this pass is issue-bound); for 3xTF32 the twin tile gets lo = x - hi,
+// exact in fp32 and left unrounded — kind::tf32 reads its top 11 significant bits, 2^-22 |x| at worst.
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rn.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 template <int ROWS, bool SPLIT>
 __device__ __forceinline__ void convert_tile(unsigned char* hi, unsigned char* lo, uint32_t off0) {
 #pragma unroll
   for (int i = 0; i < ROWS / 32; ++i) {
     const uint32_t off = off0 + i * (32 * kRowBytes);
     const float4 x = *reinterpret_cast<const float4*>(hi + off);
-    float4 h;
-    h.x = to_tf32(x.x); h.y = to_tf32(x.y); h.z = to_tf32(x.z); h.w = to_tf32(x.w);
+    const float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
     *reinterpret_cast<float4*>(hi + off) = h;
     if (SPLIT) *reinterpret_cast<float4*>(lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
   }
@@ -424,152 +430,325 @@ struct TileCfg {
   static constexpr int kABytes = kBM * kRowBytes;                    // 16 KB
   static constexpr int kWBytes = BN * kRowBytes;                     // multiple of 1024 (BN >= 32)
   static constexpr int kStageBytes = (SPLIT ? 2 : 1) * (kABytes + kWBytes);
-  static constexpr int kPatchBytes = (kThreadsV2 / 32) * 32 * 33 * 4;   // epilogue staging, reuses the ring
   static_assert(BN % 32 == 0, "tile width");
-  static_assert(2 * kStageBytes >= kPatchBytes, "epilogue patches must fit in two stages");
-};
+  };
 
-template <int BN, bool SPLIT>
-__global__ void __launch_bounds__(kThreadsV2) gemm_tf32_v2_kernel(const __grid_constant__ GemmParams p, int n_stages) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+// Epilogue of one 32-row x 32-column block of the accumulator held by one warp (thread = row, v[j] =
+// column c + j): bias, ReLU, ReLU mask, column sums, accumulate / split-K atomics, C and its
+// transposed copy.  `patch` is the warp's padded 32 x 33 shared staging area.
+//  fast path (16-byte aligned rows, full block): the thread moves its 32 consecutive columns as
+//   128-bit vectors (eight instructions fill each row's 128-byte line); the transposed copy leaves
+//   as full lines (lane = row); only the column sums go through the patch;
+//  general path: rows -> patch, then lane = column, so that every global access is a full line.
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, float (&v)[32], float* patch, int64_t wrow0,
+                                               int rows_valid, int cbase, int lane, bool fast_c) {
+  if (fast_c && cbase + 32 <= p.N) {
+    const int64_t row = wrow0 + lane;
+    const bool row_ok = lane < rows_valid;
+    if (p.bias != nullptr) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + cbase);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 b = __ldg(b4 + q);
+        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+      }
+    }
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] < 0.f ? 0.f : v[j];
+    }
+    if (p.mask_aux != nullptr && row_ok) {
+      const float4* a4 = reinterpret_cast<const float4*>(p.mask_aux + row * p.ldaux + cbase);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 m = a4[q];
+        v[4 * q] = m.x > 0.f ? v[4 * q] : 0.f; v[4 * q + 1] = m.y > 0.f ? v[4 * q + 1] : 0.f;
+        v[4 * q + 2] = m.z > 0.f ? v[4 * q + 2] : 0.f; v[4 * q + 3] = m.w > 0.f ? v[4 * q + 3] : 0.f;
+      }
+    }
+    if (!row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
+    if (p.colsum != nullptr) {                 // column sums of THIS product: transpose through the patch
+#pragma unroll
+      for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];
+      __syncwarp();
+      float cs = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) cs += patch[rr * 33 + lane];
+      atomicAdd(p.colsum + cbase + lane, cs);
+      __syncwarp();
+    }
+    if (row_ok) {
+      float4* d4 = reinterpret_cast<float4*>(p.C + row * p.ldc + cbase);
+      if (p.accumulate) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 o = d4[q];
+          v[4 * q] += o.x; v[4 * q + 1] += o.y; v[4 * q + 2] += o.z; v[4 * q + 3] += o.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (p.Ct != nullptr) {
+        float* dt = p.Ct + (int64_t)cbase * p.ldct + row;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dt[(int64_t)j * p.ldct] = v[j];
+      }
+    }
+    return;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];      // thread = row
+  __syncwarp();
+  const int col = cbase + lane;                                   // lane = column from here on
+  const bool col_ok = col < p.N;
+  const int cols_valid = p.N - cbase < 32 ? p.N - cbase : 32;
+  const float bias = (p.bias != nullptr && col_ok) ? p.bias[col] : 0.f;
+  float csum = 0.f;
+  if (col_ok) {
+    float* dst = p.C + wrow0 * p.ldc + col;
+    const float* aux = p.mask_aux != nullptr ? p.mask_aux + wrow0 * p.ldaux + col : nullptr;
+    const bool relu = p.act == ACT_RELU, split = p.k_split > 0, acc = p.accumulate != 0;
+#pragma unroll 4
+    for (int rr = 0; rr < rows_valid; ++rr) {
+      float x = patch[rr * 33 + lane] + bias;
+      if (relu) x = x < 0.f ? 0.f : x;
+      if (aux != nullptr) { x = *aux > 0.f ? x : 0.f; aux += p.ldaux; }
+      csum += x;
+      if (split) {
+        atomicAdd(dst, x);                                        // split-K partial tile
+      } else {
+        if (acc) x += *dst;
+        *dst = x;
+      }
+      dst += p.ldc;
+      patch[rr * 33 + lane] = x;                                  // final value, for the transposed copy
+    }
+    if (p.colsum != nullptr) atomicAdd(p.colsum + col, csum);
+  }
+  __syncwarp();
+  if (p.Ct != nullptr && p.k_split == 0 && lane < rows_valid) {   // lane = row again: Ct[col][row], full lines
+    float* dt = p.Ct + (int64_t)cbase * p.ldct + wrow0 + lane;
+#pragma unroll 4
+    for (int j = 0; j < cols_valid; ++j) { *dt = patch[lane * 33 + j]; dt += p.ldct; }
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ bool epilogue_fast_ok(const GemmParams& p) {
+  return (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && p.k_split == 0 &&
+         (p.mask_aux == nullptr || ((p.ldaux % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.mask_aux) & 15) == 0))) &&
+         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
+}
+
+// =====================================================================================
+// The tile kernel proper: persistent and GROUPED.  One launch runs up to kMaxGroup
+// independent GEMM problems (the layers of a time step that do not depend on each other:
+// three forward layers that read the same particles, six weight-gradient products, ...);
+// one CTA per SM walks over the tiles of all problems (grid-stride; column tile fastest so
+// that co-running CTAs share A rows in L2).  The accumulator is double buffered in TMEM,
+// so the epilogue of tile i (4 dedicated warps) overlaps the copies, rounding and MMAs of
+// tile i+1, and the operand ring runs across tile and problem boundaries.
+// Warp roles: warps 0..7 "converters" (cp.async + rounding), warp 8 MMA issuer, warps 9..12
+// epilogue.  Barriers (arrivals per phase):
+//   full[s]   8 (converter warps)   stage s holds rounded operands
+//   empty[s]  tcgen05.commit        the MMAs that read stage s are done
+//   tfull[a]  tcgen05.commit        accumulator a holds a finished tile
+//   tempty[a] 4 (epilogue warps)    accumulator a has been read out
+// =====================================================================================
+constexpr int kEpiWarps = 4;
+constexpr int kThreadsP = kThreadsV2 + 32 + kEpiWarps * 32;      // 416
+#endif  // !BFVI_EMU
+constexpr int kThreadsPhost = 416;
+constexpr int kMaxGroup = 8;
+
+struct GemmGroup {
+  GemmParams g[kMaxGroup];
+  int tile_end[kMaxGroup];                    // exclusive prefix sums of the tile counts
+  int tiles_m[kMaxGroup], tiles_n[kMaxGroup];
+  int chunks[kMaxGroup];                      // K chunks per tile (a short last split-K slice is zero padded)
+  int n, total;
+};
+#ifndef BFVI_EMU
+
+struct TileInfo {
+  int pi, chunks, col0;
+  int64_t row0, k_begin, k_end;
+};
+__device__ __forceinline__ TileInfo decode_tile(const GemmGroup& grp, int t, int BN) {
+  TileInfo ti;
+  int pi = 0, start = 0;
+#pragma unroll 1
+  while (pi + 1 < grp.n && t >= grp.tile_end[pi]) { start = grp.tile_end[pi]; ++pi; }
+  const int local = t - start;
+  const int tn = local % grp.tiles_n[pi];
+  const int rest = local / grp.tiles_n[pi];
+  const int tm = rest % grp.tiles_m[pi], tz = rest / grp.tiles_m[pi];
+  const GemmParams& q = grp.g[pi];
+  ti.pi = pi; ti.chunks = grp.chunks[pi];
+  ti.row0 = (int64_t)tm * kBM; ti.col0 = tn * BN;
+  ti.k_begin = q.k_split > 0 ? (int64_t)tz * q.k_split : 0;
+  ti.k_end = q.k_split > 0 ? (ti.k_begin + q.k_split < q.K ? ti.k_begin + q.k_split : q.K) : q.K;
+  return ti;
+}
+
+template <int BN, bool SPLIT, bool VEC>
+__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_constant__ GemmGroup grp, int n_stages) {
   using Cfg = TileCfg<BN, SPLIT>;
   extern __shared__ unsigned char tc_smem_dyn[];
-  __shared__ __align__(8) uint64_t mbar[kMaxStages];
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
-  // swizzle-128B tiles need 1024-byte aligned bases
   unsigned char* smem = tc_smem_dyn + ((1024u - (smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
   auto tileA = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
   auto tileW = [&](int s) { return tileA(s) + Cfg::kABytes; };
   auto tileAl = [&](int s) { return tileW(s) + Cfg::kWBytes; };
   auto tileWl = [&](int s) { return tileAl(s) + Cfg::kABytes; };
+  float* patches = reinterpret_cast<float*>(smem + (size_t)n_stages * Cfg::kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kBM;
-  const int col0 = blockIdx.y * BN;
-  constexpr uint32_t kCols = BN < 32 ? 32 : BN;
+  constexpr uint32_t kCols = 2 * BN;                       // two accumulators; 64 .. 512, a power of two
+  constexpr int kMmaWarp = kThreadsV2 / 32;
 
-  if (warp == 0) tmem_alloc(&tmem_base_s, kCols);
+  if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, kCols);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) mbar_init(&mbar[s], 1);
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], kThreadsV2 / 32); mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-
-  const int64_t k_begin = p.k_split > 0 ? (int64_t)blockIdx.z * p.k_split : 0;
-  const int64_t k_end = p.k_split > 0 ? (k_begin + p.k_split < p.K ? k_begin + p.k_split : p.K) : p.K;
-  const int n_chunks = (int)((k_end - k_begin + kBK - 1) / kBK);
-  const uint32_t idesc = umma_idesc_tf32(kBM, BN);
-  const OperandView va = make_view(p.A, p.lda, row0, p.M, kBM, k_begin);
-  const OperandView vw = make_view(p.W, p.ldw, col0, p.N, BN, k_begin);
-  const int64_t k_left0 = k_end - k_begin - (threadIdx.x & 7) * 4;
-  auto issue_load = [&](int chunk, int s) {
-    load_tile_async<kBM>(smem_u32(tileA(s)), va, chunk, k_left0);
-    load_tile_async<BN>(smem_u32(tileW(s)), vw, chunk, k_left0);
-  };
-  // prologue: chunks 0 .. n_stages-2 in flight (one commit group per chunk, empty groups keep the count uniform)
-  for (int c = 0; c < n_stages - 1; ++c) {
-    if (c < n_chunks) issue_load(c, c);
-    cp_async_commit();
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = tmem_base_s;
+  const uint32_t tmem_base = tmem_base_s;
 
-  int s = 0;                                   // stage of chunk i
-  for (int i = 0; i < n_chunks; ++i) {
-    // chunk i is the oldest group but (n_stages - 2) younger ones: wait for it
-    if (n_stages == 2) cp_async_wait<0>(); else if (n_stages == 3) cp_async_wait<1>(); else cp_async_wait<2>();
-    convert_tile<kBM, SPLIT>(tileA(s), tileAl(s), va.off0);
-    convert_tile<BN, SPLIT>(tileW(s), tileWl(s), vw.off0);
-    fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = ((int)blockIdx.x < grp.total) ? (grp.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < kMmaWarp) {
+    // ================= converters: copy + round, one "job" = one K chunk of one tile =================
+    const uint32_t off0 = (uint32_t)((threadIdx.x >> 3) * kRowBytes + (((threadIdx.x & 7) ^ ((threadIdx.x >> 3) & 7)) << 4));
+    OperandView va, vw;
+    int64_t k_left0 = 0;
+    int l_tile = -1, l_chunk = 0, l_chunks = 0;           // load cursor: next job to copy
+    int c_tile = 0, c_chunk = 0, c_chunks = 0;            // convert cursor
+    auto load_more = [&]() { return l_chunk < l_chunks || l_tile + 1 < my_tiles; };
+    auto issue_next_load = [&](int s) {                   // copies the job under the load cursor into stage s
+      if (l_chunk == l_chunks) {
+        l_chunk = 0; ++l_tile;
+        const TileInfo ti = decode_tile(grp, (int)blockIdx.x + l_tile * (int)gridDim.x, BN);
+        const GemmParams& q = grp.g[ti.pi];
+        l_chunks = ti.chunks;
+        va = make_view(q.A, q.lda, ti.row0, q.M, kBM, ti.k_begin);
+        vw = make_view(q.W, q.ldw, ti.col0, q.N, BN, ti.k_begin);
+        k_left0 = ti.k_end - ti.k_begin - (threadIdx.x & 7) * 4;
+      }
+      load_tile_async<kBM, VEC>(smem_u32(tileA(s)), va, l_chunk, k_left0);
+      load_tile_async<BN, VEC>(smem_u32(tileW(s)), vw, l_chunk, k_left0);
+      ++l_chunk;
+    };
+    for (int c = 0; c < n_stages - 1; ++c) {              // prologue: jobs 0 .. n_stages-2
+      if (load_more()) issue_next_load(c);
+      cp_async_commit();
+    }
+    if (my_tiles > 0) c_chunks = decode_tile(grp, (int)blockIdx.x, BN).chunks;
+    int s = 0;
+    for (int j = 0; c_tile < my_tiles; ++j) {
+      if (n_stages == 2) cp_async_wait<0>(); else if (n_stages == 3) cp_async_wait<1>(); else cp_async_wait<2>();
+#ifndef BFVI_DBG_NO_CONVERT
+      convert_tile<kBM, SPLIT>(tileA(s), tileAl(s), off0);
+      convert_tile<BN, SPLIT>(tileW(s), tileWl(s), off0);
+#endif
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (load_more()) {                                  // refill the stage job j-1 used
+        const int sp = s == 0 ? n_stages - 1 : s - 1;
+        if (j >= 1) mbar_wait(&empty_bar[sp], (uint32_t)(((j - 1) / n_stages) & 1));
+        issue_next_load(sp);
+      }
+      cp_async_commit();
+      s = s + 1 == n_stages ? 0 : s + 1;
+      if (++c_chunk == c_chunks) {
+        c_chunk = 0;
+        if (++c_tile < my_tiles) c_chunks = decode_tile(grp, (int)blockIdx.x + c_tile * (int)gridDim.x, BN).chunks;
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kBM, BN);
+      int s = 0, g = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int a = lt & 1;
+        const int chunks = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN).chunks;
+        mbar_wait(&tempty_bar[a], (uint32_t)(((lt >> 1) & 1) ^ 1));     // epilogue has drained accumulator a
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+        for (int i = 0; i < chunks; ++i, ++g) {
+          mbar_wait(&full_bar[s], (uint32_t)((g / n_stages) & 1));
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(tileA(s)), w0 = smem_u32(tileW(s));
+          const uint32_t al0 = smem_u32(tileAl(s)), wl0 = smem_u32(tileWl(s));
+#ifndef BFVI_DBG_NO_MMA
+#pragma unroll
+          for (int q = 0; q < kBK / 8; ++q) {
+            const uint64_t da = umma_desc_sw128(a0 + q * 32), dw = umma_desc_sw128(w0 + q * 32);
+            umma_tf32(tmem_acc, da, dw, idesc, (i > 0 || q > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_tf32(tmem_acc, umma_desc_sw128(al0 + q * 32), dw, idesc, 1u);
+              umma_tf32(tmem_acc, da, umma_desc_sw128(wl0 + q * 32), idesc, 1u);
+            }
+          }
+#endif
+          umma_commit(&empty_bar[s]);
+          s = s + 1 == n_stages ? 0 : s + 1;
+        }
+        umma_commit(&tfull_bar[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps: TMEM lanes 32 (warp % 4) .. =================
+    const int wq = warp & 3;
+    float* patch = patches + (warp - kMmaWarp - 1) * (32 * 33);
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int a = lt & 1;
+      const TileInfo ti = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN);
+      const GemmParams& p = grp.g[ti.pi];
+      const bool fast_c = VEC && epilogue_fast_ok(p);
+      const int64_t wrow0 = ti.row0 + wq * 32;
+      const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+      mbar_wait(&tfull_bar[a], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
-      const uint32_t a0 = smem_u32(tileA(s)), w0 = smem_u32(tileW(s));
-      const uint32_t al0 = smem_u32(tileAl(s)), wl0 = smem_u32(tileWl(s));
-#pragma unroll
-      for (int j = 0; j < kBK / 8; ++j) {      // one MMA consumes 8 floats = 32 bytes of every row's line
-        const uint64_t da = umma_desc_sw128(a0 + j * 32), dw = umma_desc_sw128(w0 + j * 32);
-        umma_tf32(tmem_d, da, dw, idesc, (i > 0 || j > 0) ? 1u : 0u);
-        if (SPLIT) {
-          umma_tf32(tmem_d, umma_desc_sw128(al0 + j * 32), dw, idesc, 1u);
-          umma_tf32(tmem_d, da, umma_desc_sw128(wl0 + j * 32), idesc, 1u);
-        }
-      }
-      umma_commit(&mbar[s]);                    // arrives when these MMAs have read their operands
-    }
-    // refill the stage chunk i-1 used with chunk i + n_stages - 1 once its MMAs are done
-    const int nxt = i + n_stages - 1;
-    if (nxt < n_chunks) {
-      const int sp = s == 0 ? n_stages - 1 : s - 1;
-      if (i >= 1) mbar_wait(&mbar[sp], (uint32_t)(((i - 1) / n_stages) & 1));
-      issue_load(nxt, sp);
-    }
-    cp_async_commit();
-    s = s + 1 == n_stages ? 0 : s + 1;
-  }
-  if (n_chunks > 0) {                           // the last commit covers every earlier MMA
-    const int last = n_chunks - 1;
-    mbar_wait(&mbar[last % n_stages], (uint32_t)((last / n_stages) & 1));
-  }
-  cp_async_wait<0>();
-  tc_fence_after();
-  __syncthreads();                              // every thread's copies have landed: the ring is free for the patches
-
-  // ---- epilogue: warps w and w + 4 own accumulator rows (TMEM lanes) 32 (w % 4) .., alternate 32-column blocks
-  float* patch = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-  const int wq = warp & 3;
-  const int64_t wrow0 = row0 + wq * 32;
-  const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
 #pragma unroll 1
-  for (int c = (warp >> 2) * 32; c < BN; c += 64) {
-    if (col0 + c >= p.N) break;
-    float v[32];
-    if (n_chunks > 0) {
-      tmem_ld32(tmem_d + ((uint32_t)(wq * 32) << 16) + (uint32_t)c, v);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = 0.f;
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) patch[lane * 33 + j] = v[j];      // thread = row
-    __syncwarp();
-    const int col = col0 + c + lane;                                // lane = column from here on
-    const bool col_ok = col < p.N;
-    const int cols_valid = p.N - (col0 + c) < 32 ? p.N - (col0 + c) : 32;
-    const float bias = (p.bias != nullptr && col_ok) ? p.bias[col] : 0.f;
-    float csum = 0.f;
-    if (col_ok) {
-      float* dst = p.C + wrow0 * p.ldc + col;
-      const float* aux = p.mask_aux != nullptr ? p.mask_aux + wrow0 * p.ldaux + col : nullptr;
-      const bool relu = p.act == ACT_RELU, split = p.k_split > 0, acc = p.accumulate != 0;
-#pragma unroll 4
-      for (int rr = 0; rr < rows_valid; ++rr) {
-        float x = patch[rr * 33 + lane] + bias;
-        if (relu) x = x < 0.f ? 0.f : x;
-        if (aux != nullptr) { x = *aux > 0.f ? x : 0.f; aux += p.ldaux; }
-        csum += x;
-        if (split) {
-          atomicAdd(dst, x);                                        // split-K partial tile
-        } else {
-          if (acc) x += *dst;
-          *dst = x;
+      for (int c = 0; c < BN; c += 32) {
+        if (ti.col0 + c >= p.N) break;
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * BN + c), v);
+        if (c + 32 >= BN || ti.col0 + c + 32 >= p.N) {    // last block read: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[a]);
         }
-        dst += p.ldc;
-        patch[rr * 33 + lane] = x;                                  // final value, for the transposed copy
+#ifndef BFVI_DBG_NO_EPI_STORE
+        epilogue_block(p, v, patch, wrow0, rows_valid, ti.col0 + c, lane, fast_c);
+#else
+        if (v[0] == 123.456f) patch[lane] = v[1];
+#endif
       }
-      if (p.colsum != nullptr) atomicAdd(p.colsum + col, csum);
     }
-    __syncwarp();
-    if (p.Ct != nullptr && p.k_split == 0 && lane < rows_valid) {   // lane = row again: Ct[col][row], full lines
-      float* dt = p.Ct + (int64_t)(col0 + c) * p.ldct + wrow0 + lane;
-#pragma unroll 4
-      for (int j = 0; j < cols_valid; ++j) { *dt = patch[lane * 33 + j]; dt += p.ldct; }
-    }
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_d, kCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kCols);
 }
 #endif  // !BFVI_EMU
 
@@ -601,6 +780,9 @@ template <int BN, bool SPLIT>
 inline size_t gemm_v2_stage_bytes() { return (size_t)(SPLIT ? 2 : 1) * (size_t)(kBM + BN) * kBK * sizeof(float); }
 template <int BN, bool SPLIT>
 inline size_t gemm_v2_smem_bytes(int stages) { return gemm_v2_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024; }
+// persistent kernel: ring + four epilogue patches
+template <int BN, bool SPLIT>
+inline size_t gemm_p_smem_bytes(int stages) { return gemm_v2_smem_bytes<BN, SPLIT>(stages) + 4 * 32 * 33 * sizeof(float); }
 
 }  // namespace tc
 }  // namespace bfvi

@@ -11,9 +11,9 @@ pytestmark = pytest.mark.gpu
 
 
 def round_tf32(x):
-    """Round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32."""
+    """Round-to-nearest-even to 10 explicit mantissa bits, like cvt.rn.tf32.f32 (the kernel's F2FP)."""
     i = x.contiguous().view(torch.int32)
-    i = (i + 0x1000) & ~0x1FFF
+    i = (i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF
     return i.view(torch.float32)
 
 
