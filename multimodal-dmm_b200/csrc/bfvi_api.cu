@@ -627,6 +627,7 @@ struct LargePlan {
   size_t g, nl, nlT, lin, as, d_as, d_asT, d_g, d_gT, d_lin, d_linT, d_nl, d_nlT, dz;
   size_t c_mu, c_sd, d_pm, d_v, zvec;
   size_t hdec, hdecT, dhd, dhdT, dmean, dstd, dmeanT, dstdT;
+  size_t side_grads;                                 // zeroed: parameter gradients of the side stream (pass A)
 };
 
 // `fonly` != null plans the workspace of a stand-alone z_filter call (bfvi_filter_fwd / _bwd of the
@@ -690,6 +691,45 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   return BFVI_OK;
 }
 
+// Second scratch set for the filter-only pass ("pass A": f_mode, one particle), which the step runs on a
+// side stream beside the particle pass and the smoother: its own row scratch (rows = chains), decoder
+// scratch, observation-gradient and parameter-gradient buffers, appended to the main plan's workspace.
+void plan_large_side(const bfvi_model* m, const bfvi_step_args* a, const LargePlan& pl, LargePlan* ps) {
+  *ps = pl;
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim;
+  (void)a;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  size_t cur = pl.total;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  const size_t f = sizeof(float);
+  ps->zero_begin = cur;
+  ps->dobs_mean = carve(f * pl.tbz * M); ps->dobs_std = carve(f * pl.tbz * M);
+  ps->side_grads = carve(f * lay.total);
+  ps->zero_end = cur;
+  const size_t R = pl.C;                               // one particle per chain
+  ps->R = R;
+  const size_t rz = f * R * Z, rh = f * R * H;
+  ps->zrows = carve(rz); ps->zrowsT = carve(rz);
+  ps->h1 = carve(rh); ps->h1T = carve(rh); ps->h3 = carve(rh); ps->h3T = carve(rh);
+  ps->dh1 = carve(rh); ps->dh1T = carve(rh); ps->dh3 = carve(rh); ps->dh3T = carve(rh);
+  size_t* zbufs[] = {&ps->g, &ps->nl, &ps->nlT, &ps->lin, &ps->as, &ps->d_as, &ps->d_asT, &ps->d_g, &ps->d_gT,
+                     &ps->d_lin, &ps->d_linT, &ps->d_nl, &ps->d_nlT, &ps->dz};
+  for (size_t* z : zbufs) *z = carve(rz);
+  ps->c_mu = carve(f * pl.C * Z); ps->c_sd = carve(f * pl.C * Z);
+  ps->d_pm = carve(f * pl.C * Z); ps->d_v = carve(f * pl.C * Z);
+  ps->hdec = carve(f * pl.tb * H); ps->hdecT = carve(f * pl.tb * H);
+  ps->dhd = carve(f * pl.tb * H); ps->dhdT = carve(f * pl.tb * H);
+  ps->dmean = carve(f * pl.tb * pl.d_max); ps->dstd = carve(f * pl.tb * pl.d_max);
+  ps->dmeanT = carve(f * pl.tb * pl.d_max); ps->dstdT = carve(f * pl.tb * pl.d_max);
+  ps->total = cur;
+}
+
+// y[i] += x[i]  (join of the side stream's gradient buffers)
+__global__ void __launch_bounds__(256) add_into_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += x[i];
+}
+
 // fills mu[z] = z0_mean, sd[z] = exp(z0_log_std) + min_std (the "infer" of the prior-matching chain)
 __global__ void prior_fill_kernel(const float* z0_mean, const float* z0_log_std, float min_std, int Z, float* mu,
                                   float* sd) {
@@ -707,9 +747,16 @@ __global__ void match_tail_kernel(const float* c_mu, const float* c_sd, const fl
 int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
                const bfvi_filter_args* fonly, bool fonly_backward, void* workspace, size_t workspace_bytes,
                float* loss_out, int32_t* launches, cudaStream_t st) {
-  LargePlan pl;
-  plan_large(m, a, fonly, &pl);
-  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  // `pl`, `grads` and `st` are the CURRENT context of every helper below (captured by reference):
+  // the main one, or — while pass A is being queued — the side scratch set, gradient buffer and stream
+  LargePlan pl_main, pl_side;
+  plan_large(m, a, fonly, &pl_main);
+  pl_side = pl_main;
+  if (!fonly) plan_large_side(m, a, pl_main, &pl_side);
+  LargePlan pl = pl_main;
+  float* const grads_main = grads;
+  const cudaStream_t st_main = st;
+  if (workspace_bytes < pl_side.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl_side.total);
   if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
   char* ws = (char*)workspace;
   bfvi_layout lay;
@@ -728,6 +775,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
 
   if (!fonly) {                      // a lone filter ACCUMULATES into the caller's (zeroed) gradient buffers
     cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
+    cudaMemsetAsync(ws + pl_side.zero_begin, 0, pl_side.zero_end - pl_side.zero_begin, st);
     if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
   }
   BFVI_CHECK_CUDA();
@@ -1063,14 +1111,9 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       if (a->s_mult != 0.f && !fc.noise.eps && (a->sample || a->sample_init)) return fail(BFVI_ERR_ARG, "eps_ssmt missing");
     }
     const bool do_f = a->f_mult != 0.f, do_s = a->s_mult != 0.f;
-    if (do_f) { if (int rc = pass_fwd(fa, with_grad ? F(pl.pa[5]) : nullptr)) return rc; }
-    if (do_s) {
-      if (int rc = pass_fwd(fb, nullptr)) return rc;
-      if (int rc = pass_fwd(fc, with_grad ? F(pl.pc[5]) : nullptr)) return rc;
-    }
-    // ---- decoders + NLL, forward and backward (models/dmm.py:207-211, models/losses.py:68-89) ----
-    for (int pass = 0; pass < 2; ++pass) {
-      if ((pass == 0 && !do_f) || (pass == 1 && !do_s)) continue;
+    // ---- decoders + NLL, forward and backward, on the samples of one pass
+    //      (models/dmm.py:207-211, models/losses.py:68-89) ----
+    auto decode_pass = [&](int pass) -> int {
       const float mult = pass == 0 ? a->f_mult : a->s_mult;
       float* samp = pass == 0 ? F(pl.pa[4]) : F(pl.pc[4]);
       float* sampT = pass == 0 ? F(pl.pa[5]) : F(pl.pc[5]);
@@ -1107,6 +1150,40 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
           if (int rc = wgrad(F(pl.dhdT), sampT + (size_t)s * pl.tbz, tb, H, Z, l.in_to_h_w)) return rc;
           if (int rc = flush()) return rc;
         }
+      BFVI_CHECK_CUDA();
+      return BFVI_OK;
+    };
+    // ---- pass A (f_mode filter, its decoders and its backward) is independent of passes B -> C until
+    //      the encoder backward: it runs on a side stream with its own scratch set and gradient buffers,
+    //      beside the particle pass; its GEMMs are latency-bound (S*B rows) and fill SMs the other
+    //      stream leaves idle.  BFVI_LARGE_SIDE=0 keeps everything on the caller's stream. ----
+    static const bool want_side = [] { const char* e = getenv("BFVI_LARGE_SIDE"); return !e || atoi(e) != 0; }();
+    SideStreams* side = (want_side && do_f && do_s && with_grad) ? side_streams() : nullptr;
+    if (do_f) {
+      if (side) {
+        if (int rc = flush()) return rc;
+        cudaEventRecord(side->fork, st_main);
+        cudaStreamWaitEvent(side->stream[0], side->fork, 0);
+        pl = pl_side; grads = F(pl_side.side_grads); st = side->stream[0];
+        for (int i = 0; i < M; ++i) {
+          fa.experts[i].d_mean = F(pl.dobs_mean) + (size_t)i * pl.tbz;
+          fa.experts[i].d_std = F(pl.dobs_std) + (size_t)i * pl.tbz;
+        }
+      }
+      if (int rc = pass_fwd(fa, with_grad ? F(pl.pa[5]) : nullptr)) return rc;
+      if (int rc = decode_pass(0)) return rc;
+      if (side) {                    // the whole backward of pass A follows on the side stream
+        fa.d_samples = F(pl.a_dsamp);
+        if (int rc = pass_bwd(fa)) return rc;
+        if (int rc = flush()) return rc;
+        cudaEventRecord(side->join[0], st);
+        pl = pl_main; grads = grads_main; st = st_main;
+      }
+    }
+    if (do_s) {
+      if (int rc = pass_fwd(fb, nullptr)) return rc;
+      if (int rc = pass_fwd(fc, with_grad ? F(pl.pc[5]) : nullptr)) return rc;
+      if (int rc = decode_pass(1)) return rc;
     }
     BFVI_CHECK_CUDA();
     // ---- backward through the three passes and the encoders ----------------------------------
@@ -1117,9 +1194,19 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
         fb.d_prior_mean = F(pl.b_dpm); fb.d_prior_std = F(pl.b_dps);
         if (int rc = pass_bwd(fb)) return rc;
       }
-      if (do_f) {
+      if (do_f && !side) {
         fa.d_samples = F(pl.a_dsamp);
         if (int rc = pass_bwd(fa)) return rc;
+      }
+      if (side) {                    // join: add the side stream's parameter / observation gradients
+        if (int rc = flush()) return rc;
+        cudaStreamWaitEvent(st_main, side->join[0], 0);
+        auto ka = add_into_kernel;
+        BFVI_LAUNCH(ka, dim3((unsigned)grid_for(lay.total, 256, 4)), dim3(256), 0, st, grads, (const float*)F(pl_side.side_grads), (int64_t)lay.total);
+        const int64_t n_obs = (int64_t)pl.tbz * M;
+        BFVI_LAUNCH(ka, dim3((unsigned)grid_for(n_obs, 256, 8)), dim3(256), 0, st, dobs_mean, (const float*)F(pl_side.dobs_mean), n_obs);
+        BFVI_LAUNCH(ka, dim3((unsigned)grid_for(n_obs, 256, 8)), dim3(256), 0, st, dobs_std, (const float*)F(pl_side.dobs_std), n_obs);
+        n_launch += 3;
       }
       for (int i = 0; i < M; ++i) {
         const bfvi_mlp_layout& l = lay.enc[i];
@@ -1591,9 +1678,10 @@ int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* by
   if (int rc = check_step(m, a)) return rc;
   if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
   if (family_of(m->z_dim, m->h_dim) == 2) {
-    LargePlan lp;
+    LargePlan lp, ls;
     plan_large(m, a, nullptr, &lp);
-    *bytes = lp.total;
+    plan_large_side(m, a, lp, &ls);
+    *bytes = ls.total;
     return BFVI_OK;
   }
   StepPlan pl;
