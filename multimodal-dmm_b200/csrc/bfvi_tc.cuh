@@ -444,6 +444,9 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
 //   128-bit vectors (eight instructions fill each row's 128-byte line); the transposed copy leaves
 //   as full lines (lane = row); only the column sums go through the patch;
 //  general path: rows -> patch, then lane = column, so that every global access is a full line.
+// (A variant staging C through the patch for full-line float4 stores measured SLOWER — 81 -> 101 us on the
+// 57 600 x 64 -> 512 layer: the four epilogue warps are issue/latency-bound, not store-bound.)
+constexpr int kPatchLd = 33;      // floats per patch row (conflict-free row <-> column transposition)
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, float (&v)[32], float* patch, int64_t wrow0,
                                                int rows_valid, int cbase, int lane, bool fast_c) {
   if (fast_c && cbase + 32 <= p.N) {
@@ -554,17 +557,17 @@ __device__ __forceinline__ bool epilogue_fast_ok(const GemmParams& p) {
 // that co-running CTAs share A rows in L2).  The accumulator is double buffered in TMEM,
 // so the epilogue of tile i (4 dedicated warps) overlaps the copies, rounding and MMAs of
 // tile i+1, and the operand ring runs across tile and problem boundaries.
-// Warp roles: warps 0..7 "converters" (cp.async + rounding), warp 8 MMA issuer, warps 9..12
+// Warp roles: warps 0..7 "converters" (cp.async + rounding), warp 8 MMA issuer, warps 9..16
 // epilogue.  Barriers (arrivals per phase):
 //   full[s]   8 (converter warps)   stage s holds rounded operands
 //   empty[s]  tcgen05.commit        the MMAs that read stage s are done
 //   tfull[a]  tcgen05.commit        accumulator a holds a finished tile
-//   tempty[a] 4 (epilogue warps)    accumulator a has been read out
+//   tempty[a] 8 (epilogue warps)    accumulator a has been read out
 // =====================================================================================
-constexpr int kEpiWarps = 4;
-constexpr int kThreadsP = kThreadsV2 + 32 + kEpiWarps * 32;      // 416
+constexpr int kEpiWarps = 8;
+constexpr int kThreadsP = kThreadsV2 + 32 + kEpiWarps * 32;      // 544
 #endif  // !BFVI_EMU
-constexpr int kThreadsPhost = 416;
+constexpr int kThreadsPhost = 544;
 constexpr int kMaxGroup = 8;
 
 struct GemmGroup {
@@ -595,6 +598,14 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmGroup& grp, int t, int
   ti.k_begin = q.k_split > 0 ? (int64_t)tz * q.k_split : 0;
   ti.k_end = q.k_split > 0 ? (ti.k_begin + q.k_split < q.K ? ti.k_begin + q.k_split : q.K) : q.K;
   return ti;
+}
+
+// K chunks of tile t (no coordinates: what the MMA issuer and the convert cursor need)
+__device__ __forceinline__ int tile_chunks(const GemmGroup& grp, int t) {
+  int pi = 0;
+#pragma unroll 1
+  while (pi + 1 < grp.n && t >= grp.tile_end[pi]) ++pi;
+  return grp.chunks[pi];
 }
 
 template <int BN, bool SPLIT, bool VEC>
@@ -633,9 +644,18 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
 
   if (warp < kMmaWarp) {
     // ================= converters: copy + round, one "job" = one K chunk of one tile =================
-    const uint32_t off0 = (uint32_t)((threadIdx.x >> 3) * kRowBytes + (((threadIdx.x & 7) ^ ((threadIdx.x >> 3) & 7)) << 4));
-    OperandView va, vw;
-    int64_t k_left0 = 0;
+    // Thread t owns the 16-byte vectors (row r0 + 32 i, column c4) of every chunk, r0 = t >> 3, c4 = t & 7.
+    // Per-tile state of the load cursor is precomputed so that an interior job costs two pointer bumps
+    // and six LDGSTS (the pass is issue-bound: profiles/r1_gemm_p_full.txt).
+    const int r0 = threadIdx.x >> 3, c4 = threadIdx.x & 7;
+    const uint32_t off0 = (uint32_t)(r0 * kRowBytes + ((c4 ^ (r0 & 7)) << 4));
+    const uint32_t ring0 = smem_u32(smem) + off0;
+    constexpr int kVA = kBM / 32, kVW = BN / 32;          // vectors per thread and chunk: A, W
+    const float* a_ptr = nullptr; const float* w_ptr = nullptr;
+    const float* a_base = nullptr; const float* w_base = nullptr;
+    int64_t a_step = 0, w_step = 0;
+    int na = 0, nw = 0;                                   // valid vectors (rows inside the matrix)
+    int64_t k_left = 0;                                   // floats from this thread's column to the end of K
     int l_tile = -1, l_chunk = 0, l_chunks = 0;           // load cursor: next job to copy
     int c_tile = 0, c_chunk = 0, c_chunks = 0;            // convert cursor
     auto load_more = [&]() { return l_chunk < l_chunks || l_tile + 1 < my_tiles; };
@@ -645,22 +665,62 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
         const TileInfo ti = decode_tile(grp, (int)blockIdx.x + l_tile * (int)gridDim.x, BN);
         const GemmParams& q = grp.g[ti.pi];
         l_chunks = ti.chunks;
-        va = make_view(q.A, q.lda, ti.row0, q.M, kBM, ti.k_begin);
-        vw = make_view(q.W, q.ldw, ti.col0, q.N, BN, ti.k_begin);
-        k_left0 = ti.k_end - ti.k_begin - (threadIdx.x & 7) * 4;
+        a_base = q.A; w_base = q.W;
+        a_ptr = q.A + (ti.row0 + r0) * q.lda + ti.k_begin + c4 * 4;
+        w_ptr = q.W + ((int64_t)ti.col0 + r0) * q.ldw + ti.k_begin + c4 * 4;
+        a_step = 32 * q.lda; w_step = 32 * q.ldw;
+        const int64_t ra = q.M - ti.row0 - r0, rw = (int64_t)q.N - ti.col0 - r0;      // rows from r0 to the edge
+        na = ra <= 0 ? 0 : ra >= kBM ? kVA : (int)((ra + 31) / 32);
+        nw = rw <= 0 ? 0 : rw >= BN ? kVW : (int)((rw + 31) / 32);
+        if (na > kVA) na = kVA;
+        if (nw > kVW) nw = kVW;
+        k_left = ti.k_end - ti.k_begin - c4 * 4;
       }
-      load_tile_async<kBM, VEC>(smem_u32(tileA(s)), va, l_chunk, k_left0);
-      load_tile_async<BN, VEC>(smem_u32(tileW(s)), vw, l_chunk, k_left0);
+      const uint32_t dst_a = ring0 + (uint32_t)s * Cfg::kStageBytes, dst_w = dst_a + Cfg::kABytes;
+      if (VEC && k_left >= 4 && na == kVA && nw == kVW) {            // interior job
+#pragma unroll
+        for (int i = 0; i < kVA; ++i) cp_async16(dst_a + i * (32 * kRowBytes), a_ptr + i * a_step, 16);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) cp_async16(dst_w + i * (32 * kRowBytes), w_ptr + i * w_step, 16);
+      } else {
+        const int kbytes = k_left >= 4 ? 16 : k_left > 0 ? (int)k_left * 4 : 0;
+#pragma unroll
+        for (int i = 0; i < kVA + kVW; ++i) {
+          const bool is_a = i < kVA;
+          const int ii = is_a ? i : i - kVA;
+          const bool in = ii < (is_a ? na : nw) && kbytes > 0;
+          const float* src = is_a ? a_ptr + ii * a_step : w_ptr + ii * w_step;
+          const float* dummy = is_a ? a_base : w_base;
+          const uint32_t dst = (is_a ? dst_a : dst_w) + ii * (32 * kRowBytes);
+          if (VEC) {
+            cp_async16(dst, in ? src : dummy, in ? kbytes : 0);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool ine = in && e * 4 < kbytes;
+              cp_async4(dst + e * 4, ine ? src + e : dummy, ine ? 4 : 0);
+            }
+          }
+        }
+      }
+      a_ptr += kBK; w_ptr += kBK; k_left -= kBK;
       ++l_chunk;
     };
-    for (int c = 0; c < n_stages - 1; ++c) {              // prologue: jobs 0 .. n_stages-2
+    // A stage is refilled `lag` jobs after the job that used it: with a 4-stage ring lag = 2, so the wait
+    // for that job's MMAs (hand-over latency MMA warp -> tensor pipe -> commit -> this warp, ~0.5 us) has a
+    // whole iteration of slack and two jobs stay in flight; shallower rings refill at once (lag 1).
+    const int lag = n_stages >= 4 ? 2 : 1;
+    for (int c = 0; c < n_stages - lag; ++c) {            // prologue: jobs 0 .. n_stages-lag-1
       if (load_more()) issue_next_load(c);
       cp_async_commit();
     }
-    if (my_tiles > 0) c_chunks = decode_tile(grp, (int)blockIdx.x, BN).chunks;
+    if (my_tiles > 0) c_chunks = tile_chunks(grp, (int)blockIdx.x);
     int s = 0;
-    for (int j = 0; c_tile < my_tiles; ++j) {
-      if (n_stages == 2) cp_async_wait<0>(); else if (n_stages == 3) cp_async_wait<1>(); else cp_async_wait<2>();
+    uint32_t round = 0;                                   // how many times the ring has wrapped (parity source)
+    int done = 0;                                         // jobs converted so far
+    while (c_tile < my_tiles) {
+      // job `done` is the oldest copy group but (n_stages - lag - 1) younger ones
+      if (n_stages - lag == 1) cp_async_wait<0>(); else cp_async_wait<1>();
 #ifndef BFVI_DBG_NO_CONVERT
       convert_tile<kBM, SPLIT>(tileA(s), tileAl(s), off0);
       convert_tile<BN, SPLIT>(tileW(s), tileWl(s), off0);
@@ -668,16 +728,17 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full_bar[s]);
-      if (load_more()) {                                  // refill the stage job j-1 used
-        const int sp = s == 0 ? n_stages - 1 : s - 1;
-        if (j >= 1) mbar_wait(&empty_bar[sp], (uint32_t)(((j - 1) / n_stages) & 1));
+      if (load_more()) {                                  // job done + n_stages - lag goes where job done - lag was
+        const int sp = s - lag < 0 ? s - lag + n_stages : s - lag;
+        if (done >= lag) mbar_wait(&empty_bar[sp], (s - lag < 0 ? round - 1u : round) & 1u);
         issue_next_load(sp);
       }
       cp_async_commit();
-      s = s + 1 == n_stages ? 0 : s + 1;
+      ++done;
+      if (++s == n_stages) { s = 0; ++round; }
       if (++c_chunk == c_chunks) {
         c_chunk = 0;
-        if (++c_tile < my_tiles) c_chunks = decode_tile(grp, (int)blockIdx.x + c_tile * (int)gridDim.x, BN).chunks;
+        if (++c_tile < my_tiles) c_chunks = tile_chunks(grp, (int)blockIdx.x + c_tile * (int)gridDim.x);
       }
     }
     cp_async_wait<0>();
@@ -685,15 +746,16 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
     // ================= MMA issuer =================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(kBM, BN);
-      int s = 0, g = 0;
+      int s = 0;
+      uint32_t round = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
         const int a = lt & 1;
-        const int chunks = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN).chunks;
+        const int chunks = tile_chunks(grp, (int)blockIdx.x + lt * (int)gridDim.x);
         mbar_wait(&tempty_bar[a], (uint32_t)(((lt >> 1) & 1) ^ 1));     // epilogue has drained accumulator a
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
-        for (int i = 0; i < chunks; ++i, ++g) {
-          mbar_wait(&full_bar[s], (uint32_t)((g / n_stages) & 1));
+        for (int i = 0; i < chunks; ++i) {
+          mbar_wait(&full_bar[s], round & 1u);
           tc_fence_after();
           const uint32_t a0 = smem_u32(tileA(s)), w0 = smem_u32(tileW(s));
           const uint32_t al0 = smem_u32(tileAl(s)), wl0 = smem_u32(tileWl(s));
@@ -709,16 +771,16 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
           }
 #endif
           umma_commit(&empty_bar[s]);
-          s = s + 1 == n_stages ? 0 : s + 1;
+          if (++s == n_stages) { s = 0; ++round; }
         }
         umma_commit(&tfull_bar[a]);
       }
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps: TMEM lanes 32 (warp % 4) .. =================
-    const int wq = warp & 3;
-    float* patch = patches + (warp - kMmaWarp - 1) * (32 * 33);
+    // ================= epilogue warps: two per TMEM lane group 32 (warp % 4) .., alternating 32-column blocks
+    const int wq = warp & 3, half = (warp - kMmaWarp - 1) >> 2;
+    float* patch = patches + (warp - kMmaWarp - 1) * (32 * kPatchLd);
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int a = lt & 1;
       const TileInfo ti = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN);
@@ -726,23 +788,30 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
       const bool fast_c = VEC && epilogue_fast_ok(p);
       const int64_t wrow0 = ti.row0 + wq * 32;
       const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+      const int limit = p.N - ti.col0 < BN ? p.N - ti.col0 : BN;      // valid columns of this tile
       mbar_wait(&tfull_bar[a], (uint32_t)((lt >> 1) & 1));
       tc_fence_after();
+      bool released = false;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (ti.col0 + c >= p.N) break;
+      for (int c = half * 32; c < limit; c += 64) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * BN + c), v);
-        if (c + 32 >= BN || ti.col0 + c + 32 >= p.N) {    // last block read: hand the accumulator back
+        if (c + 64 >= limit) {                            // this warp's last block: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tempty_bar[a]);
+          released = true;
         }
 #ifndef BFVI_DBG_NO_EPI_STORE
         epilogue_block(p, v, patch, wrow0, rows_valid, ti.col0 + c, lane, fast_c);
 #else
         if (v[0] == 123.456f) patch[lane] = v[1];
 #endif
+      }
+      if (!released) {                                    // no block for this warp in a narrow tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[a]);
       }
     }
   }
@@ -782,7 +851,7 @@ template <int BN, bool SPLIT>
 inline size_t gemm_v2_smem_bytes(int stages) { return gemm_v2_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024; }
 // persistent kernel: ring + four epilogue patches
 template <int BN, bool SPLIT>
-inline size_t gemm_p_smem_bytes(int stages) { return gemm_v2_smem_bytes<BN, SPLIT>(stages) + 4 * 32 * 33 * sizeof(float); }
+inline size_t gemm_p_smem_bytes(int stages) { return gemm_v2_smem_bytes<BN, SPLIT>(stages) + 8 * 32 * 33 * sizeof(float); }
 
 }  // namespace tc
 }  // namespace bfvi
