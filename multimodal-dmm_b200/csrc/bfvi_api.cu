@@ -565,11 +565,14 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
   return BFVI_OK;
 }
 
-// tile width of a launch: 32 when every problem is at most 32 wide, else 64 (98 kB of operands per
-// 4-stage... ring stage pair; BFVI_GEMM_BN raises the cap for experiments)
+// Tile width of a launch: the narrowest of 32 / 64 / 128 that covers the widest problem.  The kernel is bound
+// by the SM's shared-memory pipe (cp.async writes, the rounding pass, three UMMA operand reads per k-step
+// all share 128 B/clk), so a wider tile — the A chunk is copied and rounded once per 128 instead of per
+// 64 columns — is worth more than the extra ring stage a narrow one affords: C3-dims step 205 ms (cap 64),
+// 192 ms (128), 196 ms (256).  BFVI_GEMM_BN overrides the cap.
 template <bool SPLIT>
 int dispatch_gemm_bn(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
-  static const int cap = [] { const char* e = getenv("BFVI_GEMM_BN"); return e ? atoi(e) : 64; }();
+  static const int cap = [] { const char* e = getenv("BFVI_GEMM_BN"); return e ? atoi(e) : 128; }();
   int n_max = 0;
   for (int i = 0; i < n; ++i) n_max = gps[i].N > n_max ? gps[i].N : n_max;
   if (n_max <= 32 || cap <= 32) return launch_gemm_group<32, SPLIT>(gps, n, st);

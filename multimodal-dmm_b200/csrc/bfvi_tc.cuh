@@ -554,9 +554,9 @@ __device__ __forceinline__ bool epilogue_fast_ok(const GemmParams& p) {
 // independent GEMM problems (the layers of a time step that do not depend on each other:
 // three forward layers that read the same particles, six weight-gradient products, ...);
 // one CTA per SM walks over the tiles of all problems (grid-stride; column tile fastest so
-// that co-running CTAs share A rows in L2).  The accumulator is double buffered in TMEM,
-// so the epilogue of tile i (4 dedicated warps) overlaps the copies, rounding and MMAs of
-// tile i+1, and the operand ring runs across tile and problem boundaries.
+// that co-running CTAs share A rows in L2).  TMEM holds up to 8 accumulators (all 512 columns),
+// so the epilogue of tile i (8 dedicated warps) overlaps the copies, rounding and MMAs of the
+// following tiles, and the operand ring runs across tile and problem boundaries.
 // Warp roles: warps 0..7 "converters" (cp.async + rounding), warp 8 MMA issuer, warps 9..16
 // epilogue.  Barriers (arrivals per phase):
 //   full[s]   8 (converter warps)   stage s holds rounded operands
@@ -614,8 +614,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
   extern __shared__ unsigned char tc_smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-  __shared__ __align__(8) uint64_t tfull_bar[2];
-  __shared__ __align__(8) uint64_t tempty_bar[2];
+  // accumulators in TMEM: as many as fit in its 512 columns (up to 8), so the MMA issuer can run that many
+  // tiles ahead of the epilogue (with two, short-K tiles serialised: copies + MMAs + stores ADDED up)
+  constexpr int kAcc = 512 / BN > 8 ? 8 : 512 / BN;
+  __shared__ __align__(8) uint64_t tfull_bar[kAcc];
+  __shared__ __align__(8) uint64_t tempty_bar[kAcc];
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = tc_smem_dyn + ((1024u - (smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
   auto tileA = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
@@ -625,13 +628,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
   float* patches = reinterpret_cast<float*>(smem + (size_t)n_stages * Cfg::kStageBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t kCols = 2 * BN;                       // two accumulators; 64 .. 512, a power of two
+  constexpr uint32_t kCols = kAcc * BN;                    // 256 (BN = 32) or 512, a power of two
   constexpr int kMmaWarp = kThreadsV2 / 32;
 
   if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, kCols);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], kThreadsV2 / 32); mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+    for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   tc_fence_before();
@@ -749,9 +752,9 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
       int s = 0;
       uint32_t round = 0;
       for (int lt = 0; lt < my_tiles; ++lt) {
-        const int a = lt & 1;
+        const int a = lt % kAcc;
         const int chunks = tile_chunks(grp, (int)blockIdx.x + lt * (int)gridDim.x);
-        mbar_wait(&tempty_bar[a], (uint32_t)(((lt >> 1) & 1) ^ 1));     // epilogue has drained accumulator a
+        mbar_wait(&tempty_bar[a], (uint32_t)(((lt / kAcc) & 1) ^ 1));   // epilogue has drained accumulator a
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
         for (int i = 0; i < chunks; ++i) {
@@ -782,14 +785,14 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
     const int wq = warp & 3, half = (warp - kMmaWarp - 1) >> 2;
     float* patch = patches + (warp - kMmaWarp - 1) * (32 * kPatchLd);
     for (int lt = 0; lt < my_tiles; ++lt) {
-      const int a = lt & 1;
+      const int a = lt % kAcc;
       const TileInfo ti = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN);
       const GemmParams& p = grp.g[ti.pi];
       const bool fast_c = VEC && epilogue_fast_ok(p);
       const int64_t wrow0 = ti.row0 + wq * 32;
       const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
       const int limit = p.N - ti.col0 < BN ? p.N - ti.col0 : BN;      // valid columns of this tile
-      mbar_wait(&tfull_bar[a], (uint32_t)((lt >> 1) & 1));
+      mbar_wait(&tfull_bar[a], (uint32_t)((lt / kAcc) & 1));
       tc_fence_after();
       bool released = false;
 #pragma unroll 1
