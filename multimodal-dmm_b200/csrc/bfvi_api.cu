@@ -587,6 +587,18 @@ int gemm_group_tc(const bfvi::tc::GemmParams* gps, int n, int prec, cudaStream_t
 }
 int gemm_tc(const bfvi::tc::GemmParams& gp, int prec, cudaStream_t st) { return gemm_group_tc(&gp, 1, prec, st); }
 
+// A weight gradient dW (n_out, n_in) = dY^T X with few outputs and more inputs (the hidden -> head layers:
+// 64 x 512, decoder heads 16 x 512) would pad the 128 MMA rows with zeros; it runs transposed instead
+// (GemmParams::trans_out), the same shape as the fast 512 x 64 case.  BFVI_WGRAD_SWAP=0 disables.
+bool wgrad_swapped(int n_out, int n_in) {
+  static const bool on = [] {
+    const char* e = getenv("BFVI_WGRAD_SWAP");
+    const char* v1 = getenv("BFVI_GEMM_V1");            // the round-1 kernel has no transposed output
+    return (!e || atoi(e) != 0) && !(v1 && atoi(v1) != 0);
+  }();
+  return on && n_out < n_in && n_out <= 64;
+}
+
 // Split of the (long) contraction over the rows of a weight-gradient GEMM: the output has only a
 // few 128 x BN tiles, so K is cut into enough slices to put ~2 CTAs on every SM (slices are a
 // multiple of the 32-float stage and at least 256 long).
@@ -611,6 +623,24 @@ int linear_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, const fl
   gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
   return gemm_tc(gp, prec, st);
 }
+
+// a few independent y = act(x W^T + b) layers as ONE grouped launch
+struct LinearGroup {
+  bfvi::tc::GemmParams g[bfvi::tc::kMaxGroup];
+  int n = 0;
+  void add(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, float* y, int64_t ldy,
+           int64_t n_rows, int n_in, int n_out, int act) {
+    bfvi::tc::GemmParams& gp = g[n++];
+    memset(&gp, 0, sizeof(gp));
+    gp.A = x; gp.lda = ldx; gp.W = w; gp.ldw = ldw; gp.bias = bias; gp.C = y; gp.ldc = ldy;
+    gp.M = n_rows; gp.N = n_out; gp.K = n_in; gp.act = act;
+  }
+  int run(int prec, cudaStream_t st) {
+    const int rc = gemm_group_tc(g, n, prec, st);
+    n = 0;
+    return rc;
+  }
+};
 
 // ===========================================================================================
 // large-dim family: the whole MultiDMM.step + backward as a stream-ordered launch sequence of
@@ -827,6 +857,13 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   auto wgrad = [&](const float* dyT, const float* xT, int64_t rows, int n_out, int n_in, int64_t w_off) -> int {
     bfvi::tc::GemmParams gp;
     memset(&gp, 0, sizeof(gp));
+    if (wgrad_swapped(n_out, n_in)) {           // dW^T = X^T dY, added into dW transposed
+      gp.A = xT; gp.lda = rows; gp.W = dyT; gp.ldw = rows;
+      gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_in; gp.N = n_out; gp.K = rows; gp.accumulate = 1;
+      gp.trans_out = 1;
+      gp.k_split = wgrad_k_split(rows, n_in, n_out);
+      return gemm(gp);
+    }
     gp.A = dyT; gp.lda = rows; gp.W = xT; gp.ldw = rows;
     gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_out; gp.N = n_in; gp.K = rows; gp.accumulate = 1;
     gp.k_split = wgrad_k_split(rows, n_out, n_in);
@@ -1625,6 +1662,12 @@ int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
   if (lddy < n_rows || ldx < n_rows || lddw < n_in) return fail(BFVI_ERR_ARG, "leading dimension too small");
   bfvi::tc::GemmParams gp;
   memset(&gp, 0, sizeof(gp));
+  if (accumulate && wgrad_swapped(n_out, n_in)) {
+    gp.A = x; gp.lda = ldx; gp.W = dy; gp.ldw = lddy; gp.C = dw; gp.ldc = lddw;
+    gp.M = n_in; gp.N = n_out; gp.K = n_rows; gp.accumulate = 1; gp.trans_out = 1;
+    gp.k_split = wgrad_k_split(n_rows, n_in, n_out);
+    return gemm_tc(gp, (flags >> 4) & 1, (cudaStream_t)stream);
+  }
   gp.A = dy; gp.lda = lddy; gp.W = x; gp.ldw = ldx; gp.C = dw; gp.ldc = lddw;
   gp.M = n_out; gp.N = n_in; gp.K = n_rows; gp.accumulate = accumulate ? 1 : 0;
   if (accumulate) gp.k_split = wgrad_k_split(n_rows, n_out, n_in);
@@ -2026,7 +2069,7 @@ struct ForwardPlan {
   int n_present, k_max, d_max;
   size_t tb, tbz;
   size_t off_obs_mean, off_obs_std, off_obs_mask, off_x0, off_h, off_flt[4], off_samples;
-  size_t off_zrows, off_hrows, off_g, off_nl, off_lin, off_as;
+  size_t off_zrows, off_hrows, off_hrows2, off_g, off_nl, off_lin, off_as;
   size_t total;
 };
 
@@ -2061,6 +2104,7 @@ static int plan_forward(const bfvi_model* m, const bfvi_forward_args* a, Forward
   pl->off_samples = carve(sizeof(float) * pl->tbz);
   pl->off_zrows = carve(sizeof(float) * rows * m->z_dim);
   pl->off_hrows = carve(sizeof(float) * rows * m->h_dim);
+  pl->off_hrows2 = carve(sizeof(float) * rows * m->h_dim);
   pl->off_g = carve(sizeof(float) * rows * m->z_dim);
   pl->off_nl = carve(sizeof(float) * rows * m->z_dim);
   pl->off_lin = carve(sizeof(float) * rows * m->z_dim);
@@ -2099,6 +2143,8 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
   float* samples = (float*)(ws + pl.off_samples);
   float* zrows = (float*)(ws + pl.off_zrows);
   float* hrows = (float*)(ws + pl.off_hrows);
+  float* hrows2 = (float*)(ws + pl.off_hrows2);
+  LinearGroup lg;
   float* gbuf = (float*)(ws + pl.off_g);
   float* nlbuf = (float*)(ws + pl.off_nl);
   float* linbuf = (float*)(ws + pl.off_lin);
@@ -2116,8 +2162,9 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
     auto kp = bfvi::gen::prep_rows_kernel;
     BFVI_LAUNCH(kp, ew_grid(tb, 256), dim3(256), 0, st, a->inputs[i], tb, D, x0, obs_mask + (size_t)slot * pl.tb);
     if (int rc = linear_tc(x0, D, params + l.in_to_h_w, D, params + l.in_to_h_b, hbuf, H, tb, D, H, 1, prec, st)) return rc;
-    if (int rc = linear_tc(hbuf, H, params + l.mean_w, H, params + l.mean_b, mean, Z, tb, H, Z, 0, prec, st)) return rc;
-    if (int rc = linear_tc(hbuf, H, params + l.std_w, H, params + l.std_b, std, Z, tb, H, Z, 0, prec, st)) return rc;
+    lg.add(hbuf, H, params + l.mean_w, H, params + l.mean_b, mean, Z, tb, H, Z, 0);
+    lg.add(hbuf, H, params + l.std_w, H, params + l.std_b, std, Z, tb, H, Z, 0);
+    if (int rc = lg.run(prec, st)) return rc;
     auto ks = bfvi::gen::softplus_kernel;
     BFVI_LAUNCH(ks, ew_grid(tb * Z, 256), dim3(256), 0, st, std, tb * Z, bfvi::kMlpMinStd);
     ++slot;
@@ -2130,11 +2177,14 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
     const int64_t rows = (int64_t)B * f.n_particles;
     for (int i = 0; i < T; ++i) {
       if (i > 0) {
-        if (int rc = linear_tc(zrows, Z, params + g.gate0_w, Z, params + g.gate0_b, hrows, H, rows, Z, H, 1, prec, st)) return rc;
-        if (int rc = linear_tc(hrows, H, params + g.gate2_w, H, params + g.gate2_b, gbuf, Z, rows, H, Z, 0, prec, st)) return rc;
-        if (int rc = linear_tc(zrows, Z, params + g.nonlin0_w, Z, params + g.nonlin0_b, hrows, H, rows, Z, H, 1, prec, st)) return rc;
-        if (int rc = linear_tc(hrows, H, params + g.nonlin2_w, H, params + g.nonlin2_b, nlbuf, Z, rows, H, Z, 0, prec, st)) return rc;
-        if (int rc = linear_tc(zrows, Z, params + g.lin_w, Z, params + g.lin_b, linbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
+        // three grouped launches: the layers that read the particles, the two hidden -> head layers, the std head
+        lg.add(zrows, Z, params + g.gate0_w, Z, params + g.gate0_b, hrows, H, rows, Z, H, 1);
+        lg.add(zrows, Z, params + g.nonlin0_w, Z, params + g.nonlin0_b, hrows2, H, rows, Z, H, 1);
+        lg.add(zrows, Z, params + g.lin_w, Z, params + g.lin_b, linbuf, Z, rows, Z, Z, 0);
+        if (int rc = lg.run(prec, st)) return rc;
+        lg.add(hrows, H, params + g.gate2_w, H, params + g.gate2_b, gbuf, Z, rows, H, Z, 0);
+        lg.add(hrows2, H, params + g.nonlin2_w, H, params + g.nonlin2_b, nlbuf, Z, rows, H, Z, 0);
+        if (int rc = lg.run(prec, st)) return rc;
         if (int rc = linear_tc(nlbuf, Z, params + g.std_w, Z, params + g.std_b, asbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
       }
       bfvi::gen::StepParams sp;
@@ -2209,8 +2259,9 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
     const bfvi_mlp_layout& l = lay.dec[i];
     const int D = m->dims[i];
     if (int rc = linear_tc(samples, Z, params + l.in_to_h_w, Z, params + l.in_to_h_b, hbuf, H, tb, Z, H, 1, prec, st)) return rc;
-    if (int rc = linear_tc(hbuf, H, params + l.mean_w, H, params + l.mean_b, a->recon_mean[i], D, tb, H, D, 0, prec, st)) return rc;
-    if (int rc = linear_tc(hbuf, H, params + l.std_w, H, params + l.std_b, a->recon_std[i], D, tb, H, D, 0, prec, st)) return rc;
+    lg.add(hbuf, H, params + l.mean_w, H, params + l.mean_b, a->recon_mean[i], D, tb, H, D, 0);
+    lg.add(hbuf, H, params + l.std_w, H, params + l.std_b, a->recon_std[i], D, tb, H, D, 0);
+    if (int rc = lg.run(prec, st)) return rc;
     auto ks = bfvi::gen::softplus_kernel;
     BFVI_LAUNCH(ks, ew_grid(tb * D, 256), dim3(256), 0, st, a->recon_std[i], tb * D, bfvi::kMlpMinStd);
   }

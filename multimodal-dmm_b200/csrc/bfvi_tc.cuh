@@ -10,18 +10,22 @@
 // a time step (models/common.py:62-68) — run through it.
 //
 // Precision: kind::tf32 with an FP32 accumulator in TMEM.  Operands are rounded to TF32
-// with round-to-nearest (cvt.rna) while they are staged into shared memory; letting the
+// with round-to-nearest while they are staged into shared memory; letting the
 // MMA truncate raw FP32 bits would bias every product low by ~2^-11 and break the 1e-4
 // ELBO tolerance (rounded TF32 meets 1e-4 / 1e-3, plain BF16 does not).
 //
-// Data path of one CTA (128 threads, one 128 x BN output tile, cta_group::1):
-//   global --ld.global.v4--> registers --cvt.rna.tf32--> shared memory in the canonical
-//   K-major no-swizzle UMMA layout, double buffered over K chunks of 32 floats;
-//   one elected thread issues tcgen05.mma (M=128, N=BN, K=8 per instruction) and
-//   tcgen05.commit to an mbarrier per stage; the accumulator is read back with
-//   tcgen05.ld (32 lanes x 32 columns per warp) for the epilogue.
+// Two kernels live here:
+//  * gemm_tf32_kernel (round-1, BFVI_GEMM_V1=1): one 128 x BN tile per 128-thread CTA, operands staged
+//    ld.global -> cvt.rna -> st.shared in the canonical no-swizzle K-major UMMA layout, double buffered.
+//    Kept as the measured baseline of tools/time_gemm.py.
+//  * gemm_tf32_p_kernel (the product): persistent, grouped (several independent GEMMs per launch),
+//    warp-specialised — 8 converter warps (cp.async ring + rounding), 1 MMA warp, 8 epilogue warps —
+//    SWIZZLE_128B operand tiles, up to 8 accumulators in TMEM.  See the banner above it.
 //
-// Shared-memory operand layout: element (row r, float k) of a [ROWS x 32] chunk lives at
+// Both: tcgen05.mma cta_group::1, M = 128, N = BN, K = 8 per instruction, issued by one elected
+// thread; tcgen05.commit to mbarriers; accumulators read back with tcgen05.ld (32 lanes x 32 columns).
+//
+// Round-1 kernel's shared-memory operand layout: element (row r, float k) of a [ROWS x 32] chunk lives at
 // byte (k/4) * ROWS*16 + r*16 + (k%4)*4 — an array [k/4][r] of 16-byte vectors.  In UMMA
 // terms: 8-row x 16-byte core matrices, contiguous along rows (SBO = 128 B), K chunks
 // ROWS*16 B apart (LBO).  A warp storing 32 consecutive rows writes 512 contiguous bytes.
@@ -57,6 +61,9 @@ struct GemmParams {
   const float* mask_aux;            // epilogue: result *= (mask_aux[m][n] > 0)  (ReLU backward), nullable
   int64_t ldaux;
   float* colsum;                    // epilogue: colsum[n] += sum_m result[m][n] (bias gradients), nullable
+  int trans_out;                    // 1: ADD the product into C TRANSPOSED, C[n * ldc + m] += result[m][n] (atomics; no
+                                    // bias / activation / mask).  Weight gradients with few outputs and many inputs
+                                    // run as dW^T = X^T dY: the long side fills the 128 MMA rows instead of padding them
 };
 enum { PREC_TF32X3 = 0, PREC_TF32 = 1 };   // operand precision of the large-dim family
 
@@ -317,24 +324,22 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(const __grid_consta
 }
 
 // =====================================================================================
-// v2 of the tile kernel (the default): same contract and epilogue options as
-// gemm_tf32_kernel above, rebuilt around what the launch list of a C3-dims step showed
-// (profiles/r1_c3_launches_before.csv): 2.8 us per 32-float K chunk on the latency-bound
-// single-particle GEMMs and 13x the HBM time on the 57 600-row particle GEMMs, where the
-// row-per-thread epilogue wrote 32 different lines per store instruction.
+// Building blocks of the product tile kernel (gemm_tf32_p_kernel below).  It was rebuilt
+// around what the launch list and ncu captures of a C3-dims step showed for the round-1
+// kernel above (profiles/r1_c3_launches_before.csv, r1_gemm_tf32_full.txt): 2.8 us per
+// 32-float K chunk on the latency-bound single-particle GEMMs, 13x the HBM time on the
+// 57 600-row particle GEMMs, and 4 warps per SM that were issue-bound on an emulated cvt.rna.
 //
 //  * operands travel global -> shared memory with 16-byte cp.async (LDGSTS, zero-filling
-//    out-of-range rows / the K tail) into a ring of 2-4 stages, so 1-3 chunks are in flight
-//    while the current one is converted and multiplied;
+//    out-of-range rows / the K tail) into a ring of 2-4 stages;
 //  * shared-memory operand layout: K-major SWIZZLE_128B (a row's 32-float chunk is one
 //    128-byte line whose 16-byte vectors are XOR-permuted by row % 8; 8-row groups 1024 B
 //    apart) — eight lanes fetch one full global line and store one full shared line;
-//  * each thread rounds ITS vectors in place (hi = cvt.rna.tf32, lo = rna(x - hi) into the
-//    twin tile), so no barrier is needed between the copy and the conversion;
-//  * epilogue through a padded 32x33 shared patch per warp: TMEM rows -> patch, then
-//    lane = column: bias / ReLU / ReLU-mask / accumulate / split-K atomics / column sums
-//    all touch global memory as full 128-byte lines; the transposed copy leaves with
-//    lane = row, also as full lines.
+//  * each thread rounds ITS vectors in place (hi = cvt.rn.tf32, one F2FP instruction; lo = x - hi
+//    into the twin tile), so no barrier is needed between the copy and the conversion;
+//  * epilogue per 32 x 32 accumulator block: bias / ReLU / ReLU-mask / accumulate / column sums /
+//    split-K atomics / transposed copy, 128-bit row segments on the aligned path, a padded shared
+//    patch (rows -> columns) wherever a full-line access pattern needs the transposition.
 // =====================================================================================
 constexpr int kRowBytes = kBK * 4;            // 128 B: one swizzle-128B line per operand row and chunk
 constexpr int kMaxStages = 4;
@@ -354,56 +359,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// ---- per-thread view of one operand: the thread owns vectors (row r0 + 32 i, 16-byte column c4)
-// of every K chunk, with r0 = tid >> 3, c4 = tid & 7; (r & 7) does not depend on i, so the swizzled
-// offset is off0 + i * 32 rows.  Eight lanes cover one 128-byte global line and one shared line.
-constexpr int kThreadsV2 = 256;
-struct OperandView {
-  const float* src;        // &P[row0 + r0][k_begin + 4 c4]  (dereferenced only where valid)
-  const float* base;       // P (dummy source of zero-filled vectors)
-  int64_t row_step;        // 32 * ld
-  int valid;               // rows of this tile inside the matrix, minus r0: vector i is valid iff 32 i < valid
-  uint32_t off0;           // swizzled byte offset of vector (r0, c4)
-  bool vec;                // 16-byte aligned rows
-};
-__device__ __forceinline__ OperandView make_view(const float* P, int64_t ld, int64_t row0, int64_t n_rows, int tile_rows,
-                                                 int64_t k_begin) {
-  OperandView v;
-  const int r0 = threadIdx.x >> 3, c4 = threadIdx.x & 7;
-  v.src = P + (row0 + r0) * ld + k_begin + c4 * 4;
-  v.base = P;
-  v.row_step = 32 * ld;
-  const int64_t in = n_rows - row0 < tile_rows ? n_rows - row0 : tile_rows;
-  v.valid = (int)in - r0;
-  v.off0 = (uint32_t)(r0 * kRowBytes + ((c4 ^ (r0 & 7)) << 4));
-  v.vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P) & 15) == 0);
-  return v;
-}
-// asynchronous copy of K chunk `chunk` ([ROWS x 32] floats) into the swizzled tile at shared address `tile`
-// VEC: rows are 16-byte aligned (one LDGSTS.128 per vector), else four 4-byte copies
-template <int ROWS, bool VEC>
-__device__ __forceinline__ void load_tile_async(uint32_t tile, const OperandView& v, int chunk, int64_t k_left0) {
-  // k_left0 = floats between this thread's column of chunk 0 and the end of the contraction
-  const int64_t left = k_left0 - (int64_t)chunk * kBK;
-  const int kbytes = left >= 4 ? 16 : left > 0 ? (int)left * 4 : 0;
-  const float* src = v.src + (int64_t)chunk * kBK;
-  uint32_t dst = tile + v.off0;
-#pragma unroll
-  for (int i = 0; i < ROWS / 32; ++i) {
-    const bool in = 32 * i < v.valid && kbytes > 0;
-    if (VEC) {
-      cp_async16(dst, in ? src : v.base, in ? kbytes : 0);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool ine = in && e * 4 < kbytes;
-        cp_async4(dst + e * 4, ine ? src + e : v.base, ine ? 4 : 0);
-      }
-    }
-    src += v.row_step;
-    dst += 32 * kRowBytes;
-  }
-}
+constexpr int kThreadsV2 = 256;        // converter threads of the tile kernel
 // Operand preparation by the thread that copied the vectors (no barrier in between):
 // hi = rn_tf32(x) in place (round-to-nearest-even, ONE F2FP.TF32.F32 instruction on sm_100; cvt.rna is a
 // four-instruction emulation, and this pass is issue-bound); for 3xTF32 the twin tile gets lo = x - hi,
@@ -449,6 +405,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
 constexpr int kPatchLd = 33;      // floats per patch row (conflict-free row <-> column transposition)
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, float (&v)[32], float* patch, int64_t wrow0,
                                                int rows_valid, int cbase, int lane, bool fast_c) {
+  if (p.trans_out) {                           // lane = row: consecutive lanes add into consecutive addresses
+    if (lane < rows_valid) {
+      float* dt = p.C + (int64_t)cbase * p.ldc + wrow0 + lane;
+      const int cols_valid = p.N - cbase < 32 ? p.N - cbase : 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cols_valid) atomicAdd(dt + (int64_t)j * p.ldc, v[j]);
+    }
+    return;
+  }
   if (fast_c && cbase + 32 <= p.N) {
     const int64_t row = wrow0 + lane;
     const bool row_ok = lane < rows_valid;
@@ -835,6 +801,7 @@ inline void gemm_reference_emu(const GemmParams& p) {
       acc += p.bias ? p.bias[n] : 0.f;
       if (p.act == ACT_RELU) acc = acc < 0.f ? 0.f : acc;
       if (p.mask_aux != nullptr) acc = p.mask_aux[m * p.ldaux + n] > 0.f ? acc : 0.f;
+      if (p.trans_out) { p.C[(int64_t)n * p.ldc + m] += acc; continue; }
       cs += acc;
       acc = p.accumulate ? p.C[m * p.ldc + n] + acc : acc;
       p.C[m * p.ldc + n] = acc;
