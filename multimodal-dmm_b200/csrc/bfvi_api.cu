@@ -554,10 +554,26 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
     if (stages > bfvi::tc::kMaxStages) stages = bfvi::tc::kMaxStages;
     if (stages > cap) stages = cap;
     if (stages < 2) stages = 2;
+    const int slots = (num_sms() > 0 ? num_sms() : 1) * (ctas_per_sm > 1 ? 2 : 1);
+    static const bool a_in_tmem = [] { const char* e = getenv("BFVI_GEMM_TS"); return !e || atoi(e) != 0; }();
+    static const int ts_cap = [] { const char* e = getenv("BFVI_GEMM_TS_STAGES"); return e ? atoi(e) : 8; }();
+    if constexpr (BN <= 128 && SPLIT) {
+      if (a_in_tmem && vec) {        // A operand from tensor memory (aligned 3xTF32 problems)
+        int ts_stages = (int)(budget / bfvi::tc::gemm_ts_stage_bytes<BN, SPLIT>());
+        if (ts_stages > bfvi::tc::ts_max_stages(BN)) ts_stages = bfvi::tc::ts_max_stages(BN);
+        if (ts_stages > ts_cap) ts_stages = ts_cap;
+        if (ts_stages < 2) ts_stages = 2;
+        const size_t smem_ts = bfvi::tc::gemm_ts_smem_bytes<BN, SPLIT>(ts_stages);
+        auto kt = bfvi::tc::gemm_tf32_ts_kernel<BN, SPLIT, true>;
+        cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
+        kt<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem_ts, st>>>(grp, ts_stages);
+        BFVI_CHECK_CUDA();
+        return BFVI_OK;
+      }
+    }
     const size_t smem = bfvi::tc::gemm_p_smem_bytes<BN, SPLIT>(stages);
     auto k = vec ? bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, true> : bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int slots = (num_sms() > 0 ? num_sms() : 1) * (ctas_per_sm > 1 ? 2 : 1);
     k<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem, st>>>(grp, stages);
   }
 #endif

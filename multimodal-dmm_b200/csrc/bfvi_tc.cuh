@@ -389,6 +389,30 @@ struct TileCfg {
   static_assert(BN % 32 == 0, "tile width");
   };
 
+// 32 lanes x 16 consecutive fp32 columns, registers -> TMEM: thread (lane) writes its row's 16 values
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 lanes x 8 columns of tf32 per instruction) from tensor memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+// the mbarrier receives one arrival when all cp.async of this thread issued so far have landed
+__device__ __forceinline__ void cp_async_arrive(uint64_t* mbar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
 }
@@ -788,6 +812,259 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, kCols);
 }
+__host__ __device__ constexpr int ts_max_stages(int bn) { return bn <= 64 ? 6 : 4; }
+// A-from-TMEM variant of the tile kernel: the tile kernel above is bound by the SM's shared-memory pipe
+// (DESIGN.md 4b); here the rounded A chunk never returns to shared memory — converter warps 0-3 (thread =
+// row) read the raw chunk once, round it and tcgen05.st hi / lo into a TMEM ring beside the accumulators, and
+// the MMAs take A from tensor memory (tcgen05.mma [d], [a], b_desc): per job and BN = 128, 144 KB of
+// shared-memory traffic instead of 224 KB.  Copies are tracked by an mbarrier (cp.async.mbarrier.arrive), so
+// the copying and the converting thread of a vector need not be the same; warps 4-7 round W in place.
+template <int BN, bool SPLIT, bool VEC>
+__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid_constant__ GemmGroup grp, int n_stages) {
+  using Cfg = TileCfg<BN, SPLIT>;
+  static_assert(BN <= 128, "A ring + accumulators must fit in 512 TMEM columns");
+  constexpr int kStageTs = Cfg::kABytes + (SPLIT ? 2 : 1) * Cfg::kWBytes;      // raw A | W hi | W lo
+  extern __shared__ unsigned char tc_smem_dyn[];
+  // TMEM budget (512 columns): BN = 128: 2 accumulators + a 4-stage A ring (64 columns per stage: hi | lo);
+  // BN <= 64: 128 columns of accumulators + a 6-stage ring — the narrow-output GEMMs stream their A operand
+  // from HBM and want the bytes in flight (4 jobs x 32 KB per SM with lag 2)
+  constexpr int kTsStages = ts_max_stages(BN);
+  constexpr uint32_t kARing = BN <= 64 ? 128 : 256;        // first column of the A ring
+  __shared__ __align__(8) uint64_t landed_bar[kTsStages];
+  __shared__ __align__(8) uint64_t full_bar[kTsStages];
+  __shared__ __align__(8) uint64_t empty_bar[kTsStages];
+  // accumulators in TMEM: as many as fit in its 512 columns (up to 8), so the MMA issuer can run that many
+  // tiles ahead of the epilogue (with two, short-K tiles serialised: copies + MMAs + stores ADDED up)
+  constexpr int kAcc = (int)kARing / BN;
+  __shared__ __align__(8) uint64_t tfull_bar[kAcc];
+  __shared__ __align__(8) uint64_t tempty_bar[kAcc];
+  __shared__ uint32_t tmem_base_s;
+  unsigned char* smem = tc_smem_dyn + ((1024u - (smem_u32(tc_smem_dyn) & 1023u)) & 1023u);
+  auto tileA = [&](int s) { return smem + (size_t)s * kStageTs; };
+  auto tileW = [&](int s) { return tileA(s) + Cfg::kABytes; };
+  auto tileWl = [&](int s) { return tileW(s) + Cfg::kWBytes; };
+  float* patches = reinterpret_cast<float*>(smem + (size_t)n_stages * kStageTs);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t kCols = 512;
+  constexpr int kMmaWarp = kThreadsV2 / 32;
+
+  if (warp == kMmaWarp) tmem_alloc(&tmem_base_s, kCols);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTsStages; ++s) {
+      mbar_init(&landed_bar[s], kThreadsV2); mbar_init(&full_bar[s], kThreadsV2 / 32); mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < kAcc; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = ((int)blockIdx.x < grp.total) ? (grp.total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp < kMmaWarp) {
+    // ================= converters: copy + round, one "job" = one K chunk of one tile =================
+    // Thread t owns the 16-byte vectors (row r0 + 32 i, column c4) of every chunk, r0 = t >> 3, c4 = t & 7.
+    // Per-tile state of the load cursor is precomputed so that an interior job costs two pointer bumps
+    // and six LDGSTS (the pass is issue-bound: profiles/r1_gemm_p_full.txt).
+    const int r0 = threadIdx.x >> 3, c4 = threadIdx.x & 7;
+    const uint32_t off0 = (uint32_t)(r0 * kRowBytes + ((c4 ^ (r0 & 7)) << 4));
+    const uint32_t ring0 = smem_u32(smem) + off0;
+    constexpr int kVA = kBM / 32, kVW = BN / 32;          // vectors per thread and chunk: A, W
+    const float* a_ptr = nullptr; const float* w_ptr = nullptr;
+    const float* a_base = nullptr; const float* w_base = nullptr;
+    int64_t a_step = 0, w_step = 0;
+    int na = 0, nw = 0;                                   // valid vectors (rows inside the matrix)
+    int64_t k_left = 0;                                   // floats from this thread's column to the end of K
+    int l_tile = -1, l_chunk = 0, l_chunks = 0;           // load cursor: next job to copy
+    int c_tile = 0, c_chunk = 0, c_chunks = 0;            // convert cursor
+    auto load_more = [&]() { return l_chunk < l_chunks || l_tile + 1 < my_tiles; };
+    auto issue_next_load = [&](int s) {                   // copies the job under the load cursor into stage s
+      if (l_chunk == l_chunks) {
+        l_chunk = 0; ++l_tile;
+        const TileInfo ti = decode_tile(grp, (int)blockIdx.x + l_tile * (int)gridDim.x, BN);
+        const GemmParams& q = grp.g[ti.pi];
+        l_chunks = ti.chunks;
+        a_base = q.A; w_base = q.W;
+        a_ptr = q.A + (ti.row0 + r0) * q.lda + ti.k_begin + c4 * 4;
+        w_ptr = q.W + ((int64_t)ti.col0 + r0) * q.ldw + ti.k_begin + c4 * 4;
+        a_step = 32 * q.lda; w_step = 32 * q.ldw;
+        const int64_t ra = q.M - ti.row0 - r0, rw = (int64_t)q.N - ti.col0 - r0;      // rows from r0 to the edge
+        na = ra <= 0 ? 0 : ra >= kBM ? kVA : (int)((ra + 31) / 32);
+        nw = rw <= 0 ? 0 : rw >= BN ? kVW : (int)((rw + 31) / 32);
+        if (na > kVA) na = kVA;
+        if (nw > kVW) nw = kVW;
+        k_left = ti.k_end - ti.k_begin - c4 * 4;
+      }
+      const uint32_t dst_a = ring0 + (uint32_t)s * kStageTs, dst_w = dst_a + Cfg::kABytes;
+      if (VEC && k_left >= 4 && na == kVA && nw == kVW) {            // interior job
+#pragma unroll
+        for (int i = 0; i < kVA; ++i) cp_async16(dst_a + i * (32 * kRowBytes), a_ptr + i * a_step, 16);
+#pragma unroll
+        for (int i = 0; i < kVW; ++i) cp_async16(dst_w + i * (32 * kRowBytes), w_ptr + i * w_step, 16);
+      } else {
+        const int kbytes = k_left >= 4 ? 16 : k_left > 0 ? (int)k_left * 4 : 0;
+#pragma unroll
+        for (int i = 0; i < kVA + kVW; ++i) {
+          const bool is_a = i < kVA;
+          const int ii = is_a ? i : i - kVA;
+          const bool in = ii < (is_a ? na : nw) && kbytes > 0;
+          const float* src = is_a ? a_ptr + ii * a_step : w_ptr + ii * w_step;
+          const float* dummy = is_a ? a_base : w_base;
+          const uint32_t dst = (is_a ? dst_a : dst_w) + ii * (32 * kRowBytes);
+          if (VEC) {
+            cp_async16(dst, in ? src : dummy, in ? kbytes : 0);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool ine = in && e * 4 < kbytes;
+              cp_async4(dst + e * 4, ine ? src + e : dummy, ine ? 4 : 0);
+            }
+          }
+        }
+      }
+      a_ptr += kBK; w_ptr += kBK; k_left -= kBK;
+      ++l_chunk;
+      cp_async_arrive(&landed_bar[s]);
+    };
+    // A stage is refilled `lag` jobs after the job that used it: with a 4-stage ring lag = 2, so the wait
+    // for that job's MMAs (hand-over latency MMA warp -> tensor pipe -> commit -> this warp, ~0.5 us) has a
+    // whole iteration of slack and two jobs stay in flight; shallower rings refill at once (lag 1).
+    const int lag = n_stages >= 4 ? 2 : 1;
+    for (int c = 0; c < n_stages - lag; ++c)              // prologue: jobs 0 .. n_stages-lag-1
+      if (load_more()) issue_next_load(c);
+    if (my_tiles > 0) c_chunks = tile_chunks(grp, (int)blockIdx.x);
+    int s = 0;
+    uint32_t round = 0;                                   // how many times the ring has wrapped (parity source)
+    int done = 0;                                         // jobs converted so far
+    const int wt = threadIdx.x - 128;                     // W converters: vectors (row (wt >> 3) + 16 i, column wt & 7)
+    const uint32_t woff0 = (uint32_t)((wt >> 3) * kRowBytes + (((wt & 7) ^ ((wt >> 3) & 7)) << 4));
+    while (c_tile < my_tiles) {
+      mbar_wait(&landed_bar[s], round & 1u);              // every thread's copies of this job have landed
+      if (warp < 4) {
+        // thread = row: read the raw chunk (8 swizzled 16-byte vectors), round, store hi | lo to the TMEM ring
+        const unsigned char* rowp = tileA(s) + threadIdx.x * kRowBytes;
+        const uint32_t tdst = tmem_base + ((uint32_t)(warp * 32) << 16) + kARing + (uint32_t)s * 64u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float hi[16], lo[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const int cc = h * 4 + c;
+            const float4 x = *reinterpret_cast<const float4*>(rowp + ((cc ^ (threadIdx.x & 7)) << 4));
+            hi[4 * c] = rn_tf32(x.x); hi[4 * c + 1] = rn_tf32(x.y); hi[4 * c + 2] = rn_tf32(x.z); hi[4 * c + 3] = rn_tf32(x.w);
+            lo[4 * c] = x.x - hi[4 * c]; lo[4 * c + 1] = x.y - hi[4 * c + 1];
+            lo[4 * c + 2] = x.z - hi[4 * c + 2]; lo[4 * c + 3] = x.w - hi[4 * c + 3];
+          }
+          tmem_st16(tdst + h * 16, hi);
+          if (SPLIT) tmem_st16(tdst + 32 + h * 16, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+      } else {
+#pragma unroll
+        for (int i = 0; i < BN / 16; ++i) {
+          const uint32_t off = woff0 + i * (16 * kRowBytes);
+          const float4 x = *reinterpret_cast<const float4*>(tileW(s) + off);
+          const float4 h = make_float4(rn_tf32(x.x), rn_tf32(x.y), rn_tf32(x.z), rn_tf32(x.w));
+          *reinterpret_cast<float4*>(tileW(s) + off) = h;
+          if (SPLIT) *reinterpret_cast<float4*>(tileWl(s) + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        fence_async_smem();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+      if (load_more()) {                                  // job done + n_stages - lag goes where job done - lag was
+        const int sp = s - lag < 0 ? s - lag + n_stages : s - lag;
+        if (done >= lag) mbar_wait(&empty_bar[sp], (s - lag < 0 ? round - 1u : round) & 1u);
+        issue_next_load(sp);
+      }
+      ++done;
+      if (++s == n_stages) { s = 0; ++round; }
+      if (++c_chunk == c_chunks) {
+        c_chunk = 0;
+        if (++c_tile < my_tiles) c_chunks = tile_chunks(grp, (int)blockIdx.x + c_tile * (int)gridDim.x);
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(kBM, BN);
+      int s = 0;
+      uint32_t round = 0;
+      for (int lt = 0; lt < my_tiles; ++lt) {
+        const int a = lt % kAcc;
+        const int chunks = tile_chunks(grp, (int)blockIdx.x + lt * (int)gridDim.x);
+        mbar_wait(&tempty_bar[a], (uint32_t)(((lt / kAcc) & 1) ^ 1));   // epilogue has drained accumulator a
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN);
+        for (int i = 0; i < chunks; ++i) {
+          mbar_wait(&full_bar[s], round & 1u);
+          tc_fence_after();
+          const uint32_t w0 = smem_u32(tileW(s)), wl0 = smem_u32(tileWl(s));
+          const uint32_t ah = tmem_base + kARing + (uint32_t)s * 64u, al = ah + 32u;
+#pragma unroll
+          for (int q = 0; q < kBK / 8; ++q) {
+            const uint64_t dw = umma_desc_sw128(w0 + q * 32);
+            umma_tf32_ts(tmem_acc, ah + q * 8, dw, idesc, (i > 0 || q > 0) ? 1u : 0u);
+            if (SPLIT) {
+              umma_tf32_ts(tmem_acc, al + q * 8, dw, idesc, 1u);
+              umma_tf32_ts(tmem_acc, ah + q * 8, umma_desc_sw128(wl0 + q * 32), idesc, 1u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+          if (++s == n_stages) { s = 0; ++round; }
+        }
+        umma_commit(&tfull_bar[a]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue warps: two per TMEM lane group 32 (warp % 4) .., alternating 32-column blocks
+    const int wq = warp & 3, half = (warp - kMmaWarp - 1) >> 2;
+    float* patch = patches + (warp - kMmaWarp - 1) * (32 * kPatchLd);
+    for (int lt = 0; lt < my_tiles; ++lt) {
+      const int a = lt % kAcc;
+      const TileInfo ti = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN);
+      const GemmParams& p = grp.g[ti.pi];
+      const bool fast_c = VEC && epilogue_fast_ok(p);
+      const int64_t wrow0 = ti.row0 + wq * 32;
+      const int rows_valid = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+      const int limit = p.N - ti.col0 < BN ? p.N - ti.col0 : BN;      // valid columns of this tile
+      mbar_wait(&tfull_bar[a], (uint32_t)((lt / kAcc) & 1));
+      tc_fence_after();
+      bool released = false;
+#pragma unroll 1
+      for (int c = half * 32; c < limit; c += 64) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * BN + c), v);
+        if (c + 64 >= limit) {                            // this warp's last block: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[a]);
+          released = true;
+        }
+#ifndef BFVI_DBG_NO_EPI_STORE
+        epilogue_block(p, v, patch, wrow0, rows_valid, ti.col0 + c, lane, fast_c);
+#else
+        if (v[0] == 123.456f) patch[lane] = v[1];
+#endif
+      }
+      if (!released) {                                    // no block for this warp in a narrow tile
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[a]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kCols);
+}
 #endif  // !BFVI_EMU
 
 // CPU stand-in used only by the SIMT-emulator test build (exact fp32, no TF32 rounding)
@@ -820,6 +1097,11 @@ inline size_t gemm_v2_stage_bytes() { return (size_t)(SPLIT ? 2 : 1) * (size_t)(
 template <int BN, bool SPLIT>
 inline size_t gemm_v2_smem_bytes(int stages) { return gemm_v2_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024; }
 // persistent kernel: ring + four epilogue patches
+// A-from-TMEM variant: raw A | W hi | W lo per stage
+template <int BN, bool SPLIT>
+inline size_t gemm_ts_stage_bytes() { return (size_t)(kBM + (SPLIT ? 2 : 1) * BN) * kBK * sizeof(float); }
+template <int BN, bool SPLIT>
+inline size_t gemm_ts_smem_bytes(int stages) { return gemm_ts_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024 + 8 * 32 * 33 * sizeof(float); }
 template <int BN, bool SPLIT>
 inline size_t gemm_p_smem_bytes(int stages) { return gemm_v2_smem_bytes<BN, SPLIT>(stages) + 8 * 32 * 33 * sizeof(float); }
 
