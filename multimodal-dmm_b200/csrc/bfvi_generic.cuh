@@ -270,45 +270,64 @@ __global__ void __launch_bounds__(128) bwd_head_kernel(const __grid_constant__ S
 // Thread = one latent component zi walking a chunk of rows (coalesced along zi); writes the
 // pre-activation gradients and their transposed copies, accumulates bias gradients.
 constexpr int kRowsPerBlock = 32;
-__global__ void __launch_bounds__(128) bwd_rows_kernel(const __grid_constant__ StepParams p) {
+constexpr int kRowsZ = 64;          // latent components per block of bwd_rows_kernel (blockDim.x)
+__global__ void __launch_bounds__(kRowsZ) bwd_rows_kernel(const __grid_constant__ StepParams p) {
+  // transposed copies leave through shared memory: tile[a][zi][(r ^ zi) & 31] is conflict-free for the
+  // writer (thread = zi, fixed r) and the reader (lane = r, fixed zi), and the reader stores 32 consecutive
+  // rows = one 128-byte line per instruction (a direct store is one 4-byte transaction per element)
+  __shared__ float tile[3][kRowsZ][kRowsPerBlock];
   const bfvi_filter_args& a = p.a;
   const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
-  const int zi = blockIdx.y * blockDim.x + threadIdx.x;
-  if (zi >= Z) return;
+  const int zi = blockIdx.y * kRowsZ + threadIdx.x;
+  const bool active = zi < Z;
   const int t = gen_pass_time(p.i, T, a.direction);
-  const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
-  const float inv_k = 1.f / (float)K;
-  float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
   const int64_t r0 = (int64_t)blockIdx.x * kRowsPerBlock;
   const int64_t r1 = r0 + kRowsPerBlock < p.R ? r0 + kRowsPerBlock : p.R;
-  for (int64_t r = r0; r < r1; ++r) {
-    const int64_t c = r / K;
-    const int s = (int)(c / B), b = (int)(c % B);
-    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
-    const float pm = a.prior_mean[o];
-    const float d_pm = p.d_pm[c * Z + zi], d_v = p.d_v[c * Z + zi];
-    const int64_t q = r * Z + zi;
-    const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q], as = p.as[q];
-    const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(as) + p.min_std;
-    float m_k, s_k, g_gm, g_gs, d_qm, d_qs;
-    poe2_forward(gm, gs, qm, qs, m_k, s_k);
-    const float d_mk = (d_pm + 2.f * d_v * (m_k - pm)) * inv_k;      // models/dgts.py:78-83
-    const float d_sk = 2.f * d_v * s_k * inv_k;
-    poe2_backward(gm, gs, qm, qs, m_k, s_k, d_mk, d_sk, g_gm, g_gs, d_qm, d_qs);
-    d_gm += g_gm; d_gs += g_gs;
-    const float d_as = d_qs * softplus_grad(as);
-    const float d_nl = d_qm * gate;
-    const float d_lin = d_qm - d_nl;                                   // d_qm * (1 - gate)
-    const float d_g = d_lin * gate * (nl - lin);                       // through the sigmoid
-    p.d_as[q] = d_as; p.d_g[q] = d_g; p.d_lin[q] = d_lin; p.d_nl[q] = d_nl;
-    const int64_t qt = (int64_t)zi * p.R + r;
-    p.d_asT[qt] = d_as; p.d_gT[qt] = d_g; p.d_linT[qt] = d_lin;
-    b_s += d_as; b_g += d_g; b_l += d_lin; b_n += d_nl;
+  if (active) {
+    const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
+    const float inv_k = 1.f / (float)K;
+    float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
+    for (int64_t r = r0; r < r1; ++r) {
+      const int64_t c = r / K;
+      const int s = (int)(c / B), b = (int)(c % B);
+      const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
+      const float pm = a.prior_mean[o];
+      const float d_pm = p.d_pm[c * Z + zi], d_v = p.d_v[c * Z + zi];
+      const int64_t q = r * Z + zi;
+      const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q], as = p.as[q];
+      const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(as) + p.min_std;
+      float m_k, s_k, g_gm, g_gs, d_qm, d_qs;
+      poe2_forward(gm, gs, qm, qs, m_k, s_k);
+      const float d_mk = (d_pm + 2.f * d_v * (m_k - pm)) * inv_k;      // models/dgts.py:78-83
+      const float d_sk = 2.f * d_v * s_k * inv_k;
+      poe2_backward(gm, gs, qm, qs, m_k, s_k, d_mk, d_sk, g_gm, g_gs, d_qm, d_qs);
+      d_gm += g_gm; d_gs += g_gs;
+      const float d_as = d_qs * softplus_grad(as);
+      const float d_nl = d_qm * gate;
+      const float d_lin = d_qm - d_nl;                                   // d_qm * (1 - gate)
+      const float d_g = d_lin * gate * (nl - lin);                       // through the sigmoid
+      p.d_as[q] = d_as; p.d_g[q] = d_g; p.d_lin[q] = d_lin; p.d_nl[q] = d_nl;
+      const int col = ((int)(r - r0) ^ (int)threadIdx.x) & (kRowsPerBlock - 1);
+      tile[0][threadIdx.x][col] = d_as; tile[1][threadIdx.x][col] = d_g; tile[2][threadIdx.x][col] = d_lin;
+      b_s += d_as; b_g += d_g; b_l += d_lin; b_n += d_nl;
+    }
+    atomicAdd(p.gb_std + zi, b_s); atomicAdd(p.gb_gate2 + zi, b_g);
+    atomicAdd(p.gb_lin + zi, b_l); atomicAdd(p.gb_nonlin2 + zi, b_n);
+    if (d_gm != 0.f) atomicAdd(p.g_z0_mean + zi, d_gm);
+    if (d_gs != 0.f) atomicAdd(p.g_z0_log_std + zi, d_gs * expf(p.z0_log_std[zi]));
   }
-  atomicAdd(p.gb_std + zi, b_s); atomicAdd(p.gb_gate2 + zi, b_g);
-  atomicAdd(p.gb_lin + zi, b_l); atomicAdd(p.gb_nonlin2 + zi, b_n);
-  if (d_gm != 0.f) atomicAdd(p.g_z0_mean + zi, d_gm);
-  if (d_gs != 0.f) atomicAdd(p.g_z0_log_std + zi, d_gs * expf(p.z0_log_std[zi]));
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = r0 + lane;
+  if (r < r1) {
+    for (int zl = warp; zl < kRowsZ; zl += kRowsZ / 32) {
+      const int zz = blockIdx.y * kRowsZ + zl;
+      if (zz >= Z) break;
+      const int col = (lane ^ zl) & (kRowsPerBlock - 1);
+      const int64_t qt = (int64_t)zz * p.R + r;
+      p.d_asT[qt] = tile[0][zl][col]; p.d_gT[qt] = tile[1][zl][col]; p.d_linT[qt] = tile[2][zl][col];
+    }
+  }
 }
 
 // backward of one step, part 3 — particles of the previous step back to its (mu, sd):
