@@ -1215,6 +1215,15 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     //      stream leaves idle.  BFVI_LARGE_SIDE=0 keeps everything on the caller's stream. ----
     static const bool want_side = [] { const char* e = getenv("BFVI_LARGE_SIDE"); return !e || atoi(e) != 0; }();
     SideStreams* side = (want_side && do_f && do_s && with_grad) ? side_streams() : nullptr;
+    // fork AFTER the particle pass forward (BFVI_LARGE_SIDE=2: before it): pass A then runs beside pass C — two
+    // latency-bound kernel sequences of <= 148 CTAs that share the SMs — instead of beside the 148-CTA
+    // persistent launches of pass B, whose statically assigned tiles a co-running kernel only delays
+    static const bool fork_early = [] { const char* e = getenv("BFVI_LARGE_SIDE"); return e && atoi(e) == 2; }();
+    bool b_fwd_done = false;
+    if (do_s && side && !fork_early) {
+      if (int rc = pass_fwd(fb, nullptr)) return rc;
+      b_fwd_done = true;
+    }
     if (do_f) {
       if (side) {
         if (int rc = flush()) return rc;
@@ -1237,7 +1246,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       }
     }
     if (do_s) {
-      if (int rc = pass_fwd(fb, nullptr)) return rc;
+      if (!b_fwd_done) { if (int rc = pass_fwd(fb, nullptr)) return rc; }
       if (int rc = pass_fwd(fc, with_grad ? F(pl.pc[5]) : nullptr)) return rc;
       if (int rc = decode_pass(1)) return rc;
     }
