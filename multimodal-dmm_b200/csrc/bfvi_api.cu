@@ -962,6 +962,18 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     sp.dz = F(pl.dz);
     return sp;
   };
+  // particles of step i_src as GEMM input rows (+ transposed copy)
+  auto sample_rows = [&](const bfvi::gen::StepParams& sp, int i_src, int64_t rows) {
+    const bool vec4 = Z % 4 == 0 && (((uintptr_t)sp.a.infer_mean | (uintptr_t)sp.a.infer_std | (uintptr_t)sp.zrows) & 15) == 0;
+    if (vec4) {
+      auto ks = bfvi::gen::sample_rows4_kernel;
+      BFVI_LAUNCH(ks, dim3((unsigned)((rows + 31) / 32), (unsigned)((Z + 63) / 64)), dim3(64), 0, st, sp, i_src);
+    } else {
+      auto ks = bfvi::gen::sample_rows_kernel;
+      BFVI_LAUNCH(ks, ew_grid(rows * Z, 256), dim3(256), 0, st, sp, i_src);
+    }
+    ++n_launch;
+  };
   auto pass_fwd = [&](const bfvi_filter_args& f, float* samplesT) -> int {
     const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
     const int64_t chains = (int64_t)f.S * B, rows = chains * f.n_particles;
@@ -987,9 +999,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       BFVI_LAUNCH(kh, ew_grid(chains * Z, 128), dim3(128), 0, st, sp);
       ++n_launch;
       if (i == 0) break;
-      auto ks = bfvi::gen::sample_rows_kernel;                 // particles of step i-1
-      BFVI_LAUNCH(ks, ew_grid(rows * Z, 256), dim3(256), 0, st, sp, i - 1);
-      ++n_launch;
+      sample_rows(sp, i - 1, rows);                            // particles of step i-1
       if (int rc = trans_fwd(g, rows, true)) return rc;
       auto kr = bfvi::gen::bwd_rows_kernel;
       BFVI_LAUNCH(kr, dim3((unsigned)((rows + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
@@ -1044,9 +1054,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
         sp.gb_std = grads + g.std_b; sp.gb_gate2 = grads + g.gate2_b;
         sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
       }
-      auto ks = bfvi::gen::sample_rows_kernel;
-      BFVI_LAUNCH(ks, ew_grid((int64_t)Km * Z, 256), dim3(256), 0, st, sp, 0);
-      ++n_launch;
+      sample_rows(sp, 0, Km);
       if (int rc = trans_fwd(g, Km, with_grad)) return rc;
       bfvi::gen::MatchHeadParams mh;
       memset(&mh, 0, sizeof(mh));

@@ -113,6 +113,64 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const __grid_constant_
   }
 }
 
+// Same as sample_rows_kernel for Z % 4 == 0: a thread owns FOUR consecutive components of a row — one
+// Philox call instead of four, 128-bit loads / stores — and the transposed copy leaves through a swizzled
+// shared tile as full 128-byte lines (a direct store is one 4-byte transaction per element).
+// Block = 64 threads = 16 component quads x 4 rows, walking kRowsPerBlock (32) rows.
+__global__ void __launch_bounds__(64) sample_rows4_kernel(const __grid_constant__ StepParams p, int i_src) {
+  __shared__ float tile[64][32];
+  const bfvi_filter_args& a = p.a;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
+  const int t = gen_pass_time(i_src, T, a.direction);
+  const bool sampled = gen_samples(a, i_src);
+  const int quad = threadIdx.x & 15, rsub = threadIdx.x >> 4;
+  const int zl = quad * 4;                                   // first component inside the block's 64
+  const int zi = blockIdx.y * 64 + zl;
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int64_t r1 = r0 + 32 < p.R ? r0 + 32 : p.R;
+  if (zi < Z) {
+#pragma unroll 2
+    for (int rr = 0; rr < 8; ++rr) {
+      const int rl = rr * 4 + rsub;
+      const int64_t r = r0 + rl;
+      if (r >= r1) break;
+      const int k = (int)(r % K);
+      const int64_t c = r / K;
+      const int s = (int)(c / B), b = (int)(c % B);
+      const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
+      const float4 mu = *reinterpret_cast<const float4*>(a.infer_mean + o);
+      float4 z = mu;
+      if (sampled) {
+        const float4 sd = *reinterpret_cast<const float4*>(a.infer_std + o);
+        float e[4];
+        if (a.noise.eps != nullptr) {
+          const float* ep = a.noise.eps + ((((int64_t)s * T + t) * B + b) * K + k) * Z + zi;
+          e[0] = ep[0]; e[1] = ep[1]; e[2] = ep[2]; e[3] = ep[3];
+        } else {
+          normal4(a.noise.seed, a.noise.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + a.noise.b_offset,
+                  (unsigned)k, (unsigned)(zi >> 2), e);
+        }
+        z.x = fmaf(e[0], sd.x, mu.x); z.y = fmaf(e[1], sd.y, mu.y);
+        z.z = fmaf(e[2], sd.z, mu.z); z.w = fmaf(e[3], sd.w, mu.w);
+      }
+      *reinterpret_cast<float4*>(p.zrows + r * Z + zi) = z;
+      tile[zl][(rl ^ zl) & 31] = z.x; tile[zl + 1][(rl ^ (zl + 1)) & 31] = z.y;
+      tile[zl + 2][(rl ^ (zl + 2)) & 31] = z.z; tile[zl + 3][(rl ^ (zl + 3)) & 31] = z.w;
+    }
+  }
+  if (p.zrowsT == nullptr) return;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = r0 + lane;
+  if (r < r1) {
+    for (int zz = warp; zz < 64; zz += 2) {
+      const int zg = blockIdx.y * 64 + zz;
+      if (zg >= Z) break;
+      p.zrowsT[(int64_t)zg * p.R + r] = tile[zz][(lane ^ zz) & 31];
+    }
+  }
+}
+
 // one filtering step for every (chain, zi)
 __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepParams p) {
   const bfvi_filter_args& a = p.a;
