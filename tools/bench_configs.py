@@ -44,14 +44,25 @@ def timed(fn, steps, warmup):
 
 
 def c3(args):
+    """Weak-scaling data parallelism under torchrun (one rank per GPU, B sequences per GPU, one NCCL
+    all-reduce of the flat gradient per step): python -m torch.distributed.run --nproc-per-node N
+    tools/bench_configs.py c3"""
     import bfvi_oracle as bo
+    import torch.distributed as dist
     M, D, Z, H, K, KM = 8, 16, 64, 512, 25, 50
     mods, dims = ['m%d' % i for i in range(M)], [D] * M
     T, B = args.T, args.batch
-    dev = torch.device('cuda:0')
+    world, rank, local = int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda:%d' % local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(1)
     model = models.MultiDMM(mods, dims, h_dim=H, z_dim=Z, device=dev).train()
-    g = torch.Generator(device='cuda').manual_seed(1234)
+    if world > 1:
+        model.b_offset = rank * B
+        model.grad_sync = lambda flat: dist.all_reduce(flat)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = {m: torch.randn(T, B, D, device=dev, generator=g) for m in mods}
     mask = torch.ones(T, B, 1, dtype=torch.bool, device=dev)
     lengths = [T] * B
@@ -63,8 +74,18 @@ def c3(args):
         (loss / (T * B)).backward()
         for p in model.parameters():
             p.grad = None
+    if world > 1:
+        dist.barrier()
     ms = timed(step, args.steps, 1)
-    flop = 216023040.0 * T * B                       # SURVEY.md §8d algorithmic FLOP per seq-timestep
+    if world > 1:                                    # max over ranks, whole-job throughput
+        tm = torch.tensor([ms], device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+        if rank != 0:
+            dist.destroy_process_group()
+            return
+    B_total = B * world
+    flop = 216023040.0 * T * B                       # SURVEY.md §8d algorithmic FLOP per seq-timestep (per GPU)
     pk = peaks()
     peak = float(pk.get('bf16_tflops_sustained', 1400.0))
     # CPU baseline: oracle port on a bounded sample of the same model
@@ -82,7 +103,8 @@ def c3(args):
     loss.backward()
     cpu_s = time.perf_counter() - t0
     print(json.dumps({
-        'metric': METRIC, 'value': T * B / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': 1,
+        'metric': METRIC, 'value': T * B_total / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': 1,
+        'scaling': 'weak',
         'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'tf32x3 (fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': 'C3 dims: M=8 D=16 Z=64 H=512 K=25 K_match=50, REDUCED to T=%d, B=%d per GPU '
                                '(BASELINE: T=1000, B=65536): large-dim tcgen05 launch-sequence family' % (T, B)},
@@ -92,6 +114,8 @@ def c3(args):
                      'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if pk else 'fallback'},
         'cpu_baseline': {'value': tc * bc / cpu_s, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': 'oracle port, one step + backward at B=%d, T=%d' % (bc, tc)}}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def c5(args):
