@@ -121,6 +121,9 @@ typedef struct bfvi_noise {
   uint64_t seed;
   uint32_t stream_id;
   uint32_t b_offset;  /* global batch index of local b = 0 (data-parallel shards) */
+  const uint64_t* seed_dev; /* nullable: device address the kernels read the Philox seed from at run time instead of
+                               `seed` — a captured CUDA graph of the step is replayed with a fresh seed per step
+                               (large-dim family only in this version) */
 } bfvi_noise;
 
 /* MultiDMM.z_filter (models/dmm.py:319-412) over S independent chain sets. */
@@ -176,6 +179,7 @@ typedef struct bfvi_step_args {
   uint32_t b_offset;                    /* see bfvi_noise */
   float match_count;                    /* mask.sum() used by the prior-matching term
                                            (models/dmm.py:541); < 0 = count seq_mask here */
+  const uint64_t* seed_dev;             /* nullable, see bfvi_noise.seed_dev (large-dim family) */
 } bfvi_step_args;
 
 int bfvi_version(void);

@@ -57,7 +57,7 @@ class Expert(C.Structure):
 
 class Noise(C.Structure):
     _fields_ = [('eps', C.c_void_p), ('seed', C.c_uint64), ('stream_id', C.c_uint32),
-                ('b_offset', C.c_uint32)]
+                ('b_offset', C.c_uint32), ('seed_dev', C.c_void_p)]
 
 
 class FilterArgs(C.Structure):
@@ -88,7 +88,8 @@ class StepArgs(C.Structure):
                 ('sample', C.c_int32), ('sample_init', C.c_int32),
                 ('eps_match', C.c_void_p), ('eps_filt', C.c_void_p),
                 ('eps_sflt', C.c_void_p), ('eps_ssmt', C.c_void_p),
-                ('seed', C.c_uint64), ('b_offset', C.c_uint32), ('match_count', C.c_float)]
+                ('seed', C.c_uint64), ('b_offset', C.c_uint32), ('match_count', C.c_float),
+                ('seed_dev', C.c_void_p)]
 
 
 class ForwardArgs(C.Structure):

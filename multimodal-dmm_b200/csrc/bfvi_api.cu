@@ -1046,7 +1046,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       memset(&f, 0, sizeof(f));
       f.T = 1; f.B = 1; f.S = 1; f.n_particles = Km; f.sample = 1; f.direction = BFVI_DIR_FWD;
       f.noise.eps = a->eps_match ? a->eps_match + (size_t)dir * Km * Z : nullptr;
-      f.noise.seed = a->seed; f.noise.stream_id = 100u + dir;
+      f.noise.seed = a->seed; f.noise.seed_dev = a->seed_dev; f.noise.stream_id = 100u + dir;
       f.infer_mean = zvec; f.infer_std = zvec + Z; f.prior_mean = zvec + 2 * Z; f.prior_std = zvec + 3 * Z;
       bfvi::gen::StepParams sp = step_params(f, 0);
       const bfvi_gtf_layout& g = lay.trans[dir];
@@ -1129,7 +1129,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       for (int i = 0; i < M; ++i) f.experts[i] = obs_expert(i);
       for (int s = 0; s < S; ++s) f.set_expert_bits[s] = pl.set_bits[s];
       f.sample = a->sample; f.sample_init = a->sample_init;
-      f.noise.seed = a->seed; f.noise.b_offset = a->b_offset;
+      f.noise.seed = a->seed; f.noise.seed_dev = a->seed_dev; f.noise.b_offset = a->b_offset;
       f.seq_mask = a->seq_mask;
       f.loss_acc = acc;
       return f;
@@ -1794,6 +1794,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     return step_large(m, params, grads, a, nullptr, false, workspace, workspace_bytes, loss_out, launches,
                       (cudaStream_t)stream);
   }
+  if (a->seed_dev != nullptr) return fail(BFVI_ERR_UNSUPPORTED, "seed_dev (graph-replayable seed) exists for the large-dim family only");
   const bool with_grad = grads != nullptr;
   StepPlan pl;
   plan_step(m, a, with_grad, &pl);

@@ -26,12 +26,16 @@
 namespace bfvi {
 namespace gen {
 
+// Philox seed of a pass: by value, or read from device memory (CUDA-graph replay, bfvi_noise.seed_dev)
+__device__ __forceinline__ uint64_t noise_seed(const bfvi_noise& nz) {
+  return nz.seed_dev != nullptr ? *nz.seed_dev : nz.seed;
+}
 // one N(0,1) draw, component zi of particle k (same stream as load_eps<Z>)
 __device__ __forceinline__ float eps_at(const bfvi_noise& nz, int s, int t, int b, int k, int zi, int T, int B,
                                         int K, int Z) {
   if (nz.eps != nullptr) return nz.eps[((((int64_t)s * T + t) * B + b) * K + k) * Z + zi];
   float n[4];
-  normal4(nz.seed, nz.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + nz.b_offset, (unsigned)k,
+  normal4(noise_seed(nz), nz.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + nz.b_offset, (unsigned)k,
           (unsigned)(zi >> 2), n);
   return n[zi & 3];
 }
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(64) sample_rows4_kernel(const __grid_constant_
           const float* ep = a.noise.eps + ((((int64_t)s * T + t) * B + b) * K + k) * Z + zi;
           e[0] = ep[0]; e[1] = ep[1]; e[2] = ep[2]; e[3] = ep[3];
         } else {
-          normal4(a.noise.seed, a.noise.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + a.noise.b_offset,
+          normal4(noise_seed(a.noise), a.noise.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + a.noise.b_offset,
                   (unsigned)k, (unsigned)(zi >> 2), e);
         }
         z.x = fmaf(e[0], sd.x, mu.x); z.y = fmaf(e[1], sd.y, mu.y);

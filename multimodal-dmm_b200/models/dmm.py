@@ -51,6 +51,11 @@ class _StepFn(torch.autograd.Function):
         lib = _lib.load()
         # grad mode is always off inside Function.forward: the caller decides
         need_grad = bool(args_need_grad(keep)) and any(p.requires_grad for p in params)
+        if (need_grad and getattr(model, 'cuda_graph', False) and model._family == 2
+                and not (args.eps_match or args.eps_filt or args.eps_sflt or args.eps_ssmt)):
+            loss, flat_grad = _graph_step(model, lib, args, keep[-1])
+            ctx.model, ctx.flat_grad = model, flat_grad
+            return loss
         flat_grad = torch.empty_like(model._flat) if need_grad else None
         loss = torch.empty((), dtype=torch.float32, device=model._flat.device)
         nbytes = C.c_size_t(0)
@@ -74,6 +79,68 @@ class _StepFn(torch.autograd.Function):
             model.grad_sync(flat_grad)
         model.last_flat_grad = flat_grad
         return (None, None, None) + model._views(flat_grad)
+
+
+def _graph_step(model, lib, args, tens):
+    """Large-dim family: the ~4 500 launches of one step are captured ONCE per (shape, multipliers)
+    in a CUDA graph over static input / output buffers and replayed per step; the Philox seed is read
+    from device memory (bfvi_step_args.seed_dev), so every replay draws fresh noise.  Same numbers as the
+    eager call (tests/test_gpu_large.py::test_cuda_graph_step_matches_eager)."""
+    n_mods = model._cmodel.n_mods
+    key = (args.T, args.B, tuple(args.rec_mults[i] for i in range(n_mods)), args.kld_mult, args.uni_loss,
+           args.f_mode, args.s_mode, args.f_mult, args.s_mult, args.match_mult, args.train_particles,
+           args.match_particles, args.sample, args.sample_init, args.b_offset, model._flat.data_ptr())
+    cache = model.__dict__.setdefault('_graphs', {})
+    ent = cache.get(key)
+    dev = model._flat.device
+    tb = args.T * args.B
+
+    if ent is None:
+        dims = [int(model._cmodel.dims[i]) for i in range(n_mods)]
+        ent = {'inputs': [torch.empty(tb * d, device=dev) for d in dims],
+               'targets': [torch.empty(tb * d, device=dev) for d in dims],
+               'mask': torch.empty(tb, dtype=torch.uint8, device=dev),
+               'seed': torch.zeros(1, dtype=torch.int64, device=dev),
+               'loss': torch.empty((), dtype=torch.float32, device=dev),
+               'grad': torch.empty_like(model._flat)}
+        a2 = _lib.StepArgs()
+        C.memmove(C.byref(a2), C.byref(args), C.sizeof(_lib.StepArgs))
+        for i in range(n_mods):
+            a2.inputs[i] = ent['inputs'][i].data_ptr()
+            a2.targets[i] = ent['targets'][i].data_ptr()
+        a2.seq_mask = ent['mask'].data_ptr()
+        a2.seed, a2.seed_dev = 0, ent['seed'].data_ptr()
+        nbytes = C.c_size_t(0)
+        lib.call('bfvi_step_workspace', C.byref(model._cmodel), C.byref(a2), C.byref(nbytes))
+        ent['ws'] = _aligned_empty(max(nbytes.value, 256), dev)
+        ent['args'], ent['launches'] = a2, C.c_int32(0)
+        ent['graph'] = None
+        cache[key] = ent
+    # stage this step's batch and seed into the static buffers (device-to-device, stream-ordered)
+    for i in range(n_mods):
+        ent['inputs'][i].copy_(tens['inputs'][i].reshape(-1))
+        ent['targets'][i].copy_(tens['targets'][i].reshape(-1))
+    ent['mask'].copy_(tens['mask'].reshape(-1))
+    ent['seed'].fill_(int(args.seed))
+
+    def call(stream):
+        lib.call('bfvi_step_fwd_bwd', C.byref(model._cmodel), _lib.ptr(model._flat), _lib.ptr(ent['grad']),
+                 C.byref(ent['args']), _lib.ptr(ent['ws']), C.c_size_t(ent['ws'].numel()), _lib.ptr(ent['loss']),
+                 C.byref(ent['launches']), stream)
+    if ent['graph'] is None:
+        call(_stream())                 # eager once: lazy initialisation (side streams, attributes) outside capture
+        model.last_launches = ent['launches'].value
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(graph, stream=cap):
+                call(_stream())
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        ent['graph'] = graph
+    else:
+        ent['graph'].replay()
+    return ent['loss'].clone(), ent['grad']
 
 
 class _OpFn(torch.autograd.Function):
@@ -585,13 +652,17 @@ class MultiDMM(MultiDGTS):
             keep.append(t)
             return t.data_ptr()
         a.T, a.B = t_max, b_dim
+        tens = {'inputs': [], 'targets': []}       # the tensors behind the pointers (CUDA-graph staging)
         for i, m in enumerate(self.modalities):
             a.inputs[i] = dev_f32(inputs[m])
+            tens['inputs'].append(keep[-1])
             a.targets[i] = dev_f32(targets[m]) if m in targets else a.inputs[i]
+            tens['targets'].append(keep[-1])
             mult = float(rec_mults.get(m, 1.0)) if m in targets else 0.0
             a.rec_mults[i] = mult
         mk = mask.reshape(t_max, b_dim).to(device=dev, dtype=torch.uint8).contiguous()
         keep.append(mk)
+        tens['mask'] = mk
         a.seq_mask = mk.data_ptr()
         a.kld_mult, a.uni_loss = float(kld_mult), int(bool(uni_loss))
         a.f_mode = _lib.MODE_CODES[kw.get('f_mode', 'bfilter')]
@@ -609,4 +680,5 @@ class MultiDMM(MultiDGTS):
                 t = noise[name].to(dev).contiguous().float()
                 keep.append(t)
                 setattr(a, field, t.data_ptr())
+        keep.append(tens)
         return _StepFn.apply(self, a, keep, *self._slot_params())

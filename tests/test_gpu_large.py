@@ -166,3 +166,45 @@ def test_python_api_trains_a_default_sized_model():
         opt.zero_grad()
         losses.append(loss.item())
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0], losses
+
+
+def test_cuda_graph_step_matches_eager():
+    """MultiDMM.step with model.cuda_graph = True (large-dim family): the captured graph of the
+    step, replayed with the seed read from device memory, gives the eager step's loss and
+    gradients for the same seed, and different ones for a different seed."""
+    dev = torch.device('cuda:0')
+    mods, dims = ['a', 'b', 'c'], [4, 6, 3]
+    torch.manual_seed(3)
+    m = models.MultiDMM(mods, dims, h_dim=48, z_dim=32, device=dev).train()
+    g = torch.Generator().manual_seed(5)
+    t_max, b_dim = 9, 7
+    x = {k: torch.randn(t_max, b_dim, d, generator=g).to(dev) for k, d in zip(mods, dims)}
+    x['b'][2:4, 1] = float('nan')
+    mask = torch.ones(t_max, b_dim, 1, dtype=torch.bool, device=dev)
+    rec = {k: 1.0 for k in mods}
+
+    def run(seed, batch):
+        m.noise_seed = seed
+        for p in m.parameters():
+            p.grad = None
+        loss = m.step(batch, mask, 1.0, rec, targets=batch, lengths=[t_max] * b_dim, train_particles=5,
+                      match_particles=10)
+        (loss / (t_max * b_dim)).backward()
+        return loss.item(), torch.cat([p.grad.reshape(-1) for p in m.parameters()]).clone()
+
+    m.cuda_graph = False
+    e1, ge1 = run(11, x)
+    e2, ge2 = run(12, x)
+    x2 = {k: v * 0.5 for k, v in x.items()}
+    e3, ge3 = run(12, x2)
+    m.cuda_graph = True
+    g1, gg1 = run(11, x)             # first call: eager + capture
+    g2, gg2 = run(12, x)             # replay, new seed
+    g3, gg3 = run(12, x2)            # replay, new batch staged into the static buffers
+    g1b, gg1b = run(11, x)           # replay, back to the first seed
+    assert '_graphs' in m.__dict__ and len(m._graphs) == 1
+    for (a, ga), (b, gb) in (((e1, ge1), (g1, gg1)), ((e2, ge2), (g2, gg2)), ((e3, ge3), (g3, gg3)),
+                             ((e1, ge1), (g1b, gg1b))):
+        assert abs(a - b) <= 1e-5 * abs(a), (a, b)
+        assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6 * ga.abs().max().item())
+    assert abs(e1 - e2) > 1e-6 * abs(e1)          # the seed matters

@@ -59,6 +59,7 @@ def c3(args):
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(1)
     model = models.MultiDMM(mods, dims, h_dim=H, z_dim=Z, device=dev).train()
+    model.cuda_graph = not args.eager     # replay the captured step (seed read from device memory)
     if world > 1:
         model.b_offset = rank * B
         model.grad_sync = lambda flat: dist.all_reduce(flat)
@@ -107,7 +108,8 @@ def c3(args):
         'scaling': 'weak',
         'ms_per_step': ms, 'higher_is_better': True, 'dtype': 'tf32x3 (fp32 accumulate)', 'data': 'synthetic',
         'config': {'workload': 'C3 dims: M=8 D=16 Z=64 H=512 K=25 K_match=50, REDUCED to T=%d, B=%d per GPU '
-                               '(BASELINE: T=1000, B=65536): large-dim tcgen05 launch-sequence family' % (T, B)},
+                               '(BASELINE: T=1000, B=65536): large-dim tcgen05 launch-sequence family, %s' % (
+                                   T, B, 'eager launches' if args.eager else 'CUDA-graph replay of the step')},
         'gpu_launches': model.last_launches * args.steps,
         'roofline': {'bound': 'tensor', 'achieved': flop / (ms * 1e-3) / 1e12, 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': flop / (ms * 1e-3) / 1e12 / peak, 'traffic': None,
@@ -165,5 +167,6 @@ if __name__ == '__main__':
     ap.add_argument('--T', type=int, default=100)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--quick', action='store_true')
+    ap.add_argument('--eager', action='store_true', help='c3: launch the step eagerly instead of replaying its CUDA graph')
     a = ap.parse_args()
     (c3 if a.which == 'c3' else c5)(a)

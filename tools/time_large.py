@@ -25,6 +25,7 @@ def main():
     ap.add_argument('--H', type=int, default=512)
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--fwd-only', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='capture the step in a CUDA graph and time replays')
     a = ap.parse_args()
     lib = _lib.load()
     mods, dims = ['m%d' % i for i in range(a.M)], [16] * a.M
@@ -46,14 +47,32 @@ def main():
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def step():
+        nonlocal st
         lib.call('bfvi_step_fwd_bwd', C.byref(model), _lib.ptr(flat), _lib.ptr(grads), C.byref(args),
                  _lib.ptr(ws), C.c_size_t(nbytes.value), _lib.ptr(loss), C.byref(launches), st)
     step()
     torch.cuda.synchronize()
+    if a.graph:                                   # the step is stream-ordered (side stream forked / joined by events)
+        cap = torch.cuda.Stream()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(cap):
+            st = C.c_void_p(cap.cuda_stream)
+            step()                                # warm-up on the capture stream
+            cap.synchronize()
+            with torch.cuda.graph(graph, stream=cap):
+                st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+                step()
+        eager_loss = loss.item()
+        run = graph.replay
+        run()
+        torch.cuda.synchronize()
+        print('graph replay loss %.3f (eager %.3f)' % (loss.item(), eager_loss))
+    else:
+        run = step
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        step()
+        run()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
