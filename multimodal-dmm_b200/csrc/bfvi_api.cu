@@ -1003,7 +1003,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       if (int rc = trans_fwd(g, rows, true)) return rc;
       auto kr = bfvi::gen::bwd_rows_kernel;
       BFVI_LAUNCH(kr, dim3((unsigned)((rows + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                           (unsigned)((Z + bfvi::gen::kRowsZ - 1) / bfvi::gen::kRowsZ)), dim3(bfvi::gen::kRowsZ), 0, st, sp);
+                           (unsigned)((Z + bfvi::gen::kRowsZ - 1) / bfvi::gen::kRowsZ)), dim3(bfvi::gen::kRowsZ, bfvi::gen::kRowsSplit), 0, st, sp);
       ++n_launch;
       if (int rc = trans_bwd(g, rows)) return rc;
       auto kc = bfvi::gen::bwd_carry_kernel;
@@ -1069,7 +1069,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       if (with_grad) {
         auto kr = bfvi::gen::bwd_rows_kernel;
         BFVI_LAUNCH(kr, dim3((unsigned)((Km + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                             (unsigned)((Z + bfvi::gen::kRowsZ - 1) / bfvi::gen::kRowsZ)), dim3(bfvi::gen::kRowsZ), 0, st, sp);
+                             (unsigned)((Z + bfvi::gen::kRowsZ - 1) / bfvi::gen::kRowsZ)), dim3(bfvi::gen::kRowsZ, bfvi::gen::kRowsSplit), 0, st, sp);
         ++n_launch;
         if (int rc = trans_bwd(g, Km)) return rc;
         auto kc = bfvi::gen::bwd_carry_kernel;

@@ -333,23 +333,30 @@ __global__ void __launch_bounds__(128) bwd_head_kernel(const __grid_constant__ S
 // pre-activation gradients and their transposed copies, accumulates bias gradients.
 constexpr int kRowsPerBlock = 32;
 constexpr int kRowsZ = 64;          // latent components per block of bwd_rows_kernel (blockDim.x)
-__global__ void __launch_bounds__(kRowsZ) bwd_rows_kernel(const __grid_constant__ StepParams p) {
+constexpr int kRowsSplit = 4;       // row groups per block (blockDim.y): 8 rows per thread instead of 32 — the
+                                    // single-particle passes launch only rows / 32 blocks and were latency-bound
+                                    // on the 32-row serial walk (35 us per launch for 2 304 rows)
+__global__ void __launch_bounds__(kRowsZ * kRowsSplit) bwd_rows_kernel(const __grid_constant__ StepParams p) {
   // transposed copies leave through shared memory: tile[a][zi][(r ^ zi) & 31] is conflict-free for the
   // writer (thread = zi, fixed r) and the reader (lane = r, fixed zi), and the reader stores 32 consecutive
   // rows = one 128-byte line per instruction (a direct store is one 4-byte transaction per element)
   __shared__ float tile[3][kRowsZ][kRowsPerBlock];
+  __shared__ float part[kRowsSplit][6][kRowsZ];
   const bfvi_filter_args& a = p.a;
   const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T;
-  const int zi = blockIdx.y * kRowsZ + threadIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int zi = blockIdx.y * kRowsZ + tx;
   const bool active = zi < Z;
   const int t = gen_pass_time(p.i, T, a.direction);
   const int64_t r0 = (int64_t)blockIdx.x * kRowsPerBlock;
   const int64_t r1 = r0 + kRowsPerBlock < p.R ? r0 + kRowsPerBlock : p.R;
+  constexpr int kPer = kRowsPerBlock / kRowsSplit;
+  float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
   if (active) {
     const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
     const float inv_k = 1.f / (float)K;
-    float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
+    const int64_t ra = r0 + ty * kPer, rb = ra + kPer < r1 ? ra + kPer : r1;
+    for (int64_t r = ra; r < rb; ++r) {
       const int64_t c = r / K;
       const int s = (int)(c / B), b = (int)(c % B);
       const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
@@ -369,20 +376,32 @@ __global__ void __launch_bounds__(kRowsZ) bwd_rows_kernel(const __grid_constant_
       const float d_lin = d_qm - d_nl;                                   // d_qm * (1 - gate)
       const float d_g = d_lin * gate * (nl - lin);                       // through the sigmoid
       p.d_as[q] = d_as; p.d_g[q] = d_g; p.d_lin[q] = d_lin; p.d_nl[q] = d_nl;
-      const int col = ((int)(r - r0) ^ (int)threadIdx.x) & (kRowsPerBlock - 1);
-      tile[0][threadIdx.x][col] = d_as; tile[1][threadIdx.x][col] = d_g; tile[2][threadIdx.x][col] = d_lin;
+      const int col = ((int)(r - r0) ^ tx) & (kRowsPerBlock - 1);
+      tile[0][tx][col] = d_as; tile[1][tx][col] = d_g; tile[2][tx][col] = d_lin;
       b_s += d_as; b_g += d_g; b_l += d_lin; b_n += d_nl;
     }
-    atomicAdd(p.gb_std + zi, b_s); atomicAdd(p.gb_gate2 + zi, b_g);
-    atomicAdd(p.gb_lin + zi, b_l); atomicAdd(p.gb_nonlin2 + zi, b_n);
-    if (d_gm != 0.f) atomicAdd(p.g_z0_mean + zi, d_gm);
-    if (d_gs != 0.f) atomicAdd(p.g_z0_log_std + zi, d_gs * expf(p.z0_log_std[zi]));
   }
+  part[ty][0][tx] = b_s; part[ty][1][tx] = b_g; part[ty][2][tx] = b_l; part[ty][3][tx] = b_n;
+  part[ty][4][tx] = d_gm; part[ty][5][tx] = d_gs;
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (active && ty == 0) {                       // one set of atomics per component and block
+    float v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      v[j] = 0.f;
+#pragma unroll
+      for (int g = 0; g < kRowsSplit; ++g) v[j] += part[g][j][tx];
+    }
+    atomicAdd(p.gb_std + zi, v[0]); atomicAdd(p.gb_gate2 + zi, v[1]);
+    atomicAdd(p.gb_lin + zi, v[2]); atomicAdd(p.gb_nonlin2 + zi, v[3]);
+    if (v[4] != 0.f) atomicAdd(p.g_z0_mean + zi, v[4]);
+    if (v[5] != 0.f) atomicAdd(p.g_z0_log_std + zi, v[5] * expf(p.z0_log_std[zi]));
+  }
+  const int tid = ty * kRowsZ + tx;
+  const int lane = tid & 31, warp = tid >> 5;
   const int64_t r = r0 + lane;
   if (r < r1) {
-    for (int zl = warp; zl < kRowsZ; zl += kRowsZ / 32) {
+    for (int zl = warp; zl < kRowsZ; zl += kRowsZ * kRowsSplit / 32) {
       const int zz = blockIdx.y * kRowsZ + zl;
       if (zz >= Z) break;
       const int col = (lane ^ zl) & (kRowsPerBlock - 1);
