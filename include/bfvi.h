@@ -277,6 +277,23 @@ int bfvi_len_to_mask(const int32_t* lengths, int32_t T, int32_t B, uint8_t* mask
 int bfvi_pad_merge(const float* packed, const int64_t* row_start, int32_t T, int32_t B,
                    int64_t D, float* out, void* stream);
 
+/* seq_decoll (datasets/multiseq.py:388-398): de-pad and reorder a (T, B, D) batch.  Output sequence j is
+ * batch column src[j], its first (row_start[j+1] - row_start[j]) steps, written at packed row row_start[j];
+ * row_start has n_out + 1 entries, total_rows = row_start[n_out] (all device pointers). */
+int bfvi_unpad(const float* x, const int64_t* row_start, const int32_t* src, int32_t B, int32_t n_out,
+               int64_t total_rows, int64_t D, float* packed, void* stream);
+
+/* Per-sequence MSE of the evaluation metrics (spirals.py:105-111): out[b] = sum over unmasked t of
+ * sum_m sum_d (recon_m - target_m)^2, divided by lengths[b].  recon / target: HOST arrays of n_mods device
+ * pointers to (T, B, dims[m]) tensors; mask (T, B) uint8, lengths (B) float, out (B): device.
+ * n_split > 1 cuts the time axis into that many slices per sequence (more blocks for few, long sequences;
+ * bfvi_seq_mse_splits proposes a count) and needs scratch = B * n_split floats; the two-stage sum is
+ * deterministic. */
+int bfvi_seq_mse_splits(int32_t T, int32_t B);
+int bfvi_seq_mse(const float* const* recon, const float* const* target, const int64_t* dims, int32_t n_mods,
+                 const uint8_t* mask, const float* lengths, int32_t T, int32_t B, float* out, float* scratch,
+                 int32_t n_split, void* stream);
+
 /* func_delete (datasets/multiseq.py:405-420): out = copy of x with rows (t, b) set to NaN.
  * _rows: explicit (T, B) flags (any del_func; the host replays the reference's numpy draws).
  * _spans: rows lo[b] <= t < hi[b] (burst_delete :428-434, del_segment :443-448), or with

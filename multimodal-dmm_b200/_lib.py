@@ -140,6 +140,12 @@ SYMBOLS = {
     'bfvi_nll_categorical_bwd': (C.c_int, [C.c_void_p] * 3 + [C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_void_p]),
     'bfvi_len_to_mask': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'bfvi_pad_merge': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
+    'bfvi_unpad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                             C.c_void_p]),
+    'bfvi_seq_mse_splits': (C.c_int, [C.c_int32, C.c_int32]),
+    'bfvi_seq_mse': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32,
+                               C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                               C.c_void_p]),
     'bfvi_delete_rows': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'bfvi_delete_spans': (C.c_int, [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'bfvi_draw_deletions': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_uint64, C.c_uint32,

@@ -1640,6 +1640,59 @@ int bfvi_pad_merge(const float* packed, const int64_t* row_start, int32_t T, int
   return BFVI_OK;
 }
 
+int bfvi_unpad(const float* x, const int64_t* row_start, const int32_t* src, int32_t B, int32_t n_out,
+               int64_t total_rows, int64_t D, float* packed, void* stream) {
+  if (!x || !row_start || !src || !packed || B < 1 || n_out < 1 || D < 1 || total_rows < 0)
+    return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (total_rows == 0) return BFVI_OK;
+  const int64_t n = total_rows * D;
+  const bool vec = D % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)packed % 16 == 0;
+  const dim3 grid(grid_for(vec ? n / 4 : n, 256, 8)), block(256);
+  if (vec && D >= 1024) {             // wide rows: search once per row
+    auto k = bfvi::unpad_rows_kernel;
+    BFVI_LAUNCH(k, dim3((unsigned)grid_for(total_rows, 1, 8)), block, 0, (cudaStream_t)stream, x, row_start, src, (int)B, (int)n_out, D, packed);
+  } else if (vec) { auto k = bfvi::unpad_kernel<true>; BFVI_LAUNCH(k, grid, block, 0, (cudaStream_t)stream, x, row_start, src, (int)B, (int)n_out, D, packed); }
+  else { auto k = bfvi::unpad_kernel<false>; BFVI_LAUNCH(k, grid, block, 0, (cudaStream_t)stream, x, row_start, src, (int)B, (int)n_out, D, packed); }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+// time splits of bfvi_seq_mse: enough blocks (~16 per SM) when the batch has few, long sequences
+int bfvi_seq_mse_splits(int32_t T, int32_t B) {
+  if (T < 1 || B < 1) return 1;
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  int n = (16 * sms + B - 1) / B;
+  if (n > T) n = T;
+  return n < 1 ? 1 : n;
+}
+
+int bfvi_seq_mse(const float* const* recon, const float* const* target, const int64_t* dims, int32_t n_mods,
+                 const uint8_t* mask, const float* lengths, int32_t T, int32_t B, float* out, float* scratch,
+                 int32_t n_split, void* stream) {
+  if (!recon || !target || !dims || !mask || !lengths || !out || T < 1 || B < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (n_mods < 1 || n_mods > bfvi::kMaxMseMods) return fail(BFVI_ERR_ARG, "n_mods must be 1..%d", bfvi::kMaxMseMods);
+  if (n_split > 1 && !scratch) return fail(BFVI_ERR_WORKSPACE, "n_split > 1 needs scratch of B * n_split floats");
+  if (n_split < 1) n_split = 1;
+  if (n_split > T) n_split = T;
+  bfvi::SeqMseParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_mods; ++i) {
+    if (!recon[i] || !target[i] || dims[i] < 1) return fail(BFVI_ERR_ARG, "modality %d: null tensor or empty row", i);
+    p.recon[i] = recon[i]; p.target[i] = target[i]; p.D[i] = dims[i];
+  }
+  p.n_mods = n_mods; p.T = T; p.B = B; p.mask = mask; p.lengths = lengths; p.out = out;
+  p.scratch = scratch; p.n_split = n_split; p.t_per = (T + n_split - 1) / n_split;
+  auto k = bfvi::seq_mse_kernel;
+  BFVI_LAUNCH(k, dim3((unsigned)B, (unsigned)n_split), dim3(128), 0, (cudaStream_t)stream, p);
+  if (n_split > 1) {
+    auto kf = bfvi::seq_mse_finish_kernel;
+    BFVI_LAUNCH(kf, dim3((unsigned)((B + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)scratch, (int)n_split,
+                lengths, (int)B, out);
+  }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
 int bfvi_delete_rows(const float* x, const uint8_t* del_mask, int32_t T, int32_t B, int64_t D, float* out,
                      void* stream) {
   if (!x || !del_mask || !out || T < 1 || B < 1 || D < 1) return fail(BFVI_ERR_ARG, "null/empty argument");

@@ -91,6 +91,125 @@ pad_merge_kernel(const float* __restrict__ packed, const int64_t* __restrict__ r
   }
 }
 
+// seq_decoll (datasets/multiseq.py:388-398): the inverse of pad_merge — de-pad and reorder.  Output
+// sequence j = batch column src[j] (= the caller's `order`), its first lengths[src[j]] steps, packed back
+// to back at row_start[j] (B + 1 entries, rows of D floats).  One streaming pass over the OUTPUT:
+// read 4 B, write 4 B per kept element; the host then splits ONE D2H copy into per-sequence views.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+unpad_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_start, const int32_t* __restrict__ src,
+             int B, int n_out, int64_t D, float* __restrict__ packed) {
+  constexpr int W = VEC ? 4 : 1;
+  const int64_t n = row_start[n_out] * D;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W; i < n;
+       i += (int64_t)gridDim.x * blockDim.x * W) {
+    const int64_t row = i / D, e = i - row * D;
+    int lo = 0, hi = n_out;                                   // sequence j with row_start[j] <= row < row_start[j+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (row_start[mid] <= row) lo = mid; else hi = mid;
+    }
+    const int64_t t = row - row_start[lo];
+    const float* s = x + (t * B + src[lo]) * D + e;
+    if (VEC) *reinterpret_cast<float4*>(packed + i) = *reinterpret_cast<const float4*>(s);
+    else packed[i] = *s;
+  }
+}
+
+// wide rows (images): one block per output row at a time — the row -> sequence search once per row instead
+// of once per vector, then a straight 128-bit copy of the row
+__global__ void __launch_bounds__(256)
+unpad_rows_kernel(const float* __restrict__ x, const int64_t* __restrict__ row_start, const int32_t* __restrict__ src,
+                  int B, int n_out, int64_t D, float* __restrict__ packed) {
+  __shared__ int64_t s_src;
+  const int64_t n_rows = row_start[n_out];
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    if (threadIdx.x == 0) {
+      int lo = 0, hi = n_out;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row_start[mid] <= row) lo = mid; else hi = mid;
+      }
+      s_src = ((row - row_start[lo]) * B + src[lo]) * D;
+    }
+    __syncthreads();
+    const float4* s4 = reinterpret_cast<const float4*>(x + s_src);
+    float4* d4 = reinterpret_cast<float4*>(packed + row * D);
+    for (int64_t i = threadIdx.x; i < D / 4; i += blockDim.x) d4[i] = s4[i];
+    __syncthreads();
+  }
+}
+
+// Per-sequence mean squared error of the evaluation metrics (spirals.py:105-111):
+//   mse[t, b] = sum_m sum_d (recon_m[t, b, d] - target_m[t, b, d])^2, zeroed where the sequence mask is off,
+//   out[b] = sum_t mse[t, b] / lengths[b].
+// One 128-thread block per sequence: threads stride over the (t, d) elements of every modality, feature
+// index fastest (coalesced rows, 128-bit loads when rows are 16-byte multiples), then one block reduction.
+constexpr int kMaxMseMods = 8;
+struct SeqMseParams {
+  const float* recon[kMaxMseMods];
+  const float* target[kMaxMseMods];
+  int64_t D[kMaxMseMods];
+  int n_mods, T, B;
+  const uint8_t* mask;         // (T, B)
+  const float* lengths;        // (B), the divisor (reference: FloatTensor(lengths))
+  float* out;                  // (B)
+  float* scratch;              // (B, n_split) partial sums when n_split > 1 (few long sequences: more blocks)
+  int n_split;                 // blockIdx.y owns time steps [y * t_per, (y + 1) * t_per)
+  int t_per;
+};
+__global__ void __launch_bounds__(128) seq_mse_kernel(const SeqMseParams p) {
+  __shared__ float part[4];
+  const int b = blockIdx.x;
+  const int t_lo = blockIdx.y * p.t_per, t_hi = t_lo + p.t_per < p.T ? t_lo + p.t_per : p.T;
+  const int nt = t_hi - t_lo;
+  float acc = 0.f;
+  for (int m = 0; m < p.n_mods; ++m) {
+    const int64_t D = p.D[m];
+    const float* __restrict__ r = p.recon[m];
+    const float* __restrict__ x = p.target[m];
+    const bool vec = D % 4 == 0 && ((reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+    if (vec) {
+      const int64_t n4 = (int64_t)nt * (D / 4);
+      for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+        const int tl = (int)(i / (D / 4)), t = t_lo + tl;
+        if (p.mask[(int64_t)t * p.B + b] == 0) continue;
+        const int64_t o = ((int64_t)t * p.B + b) * D + (i - (int64_t)tl * (D / 4)) * 4;
+        const float4 a = *reinterpret_cast<const float4*>(r + o), c = *reinterpret_cast<const float4*>(x + o);
+        const float d0 = a.x - c.x, d1 = a.y - c.y, d2 = a.z - c.z, d3 = a.w - c.w;
+        acc += fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, d3 * d3)));
+      }
+    } else {
+      const int64_t n = (int64_t)nt * D;
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const int tl = (int)(i / D), t = t_lo + tl;
+        if (p.mask[(int64_t)t * p.B + b] == 0) continue;
+        const int64_t o = ((int64_t)t * p.B + b) * D + (i - (int64_t)tl * D);
+        const float df = r[o] - x[o];
+        acc = fmaf(df, df, acc);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float v = part[0] + part[1] + part[2] + part[3];
+    if (p.n_split > 1) p.scratch[(int64_t)b * p.n_split + blockIdx.y] = v;
+    else p.out[b] = v / p.lengths[b];
+  }
+}
+// second stage of a split reduction: fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) seq_mse_finish_kernel(const float* __restrict__ scratch, int n_split,
+                                                             const float* __restrict__ lengths, int B, float* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float v = 0.f;
+  for (int s = 0; s < n_split; ++s) v += scratch[(int64_t)b * n_split + s];
+  out[b] = v / lengths[b];
+}
+
 // Seeded device draws of the deleted rows of every sequence (one thread per sequence):
 //   mode 0 (rand_delete, datasets/multiseq.py:422-426): exactly k = int(frac * length) of the
 //     `length` steps, a uniformly random subset — selection sampling (Knuth 3.4.2 S): step t is

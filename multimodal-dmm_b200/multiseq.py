@@ -101,6 +101,71 @@ def seq_collate_dict(data, time_first=True, device='cuda'):
     return batch, len_to_mask(lengths, time_first, device=device), lengths, order, seq_ids
 
 
+def seq_decoll(batch, lengths, order, time_first=True):
+    """De-pad and reorder a device batch into a list of numpy arrays, one per sequence
+    (datasets/multiseq.py:388-398): sequence j of the result is batch column `order[j]`, its first
+    `lengths[order[j]]` steps.  One gather kernel into a packed buffer and ONE device-to-host copy
+    (the reference issues one indexed read and one D2H copy per sequence).  A tuple of batches is
+    stacked along a new axis 1 per sequence, as in the reference."""
+    if isinstance(batch, tuple):
+        parts = [seq_decoll(b, lengths, order, time_first) for b in batch]
+        return [np.stack([p[j] for p in parts], axis=1) for j in range(len(order))]
+    x = batch if time_first else batch.transpose(0, 1)
+    T, B = x.shape[:2]
+    dims = tuple(x.shape[2:])
+    D = int(np.prod(dims)) if dims else 1
+    order = [int(i) for i in order]
+    kept = [min(int(lengths[i]), T) for i in order]
+    starts = np.zeros(len(order) + 1, dtype=np.int64)
+    np.cumsum(kept, out=starts[1:])
+    total = int(starts[-1])
+    with _Runtime(x.device) as rt:
+        xc = x.detach().contiguous().float()
+        packed = torch.empty((total, D), dtype=torch.float32, device=xc.device)
+        if total > 0:
+            starts_d = torch.from_numpy(starts).to(xc.device, non_blocking=True)
+            order_d = _i32(order, xc.device)
+            rt.call('bfvi_unpad', _lib.ptr(xc), _lib.ptr(starts_d), _lib.ptr(order_d), B, len(order), total, D,
+                    _lib.ptr(packed))
+        host = packed.cpu().numpy()
+    return [host[starts[j]:starts[j + 1]].reshape((kept[j],) + dims) for j in range(len(order))]
+
+
+def seq_decoll_dict(batch_dict, lengths, order, time_first=True):
+    """Dictionary of batch tensors -> dictionary of per-sequence lists (datasets/multiseq.py:400-403)."""
+    return {k: seq_decoll(batch, lengths, order, time_first) for k, batch in batch_dict.items()}
+
+
+def seq_mse(recon, targets, mask, lengths, order=None):
+    """The per-sequence MSE of the evaluation metrics (spirals.py:105-111): squared error of the
+    reconstructed means summed over modalities and features, zero outside the sequence mask, averaged over
+    each sequence's length; `recon[m]` is the decoder's tuple (mean, std) or a mean tensor.  Returns a (B,)
+    device tensor, indexed by `order` when given — `.tolist()` of it is `metrics['mse']`."""
+    mods = list(recon.keys())
+    means = [(recon[m][0] if isinstance(recon[m], (tuple, list)) else recon[m]).detach().contiguous().float() for m in mods]
+    tgts = [targets[m].detach().contiguous().float() for m in mods]
+    T, B = means[0].shape[:2]
+    with _Runtime(means[0].device) as rt:
+        dev = means[0].device
+        mk = mask.reshape(T, B).to(device=dev, dtype=torch.uint8).contiguous()
+        if not torch.is_tensor(lengths):
+            lengths = torch.as_tensor(np.asarray(lengths, dtype=np.float32))
+        len_d = lengths.to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty(B, dtype=torch.float32, device=dev)
+        n = len(mods)
+        rp = (C.c_void_p * n)(*[t.data_ptr() for t in means])
+        tp = (C.c_void_p * n)(*[t.data_ptr() for t in tgts])
+        dims = (C.c_int64 * n)(*[int(t[0, 0].numel()) for t in means])
+        for a, b in zip(means, tgts):
+            if a.shape != b.shape:
+                raise _lib.BfviError('seq_mse: reconstruction %s and target %s differ in shape' % (tuple(a.shape), tuple(b.shape)))
+        n_split = int(rt.lib.dll.bfvi_seq_mse_splits(T, B))
+        scratch = torch.empty(B * n_split, dtype=torch.float32, device=dev) if n_split > 1 else None
+        rt.call('bfvi_seq_mse', rp, tp, dims, n, _lib.ptr(mk), _lib.ptr(len_d), T, B, _lib.ptr(out), _lib.ptr(scratch),
+                n_split)
+    return out if order is None else out[torch.as_tensor(list(order), device=out.device)]
+
+
 def _rows_view(x):
     T, B = x.shape[:2]
     D = x[0, 0].numel() if x.dim() > 2 else 1

@@ -32,6 +32,23 @@ def pad_and_merge(sequences, max_len=None):
     return out
 
 
+def seq_decoll(batch, lengths, order, time_first=True):
+    """datasets/multiseq.py:388-398 (numpy in, list of numpy out)."""
+    if isinstance(batch, tuple):
+        return [np.stack([b[:lengths[idx], idx] for b in batch], axis=1) for idx in order]
+    if time_first:
+        return [batch[:lengths[idx], idx] for idx in order]
+    return [batch[idx, :lengths[idx]] for idx in order]
+
+
+def seq_mse(recon_means, targets, mask, lengths, order):
+    """The 'mse' metric of spirals.py:105-111: float32 like the reference tensors."""
+    mse = sum([(recon_means[m] - targets[m]) ** 2 for m in recon_means])
+    mse = mse.reshape(mse.shape[0], mse.shape[1], -1).sum(axis=2, dtype=np.float32)
+    mse[~mask.reshape(mask.shape[0], mask.shape[1])] = 0.0
+    return (mse.sum(axis=0, dtype=np.float32) / np.asarray(lengths, dtype=np.float32))[list(order)]
+
+
 def func_delete(batch_in, del_func, lengths=None, modalities=None):
     """datasets/multiseq.py:405-420 (draw order: modality-major, then b)."""
     if modalities is None:

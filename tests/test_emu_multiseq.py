@@ -170,3 +170,37 @@ def test_entry_points_reject_bad_arguments():
         lib.call('bfvi_draw_deletions', None, 2, 2, 0.5, 7, 1, 0, 0, _lib.ptr(flags), None)
     with pytest.raises(_lib.BfviError):
         multiseq.burst_delete({'a': torch.zeros(3, 2, 1)}, 0.1)            # CPU tensor, real runtime
+
+
+# ---- evaluation outputs: seq_decoll / seq_decoll_dict and the per-sequence MSE metric ----
+EVAL = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'multiseq', 'eval.pt'), weights_only=False)
+
+
+@pytest.mark.parametrize('case', EVAL, ids=lambda c: c['name'])
+def test_eval_oracle_matches_reference_golden(case):
+    for m, want in case['decoll'].items():
+        got = orc.seq_decoll(case['batch'][m].numpy(), case['lengths'], case['order'])
+        assert len(got) == len(want) and all(same(a, b.numpy()) for a, b in zip(got, want))
+    mse = orc.seq_mse({m: v.numpy() for m, v in case['recon'].items()}, {m: v.numpy() for m, v in case['targets'].items()},
+                      case['mask'].numpy(), case['lengths'], case['order'])
+    assert np.allclose(mse, case['mse'].numpy(), rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize('case', EVAL, ids=lambda c: c['name'])
+def test_eval_kernels_match_reference_golden(emu, case):
+    got = multiseq.seq_decoll_dict(case['batch'], case['lengths'], case['order'])
+    for m, want in case['decoll'].items():
+        assert len(got[m]) == len(want)
+        assert all(same(a, b.numpy()) for a, b in zip(got[m], want)), m           # bit for bit
+    if case['decoll_tuple'] is not None:
+        tup = multiseq.seq_decoll(tuple(case['batch'].values()), case['lengths'], case['order'])
+        assert all(same(a, b.numpy()) for a, b in zip(tup, case['decoll_tuple']))
+    # batch-first layout gives the same sequences
+    bf = multiseq.seq_decoll(case['batch'][list(case['batch'])[0]].transpose(0, 1), case['lengths'], case['order'],
+                             time_first=False)
+    assert all(same(a, b.numpy()) for a, b in zip(bf, case['decoll'][list(case['batch'])[0]]))
+    recon = {m: (v, None) for m, v in case['recon'].items()}
+    mse = multiseq.seq_mse(recon, case['targets'], case['mask'], case['lengths'], case['order'])
+    assert torch.allclose(mse, case['mse'], rtol=2e-6, atol=0)                    # fp32 sums in another order
+    with pytest.raises(_lib.BfviError):
+        multiseq.seq_mse({'a': torch.zeros(3, 2, 1)}, {'a': torch.zeros(3, 2, 2)}, torch.ones(3, 2, 1, dtype=torch.bool), [3, 3])

@@ -1,6 +1,8 @@
 """multimodal_dmm_b200.multiseq on the GPU: bit-exact against the reference's golden outputs
 (tests/golden/multiseq, numpy draws replayed), seeded device draws against the integer
 restatement, and size-independent properties at BASELINE.json's C2 batch shape."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -81,3 +83,41 @@ def test_image_rows_use_the_vector_path():
     np.random.seed(4)
     want = orc.rand_delete({'video': x['video'].cpu().numpy()}, 0.5, [6, 6, 5, 3, 2])
     assert same(got['video'].cpu().numpy(), want['video'])
+
+
+EVAL = torch.load(os.path.join(os.path.dirname(__file__), 'golden', 'multiseq', 'eval.pt'), weights_only=False)
+
+
+@pytest.mark.parametrize('case', EVAL, ids=lambda c: c['name'])
+def test_eval_outputs_match_reference_golden(case):
+    """seq_decoll_dict (bit for bit) and the per-sequence MSE metric against the reference's outputs."""
+    dev = torch.device('cuda:0')
+    batch = {m: v.to(dev) for m, v in case['batch'].items()}
+    got = multiseq.seq_decoll_dict(batch, case['lengths'], case['order'])
+    for m, want in case['decoll'].items():
+        assert len(got[m]) == len(want)
+        assert all(same(a, b.numpy()) for a, b in zip(got[m], want)), m
+    recon = {m: (v.to(dev), None) for m, v in case['recon'].items()}
+    targets = {m: v.to(dev) for m, v in case['targets'].items()}
+    mse = multiseq.seq_mse(recon, targets, case['mask'].to(dev), case['lengths'], case['order'])
+    assert torch.allclose(mse.cpu(), case['mse'], rtol=2e-6, atol=0)
+
+
+def test_eval_outputs_at_bench_size():
+    """C2-sized batch: decollation round trip (collate -> decollate returns the sequences) and the MSE
+    metric against torch ops on the device."""
+    dev = torch.device('cuda:0')
+    rng = np.random.RandomState(3)
+    lengths = sorted(rng.randint(1, 101, size=4096).tolist(), reverse=True)
+    seqs = [rng.standard_normal((n, 3)).astype(np.float32) for n in lengths]
+    x = multiseq.pad_and_merge(seqs, device=dev)
+    order = rng.permutation(len(lengths)).tolist()
+    out = multiseq.seq_decoll(x, lengths, order)
+    assert all(np.array_equal(out[j], seqs[i]) for j, i in enumerate(order))
+    mask = multiseq.len_to_mask(lengths, device=dev)
+    tgt = torch.nan_to_num(x, nan=0.0)
+    rec = tgt + 0.1 * torch.randn_like(tgt)
+    mse = multiseq.seq_mse({'a': (rec, None)}, {'a': tgt}, mask, lengths)
+    ref = ((rec - tgt) ** 2).sum(-1) * mask.squeeze(-1)
+    ref = ref.sum(0) / torch.tensor(lengths, dtype=torch.float32, device=dev)
+    assert torch.allclose(mse, ref, rtol=1e-5, atol=0)

@@ -65,6 +65,28 @@ def main():
     report('delete_rows_kernel<vec>', ms, 8 * n, 'func_delete: read 4 B + write 4 B per element')
     ms = timed(lambda: lib.call('bfvi_pad_merge', _lib.ptr(x), _lib.ptr(starts), T, B, D, _lib.ptr(out), st))
     report('pad_merge_kernel<vec>', ms, 8 * n, 'pad_and_merge: gather rows, read 4 B + write 4 B per element')
+    # seq_decoll: de-pad (ragged lengths: 3/4 of the rows kept on average) + reorder, one gather pass
+    lens = torch.randint(T // 2, T + 1, (B,), generator=torch.Generator().manual_seed(1))
+    order = torch.randperm(B, generator=torch.Generator().manual_seed(2))
+    ustarts = torch.zeros(B + 1, dtype=torch.int64)
+    ustarts[1:] = torch.cumsum(lens[order], 0)
+    total = int(ustarts[-1])
+    ustarts_d, order_d = ustarts.cuda(), order.to(torch.int32).cuda()
+    ms = timed(lambda: lib.call('bfvi_unpad', _lib.ptr(x), _lib.ptr(ustarts_d), _lib.ptr(order_d), B, B, total, D,
+                                _lib.ptr(out), st))
+    rows_kept = total
+    gbs_n = 8 * rows_kept * D
+    report('unpad_kernel<vec>', ms, gbs_n, 'seq_decoll: read 4 B + write 4 B per KEPT element (%d of %d rows)' % (rows_kept, T * B))
+    # per-sequence MSE metric: read reconstruction + target
+    lens_f = lens.float().cuda()
+    mk = (torch.arange(T).view(T, 1) < lens.view(1, B)).to(torch.uint8).cuda()
+    mse_out = torch.empty(B, device='cuda')
+    rp, tp, dd = (C.c_void_p * 1)(x.data_ptr()), (C.c_void_p * 1)(th.data_ptr()), (C.c_int64 * 1)(D)
+    n_split = int(lib.dll.bfvi_seq_mse_splits(T, B))
+    scratch = torch.empty(B * n_split, device='cuda')
+    ms = timed(lambda: lib.call('bfvi_seq_mse', rp, tp, dd, 1, _lib.ptr(mk), _lib.ptr(lens_f), T, B, _lib.ptr(mse_out),
+                                _lib.ptr(scratch), n_split, st))
+    report('seq_mse_kernel', ms, 8 * rows_kept * D, 'per-sequence MSE: read reconstruction + target on the unmasked rows')
     ms = timed(lambda: lib.call('bfvi_nll_bernoulli_fwd', _lib.ptr(th), _lib.ptr(x), _lib.ptr(rmask), T * B, D,
                                 _lib.ptr(acc), st))
     report('nll_bernoulli_kernel<vec> fwd', ms, 8 * n, 'BCE sum: read theta + x')
