@@ -294,6 +294,14 @@ int bfvi_seq_mse(const float* const* recon, const float* const* target, const in
                  const uint8_t* mask, const float* lengths, int32_t T, int32_t B, float* out, float* scratch,
                  int32_t n_split, void* stream);
 
+/* eval_ssim / _ssim (utils.py:110-212): per-image SSIM (and contrast-structure term, nullable) of two
+ * (N, C, H, W) fp32 batches with a separable 1-D window `win` (HOST array of win_size taps, odd, <= 15;
+ * the reference default is the 11-tap Gaussian of sigma 1.5), valid padding, mean over (C, H', W').
+ * scratch: bfvi_ssim_scratch(...) bytes of device memory. */
+size_t bfvi_ssim_scratch(int32_t N, int32_t C, int32_t H, int32_t W, int32_t win_size);
+int bfvi_ssim(const float* x, const float* y, int32_t N, int32_t C, int32_t H, int32_t W, const float* win,
+              int32_t win_size, float data_range, float* ssim, float* cs, float* scratch, void* stream);
+
 /* func_delete (datasets/multiseq.py:405-420): out = copy of x with rows (t, b) set to NaN.
  * _rows: explicit (T, B) flags (any del_func; the host replays the reference's numpy draws).
  * _spans: rows lo[b] <= t < hi[b] (burst_delete :428-434, del_segment :443-448), or with

@@ -142,6 +142,9 @@ SYMBOLS = {
     'bfvi_pad_merge': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]),
     'bfvi_unpad': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                              C.c_void_p]),
+    'bfvi_ssim_scratch': (C.c_size_t, [C.c_int32] * 5),
+    'bfvi_ssim': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float),
+                            C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'bfvi_seq_mse_splits': (C.c_int, [C.c_int32, C.c_int32]),
     'bfvi_seq_mse': (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int32,
                                C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,

@@ -1693,6 +1693,39 @@ int bfvi_seq_mse(const float* const* recon, const float* const* target, const in
   return BFVI_OK;
 }
 
+size_t bfvi_ssim_scratch(int32_t N, int32_t C, int32_t H, int32_t W, int32_t win) {
+  if (N < 1 || C < 1 || win < 1 || H < win || W < win) return 0;
+  const int tx = (W - win + 1 + bfvi::kSsimTile - 1) / bfvi::kSsimTile, ty = (H - win + 1 + bfvi::kSsimTile - 1) / bfvi::kSsimTile;
+  return sizeof(float) * 2 * (size_t)N * C * tx * ty;
+}
+
+int bfvi_ssim(const float* x, const float* y, int32_t N, int32_t C, int32_t H, int32_t W, const float* win,
+              int32_t win_size, float data_range, float* ssim, float* cs, float* scratch, void* stream) {
+  if (!x || !y || !win || !ssim || !scratch || N < 1 || C < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (win_size < 1 || win_size > bfvi::kSsimMaxWin || win_size % 2 == 0)
+    return fail(BFVI_ERR_UNSUPPORTED, "window size must be odd and <= %d", bfvi::kSsimMaxWin);
+  if (H < win_size || W < win_size) return fail(BFVI_ERR_ARG, "image smaller than the window");
+  if (C > 65535 || N > 65535) return fail(BFVI_ERR_UNSUPPORTED, "N and C up to 65535 per call");
+  bfvi::SsimParams p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.y = y; p.N = N; p.C = C; p.H = H; p.W = W; p.win = win_size;
+  for (int i = 0; i < win_size; ++i) p.w[i] = win[i];           // HOST array
+  p.c1 = (0.01f * data_range) * (0.01f * data_range);
+  p.c2 = (0.03f * data_range) * (0.03f * data_range);
+  p.tiles_x = (W - win_size + 1 + bfvi::kSsimTile - 1) / bfvi::kSsimTile;
+  p.tiles_y = (H - win_size + 1 + bfvi::kSsimTile - 1) / bfvi::kSsimTile;
+  p.scratch = scratch;
+  const dim3 grid((unsigned)(p.tiles_x * p.tiles_y), (unsigned)C, (unsigned)N);
+  if (win_size == 11) { auto k = bfvi::ssim11_kernel; BFVI_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, p); }
+  else { auto k = bfvi::ssim_kernel; BFVI_LAUNCH(k, grid, dim3(256), 0, (cudaStream_t)stream, p); }
+  const float inv = 1.f / ((float)C * (float)(H - win_size + 1) * (float)(W - win_size + 1));
+  auto kf = bfvi::ssim_finish_kernel;
+  BFVI_LAUNCH(kf, dim3((unsigned)((N + 127) / 128)), dim3(128), 0, (cudaStream_t)stream, (const float*)scratch, (int)N,
+              (int)(C * p.tiles_x * p.tiles_y), inv, ssim, cs);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
 int bfvi_delete_rows(const float* x, const uint8_t* del_mask, int32_t T, int32_t B, int64_t D, float* out,
                      void* stream) {
   if (!x || !del_mask || !out || T < 1 || B < 1 || D < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
