@@ -792,6 +792,11 @@ __global__ void match_tail_kernel(const float* c_mu, const float* c_sd, const fl
   if (i < Z) { atomicAdd(g_z0_mean + i, c_mu[i]); atomicAdd(g_z0_log_std + i, c_sd[i] * expf(z0_log_std[i])); }
 }
 
+// step_kernel, or its four-components-per-thread form when the rows are 16-byte multiples
+static bool step4_ok(const bfvi::gen::StepParams& sp) {
+  return sp.Z % 4 == 0 && (((uintptr_t)sp.g | (uintptr_t)sp.nl | (uintptr_t)sp.lin | (uintptr_t)sp.as | (uintptr_t)sp.zrows) & 15) == 0;
+}
+
 // fonly != null: run only z_filter forward (fonly_backward = false) or backward on `fonly`
 int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
                const bfvi_filter_args* fonly, bool fonly_backward, void* workspace, size_t workspace_bytes,
@@ -981,8 +986,8 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       if (i > 0) { if (int rc = trans_fwd(g, rows, false)) return rc; }
       bfvi::gen::StepParams sp = step_params(f, i);
       sp.zrowsT = nullptr; sp.samplesT = samplesT;
-      auto k = bfvi::gen::step_kernel;
-      BFVI_LAUNCH(k, ew_grid(chains * Z, 128), dim3(128), 0, st, sp);
+      if (step4_ok(sp)) { auto k = bfvi::gen::step4_kernel; BFVI_LAUNCH(k, ew_grid(chains * (Z / 4), 128), dim3(128), 0, st, sp); }
+      else { auto k = bfvi::gen::step_kernel; BFVI_LAUNCH(k, ew_grid(chains * Z, 128), dim3(128), 0, st, sp); }
       ++n_launch;
     }
     BFVI_CHECK_CUDA();
@@ -2314,8 +2319,8 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
       sp.min_std = m->min_std; sp.Z = Z; sp.i = i; sp.R = rows;
       sp.g = gbuf; sp.nl = nlbuf; sp.lin = linbuf; sp.as = asbuf;
       sp.zrows = zrows;
-      auto k = bfvi::gen::step_kernel;
-      BFVI_LAUNCH(k, ew_grid((int64_t)B * Z, 128), dim3(128), 0, st, sp);
+      if (step4_ok(sp)) { auto k = bfvi::gen::step4_kernel; BFVI_LAUNCH(k, ew_grid((int64_t)B * (Z / 4), 128), dim3(128), 0, st, sp); }
+      else { auto k = bfvi::gen::step_kernel; BFVI_LAUNCH(k, ew_grid((int64_t)B * Z, 128), dim3(128), 0, st, sp); }
     }
     BFVI_CHECK_CUDA();
     return BFVI_OK;

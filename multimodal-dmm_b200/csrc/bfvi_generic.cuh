@@ -255,6 +255,124 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepP
   if (a.loss_acc != nullptr && a.kl_weight != 0.f) block_reduce_add_double(kl_sum * a.kl_weight, a.loss_acc);
 }
 
+// step_kernel for Z % 4 == 0: a thread owns FOUR consecutive components of a chain — the GTF heads arrive as
+// 128-bit loads, and the K new particles cost one Philox call each instead of four (the scalar kernel draws a
+// whole normal4 per component and keeps one value: at K = 25 the generator was most of its 38 us).  Same
+// per-component arithmetic in the same order: results are bit-identical to step_kernel.
+__global__ void __launch_bounds__(128) step4_kernel(const __grid_constant__ StepParams p) {
+  const bfvi_filter_args& a = p.a;
+  const int Z = p.Z, K = a.n_particles, B = a.B, T = a.T, Q = Z >> 2;
+  const int t = gen_pass_time(p.i, T, a.direction);
+  const float inv_k = 1.f / (float)K;
+  const int64_t n_chains = (int64_t)a.S * B;
+  float kl_sum = 0.f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chains * Q;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int zi = (int)(idx % Q) * 4;
+    const int64_t c = idx / Q;
+    const int s = (int)(c / B), b = (int)(c % B);
+    const unsigned bits = a.set_expert_bits[s];
+    float gm[4], gs[4], pm[4], ps[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gm[j] = p.z0_mean[zi + j]; gs[j] = expf(p.z0_log_std[zi + j]) + p.min_std; }
+    if (p.i == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { pm[j] = gm[j]; ps[j] = gs[j]; }
+    } else {
+      float sm[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int k = 0; k < K; ++k) {
+        const int64_t r = (c * K + k) * Z + zi;
+        const float4 g4 = *reinterpret_cast<const float4*>(p.g + r), n4 = *reinterpret_cast<const float4*>(p.nl + r);
+        const float4 l4 = *reinterpret_cast<const float4*>(p.lin + r), a4 = *reinterpret_cast<const float4*>(p.as + r);
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, nv[4] = {n4.x, n4.y, n4.z, n4.w};
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gate = sigmoid_f(gv[j]);
+          const float qm = fmaf(gate, nv[j] - lv[j], lv[j]);
+          const float qs = softplus_f(av[j]) + p.min_std;
+          float m_k, s_k;
+          poe2_forward(gm[j], gs[j], qm, qs, m_k, s_k);
+          if (K == 1) { sm[j] = m_k; sv[j] = s_k; }
+          else { sm[j] += m_k; sv[j] = fmaf(s_k, s_k, sv[j]); sq[j] = fmaf(m_k, m_k, sq[j]); }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (K == 1) { pm[j] = sm[j]; ps[j] = sv[j]; }
+        else {                                              // models/dgts.py:78-83
+          pm[j] = sm[j] * inv_k;
+          ps[j] = sqrtf(sv[j] * inv_k + (sq[j] * inv_k - pm[j] * pm[j]));
+        }
+      }
+    }
+    // product of experts, prior first then the experts in order (models/dgts.py:40-51)
+    float S[4], N[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { S[j] = poe_prec(ps[j]); N[j] = __fmul_rn(pm[j], S[j]); }
+    for (int e = 0; e < a.n_experts; ++e) {
+      if (!((bits >> e) & 1u)) continue;
+      const bfvi_expert& ex = a.experts[e];
+      bool m = true;
+      if (ex.mask != nullptr) m = ex.mask[s * ex.mstride_s + t * ex.mstride_t + b * ex.mstride_b] != 0;
+      if (ex.zero_mask_last_t && t == T - 1) m = false;
+      const float w = m ? 1.f : 0.f;
+      const int64_t off = ex.kind == BFVI_EXPERT_INV_PRIOR ? 0 : s * ex.stride_s + t * ex.stride_t + b * ex.stride_b + zi;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float mean, std;
+        if (ex.kind == BFVI_EXPERT_INV_PRIOR) { mean = gm[j]; std = -gs[j]; }
+        else { mean = ex.mean[off + j]; std = ex.std[off + j]; }
+        const float te = __fmul_rn(poe_prec(std), w);
+        S[j] = __fadd_rn(S[j], te);
+        N[j] = __fadd_rn(N[j], __fmul_rn(__fmul_rn(mean, w), te));
+      }
+    }
+    const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
+    const bool kl_on = a.kl_weight != 0.f && (a.seq_mask == nullptr || a.seq_mask[t * B + b]);
+    float mu[4], sd[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float mq = __fdiv_rn(N[j], S[j]);
+      mu[j] = (mq != mq) ? 0.f : mq;
+      sd[j] = __fsqrt_rn(__fdiv_rn(1.f, S[j]));
+      a.infer_mean[o + j] = mu[j]; a.infer_std[o + j] = sd[j];
+      a.prior_mean[o + j] = pm[j]; a.prior_std[o + j] = ps[j];
+      if (kl_on) kl_sum += kld_elem_fast(mu[j], sd[j], pm[j], ps[j]);
+    }
+    // particles of this step: input rows of the next transition and the `samples` output
+    const bool sampled = gen_samples(a, p.i);
+    float se[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < K; ++k) {
+      float z[4] = {mu[0], mu[1], mu[2], mu[3]};
+      if (sampled) {
+        float e[4];
+        if (a.noise.eps != nullptr) {
+          const float* ep = a.noise.eps + ((((int64_t)s * T + t) * B + b) * K + k) * Z + zi;
+          e[0] = ep[0]; e[1] = ep[1]; e[2] = ep[2]; e[3] = ep[3];
+        } else {
+          normal4(noise_seed(a.noise), a.noise.stream_id, (unsigned)s, (unsigned)t, (unsigned)b + a.noise.b_offset,
+                  (unsigned)k, (unsigned)(zi >> 2), e);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = fmaf(e[j], sd[j], mu[j]);
+      }
+      if (p.zrows != nullptr) *reinterpret_cast<float4*>(p.zrows + (c * K + k) * Z + zi) = make_float4(z[0], z[1], z[2], z[3]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) se[j] += z[j];
+    }
+    if (a.samples != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a.samples[o + j] = se[j] * inv_k;
+        if (p.samplesT != nullptr)
+          p.samplesT[((int64_t)s * Z + zi + j) * ((int64_t)T * B) + (int64_t)t * B + b] = se[j] * inv_k;
+      }
+    }
+  }
+  if (a.loss_acc != nullptr && a.kl_weight != 0.f) block_reduce_add_double(kl_sum * a.kl_weight, a.loss_acc);
+}
+
 // ---------------------------------------------------------------------------------------
 // backward of one step, part 1 — everything per (chain, zi) ABOVE the transition: upstream
 // gradients, the fused KL term, the product of experts.  Writes d_pm / d_v for the particle
