@@ -557,6 +557,7 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
     const int slots = (num_sms() > 0 ? num_sms() : 1) * (ctas_per_sm > 1 ? 2 : 1);
     static const bool a_in_tmem = [] { const char* e = getenv("BFVI_GEMM_TS"); return !e || atoi(e) != 0; }();
     static const int ts_cap = [] { const char* e = getenv("BFVI_GEMM_TS_STAGES"); return e ? atoi(e) : 8; }();
+    static const int lag_env = [] { const char* e = getenv("BFVI_GEMM_LAG"); return e ? atoi(e) : 0; }();   // 0: kernel default
     if constexpr (BN <= 128 && SPLIT) {
       if (a_in_tmem && vec) {        // A operand from tensor memory (aligned 3xTF32 problems)
         int ts_stages = (int)(budget / bfvi::tc::gemm_ts_stage_bytes<BN, SPLIT>());
@@ -566,7 +567,7 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
         const size_t smem_ts = bfvi::tc::gemm_ts_smem_bytes<BN, SPLIT>(ts_stages);
         auto kt = bfvi::tc::gemm_tf32_ts_kernel<BN, SPLIT, true>;
         cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
-        kt<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem_ts, st>>>(grp, ts_stages);
+        kt<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem_ts, st>>>(grp, ts_stages, lag_env);
         BFVI_CHECK_CUDA();
         return BFVI_OK;
       }
@@ -574,7 +575,7 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
     const size_t smem = bfvi::tc::gemm_p_smem_bytes<BN, SPLIT>(stages);
     auto k = vec ? bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, true> : bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, false>;
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem, st>>>(grp, stages);
+    k<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem, st>>>(grp, stages, lag_env);
   }
 #endif
   BFVI_CHECK_CUDA();

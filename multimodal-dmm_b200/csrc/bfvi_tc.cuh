@@ -599,7 +599,7 @@ __device__ __forceinline__ int tile_chunks(const GemmGroup& grp, int t) {
 }
 
 template <int BN, bool SPLIT, bool VEC>
-__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_constant__ GemmGroup grp, int n_stages) {
+__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_constant__ GemmGroup grp, int n_stages, int lag_arg) {
   using Cfg = TileCfg<BN, SPLIT>;
   extern __shared__ unsigned char tc_smem_dyn[];
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_p_kernel(const __grid_
     // A stage is refilled `lag` jobs after the job that used it: with a 4-stage ring lag = 2, so the wait
     // for that job's MMAs (hand-over latency MMA warp -> tensor pipe -> commit -> this warp, ~0.5 us) has a
     // whole iteration of slack and two jobs stay in flight; shallower rings refill at once (lag 1).
-    const int lag = n_stages >= 4 ? 2 : 1;
+    const int lag = lag_arg > 0 && lag_arg < n_stages ? lag_arg : (n_stages >= 4 ? 2 : 1);
     for (int c = 0; c < n_stages - lag; ++c) {            // prologue: jobs 0 .. n_stages-lag-1
       if (load_more()) issue_next_load(c);
       cp_async_commit();
@@ -820,7 +820,7 @@ __host__ __device__ constexpr int ts_max_stages(int bn) { return bn <= 64 ? 6 : 
 // shared-memory traffic instead of 224 KB.  Copies are tracked by an mbarrier (cp.async.mbarrier.arrive), so
 // the copying and the converting thread of a vector need not be the same; warps 4-7 round W in place.
 template <int BN, bool SPLIT, bool VEC>
-__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid_constant__ GemmGroup grp, int n_stages) {
+__global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid_constant__ GemmGroup grp, int n_stages, int lag_arg) {
   using Cfg = TileCfg<BN, SPLIT>;
   static_assert(BN <= 128, "A ring + accumulators must fit in 512 TMEM columns");
   constexpr int kStageTs = Cfg::kABytes + (SPLIT ? 2 : 1) * Cfg::kWBytes;      // raw A | W hi | W lo
@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid
     // A stage is refilled `lag` jobs after the job that used it: with a 4-stage ring lag = 2, so the wait
     // for that job's MMAs (hand-over latency MMA warp -> tensor pipe -> commit -> this warp, ~0.5 us) has a
     // whole iteration of slack and two jobs stay in flight; shallower rings refill at once (lag 1).
-    const int lag = n_stages >= 4 ? 2 : 1;
+    const int lag = lag_arg > 0 && lag_arg < n_stages ? lag_arg : (n_stages >= 4 ? 2 : 1);
     for (int c = 0; c < n_stages - lag; ++c)              // prologue: jobs 0 .. n_stages-lag-1
       if (load_more()) issue_next_load(c);
     if (my_tiles > 0) c_chunks = tile_chunks(grp, (int)blockIdx.x);
