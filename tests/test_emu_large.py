@@ -5,6 +5,7 @@ import pytest
 import torch
 
 import helpers
+from multimodal_dmm_b200 import _lib
 
 
 @pytest.fixture(scope='module')
@@ -116,3 +117,29 @@ def test_standalone_filter_of_both_families_agree(lib, monkeypatch):
     for a, b in zip(o1, o2):
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
     assert rel_err(g2, g1) < 1e-4 and rel_err(dm2, dm1) < 1e-4 and rel_err(ds2, ds1) < 1e-4
+
+
+@pytest.mark.parametrize('shape', [(77, 20, 40), (50, 5, 3), (64, 8, 96), (33, 70, 6)])
+def test_gemm_entry_points_host_logic(lib, shape):
+    """bfvi_linear_tf32 / bfvi_wgrad_tf32 through the emulated library (exact fp32 GEMM stand-in): argument
+    plumbing, leading dimensions, accumulate semantics and the transposed-output form that weight gradients
+    with few outputs and many inputs take (n_out < n_in, n_out <= 64)."""
+    rows, n_out, n_in = shape
+    g = torch.Generator().manual_seed(rows * 7 + n_out)
+    x = torch.randn(rows, n_in, generator=g)
+    w = torch.randn(n_out, n_in, generator=g)
+    b = torch.randn(n_out, generator=g)
+    y = torch.full((rows, n_out + 2), float('nan'))
+    lib.call('bfvi_linear_tf32', _lib.ptr(x), n_in, _lib.ptr(w), n_in, _lib.ptr(b), _lib.ptr(y), n_out + 2,
+             rows, n_in, n_out, 1, None)
+    assert torch.allclose(y[:, :n_out], torch.relu(x @ w.t() + b), rtol=1e-5, atol=1e-5)
+    assert torch.isnan(y[:, n_out:]).all()
+    dy = torch.randn(rows, n_out, generator=g)
+    dw0 = torch.randn(n_out, n_in, generator=g)
+    dy_t, x_t = dy.t().contiguous(), x.t().contiguous()
+    for accumulate in (1, 0):
+        dw = dw0.clone()
+        lib.call('bfvi_wgrad_tf32', _lib.ptr(dy_t), rows, _lib.ptr(x_t), rows, _lib.ptr(dw), n_in, rows, n_out,
+                 n_in, accumulate, 0, None)
+        want = dy.t() @ x + (dw0 if accumulate else 0)
+        assert torch.allclose(dw, want, rtol=1e-4, atol=1e-4), (shape, accumulate)
