@@ -674,7 +674,7 @@ struct LargePlan {
   size_t paramsT, x0[BFVI_MAX_MODS], x0T[BFVI_MAX_MODS], mask, henc, hencT, obs_mean, obs_stdpre, obs_std;
   size_t pa[6], pb[4], pc[6];                       // infer m/s, prior m/s, samples, samplesT
   size_t zrows, zrowsT, h1, h1T, h3, h3T, dh1, dh1T, dh3, dh3T;
-  size_t g, nl, nlT, lin, as, d_as, d_asT, d_g, d_gT, d_lin, d_linT, d_nl, d_nlT, dz;
+  size_t g, nl, nlT, lin, as, d_as, d_asT, d_g, d_gT, d_lin, d_linT, d_nl, d_nlT, dz, dz2;
   size_t c_mu, c_sd, d_pm, d_v, zvec;
   size_t hdec, hdecT, dhd, dhdT, dmean, dstd, dmeanT, dstdT;
   size_t side_grads;                                 // zeroed: parameter gradients of the side stream (pass A)
@@ -728,7 +728,7 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   pl->h1 = carve(rh); pl->h1T = carve(rh); pl->h3 = carve(rh); pl->h3T = carve(rh);
   pl->dh1 = carve(rh); pl->dh1T = carve(rh); pl->dh3 = carve(rh); pl->dh3T = carve(rh);
   size_t* zbufs[] = {&pl->g, &pl->nl, &pl->nlT, &pl->lin, &pl->as, &pl->d_as, &pl->d_asT, &pl->d_g, &pl->d_gT,
-                     &pl->d_lin, &pl->d_linT, &pl->d_nl, &pl->d_nlT, &pl->dz};
+                     &pl->d_lin, &pl->d_linT, &pl->d_nl, &pl->d_nlT, &pl->dz, &pl->dz2};
   for (size_t* z : zbufs) *z = carve(rz);
   pl->c_mu = carve(f * pl->C * Z); pl->c_sd = carve(f * pl->C * Z);
   pl->d_pm = carve(f * pl->C * Z); pl->d_v = carve(f * pl->C * Z);
@@ -764,7 +764,7 @@ void plan_large_side(const bfvi_model* m, const bfvi_step_args* a, const LargePl
   ps->h1 = carve(rh); ps->h1T = carve(rh); ps->h3 = carve(rh); ps->h3T = carve(rh);
   ps->dh1 = carve(rh); ps->dh1T = carve(rh); ps->dh3 = carve(rh); ps->dh3T = carve(rh);
   size_t* zbufs[] = {&ps->g, &ps->nl, &ps->nlT, &ps->lin, &ps->as, &ps->d_as, &ps->d_asT, &ps->d_g, &ps->d_gT,
-                     &ps->d_lin, &ps->d_linT, &ps->d_nl, &ps->d_nlT, &ps->dz};
+                     &ps->d_lin, &ps->d_linT, &ps->d_nl, &ps->d_nlT, &ps->dz, &ps->dz2};
   for (size_t* z : zbufs) *z = carve(rz);
   ps->c_mu = carve(f * pl.C * Z); ps->c_sd = carve(f * pl.C * Z);
   ps->d_pm = carve(f * pl.C * Z); ps->d_v = carve(f * pl.C * Z);
@@ -913,39 +913,42 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   }
 
   // ---- one transition: 6 forward GEMMs over `rows` particles --------------------------------
+  // Groups are width-homogeneous (a launch has ONE tile width: a 64-wide problem in a 128-wide launch copies,
+  // rounds and multiplies a half-empty W tile): the two z -> hidden layers (N = H) go out alone, everything
+  // that is Z wide rides with the next level.
   auto trans_fwd = [&](const bfvi_gtf_layout& g, int64_t rows, bool keep) -> int {
-    // the three layers that read the particles; then the two that read the hidden layers; then the std head
     if (int rc = lin(F(pl.zrows), Z, g.gate0_w, g.gate0_b, F(pl.h1), keep ? F(pl.h1T) : nullptr, rows, Z, H, 1)) return rc;
     if (int rc = lin(F(pl.zrows), Z, g.nonlin0_w, g.nonlin0_b, F(pl.h3), keep ? F(pl.h3T) : nullptr, rows, Z, H, 1)) return rc;
-    if (int rc = lin(F(pl.zrows), Z, g.lin_w, g.lin_b, F(pl.lin), nullptr, rows, Z, Z, 0)) return rc;
     if (int rc = flush()) return rc;
     if (int rc = lin(F(pl.h1), H, g.gate2_w, g.gate2_b, F(pl.g), nullptr, rows, H, Z, 0)) return rc;
     if (int rc = lin(F(pl.h3), H, g.nonlin2_w, g.nonlin2_b, F(pl.nl), keep ? F(pl.nlT) : nullptr, rows, H, Z, 0)) return rc;
+    if (int rc = lin(F(pl.zrows), Z, g.lin_w, g.lin_b, F(pl.lin), nullptr, rows, Z, Z, 0)) return rc;
     if (int rc = flush()) return rc;
     if (int rc = lin(F(pl.nl), Z, g.std_w, g.std_b, F(pl.as), nullptr, rows, Z, Z, 0)) return rc;
     return flush();
   };
-  // backward of one transition given d_as / d_g / d_lin / d_nl(partial) rows: input gradient dz
-  // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums),
+  // backward of one transition given d_as / d_g / d_lin / d_nl(partial) rows: input gradient dz (+ dz2, its
+  // second partial: summed by bwd_carry_kernel, so that the two H -> Z input gradients can share a launch)
+  // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums):
   // twelve GEMMs in three dependency levels
   auto trans_bwd = [&](const bfvi_gtf_layout& g, int64_t rows) -> int {
-    // level 1: everything that needs only the head gradients and the saved activations
+    // level 1 (Z wide): what needs only the head gradients and the saved activations
     if (int rc = dgrad(F(pl.d_as), g.std_w, F(pl.d_nl), F(pl.d_nlT), rows, Z, Z, true, nullptr, grads + g.nonlin2_b)) return rc;
-    if (int rc = dgrad(F(pl.d_g), g.gate2_w, F(pl.dh1), F(pl.dh1T), rows, Z, H, false, F(pl.h1), grads + g.gate0_b)) return rc;
     if (int rc = dgrad(F(pl.d_lin), g.lin_w, F(pl.dz), nullptr, rows, Z, Z, false, nullptr, nullptr)) return rc;
     if (int rc = wgrad(F(pl.d_linT), F(pl.zrowsT), rows, Z, Z, g.lin_w)) return rc;
     if (int rc = wgrad(F(pl.d_gT), F(pl.h1T), rows, Z, H, g.gate2_w)) return rc;
     if (int rc = wgrad(F(pl.d_asT), F(pl.nlT), rows, Z, Z, g.std_w)) return rc;
     if (int rc = flush()) return rc;
-    // level 2: needs the complete d_nl (+ transposed copy) and dh1
+    // level 2 (H wide): the two head -> hidden input gradients (d_nl is complete now)
+    if (int rc = dgrad(F(pl.d_g), g.gate2_w, F(pl.dh1), F(pl.dh1T), rows, Z, H, false, F(pl.h1), grads + g.gate0_b)) return rc;
     if (int rc = dgrad(F(pl.d_nl), g.nonlin2_w, F(pl.dh3), F(pl.dh3T), rows, Z, H, false, F(pl.h3), grads + g.nonlin0_b)) return rc;
-    if (int rc = dgrad(F(pl.dh1), g.gate0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
-    if (int rc = wgrad(F(pl.dh1T), F(pl.zrowsT), rows, H, Z, g.gate0_w)) return rc;
-    if (int rc = wgrad(F(pl.d_nlT), F(pl.h3T), rows, Z, H, g.nonlin2_w)) return rc;
     if (int rc = flush()) return rc;
-    // level 3: needs dh3; dz receives its third term
-    if (int rc = dgrad(F(pl.dh3), g.nonlin0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    // level 3 (Z wide): hidden -> particle input gradients and the remaining weight gradients
+    if (int rc = dgrad(F(pl.dh1), g.gate0_w, F(pl.dz), nullptr, rows, H, Z, true, nullptr, nullptr)) return rc;
+    if (int rc = dgrad(F(pl.dh3), g.nonlin0_w, F(pl.dz2), nullptr, rows, H, Z, false, nullptr, nullptr)) return rc;
+    if (int rc = wgrad(F(pl.dh1T), F(pl.zrowsT), rows, H, Z, g.gate0_w)) return rc;
     if (int rc = wgrad(F(pl.dh3T), F(pl.zrowsT), rows, H, Z, g.nonlin0_w)) return rc;
+    if (int rc = wgrad(F(pl.d_nlT), F(pl.h3T), rows, Z, H, g.nonlin2_w)) return rc;
     return flush();
   };
   auto step_params = [&](const bfvi_filter_args& f, int i) {
@@ -965,7 +968,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       sp.gb_std = grads + g.std_b; sp.gb_gate2 = grads + g.gate2_b;
       sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
     }
-    sp.dz = F(pl.dz);
+    sp.dz = F(pl.dz); sp.dz2 = F(pl.dz2);
     return sp;
   };
   // particles of step i_src as GEMM input rows (+ transposed copy)
@@ -2303,13 +2306,14 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
     const int64_t rows = (int64_t)B * f.n_particles;
     for (int i = 0; i < T; ++i) {
       if (i > 0) {
-        // three grouped launches: the layers that read the particles, the two hidden -> head layers, the std head
+        // three grouped, width-homogeneous launches: the two z -> hidden layers; the hidden -> head layers and the
+        // linear branch; the std head
         lg.add(zrows, Z, params + g.gate0_w, Z, params + g.gate0_b, hrows, H, rows, Z, H, 1);
         lg.add(zrows, Z, params + g.nonlin0_w, Z, params + g.nonlin0_b, hrows2, H, rows, Z, H, 1);
-        lg.add(zrows, Z, params + g.lin_w, Z, params + g.lin_b, linbuf, Z, rows, Z, Z, 0);
         if (int rc = lg.run(prec, st)) return rc;
         lg.add(hrows, H, params + g.gate2_w, H, params + g.gate2_b, gbuf, Z, rows, H, Z, 0);
         lg.add(hrows2, H, params + g.nonlin2_w, H, params + g.nonlin2_b, nlbuf, Z, rows, H, Z, 0);
+        lg.add(zrows, Z, params + g.lin_w, Z, params + g.lin_b, linbuf, Z, rows, Z, Z, 0);   // Z wide: rides with level 2
         if (int rc = lg.run(prec, st)) return rc;
         if (int rc = linear_tc(nlbuf, Z, params + g.std_w, Z, params + g.std_b, asbuf, Z, rows, Z, Z, 0, prec, st)) return rc;
       }

@@ -85,6 +85,7 @@ struct StepParams {
   float* d_nl; float* d_nlT;
   float* gb_std; float* gb_gate2; float* gb_lin; float* gb_nonlin2;   // bias gradient slots (Z each)
   const float* dz;             // (R, Z) gradient at the particles of the previous step
+  const float* dz2;            // nullable second partial of the same gradient (summed by bwd_carry_kernel)
 };
 
 __device__ __forceinline__ int gen_pass_time(int i, int T, int direction) {
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(128) bwd_carry_kernel(const __grid_constant__ 
     const int s = (int)(c / B), b = (int)(c % B);
     float cm = 0.f, cs = 0.f;
     for (int k = 0; k < K; ++k) {
-      const float d = p.dz[(c * K + k) * Z + zi];
+      const float d = p.dz[(c * K + k) * Z + zi] + (p.dz2 != nullptr ? p.dz2[(c * K + k) * Z + zi] : 0.f);
       cm += d;
       if (sampled) cs = fmaf(d, eps_at(a.noise, s, t, b, k, zi, T, B, K, Z), cs);
     }
