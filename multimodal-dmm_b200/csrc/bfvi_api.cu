@@ -560,11 +560,17 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
     static const int lag_env = [] { const char* e = getenv("BFVI_GEMM_LAG"); return e ? atoi(e) : 0; }();   // 0: kernel default
     if constexpr (BN <= 128 && SPLIT) {
       if (a_in_tmem && vec) {        // A operand from tensor memory (aligned 3xTF32 problems)
-        int ts_stages = (int)(budget / bfvi::tc::gemm_ts_stage_bytes<BN, SPLIT>());
+        // aligned epilogue rows leave through cp.async.bulk (one 128-byte line per row from a padded patch; the ring gives
+        // up the shared memory the larger patches need: 3 stages at 128-wide tiles, measured equal to 4);
+        // BFVI_GEMM_BULK=0 restores the per-thread 16-byte global stores
+        static const bool bulk = [] { const char* e = getenv("BFVI_GEMM_BULK"); return !e || atoi(e) != 0; }();
+        grp.bulk_store = bulk ? 1 : 0;
+        const size_t ts_budget = bulk ? (size_t)232448 - 1024 - 8 * 32 * 36 * sizeof(float) : budget;
+        int ts_stages = (int)(ts_budget / bfvi::tc::gemm_ts_stage_bytes<BN, SPLIT>());
         if (ts_stages > bfvi::tc::ts_max_stages(BN)) ts_stages = bfvi::tc::ts_max_stages(BN);
         if (ts_stages > ts_cap) ts_stages = ts_cap;
         if (ts_stages < 2) ts_stages = 2;
-        const size_t smem_ts = bfvi::tc::gemm_ts_smem_bytes<BN, SPLIT>(ts_stages);
+        const size_t smem_ts = bfvi::tc::gemm_ts_smem_bytes<BN, SPLIT>(ts_stages, bulk);
         auto kt = bfvi::tc::gemm_tf32_ts_kernel<BN, SPLIT, true>;
         cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
         kt<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem_ts, st>>>(grp, ts_stages, lag_env);

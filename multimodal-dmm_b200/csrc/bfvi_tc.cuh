@@ -427,8 +427,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
 // (A variant staging C through the patch for full-line float4 stores measured SLOWER — 81 -> 101 us on the
 // 57 600 x 64 -> 512 layer: the four epilogue warps are issue/latency-bound, not store-bound.)
 constexpr int kPatchLd = 33;      // floats per patch row (conflict-free row <-> column transposition)
+constexpr int kPatchLdBulk = 36;  // bulk-store mode: 144-byte rows (16-byte aligned, conflict-free 128-bit row writes)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, float (&v)[32], float* patch, int64_t wrow0,
-                                               int rows_valid, int cbase, int lane, bool fast_c) {
+                                               int rows_valid, int cbase, int lane, bool fast_c, bool bulk = false) {
+  if (bulk) {                                  // the bulk stores of the previous block have read the patch
+    bulk_wait_read();
+    __syncwarp();
+  }
   if (p.trans_out) {                           // lane = row: consecutive lanes add into consecutive addresses
     if (lane < rows_valid) {
       float* dt = p.C + (int64_t)cbase * p.ldc + wrow0 + lane;
@@ -476,6 +482,26 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, float (&v)[3
       for (int rr = 0; rr < 32; ++rr) cs += patch[rr * 33 + lane];
       atomicAdd(p.colsum + cbase + lane, cs);
       __syncwarp();
+    }
+    if (bulk && !p.accumulate) {
+      // thread = row: the row's 32 values go to the thread's own 144-byte patch row, then ONE 128-byte bulk copy
+      // takes the row to global memory (a full line, off the LSU path) instead of eight 16-byte stores that
+      // touch 32 lines per instruction
+      float4* s4 = reinterpret_cast<float4*>(patch + lane * kPatchLdBulk);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) s4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      fence_async_smem();
+      if (row_ok)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 128;" ::"l"(p.C + row * p.ldc + cbase),
+                     "r"(smem_u32(s4))
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      if (row_ok && p.Ct != nullptr) {
+        float* dt = p.Ct + (int64_t)cbase * p.ldct + row;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dt[(int64_t)j * p.ldct] = v[j];
+      }
+      return;
     }
     if (row_ok) {
       float4* d4 = reinterpret_cast<float4*>(p.C + row * p.ldc + cbase);
@@ -566,6 +592,7 @@ struct GemmGroup {
   int tiles_m[kMaxGroup], tiles_n[kMaxGroup];
   int chunks[kMaxGroup];                      // K chunks per tile (a short last split-K slice is zero padded)
   int n, total;
+  int bulk_store;                             // 1: aligned epilogue rows leave through cp.async.bulk from a padded patch (BFVI_GEMM_BULK)
 };
 #ifndef BFVI_EMU
 
@@ -1026,7 +1053,8 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid
   } else {
     // ================= epilogue warps: two per TMEM lane group 32 (warp % 4) .., alternating 32-column blocks
     const int wq = warp & 3, half = (warp - kMmaWarp - 1) >> 2;
-    float* patch = patches + (warp - kMmaWarp - 1) * (32 * kPatchLd);
+    const bool bulk = grp.bulk_store != 0;
+    float* patch = patches + (warp - kMmaWarp - 1) * (32 * (bulk ? kPatchLdBulk : kPatchLd));
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int a = lt % kAcc;
       const TileInfo ti = decode_tile(grp, (int)blockIdx.x + lt * (int)gridDim.x, BN);
@@ -1049,7 +1077,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid
           released = true;
         }
 #ifndef BFVI_DBG_NO_EPI_STORE
-        epilogue_block(p, v, patch, wrow0, rows_valid, ti.col0 + c, lane, fast_c);
+        epilogue_block(p, v, patch, wrow0, rows_valid, ti.col0 + c, lane, fast_c, bulk);
 #else
         if (v[0] == 123.456f) patch[lane] = v[1];
 #endif
@@ -1060,6 +1088,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) gemm_tf32_ts_kernel(const __grid
         if (lane == 0) mbar_arrive(&tempty_bar[a]);
       }
     }
+    if (bulk) bulk_wait_read();                           // shared memory stays valid until the last rows are read
   }
   tc_fence_before();
   __syncthreads();
@@ -1101,7 +1130,9 @@ inline size_t gemm_v2_smem_bytes(int stages) { return gemm_v2_stage_bytes<BN, SP
 template <int BN, bool SPLIT>
 inline size_t gemm_ts_stage_bytes() { return (size_t)(kBM + (SPLIT ? 2 : 1) * BN) * kBK * sizeof(float); }
 template <int BN, bool SPLIT>
-inline size_t gemm_ts_smem_bytes(int stages) { return gemm_ts_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024 + 8 * 32 * 33 * sizeof(float); }
+inline size_t gemm_ts_smem_bytes(int stages, bool bulk = false) {
+  return gemm_ts_stage_bytes<BN, SPLIT>() * (size_t)stages + 1024 + 8 * 32 * (bulk ? 36 : 33) * sizeof(float);
+}
 template <int BN, bool SPLIT>
 inline size_t gemm_p_smem_bytes(int stages) { return gemm_v2_smem_bytes<BN, SPLIT>(stages) + 8 * 32 * 33 * sizeof(float); }
 
