@@ -1,26 +1,31 @@
 """bench.py — BFVI ELBO fwd+bwd sequence-timesteps/sec (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1]
+                    [--batch B] [--scaling weak|strong] [--precision tf32|tf32x3]
 
 One "step" = MultiDMM.step(...) + (loss / sum(lengths)).backward() exactly as
-trainer.py:237-243 drives it, on one batch of synthetic spirals-shaped data.
+trainer.py:237-243 drives it, on one batch of synthetic data of the named shape.
 
-Workload at N GPUs (weak scaling: per-GPU batch fixed): BASELINE.json configs[1]
-"C2": spirals model (M=2, D=1, Z=5, H=20; spirals.py:44-51), T=100, B=4096 per GPU,
-50 % uniformly missing timesteps per sequence and modality in inputs AND targets
-(corrupt_(0.5,'uniform'), datasets/multiseq.py:252-267), + burst_delete(0.1) on the
-inputs, rec_mults=1.0, kld_mult=1.0, train_particles=25, match_particles=50,
-in-kernel Philox noise.  One NCCL all-reduce of the flat gradient per step for N>1.
+Workloads (BASELINE.json `configs`, made concrete in SURVEY.md §8d):
+  c3 (default) the configuration the metric's "1/2/4/8 B200" is quoted on: M=8 Gaussian modalities, D=16,
+               Z=64, H=512, T=1000, K=25, K_match=50, x ~ N(0,1), rec_mults = 1/(D*M), in-kernel Philox
+               noise; the named global batch is 65 536 = 8 192 per GPU on the 8-GPU box.  At N GPUs the run is
+               the N-GPU SHARD of that job (weak scaling, per-GPU batch fixed, see C3.batch); the per-GPU
+               batch actually timed is stated in config.workload.
+  c2           spirals model (M=2, D=1, Z=5, H=20), T=100, B=4096 per GPU, 50 % uniformly missing + burst.
+  c1           spirals defaults (spirals.py:31-50): T=100, B=100, burst_delete(0.1).
+One NCCL all-reduce of the flat gradient per step for N>1 (no collective inside the step).
 
-Printed JSON (one line, rank 0): value = device-timed throughput with inputs
-resident in HBM; e2e = the same through the public API from PINNED HOST buffers
-(H2D of every step's inputs and a D2H read of every step's loss inside the timed region,
-the loss of step i is read while step i+1 runs, so the GPU never waits for the host);
-roofline / roofline_fp32 for the dominant kernel from CUDA-event phase timing;
-cpu_baseline = the oracle port of the reference timed on this box's host cores.
+Printed JSON (one line, rank 0): value = device-timed throughput with inputs resident in HBM; e2e = the same
+through the public API from PINNED HOST buffers (H2D of every step's inputs and targets and a D2H read of
+every step's loss inside the timed region; the loss of step i is read while step i+1 runs); roofline =
+algorithmic FLOPs / measured time against the measured tensor peak (c3) or the FP32-FFMA
+bound of the dominant kernel (c2/c1); cpu_baseline = the oracle port of the reference timed on this box's
+host cores on a bounded sample.
 
---impl reference: the reference algorithm (oracle/bfvi_oracle.py, a PyTorch-CPU
-port; the Python reference itself cannot travel to the GPU box) on all host cores.
+--impl reference: the reference algorithm (oracle/bfvi_oracle.py, a PyTorch-CPU port pinned against the
+unmodified reference; the Python reference itself cannot travel to the GPU box) on all host cores, on a
+bounded sample of the SAME workload; it prints the same `config` object as our arm.
 """
 import argparse
 import ctypes as C
@@ -37,19 +42,13 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-MODS, DIMS, Z_DIM, H_DIM = ['spiral-x', 'spiral-y'], [1, 1], 5, 20
-T_MAX, B_PER_GPU = 100, 4096
-K_TRAIN, K_MATCH = 25, 50
 METRIC = 'bfvi_elbo_fwd_bwd_seq_timesteps_per_sec'
 UNIT = 'seq-timesteps/s'
-
-# algorithmic work per sequence-timestep
-F_GTF = 8 * Z_DIM * H_DIM + 4 * Z_DIM * Z_DIM                       # 900
-N_SETS = 3                                                          # {x,y}, {x}, {y}
+KLD_MULT = 1.0
 
 
 # ----------------------------------------------------------------------------
-# synthetic C2 batch (shape and missingness of datasets/spirals.py + multiseq.py)
+# workloads
 # ----------------------------------------------------------------------------
 def spirals_batch(b_dim, t_max, seed):
     """Noisy 2-D spirals like datasets/spirals.py:47-84 (vectorised restatement)."""
@@ -69,33 +68,76 @@ def spirals_batch(b_dim, t_max, seed):
             'spiral-y': y[:, :, None].astype(np.float32)}, rng
 
 
-def make_c2_batch(b_dim, t_max=T_MAX, seed=1):
+def _burst(inp, rng, t_max, b_dim, frac=0.1):
+    """burst_delete(frac): one burst per sequence per modality (datasets/multiseq.py:428-434)."""
+    burst = int(frac * t_max)
+    start = rng.randint(t_max, size=b_dim)
+    tt = np.arange(t_max)[:, None]
+    inp[(tt >= start[None, :]) & (tt < np.minimum(start + burst, t_max)[None, :]), 0] = np.nan
+
+
+def make_c2_batch(b_dim, t_max=100, seed=1):
     data, rng = spirals_batch(b_dim, t_max, seed)
     targets, inputs = {}, {}
-    n_del, burst = int(0.5 * t_max), int(0.1 * t_max)
-    for m in MODS:
+    n_del = int(0.5 * t_max)
+    for m in C2.mods:
         tgt = data[m].copy()
         # corrupt_(0.5, 'uniform'): exactly n_del timesteps per sequence, no replacement
         order = np.argsort(rng.rand(t_max, b_dim), axis=0)[:n_del]
         tgt[order, np.arange(b_dim)[None, :], 0] = np.nan
         inp = tgt.copy()
-        # burst_delete(0.1): one burst per sequence per modality (multiseq.py:428-434)
-        start = rng.randint(t_max, size=b_dim)
-        tt = np.arange(t_max)[:, None]
-        inp[(tt >= start[None, :]) & (tt < np.minimum(start + burst, t_max)[None, :]), 0] = np.nan
+        _burst(inp, rng, t_max, b_dim)
         targets[m], inputs[m] = torch.from_numpy(tgt), torch.from_numpy(inp)
-    lengths = [t_max] * b_dim
-    mask = torch.ones(t_max, b_dim, 1, dtype=torch.bool)
-    return inputs, targets, mask, lengths
+    return inputs, targets, torch.ones(t_max, b_dim, 1, dtype=torch.bool), [t_max] * b_dim
 
 
-def workload_name(b_dim):
-    return ('C2: spirals BFVI step, M=2 D=1 Z=5 H=20, T=%d, B=%d per GPU, 50%% uniform missing + 10%% burst, '
-            'K=%d, K_match=%d' % (T_MAX, b_dim, K_TRAIN, K_MATCH))
+def make_c1_batch(b_dim, t_max=100, seed=1):
+    data, rng = spirals_batch(b_dim, t_max, seed)
+    targets, inputs = {}, {}
+    for m in C2.mods:
+        inp = data[m].copy()
+        _burst(inp, rng, t_max, b_dim)
+        targets[m], inputs[m] = torch.from_numpy(data[m].copy()), torch.from_numpy(inp)
+    return inputs, targets, torch.ones(t_max, b_dim, 1, dtype=torch.bool), [t_max] * b_dim
 
 
-REC_MULTS = {m: 1.0 for m in MODS}          # (1/D)/M * 1/(1-0.5), spirals.py:64-73
-KLD_MULT = 1.0
+def make_c3_batch(b_dim, t_max=1000, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    x = {m: torch.randn(t_max, b_dim, C3.dims[0], generator=g) for m in C3.mods}
+    # targets are the same values in their own buffers (the trainer passes two dicts, trainer.py:231-237)
+    return x, {m: v.clone() for m, v in x.items()}, torch.ones(t_max, b_dim, 1, dtype=torch.bool), [t_max] * b_dim
+
+
+class Workload(object):
+    def __init__(self, key, mods, dims, z, h, t_max, batch, make, rec, desc, ref_sample, k_train=25, k_match=50):
+        self.key, self.mods, self.dims, self.z, self.h, self.t_max, self.batch = key, mods, dims, z, h, t_max, batch
+        self.make, self.rec, self.desc, self.ref_sample = make, rec, desc, ref_sample
+        self.k_train, self.k_match = k_train, k_match
+        m = len(mods)
+        f_gtf = 8 * z * h + 4 * z * z
+        f_enc = sum(2 * h * (d + 2 * z) for d in dims)
+        f_dec = sum(2 * h * (z + 2 * d) for d in dims)
+        # SURVEY.md §8d: F_fwd = (1+M)(K+2) F_gtf + sum F_enc + 4 sum F_dec ; F_step = 3 F_fwd
+        self.flops_per_seq_ts = 3 * ((1 + m) * (k_train + 2) * f_gtf + f_enc + 4 * f_dec)
+        self.bytes_per_seq_ts = 2 * 4 * sum(dims)
+        self.f_gtf, self.n_sets = f_gtf, (1 + m if m > 1 else 1)
+
+    def name(self, b_dim):
+        return self.desc % {'B': b_dim}
+
+
+C2 = Workload('c2', ['spiral-x', 'spiral-y'], [1, 1], 5, 20, 100, 4096, make_c2_batch, 1.0,
+              'C2: spirals BFVI step, M=2 D=1 Z=5 H=20, T=100, B=%(B)d per GPU, 50%% uniform missing + 10%% burst, '
+              'K=25, K_match=50', (896, 100))
+C1 = Workload('c1', ['spiral-x', 'spiral-y'], [1, 1], 5, 20, 100, 100, make_c1_batch, 0.5,
+              'C1: spirals.py defaults, M=2 D=1 Z=5 H=20, T=100, B=%(B)d, burst_delete(0.1), K=25, K_match=50',
+              (100, 100))
+# per-GPU batch of the c3 line: the 8-GPU shard of the named job is 8 192 sequences; bfvi_step_fwd_bwd walks it in
+# batch tiles (workspace bounded), so it runs as ONE step() call
+C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 8192, make_c3_batch, 1.0 / (16 * 8),
+              'C3: scaled MDMM BFVI step, M=8 D=16 Z=64 H=512, T=1000, K=25, K_match=50, B=%(B)d per GPU '
+              '(BASELINE: global batch 65536 = 8192 per GPU on 8 B200), N(0,1) data, Philox noise', (24, 100))
+WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3}
 
 
 # ----------------------------------------------------------------------------
@@ -140,53 +182,79 @@ class ClockSampler(object):
                 'samples': len(sm)}
 
 
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def config_of(wl, b_dim, world, scaling):
+    """The `config` object: IDENTICAL in our arm and in --impl reference (which times a bounded sample
+    of the same workload and says so in its cpu_baseline.sample)."""
+    return {'workload': wl.name(b_dim), 'global_batch': b_dim * world, 'seq_len': wl.t_max,
+            'parallelism': 'dp%d' % world, 'scaling': scaling,
+            'reference_arm_sample': 'CPU arm (--impl reference / cpu_baseline) times B=%d, T=%d of this model '
+                                    'and data generator on all host cores' % wl.ref_sample,
+            'l2': '256 MiB flush write between timed steps; the step streams a workspace far larger than the '
+                  '126 MB L2'}
+
+
 # ----------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ----------------------------------------------------------------------------
-def oracle_step_time(b_dim, steps, warmup, threads):
+def oracle_step_time(wl, b_dim, t_max, steps, warmup, threads):
+    """Mean seconds per step + seq-timesteps per step of the oracle port at (b_dim, t_max)."""
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import bfvi_oracle as bo
     torch.set_num_threads(threads)
-    inputs, targets, mask, lengths = make_c2_batch(b_dim, seed=1)
-    params = bo.init_params(MODS, DIMS, h_dim=H_DIM, z_dim=Z_DIM, seed=1)
+    inputs, targets, mask, lengths = wl.make(b_dim, t_max, 1)
+    rec = {m: wl.rec for m in wl.mods}
+    params = bo.init_params(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, seed=1)
     for p in params.values():
         p.requires_grad_(True)
-    orc = bo.OracleDMM(MODS, DIMS, params, h_dim=H_DIM, z_dim=Z_DIM, draw=bo.RandomDraw(seed=3))
+    orc = bo.OracleDMM(wl.mods, wl.dims, params, h_dim=wl.h, z_dim=wl.z, draw=bo.RandomDraw(seed=3))
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        loss = orc.step(inputs, mask, KLD_MULT, REC_MULTS, targets=targets, lengths=lengths,
-                        train_particles=K_TRAIN, match_particles=K_MATCH)
+        loss = orc.step(inputs, mask, KLD_MULT, rec, targets=targets, lengths=lengths,
+                        train_particles=wl.k_train, match_particles=wl.k_match)
         (loss / sum(lengths)).backward()
         for p in params.values():
             p.grad = None
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return float(np.mean(times)), b_dim * T_MAX
+    return float(np.mean(times)), b_dim * t_max
 
 
-def run_reference(args):
+def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = os.cpu_count() or 1
-    total = args.steps + args.warmup
-    # bounded sample: ~12 s/step at B=4096 on 8 cores; keep the whole run to a few minutes
-    b_dim = B_PER_GPU if total <= 6 else max(128, int(B_PER_GPU * 6 / total) // 128 * 128)
-    sec, seq_ts = oracle_step_time(b_dim, args.steps, args.warmup, cores)
+    b_ref, t_ref = wl.ref_sample
+    sec, seq_ts = oracle_step_time(wl, b_ref, t_ref, args.steps, args.warmup, cores)
     value = seq_ts / sec
-    sample = 'C2 workload at B=%d, T=%d (K=%d particles), %d timed steps' % (b_dim, T_MAX, K_TRAIN, args.steps)
+    b_dim = per_gpu_batch(args, wl, world)
+    sample = ('oracle port of the reference on %d torch threads: %s workload at B=%d, T=%d (K=%d particles), '
+              '%d warm-up + %d timed steps' % (cores, wl.key.upper(), b_ref, t_ref, wl.k_train, args.warmup, args.steps))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32',
-        'data': 'synthetic',
-        'config': {'workload': workload_name(B_PER_GPU), 'global_batch': B_PER_GPU * args.gpus, 'seq_len': T_MAX,
-                   'parallelism': 'cpu', 'reference_sample_batch': b_dim},
+        'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'fp32',
+        'data': 'synthetic', 'config': config_of(wl, b_dim, world, args.scaling),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
+
+
+def per_gpu_batch(args, wl, world):
+    b = args.batch if args.batch else wl.batch
+    if args.scaling == 'strong':
+        b = max(1, b // world)
+    return b
 
 
 # ----------------------------------------------------------------------------
@@ -195,14 +263,20 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--batch', type=int, default=B_PER_GPU, help='sequences per GPU')
+    ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='sequences per GPU (weak) / in total (strong); 0 = workload default')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
+    ap.add_argument('--precision', default='tf32', choices=['tf32', 'tf32x3'],
+                    help='GEMM operand precision of the large-dim family (c3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the end-to-end loop (0 = min(steps, 5))')
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
     if args.impl == 'reference':
-        return run_reference(args)
+        return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
 
     import multimodal_dmm_b200.models as models
@@ -222,14 +296,19 @@ def main():
 
     # ---- model + data (identical weights on every rank; per-rank data shard) ------
     torch.manual_seed(1)
-    model = models.MultiDMM(MODS, DIMS, h_dim=H_DIM, z_dim=Z_DIM, device=dev).train()
-    b_dim = args.batch
-    inputs_h, targets_h, mask_h, lengths = make_c2_batch(b_dim, seed=1 + rank)
+    model = models.MultiDMM(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, device=dev).train()
+    large = wl.key == 'c3'
+    if large:
+        model.precision = args.precision
+    b_dim = per_gpu_batch(args, wl, world)
+    t_max = wl.t_max
+    inputs_h, targets_h, mask_h, lengths = wl.make(b_dim, t_max, (1234 if large else 1) + rank)
     pin = lambda d: {k: v.pin_memory() for k, v in d.items()}
     inputs_h, targets_h = pin(inputs_h), pin(targets_h)
     mask_d = mask_h.to(dev)
     inputs_d = {k: v.to(dev) for k, v in inputs_h.items()}
     targets_d = {k: v.to(dev) for k, v in targets_h.items()}
+    rec = {m: wl.rec for m in wl.mods}
     n_global = float(sum(lengths) * world)          # normalise by the GLOBAL sum(lengths)
     model.b_offset = rank * b_dim
     if world > 1:
@@ -238,7 +317,8 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def one_step(inp, tgt):
-        loss = model.step(inp, mask_d, KLD_MULT, REC_MULTS, targets=tgt, lengths=lengths)
+        loss = model.step(inp, mask_d, KLD_MULT, rec, targets=tgt, lengths=lengths,
+                          train_particles=wl.k_train, match_particles=wl.k_match)
         (loss / n_global).backward()
         for p in model.parameters():
             p.grad = None
@@ -267,158 +347,100 @@ def main():
     barrier()
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    dispatch = _lib.load().last_dispatch()
 
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H loss ----------
+    # A training loop that does not stall the GPU on the loss: every step copies its batch from pinned host
+    # memory (same stream, ahead of the step) and copies its loss to pinned host memory asynchronously; the
+    # host reads step i's loss while step i+1 runs.  Every step still pays its H2D copy and its D2H loss read
+    # inside the timed region.
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 5)
     h2d = sum(v.numel() * 4 for v in inputs_h.values()) + sum(v.numel() * 4 for v in targets_h.values())
-    for _ in range(2):
-        one_step({k: v.to(dev, non_blocking=True) for k, v in inputs_h.items()},
-                 {k: v.to(dev, non_blocking=True) for k, v in targets_h.items()}).item()
+    del inputs_d, targets_d                           # the e2e loop owns its device copies
+    one_step({k: v.to(dev, non_blocking=True) for k, v in inputs_h.items()},
+             {k: v.to(dev, non_blocking=True) for k, v in targets_h.items()}).item()
     barrier()
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    # A training loop that does not stall the GPU on the loss: every step copies its batch from pinned host
-    # memory (same stream, ahead of the step) and copies its loss to pinned host memory asynchronously; the
-    # host reads step i's loss while step i+1 runs.  Every step still pays its H2D copy and its D2H loss read
-    # inside the timed region.  (A per-step .item() leaves the GPU idle for ~0.65 ms of launch latency per
-    # step; staging the next batch on a second stream was measured and gained nothing over this.)
     main_stream = torch.cuda.current_stream(dev)
     loss_pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
     loss_ready = [torch.cuda.Event() for _ in range(2)]
     loss_host = None
-    for i in range(args.steps):
+    for i in range(e2e_steps):
         j = i % 2
         inp = {k: v.to(dev, non_blocking=True) for k, v in inputs_h.items()}
         tgt = {k: v.to(dev, non_blocking=True) for k, v in targets_h.items()}
         loss = one_step(inp, tgt)
         loss_pinned[j].copy_(loss.detach(), non_blocking=True)
         loss_ready[j].record(main_stream)
+        del inp, tgt
         if i > 0:                                      # D2H read of the PREVIOUS step's result
             loss_ready[1 - j].synchronize()
             loss_host = float(loss_pinned[1 - j])
-    loss_ready[(args.steps - 1) % 2].synchronize()
-    loss_host = float(loss_pinned[(args.steps - 1) % 2])
+    loss_ready[(e2e_steps - 1) % 2].synchronize()
+    loss_host = float(loss_pinned[(e2e_steps - 1) % 2])
     e1.record()
     barrier()
-    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / args.steps
-
-    if os.environ.get('BFVI_BENCH_PROBE'):             # development aid: where does the e2e loop lose time?
-        def loop(fn, n):
-            torch.cuda.synchronize()
-            w0 = time.perf_counter()
-            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a0.record()
-            for _ in range(n):
-                fn()
-            a1.record()
-            torch.cuda.synchronize()
-            return a0.elapsed_time(a1) / n, (time.perf_counter() - w0) * 1e3 / n
-        print('probe device inputs, no flush, no sync   (gpu ms, wall ms):', loop(lambda: one_step(inputs_d, targets_d), args.steps), file=sys.stderr)
-        print('probe device inputs + .item() each step  (gpu ms, wall ms):', loop(lambda: one_step(inputs_d, targets_d).item(), args.steps), file=sys.stderr)
-        hs = time.perf_counter()
-        for _ in range(args.steps):
-            model.step(inputs_d, mask_d, KLD_MULT, REC_MULTS, targets=targets_d, lengths=lengths)
-        print('probe host time of step() enqueue only (ms):', (time.perf_counter() - hs) * 1e3 / args.steps, file=sys.stderr)
-        torch.cuda.synchronize()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / e2e_steps
+    inputs_d = {k: v.to(dev) for k, v in inputs_h.items()}
+    targets_d = {k: v.to(dev) for k, v in targets_h.items()}
 
     # ---- max over ranks ------------------------------------------------------------
     if dist is not None:
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t[0].item(), t[1].item()
-    seq_ts_global = b_dim * T_MAX * world
+    seq_ts_global = b_dim * t_max * world
+    peaks = load_peaks()
 
-    # ---- dominant-kernel roofline from CUDA-event phase timing (rank 0) -------------
-    roofline = roofline_fp32 = phases = None
-    if rank == 0:
-        lib = _lib.load()
-        model._ensure_flat()
-        fx_args, keep = build_step_args(model, inputs_d, targets_d, mask_d)
-        nbytes = C.c_size_t(0)
-        lib.call('bfvi_step_workspace', C.byref(model._cmodel), C.byref(fx_args), C.byref(nbytes))
-        ws = model._workspace(nbytes.value)
-        grads = torch.empty_like(model._flat)
-        loss = torch.empty((), device=dev)
-        acc = np.zeros(len(_lib.PHASES))
-        reps = max(3, min(args.steps, 10))
-        phase_ms = (C.c_float * len(_lib.PHASES))()
-        for i in range(reps + 1):
-            flush.fill_(float(i))
-            lib.call('bfvi_step_profile', C.byref(model._cmodel), _lib.ptr(model._flat), _lib.ptr(grads),
-                     C.byref(fx_args), _lib.ptr(ws), C.c_size_t(nbytes.value), _lib.ptr(loss), phase_ms,
-                     C.c_void_p(torch.cuda.current_stream().cuda_stream))
-            if i > 0:
-                acc += np.array(list(phase_ms))
-        acc /= reps
-        phases = {n: round(float(v), 4) for n, v in zip(_lib.PHASES, acc)}
-        dom = max(phases, key=phases.get)
-        chain_steps = N_SETS * b_dim * (T_MAX - 1)
-        # algorithmic work of the dominant kernel per launch (recomputation NOT counted)
-        flops = {'filter_s_flt_bwd': 2 * K_TRAIN * F_GTF, 'filter_s_flt_fwd': K_TRAIN * F_GTF}.get(dom, F_GTF)
-        flops *= chain_steps
-        # algorithmic bytes per launch: saved infer/prior (+ d_prior in backward) and the
-        # observation experts of each chain set (2 sets of 1, 1 set of 2 modalities)
-        per_chain = 4 * Z_DIM * 4 + (2 * Z_DIM * 4 if dom.endswith('bwd') else 0)
-        expert_bytes = (2 * Z_DIM * 4 + 1) * 4 * b_dim * T_MAX * (2 if dom.endswith('bwd') else 1)
-        bytes_alg = per_chain * N_SETS * b_dim * T_MAX + expert_bytes
-        dur = phases[dom] * 1e-3
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    roofline = roofline_fp32 = phases = kernel_probe = None
+    if rank == 0 and large:
+        # whole step: algorithmic FLOPs (recomputation NOT counted) over the device-timed step
+        # against the measured sustained dense BF16 tensor peak (TF32 operands run at half that rate, so a
+        # perfect TF32 step reads 0.5)
+        peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        ach = wl.flops_per_seq_ts * b_dim * t_max / (ms * 1e-3) / 1e12
         traffic = None
-        try:       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full)
-            prof = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel.json')))
-            if dom == 'filter_s_flt_bwd' and b_dim == B_PER_GPU:
-                traffic = prof['dram_bytes_read'] + prof['dram_bytes_write']
+        try:
+            prof = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dominant_kernel.json')))
+            traffic = prof.get('dram_bytes_per_launch')
+            kernel_probe = prof
         except Exception:
             pass
-        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': bytes_alg / dur / 1e9, 'peak': hbm_peak,
-                    'unit': 'GB/s', 'frac': bytes_alg / dur / 1e9 / hbm_peak, 'traffic': traffic,
-                    'algorithmic_bytes': bytes_alg,
-                    'peak_source': 'measured' if peaks else 'fallback',
-                    'note': 'kernel is FP32-FFMA bound (Z=5,H=20 cannot feed tcgen05); see roofline_fp32'}
-        # FP32 FFMA peak measured live (register-only FMA chains on every SM)
-        probe_out = torch.zeros(1, device=dev)
-        iters, blocks = 20000, 148 * 16
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        lib.call('bfvi_ffma_probe', _lib.ptr(probe_out), iters, blocks, st)
-        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        p0.record()
-        lib.call('bfvi_ffma_probe', _lib.ptr(probe_out), iters, blocks, st)
-        p1.record()
-        torch.cuda.synchronize()
-        ffma_peak = blocks * 256 * iters * 16 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
-        roofline_fp32 = {'bound': 'fp32_ffma', 'kernel': dom, 'achieved': flops / dur / 1e12,
-                         'peak': ffma_peak, 'unit': 'TFLOP/s', 'frac': flops / dur / 1e12 / ffma_peak,
-                         'peak_source': 'measured live (bfvi_ffma_probe)',
-                         'kernel_share_of_step': phases[dom] / max(sum(phases.values()), 1e-9)}
+        roofline = {'bound': 'tensor', 'kernel': 'whole step (launch sequence; dominant: fused GTF row-tile kernels)',
+                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
+                    'algorithmic_flops_per_seq_ts': wl.flops_per_seq_ts,
+                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)'}
+    if rank == 0 and not large:
+        roofline, roofline_fp32, phases = small_roofline(model, wl, inputs_d, targets_d, mask_d, rec, b_dim, t_max,
+                                                         flush, peaks, args)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sec, seq_ts = oracle_step_time(B_PER_GPU, 1, 1, cores)
+        b_ref, t_ref = wl.ref_sample
+        sec, seq_ts = oracle_step_time(wl, b_ref, t_ref, 3, 1, cores)
         cpu_baseline = {'value': seq_ts / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                        'sample': 'oracle port of the reference, 1 warm-up + 1 timed step of the full '
-                                  'C2 batch (B=%d, T=%d) on %d torch threads' % (B_PER_GPU, T_MAX, cores)}
+                        'sample': 'oracle port of the reference, 1 warm-up + 3 timed steps of the %s workload at '
+                                  'B=%d, T=%d on %d torch threads' % (wl.key.upper(), b_ref, t_ref, cores)}
 
     if rank == 0:
         out = {
             'metric': METRIC, 'value': seq_ts_global / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': workload_name(b_dim),
-                       'global_batch': b_dim * world, 'seq_len': T_MAX,
-                       'parallelism': 'dp%d' % world,
-                       'l2': '256 MiB flush write between timed steps; the step itself streams a '
-                             '>500 MB workspace (> 126 MB L2)'},
+            'scaling': args.scaling, 'vs_baseline': None,
+            'dtype': ('tf32 operands, fp32 accumulate (fp16 weight-gradient operands)' if args.precision == 'tf32'
+                      else 'tf32x3 (fp32-class), fp32 accumulate') if large else 'fp32',
+            'data': 'synthetic',
+            'config': config_of(wl, b_dim, world, args.scaling),
             'clocks': clocks,
-            'e2e': {'value': seq_ts_global / (ms_e2e * 1e-3), 'unit': UNIT, 'loop': 'loss read one step late (no per-step GPU stall)',
+            'e2e': {'value': seq_ts_global / (ms_e2e * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
+                    'loop': 'loss read one step late (no per-step GPU stall)',
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
             'gpu_launches': launches,
             'roofline': roofline, 'roofline_fp32': roofline_fp32, 'phase_ms': phases,
+            'kernel_probe': kernel_probe, 'dispatch': dispatch[:24],
             'cpu_baseline': cpu_baseline,
         }
         print(json.dumps(out))
@@ -426,23 +448,86 @@ def main():
         dist.destroy_process_group()
 
 
-def build_step_args(model, inputs, targets, mask):
+def small_roofline(model, wl, inputs_d, targets_d, mask_d, rec, b_dim, t_max, flush, peaks, args):
+    """Dominant-kernel roofline of the small-dim family from CUDA-event phase timing (bfvi_step_profile)."""
+    from multimodal_dmm_b200 import _lib
+    dev = mask_d.device
+    lib = _lib.load()
+    model._ensure_flat()
+    fx_args, keep = build_step_args(model, wl, inputs_d, targets_d, mask_d, rec)
+    nbytes = C.c_size_t(0)
+    lib.call('bfvi_step_workspace', C.byref(model._cmodel), C.byref(fx_args), C.byref(nbytes))
+    ws = model._workspace(nbytes.value)
+    grads = torch.empty_like(model._flat)
+    loss = torch.empty((), device=dev)
+    acc = np.zeros(len(_lib.PHASES))
+    reps = max(3, min(args.steps, 10))
+    phase_ms = (C.c_float * len(_lib.PHASES))()
+    for i in range(reps + 1):
+        flush.fill_(float(i))
+        lib.call('bfvi_step_profile', C.byref(model._cmodel), _lib.ptr(model._flat), _lib.ptr(grads),
+                 C.byref(fx_args), _lib.ptr(ws), C.c_size_t(nbytes.value), _lib.ptr(loss), phase_ms,
+                 C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if i > 0:
+            acc += np.array(list(phase_ms))
+    acc /= reps
+    phases = {n: round(float(v), 4) for n, v in zip(_lib.PHASES, acc)}
+    dom = max(phases, key=phases.get)
+    chain_steps = wl.n_sets * b_dim * (t_max - 1)
+    # algorithmic work of the dominant kernel per launch (recomputation NOT counted)
+    flops = {'filter_s_flt_bwd': 2 * wl.k_train * wl.f_gtf, 'filter_s_flt_fwd': wl.k_train * wl.f_gtf}.get(dom, wl.f_gtf)
+    flops *= chain_steps
+    dur = phases[dom] * 1e-3
+    # FP32 FFMA peak measured live (register-only FMA chains on every SM)
+    probe_out = torch.zeros(1, device=dev)
+    iters, blocks = 20000, 148 * 16
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    lib.call('bfvi_ffma_probe', _lib.ptr(probe_out), iters, blocks, st)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    lib.call('bfvi_ffma_probe', _lib.ptr(probe_out), iters, blocks, st)
+    p1.record()
+    torch.cuda.synchronize()
+    ffma_peak = blocks * 256 * iters * 16 * 2 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+    traffic = None
+    try:       # dram__bytes_read.sum + dram__bytes_write.sum of the same launch (ncu --set full)
+        prof = json.load(open(os.path.join(ROOT, 'profiles', 'r1_dominant_kernel.json')))
+        if dom == 'filter_s_flt_bwd' and b_dim == C2.batch and wl.key == 'c2':
+            traffic = prof['dram_bytes_read'] + prof['dram_bytes_write']
+    except Exception:
+        pass
+    # the binding roofline of this family is FP32 issue (5x20 matrices cannot feed tcgen05; HBM traffic is
+    # 0.6 % of DRAM throughput): the contract object carries that bound
+    roofline = {'bound': 'fp32_ffma', 'kernel': dom, 'achieved': flops / dur / 1e12, 'peak': ffma_peak,
+                'unit': 'TFLOP/s', 'frac': flops / dur / 1e12 / ffma_peak, 'traffic': traffic,
+                'peak_source': 'measured live (bfvi_ffma_probe: register-only FFMA chains on every SM)',
+                'kernel_share_of_step': phases[dom] / max(sum(phases.values()), 1e-9)}
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    bytes_alg = wl.bytes_per_seq_ts * b_dim * t_max
+    step_s = sum(phases.values()) * 1e-3
+    roofline_hbm = {'bound': 'hbm', 'kernel': 'whole step', 'achieved': bytes_alg / step_s / 1e9, 'peak': hbm_peak,
+                    'unit': 'GB/s', 'frac': bytes_alg / step_s / 1e9 / hbm_peak,
+                    'note': 'SURVEY 8d algorithmic bytes (inputs + targets): not the bound of this family'}
+    return roofline, roofline_hbm, phases
+
+
+def build_step_args(model, wl, inputs, targets, mask, rec):
     """bfvi_step_args for the profiling call (same values MultiDMM.step passes)."""
     from multimodal_dmm_b200 import _lib
     a = _lib.StepArgs()
     keep = []
     t_max, b_dim = mask.shape[:2]
     a.T, a.B = t_max, b_dim
-    for i, m in enumerate(MODS):
+    for i, m in enumerate(wl.mods):
         x, y = inputs[m].contiguous(), targets[m].contiguous()
         keep += [x, y]
-        a.inputs[i], a.targets[i], a.rec_mults[i] = x.data_ptr(), y.data_ptr(), REC_MULTS[m]
+        a.inputs[i], a.targets[i], a.rec_mults[i] = x.data_ptr(), y.data_ptr(), rec[m]
     mk = mask.reshape(t_max, b_dim).to(torch.uint8).contiguous()
     keep.append(mk)
     a.seq_mask, a.kld_mult, a.uni_loss = mk.data_ptr(), KLD_MULT, 1
     a.f_mode, a.s_mode = _lib.MODE_CODES['bfilter'], _lib.MODE_CODES['fsmooth']
     a.f_mult, a.s_mult, a.match_mult = 0.5, 0.5, 0.01
-    a.train_particles, a.match_particles, a.sample, a.sample_init = K_TRAIN, K_MATCH, 1, 0
+    a.train_particles, a.match_particles, a.sample, a.sample_init = wl.k_train, wl.k_match, 1, 0
     a.seed, a.b_offset, a.match_count = 2024, 0, -1.0
     return a, keep
 

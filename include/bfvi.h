@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BFVI_VERSION 112 /* 0.1.1: large-dim (tcgen05) family, Bernoulli / categorical likelihoods */
+#define BFVI_VERSION 120 /* 0.2.0: fused on-chip GTF kernels, training precision modes, batch tiles, bfvi_sizeof / bfvi_last_dispatch */
 
 #define BFVI_MAX_MODS 16
 #define BFVI_MAX_SETS (BFVI_MAX_MODS + 1)
@@ -180,18 +180,44 @@ typedef struct bfvi_step_args {
   float match_count;                    /* mask.sum() used by the prior-matching term
                                            (models/dmm.py:541); < 0 = count seq_mask here */
   const uint64_t* seed_dev;             /* nullable, see bfvi_noise.seed_dev (large-dim family) */
+  int32_t precision;                    /* large-dim family, GEMM operand precision: BFVI_PREC_TF32X3 (0) error-compensated
+                                           3xTF32 through the launch-sequence path (FP32-class, the parity reference of this
+                                           family); BFVI_PREC_TF32 (1) single-pass round-to-nearest TF32 through the FUSED
+                                           on-chip transition kernels (hidden activations never leave the SM; weight gradients
+                                           of the hidden layers contract FP16-rounded operands with FP32 accumulation) */
+  int32_t batch_tile;                   /* large-dim family: sequences per batch tile — the step loops over tiles with
+                                           the gradient accumulated, so the workspace is O(batch_tile) and B is unbounded
+                                           (SURVEY 7 "B = 65 536 at 1 GPU is a loop over batch tiles inside one step");
+                                           0 = chosen by the library (bfvi_step_workspace reports the matching size) */
 } bfvi_step_args;
+enum { BFVI_PREC_TF32X3 = 0, BFVI_PREC_TF32 = 1 };
 
 int bfvi_version(void);
 const char* bfvi_last_error(void);
 
+/* sizeof() of the argument structs as THIS build of the library sees them: a binding (ctypes / cgo / JNI
+ * stub) asserts its own struct sizes against these at load time, so a stale stub fails loudly instead of
+ * handing the library a short struct (multimodal-dmm_b200/_lib.py does; INTEGRATION.md shows it). */
+enum {
+  BFVI_STRUCT_MODEL = 0, BFVI_STRUCT_LAYOUT, BFVI_STRUCT_EXPERT, BFVI_STRUCT_NOISE, BFVI_STRUCT_FILTER_ARGS,
+  BFVI_STRUCT_STEP_ARGS, BFVI_STRUCT_FORWARD_ARGS
+};
+size_t bfvi_sizeof(int32_t which);
+
+/* Which kernel variants the last bfvi_step_fwd_bwd / bfvi_step_profile / bfvi_filter_fwd / bfvi_filter_bwd /
+ * bfvi_forward call of this host thread dispatched: a ';'-separated list of distinct entries such as
+ * "chain_fwd<5,20,5> lanes=5", "chain_bwd<5,20,1> K=25 lanes=5 warps=4", "segmented:cooperative seg=2",
+ * "step:chunks=2", "gtf_fused_fwd<tf32>".  Thread-local, valid until the next such call.  The parity tests
+ * assert on it so that a test of a throughput mapping cannot silently run the latency mapping. */
+const char* bfvi_last_dispatch(void);
+
 /* Flat parameter layout for a model (all-default MLP encoders/decoders). */
 int bfvi_param_layout(const bfvi_model* model, bfvi_layout* out);
 
-/* Which kernel family serves this model: 1 = register-resident small-dim family (every
- * entry point, training included), 2 = tcgen05 large-dim family (bfvi_forward only this
- * release: inference / evaluation; training entry points return BFVI_ERR_UNSUPPORTED),
- * 0 = invalid model. */
+/* Which kernel family serves this model: 1 = register-resident small-dim family (every entry
+ * point), 2 = tcgen05 large-dim family (bfvi_step_fwd_bwd, bfvi_forward, bfvi_filter_fwd / _bwd for
+ * all-default Gaussian models of any (z_dim, h_dim); the stand-alone bfvi_encode_* / bfvi_decode_*
+ * kernels exist for family 1 only and return BFVI_ERR_UNSUPPORTED otherwise), 0 = invalid model. */
 int bfvi_kernel_family(const bfvi_model* model);
 
 /* MultiDMM.encode for one default Gaussian-MLP encoder (models/dmm.py:165-173 +

@@ -15,6 +15,7 @@ DIST_CODES = {'Normal': 0, 'Bernoulli': 1, 'Categorical': 2}
 DIR_FWD, DIR_BWD = 0, 1
 MODE_CODES = {'bfilter': 0, 'ffilter': 1, 'fsmooth': 2, 'bsmooth': 3}
 EXPERT_TENSOR, EXPERT_INV_PRIOR = 0, 1
+PRECISION_CODES = {'tf32x3': 0, 'tf32': 1}
 PHASES = ('match', 'encode_fwd', 'filter_f_fwd', 'filter_s_flt_fwd', 'filter_s_smt_fwd', 'decode_nll',
           'filter_s_smt_bwd', 'filter_s_flt_bwd', 'filter_f_bwd', 'encode_bwd', 'finalize')
 
@@ -89,7 +90,8 @@ class StepArgs(C.Structure):
                 ('eps_match', C.c_void_p), ('eps_filt', C.c_void_p),
                 ('eps_sflt', C.c_void_p), ('eps_ssmt', C.c_void_p),
                 ('seed', C.c_uint64), ('b_offset', C.c_uint32), ('match_count', C.c_float),
-                ('seed_dev', C.c_void_p)]
+                ('seed_dev', C.c_void_p),
+                ('precision', C.c_int32), ('batch_tile', C.c_int32)]
 
 
 class ForwardArgs(C.Structure):
@@ -108,10 +110,16 @@ class BfviError(RuntimeError):
     pass
 
 
+# order of the BFVI_STRUCT_* enum (bfvi_sizeof)
+STRUCTS = (Model, Layout, Expert, Noise, FilterArgs, StepArgs, ForwardArgs)
+
+
 # every symbol include/bfvi.h declares (tests check that the library exports them all)
 SYMBOLS = {
     'bfvi_version': (C.c_int, []),
     'bfvi_last_error': (C.c_char_p, []),
+    'bfvi_last_dispatch': (C.c_char_p, []),
+    'bfvi_sizeof': (C.c_size_t, [C.c_int32]),
     'bfvi_param_layout': (C.c_int, [C.POINTER(Model), C.POINTER(Layout)]),
     'bfvi_kernel_family': (C.c_int, [C.POINTER(Model)]),
     'bfvi_encode_fwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
@@ -184,6 +192,15 @@ class Library(object):
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(self.dll, name)
             fn.restype, fn.argtypes = res, args
+        # a stale binding must fail here, not hand the library a short struct
+        for which, cls in enumerate(STRUCTS):
+            want = self.dll.bfvi_sizeof(which)
+            if want != C.sizeof(cls):
+                raise BfviError('%s: ctypes struct %s is %d bytes, the library expects %d (binding out of date)'
+                                % (path, cls.__name__, C.sizeof(cls), want))
+
+    def last_dispatch(self):
+        return self.dll.bfvi_last_dispatch().decode('utf-8', 'replace').split(';')
 
     def call(self, name, *args):
         rc = getattr(self.dll, name)(*args)

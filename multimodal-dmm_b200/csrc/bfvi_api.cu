@@ -17,6 +17,20 @@
 namespace {
 
 thread_local std::string g_err;
+// Which kernel variants the last top-level call of this host thread launched (bfvi_last_dispatch):
+// the parity tests assert that the variant they mean to check is the one that ran.
+thread_local std::string g_dispatch;
+void note_dispatch(const char* fmt, ...) {
+  char buf[160];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (g_dispatch.find(buf) != std::string::npos) return;       // distinct entries only
+  if (g_dispatch.size() > 4000) return;
+  if (!g_dispatch.empty()) g_dispatch += ';';
+  g_dispatch += buf;
+}
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -212,12 +226,13 @@ int launch_segmented(Kernel k, bfvi::FilterParams& fp, int n_seg, int64_t tasks,
     if (blocks > resident_blocks) blocks = resident_blocks;
     void* args[] = {&fp};
     const cudaError_t e = cudaLaunchCooperativeKernel((const void*)k, dim3((unsigned)blocks), dim3(threads), args, smem, st);
-    if (e == cudaSuccess) return BFVI_OK;
+    if (e == cudaSuccess) { note_dispatch("segmented:cooperative seg=%d", n_seg); return BFVI_OK; }
     cudaGetLastError();                                        // not launchable cooperatively here: fall through
   }
 #else
   (void)tasks; (void)warps; (void)resident_blocks;
 #endif
+  note_dispatch("segmented:per-launch seg=%d", n_seg);
   for (int sg = 0; sg < n_seg; ++sg) {                          // same work, ordered by the stream
     fp.seg_lo = sg; fp.seg_hi = sg + 1;
     BFVI_LAUNCH(k, plain_grid, dim3(threads), smem, st, fp);
@@ -246,6 +261,7 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
     fp.lanes = a.n_particles < 32 ? a.n_particles : 32;
     fp.rounds = (a.n_particles + fp.lanes - 1) / fp.lanes;
     auto k = bfvi::chain_fwd_kernel<Z, H, 1>;
+    note_dispatch("chain_fwd<%d,%d,1> lanes=%d", Z, H, fp.lanes);
     BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, 2)), dim3(64), 0, st, fp);
   } else if (a.n_particles > 1) {
     // (time segmentation as in the backward kernel was measured here and not kept: 2048 tasks fit
@@ -254,12 +270,14 @@ int launch_filter_fwd(bfvi::FilterParams fp, cudaStream_t st) {
     constexpr int R = 5;
     choose_lanes(a.n_particles, R, chains, &fp.lanes, &fp.rounds);
     auto k = bfvi::chain_fwd_kernel<Z, H, R>;
+    note_dispatch("chain_fwd<%d,%d,%d> lanes=%d", Z, H, R, fp.lanes);
     BFVI_LAUNCH(k, dim3(task_grid(chains, fp.lanes, wpb)), dim3(bfvi::kChainFwdThreads), 0, st, fp);
   } else {
     // single particle: latency-bound; a chain is spread over Z lanes (bfvi_zsplit.cuh), 2-warp CTAs
     // put the few warps on all SMs
     fp.lanes = Z; fp.rounds = 1;
     auto k = bfvi::zsplit_fwd_kernel<Z, H>;
+    note_dispatch("zsplit_fwd<%d,%d>", Z, H);
     BFVI_LAUNCH(k, dim3(task_grid(chains, Z, 2)), dim3(bfvi::kZsplitThreads), 0, st, fp);
   }
   BFVI_CHECK_CUDA();
@@ -280,6 +298,7 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
     const int mode = force ? atoi(force) : (warps_needed <= sms * 8 ? 1 : 0);
     if (mode == 1 || mode == 2) {
       fp.lanes = Z; fp.slices = 1;
+      note_dispatch("zsplit_bwd<%d,%d,%d>", Z, H, mode == 2 ? 1 : 0);
       const dim3 grid(task_grid(chains, Z, 2)), block(bfvi::kZsplitThreads);
       if (mode == 1) { auto k = bfvi::zsplit_bwd_kernel<Z, H, false>; BFVI_LAUNCH(k, grid, block, 0, st, fp); }
       else { auto k = bfvi::zsplit_bwd_kernel<Z, H, true>; BFVI_LAUNCH(k, grid, block, 0, st, fp); }
@@ -314,6 +333,7 @@ int launch_filter_bwd(bfvi::FilterParams fp, cudaStream_t st) {
     resident = resident_blocks_of(k, threads, smem);
     n_seg = pick_segments(tasks, resident * warps, a.T, "BFVI_BWD_SEGMENTS");
   }
+  note_dispatch("chain_bwd<%d,%d,%d> K=%d lanes=%d warps=%d", Z, H, n_seg == 1 ? 0 : 1, a.n_particles, fp.lanes, warps);
   if (n_seg == 1) {
     BFVI_LAUNCH(k1, grid, dim3(threads), smem, st, fp);
     BFVI_CHECK_CUDA();
@@ -825,7 +845,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, S = pl.S;
   const int T = fonly ? fonly->T : a->T, B = fonly ? fonly->B : a->B;
   const bool with_grad = fonly ? fonly_backward : grads != nullptr;
-  const int prec = bfvi::tc::PREC_TF32X3;
+  const int prec = (a != nullptr && a->precision == BFVI_PREC_TF32) ? bfvi::tc::PREC_TF32 : bfvi::tc::PREC_TF32X3;
   const int64_t tb = (int64_t)pl.tb;
   int n_launch = 0;
   auto F = [&](size_t off) { return (float*)(ws + off); };
@@ -1368,6 +1388,19 @@ extern "C" {
 
 int bfvi_version(void) { return BFVI_VERSION; }
 const char* bfvi_last_error(void) { return g_err.c_str(); }
+const char* bfvi_last_dispatch(void) { return g_dispatch.c_str(); }
+size_t bfvi_sizeof(int32_t which) {
+  switch (which) {
+    case BFVI_STRUCT_MODEL: return sizeof(bfvi_model);
+    case BFVI_STRUCT_LAYOUT: return sizeof(bfvi_layout);
+    case BFVI_STRUCT_EXPERT: return sizeof(bfvi_expert);
+    case BFVI_STRUCT_NOISE: return sizeof(bfvi_noise);
+    case BFVI_STRUCT_FILTER_ARGS: return sizeof(bfvi_filter_args);
+    case BFVI_STRUCT_STEP_ARGS: return sizeof(bfvi_step_args);
+    case BFVI_STRUCT_FORWARD_ARGS: return sizeof(bfvi_forward_args);
+    default: return 0;
+  }
+}
 
 int bfvi_param_layout(const bfvi_model* m, bfvi_layout* out) {
   if (int rc = check_model(m)) return rc;
@@ -1505,6 +1538,7 @@ static int filter_large(const bfvi_model* m, const float* params, float* grads, 
 }
 
 int bfvi_filter_fwd(const bfvi_model* m, const float* params, const bfvi_filter_args* a, void* stream) {
+  g_dispatch.clear();
   if (int rc = check_model(m)) return rc;
   if (int rc = check_filter_args(m, a)) return rc;
   if (!params) return fail(BFVI_ERR_ARG, "params null");
@@ -1516,6 +1550,7 @@ int bfvi_filter_fwd(const bfvi_model* m, const float* params, const bfvi_filter_
 
 int bfvi_filter_bwd(const bfvi_model* m, const float* params, float* grads, const bfvi_filter_args* a,
                     void* stream) {
+  g_dispatch.clear();
   if (int rc = check_model(m)) return rc;
   if (int rc = check_filter_args(m, a)) return rc;
   if (!params || !grads) return fail(BFVI_ERR_ARG, "params/grads null");
@@ -1851,6 +1886,8 @@ static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
   if (a->f_mode != BFVI_MODE_BFILTER && a->f_mode != BFVI_MODE_FFILTER) return fail(BFVI_ERR_ARG, "bad f_mode");
   if (a->s_mode != BFVI_MODE_FSMOOTH && a->s_mode != BFVI_MODE_BSMOOTH) return fail(BFVI_ERR_ARG, "bad s_mode");
   if (a->train_particles < 1 || a->match_particles < 1) return fail(BFVI_ERR_ARG, "particle counts must be >= 1");
+  if (a->precision != BFVI_PREC_TF32X3 && a->precision != BFVI_PREC_TF32) return fail(BFVI_ERR_ARG, "bad precision");
+  if (a->batch_tile < 0) return fail(BFVI_ERR_ARG, "batch_tile < 0");
   return BFVI_OK;
 }
 
@@ -1884,6 +1921,7 @@ struct PhaseMarks {
 static int step_impl(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
                      void* workspace, size_t workspace_bytes, float* loss_out, int32_t* launches,
                      void* stream, PhaseMarks& pm) {
+  g_dispatch.clear();
   if (int rc = check_step(m, a)) return rc;
   if (!params || !workspace || !loss_out) return fail(BFVI_ERR_ARG, "null argument");
   if (!a->seq_mask) return fail(BFVI_ERR_ARG, "seq_mask null");
@@ -2076,6 +2114,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
       }
       if (n_chunks > B) n_chunks = B;
     }
+    note_dispatch("step:chunks=%d", n_chunks);
     const bool fork_a = side != nullptr && do_f && do_s;
     const bool forked = fork_a || n_chunks > 1;
     if (forked) {

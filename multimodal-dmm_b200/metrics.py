@@ -35,7 +35,12 @@ def eval_ssim(X, Y, win_size=11, win_sigma=1.5, win=None, data_range=1.0, size_a
         raise ValueError('Window size must be odd.')
     if win is None:
         win = _fspecial_gauss_1d(win_size, win_sigma)
-    taps = win.detach().reshape(-1, win.shape[-1])[0].float().cpu()
+    rows = win.detach().reshape(-1, win.shape[-1]).float().cpu()
+    taps = rows[0]
+    if rows.shape[0] > 1 and not bool((rows == taps[None]).all()):
+        # the reference applies row c of `win` to channel c (grouped conv, utils.py:119-124); the kernel takes one
+        # window for all channels, which is what every caller in the reference passes
+        raise _lib.BfviError('eval_ssim: per-channel windows that differ are not supported by the fused kernel')
     win_size = int(taps.numel())
     N, Cc, H, W = (int(v) for v in X.shape)
     with _Runtime(X.device) as rt:
@@ -43,13 +48,22 @@ def eval_ssim(X, Y, win_size=11, win_sigma=1.5, win=None, data_range=1.0, size_a
         y = Y.detach().contiguous().float()
         ssim = torch.empty(N, dtype=torch.float32, device=x.device)
         cs = torch.empty(N, dtype=torch.float32, device=x.device)
-        nbytes = int(rt.lib.dll.bfvi_ssim_scratch(N, Cc, H, W, win_size))
-        if nbytes == 0:
-            raise _lib.BfviError('eval_ssim: images (%d x %d) smaller than the %d-tap window' % (H, W, win_size))
-        scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
         w = (C.c_float * win_size)(*[float(v) for v in taps])
-        rt.call('bfvi_ssim', _lib.ptr(x), _lib.ptr(y), N, Cc, H, W, w, win_size, C.c_float(float(data_range)),
-                _lib.ptr(ssim), _lib.ptr(cs), _lib.ptr(scratch))
+        # the kernel maps (image, channel) to grid dimensions capped at 65 535: the trainers call this on
+        # flattened T*B frame batches (weizmann.py:133), so walk N in chunks of that size
+        n_max = 65535
+        for n0 in range(0, max(N, 1), n_max):
+            n = min(n_max, N - n0)
+            if n <= 0:
+                break
+            nbytes = int(rt.lib.dll.bfvi_ssim_scratch(n, Cc, H, W, win_size))
+            if nbytes == 0:
+                raise _lib.BfviError('eval_ssim: images (%d x %d) smaller than the %d-tap window, or more than '
+                                     '65535 channels' % (H, W, win_size))
+            scratch = torch.empty(nbytes // 4, dtype=torch.float32, device=x.device)
+            rt.call('bfvi_ssim', _lib.ptr(x[n0:n0 + n]), _lib.ptr(y[n0:n0 + n]), n, Cc, H, W, w, win_size,
+                    C.c_float(float(data_range)), _lib.ptr(ssim[n0:n0 + n]), _lib.ptr(cs[n0:n0 + n]),
+                    _lib.ptr(scratch))
     if size_average:
         ssim, cs = ssim.mean(), cs.mean()
     return (ssim, cs) if full else ssim

@@ -53,9 +53,10 @@ class _StepFn(torch.autograd.Function):
         need_grad = bool(args_need_grad(keep)) and any(p.requires_grad for p in params)
         if (need_grad and getattr(model, 'cuda_graph', False) and model._family == 2
                 and not (args.eps_match or args.eps_filt or args.eps_sflt or args.eps_ssmt)):
-            loss, flat_grad = _graph_step(model, lib, args, keep[-1])
-            ctx.model, ctx.flat_grad = model, flat_grad
-            return loss
+            out = _graph_step(model, lib, args, keep[-1])
+            if out is not None:
+                ctx.model, ctx.flat_grad = model, out[1]
+                return out[0]
         flat_grad = torch.empty_like(model._flat) if need_grad else None
         loss = torch.empty((), dtype=torch.float32, device=model._flat.device)
         nbytes = C.c_size_t(0)
@@ -95,7 +96,22 @@ def _graph_step(model, lib, args, tens):
     dev = model._flat.device
     tb = args.T * args.B
 
+    if ent is not None:
+        cache[key] = cache.pop(key)                 # most recently used last
+        model._graph_misses = 0
     if ent is None:
+        # The multipliers (kld_mult anneals every batch, trainer.py:228-230) and the shape are baked into the
+        # captured launches, so a key that changes every step would capture and keep a graph + static buffers
+        # per step.  The cache is a small LRU whose evicted entries free their buffers, and after
+        # `graph_max_misses` consecutive misses graph mode switches itself off for this model (eager launches).
+        model._graph_misses = getattr(model, '_graph_misses', 0) + 1
+        if model._graph_misses > getattr(model, 'graph_max_misses', 3):
+            model.cuda_graph = False
+            cache.clear()
+            return None
+        while len(cache) >= getattr(model, 'graph_cache_size', 2):
+            old = cache.pop(next(iter(cache)))
+            old.clear()
         dims = [int(model._cmodel.dims[i]) for i in range(n_mods)]
         ent = {'inputs': [torch.empty(tb * d, device=dev) for d in dims],
                'targets': [torch.empty(tb * d, device=dev) for d in dims],
@@ -140,7 +156,9 @@ def _graph_step(model, lib, args, tens):
         ent['graph'] = graph
     else:
         ent['graph'].replay()
-    return ent['loss'].clone(), ent['grad']
+    # the static gradient buffer is overwritten by the next replay: hand out a copy (two step() calls before
+    # one backward(), e.g. gradient accumulation, must not alias)
+    return ent['loss'].clone(), ent['grad'].clone()
 
 
 class _OpFn(torch.autograd.Function):
@@ -284,6 +302,8 @@ class MultiDMM(MultiDGTS):
         self._ws = None
         self.grad_sync = None          # optional callable(flat_grad) -> None (data parallel)
         self.noise_seed = None         # fixed Philox seed (None: drawn from torch's RNG per call)
+        self.precision = 'tf32'        # large-dim family step(): 'tf32' (fused on-chip GTF kernels) | 'tf32x3'
+        self.batch_tile = 0            # large-dim family step(): sequences per batch tile (0 = library default)
         self.last_launches = 0
         self.last_flat_grad = None
         self.to(self.device)
@@ -354,6 +374,8 @@ class MultiDMM(MultiDGTS):
     def _next_seed(self):
         if self.noise_seed is not None:
             return int(self.noise_seed)
+        if getattr(self, 'seed_source', None) is not None:        # data parallel: same seed on every rank
+            return int(self.seed_source())
         return int(torch.randint(0, 2 ** 62, (1,)).item())       # host RNG, no device sync
 
     @property
@@ -613,13 +635,19 @@ class MultiDMM(MultiDGTS):
         include/bfvi.h) injects the reparameterisation draws."""
         self._ensure_flat()
         fused_kw = {'f_mode', 's_mode', 'f_mult', 's_mult', 'match_mult', 'train_particles',
-                    'match_particles', 'lengths', 'sample', 'sample_init', 'noise'}
-        if self.fused_step_available and set(kwargs) <= fused_kw and \
+                    'match_particles', 'lengths', 'sample', 'sample_init', 'noise', 'precision', 'batch_tile'}
+        # the reference forwards ANY f_mode / s_mode to forward() (models/dmm.py:547-553): the fused C call
+        # covers the default pairing (filtering ELBO + smoothing ELBO), everything else composes the ops
+        modes_ok = (kwargs.get('f_mode', 'bfilter') in ('bfilter', 'ffilter') and
+                    kwargs.get('s_mode', 'fsmooth') in ('fsmooth', 'bsmooth'))
+        if self.fused_step_available and set(kwargs) <= fused_kw and modes_ok and \
                 all(m in inputs for m in self.modalities):
             return self._fused_step(inputs, mask, kld_mult, rec_mults, targets, uni_loss, kwargs)
         # composed path (custom modules / non-Gaussian modalities / unusual kwargs)
         kwargs = dict(kwargs)
         kwargs.pop('noise', None)
+        kwargs.pop('precision', None)
+        kwargs.pop('batch_tile', None)
         f_mode, s_mode = kwargs.pop('f_mode', 'bfilter'), kwargs.pop('s_mode', 'fsmooth')
         f_mult, s_mult = kwargs.pop('f_mult', 0.5), kwargs.pop('s_mult', 0.5)
         match_mult = kwargs.pop('match_mult', 0.01)
@@ -673,6 +701,10 @@ class MultiDMM(MultiDGTS):
         a.match_particles = int(kw.get('match_particles', 50))
         a.sample, a.sample_init = int(bool(kw.get('sample', True))), int(bool(kw.get('sample_init', False)))
         a.seed, a.b_offset, a.match_count = self._next_seed(), int(getattr(self, 'b_offset', 0)), -1.0
+        # large-dim family: GEMM operand precision ('tf32x3' error-compensated / 'tf32' single pass, the fused
+        # on-chip transition kernels) and the batch tile the step walks (0 = chosen by the library)
+        a.precision = _lib.PRECISION_CODES[kw.get('precision', self.precision)]
+        a.batch_tile = int(kw.get('batch_tile', self.batch_tile))
         noise = kw.get('noise')
         if noise is not None:
             for name, field in (('match', 'eps_match'), ('filt', 'eps_filt'), ('sflt', 'eps_sflt'),

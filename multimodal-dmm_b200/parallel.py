@@ -60,10 +60,54 @@ def sync_seed(seed, group=None, device=None):
     return int(t.item())
 
 
-def attach(model, shard, group=None):
+class _SharedSeeds(object):
+    """Per-step Philox seeds that are the same on every rank without a collective per step: rank 0
+    draws ONE base seed, broadcasts it once, and every rank steps the same generator."""
+
+    def __init__(self, base):
+        self.gen = torch.Generator().manual_seed(int(base))
+
+    def __call__(self):
+        return int(torch.randint(0, 2 ** 62, (1,), generator=self.gen).item())
+
+
+def attach(model, shard, group=None, base_seed=None):
     """Wires a MultiDMM replica for data-parallel training on `shard` (from shard_batch):
-    noise offset + gradient all-reduce inside `loss.backward()`.  The caller divides the
-    loss by shard['n_global'] (trainer.py:242 with the GLOBAL sum of lengths)."""
+      * rank 0's parameters are broadcast (replicas must start identical);
+      * every rank draws the same Philox seed per step (`model.seed_source`, one broadcast here);
+      * noise is indexed by the global sequence index (`b_offset`);
+      * `loss.backward()` all-reduces the flat gradient (the step's only collective).
+    The caller divides the loss by shard['n_global'] (trainer.py:242 with the GLOBAL sum of lengths).
+    A rank whose shard is EMPTY (world > sequences) must not call model.step — use `step_or_zero`,
+    which still joins the all-reduce with a zero gradient so the other ranks do not hang."""
+    import torch.distributed as dist
+    model._ensure_flat()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(model._flat, src=0, group=group)
+    if base_seed is None:
+        base_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    model.seed_source = _SharedSeeds(sync_seed(base_seed, group, device=model._flat.device
+                                               if dist.is_initialized() and dist.get_backend(group) == 'nccl' else None))
     model.b_offset = int(shard['b_offset'])
     model.grad_sync = lambda flat_grad: all_reduce_flat(flat_grad, group)
     return model
+
+
+def step_or_zero(model, shard, kld_mult, rec_mults, group=None, **kwargs):
+    """model.step on the shard + backward of loss / n_global; an EMPTY shard contributes a zero gradient to
+    the same all-reduce (and consumes the step's shared seed) instead of failing argument checks while the
+    other ranks wait in the collective.  Returns the local un-normalised loss (0-dim tensor)."""
+    if len(shard['lengths']) == 0:
+        model._ensure_flat()
+        if getattr(model, 'seed_source', None) is not None:
+            model.seed_source()
+        zero = torch.zeros_like(model._flat)
+        all_reduce_flat(zero, group)
+        model.last_flat_grad = zero
+        for _, off, p in model._slots:
+            p.grad = zero[off:off + p.numel()].view(p.shape)
+        return torch.zeros((), device=model._flat.device)
+    loss = model.step(shard['inputs'], shard['mask'], kld_mult, rec_mults, targets=shard['targets'],
+                      lengths=shard['lengths'], **kwargs)
+    (loss / shard['n_global']).backward()
+    return loss.detach()

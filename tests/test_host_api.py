@@ -51,7 +51,7 @@ def test_cabi_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
     for name in declared:
         assert hasattr(lib.dll, name)
-    assert lib.dll.bfvi_version() == 112
+    assert lib.dll.bfvi_version() == 120
 
 
 def test_layout_and_argument_errors():
@@ -68,7 +68,7 @@ def test_layout_and_argument_errors():
     with pytest.raises(_lib.BfviError):
         lib.layout(bad)
     big = _lib.make_model([4], ['Normal'], 999, 999, 1e-3)
-    assert lib.dll.bfvi_kernel_family(C.byref(big)) == 2            # tcgen05 family: forward only
+    assert lib.dll.bfvi_kernel_family(C.byref(big)) == 2            # tcgen05 family: step, forward, z_filter
     a = _lib.StepArgs()
     a.T, a.B = 4, 4
     n = C.c_size_t(0)
