@@ -420,6 +420,26 @@ int bfvi_wgrad_tf32(const float* dy_t, int64_t lddy, const float* x_t, int64_t l
                     int64_t n_rows, int32_t n_out, int32_t n_in, int32_t accumulate, int32_t flags,
                     void* stream);
 
+/* GaussianGTF.forward (models/common.py:62-68) on n_rows latent rows (z_dim 64, h_dim a multiple of 128) through the
+ * FUSED on-chip kernels — the building block of the large-dim family's precision mode BFVI_PREC_TF32: per 128-row tile
+ * z -> hidden -> heads runs as a chain of tcgen05 MMAs whose hidden activations stay in tensor memory; weights are
+ * rounded to TF32 once and streamed by cp.async.bulk.  Outputs are the four pre-activation heads with their biases
+ * added, (n_rows, 64) each: gate_pre (before the sigmoid), nonlin, lin, std_pre (before softplus + min_std), so that
+ * mean = (1 - sigmoid(gate_pre)) * lin + sigmoid(gate_pre) * nonlin and std = softplus(std_pre) + min_std.
+ * keep != 0 also leaves the operands of bfvi_gtf_bwd in the workspace (bfvi_gtf_workspace(model, n_rows) bytes,
+ * 256-byte aligned; 0 = shape not served). */
+size_t bfvi_gtf_workspace(const bfvi_model* model, int64_t n_rows);
+int bfvi_gtf_fwd(const bfvi_model* model, const float* params, int32_t direction, const float* z, int64_t n_rows,
+                 float* gate_pre, float* nonlin, float* lin, float* std_pre, int32_t keep, void* workspace,
+                 size_t workspace_bytes, void* stream);
+/* Backward of the same rows (bfvi_gtf_fwd(keep = 1) ran on this workspace; `nonlin` is its output): from the gradients
+ * at the four heads, d_z (n_rows, 64) is written and every parameter gradient of trans[direction] is ACCUMULATED into
+ * `grads` (flat layout).  The hidden gradients never leave the SM; the H-wide weight gradients contract FP16-rounded
+ * operand tiles with FP32 accumulation. */
+int bfvi_gtf_bwd(const bfvi_model* model, const float* params, float* grads, int32_t direction, const float* z,
+                 const float* nonlin, int64_t n_rows, const float* d_gate_pre, const float* d_nonlin, const float* d_lin,
+                 const float* d_std_pre, float* d_z, void* workspace, size_t workspace_bytes, void* stream);
+
 /* The optimiser step either side of the hot path (trainer.py:248-252), fused over the flat
  * buffers: optional clip_grad_norm_ (max_norm > 0; total L2 norm over the whole flat gradient,
  * coefficient max_norm / (norm + 1e-6) clamped to 1) followed by torch.optim.Adam (no amsgrad;

@@ -12,6 +12,7 @@
 #include "bfvi_small.cuh"
 #include "bfvi_tc.cuh"
 #include "bfvi_generic.cuh"
+#include "bfvi_fused.cuh"
 #include "bfvi_data.cuh"
 
 namespace {
@@ -685,6 +686,158 @@ struct LinearGroup {
   }
 };
 
+
+// ===========================================================================================
+// fused on-chip transition kernels (bfvi_fused.cuh): host side
+// ===========================================================================================
+// served shapes: Z = 64, H a multiple of 128 (C3: 64 / 512); anything else takes the launch-sequence path
+bool fused_supported(int Z, int H) {
+#ifdef BFVI_EMU
+  (void)Z; (void)H;
+  return false;
+#else
+  static const bool off = [] { const char* e = getenv("BFVI_FUSED"); return e && atoi(e) == 0; }();
+  return !off && Z == bfvi::fused::kZ && H >= 128 && H % 128 == 0 && H <= 2048;
+#endif
+}
+struct FusedBufs {
+  unsigned char* pack_fwd[2]; unsigned char* pack_bwd[2]; float* bias[2];      // per direction, shared by all passes
+  void* h16; void* dh16; void* z16; void* dg16; void* dnl16; uint32_t* bits;   // per-row scratch (rows padded to 128)
+};
+int64_t fused_rows_pad(int64_t rows) { return (rows + 127) / 128 * 128; }
+// per-row scratch bytes: hidden activations + their gradients as FP16 tiles, three Z-wide FP16 tiles, the ReLU bits
+struct FusedRowScratch { size_t h16, dh16, z16, dg16, dnl16, bits, total; };
+FusedRowScratch fused_row_scratch(int H, int64_t rows) {
+  const size_t rp = (size_t)fused_rows_pad(rows);
+  FusedRowScratch r;
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = (cur + bytes + 1023) / 1024 * 1024; return o; };
+  r.h16 = carve(rp * 2 * H * 2); r.dh16 = carve(rp * 2 * H * 2);
+  r.z16 = carve(rp * 64 * 2); r.dg16 = carve(rp * 64 * 2); r.dnl16 = carve(rp * 64 * 2);
+  r.bits = carve(rp * (2 * H / 64) * 2 * 4);
+  r.total = cur;
+  return r;
+}
+size_t fused_pack_total(int H) {          // both directions: forward pack, backward pack, bias table
+  return 2 * (2 * bfvi::fused::pack_bytes(H) + (bfvi::fused::bias_floats(H) * 4 + 1023) / 1024 * 1024);
+}
+void fused_carve_packs(char* base, int H, FusedBufs* fb) {
+  const size_t pb = bfvi::fused::pack_bytes(H), bb = (bfvi::fused::bias_floats(H) * 4 + 1023) / 1024 * 1024;
+  for (int d = 0; d < 2; ++d) {
+    char* o = base + (size_t)d * (2 * pb + bb);
+    fb->pack_fwd[d] = (unsigned char*)o; fb->pack_bwd[d] = (unsigned char*)(o + pb); fb->bias[d] = (float*)(o + 2 * pb);
+  }
+}
+void fused_carve_rows(char* base, int H, int64_t rows, FusedBufs* fb) {
+  const FusedRowScratch r = fused_row_scratch(H, rows);
+  fb->h16 = base + r.h16; fb->dh16 = base + r.dh16; fb->z16 = base + r.z16; fb->dg16 = base + r.dg16;
+  fb->dnl16 = base + r.dnl16; fb->bits = (uint32_t*)(base + r.bits);
+}
+#ifndef BFVI_EMU
+int fused_smem_limit() { return 232448; }
+int fused_stages(size_t extra_bytes) {
+  int st = (int)((fused_smem_limit() - 1024 - extra_bytes) / bfvi::fused::kBlockBytes);
+  if (st > bfvi::fused::kMaxStages) st = bfvi::fused::kMaxStages;
+  static const int cap = [] { const char* e = getenv("BFVI_FUSED_STAGES"); return e ? atoi(e) : 99; }();
+  if (st > cap) st = cap;
+  return st;
+}
+int fused_pack(const bfvi_gtf_layout& g, const float* params, int dir, int H, const FusedBufs& fb, cudaStream_t st) {
+  bfvi::fused::PackParams pp;
+  pp.w_gate0 = params + g.gate0_w; pp.b_gate0 = params + g.gate0_b; pp.w_gate2 = params + g.gate2_w; pp.b_gate2 = params + g.gate2_b;
+  pp.w_lin = params + g.lin_w; pp.b_lin = params + g.lin_b; pp.w_non0 = params + g.nonlin0_w; pp.b_non0 = params + g.nonlin0_b;
+  pp.w_non2 = params + g.nonlin2_w; pp.b_non2 = params + g.nonlin2_b; pp.w_std = params + g.std_w; pp.b_std = params + g.std_b;
+  pp.fwd = fb.pack_fwd[dir]; pp.bwd = fb.pack_bwd[dir]; pp.bias = fb.bias[dir]; pp.H = H;
+  auto k = bfvi::fused::pack_gtf_kernel;
+  k<<<dim3((unsigned)bfvi::fused::pack_blocks(H)), dim3(256), 0, st>>>(pp);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+// heads of one transition for `rows` latent rows; keep = also write the operand tiles / ReLU bits the backward needs
+int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows, float* g, float* nl, float* lin, float* as,
+              bool keep, cudaStream_t st) {
+  bfvi::fused::FwdParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.pack = fb.pack_fwd[dir]; fp.bias = fb.bias[dir]; fp.z = z; fp.g = g; fp.nl = nl; fp.lin = lin; fp.as = as;
+  fp.h16 = (__half*)fb.h16; fp.relu_bits = fb.bits; fp.z16 = (__half*)fb.z16;
+  fp.R = rows; fp.H = H;
+  const size_t extra = bfvi::fused::bias_floats(H) * 4;
+  fp.n_stages = fused_stages(extra);
+  if (fp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: h_dim %d too wide", H);
+  const size_t smem = (size_t)fp.n_stages * bfvi::fused::kBlockBytes + extra + 1024;
+  const int64_t tiles = (rows + 127) / 128;
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  if (keep) {
+    auto k = bfvi::fused::gtf_fwd_kernel<true>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
+    note_dispatch("gtf_fwd_fused<keep> tf32 stages=%d", fp.n_stages);
+  } else {
+    auto k = bfvi::fused::gtf_fwd_kernel<false>;
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
+    note_dispatch("gtf_fwd_fused tf32 stages=%d", fp.n_stages);
+  }
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+// input gradient dz of one transition (the KEEP forward of the same rows must have run) + hidden bias gradients
+int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float* d_nl, const float* d_lin, int64_t rows,
+              float* dz, float* gb_gate0, float* gb_non0, cudaStream_t st) {
+  bfvi::fused::BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  bp.pack = fb.pack_bwd[dir]; bp.d_g = d_g; bp.d_nl = d_nl; bp.d_lin = d_lin; bp.relu_bits = fb.bits; bp.dz = dz;
+  bp.dh16 = (__half*)fb.dh16; bp.dg16 = (__half*)fb.dg16; bp.dnl16 = (__half*)fb.dnl16;
+  bp.gb_gate0 = gb_gate0; bp.gb_non0 = gb_non0; bp.R = rows; bp.H = H;
+  const size_t extra = (size_t)2 * H * 4;
+  bp.n_stages = fused_stages(extra);
+  if (bp.n_stages < 5) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: h_dim %d too wide", H);
+  const size_t smem = (size_t)bp.n_stages * bfvi::fused::kBlockBytes + extra + 1024;
+  const int64_t tiles = (rows + 127) / 128;
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  auto k = bfvi::fused::gtf_bwd_kernel;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<dim3((unsigned)(tiles < sms ? tiles : sms)), dim3(bfvi::fused::kThreads), smem, st>>>(bp);
+  note_dispatch("gtf_bwd_fused tf32 stages=%d", bp.n_stages);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+// weight gradients of the four H-wide layers from the FP16 operand tiles of fused_fwd(keep) / fused_bwd
+int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float* dw_non0, float* dw_gate2, float* dw_non2,
+                cudaStream_t st) {
+  bfvi::fused::Wgrad16Params wp;
+  memset(&wp, 0, sizeof(wp));
+  const int U = H / 64;
+  auto prob = [&](int i, const void* X, int atom0, const void* Y, float* out, int transposed) {
+    wp.pr[i].X = (const __half*)X; wp.pr[i].n_atoms_x = 2 * U; wp.pr[i].atom0 = atom0; wp.pr[i].Y = (const __half*)Y;
+    wp.pr[i].out = out; wp.pr[i].transposed = transposed;
+  };
+  prob(0, fb.dh16, 0, fb.z16, dw_gate0, 0);        // dW_gate0 (H, Z) = dh1^T z
+  prob(1, fb.dh16, U, fb.z16, dw_non0, 0);         // dW_nonlin0 (H, Z) = dh3^T z
+  prob(2, fb.h16, 0, fb.dg16, dw_gate2, 1);        // dW_gate2 (Z, H) = d_g^T h1, computed as h1^T d_g
+  prob(3, fb.h16, U, fb.dnl16, dw_non2, 1);        // dW_nonlin2 (Z, H) = d_nl^T h3
+  wp.n_problems = 4; wp.H = H;
+  wp.n_groups = fused_rows_pad(rows) / 64;
+  const int sms = num_sms() > 0 ? num_sms() : 1;
+  const int tiles = 4 * (H / 128);
+  int64_t slices = (2 * sms + tiles - 1) / tiles;
+  if (slices > wp.n_groups) slices = wp.n_groups;
+  if (slices < 1) slices = 1;
+  wp.groups_per_slice = (int)((wp.n_groups + slices - 1) / slices);
+  wp.n_slices = (int)((wp.n_groups + wp.groups_per_slice - 1) / wp.groups_per_slice);
+  wp.n_stages = bfvi::fused::kMaxStages;
+  const size_t smem = (size_t)wp.n_stages * bfvi::fused::kWgStageBytes + 1024;
+  const int items = tiles * wp.n_slices;
+  auto k = bfvi::fused::wgrad16_kernel;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<dim3((unsigned)(items < sms ? items : sms)), dim3(bfvi::fused::kWgThreads), smem, st>>>(wp);
+  note_dispatch("wgrad16 f16-mn");
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+#endif  // !BFVI_EMU
+
 // ===========================================================================================
 // large-dim family: the whole MultiDMM.step + backward as a stream-ordered launch sequence of
 // tcgen05 GEMMs (every Linear layer: forward, input gradient, weight gradient) and fused
@@ -704,6 +857,8 @@ struct LargePlan {
   size_t c_mu, c_sd, d_pm, d_v, zvec;
   size_t hdec, hdecT, dhd, dhdT, dmean, dstd, dmeanT, dstdT;
   size_t side_grads;                                 // zeroed: parameter gradients of the side stream (pass A)
+  size_t fused_packs, fused_rows;                    // fused transition kernels: weight packs (shared), per-row scratch
+  int fused;
 };
 
 // `fonly` != null plans the workspace of a stand-alone z_filter call (bfvi_filter_fwd / _bwd of the
@@ -763,6 +918,14 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   pl->dhd = carve(f * pl->tb * H); pl->dhdT = carve(f * pl->tb * H);
   pl->dmean = carve(f * pl->tb * pl->d_max); pl->dstd = carve(f * pl->tb * pl->d_max);
   pl->dmeanT = carve(f * pl->tb * pl->d_max); pl->dstdT = carve(f * pl->tb * pl->d_max);
+  pl->fused = (a != nullptr && a->precision == BFVI_PREC_TF32 && fused_supported(Z, H)) ? 1 : 0;
+  pl->fused_packs = pl->fused_rows = 0;
+  if (pl->fused) {
+    cur = align_up(cur, 1024);
+    pl->fused_packs = carve(fused_pack_total(H));
+    cur = align_up(cur, 1024);
+    pl->fused_rows = carve(fused_row_scratch(H, (int64_t)R).total);
+  }
   pl->total = cur;
   return BFVI_OK;
 }
@@ -798,6 +961,10 @@ void plan_large_side(const bfvi_model* m, const bfvi_step_args* a, const LargePl
   ps->dhd = carve(f * pl.tb * H); ps->dhdT = carve(f * pl.tb * H);
   ps->dmean = carve(f * pl.tb * pl.d_max); ps->dstd = carve(f * pl.tb * pl.d_max);
   ps->dmeanT = carve(f * pl.tb * pl.d_max); ps->dstdT = carve(f * pl.tb * pl.d_max);
+  if (pl.fused) {                                      // packs are shared with the main plan; own row scratch
+    cur = align_up(cur, 1024);
+    ps->fused_rows = carve(fused_row_scratch(H, (int64_t)R).total);
+  }
   ps->total = cur;
 }
 
@@ -938,11 +1105,35 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     BFVI_CHECK_CUDA();
   }
 
+  // ---- fused on-chip transition kernels (precision BFVI_PREC_TF32, bfvi_fused.cuh) ---------------
+  const bool fused = pl_main.fused != 0;
+#ifndef BFVI_EMU
+  auto fbufs = [&]() {                // packs are shared; the per-row scratch belongs to the CURRENT context (main / side)
+    FusedBufs fb;
+    fused_carve_packs(ws + pl_main.fused_packs, H, &fb);
+    fused_carve_rows(ws + pl.fused_rows, H, (int64_t)pl.R, &fb);
+    return fb;
+  };
+  if (fused) {                        // weights rounded to TF32 and laid out as shared-memory images ONCE per step
+    const FusedBufs fb = fbufs();
+    for (int d = 0; d < 2; ++d) { if (int rc = fused_pack(lay.trans[d], params, d, H, fb, st)) return rc; ++n_launch; }
+  }
+#endif
   // ---- one transition: 6 forward GEMMs over `rows` particles --------------------------------
   // Groups are width-homogeneous (a launch has ONE tile width: a 64-wide problem in a 128-wide launch copies,
   // rounds and multiplies a half-empty W tile): the two z -> hidden layers (N = H) go out alone, everything
   // that is Z wide rides with the next level.
   auto trans_fwd = [&](const bfvi_gtf_layout& g, int64_t rows, bool keep) -> int {
+#ifndef BFVI_EMU
+    if (fused) {                      // ONE launch: hidden activations stay in tensor memory
+      if (int rc = flush()) return rc;
+      const int dir = (&g == &lay.trans[1]) ? 1 : 0;
+      if (int rc = fused_fwd(fbufs(), dir, H, F(pl.zrows), rows, F(pl.g), F(pl.nl), F(pl.lin), F(pl.as), keep, st)) return rc;
+      ++n_launch;
+      if (keep) transpose(F(pl.nl), rows, Z, F(pl.nlT));        // operand of the Z x Z std weight gradient
+      return BFVI_OK;
+    }
+#endif
     if (int rc = lin(F(pl.zrows), Z, g.gate0_w, g.gate0_b, F(pl.h1), keep ? F(pl.h1T) : nullptr, rows, Z, H, 1)) return rc;
     if (int rc = lin(F(pl.zrows), Z, g.nonlin0_w, g.nonlin0_b, F(pl.h3), keep ? F(pl.h3T) : nullptr, rows, Z, H, 1)) return rc;
     if (int rc = flush()) return rc;
@@ -958,6 +1149,25 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   // and the weight gradients (bias gradients come from the elementwise kernels / GEMM column sums):
   // twelve GEMMs in three dependency levels
   auto trans_bwd = [&](const bfvi_gtf_layout& g, int64_t rows) -> int {
+#ifndef BFVI_EMU
+    if (fused) {
+      const int dir = (&g == &lay.trans[1]) ? 1 : 0;
+      // Z-wide level on the launch-sequence GEMMs: d_nl += d_as W_std (its column sums complete nonlin2_b's
+      // gradient) and the two Z x Z weight gradients
+      if (int rc = dgrad(F(pl.d_as), g.std_w, F(pl.d_nl), nullptr, rows, Z, Z, true, nullptr, grads + g.nonlin2_b)) return rc;
+      if (int rc = wgrad(F(pl.d_linT), F(pl.zrowsT), rows, Z, Z, g.lin_w)) return rc;
+      if (int rc = wgrad(F(pl.d_asT), F(pl.nlT), rows, Z, Z, g.std_w)) return rc;
+      if (int rc = flush()) return rc;
+      const FusedBufs fb = fbufs();
+      // input gradient with the hidden gradients on-chip (+ hidden bias gradients, FP16 operand tiles) ...
+      if (int rc = fused_bwd(fb, dir, H, F(pl.d_g), F(pl.d_nl), F(pl.d_lin), rows, F(pl.dz), grads + g.gate0_b,
+                             grads + g.nonlin0_b, st)) return rc;
+      // ... and the four H-wide weight gradients from those tiles
+      if (int rc = fused_wgrad(fb, H, rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w, st)) return rc;
+      n_launch += 2;
+      return BFVI_OK;
+    }
+#endif
     // level 1 (Z wide): what needs only the head gradients and the saved activations
     if (int rc = dgrad(F(pl.d_as), g.std_w, F(pl.d_nl), F(pl.d_nlT), rows, Z, Z, true, nullptr, grads + g.nonlin2_b)) return rc;
     if (int rc = dgrad(F(pl.d_lin), g.lin_w, F(pl.dz), nullptr, rows, Z, Z, false, nullptr, nullptr)) return rc;
@@ -994,7 +1204,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       sp.gb_std = grads + g.std_b; sp.gb_gate2 = grads + g.gate2_b;
       sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
     }
-    sp.dz = F(pl.dz); sp.dz2 = F(pl.dz2);
+    sp.dz = F(pl.dz); sp.dz2 = fused ? nullptr : F(pl.dz2);      // the fused backward writes the complete gradient
     return sp;
   };
   // particles of step i_src as GEMM input rows (+ transposed copy)
@@ -1841,6 +2051,130 @@ int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
   gp.M = n_out; gp.N = n_in; gp.K = n_rows; gp.accumulate = accumulate ? 1 : 0;
   if (accumulate) gp.k_split = wgrad_k_split(n_rows, n_out, n_in);
   return gemm_tc(gp, (flags >> 4) & 1, (cudaStream_t)stream);
+}
+
+
+// ---- GaussianGTF on latent rows through the fused on-chip kernels (bfvi_fused.cuh) --------------------------
+namespace {
+#ifndef BFVI_EMU
+// the Z x Z corners of a transition's backward for the stand-alone entry (exact fp32, CUDA cores; inside a step
+// these ride on the grouped tcgen05 launches):  d_nl = d_nonlin + d_std_pre W_std
+__global__ void __launch_bounds__(64) gtf_small_dnl_kernel(const float* __restrict__ d_nonlin, const float* __restrict__ d_std_pre,
+                                                          const float* __restrict__ w_std, int64_t rows, float* __restrict__ d_nl) {
+  __shared__ float ds[64];
+  const int j = threadIdx.x;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    ds[j] = d_std_pre[r * 64 + j];
+    __syncthreads();
+    float acc = d_nonlin[r * 64 + j];
+    for (int i = 0; i < 64; ++i) acc = fmaf(ds[i], w_std[i * 64 + j], acc);
+    d_nl[r * 64 + j] = acc;
+    __syncthreads();
+  }
+}
+// dW (64, 64) += dY^T X, bias (64) += column sums of dY; one block per slice of rows, thread = (o, 4 inputs)
+__global__ void __launch_bounds__(256) gtf_small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, int64_t rows,
+                                                             float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float sy[64], sx[64];
+  const int o = threadIdx.x >> 2, i0 = (threadIdx.x & 3) * 16;
+  float acc[16], bsum = 0.f;
+  for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+  const int64_t per = (rows + gridDim.x - 1) / gridDim.x, r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = r0 + per < rows ? r0 + per : rows;
+  for (int64_t r = r0; r < r1; ++r) {
+    if (threadIdx.x < 64) sy[threadIdx.x] = dy[r * 64 + threadIdx.x];
+    else if (threadIdx.x < 128) sx[threadIdx.x - 64] = x ? x[r * 64 + threadIdx.x - 64] : 0.f;
+    __syncthreads();
+    const float y = sy[o];
+    bsum += y;
+    if (dw != nullptr)
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(y, sx[i0 + i], acc[i]);
+    __syncthreads();
+  }
+  if (dw != nullptr)
+    for (int i = 0; i < 16; ++i) atomicAdd(dw + o * 64 + i0 + i, acc[i]);
+  if (db != nullptr && (threadIdx.x & 3) == 0) atomicAdd(db + o, bsum);
+}
+#endif
+struct GtfWs { size_t packs, rows, d_nl, total; };
+GtfWs gtf_ws_plan(int H, int64_t n_rows) {
+  GtfWs w;
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = (cur + bytes + 1023) / 1024 * 1024; return o; };
+  w.packs = carve(fused_pack_total(H));
+  w.rows = carve(fused_row_scratch(H, n_rows).total);
+  w.d_nl = carve(sizeof(float) * (size_t)n_rows * 64);
+  w.total = cur;
+  return w;
+}
+}  // namespace
+
+size_t bfvi_gtf_workspace(const bfvi_model* m, int64_t n_rows) {
+  if (check_model(m) || n_rows < 1 || !fused_supported(m->z_dim, m->h_dim)) return 0;
+  return gtf_ws_plan(m->h_dim, n_rows).total;
+}
+
+int bfvi_gtf_fwd(const bfvi_model* m, const float* params, int32_t direction, const float* z, int64_t n_rows,
+                 float* gate_pre, float* nonlin, float* lin, float* std_pre, int32_t keep, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  g_dispatch.clear();
+  if (int rc = check_model(m)) return rc;
+  if (!params || !z || !gate_pre || !nonlin || !lin || !std_pre || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (direction != BFVI_DIR_FWD && direction != BFVI_DIR_BWD) return fail(BFVI_ERR_ARG, "bad direction");
+  if (!fused_supported(m->z_dim, m->h_dim))
+    return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernels serve z_dim 64 with h_dim a multiple of 128 (got %d / %d)", m->z_dim, m->h_dim);
+#ifdef BFVI_EMU
+  (void)keep; (void)workspace; (void)workspace_bytes; (void)stream;
+  return fail(BFVI_ERR_UNSUPPORTED, "tcgen05 kernels do not exist in the emulator build");
+#else
+  const GtfWs w = gtf_ws_plan(m->h_dim, n_rows);
+  if (!workspace || workspace_bytes < w.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  FusedBufs fb;
+  fused_carve_packs((char*)workspace + w.packs, m->h_dim, &fb);
+  fused_carve_rows((char*)workspace + w.rows, m->h_dim, n_rows, &fb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = fused_pack(lay.trans[direction], params, direction, m->h_dim, fb, st)) return rc;
+  return fused_fwd(fb, direction, m->h_dim, z, n_rows, gate_pre, nonlin, lin, std_pre, keep != 0, st);
+#endif
+}
+
+int bfvi_gtf_bwd(const bfvi_model* m, const float* params, float* grads, int32_t direction, const float* z,
+                 const float* nonlin, int64_t n_rows, const float* d_gate_pre, const float* d_nonlin, const float* d_lin,
+                 const float* d_std_pre, float* d_z, void* workspace, size_t workspace_bytes, void* stream) {
+  g_dispatch.clear();
+  if (int rc = check_model(m)) return rc;
+  if (!params || !grads || !z || !nonlin || !d_gate_pre || !d_nonlin || !d_lin || !d_std_pre || !d_z || n_rows < 1)
+    return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (direction != BFVI_DIR_FWD && direction != BFVI_DIR_BWD) return fail(BFVI_ERR_ARG, "bad direction");
+  if (!fused_supported(m->z_dim, m->h_dim))
+    return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernels serve z_dim 64 with h_dim a multiple of 128 (got %d / %d)", m->z_dim, m->h_dim);
+#ifdef BFVI_EMU
+  (void)workspace; (void)workspace_bytes; (void)stream;
+  return fail(BFVI_ERR_UNSUPPORTED, "tcgen05 kernels do not exist in the emulator build");
+#else
+  const GtfWs w = gtf_ws_plan(m->h_dim, n_rows);
+  if (!workspace || workspace_bytes < w.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  const bfvi_gtf_layout& g = lay.trans[direction];
+  FusedBufs fb;
+  fused_carve_packs((char*)workspace + w.packs, m->h_dim, &fb);
+  fused_carve_rows((char*)workspace + w.rows, m->h_dim, n_rows, &fb);
+  float* d_nl = (float*)((char*)workspace + w.d_nl);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)grid_for(n_rows, 8, 4);
+  gtf_small_dnl_kernel<<<dim3(blocks), dim3(64), 0, st>>>(d_nonlin, d_std_pre, params + g.std_w, n_rows, d_nl);
+  gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_std_pre, nonlin, n_rows, grads + g.std_w, grads + g.std_b);
+  gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_lin, z, n_rows, grads + g.lin_w, grads + g.lin_b);
+  gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_gate_pre, nullptr, n_rows, nullptr, grads + g.gate2_b);
+  gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_nl, nullptr, n_rows, nullptr, grads + g.nonlin2_b);
+  BFVI_CHECK_CUDA();
+  if (int rc = fused_bwd(fb, direction, m->h_dim, d_gate_pre, d_nl, d_lin, n_rows, d_z, grads + g.gate0_b, grads + g.nonlin0_b, st)) return rc;
+  return fused_wgrad(fb, m->h_dim, n_rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w, st);
+#endif
 }
 
 int bfvi_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

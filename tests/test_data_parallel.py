@@ -63,6 +63,9 @@ def test_two_rank_gloo_step_equals_single_process(tmp_path):
         s.bind(('127.0.0.1', 0))
         port = s.getsockname()[1]
     out = str(tmp_path / 'dp.pt')
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+    import build_emu
+    build_emu.build()                      # once, here: two ranks must not rebuild the emulator library concurrently
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r['finite']
