@@ -269,7 +269,7 @@ def main():
     ap.add_argument('--workload', default='c3', choices=sorted(WORKLOADS))
     ap.add_argument('--batch', type=int, default=0, help='sequences per GPU (weak) / in total (strong); 0 = workload default')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
-    ap.add_argument('--precision', default='tf32', choices=['tf32', 'tf32x3'],
+    ap.add_argument('--precision', default='fused', choices=['fused', 'tf32', 'tf32x3'],
                     help='GEMM operand precision of the large-dim family (c3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the end-to-end loop (0 = min(steps, 5))')
@@ -430,8 +430,9 @@ def main():
             'metric': METRIC, 'value': seq_ts_global / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
             'scaling': args.scaling, 'vs_baseline': None,
-            'dtype': ('tf32 operands, fp32 accumulate (fp16 weight-gradient operands)' if args.precision == 'tf32'
-                      else 'tf32x3 (fp32-class), fp32 accumulate') if large else 'fp32',
+            'dtype': {'fused': 'fp16x3 split forward (fp32-class) / tf32 input gradients / fp16 weight-gradient '
+                               'operands, fp32 accumulate', 'tf32': 'tf32 operands, fp32 accumulate',
+                      'tf32x3': 'tf32x3 (fp32-class), fp32 accumulate'}[args.precision] if large else 'fp32',
             'data': 'synthetic',
             'config': config_of(wl, b_dim, world, args.scaling),
             'clocks': clocks,

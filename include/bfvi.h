@@ -180,17 +180,20 @@ typedef struct bfvi_step_args {
   float match_count;                    /* mask.sum() used by the prior-matching term
                                            (models/dmm.py:541); < 0 = count seq_mask here */
   const uint64_t* seed_dev;             /* nullable, see bfvi_noise.seed_dev (large-dim family) */
-  int32_t precision;                    /* large-dim family, GEMM operand precision: BFVI_PREC_TF32X3 (0) error-compensated
-                                           3xTF32 through the launch-sequence path (FP32-class, the parity reference of this
-                                           family); BFVI_PREC_TF32 (1) single-pass round-to-nearest TF32 through the FUSED
-                                           on-chip transition kernels (hidden activations never leave the SM; weight gradients
-                                           of the hidden layers contract FP16-rounded operands with FP32 accumulation) */
+  int32_t precision;                    /* large-dim family: BFVI_PREC_TF32X3 (0) error-compensated 3xTF32 through the
+                                           launch-sequence path (FP32-class everywhere); BFVI_PREC_TF32 (1) the same path with
+                                           single-pass TF32 operands; BFVI_PREC_FUSED (2) the FUSED on-chip transition kernels
+                                           where the shape is served (z_dim 64, h_dim a multiple of 128; otherwise mode 0):
+                                           hidden activations never leave the SM, forward contractions are error-compensated
+                                           FP16 hi/lo products (FP32-class: the ReLU signs match the reference's), the input
+                                           gradient contracts TF32 operands and the H-wide weight gradients FP16 operands,
+                                           all with FP32 accumulation */
   int32_t batch_tile;                   /* large-dim family: sequences per batch tile — the step loops over tiles with
                                            the gradient accumulated, so the workspace is O(batch_tile) and B is unbounded
                                            (SURVEY 7 "B = 65 536 at 1 GPU is a loop over batch tiles inside one step");
                                            0 = chosen by the library (bfvi_step_workspace reports the matching size) */
 } bfvi_step_args;
-enum { BFVI_PREC_TF32X3 = 0, BFVI_PREC_TF32 = 1 };
+enum { BFVI_PREC_TF32X3 = 0, BFVI_PREC_TF32 = 1, BFVI_PREC_FUSED = 2 };
 
 int bfvi_version(void);
 const char* bfvi_last_error(void);
@@ -421,9 +424,9 @@ int bfvi_wgrad_tf32(const float* dy_t, int64_t lddy, const float* x_t, int64_t l
                     void* stream);
 
 /* GaussianGTF.forward (models/common.py:62-68) on n_rows latent rows (z_dim 64, h_dim a multiple of 128) through the
- * FUSED on-chip kernels — the building block of the large-dim family's precision mode BFVI_PREC_TF32: per 128-row tile
+ * FUSED on-chip kernels — the building block of the large-dim family's mode BFVI_PREC_FUSED: per 128-row tile
  * z -> hidden -> heads runs as a chain of tcgen05 MMAs whose hidden activations stay in tensor memory; weights are
- * rounded to TF32 once and streamed by cp.async.bulk.  Outputs are the four pre-activation heads with their biases
+ * split into scaled FP16 hi / lo operand tiles once per call and streamed by cp.async.bulk.  Outputs are the four pre-activation heads with their biases
  * added, (n_rows, 64) each: gate_pre (before the sigmoid), nonlin, lin, std_pre (before softplus + min_std), so that
  * mean = (1 - sigmoid(gate_pre)) * lin + sigmoid(gate_pre) * nonlin and std = softplus(std_pre) + min_std.
  * keep != 0 also leaves the operands of bfvi_gtf_bwd in the workspace (bfvi_gtf_workspace(model, n_rows) bytes,

@@ -15,7 +15,7 @@ DIST_CODES = {'Normal': 0, 'Bernoulli': 1, 'Categorical': 2}
 DIR_FWD, DIR_BWD = 0, 1
 MODE_CODES = {'bfilter': 0, 'ffilter': 1, 'fsmooth': 2, 'bsmooth': 3}
 EXPERT_TENSOR, EXPERT_INV_PRIOR = 0, 1
-PRECISION_CODES = {'tf32x3': 0, 'tf32': 1}
+PRECISION_CODES = {'tf32x3': 0, 'tf32': 1, 'fused': 2}
 PHASES = ('match', 'encode_fwd', 'filter_f_fwd', 'filter_s_flt_fwd', 'filter_s_smt_fwd', 'decode_nll',
           'filter_s_smt_bwd', 'filter_s_flt_bwd', 'filter_f_bwd', 'encode_bwd', 'finalize')
 

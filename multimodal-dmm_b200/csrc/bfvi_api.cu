@@ -748,11 +748,14 @@ int fused_pack(const bfvi_gtf_layout& g, const float* params, int dir, int H, co
   pp.w_lin = params + g.lin_w; pp.b_lin = params + g.lin_b; pp.w_non0 = params + g.nonlin0_w; pp.b_non0 = params + g.nonlin0_b;
   pp.w_non2 = params + g.nonlin2_w; pp.b_non2 = params + g.nonlin2_b; pp.w_std = params + g.std_w; pp.b_std = params + g.std_b;
   pp.fwd = fb.pack_fwd[dir]; pp.bwd = fb.pack_bwd[dir]; pp.bias = fb.bias[dir]; pp.H = H;
+  auto ks = bfvi::fused::gtf_scale_kernel;
+  ks<<<dim3(6), dim3(256), 0, st>>>(pp);
   auto k = bfvi::fused::pack_gtf_kernel;
   k<<<dim3((unsigned)bfvi::fused::pack_blocks(H)), dim3(256), 0, st>>>(pp);
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
+constexpr size_t kFusedPatches = (size_t)4 * bfvi::fused::kPatchBytes;
 // heads of one transition for `rows` latent rows; keep = also write the operand tiles / ReLU bits the backward needs
 int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows, float* g, float* nl, float* lin, float* as,
               bool keep, cudaStream_t st) {
@@ -761,39 +764,46 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
   fp.pack = fb.pack_fwd[dir]; fp.bias = fb.bias[dir]; fp.z = z; fp.g = g; fp.nl = nl; fp.lin = lin; fp.as = as;
   fp.h16 = (__half*)fb.h16; fp.relu_bits = fb.bits; fp.z16 = (__half*)fb.z16;
   fp.R = rows; fp.H = H;
-  const size_t extra = bfvi::fused::bias_floats(H) * 4;
+  const size_t extra = bfvi::fused::bias_floats(H) * 4 + kFusedPatches;
   fp.n_stages = fused_stages(extra);
   if (fp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: h_dim %d too wide", H);
   const size_t smem = (size_t)fp.n_stages * bfvi::fused::kBlockBytes + extra + 1024;
   const int64_t tiles = (rows + 127) / 128;
   const int sms = num_sms() > 0 ? num_sms() : 1;
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  if (keep) {
-    auto k = bfvi::fused::gtf_fwd_kernel<true>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
-    note_dispatch("gtf_fwd_fused<keep> tf32 stages=%d", fp.n_stages);
-  } else {
-    auto k = bfvi::fused::gtf_fwd_kernel<false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
-    note_dispatch("gtf_fwd_fused tf32 stages=%d", fp.n_stages);
+  static const bool dbg = [] { const char* e = getenv("BFVI_FUSED_DBG"); return e && atoi(e) != 0; }();
+  long long* dbg_dev = nullptr;
+  if (dbg) { cudaMalloc(&dbg_dev, 16 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 16 * sizeof(long long), st); fp.dbg = dbg_dev; }
+  auto k = keep ? bfvi::fused::gtf_fwd_kernel<true> : bfvi::fused::gtf_fwd_kernel<false>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
+  note_dispatch("gtf_fwd_fused%s f16x3 stages=%d", keep ? "<keep>" : "", fp.n_stages);
+  if (dbg) {                           // development: where do the cycles of CTA 0 go?
+    cudaStreamSynchronize(st);
+    long long h[16];
+    cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(dbg_dev);
+    const double tpc = (double)((tiles + grid - 1) / grid), pairs = tpc * (H / 64);
+    fprintf(stderr, "[fused fwd dbg] rows %lld tiles/CTA %.0f | row warp 0 per PAIR: wait_d %.0f ld %.0f math %.0f st+arrive %.0f | tail+heads per tile %.0f | total %.0f per tile\n"
+                    "                issuer per PAIR: wait_a %.0f wait_blk %.0f issue %.0f\n",
+            (long long)rows, tpc, h[0] / pairs, h[1] / pairs, h[2] / pairs, h[3] / pairs, h[4] / tpc, h[5] / tpc,
+            h[8] / pairs, h[9] / pairs, h[10] / pairs);
   }
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
-// input gradient dz of one transition (the KEEP forward of the same rows must have run) + hidden bias gradients
+// input gradient dz of one transition (the KEEP forward of the same rows must have run)
 int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float* d_nl, const float* d_lin, int64_t rows,
-              float* dz, float* gb_gate0, float* gb_non0, cudaStream_t st) {
+              float* dz, cudaStream_t st) {
+  if (getenv("BFVI_DBG_SKIP_BWD")) return BFVI_OK;           // development: bisect a hang
   bfvi::fused::BwdParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.pack = fb.pack_bwd[dir]; bp.d_g = d_g; bp.d_nl = d_nl; bp.d_lin = d_lin; bp.relu_bits = fb.bits; bp.dz = dz;
   bp.dh16 = (__half*)fb.dh16; bp.dg16 = (__half*)fb.dg16; bp.dnl16 = (__half*)fb.dnl16;
-  bp.gb_gate0 = gb_gate0; bp.gb_non0 = gb_non0; bp.R = rows; bp.H = H;
-  const size_t extra = (size_t)2 * H * 4;
-  bp.n_stages = fused_stages(extra);
-  if (bp.n_stages < 5) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: h_dim %d too wide", H);
-  const size_t smem = (size_t)bp.n_stages * bfvi::fused::kBlockBytes + extra + 1024;
+  bp.R = rows; bp.H = H;
+  bp.n_stages = fused_stages(kFusedPatches);
+  if (bp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: no room for the weight ring");
+  const size_t smem = (size_t)bp.n_stages * bfvi::fused::kBlockBytes + kFusedPatches + 1024;
   const int64_t tiles = (rows + 127) / 128;
   const int sms = num_sms() > 0 ? num_sms() : 1;
   auto k = bfvi::fused::gtf_bwd_kernel;
@@ -803,20 +813,22 @@ int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 }
-// weight gradients of the four H-wide layers from the FP16 operand tiles of fused_fwd(keep) / fused_bwd
+// weight gradients of the four H-wide layers (+ the two hidden bias gradients) from the FP16 operand tiles of
+// fused_fwd(keep) / fused_bwd
 int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float* dw_non0, float* dw_gate2, float* dw_non2,
-                cudaStream_t st) {
+                float* gb_gate0, float* gb_non0, cudaStream_t st) {
+  if (getenv("BFVI_DBG_SKIP_WGRAD")) return BFVI_OK;         // development: bisect a hang
   bfvi::fused::Wgrad16Params wp;
   memset(&wp, 0, sizeof(wp));
   const int U = H / 64;
-  auto prob = [&](int i, const void* X, int atom0, const void* Y, float* out, int transposed) {
+  auto prob = [&](int i, const void* X, int atom0, const void* Y, float* out, int transposed, float* bias) {
     wp.pr[i].X = (const __half*)X; wp.pr[i].n_atoms_x = 2 * U; wp.pr[i].atom0 = atom0; wp.pr[i].Y = (const __half*)Y;
-    wp.pr[i].out = out; wp.pr[i].transposed = transposed;
+    wp.pr[i].out = out; wp.pr[i].transposed = transposed; wp.pr[i].bias = bias;
   };
-  prob(0, fb.dh16, 0, fb.z16, dw_gate0, 0);        // dW_gate0 (H, Z) = dh1^T z
-  prob(1, fb.dh16, U, fb.z16, dw_non0, 0);         // dW_nonlin0 (H, Z) = dh3^T z
-  prob(2, fb.h16, 0, fb.dg16, dw_gate2, 1);        // dW_gate2 (Z, H) = d_g^T h1, computed as h1^T d_g
-  prob(3, fb.h16, U, fb.dnl16, dw_non2, 1);        // dW_nonlin2 (Z, H) = d_nl^T h3
+  prob(0, fb.dh16, 0, fb.z16, dw_gate0, 0, gb_gate0);       // dW_gate0 (H, Z) = dh1^T z, b_gate0 = column sums of dh1
+  prob(1, fb.dh16, U, fb.z16, dw_non0, 0, gb_non0);         // dW_nonlin0 (H, Z) = dh3^T z
+  prob(2, fb.h16, 0, fb.dg16, dw_gate2, 1, nullptr);        // dW_gate2 (Z, H) = d_g^T h1, computed as h1^T d_g
+  prob(3, fb.h16, U, fb.dnl16, dw_non2, 1, nullptr);        // dW_nonlin2 (Z, H) = d_nl^T h3
   wp.n_problems = 4; wp.H = H;
   wp.n_groups = fused_rows_pad(rows) / 64;
   const int sms = num_sms() > 0 ? num_sms() : 1;
@@ -918,7 +930,7 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   pl->dhd = carve(f * pl->tb * H); pl->dhdT = carve(f * pl->tb * H);
   pl->dmean = carve(f * pl->tb * pl->d_max); pl->dstd = carve(f * pl->tb * pl->d_max);
   pl->dmeanT = carve(f * pl->tb * pl->d_max); pl->dstdT = carve(f * pl->tb * pl->d_max);
-  pl->fused = (a != nullptr && a->precision == BFVI_PREC_TF32 && fused_supported(Z, H)) ? 1 : 0;
+  pl->fused = (a != nullptr && a->precision == BFVI_PREC_FUSED && fused_supported(Z, H)) ? 1 : 0;
   pl->fused_packs = pl->fused_rows = 0;
   if (pl->fused) {
     cur = align_up(cur, 1024);
@@ -991,10 +1003,15 @@ static bool step4_ok(const bfvi::gen::StepParams& sp) {
   return sp.Z % 4 == 0 && (((uintptr_t)sp.g | (uintptr_t)sp.nl | (uintptr_t)sp.lin | (uintptr_t)sp.as | (uintptr_t)sp.zrows) & 15) == 0;
 }
 
+// One batch tile of a step that walks its batch in tiles (step_large_tiled): the loss accumulator and the mask count
+// live outside the tile's workspace, the gradient buffer is cleared by the first tile only, the prior-matching term
+// (linear in the GLOBAL mask count, models/dmm.py:541-545) is added by the first tile, the loss is finalised by the last.
+struct TileCtx { bool first, last; double* acc; const float* count; };
+
 // fonly != null: run only z_filter forward (fonly_backward = false) or backward on `fonly`
 int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
                const bfvi_filter_args* fonly, bool fonly_backward, void* workspace, size_t workspace_bytes,
-               float* loss_out, int32_t* launches, cudaStream_t st) {
+               float* loss_out, int32_t* launches, cudaStream_t st, const TileCtx* tile = nullptr) {
   // `pl`, `grads` and `st` are the CURRENT context of every helper below (captured by reference):
   // the main one, or — while pass A is being queued — the side scratch set, gradient buffer and stream
   LargePlan pl_main, pl_side;
@@ -1017,14 +1034,15 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   int n_launch = 0;
   auto F = [&](size_t off) { return (float*)(ws + off); };
   float* paramsT = F(pl.paramsT);
-  double* acc = (double*)(ws + pl.acc);
+  double* acc = tile ? tile->acc : (double*)(ws + pl.acc);
   float* count = F(pl.count);
+  const bool first_tile = tile == nullptr || tile->first, last_tile = tile == nullptr || tile->last;
   auto ew_grid = [&](int64_t n, int per) { return dim3((unsigned)grid_for(n, per, 16)); };
 
   if (!fonly) {                      // a lone filter ACCUMULATES into the caller's (zeroed) gradient buffers
     cudaMemsetAsync(ws + pl.zero_begin, 0, pl.zero_end - pl.zero_begin, st);
     cudaMemsetAsync(ws + pl_side.zero_begin, 0, pl_side.zero_end - pl_side.zero_begin, st);
-    if (with_grad) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
+    if (with_grad && first_tile) cudaMemsetAsync(grads, 0, sizeof(float) * (size_t)lay.total, st);
   }
   BFVI_CHECK_CUDA();
 
@@ -1116,7 +1134,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   };
   if (fused) {                        // weights rounded to TF32 and laid out as shared-memory images ONCE per step
     const FusedBufs fb = fbufs();
-    for (int d = 0; d < 2; ++d) { if (int rc = fused_pack(lay.trans[d], params, d, H, fb, st)) return rc; ++n_launch; }
+    for (int d = 0; d < 2; ++d) { if (int rc = fused_pack(lay.trans[d], params, d, H, fb, st)) return rc; n_launch += 2; }
   }
 #endif
   // ---- one transition: 6 forward GEMMs over `rows` particles --------------------------------
@@ -1160,10 +1178,10 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       if (int rc = flush()) return rc;
       const FusedBufs fb = fbufs();
       // input gradient with the hidden gradients on-chip (+ hidden bias gradients, FP16 operand tiles) ...
-      if (int rc = fused_bwd(fb, dir, H, F(pl.d_g), F(pl.d_nl), F(pl.d_lin), rows, F(pl.dz), grads + g.gate0_b,
-                             grads + g.nonlin0_b, st)) return rc;
-      // ... and the four H-wide weight gradients from those tiles
-      if (int rc = fused_wgrad(fb, H, rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w, st)) return rc;
+      if (int rc = fused_bwd(fb, dir, H, F(pl.d_g), F(pl.d_nl), F(pl.d_lin), rows, F(pl.dz), st)) return rc;
+      // ... and the four H-wide weight gradients (+ the two hidden bias gradients) from those tiles
+      if (int rc = fused_wgrad(fb, H, rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w,
+                               grads + g.gate0_b, grads + g.nonlin0_b, st)) return rc;
       n_launch += 2;
       return BFVI_OK;
     }
@@ -1268,11 +1286,13 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   const bool external = a->eps_filt != nullptr || a->eps_sflt != nullptr || a->eps_ssmt != nullptr ||
                         a->eps_match != nullptr;
   // ---- prior-matching term (models/dmm.py:540-545) -----------------------------------------
-  if (a->match_mult > 0.f) {
+  if (a->match_mult > 0.f && first_tile) {
     if (external && !a->eps_match) return fail(BFVI_ERR_ARG, "eps_match missing");
     const float* cnt = nullptr;
     float coef = a->match_mult * a->kld_mult;
-    if (a->match_count < 0.f) {
+    if (tile != nullptr && tile->count != nullptr) {
+      cnt = tile->count;                            // mask.sum() over the WHOLE batch, counted by the tile walker
+    } else if (a->match_count < 0.f) {
       auto k = bfvi::count_mask_kernel;
       BFVI_LAUNCH(k, dim3(grid_for(tb, 256, 4)), dim3(256), 0, st, a->seq_mask, tb, count);
       ++n_launch;
@@ -1557,10 +1577,119 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     }
   }
   if (int rc = flush()) return rc;
-  auto kfin = bfvi::finalize_loss_kernel;
-  BFVI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
+  if (last_tile) {
+    auto kfin = bfvi::finalize_loss_kernel;
+    BFVI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
+    BFVI_CHECK_CUDA();
+    ++n_launch;
+  }
+  if (launches) *launches = n_launch;
+  return BFVI_OK;
+}
+
+// ---- batch tiles -------------------------------------------------------------------------------------------
+// The workspace of a large-dim step is O(T * B) (saved posteriors / priors of three passes, encoder and decoder
+// activations: ~100 KB per sequence-timestep at the C3 shape), so B = 8 192 x T = 1 000 cannot be one piece.  Sequences
+// are independent: the step walks the batch in tiles of `bt` sequences — inputs / targets / mask of a tile are staged
+// into contiguous (T, bt, D) buffers (strided 2-D copies), the tile runs as a step of its own with the noise indexed by
+// the global sequence index, gradients and loss accumulate across tiles.
+size_t tile_budget_bytes() {
+  static const size_t b = [] { const char* e = getenv("BFVI_TILE_GB"); return (size_t)((e ? atof(e) : 40.0) * (double)(1ull << 30)); }();
+  return b;
+}
+struct TiledPlan { int bt, n_tiles; size_t acc, count, stage_in[BFVI_MAX_MODS], stage_tg[BFVI_MAX_MODS], stage_mask, tile_ws, tile_bytes, total; };
+int plan_tiled(const bfvi_model* m, const bfvi_step_args* a, TiledPlan* tp) {
+  const int B = a->B, T = a->T;
+  auto tile_bytes_of = [&](int bt) {
+    bfvi_step_args at = *a;
+    at.B = bt;
+    LargePlan lp, ls;
+    plan_large(m, &at, nullptr, &lp);
+    plan_large_side(m, &at, lp, &ls);
+    return ls.total;
+  };
+  int bt = a->batch_tile > 0 ? a->batch_tile : B;
+  if (bt > B) bt = B;
+  if (a->batch_tile <= 0 && tile_bytes_of(B) > tile_budget_bytes()) {
+    // workspace is affine in the batch: fit the budget, keep tiles a multiple of 64 sequences
+    const size_t b1 = tile_bytes_of(64), b2 = tile_bytes_of(128);
+    const double per = (double)(b2 - b1) / 64.0;
+    const double fixed = (double)b1 - 64.0 * per;
+    int fit = (int)(((double)tile_budget_bytes() - fixed) / per);
+    fit = fit / 64 * 64;
+    if (fit < 64) fit = 64;
+    bt = fit < B ? fit : B;
+    // equalise: same tile count, smaller last-tile imbalance
+    const int n = (B + bt - 1) / bt;
+    bt = ((B + n - 1) / n + 63) / 64 * 64;
+    if (bt > B) bt = B;
+  }
+  tp->bt = bt;
+  tp->n_tiles = (B + bt - 1) / bt;
+  size_t cur = 0;
+  auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+  tp->acc = carve(sizeof(double)); tp->count = carve(sizeof(float));
+  if (tp->n_tiles > 1) {
+    for (int i = 0; i < m->n_mods; ++i) {
+      tp->stage_in[i] = carve(sizeof(float) * (size_t)T * bt * m->dims[i]);
+      tp->stage_tg[i] = carve(sizeof(float) * (size_t)T * bt * m->dims[i]);
+    }
+    tp->stage_mask = carve((size_t)T * bt);
+  }
+  tp->tile_ws = carve(0);
+  tp->tile_bytes = tile_bytes_of(bt);
+  tp->total = tp->tile_ws + tp->tile_bytes;
+  return BFVI_OK;
+}
+int step_large_tiled(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a, void* workspace,
+                     size_t workspace_bytes, float* loss_out, int32_t* launches, cudaStream_t st) {
+  TiledPlan tp;
+  plan_tiled(m, a, &tp);
+  if (workspace_bytes < tp.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, tp.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  char* ws = (char*)workspace;
+  if (tp.n_tiles == 1)
+    return step_large(m, params, grads, a, nullptr, false, ws + tp.tile_ws, tp.tile_bytes, loss_out, launches, st);
+  note_dispatch("step:batch_tiles=%d x %d", tp.n_tiles, tp.bt);
+  const int T = a->T, B = a->B;
+  double* acc = (double*)(ws + tp.acc);
+  float* count = (float*)(ws + tp.count);
+  cudaMemsetAsync(acc, 0, sizeof(double), st);
+  cudaMemsetAsync(count, 0, sizeof(float), st);
+  int n_launch = 0;
+  if (a->match_mult > 0.f) {                          // mask.sum() of the whole batch (or the caller's count)
+    if (a->match_count < 0.f) {
+      auto k = bfvi::count_mask_kernel;
+      BFVI_LAUNCH(k, dim3(grid_for((int64_t)T * B, 256, 4)), dim3(256), 0, st, a->seq_mask, (int64_t)T * B, count);
+      ++n_launch;
+    }                                                 // else: the tiles use the caller's count (static coefficient)
+  }
   BFVI_CHECK_CUDA();
-  ++n_launch;
+  for (int i = 0; i < tp.n_tiles; ++i) {
+    const int b0 = i * tp.bt, bc = b0 + tp.bt <= B ? tp.bt : B - b0;
+    bfvi_step_args at = *a;
+    at.B = bc;
+    at.b_offset = a->b_offset + (uint32_t)b0;
+    for (int k = 0; k < m->n_mods; ++k) {
+      const size_t D = (size_t)m->dims[k];
+      float* si = (float*)(ws + tp.stage_in[k]);
+      float* sg = (float*)(ws + tp.stage_tg[k]);
+      cudaMemcpy2DAsync(si, bc * D * 4, a->inputs[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, st);
+      cudaMemcpy2DAsync(sg, bc * D * 4, a->targets[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, st);
+      at.inputs[k] = si; at.targets[k] = sg;
+    }
+    uint8_t* sm = (uint8_t*)(ws + tp.stage_mask);
+    cudaMemcpy2DAsync(sm, bc, a->seq_mask + b0, B, bc, T, cudaMemcpyDeviceToDevice, st);
+    at.seq_mask = sm;
+    if (a->eps_match || a->eps_filt || a->eps_sflt || a->eps_ssmt)
+      return fail(BFVI_ERR_UNSUPPORTED, "external noise tensors with batch tiles: pass batch_tile >= B (parity runs are small)");
+    BFVI_CHECK_CUDA();
+    TileCtx tc;
+    tc.first = i == 0; tc.last = i == tp.n_tiles - 1; tc.acc = acc; tc.count = a->match_count < 0.f ? count : nullptr;
+    int32_t l = 0;
+    if (int rc = step_large(m, params, grads, &at, nullptr, false, ws + tp.tile_ws, tp.tile_bytes, loss_out, &l, st, &tc)) return rc;
+    n_launch += l;
+  }
   if (launches) *launches = n_launch;
   return BFVI_OK;
 }
@@ -2172,8 +2301,9 @@ int bfvi_gtf_bwd(const bfvi_model* m, const float* params, float* grads, int32_t
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_gate_pre, nullptr, n_rows, nullptr, grads + g.gate2_b);
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_nl, nullptr, n_rows, nullptr, grads + g.nonlin2_b);
   BFVI_CHECK_CUDA();
-  if (int rc = fused_bwd(fb, direction, m->h_dim, d_gate_pre, d_nl, d_lin, n_rows, d_z, grads + g.gate0_b, grads + g.nonlin0_b, st)) return rc;
-  return fused_wgrad(fb, m->h_dim, n_rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w, st);
+  if (int rc = fused_bwd(fb, direction, m->h_dim, d_gate_pre, d_nl, d_lin, n_rows, d_z, st)) return rc;
+  return fused_wgrad(fb, m->h_dim, n_rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w,
+                     grads + g.gate0_b, grads + g.nonlin0_b, st);
 #endif
 }
 
@@ -2220,7 +2350,7 @@ static int check_step(const bfvi_model* m, const bfvi_step_args* a) {
   if (a->f_mode != BFVI_MODE_BFILTER && a->f_mode != BFVI_MODE_FFILTER) return fail(BFVI_ERR_ARG, "bad f_mode");
   if (a->s_mode != BFVI_MODE_FSMOOTH && a->s_mode != BFVI_MODE_BSMOOTH) return fail(BFVI_ERR_ARG, "bad s_mode");
   if (a->train_particles < 1 || a->match_particles < 1) return fail(BFVI_ERR_ARG, "particle counts must be >= 1");
-  if (a->precision != BFVI_PREC_TF32X3 && a->precision != BFVI_PREC_TF32) return fail(BFVI_ERR_ARG, "bad precision");
+  if (a->precision < BFVI_PREC_TF32X3 || a->precision > BFVI_PREC_FUSED) return fail(BFVI_ERR_ARG, "bad precision");
   if (a->batch_tile < 0) return fail(BFVI_ERR_ARG, "batch_tile < 0");
   return BFVI_OK;
 }
@@ -2229,10 +2359,9 @@ int bfvi_step_workspace(const bfvi_model* m, const bfvi_step_args* a, size_t* by
   if (int rc = check_step(m, a)) return rc;
   if (!bytes) return fail(BFVI_ERR_ARG, "bytes null");
   if (family_of(m->z_dim, m->h_dim) == 2) {
-    LargePlan lp, ls;
-    plan_large(m, a, nullptr, &lp);
-    plan_large_side(m, a, lp, &ls);
-    *bytes = ls.total;
+    TiledPlan tp;
+    plan_tiled(m, a, &tp);
+    *bytes = tp.total;
     return BFVI_OK;
   }
   StepPlan pl;
@@ -2264,8 +2393,7 @@ static int step_impl(const bfvi_model* m, const float* params, float* grads, con
     if (!a->inputs[i] || !a->targets[i]) return fail(BFVI_ERR_ARG, "inputs/targets[%d] null", i);
   if (family_of(m->z_dim, m->h_dim) == 2) {
     if (pm.on) return fail(BFVI_ERR_UNSUPPORTED, "phase profile exists for the small-dim family only");
-    return step_large(m, params, grads, a, nullptr, false, workspace, workspace_bytes, loss_out, launches,
-                      (cudaStream_t)stream);
+    return step_large_tiled(m, params, grads, a, workspace, workspace_bytes, loss_out, launches, (cudaStream_t)stream);
   }
   if (a->seed_dev != nullptr) return fail(BFVI_ERR_UNSUPPORTED, "seed_dev (graph-replayable seed) exists for the large-dim family only");
   const bool with_grad = grads != nullptr;

@@ -1,4 +1,4 @@
-// bfvi_fused.cuh — fused on-chip GaussianGTF kernels of the large-dim family (precision mode BFVI_PREC_TF32).
+// bfvi_fused.cuh — fused on-chip GaussianGTF kernels of the large-dim family (precision mode BFVI_PREC_FUSED).
 //
 // One transition evaluation (models/common.py:62-68) on a tile of 128 latent rows (rows = chains x particles of one
 // time step, models/dmm.py:239-258) is a chain of dense contractions
@@ -9,25 +9,40 @@
 // them to HBM and reads them back between launches: ~10 MB of DRAM traffic per sequence-timestep at the C3 shape
 // against 1 KB of algorithmic bytes (profiles/r1_particle_pass_ncu.txt).  Here they never leave the SM:
 //
-//   gtf_fwd_kernel   per row tile, per unit of 64 hidden columns:  tcgen05.mma D = z W0u^T into TMEM  ->  row warps
-//                    tcgen05.ld, + bias, ReLU, round to TF32, tcgen05.st back IN PLACE as the A operand  ->
-//                    tcgen05.mma head += A W2u^T.  z itself is the A operand from TMEM (one tcgen05.st per tile).
-//                    Heads (pre-sigmoid gate, nonlinear, linear, pre-softplus std) leave as (R, Z) fp32 rows.
-//                    KEEP mode (the backward recompute): also writes the hidden activations as FP16 operand tiles
-//                    for the weight-gradient GEMM, the ReLU sign bits (64 per row and unit) and an FP16 copy of z.
-//   gtf_bwd_kernel   same pipeline for the input gradient:  D = d_head W2u  ->  mask by the ReLU bits, column sums
-//                    (bias gradients), FP16 tile for the weight gradients, round, A in place  ->  dz += A W0u.
+//   gtf_fwd_kernel   per row tile, per PAIR of 64-column hidden units (gate unit c, nonlinear unit c):
+//                    tcgen05.mma D[128,128] = z [W0g_c ; W0n_c]^T into TMEM (one N = 128 instruction stream for both
+//                    branches)  ->  row warps tcgen05.ld, scale + bias, ReLU, split into FP16 hi | lo, tcgen05.st back
+//                    IN PLACE as the A operands  ->  tcgen05.mma gate head += A_g W2g_c^T, nonlinear head += A_n W2n_c^T.
+//                    z itself is an A operand in TMEM (one tcgen05.st per tile).  Heads (pre-sigmoid gate, nonlinear,
+//                    linear, pre-softplus std) leave as (R, Z) fp32 rows.  KEEP mode (the backward recompute) also writes
+//                    the hidden activations as FP16 operand tiles for the weight-gradient GEMM, the ReLU sign bits
+//                    (64 per row and unit) and an FP16 tile of z.
+//   gtf_bwd_kernel   same pipeline for the input gradient:  D = d_head W2u  ->  mask by the ReLU bits, FP16 tile for the
+//                    weight gradients, round to TF32, A in place  ->  dz += A W0u.
 //   wgrad16_kernel   dW^T[H, Z] += X^T Y over all rows: X (hidden activations / their gradients) and Y (z / head
 //                    gradients) are the FP16 tiles the two kernels above wrote in the MN-major SWIZZLE_128B shared-memory
-//                    image, so a stage is three cp.async.bulk copies; kind::f16 MMAs, FP32 accumulation in TMEM over a
-//                    slice of the rows, one red.global.add pass per work item.
+//                    image, so a stage is two cp.async.bulk copies; kind::f16 MMAs, FP32 accumulation in TMEM over a
+//                    slice of the rows, one red.global.add pass per work item; the otherwise idle epilogue warps sum the
+//                    columns of the hidden-gradient tiles in shared memory (bias gradients).
 //
-// Weights: tf32-rounded ONCE per step into the exact shared-memory image of every unit (pack_gtf_kernel: K-major
-// SWIZZLE_128B tiles, 32 KB per unit) and streamed through a ring of stages by ONE thread with cp.async.bulk
-// (global -> shared, mbarrier complete_tx) — no per-tile rounding pass, no LDGSTS, no converter warps.
+// Precision.  Forward contractions are error-compensated FP16 products: every operand x is split into hi = fp16(x),
+// lo = fp16(x - hi) and a_hi b_hi + a_lo b_hi + a_hi b_lo accumulates in FP32 (~2^-21 relative per product; weights are
+// pre-scaled by a power of two per layer so that their residuals are normal FP16 numbers).  That is FP32-class, and it has
+// to be: the ReLU derivative is discontinuous, so a hidden pre-activation whose SIGN differs from the reference's flips a
+// whole gradient term — with single-pass TF32 hidden layers d_z was off by 8e-3 (tests/test_gpu_fused.py).  Gradients
+// contract single-pass TF32 (input gradient) and FP16 (H-wide weight gradients) operands with FP32 accumulation.
+//
+// Weights are laid out ONCE per step as the exact shared-memory images of every operand tile (pack_gtf_kernel, K-major
+// SWIZZLE_128B) and streamed through a ring of 32 KB stages by ONE thread with cp.async.bulk (global -> shared, mbarrier
+// complete_tx; measured 57 B/clk per SM from L2 with all 148 SMs pulling, tools/probe_bulk_rate.cu) — no per-tile
+// rounding pass, no LDGSTS, no converter warps.  Row results leave through padded shared-memory patches and one
+// cp.async.bulk (shared -> global) per row segment: a thread = row layout otherwise touches 32 cache lines per store
+// instruction.
 //
 // Warp roles (320 threads): warps 0-7 "row warps" (thread = tile row = TMEM lane; two warps per 32-lane quadrant, one
 // per 32-column half), warp 8 MMA issuer (one elected thread), warp 9 weight loader (one elected thread).
+// Measured on B200 (tools/probe_mma_rate.cu): one M = 128 tcgen05.mma costs 52 / 67 / 131 cycles at N = 64 / 128 / 256
+// whatever the kind or the A source — N = 64 instructions run the tensor pipe at 61 % — hence the N = 128 hidden layers.
 #pragma once
 #include "bfvi_platform.cuh"
 #include "bfvi_tc.cuh"
@@ -42,26 +57,32 @@ namespace fused {
 constexpr int kZ = 64;                 // latent width served by the fused kernels
 constexpr int kHU = 64;                // hidden columns per unit
 constexpr int kTileRows = 128;         // rows per tile (UMMA M)
-constexpr int kBlockBytes = 32768;     // one weight block: two 64 x 64 tf32 operand tiles
+constexpr int kBlockBytes = 32768;     // one weight block (one ring stage)
 constexpr int kTileBytes = 16384;
 constexpr int kRowWarps = 8;
 constexpr int kThreads = (kRowWarps + 2) * 32;
 constexpr int kMaxStages = 6;
 constexpr int kRowGroup = 64;          // rows per FP16 operand tile of the weight-gradient GEMM (one K stage)
 constexpr int kAtomBytes = 8192;       // 64 rows x 64 halves, MN-major SWIZZLE_128B
+constexpr int kPatchBytes = 8192;      // per 32-lane quadrant (two row warps): 32 rows x 256 B, or two 32 x 128 B halves
 
 // shared-memory image of a 64 x 64 fp32 operand tile, K-major SWIZZLE_128B: two K halves of 32 floats; row r of a
 // half is one 128-byte line whose 16-byte chunks are XOR-permuted by r % 8 (8-row groups 1024 B apart)
 __host__ __device__ inline int tile_offset(int r, int k) {
   return (k >> 5) * 8192 + r * 128 + (((((k & 31) >> 2) ^ (r & 7))) << 4) + (k & 3) * 4;
 }
+// FP16 operand tile with 64 K values per row (one 128-byte line per row), element (row r, k)
+__host__ __device__ inline int tile16_offset(int r, int k) { return r * 128 + (((k >> 3) ^ (r & 7)) << 4) + (k & 7) * 2; }
 
-// Weight packs of one GaussianGTF.  FWD: blocks 0..2U-1 = units (gate branch first), block 2U = tail.
-//   unit block: tile 0 = W0[unit rows, :] (N = hidden, K = z), tile 1 = W2[:, unit cols] (N = z, K = hidden)
-//   tail block: tile 0 = W_lin, tile 1 = W_std
-// BWD: block 0 = head (tile 1 = W_lin^T), blocks 1..2U = units:
+// Weight packs of one GaussianGTF, 2U + 1 blocks of 32 KB each (U = H / 64).
+// FWD (FP16 hi | lo tiles, weights scaled by a power of two per layer):
+//   block 2c     hidden layers of pair c: 128 rows (64 gate units, 64 nonlinear units) x K = z: hi 16 KB | lo 16 KB
+//   block 2c + 1 head layers of pair c: gate W2[:, unit cols] (N = z, K = hidden) hi 8 KB | lo 8 KB, then nonlinear
+//   block 2U     tail: W_lin hi | lo, W_std hi | lo
+// BWD (TF32 tiles): block 0 = head (tile 1 = W_lin^T), blocks 1..2U = units (gate branch first):
 //   tile 0 = W2[:, unit cols]^T (N = hidden, K = z_out), tile 1 = W0[unit rows, :]^T (N = z_in, K = hidden)
-// followed by the bias table: b0 gate (H), b0 nonlin (H), gate2_b, nonlin2_b, lin_b, std_b (Z each).
+// Bias table: b0 gate (H), b0 nonlin (H), gate2_b, nonlin2_b, lin_b, std_b (Z each), then 8 floats: 1 / scale of
+// gate0, nonlin0, gate2, nonlin2, lin, std (+ 2 spares).
 struct PackParams {
   const float* w_gate0; const float* b_gate0; const float* w_gate2; const float* b_gate2;
   const float* w_lin; const float* b_lin; const float* w_non0; const float* b_non0;
@@ -71,34 +92,73 @@ struct PackParams {
 };
 inline size_t pack_blocks(int H) { return (size_t)(2 * (H / kHU) + 1); }
 inline size_t pack_bytes(int H) { return pack_blocks(H) * kBlockBytes; }
-inline size_t bias_floats(int H) { return (size_t)2 * H + 4 * kZ; }
+inline size_t bias_floats(int H) { return (size_t)2 * H + 4 * kZ + 8; }
 
 #ifndef BFVI_EMU
 using tc::smem_u32;
 using tc::mbar_init; using tc::mbar_wait; using tc::mbar_arrive; using tc::umma_commit;
 using tc::tmem_alloc; using tc::tmem_dealloc; using tc::tmem_ld32; using tc::tc_fence_before; using tc::tc_fence_after;
 using tc::umma_desc_sw128; using tc::umma_idesc_tf32; using tc::umma_tf32_ts; using tc::rn_tf32; using tc::tmem_wait_st;
+using tc::fence_async_smem;
+
+// power-of-two scale of one layer: max |w| * s in [2^13, 2^14)
+__global__ void __launch_bounds__(256) gtf_scale_kernel(const __grid_constant__ PackParams p) {
+  __shared__ float red[256];
+  const int H = p.H, layer = blockIdx.x;
+  const float* w = layer == 0 ? p.w_gate0 : layer == 1 ? p.w_non0 : layer == 2 ? p.w_gate2 : layer == 3 ? p.w_non2
+                   : layer == 4 ? p.w_lin : p.w_std;
+  const int n = layer < 4 ? H * kZ : kZ * kZ;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float a = fabsf(w[i]);
+    m = (a > m && a < 3.0e38f) ? a : m;              // ignore inf / NaN weights: they poison the step anyway
+  }
+  red[threadIdx.x] = m;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    float inv = 1.f;
+    if (red[0] > 0.f) {
+      int e;
+      frexpf(red[0], &e);                            // red[0] = f * 2^e, f in [0.5, 1)  ->  max * 2^(14 - e) in [2^13, 2^14)
+      inv = ldexpf(1.f, e - 14);
+    }
+    p.bias[2 * H + 4 * kZ + layer] = inv;
+  }
+}
+
+__device__ __forceinline__ void put_split(unsigned char* hi_tile, int lo_off, int off, float x) {
+  const __half hi = __float2half_rn(x);
+  *reinterpret_cast<__half*>(hi_tile + off) = hi;
+  *reinterpret_cast<__half*>(hi_tile + lo_off + off) = __float2half_rn(x - __half2float(hi));
+}
 
 __global__ void __launch_bounds__(256) pack_gtf_kernel(const __grid_constant__ PackParams p) {
   const int H = p.H, U = H / kHU, nb = 2 * U + 1;
   const int b = blockIdx.x;                                  // block index, both packs
-  float* fw = reinterpret_cast<float*>(p.fwd + (size_t)b * kBlockBytes);
+  unsigned char* fw = p.fwd + (size_t)b * kBlockBytes;
   float* bw = reinterpret_cast<float*>(p.bwd + (size_t)b * kBlockBytes);
+  const float* inv = p.bias + 2 * H + 4 * kZ;                // written by gtf_scale_kernel (previous launch)
   for (int e = threadIdx.x; e < 2 * 64 * 64; e += blockDim.x) {
     const int t = e >> 12, r = (e >> 6) & 63, k = e & 63;
-    const int off = (t * kTileBytes + tile_offset(r, k)) >> 2;
-    // ---- forward pack
-    float v;
-    if (b < 2 * U) {
-      const int br = b / U, c = b % U;
-      const float* w0 = br ? p.w_non0 : p.w_gate0;
-      const float* w2 = br ? p.w_non2 : p.w_gate2;
-      v = t == 0 ? w0[(size_t)(c * kHU + r) * kZ + k] : w2[(size_t)r * H + c * kHU + k];
-    } else {
-      v = t == 0 ? p.w_lin[r * kZ + k] : p.w_std[r * kZ + k];
+    // ---- forward pack (x / inv is exact: inv is a power of two)
+    if (b == 2 * U) {                                        // tail: lin | std
+      const float v = t == 0 ? p.w_lin[r * kZ + k] / inv[4] : p.w_std[r * kZ + k] / inv[5];
+      put_split(fw + t * kTileBytes, 8192, tile16_offset(r, k), v);
+    } else if ((b & 1) == 0) {                               // hidden layers of pair c: rows 0-63 gate, 64-127 nonlinear
+      const int c = b >> 1;
+      const float v = t == 0 ? p.w_gate0[(size_t)(c * kHU + r) * kZ + k] / inv[0] : p.w_non0[(size_t)(c * kHU + r) * kZ + k] / inv[1];
+      put_split(fw, kTileBytes, tile16_offset(t * 64 + r, k), v);
+    } else {                                                 // head layers of pair c: gate | nonlinear
+      const int c = b >> 1;
+      const float v = t == 0 ? p.w_gate2[(size_t)r * H + c * kHU + k] / inv[2] : p.w_non2[(size_t)r * H + c * kHU + k] / inv[3];
+      put_split(fw + t * kTileBytes, 8192, tile16_offset(r, k), v);
     }
-    fw[off] = rn_tf32(v);
     // ---- backward pack
+    float v;
     if (b == 0) {
       v = t == 0 ? 0.f : p.w_lin[k * kZ + r];
     } else {
@@ -107,7 +167,7 @@ __global__ void __launch_bounds__(256) pack_gtf_kernel(const __grid_constant__ P
       const float* w2 = br ? p.w_non2 : p.w_gate2;
       v = t == 0 ? w2[(size_t)k * H + c * kHU + r] : w0[(size_t)(c * kHU + k) * kZ + r];
     }
-    bw[off] = rn_tf32(v);
+    bw[(t * kTileBytes + tile_offset(r, k)) >> 2] = rn_tf32(v);
   }
   if (b == nb - 1) {
     for (int i = threadIdx.x; i < H; i += blockDim.x) { p.bias[i] = p.b_gate0[i]; p.bias[H + i] = p.b_non0[i]; }
@@ -131,6 +191,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(src), "r"(bytes), "r"(smem_u32(mbar))
                : "memory");
 }
+// TMA bulk copy shared -> global (SASS: UBLKCP.G.S), tracked by the thread's bulk async-group
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One elected lane of a CONVERGED warp (ptxas knows the guarded region runs in a single thread and keeps the tcgen05
+// operands in uniform registers; a `lane == 0` test gives it no such guarantee).  Always elects the same lane.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 // 32 lanes x 32 consecutive fp32 columns, registers -> TMEM
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
   asm volatile(
@@ -147,6 +223,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
       "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void load_row32(const float* __restrict__ src, bool ok, float (&v)[32]) {
   if (ok) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -160,19 +244,41 @@ __device__ __forceinline__ void load_row32(const float* __restrict__ src, bool o
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }
 }
-__device__ __forceinline__ void store_row32(float* __restrict__ dst, const float (&v)[32]) {
-  float4* d4 = reinterpret_cast<float4*>(dst);
+// Row results leave through "pair patches": the two row warps of a 32-lane quadrant (column halves 0 and 1) share an
+// 8 KB shared-memory patch that holds the 32 rows exactly as they lie in global memory, so ONE elected thread sends them
+// with ONE cp.async.bulk (per-thread bulk copies were measured at ~50 cycles of TMA issue each: 256 of them per unit).
+// Named barrier 1 + q orders the two warps around the patch.
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
+
+// 32 rows x 64 fp32 columns (256 B per row, 8 KB): thread (row = lane, half hf) writes its 128 bytes.  `n_valid` rows of
+// the quadrant exist (the copy is clipped to them).  Shared-memory writes are 8-way bank conflicted (rows are 64 words
+// apart): once per tile and head, not worth a transposition.
+__device__ __forceinline__ void store_rows_f32(unsigned char* pp, int q, int lane, int hf, bool elected, float* __restrict__ dst_row0,
+                                               int n_valid, const float (&v)[32]) {
+  if (elected) bulk_wait_read<0>();
+  pair_sync(q);
+  float4* s4 = reinterpret_cast<float4*>(pp + lane * 256 + hf * 128);
 #pragma unroll
-  for (int q = 0; q < 8; ++q) d4[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  for (int i = 0; i < 8; ++i) s4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  fence_async_smem();
+  pair_sync(q);
+  if (elected) {
+    if (n_valid > 0) bulk_s2g(dst_row0, pp, (uint32_t)n_valid * 256u);
+    bulk_commit();
+  }
 }
 // FP16 operand tiles of the weight-gradient GEMM: (row group of 64 rows) x (atom of 64 columns) = 8 KB, row r of the
 // group is a 128-byte line, 16-byte chunk c stored at c ^ (r % 8): the MN-major SWIZZLE_128B shared-memory image, so
-// the GEMM loads a tile with one bulk copy.  A thread (row, 32-column half) writes its four chunks.
-__device__ __forceinline__ void store_half32(__half* __restrict__ base, int64_t row, int n_atoms, int atom, int hf,
-                                             const float (&v)[32]) {
-  unsigned char* tile = reinterpret_cast<unsigned char*>(base) +
-                        ((size_t)(row / kRowGroup) * n_atoms + atom) * kAtomBytes + (size_t)(row % kRowGroup) * 128;
-  const int sw = (int)(row & 7);
+// the GEMM loads a tile with one bulk copy.  The quadrant's 32 rows are 4 KB contiguous in that image; thread (row,
+// half) writes its four chunks (conflict-free thanks to the XOR) into half `buf` of the pair patch, which leaves as one
+// 4 KB bulk copy.  Tiles are padded to whole row tiles, so rows past the end are written (as zeros) too.
+__device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int q, int lane, int hf, bool elected,
+                                               __half* __restrict__ base, int64_t row0, int n_atoms, int atom,
+                                               const float (&v)[32]) {
+  if (elected) bulk_wait_read<1>();                  // the copy that used this half two stores ago has read it
+  pair_sync(q);
+  unsigned char* prow = pp + buf * 4096 + lane * 128;
+  const int sw = lane & 7;                           // row0 is a multiple of 32
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint4 pk;
@@ -180,13 +286,64 @@ __device__ __forceinline__ void store_half32(__half* __restrict__ base, int64_t 
     __half2 h2 = __floats2half2_rn(v[8 * c + 4], v[8 * c + 5]), h3 = __floats2half2_rn(v[8 * c + 6], v[8 * c + 7]);
     pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-    *reinterpret_cast<uint4*>(tile + (((hf * 4 + c) ^ sw) << 4)) = pk;
+    *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ sw) << 4)) = pk;
+  }
+  fence_async_smem();
+  pair_sync(q);
+  if (elected) {
+    unsigned char* tile = reinterpret_cast<unsigned char*>(base) +
+                          ((size_t)(row0 / kRowGroup) * n_atoms + atom) * kAtomBytes + (size_t)(row0 % kRowGroup) * 128;
+    bulk_s2g(tile, pp + buf * 4096, 4096);
+    bulk_commit();
+  }
+  buf ^= 1;
+}
+
+// kind::f16 with FP16 operands, FP32 accumulate, both operands K-major; the A operand from tensor memory (two halves
+// per 32-bit column: 8 columns = one K = 16 instruction)
+__device__ __forceinline__ uint32_t umma_idesc_f16_k(int M, int N) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate));
+}
+// A thread's 32 fp32 values -> the A operand of a 64-wide contraction in tensor memory as FP16 pairs: 16 columns of
+// hi = fp16(x) followed by 16 columns of lo = fp16(x - hi), INSIDE the thread's own 32-column half (so the in-place
+// D -> A rewrite never touches columns the other half-warp still has to read).  k-step ks (16 values) reads hi at
+// (ks >> 1) * 32 + (ks & 1) * 8 and lo 16 columns further.
+__device__ __forceinline__ void store_a_split(uint32_t taddr_half, const float (&v)[32]) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y);
+    hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+    lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+  }
+  tmem_st16u(taddr_half, hi);
+  tmem_st16u(taddr_half + 16, lo);
+}
+// D[128, N] (+)= A[128, 64] B[N, 64]^T as three FP16 products; A (hi | lo pairs) from tensor memory, B tiles hi at
+// tile_addr and lo at tile_addr + lo_off (one 128-byte line per row)
+__device__ __forceinline__ void mma_split(uint32_t tb, uint32_t d_col, uint32_t a_col, uint32_t tile_addr, uint32_t lo_off,
+                                          bool fresh, uint32_t idesc) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint32_t ah = tb + a_col + (ks >> 1) * 32 + (ks & 1) * 8, al = ah + 16;
+    const uint64_t bh = umma_desc_sw128(tile_addr + ks * 32), bl = umma_desc_sw128(tile_addr + lo_off + ks * 32);
+    umma_f16_ts(tb + d_col, ah, bh, idesc, (fresh && ks == 0) ? 0u : 1u);
+    umma_f16_ts(tb + d_col, al, bh, idesc, 1u);
+    umma_f16_ts(tb + d_col, ah, bl, idesc, 1u);
   }
 }
 
 struct FwdParams {
   const unsigned char* pack;     // forward pack
-  const float* bias;             // bias table (see PackParams)
+  const float* bias;             // bias + scale table (see PackParams)
   const float* z;                // (R, 64)
   float* g; float* nl; float* lin; float* as;      // (R, 64) heads, biases added
   __half* h16;                   // KEEP: hidden activations, FP16 tiles [row group][2U atoms]
@@ -195,10 +352,15 @@ struct FwdParams {
   int64_t R;
   int H;
   int n_stages;
+  long long* dbg;                // development: cycle counters of CTA 0 (BFVI_FUSED_DBG=1), nullable
 };
+#define BFVI_DBG_T(var) const long long var = p.dbg ? clock64() : 0
+#define BFVI_DBG_ADD(i, t0) do { if (p.dbg && blockIdx.x == 0 && lane == 0) dbg_acc[i] += clock64() - (t0); } while (0)
 
-// TMEM columns of the forward kernel
-constexpr uint32_t kFZ = 0, kFG = 64, kFNL = 128, kFLIN = 192, kFAS = 256, kFHB = 320;   // 3 hidden buffers of 64
+// TMEM columns of the forward kernel: z (A operand), gate / nonlinear head accumulators, two 128-column pair buffers
+// (hidden pre-activations, rewritten in place as A operands), the linear head accumulator.  The tail reuses buffer 0
+// (the nonlinear head as A operand) and buffer 1 (std head accumulator).
+constexpr uint32_t kFZ = 0, kFG = 64, kFNL = 128, kFB = 192, kFLIN = 448;
 
 template <bool KEEP>
 __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_constant__ FwdParams p) {
@@ -206,14 +368,15 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
   __shared__ __align__(8) uint64_t full_bar[kMaxStages];
   __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t z_full, units_done, tail_a, heads_full, heads_empty;
-  __shared__ __align__(8) uint64_t d_full[3];
-  __shared__ __align__(8) uint64_t a_full[3];
+  __shared__ __align__(8) uint64_t d_full[2];
+  __shared__ __align__(8) uint64_t a_full[2];
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = fused_smem_dyn + ((1024u - (smem_u32(fused_smem_dyn) & 1023u)) & 1023u);
   const int n_stages = p.n_stages;
-  float* bias_s = reinterpret_cast<float*>(smem + (size_t)n_stages * kBlockBytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, U = H / kHU, U2 = 2 * U, n_blocks = U2 + 1;
+  unsigned char* patches = smem + (size_t)n_stages * kBlockBytes;
+  float* bias_s = reinterpret_cast<float*>(patches + 4 * kPatchBytes);
   const int64_t n_tiles = (p.R + kTileRows - 1) / kTileRows;
   const int my_tiles = ((int64_t)blockIdx.x < n_tiles) ? (int)((n_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0;
 
@@ -222,20 +385,26 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&z_full, kRowWarps); mbar_init(&units_done, 1); mbar_init(&tail_a, kRowWarps);
     mbar_init(&heads_full, 1); mbar_init(&heads_empty, kRowWarps);
-    for (int i = 0; i < 3; ++i) { mbar_init(&d_full[i], 1); mbar_init(&a_full[i], kRowWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&a_full[i], kRowWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * H + 4 * kZ; i += blockDim.x) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < 2 * H + 4 * kZ + 8; i += blockDim.x) bias_s[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = tmem_base_s;
+  const float* inv_s = bias_s + 2 * H + 4 * kZ;        // 1 / scale of gate0, nonlin0, gate2, nonlin2, lin, std
 
   if (warp < kRowWarps) {
     // ================= row warps =================
     const int q = warp & 3, hf = warp >> 2;
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);   // my lane group, my column half
+    unsigned char* pp = patches + q * kPatchBytes;    // the quadrant's pair patch
+    const bool elected = hf == 0 && lane == 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
+    int hp = 0;                                       // which half of the pair patch the next FP16 tile goes through
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    BFVI_DBG_T(t_begin);
     float zreg[32];
     {
       const int64_t row = (int64_t)blockIdx.x * kTileRows + q * 32 + lane;
@@ -245,12 +414,15 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)lt * gridDim.x;
       const int64_t row = tile * kTileRows + q * 32 + lane;
       const bool row_ok = row < p.R;
-      // ---- z -> TMEM (A operand of the hidden layers and of the linear head), rounded once
+      // ---- z -> TMEM (A operand of the hidden layers and of the linear head)
       // (all MMAs of the previous tile are complete: this warp has passed heads_full of that tile)
-      if (KEEP) store_half32(p.z16, row, 1, 0, hf, zreg);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) zreg[j] = rn_tf32(zreg[j]);
-      tmem_st32(tl + kFZ, zreg);
+      const int64_t row0 = tile * kTileRows + q * 32;
+      const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
+      if (KEEP) {
+        if (elected) bulk_wait_read<0>();             // the fp32 rows of the previous tile used the whole patch
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 1, 0, zreg);
+      }
+      store_a_split(tl + kFZ, zreg);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -259,129 +431,177 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         const int64_t nrow = (tile + gridDim.x) * kTileRows + q * 32 + lane;
         load_row32(p.z + nrow * kZ + hf * 32, nrow < p.R, zreg);
       }
-      // ---- hidden units: D -> + bias, ReLU, round -> A, in place
+      // ---- hidden pairs: D -> scale + bias, ReLU -> A (FP16 hi | lo), in place
 #pragma unroll 1
-      for (int u = 0; u < U2; ++u) {
-        const int hb = u % 3;
-        mbar_wait(&d_full[hb], (par_d >> hb) & 1u);
-        par_d ^= 1u << hb;
+      for (int c = 0; c < U; ++c) {
+        const int b = c & 1;
+        BFVI_DBG_T(t0);
+        mbar_wait(&d_full[b], (par_d >> b) & 1u);
+        par_d ^= 1u << b;
         tc_fence_after();
-        float v[32];
-        tmem_ld32(tl + kFHB + hb * 64, v);
-        const float4* b4 = reinterpret_cast<const float4*>(bias_s + u * kHU + hf * 32);
+        BFVI_DBG_ADD(0, t0);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float4 b = b4[c];
-          v[4 * c] = fmaxf(v[4 * c] + b.x, 0.f); v[4 * c + 1] = fmaxf(v[4 * c + 1] + b.y, 0.f);
-          v[4 * c + 2] = fmaxf(v[4 * c + 2] + b.z, 0.f); v[4 * c + 3] = fmaxf(v[4 * c + 3] + b.w, 0.f);
-        }
-        if (KEEP) {
-          uint32_t bits = 0;
+        for (int br = 0; br < 2; ++br) {              // gate unit c, nonlinear unit c
+          BFVI_DBG_T(t1);
+          float v[32];
+          tmem_ld32(tl + kFB + b * 128 + br * 64, v);
+          BFVI_DBG_ADD(1, t1);
+          BFVI_DBG_T(t2);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + br * H + c * kHU + hf * 32);
+          const float sc = inv_s[br];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-          if (!row_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;      // rows past the end contribute nothing to the weight gradients
+          for (int cc = 0; cc < 8; ++cc) {
+            const float4 bb = b4[cc];
+            float x;                                  // ReLU that keeps NaN like torch.relu (fmaxf would drop it)
+            x = fmaf(v[4 * cc], sc, bb.x); v[4 * cc] = x < 0.f ? 0.f : x;
+            x = fmaf(v[4 * cc + 1], sc, bb.y); v[4 * cc + 1] = x < 0.f ? 0.f : x;
+            x = fmaf(v[4 * cc + 2], sc, bb.z); v[4 * cc + 2] = x < 0.f ? 0.f : x;
+            x = fmaf(v[4 * cc + 3], sc, bb.w); v[4 * cc + 3] = x < 0.f ? 0.f : x;
           }
-          p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
-          store_half32(p.h16, row, U2, u, hf, v);
-        }
+          if (KEEP) {
+            const int u = br * U + c;
+            uint32_t bits = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
-        tmem_st32(tl + kFHB + hb * 64, v);
+            for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+            p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
+            // rows past the end contribute nothing to the weight gradients (their A operand is irrelevant: no output
+            // row is stored for them).  Selected, not branched: the named barriers inside must be reached convergently.
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+            store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, U2, u, v);
+          }
+          BFVI_DBG_ADD(2, t2);
+          BFVI_DBG_T(t3);
+          store_a_split(tl + kFB + b * 128 + br * 64, v);
+          BFVI_DBG_ADD(3, t3);
+        }
+        BFVI_DBG_T(t3b);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[hb]);
+        if (lane == 0) mbar_arrive(&a_full[b]);
+        BFVI_DBG_ADD(3, t3b);
       }
       // ---- tail: the finished nonlinear head is the A operand of the std head
+      BFVI_DBG_T(t4);
       {
         mbar_wait(&units_done, par_misc & 1u);
         tc_fence_after();
         float v[32];
         tmem_ld32(tl + kFNL, v);
-        const float* b = bias_s + 2 * H + kZ + hf * 32;
+        const float* bb = bias_s + 2 * H + kZ + hf * 32;
+        const float sc = inv_s[3];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += b[j];
-        if (row_ok) store_row32(p.nl + row * kZ + hf * 32, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
-        tmem_st32(tl + kFHB, v);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sc, bb[j]);
+        store_a_split(tl + kFB, v);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail_a);
+        store_rows_f32(pp, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v);
       }
       // ---- heads out
       {
         mbar_wait(&heads_full, par_misc & 1u);
         tc_fence_after();
+        const float* bb = bias_s + 2 * H + hf * 32;
         float v[32];
         tmem_ld32(tl + kFG, v);
-        const float* b = bias_s + 2 * H + hf * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += b[j];
-        if (row_ok) store_row32(p.g + row * kZ + hf * 32, v);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[2], bb[j]);
+        store_rows_f32(pp, q, lane, hf, elected, p.g + row0 * kZ, n_valid, v);
         tmem_ld32(tl + kFLIN, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += b[2 * kZ + j];
-        if (row_ok) store_row32(p.lin + row * kZ + hf * 32, v);
-        tmem_ld32(tl + kFAS, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += b[3 * kZ + j];
-        if (row_ok) store_row32(p.as + row * kZ + hf * 32, v);
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[4], bb[2 * kZ + j]);
+        store_rows_f32(pp, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, v);
+        tmem_ld32(tl + kFB + 128, v);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&heads_empty);
+        if (lane == 0) mbar_arrive(&heads_empty);     // every accumulator has been read: the next tile may start
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[5], bb[3 * kZ + j]);
+        store_rows_f32(pp, q, lane, hf, elected, p.as + row0 * kZ, n_valid, v);
       }
+      BFVI_DBG_ADD(4, t4);
       par_misc ^= 1u;
     }
+    if (elected) bulk_wait_all();                     // results are in global memory before the kernel ends
+    BFVI_DBG_ADD(5, t_begin);
+    if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
+      for (int i = 0; i < 8; ++i) p.dbg[i] = dbg_acc[i];
   } else if (warp == kRowWarps) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(kTileRows, 64);
+    // The WHOLE warp walks the schedule with warp-uniform values (TMEM base broadcast by a shuffle, ring addresses
+    // from uniform loop counters) and one elected lane issues: under an `if (lane == 0)` around the loop the compiler cannot prove
+    // the tcgen05 operands uniform and wraps every instruction in an ELECT / R2UR.BROADCAST waterfall loop (measured:
+    // 81 cycles per MMA issued instead of the tensor pipe's 52-67).
+    {
+      long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
+      const uint32_t idesc64 = umma_idesc_f16_k(kTileRows, 64), idesc128 = umma_idesc_f16_k(kTileRows, 128);
       const uint32_t ring = smem_u32(smem);
       uint32_t par_a = 0;
       int64_t gblk = 0;                               // blocks consumed so far (ring position)
       auto stage_of = [&](int64_t g) { return (int)(g % n_stages); };
       auto wait_block = [&](int64_t g) { mbar_wait(&full_bar[stage_of(g)], (uint32_t)((g / n_stages) & 1)); tc_fence_after(); };
-      auto mma8 = [&](uint32_t d_col, uint32_t a_col, uint32_t tile_addr, bool fresh) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_tf32_ts(tb + d_col, tb + a_col + k * 8, umma_desc_sw128(tile_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc,
-                       (fresh && k == 0) ? 0u : 1u);
-      };
       for (int lt = 0; lt < my_tiles; ++lt) {
         mbar_wait(&z_full, (uint32_t)(lt & 1));
         tc_fence_after();
-        auto issue1 = [&](int u) {                    // hidden pre-activations of unit u
-          wait_block(gblk + u);
-          mma8(kFHB + (u % 3) * 64, kFZ, ring + stage_of(gblk + u) * kBlockBytes, true);
-          umma_commit(&d_full[u % 3]);
+        auto issue1 = [&](int c) {                    // hidden pre-activations of pair c: one N = 128 stream
+          BFVI_DBG_T(tw);
+          wait_block(gblk + 2 * c);
+          BFVI_DBG_ADD(1, tw);
+          BFVI_DBG_T(ti);
+          if (elect_one()) {
+            mma_split(tbu, kFB + (c & 1) * 128, kFZ, ring + stage_of(gblk + 2 * c) * kBlockBytes, kTileBytes, true, idesc128);
+            umma_commit(&d_full[c & 1]);
+            umma_commit(&empty_bar[stage_of(gblk + 2 * c)]);
+          }
+          __syncwarp();
+          BFVI_DBG_ADD(2, ti);
         };
         issue1(0);
-        if (U2 > 1) issue1(1);
-        for (int u = 0; u < U2; ++u) {
-          const int hb = u % 3;
-          mbar_wait(&a_full[hb], (par_a >> hb) & 1u);
-          par_a ^= 1u << hb;
+        for (int c = 0; c < U; ++c) {
+          const int b = c & 1;
+          if (c + 1 < U) issue1(c + 1);               // overlaps the row warps' work on pair c
+          BFVI_DBG_T(ta);
+          mbar_wait(&a_full[b], (par_a >> b) & 1u);
+          par_a ^= 1u << b;
           tc_fence_after();
-          if (u == 0) { mbar_wait(&heads_empty, (uint32_t)((lt & 1) ^ 1)); tc_fence_after(); }   // previous heads read out
-          mma8(u < U ? kFG : kFNL, kFHB + hb * 64, ring + stage_of(gblk + u) * kBlockBytes + kTileBytes, u == 0 || u == U);
-          umma_commit(&empty_bar[stage_of(gblk + u)]);
-          if (u + 2 < U2) issue1(u + 2);
+          if (c == 0) { mbar_wait(&heads_empty, (uint32_t)((lt & 1) ^ 1)); tc_fence_after(); }   // previous heads read out
+          BFVI_DBG_ADD(0, ta);
+          BFVI_DBG_T(tw);
+          wait_block(gblk + 2 * c + 1);
+          BFVI_DBG_ADD(1, tw);
+          BFVI_DBG_T(ti);
+          const uint32_t blk = ring + stage_of(gblk + 2 * c + 1) * kBlockBytes;
+          if (elect_one()) {
+            mma_split(tbu, kFG, kFB + b * 128, blk, 8192, c == 0, idesc64);
+            mma_split(tbu, kFNL, kFB + b * 128 + 64, blk + kTileBytes, 8192, c == 0, idesc64);
+            umma_commit(&empty_bar[stage_of(gblk + 2 * c + 1)]);
+          }
+          __syncwarp();
+          BFVI_DBG_ADD(2, ti);
         }
-        umma_commit(&units_done);
+        if (elect_one()) umma_commit(&units_done);
+        __syncwarp();
         const int64_t gt = gblk + U2;
         wait_block(gt);
-        mma8(kFLIN, kFZ, ring + stage_of(gt) * kBlockBytes, true);
+        const uint32_t blk = ring + stage_of(gt) * kBlockBytes;
+        if (elect_one()) mma_split(tbu, kFLIN, kFZ, blk, 8192, true, idesc64);
+        __syncwarp();
         mbar_wait(&tail_a, (uint32_t)(lt & 1));
         tc_fence_after();
-        mma8(kFAS, kFHB, ring + stage_of(gt) * kBlockBytes + kTileBytes, true);
-        umma_commit(&empty_bar[stage_of(gt)]);
-        umma_commit(&heads_full);
+        if (elect_one()) {
+          mma_split(tbu, kFB + 128, kFB, blk + kTileBytes, 8192, true, idesc64);
+          umma_commit(&empty_bar[stage_of(gt)]);
+          umma_commit(&heads_full);
+        }
+        __syncwarp();
         gblk += n_blocks;
       }
+      if (p.dbg && blockIdx.x == 0 && lane == 0)
+        for (int i = 0; i < 8; ++i) p.dbg[8 + i] = dbg_acc[i];
     }
     __syncwarp();
   } else {
@@ -413,12 +633,19 @@ struct BwdParams {
   float* dz;                     // (R, 64) out
   __half* dh16;                  // masked hidden gradients, FP16 tiles [row group][2U atoms]
   __half* dg16; __half* dnl16;   // FP16 tiles of d_g / d_nl [row group][1 atom]
-  float* gb_gate0; float* gb_non0;   // bias gradients of the two hidden layers (H each), accumulated; both null = skip
   int64_t R;
   int H;
   int n_stages;
 };
 constexpr uint32_t kBDG = 0, kBDNL = 64, kBDZ = 128, kBHB = 192;        // 4 hidden buffers + d_lin buffer (index 4)
+
+__device__ __forceinline__ void mma8_tf32(uint32_t tb, uint32_t d_col, uint32_t a_col, uint32_t tile_addr, bool fresh,
+                                          uint32_t idesc) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    umma_tf32_ts(tb + d_col, tb + a_col + k * 8, umma_desc_sw128(tile_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc,
+                 (fresh && k == 0) ? 0u : 1u);
+}
 
 __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ unsigned char fused_smem_dyn[];
@@ -430,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = fused_smem_dyn + ((1024u - (smem_u32(fused_smem_dyn) & 1023u)) & 1023u);
   const int n_stages = p.n_stages;
-  float* gb_s = reinterpret_cast<float*>(smem + (size_t)n_stages * kBlockBytes);      // (2H) column sums of this CTA
+  unsigned char* patches = smem + (size_t)n_stages * kBlockBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, U = H / kHU, U2 = 2 * U, n_blocks = U2 + 1;
   const int64_t n_tiles = (p.R + kTileRows - 1) / kTileRows;
@@ -443,7 +670,6 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
     for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&a_full[i], kRowWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 2 * H; i += blockDim.x) gb_s[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -452,24 +678,33 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
   if (warp < kRowWarps) {
     const int q = warp & 3, hf = warp >> 2;
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);
+    unsigned char* pp = patches + q * kPatchBytes;
+    const bool elected = hf == 0 && lane == 0;
     uint32_t par_d = 0, par_misc = 0;
+    int hp = 0;
+    float rg[32], rn[32];                             // next tile's d_g / d_nl half rows (prefetched during the units)
+    {
+      const int64_t row = (int64_t)blockIdx.x * kTileRows + q * 32 + lane;
+      const bool ok = my_tiles > 0 && row < p.R;
+      load_row32(p.d_g + row * kZ + hf * 32, ok, rg);
+      load_row32(p.d_nl + row * kZ + hf * 32, ok, rn);
+    }
     for (int lt = 0; lt < my_tiles; ++lt) {
       const int64_t tile = (int64_t)blockIdx.x + (int64_t)lt * gridDim.x;
       const int64_t row = tile * kTileRows + q * 32 + lane;
       const bool row_ok = row < p.R;
       // ---- head gradients -> TMEM (A operands), FP16 tiles for the weight-gradient GEMM
+      const int64_t row0 = tile * kTileRows + q * 32;
+      const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
       {
+        if (elected) bulk_wait_read<0>();             // dz of the previous tile used the whole patch
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 1, 0, rg);
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 1, 0, rn);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rg[j] = rn_tf32(rg[j]); rn[j] = rn_tf32(rn[j]); }
+        tmem_st32(tl + kBDG, rg);
+        tmem_st32(tl + kBDNL, rn);
         float v[32];
-        load_row32(p.d_g + row * kZ + hf * 32, row_ok, v);
-        store_half32(p.dg16, row, 1, 0, hf, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
-        tmem_st32(tl + kBDG, v);
-        load_row32(p.d_nl + row * kZ + hf * 32, row_ok, v);
-        store_half32(p.dnl16, row, 1, 0, hf, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
-        tmem_st32(tl + kBDNL, v);
         load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
@@ -478,6 +713,11 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&in_full);
+        if (lt + 1 < my_tiles) {
+          const int64_t nrow = (tile + gridDim.x) * kTileRows + q * 32 + lane;
+          load_row32(p.d_g + nrow * kZ + hf * 32, nrow < p.R, rg);
+          load_row32(p.d_nl + nrow * kZ + hf * 32, nrow < p.R, rn);
+        }
       }
 #pragma unroll 1
       for (int u = 0; u < U2; ++u) {
@@ -490,27 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tmem_ld32(tl + kBHB + hb * 64, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-        store_half32(p.dh16, row, U2, u, hf, v);
-        if (p.gb_gate0 != nullptr) {
-          // column sums over the warp's 32 rows by a transposing butterfly: after 5 exchange steps lane j holds the
-          // sum of column j (31 shuffles instead of 160)
-          float s[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s[j] = v[j];
-#pragma unroll
-          for (int w = 16; w >= 1; w >>= 1) {
-            const bool up = (lane & w) != 0;
-#pragma unroll
-            for (int j = 0; j < w; ++j) {
-              const float mine = up ? s[j + w] : s[j];            // the half this lane keeps
-              const float give = up ? s[j] : s[j + w];            // the half its partner keeps
-              s[j] = mine + __shfl_xor_sync(0xffffffffu, give, w);
-            }
-          }
-          // lane's column: bit-reversal-free order — after the steps lane l holds column index equal to l's bits
-          // consumed high to low, i.e. column l
-          atomicAdd(gb_s + u * kHU + hf * 32 + lane, s[0]);
-        }
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, U2, u, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
         tmem_st32(tl + kBHB + hb * 64, v);
@@ -527,24 +747,21 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dz_empty);
-        if (row_ok) store_row32(p.dz + row * kZ + hf * 32, v);
+        store_rows_f32(pp, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v);
       }
       par_misc ^= 1u;
     }
+    if (elected) bulk_wait_all();
   } else if (warp == kRowWarps) {
-    if (lane == 0) {
+    // whole warp walks the schedule, one elected lane issues (see gtf_fwd_kernel)
+    {
+      const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
       const uint32_t idesc = umma_idesc_tf32(kTileRows, 64);
       const uint32_t ring = smem_u32(smem);
       uint32_t par_a = 0;
       int64_t gblk = 0;
       auto stage_of = [&](int64_t g) { return (int)(g % n_stages); };
       auto wait_block = [&](int64_t g) { mbar_wait(&full_bar[stage_of(g)], (uint32_t)((g / n_stages) & 1)); tc_fence_after(); };
-      auto mma8 = [&](uint32_t d_col, uint32_t a_col, uint32_t tile_addr, bool fresh) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_tf32_ts(tb + d_col, tb + a_col + k * 8, umma_desc_sw128(tile_addr + (k >> 2) * 8192 + (k & 3) * 32), idesc,
-                       (fresh && k == 0) ? 0u : 1u);
-      };
       for (int lt = 0; lt < my_tiles; ++lt) {
         mbar_wait(&in_full, (uint32_t)(lt & 1));
         tc_fence_after();
@@ -552,26 +769,35 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         mbar_wait(&dz_empty, (uint32_t)((lt & 1) ^ 1));
         tc_fence_after();
         wait_block(gblk);
-        mma8(kBDZ, kBHB + 4 * 64, ring + stage_of(gblk) * kBlockBytes + kTileBytes, true);
-        umma_commit(&empty_bar[stage_of(gblk)]);
+        if (elect_one()) {
+          mma8_tf32(tbu, kBDZ, kBHB + 4 * 64, ring + stage_of(gblk) * kBlockBytes + kTileBytes, true, idesc);
+          umma_commit(&empty_bar[stage_of(gblk)]);
+        }
+        __syncwarp();
         auto issue1 = [&](int u) {                    // hidden gradients of unit u: d_head W2u
           wait_block(gblk + 1 + u);
-          mma8(kBHB + (u & 3) * 64, u < U ? kBDG : kBDNL, ring + stage_of(gblk + 1 + u) * kBlockBytes, true);
-          umma_commit(&d_full[u & 3]);
+          if (elect_one()) {
+            mma8_tf32(tbu, kBHB + (u & 3) * 64, u < U ? kBDG : kBDNL, ring + stage_of(gblk + 1 + u) * kBlockBytes, true, idesc);
+            umma_commit(&d_full[u & 3]);
+          }
+          __syncwarp();
         };
         issue1(0);
         if (U2 > 1) issue1(1);
-        if (U2 > 2) issue1(2);
         for (int u = 0; u < U2; ++u) {
           const int hb = u & 3;
+          if (u + 2 < U2) issue1(u + 2);
           mbar_wait(&a_full[hb], (par_a >> hb) & 1u);
           par_a ^= 1u << hb;
           tc_fence_after();
-          mma8(kBDZ, kBHB + hb * 64, ring + stage_of(gblk + 1 + u) * kBlockBytes + kTileBytes, false);
-          umma_commit(&empty_bar[stage_of(gblk + 1 + u)]);
-          if (u + 3 < U2) issue1(u + 3);
+          if (elect_one()) {
+            mma8_tf32(tbu, kBDZ, kBHB + hb * 64, ring + stage_of(gblk + 1 + u) * kBlockBytes + kTileBytes, false, idesc);
+            umma_commit(&empty_bar[stage_of(gblk + 1 + u)]);
+          }
+          __syncwarp();
         }
-        umma_commit(&dz_full);
+        if (elect_one()) umma_commit(&dz_full);
+        __syncwarp();
         gblk += n_blocks;
       }
     }
@@ -590,9 +816,6 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (p.gb_gate0 != nullptr)
-    for (int i = threadIdx.x; i < 2 * H; i += blockDim.x)
-      if (gb_s[i] != 0.f) atomicAdd(i < H ? p.gb_gate0 + i : p.gb_non0 + (i - H), gb_s[i]);
   if (warp == kRowWarps) tmem_dealloc(tb, 512);
 }
 
@@ -601,11 +824,13 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------------------
 // out^T[h, zc] += sum_rows X[row, h] * Y[row, zc].  X: FP16 tiles [row group][n_atoms_x atoms], the problem uses atoms
 // atom0 .. (H/64 of them); Y: FP16 tiles [row group][1 atom].  out is either (H, Z) row-major (dW of a z -> hidden
-// layer: direct) or (Z, H) row-major (dW of a hidden -> head layer: transposed add).
+// layer: direct) or (Z, H) row-major (dW of a hidden -> head layer: transposed add).  bias (nullable): (H) += column
+// sums of X (the bias gradient of a z -> hidden layer whose X is the hidden gradient).
 struct Wgrad16Problem {
   const __half* X; int n_atoms_x; int atom0;
   const __half* Y;
   float* out; int transposed;
+  float* bias;
 };
 struct Wgrad16Params {
   Wgrad16Problem pr[4];
@@ -617,7 +842,7 @@ struct Wgrad16Params {
   int n_stages;
 };
 constexpr int kWgStageBytes = 3 * kAtomBytes;        // X atoms (2) + Y atom
-constexpr int kWgThreads = 6 * 32;                   // 4 epilogue warps, MMA warp, loader warp
+constexpr int kWgThreads = 6 * 32;                   // 4 epilogue / column-sum warps, MMA warp, loader warp
 
 // MN-major SWIZZLE_128B shared-memory descriptor: LBO = stride between 64-element MN atoms, SBO = stride between
 // 8-row K groups (cute::UMMA canonical layout ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), T = 8 halves)
@@ -657,7 +882,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
   };
   if (warp == 4) tmem_alloc(&tmem_base_s, 64);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }   // MMA commit + 4 warps
     mbar_init(&acc_full, 1); mbar_init(&acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -667,11 +892,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
   const uint32_t tb = tmem_base_s;
 
   if (warp < 4) {
-    // ===== epilogue: accumulator (128 hidden rows x 64 z columns) -> red.global.add =====
+    // ===== column sums of the X tiles while they sit in shared memory, then the accumulator epilogue =====
+    int64_t gpos = 0;
+    const int t = threadIdx.x;                        // column of the 128-wide X tile: atom t / 64, column t % 64
+    const uint32_t col_off = (uint32_t)((t >> 6) * kAtomBytes + (t & 7) * 2);
+    const int chunk = (t & 63) >> 3;
     for (int li = 0; li < my_items; ++li) {
       int pi, mt; int64_t g0, g1;
       item_of(li, pi, mt, g0, g1);
       const Wgrad16Problem& pr = p.pr[pi];
+      float csum = 0.f;
+      for (int64_t g = g0; g < g1; ++g, ++gpos) {
+        const int s = (int)(gpos % n_stages);
+        mbar_wait(&full_bar[s], (uint32_t)((gpos / n_stages) & 1));        // never ahead of the ring
+        if (pr.bias != nullptr) {
+          const unsigned char* x = smem + (size_t)s * kWgStageBytes + col_off;
+#pragma unroll 8
+          for (int r = 0; r < kRowGroup; ++r)
+            csum += __half2float(*reinterpret_cast<const __half*>(x + r * 128 + ((chunk ^ (r & 7)) << 4)));
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+      if (pr.bias != nullptr && g1 > g0) atomicAdd(pr.bias + mt * 128 + t, csum);
       mbar_wait(&acc_full, (uint32_t)(li & 1));
       tc_fence_after();
       const int h = mt * 128 + warp * 32 + lane;
@@ -696,7 +939,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
       }
     }
   } else if (warp == 4) {
-    if (lane == 0) {
+    {
+      const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
       const uint32_t idesc = umma_idesc_f16_mn(128, 64);
       const uint32_t ring = smem_u32(smem);
       int64_t gpos = 0;
@@ -710,13 +954,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
           mbar_wait(&full_bar[s], (uint32_t)((gpos / n_stages) & 1));
           tc_fence_after();
           const uint32_t xa = ring + s * kWgStageBytes, ya = xa + 2 * kAtomBytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)                 // 16 rows (two 8-row K groups = 2 KB) per instruction
-            umma_f16_ss(tb, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, kAtomBytes, 1024),
-                        idesc, (g > g0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+            for (int k = 0; k < 4; ++k)               // 16 rows (two 8-row K groups = 2 KB) per instruction
+              umma_f16_ss(tbu, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, kAtomBytes, 1024),
+                          idesc, (g > g0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);
+          }
+          __syncwarp();
         }
-        umma_commit(&acc_full);
+        if (elect_one()) umma_commit(&acc_full);
+        __syncwarp();
       }
     }
     __syncwarp();

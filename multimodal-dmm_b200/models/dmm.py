@@ -302,7 +302,7 @@ class MultiDMM(MultiDGTS):
         self._ws = None
         self.grad_sync = None          # optional callable(flat_grad) -> None (data parallel)
         self.noise_seed = None         # fixed Philox seed (None: drawn from torch's RNG per call)
-        self.precision = 'tf32'        # large-dim family step(): 'tf32' (fused on-chip GTF kernels) | 'tf32x3'
+        self.precision = 'fused'       # large-dim family step(): 'fused' (on-chip GTF kernels) | 'tf32x3' | 'tf32'
         self.batch_tile = 0            # large-dim family step(): sequences per batch tile (0 = library default)
         self.last_launches = 0
         self.last_flat_grad = None
@@ -701,8 +701,8 @@ class MultiDMM(MultiDGTS):
         a.match_particles = int(kw.get('match_particles', 50))
         a.sample, a.sample_init = int(bool(kw.get('sample', True))), int(bool(kw.get('sample_init', False)))
         a.seed, a.b_offset, a.match_count = self._next_seed(), int(getattr(self, 'b_offset', 0)), -1.0
-        # large-dim family: GEMM operand precision ('tf32x3' error-compensated / 'tf32' single pass, the fused
-        # on-chip transition kernels) and the batch tile the step walks (0 = chosen by the library)
+        # large-dim family: 'fused' (on-chip transition kernels, FP32-class forward) / 'tf32x3' / 'tf32'
+        # (launch-sequence path) and the batch tile the step walks (0 = chosen by the library)
         a.precision = _lib.PRECISION_CODES[kw.get('precision', self.precision)]
         a.batch_tile = int(kw.get('batch_tile', self.batch_tile))
         noise = kw.get('noise')

@@ -67,6 +67,11 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, int, int) { *v = 2; ret
 static inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) { memset(p, v, n); return cudaSuccess; }
 enum cudaMemcpyKind { cudaMemcpyDeviceToDevice = 3 };
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width, size_t height, int,
+                                            cudaStream_t) {
+  for (size_t r = 0; r < height; ++r) memcpy((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+  return cudaSuccess;
+}
 typedef int cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2 };
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }

@@ -78,6 +78,7 @@ def step_args(fx, device, noise=None, seed=0, kwargs=None, b_offset=0):
     a.match_particles = int(kw.get('match_particles', 50))
     a.sample, a.sample_init = int(kw.get('sample', True)), int(kw.get('sample_init', False))
     a.seed, a.b_offset, a.match_count = seed, b_offset, -1.0
+    a.precision, a.batch_tile = int(kw.get('precision', 0)), int(kw.get('batch_tile', 0))   # large-dim family knobs
     if noise is not None:
         for name, field in (('match', 'eps_match'), ('filt', 'eps_filt'), ('sflt', 'eps_sflt'),
                             ('ssmt', 'eps_ssmt')):

@@ -124,13 +124,17 @@ def step_case(name, k_train, k_match, seed):
     return fx
 
 
-@pytest.mark.parametrize('name', ['default32', 'c3_dims', 'odd'])
-def test_large_family_step_matches_oracle(name):
+@pytest.mark.parametrize('name,precision', [('default32', 0), ('c3_dims', 0), ('odd', 0), ('c3_dims', 2)])
+def test_large_family_step_matches_oracle(name, precision):
     """MultiDMM.step + backward at large dims (C3: M=8, Z=64, H=512) against the fp64 oracle on
-    identical injected noise: ELBO 1e-4 relative, every parameter gradient 1e-3 relative."""
+    identical injected noise: ELBO 1e-4 relative, every parameter gradient 1e-3 relative.
+    precision 0 = 3xTF32 launch sequence, 2 = the fused on-chip transition kernels (what bench.py times)."""
     lib = _lib.load()
     fx = step_case(name, k_train=5, k_match=7, seed=21)
-    loss, grads, launches = helpers.run_step(lib, fx, 'cuda')
+    loss, grads, launches = helpers.run_step(lib, fx, 'cuda', kwargs={'precision': precision})
+    if precision == 2:
+        ran = ';'.join(lib.last_dispatch())
+        assert 'gtf_fwd_fused<keep>' in ran and 'gtf_bwd_fused' in ran and 'wgrad16' in ran, ran
     params = {k: v.clone().double().requires_grad_(True) for k, v in fx['state_dict'].items()}
     orc = bo.OracleDMM(fx['modalities'], fx['dims'], params, h_dim=fx['h_dim'], z_dim=fx['z_dim'],
                        min_std=fx['min_std'], draw=bo.step_noise_tape(fx['noise']))
@@ -144,7 +148,8 @@ def test_large_family_step_matches_oracle(name):
     # handful of ReLU pre-activations lie that close to zero, their mask flips against the fp64
     # oracle and moves ONE tensor by up to 3e-3 (which tensor depends on the batch; the run is
     # bit-reproducible).  Every other tensor is two orders of magnitude inside the 1e-3 bar.
-    assert errs[len(errs) // 2][0] < 1e-4, errs[len(errs) // 2]
+    print('large-step grad errors (worst 4):', errs[-4:], 'median', errs[len(errs) // 2])
+    assert errs[len(errs) // 2][0] < (1e-4 if precision == 0 else 5e-4), errs[len(errs) // 2]
     assert errs[-1][0] < (5e-3 if name == 'c3_dims' else 1e-3), errs[-1]
 
 
@@ -208,3 +213,19 @@ def test_cuda_graph_step_matches_eager():
         assert abs(a - b) <= 1e-5 * abs(a), (a, b)
         assert torch.allclose(ga, gb, rtol=1e-4, atol=1e-6 * ga.abs().max().item())
     assert abs(e1 - e2) > 1e-6 * abs(e1)          # the seed matters
+
+
+@pytest.mark.parametrize('precision', [0, 2])
+@pytest.mark.parametrize('tile', [4, 7])
+def test_batch_tiled_step_equals_whole_batch_step(precision, tile):
+    """The step walks the batch in tiles (bfvi_step_args.batch_tile): same loss and gradients as the one-piece
+    step on the same Philox seed, both for the launch-sequence path and the fused kernels (C3 dims, B = 11)."""
+    lib = _lib.load()
+    fx = step_case('c3_dims', k_train=5, k_match=7, seed=21)
+    l0, g0, _ = helpers.run_step(lib, fx, 'cuda', noise=None, seed=5, return_flat=True, kwargs={'precision': precision})
+    l1, g1, _ = helpers.run_step(lib, fx, 'cuda', noise=None, seed=5, return_flat=True,
+                                 kwargs={'precision': precision, 'batch_tile': tile})
+    assert 'step:batch_tiles' in ';'.join(lib.last_dispatch())
+    assert abs(l0 - l1) <= 2e-5 * abs(l0), (l0, l1)
+    assert torch.isfinite(g1).all()
+    assert ((g0 - g1).norm() / g0.norm()).item() < 1e-4

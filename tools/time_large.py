@@ -26,6 +26,8 @@ def main():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--fwd-only', action='store_true')
     ap.add_argument('--graph', action='store_true', help='capture the step in a CUDA graph and time replays')
+    ap.add_argument('--precision', type=int, default=2, help='0 tf32x3 launch sequence, 1 tf32, 2 fused on-chip kernels')
+    ap.add_argument('--batch-tile', type=int, default=0)
     a = ap.parse_args()
     lib = _lib.load()
     mods, dims = ['m%d' % i for i in range(a.M)], [16] * a.M
@@ -37,7 +39,7 @@ def main():
               state_dict=bo.init_params(mods, dims, h_dim=a.H, z_dim=a.Z, seed=1))
     model, dists = helpers.fixture_model(fx)
     flat, lay = helpers.pack_params(lib, model, mods, dists, fx['state_dict'], 'cuda')
-    args, keep = helpers.step_args(fx, 'cuda', None, seed=2024)
+    args, keep = helpers.step_args(fx, 'cuda', None, seed=2024, kwargs={'precision': a.precision, 'batch_tile': a.batch_tile})
     nbytes = C.c_size_t(0)
     lib.call('bfvi_step_workspace', C.byref(model), C.byref(args), C.byref(nbytes))
     ws = helpers.aligned_empty(nbytes.value, 'cuda')
@@ -77,6 +79,7 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
     flop = 216023040.0 * a.B * a.T if (a.M, a.Z, a.H, a.K) == (8, 64, 512, 25) else float('nan')
+    print('dispatch:', ';'.join(lib.last_dispatch())[:400])
     print('C3 dims B=%d T=%d K=%d: %.1f ms/step  %.3e seq-ts/s  %.1f TFLOP/s algorithmic  loss=%.3f  launches=%d  ws=%.0f MB'
           % (a.B, a.T, a.K, ms, a.B * a.T / ms * 1e3, flop / ms / 1e9, loss.item(), launches.value, nbytes.value / 1e6))
 
