@@ -784,9 +784,9 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
     const double tpc = (double)((tiles + grid - 1) / grid), pairs = tpc * (H / 64);
-    fprintf(stderr, "[fused fwd dbg] rows %lld tiles/CTA %.0f | row warp 0 per PAIR: wait_d %.0f ld %.0f math %.0f st+arrive %.0f | tail+heads per tile %.0f | total %.0f per tile\n"
+    fprintf(stderr, "[fused fwd dbg] rows %lld tiles/CTA %.0f | row warp 0 per PAIR: wait_d %.0f ld %.0f math %.0f st+arrive %.0f | tail+heads per tile %.0f (wait units_done %.0f, wait heads_full %.0f) | total %.0f per tile\n"
                     "                issuer per PAIR: wait_a %.0f wait_blk %.0f issue %.0f\n",
-            (long long)rows, tpc, h[0] / pairs, h[1] / pairs, h[2] / pairs, h[3] / pairs, h[4] / tpc, h[5] / tpc,
+            (long long)rows, tpc, h[0] / pairs, h[1] / pairs, h[2] / pairs, h[3] / pairs, h[4] / tpc, h[6] / tpc, h[7] / tpc, h[5] / tpc,
             h[8] / pairs, h[9] / pairs, h[10] / pairs);
   }
   BFVI_CHECK_CUDA();
@@ -839,7 +839,7 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
   wp.groups_per_slice = (int)((wp.n_groups + slices - 1) / slices);
   wp.n_slices = (int)((wp.n_groups + wp.groups_per_slice - 1) / wp.groups_per_slice);
   wp.n_stages = bfvi::fused::kMaxStages;
-  const size_t smem = (size_t)wp.n_stages * bfvi::fused::kWgStageBytes + 1024;
+  const size_t smem = (size_t)wp.n_stages * bfvi::fused::kWgStageBytes + bfvi::fused::kAtomBytes + 1024;
   const int items = tiles * wp.n_slices;
   auto k = bfvi::fused::wgrad16_kernel;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1102,9 +1102,9 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     gp.k_split = wgrad_k_split(rows, n_out, n_in);
     return gemm(gp);
   };
-  auto transpose = [&](const float* in, int64_t rows, int cols, float* out) {
+  auto transpose = [&](const float* in, int64_t rows, int cols, float* out, int swz = 0) {
     auto k = bfvi::gen::transpose_kernel;
-    BFVI_LAUNCH(k, dim3((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), dim3(256), 0, st, in, rows, cols, out);
+    BFVI_LAUNCH(k, dim3((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), dim3(256), 0, st, in, rows, cols, out, swz);
     ++n_launch;
   };
 
@@ -1148,7 +1148,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       const int dir = (&g == &lay.trans[1]) ? 1 : 0;
       if (int rc = fused_fwd(fbufs(), dir, H, F(pl.zrows), rows, F(pl.g), F(pl.nl), F(pl.lin), F(pl.as), keep, st)) return rc;
       ++n_launch;
-      if (keep) transpose(F(pl.nl), rows, Z, F(pl.nlT));        // operand of the Z x Z std weight gradient
+      if (keep) transpose(F(pl.nl), rows, Z, F(pl.nlT), 1);     // operand of the Z x Z std weight gradient (nl is swz64)
       return BFVI_OK;
     }
 #endif
@@ -1210,6 +1210,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     memset(&sp, 0, sizeof(sp));
     const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
     sp.a = f;
+    sp.swz = fused ? 1 : 0;
     sp.z0_mean = params + lay.z0_mean; sp.z0_log_std = params + lay.z0_log_std;
     sp.g_z0_mean = grads ? grads + lay.z0_mean : nullptr; sp.g_z0_log_std = grads ? grads + lay.z0_log_std : nullptr;
     sp.min_std = m->min_std; sp.Z = Z; sp.i = i; sp.R = (int64_t)f.S * f.B * f.n_particles;
@@ -1327,7 +1328,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       mh.g = F(pl.g); mh.nl = F(pl.nl); mh.lin = F(pl.lin); mh.as = F(pl.as);
       mh.pm = zvec + 2 * Z; mh.d_pm = F(pl.d_pm); mh.d_v = F(pl.d_v);
       mh.min_std = m->min_std; mh.coef_static = coef; mh.count = cnt; mh.loss_acc = acc;
-      mh.K = Km; mh.Z = Z; mh.with_grad = with_grad ? 1 : 0;
+      mh.K = Km; mh.Z = Z; mh.with_grad = with_grad ? 1 : 0; mh.swz = fused ? 1 : 0;
       auto km = bfvi::gen::match_head_kernel;
       BFVI_LAUNCH(km, dim3((Z + 127) / 128), dim3(128), 0, st, mh);
       ++n_launch;
@@ -2225,6 +2226,18 @@ __global__ void __launch_bounds__(256) gtf_small_wgrad_kernel(const float* __res
   if (db != nullptr && (threadIdx.x & 3) == 0) atomicAdd(db + o, bsum);
 }
 #endif
+// in-place swz64 -> row-major of an (R, 64) array (the stand-alone entries hand plain rows to the caller): a warp per
+// row, lane = 16-byte chunk of the row (16 chunks; lanes 16-31 idle)
+__global__ void __launch_bounds__(256) unswz64_kernel(float* __restrict__ x, int64_t rows) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (int64_t)gridDim.x * 8) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* row = reinterpret_cast<float4*>(x + r * 64);
+    if (lane < 16) v = row[(lane & 8) | ((lane & 7) ^ (int)(r & 7))];       // chunk `lane` of the row-major row
+    __syncwarp();
+    if (lane < 16) row[lane] = v;
+  }
+}
 struct GtfWs { size_t packs, rows, d_nl, total; };
 GtfWs gtf_ws_plan(int H, int64_t n_rows) {
   GtfWs w;
@@ -2266,7 +2279,11 @@ int bfvi_gtf_fwd(const bfvi_model* m, const float* params, int32_t direction, co
   fused_carve_rows((char*)workspace + w.rows, m->h_dim, n_rows, &fb);
   cudaStream_t st = (cudaStream_t)stream;
   if (int rc = fused_pack(lay.trans[direction], params, direction, m->h_dim, fb, st)) return rc;
-  return fused_fwd(fb, direction, m->h_dim, z, n_rows, gate_pre, nonlin, lin, std_pre, keep != 0, st);
+  if (int rc = fused_fwd(fb, direction, m->h_dim, z, n_rows, gate_pre, nonlin, lin, std_pre, keep != 0, st)) return rc;
+  for (float* x : {gate_pre, nonlin, lin, std_pre})      // the kernels write the swz64 layout; callers get plain rows
+    unswz64_kernel<<<dim3((unsigned)grid_for(n_rows, 8, 8)), dim3(256), 0, st>>>(x, n_rows);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
 #endif
 }
 
@@ -2302,6 +2319,7 @@ int bfvi_gtf_bwd(const bfvi_model* m, const float* params, float* grads, int32_t
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_nl, nullptr, n_rows, nullptr, grads + g.nonlin2_b);
   BFVI_CHECK_CUDA();
   if (int rc = fused_bwd(fb, direction, m->h_dim, d_gate_pre, d_nl, d_lin, n_rows, d_z, st)) return rc;
+  unswz64_kernel<<<dim3((unsigned)grid_for(n_rows, 8, 8)), dim3(256), 0, st>>>(d_z, n_rows);
   return fused_wgrad(fb, m->h_dim, n_rows, grads + g.gate0_w, grads + g.nonlin0_w, grads + g.gate2_w, grads + g.nonlin2_w,
                      grads + g.gate0_b, grads + g.nonlin0_b, st);
 #endif

@@ -22,8 +22,8 @@
 //   wgrad16_kernel   dW^T[H, Z] += X^T Y over all rows: X (hidden activations / their gradients) and Y (z / head
 //                    gradients) are the FP16 tiles the two kernels above wrote in the MN-major SWIZZLE_128B shared-memory
 //                    image, so a stage is two cp.async.bulk copies; kind::f16 MMAs, FP32 accumulation in TMEM over a
-//                    slice of the rows, one red.global.add pass per work item; the otherwise idle epilogue warps sum the
-//                    columns of the hidden-gradient tiles in shared memory (bias gradients).
+//                    slice of the rows, one red.global.add pass per work item; a constant all-ones column appended to
+//                    the Y operand (N = 80) makes the MMA produce the column sums of X (bias gradients) for free.
 //
 // Precision.  Forward contractions are error-compensated FP16 products: every operand x is split into hi = fp16(x),
 // lo = fp16(x - hi) and a_hi b_hi + a_lo b_hi + a_hi b_lo accumulates in FP32 (~2^-21 relative per product; weights are
@@ -64,7 +64,7 @@ constexpr int kThreads = (kRowWarps + 2) * 32;
 constexpr int kMaxStages = 6;
 constexpr int kRowGroup = 64;          // rows per FP16 operand tile of the weight-gradient GEMM (one K stage)
 constexpr int kAtomBytes = 8192;       // 64 rows x 64 halves, MN-major SWIZZLE_128B
-constexpr int kPatchBytes = 8192;      // per 32-lane quadrant (two row warps): 32 rows x 256 B, or two 32 x 128 B halves
+constexpr int kPatchBytes = 16384;     // per 32-lane quadrant (two row warps): two 32 rows x 256 B slots = four 32 x 128 B slots
 
 // shared-memory image of a 64 x 64 fp32 operand tile, K-major SWIZZLE_128B: two K halves of 32 floats; row r of a
 // half is one 128-byte line whose 16-byte chunks are XOR-permuted by r % 8 (8-row groups 1024 B apart)
@@ -251,21 +251,27 @@ __device__ __forceinline__ void load_row32(const float* __restrict__ src, bool o
 __device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); }
 
 // 32 rows x 64 fp32 columns (256 B per row, 8 KB): thread (row = lane, half hf) writes its 128 bytes.  `n_valid` rows of
-// the quadrant exist (the copy is clipped to them).  Shared-memory writes are 8-way bank conflicted (rows are 64 words
-// apart): once per tile and head, not worth a transposition.
-__device__ __forceinline__ void store_rows_f32(unsigned char* pp, int q, int lane, int hf, bool elected, float* __restrict__ dst_row0,
-                                               int n_valid, const float (&v)[32]) {
-  if (elected) bulk_wait_read<0>();
+// the quadrant exist (the copy is clipped to them).  The array is stored in the "swz64" layout (bfvi_generic.cuh
+// row64): the 16-byte chunks of each 128-byte half row are XOR-permuted by row % 8 — a linear row layout puts all 32
+// lanes of a store on the same four banks (rows are 64 words apart; measured 2 500 cycles per 8 KB) — and the consumers
+// (step / bwd_rows / carry / match kernels) apply the same permutation when they read.
+__device__ __forceinline__ void store_rows_f32(unsigned char* pp, int& slot, int q, int lane, int hf, bool elected,
+                                               float* __restrict__ dst_row0, int n_valid, const float (&v)[32]) {
+  if (elected) bulk_wait_read<1>();                  // the copy that used this slot two stores ago has read it
   pair_sync(q);
-  float4* s4 = reinterpret_cast<float4*>(pp + lane * 256 + hf * 128);
+  unsigned char* base = pp + slot * 8192;
+  unsigned char* prow = base + lane * 256 + hf * 128;
+  const int sw = lane & 7;                           // = row % 8 (row0 is a multiple of 32)
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  for (int i = 0; i < 8; ++i)                        // swz64: chunk i of the half row sits at i ^ (row % 8)
+    *reinterpret_cast<float4*>(prow + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
   fence_async_smem();
   pair_sync(q);
   if (elected) {
-    if (n_valid > 0) bulk_s2g(dst_row0, pp, (uint32_t)n_valid * 256u);
+    if (n_valid > 0) bulk_s2g(dst_row0, base, (uint32_t)n_valid * 256u);
     bulk_commit();
   }
+  slot ^= 1;
 }
 // FP16 operand tiles of the weight-gradient GEMM: (row group of 64 rows) x (atom of 64 columns) = 8 KB, row r of the
 // group is a 128-byte line, 16-byte chunk c stored at c ^ (r % 8): the MN-major SWIZZLE_128B shared-memory image, so
@@ -275,7 +281,7 @@ __device__ __forceinline__ void store_rows_f32(unsigned char* pp, int q, int lan
 __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int q, int lane, int hf, bool elected,
                                                __half* __restrict__ base, int64_t row0, int n_atoms, int atom,
                                                const float (&v)[32]) {
-  if (elected) bulk_wait_read<1>();                  // the copy that used this half two stores ago has read it
+  if (elected) bulk_wait_read<3>();                  // the copy that used this slot four stores ago has read it
   pair_sync(q);
   unsigned char* prow = pp + buf * 4096 + lane * 128;
   const int sw = lane & 7;                           // row0 is a multiple of 32
@@ -296,7 +302,7 @@ __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int 
     bulk_s2g(tile, pp + buf * 4096, 4096);
     bulk_commit();
   }
-  buf ^= 1;
+  buf = (buf + 1) & 3;
 }
 
 // kind::f16 with FP16 operands, FP32 accumulate, both operands K-major; the A operand from tensor memory (two halves
@@ -402,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     unsigned char* pp = patches + q * kPatchBytes;    // the quadrant's pair patch
     const bool elected = hf == 0 && lane == 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
-    int hp = 0;                                       // which half of the pair patch the next FP16 tile goes through
+    int hp = 0, fs = 0;                               // next FP16 tile slot (4 x 4 KB) / fp32 rows slot (2 x 8 KB) of the patch
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     BFVI_DBG_T(t_begin);
     float zreg[32];
@@ -419,14 +425,16 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       const int64_t row0 = tile * kTileRows + q * 32;
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
       if (KEEP) {
-        if (elected) bulk_wait_read<0>();             // the fp32 rows of the previous tile used the whole patch
+        if (elected) bulk_wait_read<0>();             // the fp32 rows of the previous tile used the same shared memory
         store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 1, 0, zreg);
       }
-      store_a_split(tl + kFZ, zreg);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&z_full);
+      if (lt == 0) {                                  // (later tiles: written during the previous tile's tail)
+        store_a_split(tl + kFZ, zreg);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&z_full);
+      }
       if (lt + 1 < my_tiles) {                        // next tile's rows fly during this tile's units
         const int64_t nrow = (tile + gridDim.x) * kTileRows + q * 32 + lane;
         load_row32(p.z + nrow * kZ + hf * 32, nrow < p.R, zreg);
@@ -487,6 +495,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       {
         mbar_wait(&units_done, par_misc & 1u);
         tc_fence_after();
+        BFVI_DBG_ADD(6, t4);
         float v[32];
         tmem_ld32(tl + kFNL, v);
         const float* bb = bias_s + 2 * H + kZ + hf * 32;
@@ -498,29 +507,41 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail_a);
-        store_rows_f32(pp, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v);
+        if (KEEP && elected) bulk_wait_read<0>();     // FP16 tile slots and fp32 row slots share the patch
+        store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v);
       }
-      // ---- heads out
+      // ---- heads out.  First hand the tensor pipe its next tile: z of the next tile goes to TMEM (the linear head has
+      // consumed the old one) and the three accumulators move to registers, so that the issuer starts the next hidden
+      // layers while this warp still scales, biases and stores the heads.
       {
+        BFVI_DBG_T(t5);
         mbar_wait(&heads_full, par_misc & 1u);
         tc_fence_after();
+        BFVI_DBG_ADD(7, t5);
+        if (lt + 1 < my_tiles) {
+          store_a_split(tl + kFZ, zreg);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_full);
+        }
         const float* bb = bias_s + 2 * H + hf * 32;
-        float v[32];
-        tmem_ld32(tl + kFG, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[2], bb[j]);
-        store_rows_f32(pp, q, lane, hf, elected, p.g + row0 * kZ, n_valid, v);
-        tmem_ld32(tl + kFLIN, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[4], bb[2 * kZ + j]);
-        store_rows_f32(pp, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, v);
-        tmem_ld32(tl + kFB + 128, v);
+        float vg[32], vl[32], va[32];
+        tmem_ld32(tl + kFG, vg);
+        tmem_ld32(tl + kFLIN, vl);
+        tmem_ld32(tl + kFB + 128, va);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&heads_empty);     // every accumulator has been read: the next tile may start
+        if (lane == 0) mbar_arrive(&heads_empty);     // every accumulator has been read
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_s[5], bb[3 * kZ + j]);
-        store_rows_f32(pp, q, lane, hf, elected, p.as + row0 * kZ, n_valid, v);
+        for (int j = 0; j < 32; ++j) {
+          vg[j] = fmaf(vg[j], inv_s[2], bb[j]);
+          vl[j] = fmaf(vl[j], inv_s[4], bb[2 * kZ + j]);
+          va[j] = fmaf(va[j], inv_s[5], bb[3 * kZ + j]);
+        }
+        store_rows_f32(pp, fs, q, lane, hf, elected, p.g + row0 * kZ, n_valid, vg);
+        store_rows_f32(pp, fs, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, vl);
+        store_rows_f32(pp, fs, q, lane, hf, elected, p.as + row0 * kZ, n_valid, va);
       }
       BFVI_DBG_ADD(4, t4);
       par_misc ^= 1u;
@@ -560,7 +581,9 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           __syncwarp();
           BFVI_DBG_ADD(2, ti);
         };
-        issue1(0);
+        issue1(0);                                    // buffer 0: free since the std head's MMAs (in order) completed
+        mbar_wait(&heads_empty, (uint32_t)((lt & 1) ^ 1));   // previous tile's accumulators (one sits in buffer 1) read out
+        tc_fence_after();
         for (int c = 0; c < U; ++c) {
           const int b = c & 1;
           if (c + 1 < U) issue1(c + 1);               // overlaps the row warps' work on pair c
@@ -568,7 +591,6 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           mbar_wait(&a_full[b], (par_a >> b) & 1u);
           par_a ^= 1u << b;
           tc_fence_after();
-          if (c == 0) { mbar_wait(&heads_empty, (uint32_t)((lt & 1) ^ 1)); tc_fence_after(); }   // previous heads read out
           BFVI_DBG_ADD(0, ta);
           BFVI_DBG_T(tw);
           wait_block(gblk + 2 * c + 1);
@@ -681,7 +703,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
     unsigned char* pp = patches + q * kPatchBytes;
     const bool elected = hf == 0 && lane == 0;
     uint32_t par_d = 0, par_misc = 0;
-    int hp = 0;
+    int hp = 0, fs = 0;
     float rg[32], rn[32];                             // next tile's d_g / d_nl half rows (prefetched during the units)
     {
       const int64_t row = (int64_t)blockIdx.x * kTileRows + q * 32 + lane;
@@ -747,7 +769,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dz_empty);
-        store_rows_f32(pp, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v);
+        if (elected) bulk_wait_read<0>();             // FP16 tile slots and fp32 row slots share the patch
+        store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v);
       }
       par_misc ^= 1u;
     }
@@ -869,6 +892,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = fused_smem_dyn + ((1024u - (smem_u32(fused_smem_dyn) & 1023u)) & 1023u);
   const int n_stages = p.n_stages;
+  // Bias gradients ride on the MMA: a constant MN-major atom whose column 0 is all ones is appended to the Y operand
+  // (N = 80 instead of 64: the B descriptor's leading-dimension offset points from the stage's Y atom to it), so
+  // accumulator column 64 = sum over the rows of X = the column sums the z -> hidden bias gradients need.
+  unsigned char* ones = smem + (size_t)n_stages * kWgStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = p.H / 128;
   const int n_items = p.n_problems * m_tiles * p.n_slices;
@@ -880,73 +907,66 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
     g0 = (int64_t)sl * p.groups_per_slice;
     g1 = g0 + p.groups_per_slice < p.n_groups ? g0 + p.groups_per_slice : p.n_groups;
   };
-  if (warp == 4) tmem_alloc(&tmem_base_s, 64);
+  if (warp == 4) tmem_alloc(&tmem_base_s, 128);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 5); }   // MMA commit + 4 warps
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&acc_full, 1); mbar_init(&acc_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < kAtomBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0u;
+  __syncthreads();
+  if (threadIdx.x < kRowGroup) {                     // element (row k, column 0) of the atom: chunk 0 ^ (k % 8), first half
+    const int k = threadIdx.x;
+    *reinterpret_cast<__half*>(ones + k * 128 + ((k & 7) << 4)) = __float2half_rn(1.f);
+  }
+  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = tmem_base_s;
 
   if (warp < 4) {
-    // ===== column sums of the X tiles while they sit in shared memory, then the accumulator epilogue =====
-    int64_t gpos = 0;
-    const int t = threadIdx.x;                        // column of the 128-wide X tile: atom t / 64, column t % 64
-    const uint32_t col_off = (uint32_t)((t >> 6) * kAtomBytes + (t & 7) * 2);
-    const int chunk = (t & 63) >> 3;
+    // ===== epilogue: accumulator (128 hidden rows x 64 z columns [+ column sums]) -> red.global.add =====
     for (int li = 0; li < my_items; ++li) {
       int pi, mt; int64_t g0, g1;
       item_of(li, pi, mt, g0, g1);
       const Wgrad16Problem& pr = p.pr[pi];
-      float csum = 0.f;
-      for (int64_t g = g0; g < g1; ++g, ++gpos) {
-        const int s = (int)(gpos % n_stages);
-        mbar_wait(&full_bar[s], (uint32_t)((gpos / n_stages) & 1));        // never ahead of the ring
-        if (pr.bias != nullptr) {
-          const unsigned char* x = smem + (size_t)s * kWgStageBytes + col_off;
-#pragma unroll 8
-          for (int r = 0; r < kRowGroup; ++r)
-            csum += __half2float(*reinterpret_cast<const __half*>(x + r * 128 + ((chunk ^ (r & 7)) << 4)));
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-      }
-      if (pr.bias != nullptr && g1 > g0) atomicAdd(pr.bias + mt * 128 + t, csum);
       mbar_wait(&acc_full, (uint32_t)(li & 1));
       tc_fence_after();
       const int h = mt * 128 + warp * 32 + lane;
-#pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
-        float v[32];
-        tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-        if (c == 32) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&acc_empty);
-        }
-        if (g1 > g0) {
-          if (pr.transposed) {                       // out (Z, H): lanes = consecutive h -> coalesced per column
+      float v0[32], v1[32], vb[32];
+      tmem_ld32(tb + ((uint32_t)(warp * 32) << 16), v0);
+      tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + 32u, v1);
+      if (pr.bias != nullptr) tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + 64u, vb);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty);
+      if (g1 > g0) {
+        if (pr.transposed) {                         // out (Z, H): lanes = consecutive h -> coalesced per column
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)(c + j) * p.H + h, v[j]);
-          } else {                                   // out (H, Z): a thread owns 32 consecutive columns of its row
+          for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)j * p.H + h, v0[j]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)h * kZ + c + j, v[j]);
-          }
+          for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)(32 + j) * p.H + h, v1[j]);
+        } else {                                     // out (H, Z): a thread owns the 64 columns of its row
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)h * kZ + j, v0[j]);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)h * kZ + 32 + j, v1[j]);
         }
+        if (pr.bias != nullptr) atomicAdd(pr.bias + h, vb[0]);
       }
     }
   } else if (warp == 4) {
     {
       const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
-      const uint32_t idesc = umma_idesc_f16_mn(128, 64);
-      const uint32_t ring = smem_u32(smem);
+      const uint32_t idesc64 = umma_idesc_f16_mn(128, 64), idesc80 = umma_idesc_f16_mn(128, 80);
+      const uint32_t ring = smem_u32(smem), ones_addr = smem_u32(ones);
       int64_t gpos = 0;
       for (int li = 0; li < my_items; ++li) {
         int pi, mt; int64_t g0, g1;
         item_of(li, pi, mt, g0, g1);
+        const bool with_bias = p.pr[pi].bias != nullptr;
+        const uint32_t idesc = with_bias ? idesc80 : idesc64;
         mbar_wait(&acc_empty, (uint32_t)((li & 1) ^ 1));
         tc_fence_after();
         for (int64_t g = g0; g < g1; ++g, ++gpos) {
@@ -954,10 +974,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
           mbar_wait(&full_bar[s], (uint32_t)((gpos / n_stages) & 1));
           tc_fence_after();
           const uint32_t xa = ring + s * kWgStageBytes, ya = xa + 2 * kAtomBytes;
+          const uint32_t y_lbo = with_bias ? ones_addr - ya : (uint32_t)kAtomBytes;
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)               // 16 rows (two 8-row K groups = 2 KB) per instruction
-              umma_f16_ss(tbu, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, kAtomBytes, 1024),
+              umma_f16_ss(tbu, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, y_lbo, 1024),
                           idesc, (g > g0 || k > 0) ? 1u : 0u);
             umma_commit(&empty_bar[s]);
           }
@@ -992,7 +1013,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tb, 64);
+  if (warp == 4) tmem_dealloc(tb, 128);
 }
 #endif  // !BFVI_EMU
 

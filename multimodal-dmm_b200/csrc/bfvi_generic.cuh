@@ -60,7 +60,15 @@ __global__ void __launch_bounds__(256) softplus_kernel(float* __restrict__ a, in
     a[i] = softplus_f(a[i]) + min_std;
 }
 
+// (R, 64) fp32 arrays written by the fused transition kernels (heads, dz) are stored with the 16-byte chunks of every
+// 128-byte half row XOR-permuted by row % 8 ("swz64"): the producing thread = row layout then writes shared memory
+// without bank conflicts and the 32 rows of a warp quadrant leave as ONE contiguous bulk copy (bfvi_fused.cuh).
+__device__ __forceinline__ int64_t row64(int64_t row, int zi, int Z, int swz) {
+  return swz ? row * 64 + (zi & 32) + ((((zi & 31) >> 2) ^ (int)(row & 7)) << 2) + (zi & 3) : row * Z + zi;
+}
+
 struct StepParams {
+  int swz;                     // heads (g, nl, lin, as) and dz are in the swz64 layout (fused path, Z = 64)
   bfvi_filter_args a;          // experts / outputs / noise of the pass (S chain sets)
   const float* z0_mean;
   const float* z0_log_std;
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ StepP
     else {
       float sm = 0.f, sv = 0.f, sq = 0.f;
       for (int k = 0; k < K; ++k) {
-        const int64_t r = (c * K + k) * Z + zi;
+        const int64_t r = row64(c * K + k, zi, Z, p.swz);
         const float gate = sigmoid_f(p.g[r]);
         const float nl = p.nl[r], lin = p.lin[r];
         const float qm = fmaf(gate, nl - lin, lin);
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(128) step4_kernel(const __grid_constant__ Step
     } else {
       float sm[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {0.f, 0.f, 0.f, 0.f}, sq[4] = {0.f, 0.f, 0.f, 0.f};
       for (int k = 0; k < K; ++k) {
-        const int64_t r = (c * K + k) * Z + zi;
+        const int64_t r = row64(c * K + k, zi, Z, p.swz);
         const float4 g4 = *reinterpret_cast<const float4*>(p.g + r), n4 = *reinterpret_cast<const float4*>(p.nl + r);
         const float4 l4 = *reinterpret_cast<const float4*>(p.lin + r), a4 = *reinterpret_cast<const float4*>(p.as + r);
         const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, nv[4] = {n4.x, n4.y, n4.z, n4.w};
@@ -481,8 +489,8 @@ __global__ void __launch_bounds__(kRowsZ * kRowsSplit) bwd_rows_kernel(const __g
       const int64_t o = (((int64_t)s * T + t) * B + b) * Z + zi;
       const float pm = a.prior_mean[o];
       const float d_pm = p.d_pm[c * Z + zi], d_v = p.d_v[c * Z + zi];
-      const int64_t q = r * Z + zi;
-      const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q], as = p.as[q];
+      const int64_t q = r * Z + zi, qh = row64(r, zi, Z, p.swz);
+      const float gate = sigmoid_f(p.g[qh]), nl = p.nl[qh], lin = p.lin[qh], as = p.as[qh];
       const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(as) + p.min_std;
       float m_k, s_k, g_gm, g_gs, d_qm, d_qs;
       poe2_forward(gm, gs, qm, qs, m_k, s_k);
@@ -545,7 +553,8 @@ __global__ void __launch_bounds__(128) bwd_carry_kernel(const __grid_constant__ 
     const int s = (int)(c / B), b = (int)(c % B);
     float cm = 0.f, cs = 0.f;
     for (int k = 0; k < K; ++k) {
-      const float d = p.dz[(c * K + k) * Z + zi] + (p.dz2 != nullptr ? p.dz2[(c * K + k) * Z + zi] : 0.f);
+      const int64_t qd = row64(c * K + k, zi, Z, p.swz);
+      const float d = p.dz[qd] + (p.dz2 != nullptr ? p.dz2[(c * K + k) * Z + zi] : 0.f);
       cm += d;
       if (sampled) cs = fmaf(d, eps_at(a.noise, s, t, b, k, zi, T, B, K, Z), cs);
     }
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(128) head_kernel(const __grid_constant__ HeadP
 // plain 2-D transpose (rows x cols) -> (cols x rows), used for per-step weight transposes
 // and the encoder inputs
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int64_t rows, int cols,
-                                                        float* __restrict__ out) {
+                                                        float* __restrict__ out, int swz = 0) {
   __shared__ float tile[32][33];
   const int64_t r0 = (int64_t)blockIdx.x * 32;
   const int c0 = blockIdx.y * 32;
@@ -614,7 +623,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   for (int j = ty; j < 32; j += 8) {
     const int64_t r = r0 + j;
     const int c = c0 + tx;
-    tile[j][tx] = (r < rows && c < cols) ? in[r * cols + c] : 0.f;
+    tile[j][tx] = (r < rows && c < cols) ? in[row64(r, c, cols, swz)] : 0.f;
   }
   __syncthreads();
   for (int j = ty; j < 32; j += 8) {
@@ -632,6 +641,7 @@ struct MatchHeadParams {
   const float* g; const float* nl; const float* lin; const float* as;   // (K, Z) GTF heads
   float* pm; float* d_pm; float* d_v;                                    // (Z)
   float min_std, coef_static;
+  int swz;                 // heads in the swz64 layout (fused path)
   const float* count;      // device scalar mask.sum() (nullable)
   double* loss_acc;
   int K, Z, with_grad;
@@ -644,7 +654,7 @@ __global__ void __launch_bounds__(128) match_head_kernel(const __grid_constant__
     const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
     float sm = 0.f, sv = 0.f, sq = 0.f;
     for (int k = 0; k < p.K; ++k) {
-      const int64_t q = (int64_t)k * p.Z + zi;
+      const int64_t q = row64(k, zi, p.Z, p.swz);
       const float gate = sigmoid_f(p.g[q]), nl = p.nl[q], lin = p.lin[q];
       const float qm = fmaf(gate, nl - lin, lin), qs = softplus_f(p.as[q]) + p.min_std;
       float m_k, s_k;
