@@ -132,11 +132,13 @@ C2 = Workload('c2', ['spiral-x', 'spiral-y'], [1, 1], 5, 20, 100, 4096, make_c2_
 C1 = Workload('c1', ['spiral-x', 'spiral-y'], [1, 1], 5, 20, 100, 100, make_c1_batch, 0.5,
               'C1: spirals.py defaults, M=2 D=1 Z=5 H=20, T=100, B=%(B)d, burst_delete(0.1), K=25, K_match=50',
               (100, 100))
-# per-GPU batch of the c3 line: the 8-GPU shard of the named job is 8 192 sequences; bfvi_step_fwd_bwd walks it in
-# batch tiles (workspace bounded), so it runs as ONE step() call
-C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 8192, make_c3_batch, 1.0 / (16 * 8),
-              'C3: scaled MDMM BFVI step, M=8 D=16 Z=64 H=512, T=1000, K=25, K_match=50, B=%(B)d per GPU '
-              '(BASELINE: global batch 65536 = 8192 per GPU on 8 B200), N(0,1) data, Philox noise', (24, 100))
+# per-GPU batch of the c3 line: the 8-GPU shard of the named job is 8 192 sequences; bfvi_step_fwd_bwd walks the batch
+# in tiles (workspace bounded), so any batch runs as ONE step() call; the default keeps a driver run within minutes
+C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 2048, make_c3_batch, 1.0 / (16 * 8),
+              'C3: scaled MDMM BFVI step, M=8 D=16 Z=64 H=512, T=1000, K=25, K_match=50, B=%(B)d per GPU, N(0,1) data, '
+              'Philox noise (BASELINE names global batch 65536 = 8192 per GPU on 8 B200; the per-GPU batch is cut to '
+              'keep a 25-step run within minutes: a step of 8192 x 1000 takes ~20 s; --batch 8192 runs the full shard, '
+              'same code path: the step walks the batch in tiles)', (24, 100))
 WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3}
 
 
@@ -273,8 +275,12 @@ def main():
                     help='GEMM operand precision of the large-dim family (c3)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the end-to-end loop (0 = min(steps, 5))')
+    ap.add_argument('--seq-len', type=int, default=0, help='override T (profiling runs under ncu only; 0 = workload T)')
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.seq_len > 0:
+        wl.t_max = args.seq_len
+        wl.desc = wl.desc.replace('T=1000', 'T=%d (PROFILING OVERRIDE of T=1000)' % args.seq_len)
     if args.impl == 'reference':
         return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
@@ -408,10 +414,23 @@ def main():
             kernel_probe = prof
         except Exception:
             pass
-        roofline = {'bound': 'tensor', 'kernel': 'whole step (launch sequence; dominant: fused GTF row-tile kernels)',
-                    'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
-                    'algorithmic_flops_per_seq_ts': wl.flops_per_seq_ts,
-                    'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)'}
+        step_roofline = {'bound': 'tensor', 'kernel': 'whole step', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
+                         'frac': ach / peak, 'algorithmic_flops_per_seq_ts': wl.flops_per_seq_ts,
+                         'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback (B200_PROFILING.md)'}
+        # dominant kernels, each timed alone (CUDA events around back-to-back launches on the launching stream) on the
+        # rows ONE particle-pass time step launches: (1 + M) chain sets x batch tile x K particles
+        tile = b_dim
+        for d in dispatch:
+            if d.startswith('step:batch_tiles='):
+                tile = int(d.split('x')[-1])
+        rows = (1 + len(wl.mods)) * tile * wl.k_train
+        kernel_probe = gtf_kernel_rooflines(model, wl, rows, peaks)
+        dom = kernel_probe['gtf_fwd_kernel<keep>']
+        roofline = {'bound': 'tensor', 'kernel': 'gtf_fwd_kernel<keep> (fused transition forward, the largest share of the '
+                                                 'step; one launch = one particle-pass time step of a batch tile)',
+                    'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s', 'frac': dom['frac'],
+                    'traffic': traffic, 'algorithmic_flops_per_launch': dom['flops'], 'rows_per_launch': rows,
+                    'ms_per_launch': dom['ms'], 'peak_source': dom['peak_source'], 'whole_step': step_roofline}
     if rank == 0 and not large:
         roofline, roofline_fp32, phases = small_roofline(model, wl, inputs_d, targets_d, mask_d, rec, b_dim, t_max,
                                                          flush, peaks, args)
@@ -447,6 +466,41 @@ def main():
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def gtf_kernel_rooflines(model, wl, rows, peaks):
+    """Per-kernel roofline of the fused transition kernels: bfvi_gtf_probe times each kernel alone on `rows` latent rows.
+    Algorithmic FLOPs per row (F_gtf = 8ZH + 4Z^2): forward F_gtf; input gradient F_gtf; weight gradients F_gtf
+    (the KEEP forward is the backward's recompute: its F_gtf is NOT algorithmic work of the step, but it is what the
+    launch computes, and it is reported as such).  Peak: measured burst dense BF16 (a kernel timed alone)."""
+    from multimodal_dmm_b200 import _lib
+    lib = _lib.load()
+    dev = model._flat.device
+    peak = float(peaks.get('bf16_tflops', 1590.0))
+    nbytes = int(lib.dll.bfvi_gtf_workspace(C.byref(model._cmodel), rows))
+    if nbytes == 0:
+        return None
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    ws = ws[(-ws.data_ptr()) % 256:]
+    z = torch.randn(rows, wl.z, device=dev)
+    scratch = torch.empty(5 * rows * 64, device=dev)
+    out = {}
+    names = ['gtf_fwd_kernel', 'gtf_fwd_kernel<keep>', 'gtf_bwd_kernel', 'wgrad16_kernel']
+    ms = C.c_float(0.0)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for which, name in enumerate(names):
+        lib.call('bfvi_gtf_probe', C.byref(model._cmodel), _lib.ptr(model._flat), 1, which, _lib.ptr(z), rows, 3,
+                 _lib.ptr(scratch), _lib.ptr(ws), C.c_size_t(nbytes), C.byref(ms), st)      # warm-up
+        lib.call('bfvi_gtf_probe', C.byref(model._cmodel), _lib.ptr(model._flat), 1, which, _lib.ptr(z), rows, 10,
+                 _lib.ptr(scratch), _lib.ptr(ws), C.c_size_t(nbytes), C.byref(ms), st)
+        # the Z x Z corners outside a kernel are not counted for it: input gradient without the std layer, weight
+        # gradients of the four H-wide layers only
+        per_row = [wl.f_gtf, wl.f_gtf, wl.f_gtf - 2 * wl.z * wl.z, 8 * wl.z * wl.h][which]
+        flops = float(rows) * per_row
+        out[name] = {'ms': ms.value, 'flops': flops, 'achieved': flops / (ms.value * 1e-3) / 1e12, 'peak': peak,
+                     'frac': flops / (ms.value * 1e-3) / 1e12 / peak,
+                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst)' if peaks else 'fallback'}
+    return out
 
 
 def small_roofline(model, wl, inputs_d, targets_d, mask_d, rec, b_dim, t_max, flush, peaks, args):

@@ -443,6 +443,15 @@ int bfvi_gtf_bwd(const bfvi_model* model, const float* params, float* grads, int
                  const float* nonlin, int64_t n_rows, const float* d_gate_pre, const float* d_nonlin, const float* d_lin,
                  const float* d_std_pre, float* d_z, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's per-kernel roofline): average device time of ONE launch of a fused transition kernel on
+ * n_rows latent rows, CUDA events on `stream` around `iters` back-to-back launches (SYNCHRONISES).  which: 0 = forward
+ * (gtf_fwd_kernel), 1 = forward<keep> (the backward's recompute), 2 = input gradient (gtf_bwd_kernel), 3 = H-wide weight
+ * gradients (wgrad16_kernel).  scratch_rows: 5 * n_rows * 64 floats (n_rows >= 4 * h_dim for which = 3); workspace as
+ * bfvi_gtf_workspace. */
+int bfvi_gtf_probe(const bfvi_model* model, const float* params, int32_t direction, int32_t which, const float* z,
+                   int64_t n_rows, int32_t iters, float* scratch_rows, void* workspace, size_t workspace_bytes,
+                   float* ms_per_launch, void* stream);
+
 /* The optimiser step either side of the hot path (trainer.py:248-252), fused over the flat
  * buffers: optional clip_grad_norm_ (max_norm > 0; total L2 norm over the whole flat gradient,
  * coefficient max_norm / (norm + 1e-6) clamped to 1) followed by torch.optim.Adam (no amsgrad;

@@ -180,6 +180,8 @@ SYMBOLS = {
                      + [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),
     'bfvi_gtf_bwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
                      + [C.c_void_p] * 5 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'bfvi_gtf_probe': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float), C.c_void_p]),
     'bfvi_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float, C.c_float,
                                                                                     C.c_void_p, C.c_void_p]),
     'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),

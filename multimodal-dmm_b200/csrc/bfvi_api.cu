@@ -1594,8 +1594,18 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
 // are independent: the step walks the batch in tiles of `bt` sequences — inputs / targets / mask of a tile are staged
 // into contiguous (T, bt, D) buffers (strided 2-D copies), the tile runs as a step of its own with the noise indexed by
 // the global sequence index, gradients and loss accumulate across tiles.
+// Workspace budget of one batch tile: 60 % of the device's memory (a B200: 107 GB -> ~1 000 sequences of T = 1 000 at
+// the C3 shape; larger tiles amortise the latency-bound single-particle passes), BFVI_TILE_GB overrides.  A function of
+// the TOTAL memory, so bfvi_step_workspace and bfvi_step_fwd_bwd always agree.
 size_t tile_budget_bytes() {
-  static const size_t b = [] { const char* e = getenv("BFVI_TILE_GB"); return (size_t)((e ? atof(e) : 40.0) * (double)(1ull << 30)); }();
+  static const size_t b = [] {
+    if (const char* e = getenv("BFVI_TILE_GB")) return (size_t)(atof(e) * (double)(1ull << 30));
+#ifndef BFVI_EMU
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) return (size_t)(0.6 * (double)total_b);
+#endif
+    return (size_t)40 << 30;
+  }();
   return b;
 }
 struct TiledPlan { int bt, n_tiles; size_t acc, count, stage_in[BFVI_MAX_MODS], stage_tg[BFVI_MAX_MODS], stage_mask, tile_ws, tile_bytes, total; };
@@ -2282,6 +2292,55 @@ int bfvi_gtf_fwd(const bfvi_model* m, const float* params, int32_t direction, co
   if (int rc = fused_fwd(fb, direction, m->h_dim, z, n_rows, gate_pre, nonlin, lin, std_pre, keep != 0, st)) return rc;
   for (float* x : {gate_pre, nonlin, lin, std_pre})      // the kernels write the swz64 layout; callers get plain rows
     unswz64_kernel<<<dim3((unsigned)grid_for(n_rows, 8, 8)), dim3(256), 0, st>>>(x, n_rows);
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+#endif
+}
+
+int bfvi_gtf_probe(const bfvi_model* m, const float* params, int32_t direction, int32_t which, const float* z, int64_t n_rows,
+                   int32_t iters, float* scratch_rows, void* workspace, size_t workspace_bytes, float* ms_per_launch, void* stream) {
+  g_dispatch.clear();
+  if (int rc = check_model(m)) return rc;
+  if (!params || !z || !scratch_rows || !ms_per_launch || n_rows < 1 || iters < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (which < 0 || which > 3) return fail(BFVI_ERR_ARG, "which: 0 forward, 1 forward<keep>, 2 input gradient, 3 weight gradients");
+  if (!fused_supported(m->z_dim, m->h_dim)) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernels do not serve this shape");
+#ifdef BFVI_EMU
+  (void)direction; (void)workspace; (void)workspace_bytes; (void)stream;
+  return fail(BFVI_ERR_UNSUPPORTED, "tcgen05 kernels do not exist in the emulator build");
+#else
+  const GtfWs w = gtf_ws_plan(m->h_dim, n_rows);
+  if (!workspace || workspace_bytes < w.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, w.total);
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  FusedBufs fb;
+  fused_carve_packs((char*)workspace + w.packs, m->h_dim, &fb);
+  fused_carve_rows((char*)workspace + w.rows, m->h_dim, n_rows, &fb);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int H = m->h_dim;
+  float* o[5];
+  for (int i = 0; i < 5; ++i) o[i] = scratch_rows + (size_t)i * n_rows * 64;
+  if (int rc = fused_pack(lay.trans[direction], params, direction, H, fb, st)) return rc;
+  // operands of the later kernels: one KEEP forward (whose heads double as head gradients: any finite values do)
+  if (int rc = fused_fwd(fb, direction, H, z, n_rows, o[0], o[1], o[2], o[3], true, st)) return rc;
+  if (which >= 3) { if (int rc = fused_bwd(fb, direction, H, o[0], o[1], o[2], n_rows, o[4], st)) return rc; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = BFVI_OK;
+  // throw-away gradient buffer for which = 3: the first floats of the row scratch are not read by that kernel
+  cudaEventRecord(e0, st);
+  for (int it = 0; it < iters && rc == BFVI_OK; ++it) {
+    if (which == 0) rc = fused_fwd(fb, direction, H, z, n_rows, o[0], o[1], o[2], o[3], false, st);
+    else if (which == 1) rc = fused_fwd(fb, direction, H, z, n_rows, o[0], o[1], o[2], o[3], true, st);
+    else if (which == 2) rc = fused_bwd(fb, direction, H, o[0], o[1], o[2], n_rows, o[4], st);
+    else rc = fused_wgrad(fb, H, n_rows, o[4], o[4] + (size_t)H * 64, o[4] + (size_t)2 * H * 64, o[4] + (size_t)3 * H * 64, o[3], o[3] + H, st);
+  }
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (rc != BFVI_OK) return rc;
+  *ms_per_launch = ms / (float)iters;
   BFVI_CHECK_CUDA();
   return BFVI_OK;
 #endif
