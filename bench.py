@@ -230,6 +230,44 @@ def oracle_step_time(wl, b_dim, t_max, steps, warmup, threads):
     return float(np.mean(times)), b_dim * t_max
 
 
+def reference_step_time(wl, b_dim, t_max, steps, warmup, threads):
+    """Mean seconds per step + seq-timesteps per step of the UNMODIFIED reference's own MultiDMM.step + backward
+    (models/dmm.py:503-554, trainer.py:237-243) on the host cores, imported from the byte-compiled copy under
+    oracle/_ref/ (oracle/build_ref.py; /root/reference itself does not exist on the GPU box).  None when absent."""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import ref_shim
+    if ref_shim.reference_root() is None:
+        return None
+    ref_models = ref_shim.import_reference_models()
+    torch.set_num_threads(threads)
+    inputs, targets, mask, lengths = wl.make(b_dim, t_max, 1)
+    rec = {m: wl.rec for m in wl.mods}
+    torch.manual_seed(1)
+    model = ref_models.MultiDMM(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, device=torch.device('cpu'))
+    model.train()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        loss = model.step(inputs, mask, KLD_MULT, rec, targets=targets, lengths=lengths,
+                          train_particles=wl.k_train, match_particles=wl.k_match)
+        (loss / sum(lengths)).backward()
+        model.zero_grad()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return float(np.mean(times)), b_dim * t_max
+
+
+def cpu_step_time(wl, b_dim, t_max, steps, warmup, threads):
+    """(seconds per step, seq-timesteps per step, kind): the reference itself when oracle/_ref/ holds it, else the
+    oracle port of the same algorithm."""
+    r = reference_step_time(wl, b_dim, t_max, steps, warmup, threads)
+    if r is not None:
+        return r[0], r[1], 'reference'
+    sec, seq_ts = oracle_step_time(wl, b_dim, t_max, steps, warmup, threads)
+    return sec, seq_ts, 'port'
+
+
 def run_reference(args, wl):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -237,17 +275,19 @@ def run_reference(args, wl):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     cores = os.cpu_count() or 1
     b_ref, t_ref = wl.ref_sample
-    sec, seq_ts = oracle_step_time(wl, b_ref, t_ref, args.steps, args.warmup, cores)
+    sec, seq_ts, kind = cpu_step_time(wl, b_ref, t_ref, args.steps, args.warmup, cores)
     value = seq_ts / sec
     b_dim = per_gpu_batch(args, wl, world)
-    sample = ('oracle port of the reference on %d torch threads: %s workload at B=%d, T=%d (K=%d particles), '
-              '%d warm-up + %d timed steps' % (cores, wl.key.upper(), b_ref, t_ref, wl.k_train, args.warmup, args.steps))
+    sample = ('%s on %d torch threads: %s workload at B=%d, T=%d (K=%d particles), %d warm-up + %d timed steps' %
+              ("the reference's own MultiDMM.step + backward (byte-compiled from the unmodified sources, oracle/_ref)"
+               if kind == 'reference' else 'oracle port of the reference', cores, wl.key.upper(), b_ref, t_ref,
+               wl.k_train, args.warmup, args.steps))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'fp32',
         'data': 'synthetic', 'config': config_of(wl, b_dim, world, args.scaling),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
 
@@ -439,10 +479,11 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         b_ref, t_ref = wl.ref_sample
-        sec, seq_ts = oracle_step_time(wl, b_ref, t_ref, 3, 1, cores)
-        cpu_baseline = {'value': seq_ts / sec, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                        'sample': 'oracle port of the reference, 1 warm-up + 3 timed steps of the %s workload at '
-                                  'B=%d, T=%d on %d torch threads' % (wl.key.upper(), b_ref, t_ref, cores)}
+        sec, seq_ts, kind = cpu_step_time(wl, b_ref, t_ref, 3, 1, cores)
+        cpu_baseline = {'value': seq_ts / sec, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                        'sample': '%s, 1 warm-up + 3 timed steps of the %s workload at B=%d, T=%d on %d torch threads' %
+                                  ("the reference's own MultiDMM.step + backward (oracle/_ref)" if kind == 'reference'
+                                   else 'oracle port of the reference', wl.key.upper(), b_ref, t_ref, cores)}
 
     if rank == 0:
         out = {
