@@ -735,9 +735,11 @@ void fused_carve_rows(char* base, int H, int64_t rows, FusedBufs* fb) {
 }
 #ifndef BFVI_EMU
 int fused_smem_limit() { return 232448; }
+// development: ablation mask of the fused kernels (timing probes only; read per call so a probe can switch it)
+int fused_abl() { const char* e = getenv("BFVI_FUSED_ABL"); return e ? atoi(e) : 0; }
 int fused_stages(size_t extra_bytes) {
   int st = (int)((fused_smem_limit() - 1024 - extra_bytes) / bfvi::fused::kBlockBytes);
-  if (st > bfvi::fused::kMaxStages) st = bfvi::fused::kMaxStages;
+  if (st > 6) st = 6;
   static const int cap = [] { const char* e = getenv("BFVI_FUSED_STAGES"); return e ? atoi(e) : 99; }();
   if (st > cap) st = cap;
   return st;
@@ -763,7 +765,7 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
   memset(&fp, 0, sizeof(fp));
   fp.pack = fb.pack_fwd[dir]; fp.bias = fb.bias[dir]; fp.z = z; fp.g = g; fp.nl = nl; fp.lin = lin; fp.as = as;
   fp.h16 = (__half*)fb.h16; fp.relu_bits = fb.bits; fp.z16 = (__half*)fb.z16;
-  fp.R = rows; fp.H = H;
+  fp.R = rows; fp.H = H; fp.abl = fused_abl();
   const size_t extra = bfvi::fused::bias_floats(H) * 4 + kFusedPatches;
   fp.n_stages = fused_stages(extra);
   if (fp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: h_dim %d too wide", H);
@@ -800,7 +802,7 @@ int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float
   memset(&bp, 0, sizeof(bp));
   bp.pack = fb.pack_bwd[dir]; bp.d_g = d_g; bp.d_nl = d_nl; bp.d_lin = d_lin; bp.relu_bits = fb.bits; bp.dz = dz;
   bp.dh16 = (__half*)fb.dh16; bp.dg16 = (__half*)fb.dg16; bp.dnl16 = (__half*)fb.dnl16;
-  bp.R = rows; bp.H = H;
+  bp.R = rows; bp.H = H; bp.abl = fused_abl();
   bp.n_stages = fused_stages(kFusedPatches);
   if (bp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: no room for the weight ring");
   const size_t smem = (size_t)bp.n_stages * bfvi::fused::kBlockBytes + kFusedPatches + 1024;
@@ -829,7 +831,7 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
   prob(1, fb.dh16, U, fb.z16, dw_non0, 0, gb_non0);         // dW_nonlin0 (H, Z) = dh3^T z
   prob(2, fb.h16, 0, fb.dg16, dw_gate2, 1, nullptr);        // dW_gate2 (Z, H) = d_g^T h1, computed as h1^T d_g
   prob(3, fb.h16, U, fb.dnl16, dw_non2, 1, nullptr);        // dW_nonlin2 (Z, H) = d_nl^T h3
-  wp.n_problems = 4; wp.H = H;
+  wp.n_problems = 4; wp.H = H; wp.abl = fused_abl();
   wp.n_groups = fused_rows_pad(rows) / 64;
   const int sms = num_sms() > 0 ? num_sms() : 1;
   const int tiles = 4 * (H / 128);
@@ -838,7 +840,8 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
   if (slices < 1) slices = 1;
   wp.groups_per_slice = (int)((wp.n_groups + slices - 1) / slices);
   wp.n_slices = (int)((wp.n_groups + wp.groups_per_slice - 1) / wp.groups_per_slice);
-  wp.n_stages = bfvi::fused::kMaxStages;
+  wp.n_stages = 6;
+  if (const char* e = getenv("BFVI_WGRAD_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= bfvi::fused::kMaxStages) wp.n_stages = v; }
   const size_t smem = (size_t)wp.n_stages * bfvi::fused::kWgStageBytes + bfvi::fused::kAtomBytes + 1024;
   const int items = tiles * wp.n_slices;
   auto k = bfvi::fused::wgrad16_kernel;
@@ -916,7 +919,10 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   for (int i = 0; i < 6; ++i) pl->pa[i] = carve(fS);
   for (int i = 0; i < 4; ++i) pl->pb[i] = carve(fS);
   for (int i = 0; i < 6; ++i) pl->pc[i] = carve(fS);
-  const size_t rz = f * R * Z, rh = f * R * H;
+  pl->fused = (a != nullptr && a->precision == BFVI_PREC_FUSED && fused_supported(Z, H)) ? 1 : 0;
+  // hidden activations / gradients of a time step's transition (+ transposed copies): launch-sequence path only
+  // (the fused kernels keep them on-chip and write FP16 operand tiles into `fused_rows` instead)
+  const size_t rz = f * R * Z, rh = pl->fused ? 256 : f * R * H;
   pl->zrows = carve(rz); pl->zrowsT = carve(rz);
   pl->h1 = carve(rh); pl->h1T = carve(rh); pl->h3 = carve(rh); pl->h3T = carve(rh);
   pl->dh1 = carve(rh); pl->dh1T = carve(rh); pl->dh3 = carve(rh); pl->dh3T = carve(rh);
@@ -930,7 +936,6 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   pl->dhd = carve(f * pl->tb * H); pl->dhdT = carve(f * pl->tb * H);
   pl->dmean = carve(f * pl->tb * pl->d_max); pl->dstd = carve(f * pl->tb * pl->d_max);
   pl->dmeanT = carve(f * pl->tb * pl->d_max); pl->dstdT = carve(f * pl->tb * pl->d_max);
-  pl->fused = (a != nullptr && a->precision == BFVI_PREC_FUSED && fused_supported(Z, H)) ? 1 : 0;
   pl->fused_packs = pl->fused_rows = 0;
   if (pl->fused) {
     cur = align_up(cur, 1024);
@@ -960,7 +965,7 @@ void plan_large_side(const bfvi_model* m, const bfvi_step_args* a, const LargePl
   ps->zero_end = cur;
   const size_t R = pl.C;                               // one particle per chain
   ps->R = R;
-  const size_t rz = f * R * Z, rh = f * R * H;
+  const size_t rz = f * R * Z, rh = pl.fused ? 256 : f * R * H;
   ps->zrows = carve(rz); ps->zrowsT = carve(rz);
   ps->h1 = carve(rh); ps->h1T = carve(rh); ps->h3 = carve(rh); ps->h3T = carve(rh);
   ps->dh1 = carve(rh); ps->dh1T = carve(rh); ps->dh3 = carve(rh); ps->dh3T = carve(rh);
@@ -1594,15 +1599,16 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
 // are independent: the step walks the batch in tiles of `bt` sequences — inputs / targets / mask of a tile are staged
 // into contiguous (T, bt, D) buffers (strided 2-D copies), the tile runs as a step of its own with the noise indexed by
 // the global sequence index, gradients and loss accumulate across tiles.
-// Workspace budget of one batch tile: 60 % of the device's memory (a B200: 107 GB -> ~1 000 sequences of T = 1 000 at
-// the C3 shape; larger tiles amortise the latency-bound single-particle passes), BFVI_TILE_GB overrides.  A function of
+// Workspace budget of one batch tile: 78 % of the device's memory (a B200: 139 GB -> 1 152 sequences of T = 1 000 at
+// the C3 shape; larger tiles amortise the latency-bound single-particle passes: a time step of a tile costs
+// ~0.6 ms + 1.6 us per sequence, gpurun_out/r2_pass_breakdown.txt), BFVI_TILE_GB overrides.  A function of
 // the TOTAL memory, so bfvi_step_workspace and bfvi_step_fwd_bwd always agree.
 size_t tile_budget_bytes() {
   static const size_t b = [] {
     if (const char* e = getenv("BFVI_TILE_GB")) return (size_t)(atof(e) * (double)(1ull << 30));
 #ifndef BFVI_EMU
     size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) return (size_t)(0.6 * (double)total_b);
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && total_b > 0) return (size_t)(0.78 * (double)total_b);
 #endif
     return (size_t)40 << 30;
   }();

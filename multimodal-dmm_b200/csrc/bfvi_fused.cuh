@@ -61,10 +61,18 @@ constexpr int kBlockBytes = 32768;     // one weight block (one ring stage)
 constexpr int kTileBytes = 16384;
 constexpr int kRowWarps = 8;
 constexpr int kThreads = (kRowWarps + 2) * 32;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 9;
 constexpr int kRowGroup = 64;          // rows per FP16 operand tile of the weight-gradient GEMM (one K stage)
 constexpr int kAtomBytes = 8192;       // 64 rows x 64 halves, MN-major SWIZZLE_128B
-constexpr int kPatchBytes = 16384;     // per 32-lane quadrant (two row warps): two 32 rows x 256 B slots = four 32 x 128 B slots
+constexpr int kPatchBytes = 16384;
+// development ablations (timing only, results are garbage): skip FP16 tile stores / fp32 row stores / ReLU bits /
+// second-level MMAs (heads, dz) / first-level MMAs (hidden) / row-warp arithmetic
+constexpr int kAblTile16 = 1, kAblRows = 2, kAblBits = 4, kAblMma2 = 8, kAblMma1 = 16, kAblMath = 32;
+// kStoreLsu (64, a real variant, results valid): results leave through coalesced st.global by the pair's 64 threads instead
+// of cp.async.bulk (whose requests queue behind the weight ring's bulk loads in the SM's one copy engine)
+constexpr int kStoreLsu = 64;
+// 128 (timing only): the loaders stop copying after the first lap of the ring (stale operands): is the ring the limit?
+constexpr int kAblRing = 128;     // per 32-lane quadrant (two row warps): two 32 rows x 256 B slots = four 32 x 128 B slots
 
 // shared-memory image of a 64 x 64 fp32 operand tile, K-major SWIZZLE_128B: two K halves of 32 floats; row r of a
 // half is one 128-byte line whose 16-byte chunks are XOR-permuted by r % 8 (8-row groups 1024 B apart)
@@ -256,12 +264,30 @@ __device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64
 // lanes of a store on the same four banks (rows are 64 words apart; measured 2 500 cycles per 8 KB) — and the consumers
 // (step / bwd_rows / carry / match kernels) apply the same permutation when they read.
 __device__ __forceinline__ void store_rows_f32(unsigned char* pp, int& slot, int q, int lane, int hf, bool elected,
-                                               float* __restrict__ dst_row0, int n_valid, const float (&v)[32]) {
-  if (elected) bulk_wait_read<1>();                  // the copy that used this slot two stores ago has read it
-  pair_sync(q);
+                                               float* __restrict__ dst_row0, int n_valid, const float (&v)[32],
+                                               bool lsu = false) {
   unsigned char* base = pp + slot * 8192;
   unsigned char* prow = base + lane * 256 + hf * 128;
   const int sw = lane & 7;                           // = row % 8 (row0 is a multiple of 32)
+  if (lsu) {
+    // two slots alternate and every call has one barrier between its writes and its reads: a thread can run at most
+    // one barrier ahead, i.e. write the OTHER slot while a slower thread still reads this one
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      *reinterpret_cast<float4*>(prow + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    pair_sync(q);
+    const int tid = hf * 32 + lane;
+    unsigned char* dst = reinterpret_cast<unsigned char*>(dst_row0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {                    // 64 threads x 16 B = 1 KB (four rows) per round, full lines
+      const int chunk = i * 64 + tid;
+      if ((chunk >> 4) < n_valid) __stcs(reinterpret_cast<float4*>(dst + chunk * 16), *reinterpret_cast<const float4*>(base + chunk * 16));
+    }
+    slot ^= 1;
+    return;
+  }
+  if (elected) bulk_wait_read<1>();                  // the copy that used this slot two stores ago has read it
+  pair_sync(q);
 #pragma unroll
   for (int i = 0; i < 8; ++i)                        // swz64: chunk i of the half row sits at i ^ (row % 8)
     *reinterpret_cast<float4*>(prow + ((i ^ sw) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -273,16 +299,27 @@ __device__ __forceinline__ void store_rows_f32(unsigned char* pp, int& slot, int
   }
   slot ^= 1;
 }
+// the patch changes hands between FP16 tile slots and fp32 row slots (they overlap): every earlier copy has read it
+__device__ __forceinline__ void patch_switch(int q, bool elected, bool lsu) {
+  if (lsu) pair_sync(q);
+  else if (elected) bulk_wait_read<0>();
+}
 // FP16 operand tiles of the weight-gradient GEMM: (row group of 64 rows) x (atom of 64 columns) = 8 KB, row r of the
 // group is a 128-byte line, 16-byte chunk c stored at c ^ (r % 8): the MN-major SWIZZLE_128B shared-memory image, so
-// the GEMM loads a tile with one bulk copy.  The quadrant's 32 rows are 4 KB contiguous in that image; thread (row,
+// the GEMM loads a tile with one bulk copy.  Tiles of a multi-atom array (hidden-sized: 2U atoms) are laid out
+// [atom pair][row group][2 atoms]: a weight-gradient work item (128 hidden columns = one atom pair, a slice of the row
+// groups) then streams ONE contiguous run of 16 KB blocks — with row-group-major tiles the same item read 16 KB every
+// 128 KB, 304 such streams at once, and the launch reached 45 % of the DRAM bandwidth
+// (profiles/r2_wgrad16_big_full.txt).  The quadrant's 32 rows are 4 KB contiguous in that image; thread (row,
 // half) writes its four chunks (conflict-free thanks to the XOR) into half `buf` of the pair patch, which leaves as one
 // 4 KB bulk copy.  Tiles are padded to whole row tiles, so rows past the end are written (as zeros) too.
 __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int q, int lane, int hf, bool elected,
-                                               __half* __restrict__ base, int64_t row0, int n_atoms, int atom,
-                                               const float (&v)[32]) {
-  if (elected) bulk_wait_read<3>();                  // the copy that used this slot four stores ago has read it
-  pair_sync(q);
+                                               __half* __restrict__ base, int64_t row0, int64_t n_groups, int n_atoms,
+                                               int atom, const float (&v)[32], bool lsu = false) {
+  if (!lsu) {
+    if (elected) bulk_wait_read<3>();                // the copy that used this slot four stores ago has read it
+    pair_sync(q);
+  }
   unsigned char* prow = pp + buf * 4096 + lane * 128;
   const int sw = lane & 7;                           // row0 is a multiple of 32
 #pragma unroll
@@ -294,11 +331,23 @@ __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int 
     pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
     *reinterpret_cast<uint4*>(prow + (((hf * 4 + c) ^ sw) << 4)) = pk;
   }
+  const size_t g = (size_t)(row0 / kRowGroup);
+  const size_t idx = n_atoms == 1 ? g : ((size_t)(atom >> 1) * (size_t)n_groups + g) * 2 + (size_t)(atom & 1);
+  unsigned char* tile = reinterpret_cast<unsigned char*>(base) + idx * kAtomBytes + (size_t)(row0 % kRowGroup) * 128;
+  if (lsu) {                                         // (slots rotate: see store_rows_f32)
+    pair_sync(q);
+    const int tid = hf * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = i * 64 + tid;
+      __stcs(reinterpret_cast<uint4*>(tile + chunk * 16), *reinterpret_cast<const uint4*>(pp + buf * 4096 + chunk * 16));
+    }
+    buf = (buf + 1) & 3;
+    return;
+  }
   fence_async_smem();
   pair_sync(q);
   if (elected) {
-    unsigned char* tile = reinterpret_cast<unsigned char*>(base) +
-                          ((size_t)(row0 / kRowGroup) * n_atoms + atom) * kAtomBytes + (size_t)(row0 % kRowGroup) * 128;
     bulk_s2g(tile, pp + buf * 4096, 4096);
     bulk_commit();
   }
@@ -347,18 +396,30 @@ __device__ __forceinline__ void mma_split(uint32_t tb, uint32_t d_col, uint32_t 
   }
 }
 
+// Ring positions are small unsigned counters divided by a launch constant (ring depth, blocks per tile): a multiply
+// by the rounded-up reciprocal is exact for g < 2^32 / n.  The 64-bit `%` and `/` these loops used first are ~50
+// dependent instructions EACH in the one thread that issues the MMAs / the bulk copies (measured: 720 cycles per
+// ring step with nothing else left in the loop, tools/probe_fused_ablate.py masks 191 / 0).
+struct FastDiv {
+  uint32_t n, m;
+  __device__ __forceinline__ explicit FastDiv(int n_) : n((uint32_t)n_), m((uint32_t)(0x100000000ull / (uint32_t)n_) + 1u) {}
+  __device__ __forceinline__ uint32_t div(uint32_t g) const { return __umulhi(g, m); }
+  __device__ __forceinline__ uint32_t mod(uint32_t g) const { return g - __umulhi(g, m) * n; }
+};
+
 struct FwdParams {
   const unsigned char* pack;     // forward pack
   const float* bias;             // bias + scale table (see PackParams)
   const float* z;                // (R, 64)
   float* g; float* nl; float* lin; float* as;      // (R, 64) heads, biases added
-  __half* h16;                   // KEEP: hidden activations, FP16 tiles [row group][2U atoms]
+  __half* h16;                   // KEEP: hidden activations, FP16 tiles [atom pair][row group][2 atoms]
   uint32_t* relu_bits;           // KEEP: sign bits of the hidden activations, [row tile][unit][half][128 rows] words
   __half* z16;                   // KEEP: FP16 tiles of z [row group][1 atom]
   int64_t R;
   int H;
   int n_stages;
   long long* dbg;                // development: cycle counters of CTA 0 (BFVI_FUSED_DBG=1), nullable
+  int abl;                       // development: ablation mask (BFVI_FUSED_ABL, tools/probe_fused_ablate.py); 0 in the product
 };
 #define BFVI_DBG_T(var) const long long var = p.dbg ? clock64() : 0
 #define BFVI_DBG_ADD(i, t0) do { if (p.dbg && blockIdx.x == 0 && lane == 0) dbg_acc[i] += clock64() - (t0); } while (0)
@@ -407,6 +468,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);   // my lane group, my column half
     unsigned char* pp = patches + q * kPatchBytes;    // the quadrant's pair patch
     const bool elected = hf == 0 && lane == 0;
+    const bool lsu = (p.abl & kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
     int hp = 0, fs = 0;                               // next FP16 tile slot (4 x 4 KB) / fp32 rows slot (2 x 8 KB) of the patch
     long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -424,9 +486,9 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       // (all MMAs of the previous tile are complete: this warp has passed heads_full of that tile)
       const int64_t row0 = tile * kTileRows + q * 32;
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
-      if (KEEP) {
-        if (elected) bulk_wait_read<0>();             // the fp32 rows of the previous tile used the same shared memory
-        store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 1, 0, zreg);
+      if (KEEP && !(p.abl & kAblTile16)) {
+        patch_switch(q, elected, lsu);                // the fp32 rows of the previous tile used the same shared memory
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 2 * n_tiles, 1, 0, zreg, lsu);
       }
       if (lt == 0) {                                  // (later tiles: written during the previous tile's tail)
         store_a_split(tl + kFZ, zreg);
@@ -457,6 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_T(t2);
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + br * H + c * kHU + hf * 32);
           const float sc = inv_s[br];
+          if (!(p.abl & kAblMath))
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 bb = b4[cc];
@@ -471,15 +534,20 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
             uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-            p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
+            if (!(p.abl & kAblBits)) p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
             // rows past the end contribute nothing to the weight gradients (their A operand is irrelevant: no output
-            // row is stored for them).  Selected, not branched: the named barriers inside must be reached convergently.
+            // row is stored for them).  Only the last tile has such rows: a warp-uniform test skips the 32 selects
+            // elsewhere (and lets the FP16 conversions of the tile store and of the A operand share their work); the
+            // selects themselves stay branch-free, the named barriers further down are reached convergently.
+            if (n_valid < 32) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
-            store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, U2, u, v);
+              for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+            }
+            if (!(p.abl & kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, 2 * n_tiles, U2, u, v, lsu);
           }
           BFVI_DBG_ADD(2, t2);
           BFVI_DBG_T(t3);
+          if (p.abl & kAblMath) tmem_st32(tl + kFB + b * 128 + br * 64, v); else
           store_a_split(tl + kFB + b * 128 + br * 64, v);
           BFVI_DBG_ADD(3, t3);
         }
@@ -507,8 +575,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail_a);
-        if (KEEP && elected) bulk_wait_read<0>();     // FP16 tile slots and fp32 row slots share the patch
-        store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v);
+        if (KEEP) patch_switch(q, elected, lsu);      // FP16 tile slots and fp32 row slots share the patch
+        if (!(p.abl & kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v, lsu);
       }
       // ---- heads out.  First hand the tensor pipe its next tile: z of the next tile goes to TMEM (the linear head has
       // consumed the old one) and the three accumulators move to registers, so that the issuer starts the next hidden
@@ -539,9 +607,11 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           vl[j] = fmaf(vl[j], inv_s[4], bb[2 * kZ + j]);
           va[j] = fmaf(va[j], inv_s[5], bb[3 * kZ + j]);
         }
-        store_rows_f32(pp, fs, q, lane, hf, elected, p.g + row0 * kZ, n_valid, vg);
-        store_rows_f32(pp, fs, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, vl);
-        store_rows_f32(pp, fs, q, lane, hf, elected, p.as + row0 * kZ, n_valid, va);
+        if (!(p.abl & kAblRows)) {
+          store_rows_f32(pp, fs, q, lane, hf, elected, p.g + row0 * kZ, n_valid, vg, lsu);
+          store_rows_f32(pp, fs, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, vl, lsu);
+          store_rows_f32(pp, fs, q, lane, hf, elected, p.as + row0 * kZ, n_valid, va, lsu);
+        }
       }
       BFVI_DBG_ADD(4, t4);
       par_misc ^= 1u;
@@ -562,9 +632,10 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       const uint32_t idesc64 = umma_idesc_f16_k(kTileRows, 64), idesc128 = umma_idesc_f16_k(kTileRows, 128);
       const uint32_t ring = smem_u32(smem);
       uint32_t par_a = 0;
-      int64_t gblk = 0;                               // blocks consumed so far (ring position)
-      auto stage_of = [&](int64_t g) { return (int)(g % n_stages); };
-      auto wait_block = [&](int64_t g) { mbar_wait(&full_bar[stage_of(g)], (uint32_t)((g / n_stages) & 1)); tc_fence_after(); };
+      uint32_t gblk = 0;                              // blocks consumed so far (ring position)
+      const FastDiv ring_div(n_stages);
+      auto stage_of = [&](uint32_t g) { return (int)ring_div.mod(g); };
+      auto wait_block = [&](uint32_t g) { const uint32_t lap = ring_div.div(g); mbar_wait(&full_bar[g - lap * ring_div.n], lap & 1u); tc_fence_after(); };
       for (int lt = 0; lt < my_tiles; ++lt) {
         mbar_wait(&z_full, (uint32_t)(lt & 1));
         tc_fence_after();
@@ -574,6 +645,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_ADD(1, tw);
           BFVI_DBG_T(ti);
           if (elect_one()) {
+            if (!(p.abl & kAblMma1))
             mma_split(tbu, kFB + (c & 1) * 128, kFZ, ring + stage_of(gblk + 2 * c) * kBlockBytes, kTileBytes, true, idesc128);
             umma_commit(&d_full[c & 1]);
             umma_commit(&empty_bar[stage_of(gblk + 2 * c)]);
@@ -598,8 +670,10 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_T(ti);
           const uint32_t blk = ring + stage_of(gblk + 2 * c + 1) * kBlockBytes;
           if (elect_one()) {
+            if (!(p.abl & kAblMma2)) {
             mma_split(tbu, kFG, kFB + b * 128, blk, 8192, c == 0, idesc64);
             mma_split(tbu, kFNL, kFB + b * 128 + 64, blk + kTileBytes, 8192, c == 0, idesc64);
+            }
             umma_commit(&empty_bar[stage_of(gblk + 2 * c + 1)]);
           }
           __syncwarp();
@@ -607,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         }
         if (elect_one()) umma_commit(&units_done);
         __syncwarp();
-        const int64_t gt = gblk + U2;
+        const uint32_t gt = gblk + (uint32_t)U2;
         wait_block(gt);
         const uint32_t blk = ring + stage_of(gt) * kBlockBytes;
         if (elect_one()) mma_split(tbu, kFLIN, kFZ, blk, 8192, true, idesc64);
@@ -629,12 +703,15 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
   } else {
     // ================= weight loader =================
     if (lane == 0) {
-      const int64_t total = (int64_t)my_tiles * n_blocks;
-      for (int64_t g = 0; g < total; ++g) {
-        const int s = (int)(g % n_stages);
-        if (g >= n_stages) mbar_wait(&empty_bar[s], (uint32_t)(((g / n_stages) - 1) & 1));
+      const uint32_t total = (uint32_t)my_tiles * (uint32_t)n_blocks;
+      int s = 0, blk = 0;                             // ring stage / block of the pack, advanced with the counter
+      uint32_t lap = 0;
+      for (uint32_t g = 0; g < total; ++g, s = (s + 1 == n_stages ? 0 : s + 1), blk = (blk + 1 == n_blocks ? 0 : blk + 1)) {
+        if (g > 0 && s == 0) ++lap;
+        if (g >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
+        if ((p.abl & kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
         mbar_expect_tx(&full_bar[s], kBlockBytes);
-        bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)(g % n_blocks) * kBlockBytes, kBlockBytes, &full_bar[s]);
+        bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)blk * kBlockBytes, kBlockBytes, &full_bar[s]);
       }
     }
     __syncwarp();
@@ -653,11 +730,12 @@ struct BwdParams {
                                                               // std path included) / linear heads
   const uint32_t* relu_bits;     // [row tile][unit][half][128 rows] from the KEEP forward
   float* dz;                     // (R, 64) out
-  __half* dh16;                  // masked hidden gradients, FP16 tiles [row group][2U atoms]
+  __half* dh16;                  // masked hidden gradients, FP16 tiles [atom pair][row group][2 atoms]
   __half* dg16; __half* dnl16;   // FP16 tiles of d_g / d_nl [row group][1 atom]
   int64_t R;
   int H;
   int n_stages;
+  int abl;                       // development: ablation mask, 0 in the product
 };
 constexpr uint32_t kBDG = 0, kBDNL = 64, kBDZ = 128, kBHB = 192;        // 4 hidden buffers + d_lin buffer (index 4)
 
@@ -702,6 +780,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);
     unsigned char* pp = patches + q * kPatchBytes;
     const bool elected = hf == 0 && lane == 0;
+    const bool lsu = (p.abl & kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;
     int hp = 0, fs = 0;
     float rg[32], rn[32];                             // next tile's d_g / d_nl half rows (prefetched during the units)
@@ -719,9 +798,11 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       const int64_t row0 = tile * kTileRows + q * 32;
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
       {
-        if (elected) bulk_wait_read<0>();             // dz of the previous tile used the whole patch
-        store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 1, 0, rg);
-        store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 1, 0, rn);
+        patch_switch(q, elected, lsu);                // dz of the previous tile used the whole patch
+        if (!(p.abl & kAblTile16)) {
+          store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu);
+          store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 2 * n_tiles, 1, 0, rn, lsu);
+        }
 #pragma unroll
         for (int j = 0; j < 32; ++j) { rg[j] = rn_tf32(rg[j]); rn[j] = rn_tf32(rn[j]); }
         tmem_st32(tl + kBDG, rg);
@@ -741,10 +822,15 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
           load_row32(p.d_nl + nrow * kZ + hf * 32, nrow < p.R, rn);
         }
       }
+      // ReLU bits of unit u + 1 are fetched while unit u is processed (a load issued at the top of its own iteration
+      // was exposed whenever the hidden gradients were already waiting: ~4 000 cycles per tile)
+      const uint32_t* bits_p = p.relu_bits + (tile * U2 * 2 + hf) * kTileRows + q * 32 + lane;
+      uint32_t bits_next = (p.abl & kAblBits) ? 0xffffffffu : __ldg(bits_p);
 #pragma unroll 1
       for (int u = 0; u < U2; ++u) {
         const int hb = u & 3;
-        const uint32_t bits = __ldg(p.relu_bits + ((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane);
+        const uint32_t bits = bits_next;
+        if (u + 1 < U2 && !(p.abl & kAblBits)) bits_next = __ldg(bits_p + (size_t)(u + 1) * 2 * kTileRows);
         mbar_wait(&d_full[hb], (par_d >> hb) & 1u);
         par_d ^= 1u << hb;
         tc_fence_after();
@@ -752,7 +838,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tmem_ld32(tl + kBHB + hb * 64, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-        store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, U2, u, v);
+        if (!(p.abl & kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, 2 * n_tiles, U2, u, v, lsu);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
         tmem_st32(tl + kBHB + hb * 64, v);
@@ -769,8 +855,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dz_empty);
-        if (elected) bulk_wait_read<0>();             // FP16 tile slots and fp32 row slots share the patch
-        store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v);
+        patch_switch(q, elected, lsu);                // FP16 tile slots and fp32 row slots share the patch
+        if (!(p.abl & kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v, lsu);
       }
       par_misc ^= 1u;
     }
@@ -782,9 +868,10 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       const uint32_t idesc = umma_idesc_tf32(kTileRows, 64);
       const uint32_t ring = smem_u32(smem);
       uint32_t par_a = 0;
-      int64_t gblk = 0;
-      auto stage_of = [&](int64_t g) { return (int)(g % n_stages); };
-      auto wait_block = [&](int64_t g) { mbar_wait(&full_bar[stage_of(g)], (uint32_t)((g / n_stages) & 1)); tc_fence_after(); };
+      uint32_t gblk = 0;
+      const FastDiv ring_div(n_stages);
+      auto stage_of = [&](uint32_t g) { return (int)ring_div.mod(g); };
+      auto wait_block = [&](uint32_t g) { const uint32_t lap = ring_div.div(g); mbar_wait(&full_bar[g - lap * ring_div.n], lap & 1u); tc_fence_after(); };
       for (int lt = 0; lt < my_tiles; ++lt) {
         mbar_wait(&in_full, (uint32_t)(lt & 1));
         tc_fence_after();
@@ -800,6 +887,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         auto issue1 = [&](int u) {                    // hidden gradients of unit u: d_head W2u
           wait_block(gblk + 1 + u);
           if (elect_one()) {
+            if (!(p.abl & kAblMma1))
             mma8_tf32(tbu, kBHB + (u & 3) * 64, u < U ? kBDG : kBDNL, ring + stage_of(gblk + 1 + u) * kBlockBytes, true, idesc);
             umma_commit(&d_full[u & 3]);
           }
@@ -814,6 +902,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
           par_a ^= 1u << hb;
           tc_fence_after();
           if (elect_one()) {
+            if (!(p.abl & kAblMma2))
             mma8_tf32(tbu, kBDZ, kBHB + hb * 64, ring + stage_of(gblk + 1 + u) * kBlockBytes + kTileBytes, false, idesc);
             umma_commit(&empty_bar[stage_of(gblk + 1 + u)]);
           }
@@ -827,12 +916,15 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
     __syncwarp();
   } else {
     if (lane == 0) {
-      const int64_t total = (int64_t)my_tiles * n_blocks;
-      for (int64_t g = 0; g < total; ++g) {
-        const int s = (int)(g % n_stages);
-        if (g >= n_stages) mbar_wait(&empty_bar[s], (uint32_t)(((g / n_stages) - 1) & 1));
+      const uint32_t total = (uint32_t)my_tiles * (uint32_t)n_blocks;
+      int s = 0, blk = 0;                             // ring stage / block of the pack, advanced with the counter
+      uint32_t lap = 0;
+      for (uint32_t g = 0; g < total; ++g, s = (s + 1 == n_stages ? 0 : s + 1), blk = (blk + 1 == n_blocks ? 0 : blk + 1)) {
+        if (g > 0 && s == 0) ++lap;
+        if (g >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
+        if ((p.abl & kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
         mbar_expect_tx(&full_bar[s], kBlockBytes);
-        bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)(g % n_blocks) * kBlockBytes, kBlockBytes, &full_bar[s]);
+        bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)blk * kBlockBytes, kBlockBytes, &full_bar[s]);
       }
     }
     __syncwarp();
@@ -846,7 +938,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
 // weight gradients of the four H-wide layers from the FP16 operand tiles
 // ---------------------------------------------------------------------------------------------------------
 // out^T[h, zc] += sum_rows X[row, h] * Y[row, zc].  X: FP16 tiles [row group][n_atoms_x atoms], the problem uses atoms
-// atom0 .. (H/64 of them); Y: FP16 tiles [row group][1 atom].  out is either (H, Z) row-major (dW of a z -> hidden
+// atom0 .. (H/64 of them; [atom pair][row group][2 atoms], n_groups = the launch's); Y: FP16 tiles [row group][1 atom].  out is either (H, Z) row-major (dW of a z -> hidden
 // layer: direct) or (Z, H) row-major (dW of a hidden -> head layer: transposed add).  bias (nullable): (H) += column
 // sums of X (the bias gradient of a z -> hidden layer whose X is the hidden gradient).
 struct Wgrad16Problem {
@@ -863,6 +955,7 @@ struct Wgrad16Params {
   int groups_per_slice;        // K split: a work item contracts this many row groups
   int n_slices;
   int n_stages;
+  int abl;                     // development: ablation mask, 0 in the product
 };
 constexpr int kWgStageBytes = 3 * kAtomBytes;        // X atoms (2) + Y atom
 constexpr int kWgThreads = 6 * 32;                   // 4 epilogue / column-sum warps, MMA warp, loader warp
@@ -941,7 +1034,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
-      if (g1 > g0) {
+      if (g1 > g0 && !(p.abl & kAblRows)) {
         if (pr.transposed) {                         // out (Z, H): lanes = consecutive h -> coalesced per column
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)j * p.H + h, v0[j]);
@@ -961,7 +1054,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
       const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
       const uint32_t idesc64 = umma_idesc_f16_mn(128, 64), idesc80 = umma_idesc_f16_mn(128, 80);
       const uint32_t ring = smem_u32(smem), ones_addr = smem_u32(ones);
-      int64_t gpos = 0;
+      int s = 0;                                      // ring stage and lap parity, advanced with the position
+      uint32_t lap = 0;
       for (int li = 0; li < my_items; ++li) {
         int pi, mt; int64_t g0, g1;
         item_of(li, pi, mt, g0, g1);
@@ -969,13 +1063,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
         const uint32_t idesc = with_bias ? idesc80 : idesc64;
         mbar_wait(&acc_empty, (uint32_t)((li & 1) ^ 1));
         tc_fence_after();
-        for (int64_t g = g0; g < g1; ++g, ++gpos) {
-          const int s = (int)(gpos % n_stages);
-          mbar_wait(&full_bar[s], (uint32_t)((gpos / n_stages) & 1));
+        for (int64_t g = g0; g < g1; ++g) {
+          mbar_wait(&full_bar[s], lap & 1u);
           tc_fence_after();
           const uint32_t xa = ring + s * kWgStageBytes, ya = xa + 2 * kAtomBytes;
           const uint32_t y_lbo = with_bias ? ones_addr - ya : (uint32_t)kAtomBytes;
           if (elect_one()) {
+            if (!(p.abl & kAblMma1))
 #pragma unroll
             for (int k = 0; k < 4; ++k)               // 16 rows (two 8-row K groups = 2 KB) per instruction
               umma_f16_ss(tbu, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, y_lbo, 1024),
@@ -983,6 +1077,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
             umma_commit(&empty_bar[s]);
           }
           __syncwarp();
+          if (++s == n_stages) { s = 0; ++lap; }
         }
         if (elect_one()) umma_commit(&acc_full);
         __syncwarp();
@@ -991,21 +1086,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
     __syncwarp();
   } else {
     if (lane == 0) {
-      int64_t gpos = 0;
+      int s = 0;
+      uint32_t lap = 0, gpos = 0;
       for (int li = 0; li < my_items; ++li) {
         int pi, mt; int64_t g0, g1;
         item_of(li, pi, mt, g0, g1);
         const Wgrad16Problem& pr = p.pr[pi];
-        for (int64_t g = g0; g < g1; ++g, ++gpos) {
-          const int s = (int)(gpos % n_stages);
-          if (gpos >= n_stages) mbar_wait(&empty_bar[s], (uint32_t)(((gpos / n_stages) - 1) & 1));
-          unsigned char* dst = smem + (size_t)s * kWgStageBytes;
-          const unsigned char* xs = reinterpret_cast<const unsigned char*>(pr.X) +
-                                    ((size_t)g * pr.n_atoms_x + pr.atom0 + mt * 2) * kAtomBytes;
-          mbar_expect_tx(&full_bar[s], kWgStageBytes);
-          bulk_g2s(dst, xs, 2 * kAtomBytes, &full_bar[s]);                   // two adjacent 64-column atoms
-          bulk_g2s(dst + 2 * kAtomBytes, reinterpret_cast<const unsigned char*>(pr.Y) + (size_t)g * kAtomBytes, kAtomBytes,
-                   &full_bar[s]);
+        const unsigned char* xs = reinterpret_cast<const unsigned char*>(pr.X) +
+                                  ((size_t)((pr.atom0 >> 1) + mt) * (size_t)p.n_groups + (size_t)g0) * 2 * kAtomBytes;
+        const unsigned char* ys = reinterpret_cast<const unsigned char*>(pr.Y) + (size_t)g0 * kAtomBytes;
+        for (int64_t g = g0; g < g1; ++g, ++gpos, xs += 2 * kAtomBytes, ys += kAtomBytes) {
+          if (gpos >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
+          if (!((p.abl & kAblRing) && gpos >= (uint32_t)n_stages)) {
+            unsigned char* dst = smem + (size_t)s * kWgStageBytes;
+            mbar_expect_tx(&full_bar[s], kWgStageBytes);
+            bulk_g2s(dst, xs, 2 * kAtomBytes, &full_bar[s]);                 // two adjacent 64-column atoms
+            bulk_g2s(dst + 2 * kAtomBytes, ys, kAtomBytes, &full_bar[s]);
+          } else {
+            mbar_arrive(&full_bar[s]);
+          }
+          if (++s == n_stages) { s = 0; ++lap; }
         }
       }
     }

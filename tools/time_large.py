@@ -28,6 +28,9 @@ def main():
     ap.add_argument('--graph', action='store_true', help='capture the step in a CUDA graph and time replays')
     ap.add_argument('--precision', type=int, default=2, help='0 tf32x3 launch sequence, 1 tf32, 2 fused on-chip kernels')
     ap.add_argument('--batch-tile', type=int, default=0)
+    ap.add_argument('--f-mult', type=float, default=0.5, help='0 skips pass A (the f_mode filter)')
+    ap.add_argument('--s-mult', type=float, default=0.5, help='0 skips passes B and C (the s_mode smoother)')
+    ap.add_argument('--match-mult', type=float, default=0.01)
     a = ap.parse_args()
     lib = _lib.load()
     mods, dims = ['m%d' % i for i in range(a.M)], [16] * a.M
@@ -39,7 +42,8 @@ def main():
               state_dict=bo.init_params(mods, dims, h_dim=a.H, z_dim=a.Z, seed=1))
     model, dists = helpers.fixture_model(fx)
     flat, lay = helpers.pack_params(lib, model, mods, dists, fx['state_dict'], 'cuda')
-    args, keep = helpers.step_args(fx, 'cuda', None, seed=2024, kwargs={'precision': a.precision, 'batch_tile': a.batch_tile})
+    args, keep = helpers.step_args(fx, 'cuda', None, seed=2024, kwargs={'precision': a.precision, 'batch_tile': a.batch_tile, 'f_mult': a.f_mult,
+                                                                    's_mult': a.s_mult, 'match_mult': a.match_mult})
     nbytes = C.c_size_t(0)
     lib.call('bfvi_step_workspace', C.byref(model), C.byref(args), C.byref(nbytes))
     ws = helpers.aligned_empty(nbytes.value, 'cuda')
