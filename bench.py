@@ -447,11 +447,11 @@ def main():
         # perfect TF32 step reads 0.5)
         peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
         ach = wl.flops_per_seq_ts * b_dim * t_max / (ms * 1e-3) / 1e12
-        traffic = None
-        try:
+        traffic = traffic_src = None
+        try:                                         # committed ncu --set full capture of the dominant kernel
             prof = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dominant_kernel.json')))
-            traffic = prof.get('dram_bytes_per_launch')
-            kernel_probe = prof
+            traffic = (prof['dram_bytes_read'] + prof['dram_bytes_write']) / float(prof['rows'])   # per latent row
+            traffic_src = prof['source']
         except Exception:
             pass
         step_roofline = {'bound': 'tensor', 'kernel': 'whole step', 'achieved': ach, 'peak': peak, 'unit': 'TFLOP/s',
@@ -469,7 +469,8 @@ def main():
         roofline = {'bound': 'tensor', 'kernel': 'gtf_fwd_kernel<keep> (fused transition forward, the largest share of the '
                                                  'step; one launch = one particle-pass time step of a batch tile)',
                     'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s', 'frac': dom['frac'],
-                    'traffic': traffic, 'algorithmic_flops_per_launch': dom['flops'], 'rows_per_launch': rows,
+                    'traffic': None if traffic is None else traffic * rows, 'traffic_source': traffic_src,
+                    'algorithmic_flops_per_launch': dom['flops'], 'rows_per_launch': rows,
                     'ms_per_launch': dom['ms'], 'peak_source': dom['peak_source'], 'whole_step': step_roofline}
     if rank == 0 and not large:
         roofline, roofline_fp32, phases = small_roofline(model, wl, inputs_d, targets_d, mask_d, rec, b_dim, t_max,

@@ -775,21 +775,21 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   static const bool dbg = [] { const char* e = getenv("BFVI_FUSED_DBG"); return e && atoi(e) != 0; }();
   long long* dbg_dev = nullptr;
-  if (dbg) { cudaMalloc(&dbg_dev, 16 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 16 * sizeof(long long), st); fp.dbg = dbg_dev; }
+  if (dbg) { cudaMalloc(&dbg_dev, 32 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 32 * sizeof(long long), st); fp.dbg = dbg_dev; }
   auto k = keep ? bfvi::fused::gtf_fwd_kernel<true> : bfvi::fused::gtf_fwd_kernel<false>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
   note_dispatch("gtf_fwd_fused%s f16x3 stages=%d", keep ? "<keep>" : "", fp.n_stages);
   if (dbg) {                           // development: where do the cycles of CTA 0 go?
     cudaStreamSynchronize(st);
-    long long h[16];
+    long long h[32];
     cudaMemcpy(h, dbg_dev, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(dbg_dev);
     const double tpc = (double)((tiles + grid - 1) / grid), pairs = tpc * (H / 64);
-    fprintf(stderr, "[fused fwd dbg] rows %lld tiles/CTA %.0f | row warp 0 per PAIR: wait_d %.0f ld %.0f math %.0f st+arrive %.0f | tail+heads per tile %.0f (wait units_done %.0f, wait heads_full %.0f) | total %.0f per tile\n"
+    fprintf(stderr, "[fused fwd dbg] rows %lld tiles/CTA %.0f | row warp 0 per PAIR: wait_d %.0f ld %.0f math %.0f st+arrive %.0f | tail+heads per tile %.0f (wait units_done %.0f, std-head operand %.0f, nl rows %.0f, wait heads_full %.0f, next z + heads to registers %.0f, scale + 3 row stores %.0f) | total %.0f per tile\n"
                     "                issuer per PAIR: wait_a %.0f wait_blk %.0f issue %.0f\n",
-            (long long)rows, tpc, h[0] / pairs, h[1] / pairs, h[2] / pairs, h[3] / pairs, h[4] / tpc, h[6] / tpc, h[7] / tpc, h[5] / tpc,
-            h[8] / pairs, h[9] / pairs, h[10] / pairs);
+            (long long)rows, tpc, h[0] / pairs, h[1] / pairs, h[2] / pairs, h[3] / pairs, h[4] / tpc, h[6] / tpc, h[8] / tpc, h[9] / tpc, h[7] / tpc, h[10] / tpc, h[11] / tpc, h[5] / tpc,
+            h[16] / pairs, h[17] / pairs, h[18] / pairs);
   }
   BFVI_CHECK_CUDA();
   return BFVI_OK;

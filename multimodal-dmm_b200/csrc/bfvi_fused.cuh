@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     const bool lsu = (p.abl & kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
     int hp = 0, fs = 0;                               // next FP16 tile slot (4 x 4 KB) / fp32 rows slot (2 x 8 KB) of the patch
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     BFVI_DBG_T(t_begin);
     float zreg[32];
     {
@@ -564,6 +564,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         mbar_wait(&units_done, par_misc & 1u);
         tc_fence_after();
         BFVI_DBG_ADD(6, t4);
+        BFVI_DBG_T(t8);
         float v[32];
         tmem_ld32(tl + kFNL, v);
         const float* bb = bias_s + 2 * H + kZ + hf * 32;
@@ -575,8 +576,11 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tail_a);
+        BFVI_DBG_ADD(8, t8);
+        BFVI_DBG_T(t9);
         if (KEEP) patch_switch(q, elected, lsu);      // FP16 tile slots and fp32 row slots share the patch
         if (!(p.abl & kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v, lsu);
+        BFVI_DBG_ADD(9, t9);
       }
       // ---- heads out.  First hand the tensor pipe its next tile: z of the next tile goes to TMEM (the linear head has
       // consumed the old one) and the three accumulators move to registers, so that the issuer starts the next hidden
@@ -586,6 +590,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         mbar_wait(&heads_full, par_misc & 1u);
         tc_fence_after();
         BFVI_DBG_ADD(7, t5);
+        BFVI_DBG_T(t10);
         if (lt + 1 < my_tiles) {
           store_a_split(tl + kFZ, zreg);
           tmem_wait_st();
@@ -601,6 +606,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&heads_empty);     // every accumulator has been read
+        BFVI_DBG_ADD(10, t10);
+        BFVI_DBG_T(t11);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           vg[j] = fmaf(vg[j], inv_s[2], bb[j]);
@@ -612,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           store_rows_f32(pp, fs, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, vl, lsu);
           store_rows_f32(pp, fs, q, lane, hf, elected, p.as + row0 * kZ, n_valid, va, lsu);
         }
+        BFVI_DBG_ADD(11, t11);
       }
       BFVI_DBG_ADD(4, t4);
       par_misc ^= 1u;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     if (elected) bulk_wait_all();                     // results are in global memory before the kernel ends
     BFVI_DBG_ADD(5, t_begin);
     if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
-      for (int i = 0; i < 8; ++i) p.dbg[i] = dbg_acc[i];
+      for (int i = 0; i < 12; ++i) p.dbg[i] = dbg_acc[i];
   } else if (warp == kRowWarps) {
     // ================= MMA issuer =================
     // The WHOLE warp walks the schedule with warp-uniform values (TMEM base broadcast by a shuffle, ring addresses
@@ -697,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         gblk += n_blocks;
       }
       if (p.dbg && blockIdx.x == 0 && lane == 0)
-        for (int i = 0; i < 8; ++i) p.dbg[8 + i] = dbg_acc[i];
+        for (int i = 0; i < 8; ++i) p.dbg[16 + i] = dbg_acc[i];
     }
     __syncwarp();
   } else {
@@ -798,6 +806,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       const int64_t row0 = tile * kTileRows + q * 32;
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
       {
+        float v[32];                                  // d_lin rows: in flight while the FP16 tiles below are written
+        load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
         patch_switch(q, elected, lsu);                // dz of the previous tile used the whole patch
         if (!(p.abl & kAblTile16)) {
           store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu);
@@ -807,8 +817,6 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         for (int j = 0; j < 32; ++j) { rg[j] = rn_tf32(rg[j]); rn[j] = rn_tf32(rn[j]); }
         tmem_st32(tl + kBDG, rg);
         tmem_st32(tl + kBDNL, rn);
-        float v[32];
-        load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
         tmem_st32(tl + kBHB + 4 * 64, v);
