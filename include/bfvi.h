@@ -392,7 +392,9 @@ typedef struct bfvi_forward_args {
   const float* eps_smt;                /* (T,B,smt_particles,Z) */
   uint64_t seed;
   uint32_t b_offset;
-  int32_t precision;                   /* 0 = error-compensated 3xTF32 (default), 1 = TF32 */
+  int32_t precision;                   /* BFVI_PREC_TF32X3 (0, default), BFVI_PREC_TF32 (1), BFVI_PREC_FUSED (2): the transitions
+                                          run in the fused on-chip kernels (z_dim 64, h_dim a multiple of 128; other shapes
+                                          take the 3xTF32 launch sequence) */
   float* infer_mean; float* infer_std; /* outputs (T,B,Z) */
   float* prior_mean; float* prior_std;
   float* recon_mean[BFVI_MAX_MODS];    /* outputs (T,B,D_m), nullable per modality */

@@ -2788,8 +2788,9 @@ struct ForwardPlan {
   int n_present, k_max, d_max;
   size_t tb, tbz;
   size_t off_obs_mean, off_obs_std, off_obs_mask, off_x0, off_h, off_flt[4], off_samples;
-  size_t off_zrows, off_hrows, off_hrows2, off_g, off_nl, off_lin, off_as;
+  size_t off_zrows, off_hrows, off_hrows2, off_g, off_nl, off_lin, off_as, off_packs;
   size_t total;
+  int fused;
 };
 
 static int plan_forward(const bfvi_model* m, const bfvi_forward_args* a, ForwardPlan* pl) {
@@ -2798,7 +2799,7 @@ static int plan_forward(const bfvi_model* m, const bfvi_forward_args* a, Forward
   if (a->T < 1 || a->B < 1) return fail(BFVI_ERR_ARG, "bad T/B");
   if (a->mode < BFVI_MODE_BFILTER || a->mode > BFVI_MODE_BSMOOTH) return fail(BFVI_ERR_ARG, "bad mode");
   if (a->flt_particles < 1 || a->smt_particles < 1) return fail(BFVI_ERR_ARG, "particle counts must be >= 1");
-  if (a->precision != 0 && a->precision != 1) return fail(BFVI_ERR_ARG, "bad precision");
+  if (a->precision < BFVI_PREC_TF32X3 || a->precision > BFVI_PREC_FUSED) return fail(BFVI_ERR_ARG, "bad precision");
   for (int i = 0; i < m->n_mods; ++i)
     if (m->dists[i] != BFVI_DIST_NORMAL)
       return fail(BFVI_ERR_UNSUPPORTED, "bfvi_forward covers Normal modalities; compose the ops for others");
@@ -2822,12 +2823,20 @@ static int plan_forward(const bfvi_model* m, const bfvi_forward_args* a, Forward
   for (int i = 0; i < 4; ++i) pl->off_flt[i] = carve(sizeof(float) * pl->tbz);
   pl->off_samples = carve(sizeof(float) * pl->tbz);
   pl->off_zrows = carve(sizeof(float) * rows * m->z_dim);
-  pl->off_hrows = carve(sizeof(float) * rows * m->h_dim);
-  pl->off_hrows2 = carve(sizeof(float) * rows * m->h_dim);
+  // BFVI_PREC_FUSED: the transitions run in the fused on-chip kernels (hidden activations never reach HBM); shapes
+  // they do not serve fall back to the 3xTF32 launch sequence (same numerics class)
+  pl->fused = (a->precision == BFVI_PREC_FUSED && fused_supported(m->z_dim, m->h_dim)) ? 1 : 0;
+  pl->off_hrows = carve(pl->fused ? 256 : sizeof(float) * rows * m->h_dim);
+  pl->off_hrows2 = carve(pl->fused ? 256 : sizeof(float) * rows * m->h_dim);
   pl->off_g = carve(sizeof(float) * rows * m->z_dim);
   pl->off_nl = carve(sizeof(float) * rows * m->z_dim);
   pl->off_lin = carve(sizeof(float) * rows * m->z_dim);
   pl->off_as = carve(sizeof(float) * rows * m->z_dim);
+  pl->off_packs = 0;
+  if (pl->fused) {
+    cur = align_up(cur, 1024);
+    pl->off_packs = carve(fused_pack_total(m->h_dim));
+  }
   pl->total = cur;
   return BFVI_OK;
 }
@@ -2852,7 +2861,8 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
   char* ws = (char*)workspace;
   bfvi_layout lay;
   bfvi_param_layout(m, &lay);
-  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, T = a->T, B = a->B, prec = a->precision;
+  const int M = m->n_mods, Z = m->z_dim, H = m->h_dim, T = a->T, B = a->B;
+  const int prec = a->precision == BFVI_PREC_TF32 ? bfvi::tc::PREC_TF32 : bfvi::tc::PREC_TF32X3;
   const int64_t tb = (int64_t)pl.tb;
   float* obs_mean = (float*)(ws + pl.off_obs_mean);
   float* obs_std = (float*)(ws + pl.off_obs_std);
@@ -2891,10 +2901,28 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
   BFVI_CHECK_CUDA();
 
   // ---- one filtering pass: T steps, each = 6 GEMMs over (B*K) rows + one fused kernel ----
+#ifndef BFVI_EMU
+  FusedBufs fb;
+  memset(&fb, 0, sizeof(fb));
+  bool packed[2] = {false, false};
+  if (pl.fused) fused_carve_packs(ws + pl.off_packs, H, &fb);
+#endif
   auto run_pass = [&](bfvi_filter_args& f) -> int {
-    const bfvi_gtf_layout& g = lay.trans[f.direction == BFVI_DIR_BWD ? 1 : 0];
+    const int dir = f.direction == BFVI_DIR_BWD ? 1 : 0;
+    const bfvi_gtf_layout& g = lay.trans[dir];
     const int64_t rows = (int64_t)B * f.n_particles;
+#ifndef BFVI_EMU
+    if (pl.fused && !packed[dir]) {              // weights as shared-memory images, once per direction and call
+      if (int rc = fused_pack(g, params, dir, H, fb, st)) return rc;
+      packed[dir] = true;
+    }
+#endif
     for (int i = 0; i < T; ++i) {
+#ifndef BFVI_EMU
+      if (i > 0 && pl.fused) {                     // ONE launch per transition
+        if (int rc = fused_fwd(fb, dir, H, zrows, rows, gbuf, nlbuf, linbuf, asbuf, false, st)) return rc;
+      } else
+#endif
       if (i > 0) {
         // three grouped, width-homogeneous launches: the two z -> hidden layers; the hidden -> head layers and the
         // linear branch; the std head
@@ -2914,6 +2942,7 @@ int bfvi_forward(const bfvi_model* m, const float* params, const bfvi_forward_ar
       sp.min_std = m->min_std; sp.Z = Z; sp.i = i; sp.R = rows;
       sp.g = gbuf; sp.nl = nlbuf; sp.lin = linbuf; sp.as = asbuf;
       sp.zrows = zrows;
+      sp.swz = pl.fused ? 1 : 0;                   // the fused kernels write their heads in the swz64 layout
       if (step4_ok(sp)) { auto k = bfvi::gen::step4_kernel; BFVI_LAUNCH(k, ew_grid((int64_t)B * (Z / 4), 128), dim3(128), 0, st, sp); }
       else { auto k = bfvi::gen::step_kernel; BFVI_LAUNCH(k, ew_grid((int64_t)B * Z, 128), dim3(128), 0, st, sp); }
     }

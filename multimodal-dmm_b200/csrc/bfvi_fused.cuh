@@ -421,8 +421,17 @@ struct FwdParams {
   long long* dbg;                // development: cycle counters of CTA 0 (BFVI_FUSED_DBG=1), nullable
   int abl;                       // development: ablation mask (BFVI_FUSED_ABL, tools/probe_fused_ablate.py); 0 in the product
 };
+// cycle counters of CTA 0: compiled in only with -DBFVI_FUSED_COUNTERS (python tools/variants.py counters:BFVI_FUSED_COUNTERS;
+// BFVI_LIB_PATH=tools/_variants/libbfvi_counters.so BFVI_FUSED_DBG=1 ...): the accumulators cost registers and a spill
+#ifdef BFVI_FUSED_COUNTERS
 #define BFVI_DBG_T(var) const long long var = p.dbg ? clock64() : 0
 #define BFVI_DBG_ADD(i, t0) do { if (p.dbg && blockIdx.x == 0 && lane == 0) dbg_acc[i] += clock64() - (t0); } while (0)
+#define BFVI_DBG_ONLY(...) __VA_ARGS__
+#else
+#define BFVI_DBG_T(var) do { } while (0)
+#define BFVI_DBG_ADD(i, t0) do { } while (0)
+#define BFVI_DBG_ONLY(...)
+#endif
 
 // TMEM columns of the forward kernel: z (A operand), gate / nonlinear head accumulators, two 128-column pair buffers
 // (hidden pre-activations, rewritten in place as A operands), the linear head accumulator.  The tail reuses buffer 0
@@ -471,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     const bool lsu = (p.abl & kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
     int hp = 0, fs = 0;                               // next FP16 tile slot (4 x 4 KB) / fp32 rows slot (2 x 8 KB) of the patch
-    long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    BFVI_DBG_ONLY(long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};)
     BFVI_DBG_T(t_begin);
     float zreg[32];
     {
@@ -626,8 +635,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     }
     if (elected) bulk_wait_all();                     // results are in global memory before the kernel ends
     BFVI_DBG_ADD(5, t_begin);
-    if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
-      for (int i = 0; i < 12; ++i) p.dbg[i] = dbg_acc[i];
+    BFVI_DBG_ONLY(if (p.dbg && blockIdx.x == 0 && warp == 0 && lane == 0)
+      for (int i = 0; i < 12; ++i) p.dbg[i] = dbg_acc[i];)
   } else if (warp == kRowWarps) {
     // ================= MMA issuer =================
     // The WHOLE warp walks the schedule with warp-uniform values (TMEM base broadcast by a shuffle, ring addresses
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     // the tcgen05 operands uniform and wraps every instruction in an ELECT / R2UR.BROADCAST waterfall loop (measured:
     // 81 cycles per MMA issued instead of the tensor pipe's 52-67).
     {
-      long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      BFVI_DBG_ONLY(long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};)
       const uint32_t tbu = __shfl_sync(0xffffffffu, tb, 0);
       const uint32_t idesc64 = umma_idesc_f16_k(kTileRows, 64), idesc128 = umma_idesc_f16_k(kTileRows, 128);
       const uint32_t ring = smem_u32(smem);
@@ -704,8 +713,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         __syncwarp();
         gblk += n_blocks;
       }
-      if (p.dbg && blockIdx.x == 0 && lane == 0)
-        for (int i = 0; i < 8; ++i) p.dbg[16 + i] = dbg_acc[i];
+      BFVI_DBG_ONLY(if (p.dbg && blockIdx.x == 0 && lane == 0)
+        for (int i = 0; i < 8; ++i) p.dbg[16 + i] = dbg_acc[i];)
     }
     __syncwarp();
   } else {

@@ -553,7 +553,7 @@ class MultiDMM(MultiDGTS):
         if self._family == 2 and all_default and not needs_graph:
             # inference fast path: ONE C call, every Linear layer a tcgen05 GEMM
             return self._forward_large(inputs, t_max, b_dim, mode, sample, sample_init, flt_particles,
-                                       smt_particles, eps_flt, eps_smt, kwargs.get('precision', 'tf32x3'))
+                                       smt_particles, eps_flt, eps_smt, kwargs.get('precision', self.precision))
         # composed, differentiable path: encode -> z_filter (fused temporal core) -> decode
 
         obs_mean, obs_std, obs_mask = self.encode(inputs)
@@ -603,7 +603,7 @@ class MultiDMM(MultiDGTS):
                 keep.append(t)
                 setattr(a, field, t.data_ptr())
         a.seed, a.b_offset = self._next_seed(), int(getattr(self, 'b_offset', 0))
-        a.precision = {'tf32x3': 0, 'tf32': 1}[precision]
+        a.precision = _lib.PRECISION_CODES[precision]
         outs = [torch.empty(t_max, b_dim, self.z_dim, device=dev) for _ in range(4)]
         a.infer_mean, a.infer_std, a.prior_mean, a.prior_std = [t.data_ptr() for t in outs]
         recon = {}

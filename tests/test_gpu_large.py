@@ -39,6 +39,21 @@ def test_forward_3xtf32_matches_oracle(name, mode, sample, k_flt):
     assert not bad, bad
 
 
+@pytest.mark.parametrize('mode,sample,k_flt', [('bfilter', False, 1), ('ffilter', True, 1), ('fsmooth', True, 5),
+                                               ('bsmooth', True, 1), ('fsmooth', False, 25)])
+def test_forward_fused_matches_oracle(mode, sample, k_flt):
+    """bfvi_forward with the transitions in the fused on-chip kernels (precision 2: what inference at C3 dims runs by
+    default): same tolerance as the 3xTF32 launch sequence."""
+    lib = _lib.load()
+    fx = helpers.large_case(**CASES['c3_dims'])
+    eps_flt, eps_smt = noise(fx, k_flt, 7)
+    ours = helpers.run_forward_large(lib, fx, 'cuda', mode, sample, k_flt, eps_flt, eps_smt, precision=2)
+    assert 'gtf_fwd_fused' in ';'.join(lib.last_dispatch())
+    ref = helpers.oracle_forward(fx, mode, sample, k_flt, eps_flt, eps_smt, dtype=torch.float64)
+    bad = helpers.compare_forward(ours, ref, rtol=5e-4, atol=5e-5)
+    assert not bad, bad
+
+
 @pytest.mark.parametrize('name', ['default32', 'c3_dims'])
 def test_forward_tf32_fast_mode(name):
     lib = _lib.load()
