@@ -67,6 +67,13 @@ constexpr int kAtomBytes = 8192;       // 64 rows x 64 halves, MN-major SWIZZLE_
 constexpr int kPatchBytes = 16384;
 // development ablations (timing only, results are garbage): skip FP16 tile stores / fp32 row stores / ReLU bits /
 // second-level MMAs (heads, dz) / first-level MMAs (hidden) / row-warp arithmetic
+// (masks are compiled in only with -DBFVI_FUSED_ABLATE: python tools/variants.py ablate:BFVI_FUSED_ABLATE, then
+// BFVI_LIB_PATH=tools/_variants/libbfvi_ablate.so python tools/probe_fused_ablate.py; the product build tests nothing)
+#ifdef BFVI_FUSED_ABLATE
+#define BFVI_ABL(f) (p.abl & (f))
+#else
+#define BFVI_ABL(f) 0
+#endif
 constexpr int kAblTile16 = 1, kAblRows = 2, kAblBits = 4, kAblMma2 = 8, kAblMma1 = 16, kAblMath = 32;
 // kStoreLsu (64, a real variant, results valid): results leave through coalesced st.global by the pair's 64 threads instead
 // of cp.async.bulk (whose requests queue behind the weight ring's bulk loads in the SM's one copy engine)
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);   // my lane group, my column half
     unsigned char* pp = patches + q * kPatchBytes;    // the quadrant's pair patch
     const bool elected = hf == 0 && lane == 0;
-    const bool lsu = (p.abl & kStoreLsu) != 0;
+    const bool lsu = BFVI_ABL(kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;                 // phase bits: d_full[i] in bit i; misc flips once per tile
     int hp = 0, fs = 0;                               // next FP16 tile slot (4 x 4 KB) / fp32 rows slot (2 x 8 KB) of the patch
     BFVI_DBG_ONLY(long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};)
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       // (all MMAs of the previous tile are complete: this warp has passed heads_full of that tile)
       const int64_t row0 = tile * kTileRows + q * 32;
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
-      if (KEEP && !(p.abl & kAblTile16)) {
+      if (KEEP && !BFVI_ABL(kAblTile16)) {
         patch_switch(q, elected, lsu);                // the fp32 rows of the previous tile used the same shared memory
         store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 2 * n_tiles, 1, 0, zreg, lsu);
       }
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_T(t2);
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + br * H + c * kHU + hf * 32);
           const float sc = inv_s[br];
-          if (!(p.abl & kAblMath))
+          if (!BFVI_ABL(kAblMath))
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 bb = b4[cc];
@@ -543,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
             uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-            if (!(p.abl & kAblBits)) p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
+            if (!BFVI_ABL(kAblBits)) p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
             // rows past the end contribute nothing to the weight gradients (their A operand is irrelevant: no output
             // row is stored for them).  Only the last tile has such rows: a warp-uniform test skips the 32 selects
             // elsewhere (and lets the FP16 conversions of the tile store and of the A operand share their work); the
@@ -552,11 +559,11 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
             }
-            if (!(p.abl & kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, 2 * n_tiles, U2, u, v, lsu);
+            if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, 2 * n_tiles, U2, u, v, lsu);
           }
           BFVI_DBG_ADD(2, t2);
           BFVI_DBG_T(t3);
-          if (p.abl & kAblMath) tmem_st32(tl + kFB + b * 128 + br * 64, v); else
+          if (BFVI_ABL(kAblMath)) tmem_st32(tl + kFB + b * 128 + br * 64, v); else
           store_a_split(tl + kFB + b * 128 + br * 64, v);
           BFVI_DBG_ADD(3, t3);
         }
@@ -588,7 +595,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
         BFVI_DBG_ADD(8, t8);
         BFVI_DBG_T(t9);
         if (KEEP) patch_switch(q, elected, lsu);      // FP16 tile slots and fp32 row slots share the patch
-        if (!(p.abl & kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v, lsu);
+        if (!BFVI_ABL(kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.nl + row0 * kZ, n_valid, v, lsu);
         BFVI_DBG_ADD(9, t9);
       }
       // ---- heads out.  First hand the tensor pipe its next tile: z of the next tile goes to TMEM (the linear head has
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           vl[j] = fmaf(vl[j], inv_s[4], bb[2 * kZ + j]);
           va[j] = fmaf(va[j], inv_s[5], bb[3 * kZ + j]);
         }
-        if (!(p.abl & kAblRows)) {
+        if (!BFVI_ABL(kAblRows)) {
           store_rows_f32(pp, fs, q, lane, hf, elected, p.g + row0 * kZ, n_valid, vg, lsu);
           store_rows_f32(pp, fs, q, lane, hf, elected, p.lin + row0 * kZ, n_valid, vl, lsu);
           store_rows_f32(pp, fs, q, lane, hf, elected, p.as + row0 * kZ, n_valid, va, lsu);
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_ADD(1, tw);
           BFVI_DBG_T(ti);
           if (elect_one()) {
-            if (!(p.abl & kAblMma1))
+            if (!BFVI_ABL(kAblMma1))
             mma_split(tbu, kFB + (c & 1) * 128, kFZ, ring + stage_of(gblk + 2 * c) * kBlockBytes, kTileBytes, true, idesc128);
             umma_commit(&d_full[c & 1]);
             umma_commit(&empty_bar[stage_of(gblk + 2 * c)]);
@@ -687,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
           BFVI_DBG_T(ti);
           const uint32_t blk = ring + stage_of(gblk + 2 * c + 1) * kBlockBytes;
           if (elect_one()) {
-            if (!(p.abl & kAblMma2)) {
+            if (!BFVI_ABL(kAblMma2)) {
             mma_split(tbu, kFG, kFB + b * 128, blk, 8192, c == 0, idesc64);
             mma_split(tbu, kFNL, kFB + b * 128 + 64, blk + kTileBytes, 8192, c == 0, idesc64);
             }
@@ -726,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       for (uint32_t g = 0; g < total; ++g, s = (s + 1 == n_stages ? 0 : s + 1), blk = (blk + 1 == n_blocks ? 0 : blk + 1)) {
         if (g > 0 && s == 0) ++lap;
         if (g >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
-        if ((p.abl & kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
+        if (BFVI_ABL(kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
         mbar_expect_tx(&full_bar[s], kBlockBytes);
         bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)blk * kBlockBytes, kBlockBytes, &full_bar[s]);
       }
@@ -797,7 +804,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
     const uint32_t tl = tb + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * 32);
     unsigned char* pp = patches + q * kPatchBytes;
     const bool elected = hf == 0 && lane == 0;
-    const bool lsu = (p.abl & kStoreLsu) != 0;
+    const bool lsu = BFVI_ABL(kStoreLsu) != 0;
     uint32_t par_d = 0, par_misc = 0;
     int hp = 0, fs = 0;
     float rg[32], rn[32];                             // next tile's d_g / d_nl half rows (prefetched during the units)
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         float v[32];                                  // d_lin rows: in flight while the FP16 tiles below are written
         load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
         patch_switch(q, elected, lsu);                // dz of the previous tile used the whole patch
-        if (!(p.abl & kAblTile16)) {
+        if (!BFVI_ABL(kAblTile16)) {
           store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu);
           store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 2 * n_tiles, 1, 0, rn, lsu);
         }
@@ -842,12 +849,12 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       // ReLU bits of unit u + 1 are fetched while unit u is processed (a load issued at the top of its own iteration
       // was exposed whenever the hidden gradients were already waiting: ~4 000 cycles per tile)
       const uint32_t* bits_p = p.relu_bits + (tile * U2 * 2 + hf) * kTileRows + q * 32 + lane;
-      uint32_t bits_next = (p.abl & kAblBits) ? 0xffffffffu : __ldg(bits_p);
+      uint32_t bits_next = BFVI_ABL(kAblBits) ? 0xffffffffu : __ldg(bits_p);
 #pragma unroll 1
       for (int u = 0; u < U2; ++u) {
         const int hb = u & 3;
         const uint32_t bits = bits_next;
-        if (u + 1 < U2 && !(p.abl & kAblBits)) bits_next = __ldg(bits_p + (size_t)(u + 1) * 2 * kTileRows);
+        if (u + 1 < U2 && !BFVI_ABL(kAblBits)) bits_next = __ldg(bits_p + (size_t)(u + 1) * 2 * kTileRows);
         mbar_wait(&d_full[hb], (par_d >> hb) & 1u);
         par_d ^= 1u << hb;
         tc_fence_after();
@@ -855,7 +862,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tmem_ld32(tl + kBHB + hb * 64, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-        if (!(p.abl & kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, 2 * n_tiles, U2, u, v, lsu);
+        if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, 2 * n_tiles, U2, u, v, lsu);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
         tmem_st32(tl + kBHB + hb * 64, v);
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) mbar_arrive(&dz_empty);
         patch_switch(q, elected, lsu);                // FP16 tile slots and fp32 row slots share the patch
-        if (!(p.abl & kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v, lsu);
+        if (!BFVI_ABL(kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v, lsu);
       }
       par_misc ^= 1u;
     }
@@ -904,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         auto issue1 = [&](int u) {                    // hidden gradients of unit u: d_head W2u
           wait_block(gblk + 1 + u);
           if (elect_one()) {
-            if (!(p.abl & kAblMma1))
+            if (!BFVI_ABL(kAblMma1))
             mma8_tf32(tbu, kBHB + (u & 3) * 64, u < U ? kBDG : kBDNL, ring + stage_of(gblk + 1 + u) * kBlockBytes, true, idesc);
             umma_commit(&d_full[u & 3]);
           }
@@ -919,7 +926,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
           par_a ^= 1u << hb;
           tc_fence_after();
           if (elect_one()) {
-            if (!(p.abl & kAblMma2))
+            if (!BFVI_ABL(kAblMma2))
             mma8_tf32(tbu, kBDZ, kBHB + hb * 64, ring + stage_of(gblk + 1 + u) * kBlockBytes + kTileBytes, false, idesc);
             umma_commit(&empty_bar[stage_of(gblk + 1 + u)]);
           }
@@ -939,7 +946,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       for (uint32_t g = 0; g < total; ++g, s = (s + 1 == n_stages ? 0 : s + 1), blk = (blk + 1 == n_blocks ? 0 : blk + 1)) {
         if (g > 0 && s == 0) ++lap;
         if (g >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
-        if ((p.abl & kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
+        if (BFVI_ABL(kAblRing) && g >= n_stages) { mbar_arrive(&full_bar[s]); continue; }
         mbar_expect_tx(&full_bar[s], kBlockBytes);
         bulk_g2s(smem + (size_t)s * kBlockBytes, p.pack + (size_t)blk * kBlockBytes, kBlockBytes, &full_bar[s]);
       }
@@ -1051,7 +1058,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
-      if (g1 > g0 && !(p.abl & kAblRows)) {
+      if (g1 > g0 && !BFVI_ABL(kAblRows)) {
         if (pr.transposed) {                         // out (Z, H): lanes = consecutive h -> coalesced per column
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)j * p.H + h, v0[j]);
@@ -1086,7 +1093,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
           const uint32_t xa = ring + s * kWgStageBytes, ya = xa + 2 * kAtomBytes;
           const uint32_t y_lbo = with_bias ? ones_addr - ya : (uint32_t)kAtomBytes;
           if (elect_one()) {
-            if (!(p.abl & kAblMma1))
+            if (!BFVI_ABL(kAblMma1))
 #pragma unroll
             for (int k = 0; k < 4; ++k)               // 16 rows (two 8-row K groups = 2 KB) per instruction
               umma_f16_ss(tbu, umma_desc_mn128(xa + k * 2048, kAtomBytes, 1024), umma_desc_mn128(ya + k * 2048, y_lbo, 1024),
@@ -1114,7 +1121,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
         const unsigned char* ys = reinterpret_cast<const unsigned char*>(pr.Y) + (size_t)g0 * kAtomBytes;
         for (int64_t g = g0; g < g1; ++g, ++gpos, xs += 2 * kAtomBytes, ys += kAtomBytes) {
           if (gpos >= (uint32_t)n_stages) mbar_wait(&empty_bar[s], (lap - 1u) & 1u);
-          if (!((p.abl & kAblRing) && gpos >= (uint32_t)n_stages)) {
+          if (!(BFVI_ABL(kAblRing) && gpos >= (uint32_t)n_stages)) {
             unsigned char* dst = smem + (size_t)s * kWgStageBytes;
             mbar_expect_tx(&full_bar[s], kWgStageBytes);
             bulk_g2s(dst, xs, 2 * kAtomBytes, &full_bar[s]);                 // two adjacent 64-column atoms

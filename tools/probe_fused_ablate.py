@@ -1,7 +1,11 @@
 """Where do the fused GTF kernels spend their time?  bfvi_gtf_probe (each kernel alone on ROWS latent rows, the
 particle-pass launch of a C3 batch tile) under the development ablation masks of csrc/bfvi_fused.cuh (BFVI_FUSED_ABL:
 1 no FP16 tile stores, 2 no fp32 row stores, 4 no ReLU bits, 8 no second-level MMAs (heads / dz), 16 no first-level
-MMAs (hidden), 32 no row-warp arithmetic).  Ablated results are garbage: timing only."""
+MMAs (hidden), 32 no row-warp arithmetic, 64 row results through st.global, 128 no ring copies).  Ablated results are
+garbage: timing only.  The masks exist only in the ablation build:
+    python tools/variants.py ablate:BFVI_FUSED_ABLATE
+    BFVI_LIB_PATH=$PWD/tools/_variants/libbfvi_ablate.so python tools/probe_fused_ablate.py 0 1 2 4 8 16 32 63 191
+(the product library ignores BFVI_FUSED_ABL: mask 0 there times the shipped kernels)."""
 import ctypes as C
 import os
 import sys
