@@ -454,6 +454,38 @@ int bfvi_gtf_probe(const bfvi_model* model, const float* params, int32_t directi
                    int64_t n_rows, int32_t iters, float* scratch_rows, void* workspace, size_t workspace_bytes,
                    float* ms_per_launch, void* stream);
 
+/* One per-modality encoder / decoder MLP of the composed path at ANY size, weights passed by pointer (the modules that
+ * own them keep the reference's state_dict keys): common.GaussianMLP (models/common.py:25-41), common.CategoricalMLP
+ * (models/common.py:9-23) and the categorical encoder Embedding -> ReLU -> GaussianMLP (models/dmm.py:78-82).  Dense
+ * layers run on the tcgen05 tensor cores (error-compensated 3xTF32, FP32-class), everything between them in fused
+ * elementwise kernels; nothing here calls a library GEMM.
+ *   x        (n_rows, n_in) fp32; with `emb` set: (n_rows) class indices stored as floats (NaN counts as class 0, the
+ *            reference zero-fills before .long(), models/dmm.py:166-167)
+ *   out_a    (n_rows, n_out): mean (BFVI_HEAD_GAUSSIAN) or class probabilities (BFVI_HEAD_SOFTMAX)
+ *   out_b    (n_rows, n_out): std = softplus(.) + min_std (Gaussian head only)
+ *   mask     (n_rows) u8, nullable: 1 where the row has no NaN (written when nan_mask != 0; NaNs are zero-filled)
+ * bfvi_mlp_bwd recomputes the hidden activations from x, takes the forward outputs and their gradients, ACCUMULATES the
+ * parameter gradients (+=) and writes d_x (n_rows, n_in; nullable; unused with `emb`). */
+enum { BFVI_HEAD_GAUSSIAN = 0, BFVI_HEAD_SOFTMAX = 1 };
+typedef struct bfvi_mlp_desc {
+  const float* emb;                     /* nullable: (n_classes, h_dim) embedding table (then n_in == h_dim) */
+  const float* w1; const float* b1;     /* in_to_h.0: (h_dim, n_in), (h_dim) */
+  const float* wa; const float* ba;     /* h_to_mean | h_to_out.0: (n_out, h_dim), (n_out) */
+  const float* wb; const float* bb;     /* h_to_std.0 (Gaussian head); null for the softmax head */
+  int32_t n_in, h_dim, n_out, n_classes;
+  int32_t head;                         /* BFVI_HEAD_* */
+  int32_t nan_mask;                     /* encoders: NaN -> mask + zero fill (models/dmm.py:165-167) */
+  float min_std;                        /* 1e-3 for every GaussianMLP of the reference (models/common.py:27) */
+  int32_t pad_;
+} bfvi_mlp_desc;
+typedef struct bfvi_mlp_grads { float* emb; float* w1; float* b1; float* wa; float* ba; float* wb; float* bb; } bfvi_mlp_grads;
+int bfvi_mlp_workspace(const bfvi_mlp_desc* desc, int64_t n_rows, int32_t backward, size_t* bytes);
+int bfvi_mlp_fwd(const bfvi_mlp_desc* desc, const float* x, int64_t n_rows, float* out_a, float* out_b, uint8_t* mask,
+                 void* workspace, size_t workspace_bytes, void* stream);
+int bfvi_mlp_bwd(const bfvi_mlp_desc* desc, const bfvi_mlp_grads* grads, const float* x, int64_t n_rows, const float* out_a,
+                 const float* out_b, const float* d_out_a, const float* d_out_b, float* d_x, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
 /* The optimiser step either side of the hot path (trainer.py:248-252), fused over the flat
  * buffers: optional clip_grad_norm_ (max_norm > 0; total L2 norm over the whole flat gradient,
  * coefficient max_norm / (norm + 1e-6) clamped to 1) followed by torch.optim.Adam (no amsgrad;

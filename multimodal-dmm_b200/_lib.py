@@ -106,6 +106,20 @@ class ForwardArgs(C.Structure):
                 ('recon_mean', C.c_void_p * MAX_MODS), ('recon_std', C.c_void_p * MAX_MODS)]
 
 
+class MlpDesc(C.Structure):           # bfvi_mlp_desc
+    _fields_ = [('emb', C.c_void_p), ('w1', C.c_void_p), ('b1', C.c_void_p), ('wa', C.c_void_p), ('ba', C.c_void_p),
+                ('wb', C.c_void_p), ('bb', C.c_void_p),
+                ('n_in', C.c_int32), ('h_dim', C.c_int32), ('n_out', C.c_int32), ('n_classes', C.c_int32),
+                ('head', C.c_int32), ('nan_mask', C.c_int32), ('min_std', C.c_float), ('pad_', C.c_int32)]
+
+
+class MlpGrads(C.Structure):          # bfvi_mlp_grads
+    _fields_ = [(k, C.c_void_p) for k in ('emb', 'w1', 'b1', 'wa', 'ba', 'wb', 'bb')]
+
+
+HEAD_GAUSSIAN, HEAD_SOFTMAX = 0, 1
+
+
 class BfviError(RuntimeError):
     pass
 
@@ -175,6 +189,11 @@ SYMBOLS = {
                                    C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_wgrad_tf32': (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                   C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'bfvi_mlp_workspace': (C.c_int, [C.POINTER(MlpDesc), C.c_int64, C.c_int32, C.POINTER(C.c_size_t)]),
+    'bfvi_mlp_fwd': (C.c_int, [C.POINTER(MlpDesc), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    'bfvi_mlp_bwd': (C.c_int, [C.POINTER(MlpDesc), C.POINTER(MlpGrads), C.c_void_p, C.c_int64] + [C.c_void_p] * 5
+                     + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'bfvi_gtf_workspace': (C.c_size_t, [C.POINTER(Model), C.c_int64]),
     'bfvi_gtf_fwd': (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64] + [C.c_void_p] * 4
                      + [C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p]),

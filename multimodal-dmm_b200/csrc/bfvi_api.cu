@@ -2200,6 +2200,205 @@ int bfvi_wgrad_tf32(const float* dy, int64_t lddy, const float* x, int64_t ldx, 
 }
 
 
+// ---- per-modality MLPs of the composed path (any size, weights by pointer): bfvi_mlp_* -----------------------
+namespace {
+struct MlpPlan { size_t x0, x0T, h, hT, da, db, daT, dbT, dh, dhT, w1T, waT, wbT, mask, total; };
+int check_mlp(const bfvi_mlp_desc* d) {
+  if (!d) return fail(BFVI_ERR_ARG, "mlp desc null");
+  if (!d->w1 || !d->b1 || !d->wa || !d->ba) return fail(BFVI_ERR_ARG, "mlp weights null");
+  if (d->n_in < 1 || d->h_dim < 1 || d->n_out < 1) return fail(BFVI_ERR_ARG, "bad mlp dims");
+  if (d->head != BFVI_HEAD_GAUSSIAN && d->head != BFVI_HEAD_SOFTMAX) return fail(BFVI_ERR_ARG, "bad head");
+  if (d->head == BFVI_HEAD_GAUSSIAN && (!d->wb || !d->bb)) return fail(BFVI_ERR_ARG, "Gaussian head needs wb / bb");
+  if (d->emb && (d->n_classes < 1 || d->n_in != d->h_dim)) return fail(BFVI_ERR_ARG, "embedding: n_classes >= 1, n_in == h_dim");
+  return BFVI_OK;
+}
+void plan_mlp(const bfvi_mlp_desc* d, int64_t n, bool backward, MlpPlan* pl) {
+  size_t cur = 0;
+  auto carve = [&](size_t floats) { size_t o = cur; cur = align_up(cur + floats * sizeof(float), 256); return o; };
+  const size_t H = d->h_dim, I = d->n_in, O = d->n_out, R = (size_t)n;
+  memset(pl, 0, sizeof(*pl));
+  pl->x0 = carve(R * I);
+  pl->h = carve(R * H);
+  pl->mask = carve((R + 3) / 4);                     // u8 row mask scratch (the backward's recompute)
+  if (backward) {
+    pl->x0T = carve(R * I); pl->hT = carve(R * H);
+    pl->da = carve(R * O); pl->db = carve(R * O); pl->daT = carve(R * O); pl->dbT = carve(R * O);
+    pl->dh = carve(R * H); pl->dhT = carve(R * H);
+    pl->w1T = carve(H * I); pl->waT = carve(O * H); pl->wbT = carve(O * H);
+  }
+  pl->total = cur;
+}
+// x -> MLP input rows x0 (NaN -> mask + zero fill; Embedding -> ReLU) and hidden activations h (+ transposed copies)
+int mlp_hidden(const bfvi_mlp_desc* d, const float* x, int64_t n, uint8_t* mask, char* ws, const MlpPlan& pl, bool backward,
+               const float** x0_out, cudaStream_t st) {
+  float* x0 = (float*)(ws + pl.x0);
+  const float* in = x;
+  if (mask == nullptr && !d->emb) mask = (uint8_t*)(ws + pl.mask);
+  auto ew = [&](int64_t work) { return dim3((unsigned)grid_for(work, 256, 8)); };
+  if (d->emb) {
+    auto k = bfvi::gen::embed_relu_kernel;
+    BFVI_LAUNCH(k, ew(n * d->h_dim), dim3(256), 0, st, d->emb, x, n, d->h_dim, d->n_classes, x0);
+    if (mask != nullptr && d->nan_mask) {            // a NaN label masks the row (models/dmm.py:165)
+      auto kp = bfvi::gen::prep_rows_kernel;
+      BFVI_LAUNCH(kp, ew(n), dim3(256), 0, st, x, n, 1, (float*)(ws + pl.h), mask);   // zero-filled copy is scratch
+    }
+    in = x0;
+  } else if (d->nan_mask) {
+    auto kp = bfvi::gen::prep_rows_kernel;
+    BFVI_LAUNCH(kp, ew(n), dim3(256), 0, st, x, n, d->n_in, x0, mask);
+    in = x0;
+  }
+  BFVI_CHECK_CUDA();
+  bfvi::tc::GemmParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.A = in; gp.lda = d->n_in; gp.W = d->w1; gp.ldw = d->n_in; gp.bias = d->b1;
+  gp.C = (float*)(ws + pl.h); gp.ldc = d->h_dim; gp.M = n; gp.N = d->h_dim; gp.K = d->n_in; gp.act = bfvi::tc::ACT_RELU;
+  if (backward) { gp.Ct = (float*)(ws + pl.hT); gp.ldct = n; }
+  *x0_out = in;
+  return gemm_tc(gp, bfvi::tc::PREC_TF32X3, st);
+}
+}  // namespace
+
+int bfvi_mlp_workspace(const bfvi_mlp_desc* d, int64_t n_rows, int32_t backward, size_t* bytes) {
+  if (int rc = check_mlp(d)) return rc;
+  if (!bytes || n_rows < 1) return fail(BFVI_ERR_ARG, "null/empty argument");
+  MlpPlan pl;
+  plan_mlp(d, n_rows, backward != 0, &pl);
+  *bytes = pl.total;
+  return BFVI_OK;
+}
+
+int bfvi_mlp_fwd(const bfvi_mlp_desc* d, const float* x, int64_t n_rows, float* out_a, float* out_b, uint8_t* mask,
+                 void* workspace, size_t workspace_bytes, void* stream) {
+  g_dispatch.clear();
+  if (int rc = check_mlp(d)) return rc;
+  if (!x || !out_a || n_rows < 1 || !workspace) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (d->head == BFVI_HEAD_GAUSSIAN && !out_b) return fail(BFVI_ERR_ARG, "out_b null");
+  MlpPlan pl;
+  plan_mlp(d, n_rows, false, &pl);
+  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const float* x0 = nullptr;
+  if (int rc = mlp_hidden(d, x, n_rows, mask, ws, pl, false, &x0, st)) return rc;
+  LinearGroup lg;
+  lg.add((const float*)(ws + pl.h), d->h_dim, d->wa, d->h_dim, d->ba, out_a, d->n_out, n_rows, d->h_dim, d->n_out, 0);
+  if (d->head == BFVI_HEAD_GAUSSIAN)
+    lg.add((const float*)(ws + pl.h), d->h_dim, d->wb, d->h_dim, d->bb, out_b, d->n_out, n_rows, d->h_dim, d->n_out, 0);
+  if (int rc = lg.run(bfvi::tc::PREC_TF32X3, st)) return rc;
+  const int64_t no = n_rows * d->n_out;
+  if (d->head == BFVI_HEAD_GAUSSIAN) {
+    auto ks = bfvi::gen::softplus_kernel;
+    BFVI_LAUNCH(ks, dim3((unsigned)grid_for(no, 256, 8)), dim3(256), 0, st, out_b, no, d->min_std);
+  } else {
+    auto ks = bfvi::gen::softmax_rows_kernel;
+    BFVI_LAUNCH(ks, dim3((unsigned)grid_for(n_rows, 8, 8)), dim3(256), 0, st, out_a, n_rows, d->n_out);
+  }
+  note_dispatch("mlp_fwd %s%s tf32x3", d->emb ? "embed+" : "", d->head == BFVI_HEAD_SOFTMAX ? "softmax" : "gaussian");
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_mlp_bwd(const bfvi_mlp_desc* d, const bfvi_mlp_grads* g, const float* x, int64_t n_rows, const float* out_a,
+                 const float* out_b, const float* d_out_a, const float* d_out_b, float* d_x, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  g_dispatch.clear();
+  if (int rc = check_mlp(d)) return rc;
+  if (!g || !x || !out_a || n_rows < 1 || !workspace) return fail(BFVI_ERR_ARG, "null/empty argument");
+  if (!g->w1 || !g->b1 || !g->wa || !g->ba) return fail(BFVI_ERR_ARG, "gradient slots null");
+  const bool gauss = d->head == BFVI_HEAD_GAUSSIAN;
+  if (gauss && (!out_b || !g->wb || !g->bb)) return fail(BFVI_ERR_ARG, "Gaussian head: out_b / wb / bb slots null");
+  if (!gauss && !d_out_a) return fail(BFVI_ERR_ARG, "d_out_a null");
+  if (d->emb && !g->emb) return fail(BFVI_ERR_ARG, "embedding gradient slot null");
+  MlpPlan pl;
+  plan_mlp(d, n_rows, true, &pl);
+  if (workspace_bytes < pl.total) return fail(BFVI_ERR_WORKSPACE, "workspace %zu < %zu bytes", workspace_bytes, pl.total);
+  if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int H = d->h_dim, I = d->n_in, O = d->n_out;
+  const int64_t n = n_rows;
+  auto F = [&](size_t off) { return (float*)(ws + off); };
+  auto transpose = [&](const float* in, int64_t rows, int cols, float* out) {
+    auto k = bfvi::gen::transpose_kernel;
+    BFVI_LAUNCH(k, dim3((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32)), dim3(256), 0, st, in, rows, cols, out, 0);
+  };
+  // recompute: MLP input rows and hidden activations (+ transposed copies for the weight gradients)
+  const float* x0 = nullptr;
+  if (int rc = mlp_hidden(d, x, n, nullptr, ws, pl, true, &x0, st)) return rc;
+  transpose(x0, n, I, F(pl.x0T));
+  transpose(d->w1, H, I, F(pl.w1T));
+  transpose(d->wa, O, H, F(pl.waT));
+  if (gauss) transpose(d->wb, O, H, F(pl.wbT));
+  // head backward from the forward outputs; bias gradients
+  {
+    auto k = bfvi::gen::mlp_head_bwd_kernel;
+    BFVI_LAUNCH(k, dim3((unsigned)grid_for(n, 8, 8)), dim3(256), 0, st, out_a, out_b, d_out_a, d_out_b, n, O, gauss ? 0 : 1,
+                d->min_std, F(pl.da), F(pl.db));
+    auto kc = bfvi::gen::colsum_kernel;
+    const unsigned gy = (unsigned)(n / 256 + 1 < 64 ? n / 256 + 1 : 64);
+    BFVI_LAUNCH(kc, dim3((unsigned)((O + 127) / 128), gy), dim3(128), 0, st, (const float*)F(pl.da), n, O, g->ba);
+    transpose(F(pl.da), n, O, F(pl.daT));
+    if (gauss) {
+      BFVI_LAUNCH(kc, dim3((unsigned)((O + 127) / 128), gy), dim3(128), 0, st, (const float*)F(pl.db), n, O, g->bb);
+      transpose(F(pl.db), n, O, F(pl.dbT));
+    }
+  }
+  BFVI_CHECK_CUDA();
+  auto wgrad = [&](const float* dyT, const float* xT, int n_out, int n_in, float* dw) {
+    bfvi::tc::GemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    if (wgrad_swapped(n_out, n_in)) {
+      gp.A = xT; gp.lda = n; gp.W = dyT; gp.ldw = n; gp.C = dw; gp.ldc = n_in; gp.M = n_in; gp.N = n_out; gp.K = n;
+      gp.accumulate = 1; gp.trans_out = 1; gp.k_split = wgrad_k_split(n, n_in, n_out);
+    } else {
+      gp.A = dyT; gp.lda = n; gp.W = xT; gp.ldw = n; gp.C = dw; gp.ldc = n_in; gp.M = n_out; gp.N = n_in; gp.K = n;
+      gp.accumulate = 1; gp.k_split = wgrad_k_split(n, n_out, n_in);
+    }
+    return gp;
+  };
+  // level 1: head weight gradients and dh = (d_a Wa) masked by h > 0
+  {
+    bfvi::tc::GemmParams grp[3];
+    int k = 0;
+    grp[k++] = wgrad(F(pl.daT), F(pl.hT), O, H, g->wa);
+    if (gauss) grp[k++] = wgrad(F(pl.dbT), F(pl.hT), O, H, g->wb);
+    if (int rc = gemm_group_tc(grp, k, bfvi::tc::PREC_TF32X3, st)) return rc;
+    bfvi::tc::GemmParams gp;
+    memset(&gp, 0, sizeof(gp));
+    gp.A = F(pl.da); gp.lda = O; gp.W = F(pl.waT); gp.ldw = O; gp.C = F(pl.dh); gp.ldc = H; gp.M = n; gp.N = H; gp.K = O;
+    gp.mask_aux = F(pl.h); gp.ldaux = H;
+    gp.colsum = g->b1;                              // column sums of every (masked) partial: the first-layer bias gradient
+    if (!gauss) { gp.Ct = F(pl.dhT); gp.ldct = n; }
+    if (int rc = gemm_tc(gp, bfvi::tc::PREC_TF32X3, st)) return rc;
+    if (gauss) {                                    // += d_b Wb: complete now, transposed copy for the weight gradient
+      gp.A = F(pl.db); gp.W = F(pl.wbT); gp.accumulate = 1; gp.Ct = F(pl.dhT); gp.ldct = n;
+      if (int rc = gemm_tc(gp, bfvi::tc::PREC_TF32X3, st)) return rc;
+    }
+  }
+  // level 2: first-layer weight gradient, input gradient
+  {
+    bfvi::tc::GemmParams gw = wgrad(F(pl.dhT), F(pl.x0T), H, I, g->w1);
+    if (int rc = gemm_tc(gw, bfvi::tc::PREC_TF32X3, st)) return rc;
+    if (d->emb || d_x) {
+      bfvi::tc::GemmParams gp;
+      memset(&gp, 0, sizeof(gp));
+      float* dx = d->emb ? F(pl.hT) : d_x;          // embedding rows: scratch (hT is spent after the head weight gradients)
+      gp.A = F(pl.dh); gp.lda = H; gp.W = F(pl.w1T); gp.ldw = H; gp.C = dx; gp.ldc = I; gp.M = n; gp.N = I; gp.K = H;
+      if (d->emb) { gp.mask_aux = x0; gp.ldaux = I; }            // ReLU of the embedding rows
+      if (int rc = gemm_tc(gp, bfvi::tc::PREC_TF32X3, st)) return rc;
+      if (d->emb) {
+        auto ke = bfvi::gen::embed_bwd_kernel;
+        BFVI_LAUNCH(ke, dim3((unsigned)grid_for(n * H, 256, 8)), dim3(256), 0, st, (const float*)dx, x, n, H, d->n_classes, g->emb);
+      }
+    }
+  }
+  note_dispatch("mlp_bwd %s%s tf32x3", d->emb ? "embed+" : "", gauss ? "gaussian" : "softmax");
+  BFVI_CHECK_CUDA();
+  return BFVI_OK;
+}
+
 // ---- GaussianGTF on latent rows through the fused on-chip kernels (bfvi_fused.cuh) --------------------------
 namespace {
 #ifndef BFVI_EMU

@@ -633,6 +633,89 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// elementwise pieces of the per-modality MLPs of the composed path (bfvi_mlp_fwd / bfvi_mlp_bwd: GaussianMLP and
+// CategoricalMLP at any size, the categorical encoder's Embedding -> ReLU; models/common.py:9-41, models/dmm.py:78-82)
+// ---------------------------------------------------------------------------------------------------------
+// class index of a row: the reference casts the (NaN-zero-filled) float label with .long() (models/dmm.py:96-98)
+__device__ __forceinline__ int label_of(const float* __restrict__ labels, int64_t r, int n_classes) {
+  const float v = labels[r];
+  int c = (v != v) ? 0 : (int)v;
+  return c < 0 ? 0 : (c >= n_classes ? n_classes - 1 : c);
+}
+// out[r, :] = relu(emb[label[r], :])
+__global__ void __launch_bounds__(256) embed_relu_kernel(const float* __restrict__ emb, const float* __restrict__ labels,
+                                                         int64_t n_rows, int H, int n_classes, float* __restrict__ out) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_rows * H;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / H;
+    const int j = (int)(idx % H);
+    const float v = emb[(int64_t)label_of(labels, r, n_classes) * H + j];
+    out[idx] = v < 0.f ? 0.f : v;
+  }
+}
+// d_emb[label[r], :] += de[r, :]  (de already carries the ReLU mask)
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const float* __restrict__ de, const float* __restrict__ labels,
+                                                        int64_t n_rows, int H, int n_classes, float* __restrict__ d_emb) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_rows * H;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = idx / H;
+    const int j = (int)(idx % H);
+    const float g = de[idx];
+    if (g != 0.f) atomicAdd(d_emb + (int64_t)label_of(labels, r, n_classes) * H + j, g);
+  }
+}
+// softmax over the columns of every row, in place (one warp per row; torch.softmax: max-shifted)
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, int64_t n_rows, int D) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * wpb) {
+    float* row = x + r * D;
+    float mx = -INFINITY;
+    for (int j = lane; j < D; j += 32) mx = fmaxf(mx, row[j]);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < D; j += 32) sum += expf(row[j] - mx);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    for (int j = lane; j < D; j += 32) row[j] = expf(row[j] - mx) * inv;
+  }
+}
+// head backward (one warp per row), from the forward OUTPUTS:
+//  Gaussian head: d_a = d_mean, d_b = d_std * sigmoid(pre) with sigmoid(pre) = 1 - exp(-(std - min_std))
+//                 (std = softplus(pre) + min_std, models/common.py:41; torch's softplus is the identity above 20)
+//  softmax head:  d_a = p * (d_p - sum_j d_p[j] p[j])
+__global__ void __launch_bounds__(256) mlp_head_bwd_kernel(const float* __restrict__ out_a, const float* __restrict__ out_b,
+                                                           const float* __restrict__ d_out_a, const float* __restrict__ d_out_b,
+                                                           int64_t n_rows, int D, int softmax, float min_std,
+                                                           float* __restrict__ d_a, float* __restrict__ d_b) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int64_t r = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); r < n_rows; r += (int64_t)gridDim.x * wpb) {
+    if (softmax) {
+      float dot = 0.f;
+      for (int j = lane; j < D; j += 32) dot = fmaf(d_out_a[r * D + j], out_a[r * D + j], dot);
+      for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      for (int j = lane; j < D; j += 32) d_a[r * D + j] = out_a[r * D + j] * (d_out_a[r * D + j] - dot);
+    } else {
+      for (int j = lane; j < D; j += 32) {
+        d_a[r * D + j] = d_out_a ? d_out_a[r * D + j] : 0.f;
+        const float sp = out_b[r * D + j] - min_std;                 // softplus(pre)
+        const float sg = sp > 20.f ? 1.f : -expm1f(-sp);             // sigmoid(pre)
+        d_b[r * D + j] = d_out_b ? d_out_b[r * D + j] * sg : 0.f;
+      }
+    }
+  }
+}
+// out[j] += sum_r x[r, j]  (bias gradients): thread = column, blockIdx.y = slice of the rows
+__global__ void __launch_bounds__(128) colsum_kernel(const float* __restrict__ x, int64_t n_rows, int D, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  const int64_t per = (n_rows + gridDim.y - 1) / gridDim.y;
+  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = r0 + per < n_rows ? r0 + per : n_rows;
+  float s = 0.f;
+  for (int64_t r = r0; r < r1; ++r) s += x[r * D + j];
+  if (r1 > r0) atomicAdd(out + j, s);
+}
+
 // prior-matching term (models/dmm.py:496-501,541-545), one direction: moments of the K
 // propagated particles of the global prior, KL(global || next), and its gradient wired into
 // the same d_pm / d_v slots bwd_rows_kernel reads (a single chain, no experts)

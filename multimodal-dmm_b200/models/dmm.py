@@ -209,6 +209,76 @@ class _OpFn(torch.autograd.Function):
         return (None, None, None, d_x) + model._views(flat_grad)
 
 
+class _MlpFn(torch.autograd.Function):
+    """One default encoder / decoder module of the composed path through bfvi_mlp_fwd / _bwd: GaussianMLP,
+    CategoricalMLP and the categorical encoder Embedding -> ReLU -> GaussianMLP (models/common.py:9-41,
+    models/dmm.py:78-82) at any size — tcgen05 GEMMs + fused elementwise kernels, weights by pointer (the modules
+    only own them).  `weights` = (emb | None, w1, b1, wa, ba, wb | None, bb | None)."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, *weights):
+        lib = _lib.load()
+        head, nan_mask, min_std = cfg
+        emb, w1, b1, wa, ba, wb, bb = [None if w is None else w.detach().contiguous().float() for w in weights]
+        x = x.detach().contiguous().float()
+        rows = x.shape[0]
+        d = _lib.MlpDesc()
+        d.emb = 0 if emb is None else emb.data_ptr()
+        d.w1, d.b1, d.wa, d.ba = w1.data_ptr(), b1.data_ptr(), wa.data_ptr(), ba.data_ptr()
+        d.wb = 0 if wb is None else wb.data_ptr()
+        d.bb = 0 if bb is None else bb.data_ptr()
+        d.n_in, d.h_dim, d.n_out = w1.shape[1], w1.shape[0], wa.shape[0]
+        d.n_classes = 0 if emb is None else emb.shape[0]
+        d.head, d.nan_mask, d.min_std = head, int(nan_mask), float(min_std)
+        out_a = torch.empty(rows, d.n_out, device=x.device)
+        out_b = torch.empty_like(out_a) if head == _lib.HEAD_GAUSSIAN else None
+        mask = torch.empty(rows, dtype=torch.uint8, device=x.device) if nan_mask else None
+        nbytes = C.c_size_t(0)
+        lib.call('bfvi_mlp_workspace', C.byref(d), rows, 0, C.byref(nbytes))
+        ws = _aligned_bytes(nbytes.value, x.device)
+        lib.call('bfvi_mlp_fwd', C.byref(d), _lib.ptr(x), rows, _lib.ptr(out_a), _lib.ptr(out_b), _lib.ptr(mask),
+                 _lib.ptr(ws), C.c_size_t(nbytes.value), _stream())
+        ctx.desc, ctx.keep = d, (emb, w1, b1, wa, ba, wb, bb)
+        ctx.save_for_backward(x, out_a, *(() if out_b is None else (out_b,)))
+        outs = (out_a,) + (() if out_b is None else (out_b,)) + (() if mask is None else (mask,))
+        if mask is not None:
+            ctx.mark_non_differentiable(mask)
+        ctx.n_out = len(outs)
+        return outs
+
+    @staticmethod
+    def backward(ctx, *d_outs):
+        lib = _lib.load()
+        d, (emb, w1, b1, wa, ba, wb, bb) = ctx.desc, ctx.keep
+        saved = ctx.saved_tensors
+        x, out_a = saved[0], saved[1]
+        out_b = saved[2] if len(saved) > 2 else None
+        rows = x.shape[0]
+        gauss = d.head == _lib.HEAD_GAUSSIAN
+        cont = lambda t: None if t is None else t.contiguous().float()
+        d_a = cont(d_outs[0])
+        d_b = cont(d_outs[1]) if gauss else None
+        if d_a is None and not gauss:
+            d_a = torch.zeros_like(out_a)
+        grads = [None if w is None else torch.zeros_like(w) for w in (emb, w1, b1, wa, ba, wb, bb)]
+        g = _lib.MlpGrads()
+        for name, t in zip(('emb', 'w1', 'b1', 'wa', 'ba', 'wb', 'bb'), grads):
+            setattr(g, name, 0 if t is None else t.data_ptr())
+        want_dx = ctx.needs_input_grad[1] and emb is None
+        d_x = torch.empty(rows, d.n_in, device=x.device) if want_dx else None
+        nbytes = C.c_size_t(0)
+        lib.call('bfvi_mlp_workspace', C.byref(d), rows, 1, C.byref(nbytes))
+        ws = _aligned_bytes(nbytes.value, x.device)
+        lib.call('bfvi_mlp_bwd', C.byref(d), C.byref(g), _lib.ptr(x), rows, _lib.ptr(out_a), _lib.ptr(out_b),
+                 _lib.ptr(d_a), _lib.ptr(d_b), _lib.ptr(d_x), _lib.ptr(ws), C.c_size_t(nbytes.value), _stream())
+        return (None, d_x) + tuple(grads)
+
+
+def _aligned_bytes(nbytes, device):
+    buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+    return buf[(-buf.data_ptr()) % 256:]
+
+
 class _FilterFn(torch.autograd.Function):
     """MultiDMM.z_filter (models/dmm.py:319-412) on arbitrary expert tensors."""
 
@@ -406,11 +476,14 @@ class MultiDMM(MultiDGTS):
                 mu, sd, mk = _OpFn.apply(self, 'enc', i, x.reshape(t_max * b_dim, -1),
                                          *self._slot_params())
                 mk = mk.bool().reshape(t_max, b_dim)
+            elif m not in self._custom_enc:
+                # default modules outside the register-resident family: tcgen05 GEMMs + fused elementwise kernels
+                # (bfvi_mlp_fwd / _bwd), the modules only own the weights
+                mu, sd, mk = self._mlp_encode(m, x.reshape(t_max * b_dim, -1))
+                mk = mk.bool().reshape(t_max, b_dim)
             else:
                 mk = ~torch.isnan(x).flatten(2, -1).any(dim=-1)
                 xz = torch.nan_to_num(x.detach(), nan=0.0)
-                if self.dists[m] == 'Categorical':
-                    xz = xz.long()
                 mu, sd = self.enc[m](xz.flatten(0, 1))
             means.append(mu.reshape(t_max, b_dim, -1))
             stds.append(sd.reshape(t_max, b_dim, -1))
@@ -430,10 +503,35 @@ class MultiDMM(MultiDGTS):
             flat = z.reshape(-1, self.z_dim)
             if self._default_dec(m) and self._family == 1:
                 out = _OpFn.apply(self, 'dec', i, flat, *self._slot_params())
+            elif m not in self._custom_dec:            # GaussianMLP / CategoricalMLP through bfvi_mlp_fwd / _bwd
+                out = self._mlp_decode(m, flat)
             else:
                 out = self.dec[m](flat)
             recon[m] = tuple(r.reshape(t_max, b_dim, *r.shape[1:]) for r in out)
         return recon
+
+    def _mlp_encode(self, m, x):
+        """Default encoder of modality m on (rows, D) inputs -> (mean, std, mask) through bfvi_mlp_fwd."""
+        enc = self.enc[m]
+        if self.dists[m] == 'Categorical':            # Embedding -> ReLU -> GaussianMLP (models/dmm.py:78-82)
+            emb, mlp = enc[0].weight, enc[2]
+            x = x.reshape(-1)
+        else:
+            emb, mlp = None, enc
+        cfg = (_lib.HEAD_GAUSSIAN, True, mlp.min_std)
+        return _MlpFn.apply(cfg, x, emb, mlp.in_to_h[0].weight, mlp.in_to_h[0].bias, mlp.h_to_mean.weight,
+                            mlp.h_to_mean.bias, mlp.h_to_std[0].weight, mlp.h_to_std[0].bias)
+
+    def _mlp_decode(self, m, z):
+        """Default decoder of modality m on (rows, Z) latents through bfvi_mlp_fwd: (mean, std) or (probs,)."""
+        dec = self.dec[m]
+        if self.dists[m] == 'Categorical':            # CategoricalMLP (models/common.py:9-23)
+            cfg = (_lib.HEAD_SOFTMAX, False, 0.0)
+            return _MlpFn.apply(cfg, z, None, dec.in_to_h[0].weight, dec.in_to_h[0].bias, dec.h_to_out[0].weight,
+                                dec.h_to_out[0].bias, None, None)
+        cfg = (_lib.HEAD_GAUSSIAN, False, dec.min_std)
+        return _MlpFn.apply(cfg, z, None, dec.in_to_h[0].weight, dec.in_to_h[0].bias, dec.h_to_mean.weight,
+                            dec.h_to_mean.bias, dec.h_to_std[0].weight, dec.h_to_std[0].bias)
 
     def z_next(self, z, direction='fwd', glb_prior=None):
         """p(z_next | particles z) (models/dmm.py:214-258); tensor-level helper."""
