@@ -139,17 +139,9 @@ def step_case(name, k_train, k_match, seed):
     return fx
 
 
-@pytest.mark.parametrize('name,precision', [('default32', 0), ('c3_dims', 0), ('odd', 0), ('c3_dims', 2)])
-def test_large_family_step_matches_oracle(name, precision):
-    """MultiDMM.step + backward at large dims (C3: M=8, Z=64, H=512) against the fp64 oracle on
-    identical injected noise: ELBO 1e-4 relative, every parameter gradient 1e-3 relative.
-    precision 0 = 3xTF32 launch sequence, 2 = the fused on-chip transition kernels (what bench.py times)."""
-    lib = _lib.load()
-    fx = step_case(name, k_train=5, k_match=7, seed=21)
-    loss, grads, launches = helpers.run_step(lib, fx, 'cuda', kwargs={'precision': precision})
-    if precision == 2:
-        ran = ';'.join(lib.last_dispatch())
-        assert 'gtf_fwd_fused<keep>' in ran and 'gtf_bwd_fused' in ran and 'wgrad16' in ran, ran
+def assert_step_parity(fx, loss, grads, precision):
+    """ELBO 1e-4 and per-tensor gradients 1e-3 against the fp64 oracle on the same injected noise (see the comment on
+    the ReLU-input tensors below)."""
     params = {k: v.clone().double().requires_grad_(True) for k, v in fx['state_dict'].items()}
     orc = bo.OracleDMM(fx['modalities'], fx['dims'], params, h_dim=fx['h_dim'], z_dim=fx['z_dim'],
                        min_std=fx['min_std'], draw=bo.step_noise_tape(fx['noise']))
@@ -187,6 +179,34 @@ def test_large_family_step_matches_oracle(name, precision):
                                  if first_layer(k) and p.grad.norm() > 0))
         print('condition of the ReLU-input tensors under a 4e-6 parameter perturbation: %.2e' % cond)
         assert over[-1][0] < max(1e-3, 2 * cond), (over, cond)
+
+
+
+@pytest.mark.parametrize('name,precision', [('default32', 0), ('c3_dims', 0), ('odd', 0), ('c3_dims', 2)])
+def test_large_family_step_matches_oracle(name, precision):
+    """MultiDMM.step + backward at large dims (C3: M=8, Z=64, H=512) against the fp64 oracle on
+    identical injected noise: ELBO 1e-4 relative, every parameter gradient 1e-3 relative.
+    precision 0 = 3xTF32 launch sequence, 2 = the fused on-chip transition kernels (what bench.py times)."""
+    lib = _lib.load()
+    fx = step_case(name, k_train=5, k_match=7, seed=21)
+    loss, grads, launches = helpers.run_step(lib, fx, 'cuda', kwargs={'precision': precision})
+    if precision == 2:
+        ran = ';'.join(lib.last_dispatch())
+        assert 'gtf_fwd_fused<keep>' in ran and 'gtf_bwd_fused' in ran and 'wgrad16' in ran, ran
+    assert_step_parity(fx, loss, grads, precision)
+
+
+@pytest.mark.parametrize('precision', [2, 0])
+def test_c3_dims_long_chain_matches_oracle(precision):
+    """Error growth over a long chain at the C3 dims: T = 100, ragged lengths, the bench's particle counts (K = 25,
+    K_match = 50), both precision modes, against the fp64 oracle on identical injected noise."""
+    CASES['c3_long'] = dict(z_dim=64, h_dim=512, dims=[16] * 8, t_max=100, lengths=[100, 100, 73], seed=5)
+    lib = _lib.load()
+    fx = step_case('c3_long', k_train=25, k_match=50, seed=22)
+    loss, grads, launches = helpers.run_step(lib, fx, 'cuda', kwargs={'precision': precision})
+    if precision == 2:
+        assert 'gtf_fwd_fused<keep>' in ';'.join(lib.last_dispatch())
+    assert_step_parity(fx, loss, grads, precision)
 
 
 def test_python_api_trains_a_default_sized_model():
