@@ -466,11 +466,14 @@ struct SideStreams {
   cudaEvent_t fork, join[kSideStreams];
   bool ok;
 };
-SideStreams* side_streams() {
-  static thread_local SideStreams cache[64];
-  static thread_local bool made[64];
+constexpr int kTileLanes = 2;            // batch tiles in flight (step_large_tiled)
+SideStreams* side_streams(int lane = 0) {
+  static thread_local SideStreams cache_l[64 * kTileLanes];
+  static thread_local bool made_l[64 * kTileLanes];
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || lane < 0 || lane >= kTileLanes) return nullptr;
+  SideStreams* cache = cache_l + (size_t)lane * 64;
+  bool* made = made_l + (size_t)lane * 64;
   if (!made[dev]) {
     made[dev] = true;
     SideStreams& c = cache[dev];
@@ -1011,7 +1014,7 @@ static bool step4_ok(const bfvi::gen::StepParams& sp) {
 // One batch tile of a step that walks its batch in tiles (step_large_tiled): the loss accumulator and the mask count
 // live outside the tile's workspace, the gradient buffer is cleared by the first tile only, the prior-matching term
 // (linear in the GLOBAL mask count, models/dmm.py:541-545) is added by the first tile, the loss is finalised by the last.
-struct TileCtx { bool first, last; double* acc; const float* count; };
+struct TileCtx { bool first, last; double* acc; const float* count; bool match; int lane; };
 
 // fonly != null: run only z_filter forward (fonly_backward = false) or backward on `fonly`
 int step_large(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a,
@@ -1292,7 +1295,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   const bool external = a->eps_filt != nullptr || a->eps_sflt != nullptr || a->eps_ssmt != nullptr ||
                         a->eps_match != nullptr;
   // ---- prior-matching term (models/dmm.py:540-545) -----------------------------------------
-  if (a->match_mult > 0.f && first_tile) {
+  if (a->match_mult > 0.f && (tile == nullptr || tile->match)) {
     if (external && !a->eps_match) return fail(BFVI_ERR_ARG, "eps_match missing");
     const float* cnt = nullptr;
     float coef = a->match_mult * a->kld_mult;
@@ -1493,7 +1496,7 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     //      beside the particle pass; its GEMMs are latency-bound (S*B rows) and fill SMs the other
     //      stream leaves idle.  BFVI_LARGE_SIDE=0 keeps everything on the caller's stream. ----
     static const bool want_side = [] { const char* e = getenv("BFVI_LARGE_SIDE"); return !e || atoi(e) != 0; }();
-    SideStreams* side = (want_side && do_f && do_s && with_grad) ? side_streams() : nullptr;
+    SideStreams* side = (want_side && do_f && do_s && with_grad) ? side_streams(tile ? tile->lane : 0) : nullptr;
     // fork AFTER the particle pass forward (BFVI_LARGE_SIDE=2: before it): pass A then runs beside pass C — two
     // latency-bound kernel sequences of <= 148 CTAs that share the SMs — instead of beside the 148-CTA
     // persistent launches of pass B, whose statically assigned tiles a co-running kernel only delays
@@ -1614,7 +1617,25 @@ size_t tile_budget_bytes() {
   }();
   return b;
 }
-struct TiledPlan { int bt, n_tiles; size_t acc, count, stage_in[BFVI_MAX_MODS], stage_tg[BFVI_MAX_MODS], stage_mask, tile_ws, tile_bytes, total; };
+// Optionally two tiles are in flight at a time ("lanes", BFVI_TILE_LANES=2; each lane has its own streams, staging
+// buffers, tile workspace and — lane 1 — gradient buffer): a time step of a tile is ~0.6 ms of dependent latency-bound
+// launches (the single-particle passes sit on the critical path B fwd -> C fwd -> C bwd -> B bwd) plus 1.6 us per sequence
+// of throughput-bound work, so a second lane can fill the SMs the first one leaves idle.  Measured (C3 dims, T = 40,
+// tools/r2_gpu27.sh): at EQUAL tile size two lanes win (2 x 512: 98.9 -> 84.6 ms; 2 x 1 024: 171.8 -> 158.5 ms), but the
+// lanes share the memory budget, and four tiles of 512 in two lanes (168.1 ms) barely beat two tiles of 1 024 one after
+// the other (171.8 ms) — the persistent 148-CTA kernels of the two lanes cannot co-reside, and at T = 1 000 the host
+// enqueues a whole tile (~0.4 s of launches) before the other lane gets its first kernel.  Default: one lane.
+struct TiledPlan {
+  int bt, n_tiles, n_lanes;
+  size_t acc, count, lane0, lane_bytes, lane_grads;       // lane l: [lane0 + l * lane_bytes, ...)
+  size_t stage_in[BFVI_MAX_MODS], stage_tg[BFVI_MAX_MODS], stage_mask, tile_ws, tile_bytes;   // offsets INSIDE a lane
+  size_t total;
+};
+int tile_lanes_wanted() {                 // read per call: bfvi_step_workspace and bfvi_step_fwd_bwd see the same value
+  const char* e = getenv("BFVI_TILE_LANES");
+  const int v = e ? atoi(e) : 1;
+  return v < 1 ? 1 : (v > kTileLanes ? kTileLanes : v);
+}
 int plan_tiled(const bfvi_model* m, const bfvi_step_args* a, TiledPlan* tp) {
   const int B = a->B, T = a->T;
   auto tile_bytes_of = [&](int bt) {
@@ -1627,25 +1648,37 @@ int plan_tiled(const bfvi_model* m, const bfvi_step_args* a, TiledPlan* tp) {
   };
   int bt = a->batch_tile > 0 ? a->batch_tile : B;
   if (bt > B) bt = B;
+  int lanes = 1;
   if (a->batch_tile <= 0 && tile_bytes_of(B) > tile_budget_bytes()) {
-    // workspace is affine in the batch: fit the budget, keep tiles a multiple of 64 sequences
+    // workspace is affine in the batch: fit the budget (shared by the lanes), keep tiles a multiple of 64 sequences
+    lanes = tile_lanes_wanted();
     const size_t b1 = tile_bytes_of(64), b2 = tile_bytes_of(128);
     const double per = (double)(b2 - b1) / 64.0;
     const double fixed = (double)b1 - 64.0 * per;
-    int fit = (int)(((double)tile_budget_bytes() - fixed) / per);
+    int fit = (int)(((double)tile_budget_bytes() / lanes - fixed) / per);
     fit = fit / 64 * 64;
     if (fit < 64) fit = 64;
     bt = fit < B ? fit : B;
-    // equalise: same tile count, smaller last-tile imbalance
-    const int n = (B + bt - 1) / bt;
+    // equalise: same tile count (a multiple of the lane count), smaller last-tile imbalance
+    int n = (B + bt - 1) / bt;
+    n = (n + lanes - 1) / lanes * lanes;
     bt = ((B + n - 1) / n + 63) / 64 * 64;
     if (bt > B) bt = B;
+  } else if (a->batch_tile > 0 && bt < B) {
+    lanes = tile_lanes_wanted();                       // explicit tile size (tests): the caller sized it
   }
   tp->bt = bt;
   tp->n_tiles = (B + bt - 1) / bt;
+  if (tp->n_tiles < 2) lanes = 1;
+  tp->n_lanes = lanes;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
   size_t cur = 0;
   auto carve = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
   tp->acc = carve(sizeof(double)); tp->count = carve(sizeof(float));
+  tp->lane_grads = carve(lanes > 1 ? sizeof(float) * (size_t)lay.total * (lanes - 1) : 0);
+  tp->lane0 = carve(0);
+  cur = 0;                                             // offsets inside one lane
   if (tp->n_tiles > 1) {
     for (int i = 0; i < m->n_mods; ++i) {
       tp->stage_in[i] = carve(sizeof(float) * (size_t)T * bt * m->dims[i]);
@@ -1655,7 +1688,8 @@ int plan_tiled(const bfvi_model* m, const bfvi_step_args* a, TiledPlan* tp) {
   }
   tp->tile_ws = carve(0);
   tp->tile_bytes = tile_bytes_of(bt);
-  tp->total = tp->tile_ws + tp->tile_bytes;
+  tp->lane_bytes = align_up(tp->tile_ws + tp->tile_bytes, 256);
+  tp->total = tp->lane0 + (size_t)lanes * tp->lane_bytes;
   return BFVI_OK;
 }
 int step_large_tiled(const bfvi_model* m, const float* params, float* grads, const bfvi_step_args* a, void* workspace,
@@ -1666,9 +1700,18 @@ int step_large_tiled(const bfvi_model* m, const float* params, float* grads, con
   if (((uintptr_t)workspace & 255) != 0) return fail(BFVI_ERR_ARG, "workspace must be 256-byte aligned");
   char* ws = (char*)workspace;
   if (tp.n_tiles == 1)
-    return step_large(m, params, grads, a, nullptr, false, ws + tp.tile_ws, tp.tile_bytes, loss_out, launches, st);
-  note_dispatch("step:batch_tiles=%d x %d", tp.n_tiles, tp.bt);
+    return step_large(m, params, grads, a, nullptr, false, ws + tp.lane0 + tp.tile_ws, tp.tile_bytes, loss_out, launches, st);
+  if (a->eps_match || a->eps_filt || a->eps_sflt || a->eps_ssmt)
+    return fail(BFVI_ERR_UNSUPPORTED, "external noise tensors with batch tiles: pass batch_tile >= B (parity runs are small)");
   const int T = a->T, B = a->B;
+  bfvi_layout lay;
+  bfvi_param_layout(m, &lay);
+  // lane 1 runs on a stream of its own (forked from / joined into the caller's stream by events: the call stays
+  // asynchronous and stream-ordered, and capturable in a CUDA graph)
+  int lanes = tp.n_lanes;
+  SideStreams* lane_side = lanes > 1 ? side_streams(1) : nullptr;
+  if (lanes > 1 && (lane_side == nullptr || grads == nullptr)) lanes = 1;        // (no streams / forward only: one lane)
+  note_dispatch("step:batch_tiles=%d x %d lanes=%d", tp.n_tiles, tp.bt, lanes);
   double* acc = (double*)(ws + tp.acc);
   float* count = (float*)(ws + tp.count);
   cudaMemsetAsync(acc, 0, sizeof(double), st);
@@ -1682,30 +1725,53 @@ int step_large_tiled(const bfvi_model* m, const float* params, float* grads, con
     }                                                 // else: the tiles use the caller's count (static coefficient)
   }
   BFVI_CHECK_CUDA();
+  cudaStream_t lane_st[kTileLanes] = {st, st};
+  float* lane_grads[kTileLanes] = {grads, grads};
+  if (lanes > 1) {
+    lane_st[1] = lane_side->stream[1];                // (stream[0] of a lane's set is its pass-A side stream)
+    lane_grads[1] = (float*)(ws + tp.lane_grads);
+    cudaEventRecord(lane_side->fork, st);
+    cudaStreamWaitEvent(lane_st[1], lane_side->fork, 0);
+  }
   for (int i = 0; i < tp.n_tiles; ++i) {
+    const int lane = i % lanes;
+    char* lw = ws + tp.lane0 + (size_t)lane * tp.lane_bytes;
+    cudaStream_t ls = lane_st[lane];
     const int b0 = i * tp.bt, bc = b0 + tp.bt <= B ? tp.bt : B - b0;
     bfvi_step_args at = *a;
     at.B = bc;
     at.b_offset = a->b_offset + (uint32_t)b0;
     for (int k = 0; k < m->n_mods; ++k) {
       const size_t D = (size_t)m->dims[k];
-      float* si = (float*)(ws + tp.stage_in[k]);
-      float* sg = (float*)(ws + tp.stage_tg[k]);
-      cudaMemcpy2DAsync(si, bc * D * 4, a->inputs[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, st);
-      cudaMemcpy2DAsync(sg, bc * D * 4, a->targets[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, st);
+      float* si = (float*)(lw + tp.stage_in[k]);
+      float* sg = (float*)(lw + tp.stage_tg[k]);
+      cudaMemcpy2DAsync(si, bc * D * 4, a->inputs[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, ls);
+      cudaMemcpy2DAsync(sg, bc * D * 4, a->targets[k] + (size_t)b0 * D, (size_t)B * D * 4, bc * D * 4, T, cudaMemcpyDeviceToDevice, ls);
       at.inputs[k] = si; at.targets[k] = sg;
     }
-    uint8_t* sm = (uint8_t*)(ws + tp.stage_mask);
-    cudaMemcpy2DAsync(sm, bc, a->seq_mask + b0, B, bc, T, cudaMemcpyDeviceToDevice, st);
+    uint8_t* sm = (uint8_t*)(lw + tp.stage_mask);
+    cudaMemcpy2DAsync(sm, bc, a->seq_mask + b0, B, bc, T, cudaMemcpyDeviceToDevice, ls);
     at.seq_mask = sm;
-    if (a->eps_match || a->eps_filt || a->eps_sflt || a->eps_ssmt)
-      return fail(BFVI_ERR_UNSUPPORTED, "external noise tensors with batch tiles: pass batch_tile >= B (parity runs are small)");
     BFVI_CHECK_CUDA();
     TileCtx tc;
-    tc.first = i == 0; tc.last = i == tp.n_tiles - 1; tc.acc = acc; tc.count = a->match_count < 0.f ? count : nullptr;
+    tc.first = i < lanes;                             // first tile of its lane: clears the lane's gradient buffer
+    tc.last = lanes == 1 && i == tp.n_tiles - 1;      // one lane: the last tile finalises the loss
+    tc.match = i == 0;                                // the prior-matching term is computed once
+    tc.lane = lane;
+    tc.acc = acc; tc.count = a->match_count < 0.f ? count : nullptr;
     int32_t l = 0;
-    if (int rc = step_large(m, params, grads, &at, nullptr, false, ws + tp.tile_ws, tp.tile_bytes, loss_out, &l, st, &tc)) return rc;
+    if (int rc = step_large(m, params, lane_grads[lane], &at, nullptr, false, lw + tp.tile_ws, tp.tile_bytes, loss_out, &l, ls, &tc)) return rc;
     n_launch += l;
+  }
+  if (lanes > 1) {                                    // join: add lane 1's gradients, then the loss
+    cudaEventRecord(lane_side->join[1], lane_st[1]);
+    cudaStreamWaitEvent(st, lane_side->join[1], 0);
+    auto ka = add_into_kernel;
+    BFVI_LAUNCH(ka, dim3((unsigned)grid_for(lay.total, 256, 4)), dim3(256), 0, st, grads, (const float*)lane_grads[1], (int64_t)lay.total);
+    auto kfin = bfvi::finalize_loss_kernel;
+    BFVI_LAUNCH(kfin, dim3(1), dim3(32), 0, st, (const double*)acc, loss_out);
+    BFVI_CHECK_CUDA();
+    n_launch += 2;
   }
   if (launches) *launches = n_launch;
   return BFVI_OK;

@@ -272,16 +272,18 @@ def test_cuda_graph_step_matches_eager():
 
 
 @pytest.mark.parametrize('precision', [0, 2])
-@pytest.mark.parametrize('tile', [4, 7])
-def test_batch_tiled_step_equals_whole_batch_step(precision, tile):
+@pytest.mark.parametrize('tile,lanes', [(4, 1), (7, 1), (4, 2), (3, 2)])
+def test_batch_tiled_step_equals_whole_batch_step(precision, tile, lanes, monkeypatch):
     """The step walks the batch in tiles (bfvi_step_args.batch_tile): same loss and gradients as the one-piece
-    step on the same Philox seed, both for the launch-sequence path and the fused kernels (C3 dims, B = 11)."""
+    step on the same Philox seed, both for the launch-sequence path and the fused kernels (C3 dims, B = 11); one
+    tile at a time or two tiles in flight on two streams (BFVI_TILE_LANES=2)."""
+    monkeypatch.setenv('BFVI_TILE_LANES', str(lanes))
     lib = _lib.load()
     fx = step_case('c3_dims', k_train=5, k_match=7, seed=21)
     l0, g0, _ = helpers.run_step(lib, fx, 'cuda', noise=None, seed=5, return_flat=True, kwargs={'precision': precision})
     l1, g1, _ = helpers.run_step(lib, fx, 'cuda', noise=None, seed=5, return_flat=True,
                                  kwargs={'precision': precision, 'batch_tile': tile})
-    assert 'step:batch_tiles' in ';'.join(lib.last_dispatch())
+    assert 'step:batch_tiles' in ';'.join(lib.last_dispatch()) and 'lanes=%d' % lanes in ';'.join(lib.last_dispatch())
     assert abs(l0 - l1) <= 2e-5 * abs(l0), (l0, l1)
     assert torch.isfinite(g1).all()
     assert ((g0 - g1).norm() / g0.norm()).item() < 1e-4
