@@ -862,10 +862,17 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
 // elementwise kernels (bfvi_generic.cuh).  Same passes, chain sets and workspace roles as the
 // small-dim step_impl below; rows of a GEMM = chains x particles of ONE time step.
 // ===========================================================================================
+constexpr size_t kMlpChunkRows = 262144;          // rows per chunk of the encoder / decoder passes (BFVI_MLP_CHUNK overrides)
+size_t mlp_chunk_rows() {
+  const char* e = getenv("BFVI_MLP_CHUNK");
+  const long v = e ? atol(e) : 0;
+  return v >= 32 ? (size_t)v : kMlpChunkRows;
+}
 struct LargePlan {
   int S, k_b;
   unsigned set_bits[BFVI_MAX_SETS];
   size_t tb, tbz, C, R, d_max;
+  size_t rc;                                       // rows per chunk of the encoder / decoder scratch (<= tb)
   size_t zero_begin, zero_end, total;
   size_t acc, count, dobs_mean, dobs_std, a_dsamp, c_dsamp, b_dpm, b_dps;        // zeroed
   size_t paramsT, x0[BFVI_MAX_MODS], x0T[BFVI_MAX_MODS], mask, henc, hencT, obs_mean, obs_stdpre, obs_std;
@@ -917,7 +924,11 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   (void)Mx;
   for (int i = 0; i < M; ++i) { pl->x0[i] = carve(f * pl->tb * m->dims[i]); pl->x0T[i] = carve(f * pl->tb * m->dims[i]); }
   pl->mask = carve(pl->tb * M);
-  pl->henc = carve(f * pl->tb * H * M); pl->hencT = carve(f * pl->tb * H * M);
+  // encoder / decoder hidden activations live in a ROW-CHUNK scratch (hdec, hdecT, dhd, dhdT: rc x H each): the encoder
+  // backward recomputes its hidden layer per chunk instead of keeping (T*B, H) x M activations and their transposed copies
+  // (32 KB per sequence-timestep at the C3 shape, 29 % of the step's workspace), and the decoders walk T*B in chunks
+  pl->rc = pl->tb < mlp_chunk_rows() ? pl->tb : mlp_chunk_rows();
+  pl->henc = pl->hencT = 0;
   pl->obs_mean = carve(f * pl->tbz * M); pl->obs_stdpre = carve(f * pl->tbz * M); pl->obs_std = carve(f * pl->tbz * M);
   for (int i = 0; i < 6; ++i) pl->pa[i] = carve(fS);
   for (int i = 0; i < 4; ++i) pl->pb[i] = carve(fS);
@@ -935,10 +946,10 @@ int plan_large(const bfvi_model* m, const bfvi_step_args* a, const bfvi_filter_a
   pl->c_mu = carve(f * pl->C * Z); pl->c_sd = carve(f * pl->C * Z);
   pl->d_pm = carve(f * pl->C * Z); pl->d_v = carve(f * pl->C * Z);
   pl->zvec = carve(f * Z * 4);
-  pl->hdec = carve(f * pl->tb * H); pl->hdecT = carve(f * pl->tb * H);
-  pl->dhd = carve(f * pl->tb * H); pl->dhdT = carve(f * pl->tb * H);
-  pl->dmean = carve(f * pl->tb * pl->d_max); pl->dstd = carve(f * pl->tb * pl->d_max);
-  pl->dmeanT = carve(f * pl->tb * pl->d_max); pl->dstdT = carve(f * pl->tb * pl->d_max);
+  pl->hdec = carve(f * pl->rc * H); pl->hdecT = carve(f * pl->rc * H);
+  pl->dhd = carve(f * pl->rc * H); pl->dhdT = carve(f * pl->rc * H);
+  pl->dmean = carve(f * pl->rc * pl->d_max); pl->dstd = carve(f * pl->rc * pl->d_max);
+  pl->dmeanT = carve(f * pl->rc * pl->d_max); pl->dstdT = carve(f * pl->rc * pl->d_max);
   pl->fused_packs = pl->fused_rows = 0;
   if (pl->fused) {
     cur = align_up(cur, 1024);
@@ -977,10 +988,10 @@ void plan_large_side(const bfvi_model* m, const bfvi_step_args* a, const LargePl
   for (size_t* z : zbufs) *z = carve(rz);
   ps->c_mu = carve(f * pl.C * Z); ps->c_sd = carve(f * pl.C * Z);
   ps->d_pm = carve(f * pl.C * Z); ps->d_v = carve(f * pl.C * Z);
-  ps->hdec = carve(f * pl.tb * H); ps->hdecT = carve(f * pl.tb * H);
-  ps->dhd = carve(f * pl.tb * H); ps->dhdT = carve(f * pl.tb * H);
-  ps->dmean = carve(f * pl.tb * pl.d_max); ps->dstd = carve(f * pl.tb * pl.d_max);
-  ps->dmeanT = carve(f * pl.tb * pl.d_max); ps->dstdT = carve(f * pl.tb * pl.d_max);
+  ps->hdec = carve(f * pl.rc * H); ps->hdecT = carve(f * pl.rc * H);
+  ps->dhd = carve(f * pl.rc * H); ps->dhdT = carve(f * pl.rc * H);
+  ps->dmean = carve(f * pl.rc * pl.d_max); ps->dstd = carve(f * pl.rc * pl.d_max);
+  ps->dmeanT = carve(f * pl.rc * pl.d_max); ps->dstdT = carve(f * pl.rc * pl.d_max);
   if (pl.fused) {                                      // packs are shared with the main plan; own row scratch
     cur = align_up(cur, 1024);
     ps->fused_rows = carve(fused_row_scratch(H, (int64_t)R).total);
@@ -1095,17 +1106,20 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     return gemm(gp);
   };
   // dW (n_out, n_in) += dy^T x from the transposed copies
-  auto wgrad = [&](const float* dyT, const float* xT, int64_t rows, int n_out, int n_in, int64_t w_off) -> int {
+  auto wgrad = [&](const float* dyT, const float* xT, int64_t rows, int n_out, int n_in, int64_t w_off, int64_t ld_dy = 0,
+                   int64_t ld_x = 0) -> int {
     bfvi::tc::GemmParams gp;
     memset(&gp, 0, sizeof(gp));
+    if (ld_dy == 0) ld_dy = rows;               // leading dimensions of the transposed operands (a row chunk of a
+    if (ld_x == 0) ld_x = rows;                 // (width, T*B) array keeps the array's)
     if (wgrad_swapped(n_out, n_in)) {           // dW^T = X^T dY, added into dW transposed
-      gp.A = xT; gp.lda = rows; gp.W = dyT; gp.ldw = rows;
+      gp.A = xT; gp.lda = ld_x; gp.W = dyT; gp.ldw = ld_dy;
       gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_in; gp.N = n_out; gp.K = rows; gp.accumulate = 1;
       gp.trans_out = 1;
       gp.k_split = wgrad_k_split(rows, n_in, n_out);
       return gemm(gp);
     }
-    gp.A = dyT; gp.lda = rows; gp.W = xT; gp.ldw = rows;
+    gp.A = dyT; gp.lda = ld_dy; gp.W = xT; gp.ldw = ld_x;
     gp.C = grads + w_off; gp.ldc = n_in; gp.M = n_out; gp.N = n_in; gp.K = rows; gp.accumulate = 1;
     gp.k_split = wgrad_k_split(rows, n_out, n_in);
     return gemm(gp);
@@ -1365,17 +1379,18 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
     for (int i = 0; i < M; ++i) {
       const bfvi_mlp_layout& l = lay.enc[i];
       const int D = m->dims[i];
-      float* henc = F(pl.henc) + (size_t)i * pl.tb * H;
-      float* hencT = F(pl.hencT) + (size_t)i * pl.tb * H;
       auto kp = bfvi::gen::prep_rows_kernel;
       BFVI_LAUNCH(kp, ew_grid(tb, 256), dim3(256), 0, st, a->inputs[i], tb, D, F(pl.x0[i]), obs_mask + (size_t)i * pl.tb);
       ++n_launch;
       if (with_grad) transpose(F(pl.x0[i]), tb, D, F(pl.x0T[i]));
-      if (int rc = lin(F(pl.x0[i]), D, l.in_to_h_w, l.in_to_h_b, henc, with_grad ? hencT : nullptr, tb, D, H, 1)) return rc;
-      if (int rc = flush()) return rc;
-      if (int rc = lin(henc, H, l.mean_w, l.mean_b, obs_mean + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
-      if (int rc = lin(henc, H, l.std_w, l.std_b, obs_stdpre + (size_t)i * pl.tbz, nullptr, tb, H, Z, 0)) return rc;
-      if (int rc = flush()) return rc;
+      for (int64_t r0 = 0; r0 < tb; r0 += (int64_t)pl.rc) {        // row chunks: the hidden layer is scratch
+        const int64_t n = tb - r0 < (int64_t)pl.rc ? tb - r0 : (int64_t)pl.rc;
+        if (int rc = lin(F(pl.x0[i]) + r0 * D, D, l.in_to_h_w, l.in_to_h_b, F(pl.hdec), nullptr, n, D, H, 1)) return rc;
+        if (int rc = flush()) return rc;
+        if (int rc = lin(F(pl.hdec), H, l.mean_w, l.mean_b, obs_mean + (size_t)i * pl.tbz + r0 * Z, nullptr, n, H, Z, 0)) return rc;
+        if (int rc = lin(F(pl.hdec), H, l.std_w, l.std_b, obs_stdpre + (size_t)i * pl.tbz + r0 * Z, nullptr, n, H, Z, 0)) return rc;
+        if (int rc = flush()) return rc;
+      }
       cudaMemcpyAsync(obs_std + (size_t)i * pl.tbz, obs_stdpre + (size_t)i * pl.tbz, sizeof(float) * pl.tbz,
                       cudaMemcpyDeviceToDevice, st);
       auto ks = bfvi::gen::softplus_kernel;
@@ -1461,32 +1476,36 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
           if (!((pl.set_bits[s] >> i) & 1u) || a->rec_mults[i] == 0.f) continue;
           const bfvi_mlp_layout& l = lay.dec[i];
           const int D = m->dims[i];
-          const float* zs = samp + (size_t)s * pl.tbz;
-          if (int rc = lin(zs, Z, l.in_to_h_w, l.in_to_h_b, F(pl.hdec), with_grad ? F(pl.hdecT) : nullptr, tb, Z, H, 1)) return rc;
-          if (int rc = flush()) return rc;
-          if (int rc = lin(F(pl.hdec), H, l.mean_w, l.mean_b, F(pl.dmean), nullptr, tb, H, D, 0)) return rc;
-          if (int rc = lin(F(pl.hdec), H, l.std_w, l.std_b, F(pl.dstd), nullptr, tb, H, D, 0)) return rc;
-          if (int rc = flush()) return rc;
-          bfvi::gen::HeadParams hp;
-          memset(&hp, 0, sizeof(hp));
-          hp.mean = F(pl.dmean); hp.stdpre = F(pl.dstd); hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
-          hp.target = a->targets[i]; hp.row_mask = a->seq_mask;
-          hp.gb_mean = with_grad ? grads + l.mean_b : F(pl.dz); hp.gb_std = with_grad ? grads + l.std_b : F(pl.dz);
-          hp.n_rows = tb; hp.D = D; hp.weight = mult * a->rec_mults[i]; hp.loss_acc = acc;
-          auto kh = bfvi::gen::head_kernel;
-          BFVI_LAUNCH(kh, dim3((unsigned)((tb + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                               (unsigned)((D + 127) / 128)), dim3(128), 0, st, hp);
-          ++n_launch;
-          if (!with_grad) continue;
-          if (int rc = dgrad(F(pl.dmean), l.mean_w, F(pl.dhd), nullptr, tb, D, H, false, F(pl.hdec), grads + l.in_to_h_b)) return rc;
-          if (int rc = wgrad(F(pl.dmeanT), F(pl.hdecT), tb, D, H, l.mean_w)) return rc;
-          if (int rc = wgrad(F(pl.dstdT), F(pl.hdecT), tb, D, H, l.std_w)) return rc;
-          if (int rc = flush()) return rc;
-          if (int rc = dgrad(F(pl.dstd), l.std_w, F(pl.dhd), F(pl.dhdT), tb, D, H, true, F(pl.hdec), grads + l.in_to_h_b)) return rc;
-          if (int rc = flush()) return rc;
-          if (int rc = dgrad(F(pl.dhd), l.in_to_h_w, dsamp + (size_t)s * pl.tbz, nullptr, tb, H, Z, true, nullptr, nullptr)) return rc;
-          if (int rc = wgrad(F(pl.dhdT), sampT + (size_t)s * pl.tbz, tb, H, Z, l.in_to_h_w)) return rc;
-          if (int rc = flush()) return rc;
+          for (int64_t r0 = 0; r0 < tb; r0 += (int64_t)pl.rc) {   // row chunks of the (T*B) samples: hidden layers are scratch
+            const int64_t n = tb - r0 < (int64_t)pl.rc ? tb - r0 : (int64_t)pl.rc;
+            const float* zs = samp + (size_t)s * pl.tbz + r0 * Z;
+            if (int rc = lin(zs, Z, l.in_to_h_w, l.in_to_h_b, F(pl.hdec), with_grad ? F(pl.hdecT) : nullptr, n, Z, H, 1)) return rc;
+            if (int rc = flush()) return rc;
+            if (int rc = lin(F(pl.hdec), H, l.mean_w, l.mean_b, F(pl.dmean), nullptr, n, H, D, 0)) return rc;
+            if (int rc = lin(F(pl.hdec), H, l.std_w, l.std_b, F(pl.dstd), nullptr, n, H, D, 0)) return rc;
+            if (int rc = flush()) return rc;
+            bfvi::gen::HeadParams hp;
+            memset(&hp, 0, sizeof(hp));
+            hp.mean = F(pl.dmean); hp.stdpre = F(pl.dstd); hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
+            hp.target = a->targets[i] + r0 * D; hp.row_mask = a->seq_mask ? a->seq_mask + r0 : nullptr;
+            hp.gb_mean = with_grad ? grads + l.mean_b : F(pl.dz); hp.gb_std = with_grad ? grads + l.std_b : F(pl.dz);
+            hp.n_rows = n; hp.D = D; hp.weight = mult * a->rec_mults[i]; hp.loss_acc = acc;
+            auto kh = bfvi::gen::head_kernel;
+            BFVI_LAUNCH(kh, dim3((unsigned)((n + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                                 (unsigned)((D + 127) / 128)), dim3(128), 0, st, hp);
+            ++n_launch;
+            if (!with_grad) continue;
+            if (int rc = dgrad(F(pl.dmean), l.mean_w, F(pl.dhd), nullptr, n, D, H, false, F(pl.hdec), grads + l.in_to_h_b)) return rc;
+            if (int rc = wgrad(F(pl.dmeanT), F(pl.hdecT), n, D, H, l.mean_w)) return rc;
+            if (int rc = wgrad(F(pl.dstdT), F(pl.hdecT), n, D, H, l.std_w)) return rc;
+            if (int rc = flush()) return rc;
+            if (int rc = dgrad(F(pl.dstd), l.std_w, F(pl.dhd), F(pl.dhdT), n, D, H, true, F(pl.hdec), grads + l.in_to_h_b)) return rc;
+            if (int rc = flush()) return rc;
+            if (int rc = dgrad(F(pl.dhd), l.in_to_h_w, dsamp + (size_t)s * pl.tbz + r0 * Z, nullptr, n, H, Z, true, nullptr, nullptr)) return rc;
+            // the transposed samples are a (Z, T*B) array per chain set: a chunk keeps its leading dimension
+            if (int rc = wgrad(F(pl.dhdT), sampT + (size_t)s * pl.tbz + r0, n, H, Z, l.in_to_h_w, n, tb)) return rc;
+            if (int rc = flush()) return rc;
+          }
         }
       BFVI_CHECK_CUDA();
       return BFVI_OK;
@@ -1558,29 +1577,35 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       for (int i = 0; i < M; ++i) {
         const bfvi_mlp_layout& l = lay.enc[i];
         const int D = m->dims[i];
-        float* henc = F(pl.henc) + (size_t)i * pl.tb * H;
-        float* hencT = F(pl.hencT) + (size_t)i * pl.tb * H;
-        // d_mean / d_stdpre live in the obs_mean / obs_stdpre slots from here on (their values are spent)
-        float* dm = obs_mean + (size_t)i * pl.tbz;
-        float* dsp = obs_stdpre + (size_t)i * pl.tbz;
-        bfvi::gen::HeadParams hp;
-        memset(&hp, 0, sizeof(hp));
-        hp.mean = dm; hp.stdpre = dsp; hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
-        hp.d_mean_in = dobs_mean + (size_t)i * pl.tbz; hp.d_std_in = dobs_std + (size_t)i * pl.tbz;
-        hp.gb_mean = grads + l.mean_b; hp.gb_std = grads + l.std_b;
-        hp.n_rows = tb; hp.D = Z; hp.weight = 1.f;
-        auto kh = bfvi::gen::head_kernel;
-        BFVI_LAUNCH(kh, dim3((unsigned)((tb + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                             (unsigned)((Z + 127) / 128)), dim3(128), 0, st, hp);
-        ++n_launch;
-        if (int rc = dgrad(dm, l.mean_w, F(pl.dhd), nullptr, tb, Z, H, false, henc, grads + l.in_to_h_b)) return rc;
-        if (int rc = wgrad(F(pl.dmeanT), hencT, tb, Z, H, l.mean_w)) return rc;
-        if (int rc = wgrad(F(pl.dstdT), hencT, tb, Z, H, l.std_w)) return rc;
-        if (int rc = flush()) return rc;
-        if (int rc = dgrad(dsp, l.std_w, F(pl.dhd), F(pl.dhdT), tb, Z, H, true, henc, grads + l.in_to_h_b)) return rc;
-        if (int rc = flush()) return rc;
-        if (int rc = wgrad(F(pl.dhdT), F(pl.x0T[i]), tb, H, D, l.in_to_h_w)) return rc;
-        if (int rc = flush()) return rc;
+        // d_mean / d_stdpre live in the obs_mean / obs_stdpre slots from here on (their values are spent).  Row chunks: the
+        // hidden activations (and their transposed copy) are RECOMPUTED into the decoder scratch, free by now
+        for (int64_t r0 = 0; r0 < tb; r0 += (int64_t)pl.rc) {
+          const int64_t n = tb - r0 < (int64_t)pl.rc ? tb - r0 : (int64_t)pl.rc;
+          float* henc = F(pl.hdec);
+          float* hencT = F(pl.hdecT);
+          if (int rc = lin(F(pl.x0[i]) + r0 * D, D, l.in_to_h_w, l.in_to_h_b, henc, hencT, n, D, H, 1)) return rc;
+          if (int rc = flush()) return rc;
+          float* dm = obs_mean + (size_t)i * pl.tbz + r0 * Z;
+          float* dsp = obs_stdpre + (size_t)i * pl.tbz + r0 * Z;
+          bfvi::gen::HeadParams hp;
+          memset(&hp, 0, sizeof(hp));
+          hp.mean = dm; hp.stdpre = dsp; hp.meanT = F(pl.dmeanT); hp.stdpreT = F(pl.dstdT);
+          hp.d_mean_in = dobs_mean + (size_t)i * pl.tbz + r0 * Z; hp.d_std_in = dobs_std + (size_t)i * pl.tbz + r0 * Z;
+          hp.gb_mean = grads + l.mean_b; hp.gb_std = grads + l.std_b;
+          hp.n_rows = n; hp.D = Z; hp.weight = 1.f;
+          auto kh = bfvi::gen::head_kernel;
+          BFVI_LAUNCH(kh, dim3((unsigned)((n + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
+                               (unsigned)((Z + 127) / 128)), dim3(128), 0, st, hp);
+          ++n_launch;
+          if (int rc = dgrad(dm, l.mean_w, F(pl.dhd), nullptr, n, Z, H, false, henc, grads + l.in_to_h_b)) return rc;
+          if (int rc = wgrad(F(pl.dmeanT), hencT, n, Z, H, l.mean_w)) return rc;
+          if (int rc = wgrad(F(pl.dstdT), hencT, n, Z, H, l.std_w)) return rc;
+          if (int rc = flush()) return rc;
+          if (int rc = dgrad(dsp, l.std_w, F(pl.dhd), F(pl.dhdT), n, Z, H, true, henc, grads + l.in_to_h_b)) return rc;
+          if (int rc = flush()) return rc;
+          if (int rc = wgrad(F(pl.dhdT), F(pl.x0T[i]) + r0, n, H, D, l.in_to_h_w, n, tb)) return rc;
+          if (int rc = flush()) return rc;
+        }
       }
       BFVI_CHECK_CUDA();
     }
