@@ -79,7 +79,9 @@ constexpr int kAblTile16 = 1, kAblRows = 2, kAblBits = 4, kAblMma2 = 8, kAblMma1
 // of cp.async.bulk (whose requests queue behind the weight ring's bulk loads in the SM's one copy engine)
 constexpr int kStoreLsu = 64;
 // 128 (timing only): the loaders stop copying after the first lap of the ring (stale operands): is the ring the limit?
-constexpr int kAblRing = 128;     // per 32-lane quadrant (two row warps): two 32 rows x 256 B slots = four 32 x 128 B slots
+constexpr int kAblRing = 128;
+// 256 (timing only): no proxy fence before the bulk stores (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC in SASS)
+constexpr int kAblFence = 256;     // per 32-lane quadrant (two row warps): two 32 rows x 256 B slots = four 32 x 128 B slots
 
 // shared-memory image of a 64 x 64 fp32 operand tile, K-major SWIZZLE_128B: two K halves of 32 floats; row r of a
 // half is one 128-byte line whose 16-byte chunks are XOR-permuted by r % 8 (8-row groups 1024 B apart)
@@ -322,7 +324,7 @@ __device__ __forceinline__ void patch_switch(int q, bool elected, bool lsu) {
 // 4 KB bulk copy.  Tiles are padded to whole row tiles, so rows past the end are written (as zeros) too.
 __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int q, int lane, int hf, bool elected,
                                                __half* __restrict__ base, int64_t row0, int64_t n_groups, int n_atoms,
-                                               int atom, const float (&v)[32], bool lsu = false) {
+                                               int atom, const float (&v)[32], bool lsu = false, bool nofence = false) {
   if (!lsu) {
     if (elected) bulk_wait_read<3>();                // the copy that used this slot four stores ago has read it
     pair_sync(q);
@@ -352,7 +354,7 @@ __device__ __forceinline__ void store_tile_f16(unsigned char* pp, int& buf, int 
     buf = (buf + 1) & 3;
     return;
   }
-  fence_async_smem();
+  if (!nofence) fence_async_smem();
   pair_sync(q);
   if (elected) {
     bulk_s2g(tile, pp + buf * 4096, 4096);
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
       const int n_valid = (int)(p.R - row0 < 32 ? (p.R - row0 < 0 ? 0 : p.R - row0) : 32);
       if (KEEP && !BFVI_ABL(kAblTile16)) {
         patch_switch(q, elected, lsu);                // the fp32 rows of the previous tile used the same shared memory
-        store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 2 * n_tiles, 1, 0, zreg, lsu);
+        store_tile_f16(pp, hp, q, lane, hf, elected, p.z16, row0, 2 * n_tiles, 1, 0, zreg, lsu, BFVI_ABL(kAblFence) != 0);
       }
       if (lt == 0) {                                  // (later tiles: written during the previous tile's tail)
         store_a_split(tl + kFZ, zreg);
@@ -550,7 +552,6 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
             uint32_t bits = 0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
-            if (!BFVI_ABL(kAblBits)) p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
             // rows past the end contribute nothing to the weight gradients (their A operand is irrelevant: no output
             // row is stored for them).  Only the last tile has such rows: a warp-uniform test skips the 32 selects
             // elsewhere (and lets the FP16 conversions of the tile store and of the A operand share their work); the
@@ -559,7 +560,10 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
             }
-            if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, 2 * n_tiles, U2, u, v, lsu);
+            if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.h16, row0, 2 * n_tiles, U2, u, v, lsu, BFVI_ABL(kAblFence) != 0);
+            // AFTER the tile store: its proxy fence is a MEMBAR.ALL.CTA in SASS, which waits for every global access this
+            // thread has in flight — a store issued just before it cost the fence a round trip to L2 per unit
+            if (!BFVI_ABL(kAblBits)) p.relu_bits[((tile * U2 + u) * 2 + hf) * kTileRows + q * 32 + lane] = row_ok ? bits : 0u;   // coalesced
           }
           BFVI_DBG_ADD(2, t2);
           BFVI_DBG_T(t3);
@@ -826,8 +830,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
         patch_switch(q, elected, lsu);                // dz of the previous tile used the whole patch
         if (!BFVI_ABL(kAblTile16)) {
-          store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu);
-          store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 2 * n_tiles, 1, 0, rn, lsu);
+          store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu, BFVI_ABL(kAblFence) != 0);
+          store_tile_f16(pp, hp, q, lane, hf, elected, p.dnl16, row0, 2 * n_tiles, 1, 0, rn, lsu, BFVI_ABL(kAblFence) != 0);
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) { rg[j] = rn_tf32(rg[j]); rn[j] = rn_tf32(rn[j]); }
@@ -854,6 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       for (int u = 0; u < U2; ++u) {
         const int hb = u & 3;
         const uint32_t bits = bits_next;
+        // (issued here, a whole iteration ahead: after the tile store — behind its MEMBAR — measured 170 -> 196 us)
         if (u + 1 < U2 && !BFVI_ABL(kAblBits)) bits_next = __ldg(bits_p + (size_t)(u + 1) * 2 * kTileRows);
         mbar_wait(&d_full[hb], (par_d >> hb) & 1u);
         par_d ^= 1u << hb;
@@ -862,7 +867,7 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tmem_ld32(tl + kBHB + hb * 64, v);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? v[j] : 0.f;
-        if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, 2 * n_tiles, U2, u, v, lsu);
+        if (!BFVI_ABL(kAblTile16)) store_tile_f16(pp, hp, q, lane, hf, elected, p.dh16, row0, 2 * n_tiles, U2, u, v, lsu, BFVI_ABL(kAblFence) != 0);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = rn_tf32(v[j]);
         tmem_st32(tl + kBHB + hb * 64, v);
