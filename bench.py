@@ -1,7 +1,7 @@
 """bench.py — BFVI ELBO fwd+bwd sequence-timesteps/sec (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1]
-                    [--batch B] [--scaling weak|strong] [--precision tf32|tf32x3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1|c5]
+                    [--batch B] [--scaling weak|strong] [--precision fused|tf32|tf32x3]
 
 One "step" = MultiDMM.step(...) + (loss / sum(lengths)).backward() exactly as
 trainer.py:237-243 drives it, on one batch of synthetic data of the named shape.
@@ -14,18 +14,23 @@ Workloads (BASELINE.json `configs`, made concrete in SURVEY.md §8d):
                batch actually timed is stated in config.workload.
   c2           spirals model (M=2, D=1, Z=5, H=20), T=100, B=4096 per GPU, 50 % uniformly missing + burst.
   c1           spirals defaults (spirals.py:31-50): T=100, B=100, burst_delete(0.1).
+  c5           inference only (BASELINE configs[4]): MultiDMM.forward as Trainer.evaluate calls it (fsmooth, MAP
+               estimate, 25 particles in the filtering pass) on the C3-dims model, T=1000, B=1024 per GPU;
+               metric bfvi_forward_seq_timesteps_per_sec (forward only), ranks run independent shards.
 One NCCL all-reduce of the flat gradient per step for N>1 (no collective inside the step).
 
 Printed JSON (one line, rank 0): value = device-timed throughput with inputs resident in HBM; e2e = the same
 through the public API from PINNED HOST buffers (H2D of every step's inputs and targets and a D2H read of
 every step's loss inside the timed region; the loss of step i is read while step i+1 runs); roofline =
 algorithmic FLOPs / measured time against the measured tensor peak (c3) or the FP32-FFMA
-bound of the dominant kernel (c2/c1); cpu_baseline = the oracle port of the reference timed on this box's
-host cores on a bounded sample.
+bound of the dominant kernel (c2/c1); cpu_baseline = the reference itself (byte-compiled from the unmodified
+sources into oracle/_ref by oracle/build_ref.py; kind "reference") timed on this box's host cores on a bounded
+sample — the oracle port (kind "port") only where oracle/_ref is absent.
 
---impl reference: the reference algorithm (oracle/bfvi_oracle.py, a PyTorch-CPU port pinned against the
-unmodified reference; the Python reference itself cannot travel to the GPU box) on all host cores, on a
-bounded sample of the SAME workload; it prints the same `config` object as our arm.
+--impl reference: the reference's own MultiDMM.step + backward (oracle/_ref: sourceless bytecode of the unmodified
+reference, which travels to the GPU box; falls back to the pinned PyTorch-CPU port oracle/bfvi_oracle.py where that
+directory is absent) on all host cores, on a bounded sample of the SAME workload; it prints the same `config`
+object as our arm.
 """
 import argparse
 import ctypes as C
@@ -139,7 +144,13 @@ C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 2048
               'Philox noise (BASELINE names global batch 65536 = 8192 per GPU on 8 B200; the per-GPU batch is cut to '
               'keep a 25-step run within minutes: a step of 8192 x 1000 takes ~20 s; --batch 8192 runs the full shard, '
               'same code path: the step walks the batch in tiles)', (24, 100))
-WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3}
+# C5 (BASELINE configs[4]): inference-only reconstruction sweep point — forward(), fsmooth, MAP estimate, K particles in the
+# filtering pass — on the C3-dims model; metric = seq-timesteps/s of forward (NOT the fwd+bwd training metric)
+C5 = Workload('c5', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 1024, make_c3_batch, 1.0 / (16 * 8),
+              'C5: inference-only forward (fsmooth, sample=False, flt_particles=25) of the scaled MDMM, M=8 D=16 Z=64 H=512, '
+              'T=1000, B=%(B)d per GPU, N(0,1) data, Philox noise', (24, 100))
+WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3, 'c5': C5}
+METRIC_FORWARD = 'bfvi_forward_seq_timesteps_per_sec'
 
 
 # ----------------------------------------------------------------------------
@@ -248,6 +259,14 @@ def reference_step_time(wl, b_dim, t_max, steps, warmup, threads):
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
+        if wl.key == 'c5':                           # Trainer.evaluate's call (trainer.py:294-296)
+            model.eval()
+            with torch.no_grad():
+                model(inputs, lengths=lengths, sample=False, flt_particles=wl.k_train)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+            continue
         loss = model.step(inputs, mask, KLD_MULT, rec, targets=targets, lengths=lengths,
                           train_particles=wl.k_train, match_particles=wl.k_match)
         (loss / sum(lengths)).backward()
@@ -283,7 +302,7 @@ def run_reference(args, wl):
                if kind == 'reference' else 'oracle port of the reference', cores, wl.key.upper(), b_ref, t_ref,
                wl.k_train, args.warmup, args.steps))
     print(json.dumps({
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'impl': 'reference', 'metric': METRIC_FORWARD if wl.key == 'c5' else METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': sec * 1e3,
         'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'fp32',
         'data': 'synthetic', 'config': config_of(wl, b_dim, world, args.scaling),
@@ -346,6 +365,8 @@ def main():
     large = wl.key == 'c3'
     if large:
         model.precision = args.precision
+    if wl.key == 'c5':
+        return run_inference(args, wl, model, dev, rank, local_rank, world, dist)
     b_dim = per_gpu_batch(args, wl, world)
     t_max = wl.t_max
     inputs_h, targets_h, mask_h, lengths = wl.make(b_dim, t_max, (1234 if large else 1) + rank)
@@ -508,6 +529,96 @@ def main():
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_inference(args, wl, model, dev, rank, local_rank, world, dist):
+    """--workload c5: MultiDMM.forward (models/dmm.py:420-494 as Trainer.evaluate calls it) on one batch per step;
+    ranks run independent shards (no collective on this path)."""
+    from multimodal_dmm_b200 import _lib
+    model.eval()
+    model.precision = args.precision
+    b_dim, t_max = per_gpu_batch(args, wl, world), wl.t_max
+    inputs_h, _, _, lengths = wl.make(b_dim, t_max, 1234 + rank)
+    inputs_h = {k: v.pin_memory() for k, v in inputs_h.items()}
+    inputs_d = {k: v.to(dev) for k, v in inputs_h.items()}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def one_step(inp):
+        with torch.no_grad():
+            infer, prior, recon = model(inp, lengths=lengths, sample=False, flt_particles=wl.k_train)
+        return recon[wl.mods[0]][0].sum() + infer[0].sum()          # a scalar that depends on the whole result
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(inputs_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        one_step(inputs_d)
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    dispatch = _lib.load().last_dispatch()
+    # end to end: pinned host inputs -> H2D -> forward -> D2H of the result scalar, every step
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 5)
+    h2d = sum(v.numel() * 4 for v in inputs_h.values())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in inputs_h.items()}
+        float(one_step(inp))
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t[0].item(), t[1].item()
+    if rank != 0:
+        return
+    peaks = load_peaks()
+    m = len(wl.mods)
+    f_enc = sum(2 * wl.h * (d + 2 * wl.z) for d in wl.dims)
+    f_dec = sum(2 * wl.h * (wl.z + 2 * d) for d in wl.dims)
+    flops_per_seq_ts = f_enc + (wl.k_train + 1) * wl.f_gtf + f_dec        # SURVEY 8d, C5
+    seq_ts = b_dim * t_max * world
+    peak = float(peaks.get('bf16_tflops_sustained', 1400.0))
+    ach = flops_per_seq_ts * b_dim * t_max / (ms * 1e-3) / 1e12
+    probe = gtf_kernel_rooflines(model, wl, b_dim * wl.k_train, peaks)
+    dom = probe['gtf_fwd_kernel'] if probe else None
+    # launches: per present modality prep + 2 GEMM launches + softplus; per pass T step kernels + (T - 1) transitions
+    # (+ 2 pack launches per direction); per decoder 2 GEMM launches + softplus
+    launches = (m * 4 + 2 * (2 * t_max - 1) + 4 + m * 3) * args.steps
+    roofline = None if dom is None else {
+        'bound': 'tensor', 'kernel': 'gtf_fwd_kernel (fused transition forward of the K-particle filtering pass)',
+        'achieved': dom['achieved'], 'peak': dom['peak'], 'unit': 'TFLOP/s', 'frac': dom['frac'], 'traffic': None,
+        'ms_per_launch': dom['ms'], 'rows_per_launch': b_dim * wl.k_train, 'peak_source': dom['peak_source'],
+        'whole_step': {'achieved': ach, 'peak': peak, 'frac': ach / peak, 'algorithmic_flops_per_seq_ts': flops_per_seq_ts}}
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        b_ref, t_ref = wl.ref_sample
+        sec, n_ts, kind = cpu_step_time(wl, b_ref, t_ref, 3, 1, cores)
+        cpu_baseline = {'value': n_ts / sec, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                        'sample': 'forward() of the C5 workload at B=%d, T=%d on %d torch threads, 1 warm-up + 3 timed' %
+                                  (b_ref, t_ref, cores)}
+    print(json.dumps({
+        'metric': METRIC_FORWARD, 'value': seq_ts / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+        'dtype': 'fp16x3 split forward (fp32-class), fp32 accumulate' if args.precision == 'fused' else args.precision,
+        'data': 'synthetic', 'config': config_of(wl, b_dim, world, args.scaling), 'clocks': clocks,
+        'e2e': {'value': seq_ts / (ms_e2e * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': launches, 'roofline': roofline, 'kernel_probe': probe, 'dispatch': dispatch,
+        'cpu_baseline': cpu_baseline}))
 
 
 def gtf_kernel_rooflines(model, wl, rows, peaks):
