@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define BFVI_VERSION 120 /* 0.2.0: fused on-chip GTF kernels, training precision modes, batch tiles, bfvi_sizeof / bfvi_last_dispatch */
+#define BFVI_VERSION 130 /* 0.3.0: bfvi_mlp_* (encoder / decoder modules by pointer), fused transitions in bfvi_forward;
+                            0.2.0: fused on-chip GTF kernels, training precision modes, batch tiles, bfvi_sizeof / bfvi_last_dispatch */
 
 #define BFVI_MAX_MODS 16
 #define BFVI_MAX_SETS (BFVI_MAX_MODS + 1)

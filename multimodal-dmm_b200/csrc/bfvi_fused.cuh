@@ -248,6 +248,11 @@ __device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&r)[1
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+__device__ __forceinline__ float relu_nan(float x) {
+  float y;
+  asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void load_row32(const float* __restrict__ src, bool ok, float (&v)[32]) {
   if (ok) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
@@ -541,11 +546,12 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_fwd_kernel(const __grid_const
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const float4 bb = b4[cc];
-            float x;                                  // ReLU that keeps NaN like torch.relu (fmaxf would drop it)
-            x = fmaf(v[4 * cc], sc, bb.x); v[4 * cc] = x < 0.f ? 0.f : x;
-            x = fmaf(v[4 * cc + 1], sc, bb.y); v[4 * cc + 1] = x < 0.f ? 0.f : x;
-            x = fmaf(v[4 * cc + 2], sc, bb.z); v[4 * cc + 2] = x < 0.f ? 0.f : x;
-            x = fmaf(v[4 * cc + 3], sc, bb.w); v[4 * cc + 3] = x < 0.f ? 0.f : x;
+            // ReLU that keeps NaN like torch.relu (fmaxf would drop it): max.NaN is ONE instruction (FMNMX.NAN)
+            // where `x < 0 ? 0 : x` is a compare and a select
+            v[4 * cc] = relu_nan(fmaf(v[4 * cc], sc, bb.x));
+            v[4 * cc + 1] = relu_nan(fmaf(v[4 * cc + 1], sc, bb.y));
+            v[4 * cc + 2] = relu_nan(fmaf(v[4 * cc + 2], sc, bb.z));
+            v[4 * cc + 3] = relu_nan(fmaf(v[4 * cc + 3], sc, bb.w));
           }
           if (KEEP) {
             const int u = br * U + c;
