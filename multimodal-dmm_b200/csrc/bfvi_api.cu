@@ -706,10 +706,11 @@ bool fused_supported(int Z, int H) {
 struct FusedBufs {
   unsigned char* pack_fwd[2]; unsigned char* pack_bwd[2]; float* bias[2];      // per direction, shared by all passes
   void* h16; void* dh16; void* z16; void* dg16; void* dnl16; uint32_t* bits;   // per-row scratch (rows padded to 128)
+  unsigned* gstat;               // 8 words: [0..2] maxima of the head gradients (float bits), [4] the scale gtf_bwd_kernel chose
 };
 int64_t fused_rows_pad(int64_t rows) { return (rows + 127) / 128 * 128; }
 // per-row scratch bytes: hidden activations + their gradients as FP16 tiles, three Z-wide FP16 tiles, the ReLU bits
-struct FusedRowScratch { size_t h16, dh16, z16, dg16, dnl16, bits, total; };
+struct FusedRowScratch { size_t h16, dh16, z16, dg16, dnl16, bits, gstat, total; };
 FusedRowScratch fused_row_scratch(int H, int64_t rows) {
   const size_t rp = (size_t)fused_rows_pad(rows);
   FusedRowScratch r;
@@ -718,6 +719,7 @@ FusedRowScratch fused_row_scratch(int H, int64_t rows) {
   r.h16 = carve(rp * 2 * H * 2); r.dh16 = carve(rp * 2 * H * 2);
   r.z16 = carve(rp * 64 * 2); r.dg16 = carve(rp * 64 * 2); r.dnl16 = carve(rp * 64 * 2);
   r.bits = carve(rp * (2 * H / 64) * 2 * 4);
+  r.gstat = carve(256);
   r.total = cur;
   return r;
 }
@@ -735,6 +737,7 @@ void fused_carve_rows(char* base, int H, int64_t rows, FusedBufs* fb) {
   const FusedRowScratch r = fused_row_scratch(H, rows);
   fb->h16 = base + r.h16; fb->dh16 = base + r.dh16; fb->z16 = base + r.z16; fb->dg16 = base + r.dg16;
   fb->dnl16 = base + r.dnl16; fb->bits = (uint32_t*)(base + r.bits);
+  fb->gstat = (unsigned*)(base + r.gstat);
 }
 #ifndef BFVI_EMU
 int fused_smem_limit() { return 232448; }
@@ -754,7 +757,7 @@ int fused_pack(const bfvi_gtf_layout& g, const float* params, int dir, int H, co
   pp.w_non2 = params + g.nonlin2_w; pp.b_non2 = params + g.nonlin2_b; pp.w_std = params + g.std_w; pp.b_std = params + g.std_b;
   pp.fwd = fb.pack_fwd[dir]; pp.bwd = fb.pack_bwd[dir]; pp.bias = fb.bias[dir]; pp.H = H;
   auto ks = bfvi::fused::gtf_scale_kernel;
-  ks<<<dim3(6), dim3(256), 0, st>>>(pp);
+  ks<<<dim3(8), dim3(256), 0, st>>>(pp);
   auto k = bfvi::fused::pack_gtf_kernel;
   k<<<dim3((unsigned)bfvi::fused::pack_blocks(H)), dim3(256), 0, st>>>(pp);
   BFVI_CHECK_CUDA();
@@ -806,6 +809,11 @@ int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float
   bp.pack = fb.pack_bwd[dir]; bp.d_g = d_g; bp.d_nl = d_nl; bp.d_lin = d_lin; bp.relu_bits = fb.bits; bp.dz = dz;
   bp.dh16 = (__half*)fb.dh16; bp.dg16 = (__half*)fb.dg16; bp.dnl16 = (__half*)fb.dnl16;
   bp.R = rows; bp.H = H; bp.abl = fused_abl();
+  // power-of-two gradient scale from the maxima the producer of the head gradients keeps (BFVI_FUSED_GSCALE=0: none)
+  static const bool gscale_on = [] { const char* e = getenv("BFVI_FUSED_GSCALE"); return !e || atoi(e) != 0; }();
+  bp.gmax = gscale_on ? fb.gstat : nullptr;
+  bp.l1 = fb.bias[dir] + 2 * H + 4 * bfvi::fused::kZ + 6;
+  bp.gscale = reinterpret_cast<float*>(fb.gstat + 4);
   bp.n_stages = fused_stages(kFusedPatches);
   if (bp.n_stages < 4) return fail(BFVI_ERR_UNSUPPORTED, "fused transition kernel: no room for the weight ring");
   const size_t smem = (size_t)bp.n_stages * bfvi::fused::kBlockBytes + kFusedPatches + 1024;
@@ -835,6 +843,7 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
   prob(2, fb.h16, 0, fb.dg16, dw_gate2, 1, nullptr);        // dW_gate2 (Z, H) = d_g^T h1, computed as h1^T d_g
   prob(3, fb.h16, U, fb.dnl16, dw_non2, 1, nullptr);        // dW_nonlin2 (Z, H) = d_nl^T h3
   wp.n_problems = 4; wp.H = H; wp.abl = fused_abl();
+  wp.gscale = reinterpret_cast<const float*>(fb.gstat + 4);      // written by the fused_bwd launch before this one
   wp.n_groups = fused_rows_pad(rows) / 64;
   const int sms = num_sms() > 0 ? num_sms() : 1;
   const int tiles = 4 * (H / 128);
@@ -1156,6 +1165,12 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
   };
   if (fused) {                        // weights rounded to TF32 and laid out as shared-memory images ONCE per step
     const FusedBufs fb = fbufs();
+    {                                 // gradient-scale statistics of both contexts start at zero
+      FusedBufs fs;
+      fused_carve_rows(ws + pl_side.fused_rows, H, (int64_t)pl_side.R, &fs);
+      cudaMemsetAsync(fb.gstat, 0, 32, st);
+      if (!fonly) cudaMemsetAsync(fs.gstat, 0, 32, st);
+    }
     for (int d = 0; d < 2; ++d) { if (int rc = fused_pack(lay.trans[d], params, d, H, fb, st)) return rc; n_launch += 2; }
   }
 #endif
@@ -1246,6 +1261,9 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
       sp.gb_lin = grads + g.lin_b; sp.gb_nonlin2 = grads + g.nonlin2_b;
     }
     sp.dz = F(pl.dz); sp.dz2 = fused ? nullptr : F(pl.dz2);      // the fused backward writes the complete gradient
+#ifndef BFVI_EMU
+    sp.gmax = fused ? fbufs().gstat : nullptr;                   // maxima of the head gradients for the FP16 tile scale
+#endif
     return sp;
   };
   // particles of step i_src as GEMM input rows (+ transposed copy)
@@ -2616,6 +2634,7 @@ int bfvi_gtf_probe(const bfvi_model* m, const float* params, int32_t direction, 
   float* o[5];
   for (int i = 0; i < 5; ++i) o[i] = scratch_rows + (size_t)i * n_rows * 64;
   if (int rc = fused_pack(lay.trans[direction], params, direction, H, fb, st)) return rc;
+  cudaMemsetAsync(fb.gstat, 0, 32, st);             // no gradient statistics in the probe: scale 1
   // operands of the later kernels: one KEEP forward (whose heads double as head gradients: any finite values do)
   if (int rc = fused_fwd(fb, direction, H, z, n_rows, o[0], o[1], o[2], o[3], true, st)) return rc;
   if (which >= 3) { if (int rc = fused_bwd(fb, direction, H, o[0], o[1], o[2], n_rows, o[4], st)) return rc; }
@@ -2672,6 +2691,9 @@ int bfvi_gtf_bwd(const bfvi_model* m, const float* params, float* grads, int32_t
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_lin, z, n_rows, grads + g.lin_w, grads + g.lin_b);
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_gate_pre, nullptr, n_rows, nullptr, grads + g.gate2_b);
   gtf_small_wgrad_kernel<<<dim3(blocks), dim3(256), 0, st>>>(d_nl, nullptr, n_rows, nullptr, grads + g.nonlin2_b);
+  // maxima of the head gradients for the FP16 tile scale (inside a step bwd_rows_kernel keeps them)
+  cudaMemsetAsync(fb.gstat, 0, 32, st);
+  bfvi::fused::absmax2_kernel<<<dim3((unsigned)grid_for(n_rows * 64, 256, 8)), dim3(256), 0, st>>>(d_gate_pre, d_nl, n_rows * 64, fb.gstat);
   BFVI_CHECK_CUDA();
   if (int rc = fused_bwd(fb, direction, m->h_dim, d_gate_pre, d_nl, d_lin, n_rows, d_z, st)) return rc;
   unswz64_kernel<<<dim3((unsigned)grid_for(n_rows, 8, 8)), dim3(256), 0, st>>>(d_z, n_rows);

@@ -119,9 +119,38 @@ using tc::umma_desc_sw128; using tc::umma_idesc_tf32; using tc::umma_tf32_ts; us
 using tc::fence_async_smem;
 
 // power-of-two scale of one layer: max |w| * s in [2^13, 2^14)
+// blocks 0..5: power-of-two scale of one layer; blocks 6, 7: column L1 norms that bound what a head gradient can become
+// downstream (slot 6: max_h sum_zc |W2[zc, h]| over both hidden -> head layers bounds |dh| / max|d_head|; slot 7:
+// max_j sum_i |W_std[i, j]| bounds the std path's share of d_nl / max|d_as|) — the input-gradient kernel scales its
+// operands by a power of two derived from them so that the FP16 weight-gradient tiles use the FP16 range whatever the
+// scale of the loss (tools/probe_f16_range.py)
 __global__ void __launch_bounds__(256) gtf_scale_kernel(const __grid_constant__ PackParams p) {
   __shared__ float red[256];
   const int H = p.H, layer = blockIdx.x;
+  if (layer >= 6) {
+    float m = 0.f;
+    if (layer == 6) {
+      for (int h = threadIdx.x; h < H; h += blockDim.x) {
+        float sg = 0.f, sn = 0.f;
+        for (int zc = 0; zc < kZ; ++zc) { sg += fabsf(p.w_gate2[(size_t)zc * H + h]); sn += fabsf(p.w_non2[(size_t)zc * H + h]); }
+        m = fmaxf(m, fmaxf(sg, sn));
+      }
+    } else {
+      for (int j = threadIdx.x; j < kZ; j += blockDim.x) {
+        float sa = 0.f;
+        for (int i = 0; i < kZ; ++i) sa += fabsf(p.w_std[i * kZ + j]);
+        m = fmaxf(m, sa);
+      }
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if ((int)threadIdx.x < o) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + o]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) p.bias[2 * H + 4 * kZ + layer] = red[0];
+    return;
+  }
   const float* w = layer == 0 ? p.w_gate0 : layer == 1 ? p.w_non0 : layer == 2 ? p.w_gate2 : layer == 3 ? p.w_non2
                    : layer == 4 ? p.w_lin : p.w_std;
   const int n = layer < 4 ? H * kZ : kZ * kZ;
@@ -192,6 +221,22 @@ __global__ void __launch_bounds__(256) pack_gtf_kernel(const __grid_constant__ P
       p.bias[2 * H + i] = p.b_gate2[i]; p.bias[2 * H + kZ + i] = p.b_non2[i];
       p.bias[2 * H + 2 * kZ + i] = p.b_lin[i]; p.bias[2 * H + 3 * kZ + i] = p.b_std[i];
     }
+  }
+}
+
+// maxima of |a| and |b| over n floats as float bit patterns (stand-alone entries: inside a step bwd_rows_kernel keeps them)
+__global__ void __launch_bounds__(256) absmax2_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
+                                                      unsigned* __restrict__ out) {
+  float ma = 0.f, mb = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    ma = fmaxf(ma, fabsf(a[i])); mb = fmaxf(mb, fabsf(b[i]));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (__float_as_uint(ma) > *(volatile unsigned*)(out + 0)) atomicMax(out + 0, __float_as_uint(ma));
+    if (__float_as_uint(mb) > *(volatile unsigned*)(out + 1)) atomicMax(out + 1, __float_as_uint(mb));
   }
 }
 
@@ -766,6 +811,9 @@ struct BwdParams {
   float* dz;                     // (R, 64) out
   __half* dh16;                  // masked hidden gradients, FP16 tiles [atom pair][row group][2 atoms]
   __half* dg16; __half* dnl16;   // FP16 tiles of d_g / d_nl [row group][1 atom]
+  const unsigned* gmax;          // nullable: maxima [|d_g|, |d_nl| before the std path, |d_as|] of the launch's head gradients (float bits)
+  const float* l1;               // 2 floats: the pack's column L1 norms (gtf_scale_kernel slots 6, 7)
+  float* gscale;                 // out (nullable): the power-of-two scale s the FP16 tiles carry; wgrad16_kernel divides by it
   int64_t R;
   int H;
   int n_stages;
@@ -808,6 +856,26 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tb = tmem_base_s;
+  // Power-of-two scale of this launch's gradients: head gradients (and with them the hidden gradients the MMAs produce,
+  // the FP16 tiles of both, and dz) are multiplied by s so that the largest hidden gradient this launch can produce sits
+  // at ~2^14; dz is divided by s on the way out, the weight-gradient kernel divides its accumulators.  Exact (a power of
+  // two), and the TF32 operands have exponent range to spare.  Without it FP16 tiles of gradients below ~1e-4 went
+  // subnormal: 3e-3 error at 2^-14 of O(1), 5e-2 at 2^-18 (tools/probe_f16_range.py).
+  float gs = 1.f;
+  if (p.gmax != nullptr) {
+    const float mg = __uint_as_float(p.gmax[0]), mn = __uint_as_float(p.gmax[1]), ma = __uint_as_float(p.gmax[2]);
+    const float m_head = fmaxf(mg, fmaf(ma, p.l1[1], mn));
+    const float m = fmaxf(m_head, m_head * p.l1[0]);
+    if (m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);                                  // m = f * 2^e, f in [0.5, 1)
+      e = 14 - e;
+      e = e < -60 ? -60 : (e > 60 ? 60 : e);
+      gs = ldexpf(1.f, e);
+    }
+  }
+  const float inv_gs = 1.f / gs;
+  if (p.gscale != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.gscale[0] = gs;
 
   if (warp < kRowWarps) {
     const int q = warp & 3, hf = warp >> 2;
@@ -834,6 +902,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
       {
         float v[32];                                  // d_lin rows: in flight while the FP16 tiles below are written
         load_row32(p.d_lin + row * kZ + hf * 32, row_ok, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { rg[j] *= gs; rn[j] *= gs; v[j] *= gs; }
         patch_switch(q, elected, lsu);                // dz of the previous tile used the whole patch
         if (!BFVI_ABL(kAblTile16)) {
           store_tile_f16(pp, hp, q, lane, hf, elected, p.dg16, row0, 2 * n_tiles, 1, 0, rg, lsu, BFVI_ABL(kAblFence) != 0);
@@ -890,6 +960,8 @@ __global__ void __launch_bounds__(kThreads, 1) gtf_bwd_kernel(const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&dz_empty);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= inv_gs;
         patch_switch(q, elected, lsu);                // FP16 tile slots and fp32 row slots share the patch
         if (!BFVI_ABL(kAblRows)) store_rows_f32(pp, fs, q, lane, hf, elected, p.dz + row0 * kZ, n_valid, v, lsu);
       }
@@ -991,6 +1063,7 @@ struct Wgrad16Params {
   int n_slices;
   int n_stages;
   int abl;                     // development: ablation mask, 0 in the product
+  const float* gscale;         // nullable: the scale the gradient tiles carry (gtf_bwd_kernel); accumulators are divided by it
 };
 constexpr int kWgStageBytes = 3 * kAtomBytes;        // X atoms (2) + Y atom
 constexpr int kWgThreads = 6 * 32;                   // 4 epilogue / column-sum warps, MMA warp, loader warp
@@ -1070,6 +1143,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad16_kernel(const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty);
       if (g1 > g0 && !BFVI_ABL(kAblRows)) {
+        const float inv = p.gscale != nullptr ? 1.f / p.gscale[0] : 1.f;      // a power of two: exact
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { v0[j] *= inv; v1[j] *= inv; }
+        if (pr.bias != nullptr) vb[0] *= inv;
         if (pr.transposed) {                         // out (Z, H): lanes = consecutive h -> coalesced per column
 #pragma unroll
           for (int j = 0; j < 32; ++j) atomicAdd(pr.out + (size_t)j * p.H + h, v0[j]);

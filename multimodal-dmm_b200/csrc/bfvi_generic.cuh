@@ -94,6 +94,10 @@ struct StepParams {
   float* gb_std; float* gb_gate2; float* gb_lin; float* gb_nonlin2;   // bias gradient slots (Z each)
   const float* dz;             // (R, Z) gradient at the particles of the previous step
   const float* dz2;            // nullable second partial of the same gradient (summed by bwd_carry_kernel)
+  // fused path (nullable): running maxima [|d_g|, |d_nl| (before the std path), |d_as|] of this time step's head gradients as
+  // float bit patterns: the fused input-gradient kernel derives the power-of-two scale of its FP16 operand tiles from them;
+  // bwd_rows_kernel raises them, bwd_carry_kernel (the last kernel of the time step) clears them
+  unsigned* gmax;
 };
 
 __device__ __forceinline__ int gen_pass_time(int i, int T, int direction) {
@@ -479,6 +483,7 @@ __global__ void __launch_bounds__(kRowsZ * kRowsSplit) bwd_rows_kernel(const __g
   const int64_t r1 = r0 + kRowsPerBlock < p.R ? r0 + kRowsPerBlock : p.R;
   constexpr int kPer = kRowsPerBlock / kRowsSplit;
   float d_gm = 0.f, d_gs = 0.f, b_s = 0.f, b_g = 0.f, b_l = 0.f, b_n = 0.f;
+  float m_g = 0.f, m_n = 0.f, m_a = 0.f;
   if (active) {
     const float gm = p.z0_mean[zi], gs = expf(p.z0_log_std[zi]) + p.min_std;
     const float inv_k = 1.f / (float)K;
@@ -506,6 +511,18 @@ __global__ void __launch_bounds__(kRowsZ * kRowsSplit) bwd_rows_kernel(const __g
       const int col = ((int)(r - r0) ^ tx) & (kRowsPerBlock - 1);
       tile[0][tx][col] = d_as; tile[1][tx][col] = d_g; tile[2][tx][col] = d_lin;
       b_s += d_as; b_g += d_g; b_l += d_lin; b_n += d_nl;
+      m_g = fmaxf(m_g, fabsf(d_g)); m_n = fmaxf(m_n, fabsf(d_nl)); m_a = fmaxf(m_a, fabsf(d_as));
+    }
+  }
+  if (p.gmax != nullptr) {                       // (NaN never wins fmaxf: a NaN gradient leaves the maxima alone)
+    const float mm[3] = {m_g, m_n, m_a};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float m = mm[k];
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      // test before the atomic: after the first blocks almost nobody raises the maximum (same-address atomics serialise)
+      if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && __float_as_uint(m) > *(volatile unsigned*)(p.gmax + k))
+        atomicMax(p.gmax + k, __float_as_uint(m));
     }
   }
   part[ty][0][tx] = b_s; part[ty][1][tx] = b_g; part[ty][2][tx] = b_l; part[ty][3][tx] = b_n;
@@ -546,6 +563,7 @@ __global__ void __launch_bounds__(128) bwd_carry_kernel(const __grid_constant__ 
   const int t = gen_pass_time(i_prev, T, a.direction);
   const bool sampled = gen_samples(a, i_prev);
   const int64_t n_chains = (int64_t)a.S * B;
+  if (p.gmax != nullptr && blockIdx.x == 0 && threadIdx.x < 3) p.gmax[threadIdx.x] = 0u;   // next time step starts afresh
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chains * Z;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int zi = (int)(idx % Z);

@@ -256,6 +256,7 @@ static inline float atomicAdd(float* a, float v) { float o = *a; *a = o + v; ret
 static inline double atomicAdd(double* a, double v) { double o = *a; *a = o + v; return o; }
 static inline int atomicAdd(int* a, int v) { int o = *a; *a = o + v; return o; }
 static inline unsigned atomicAdd(unsigned* a, unsigned v) { unsigned o = *a; *a = o + v; return o; }
+static inline unsigned atomicMax(unsigned* a, unsigned v) { unsigned o = *a; *a = o > v ? o : v; return o; }
 
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 #define __expf(x) expf(x)
