@@ -1034,6 +1034,9 @@ static bool step4_ok(const bfvi::gen::StepParams& sp) {
 // One batch tile of a step that walks its batch in tiles (step_large_tiled): the loss accumulator and the mask count
 // live outside the tile's workspace, the gradient buffer is cleared by the first tile only, the prior-matching term
 // (linear in the GLOBAL mask count, models/dmm.py:541-545) is added by the first tile, the loss is finalised by the last.
+// block width of head_kernel (thread = output column, 32 rows per block): the narrowest warp multiple that covers D, so a
+// 16-wide decoder head does not idle 112 of 128 threads
+inline int head_block(int D) { return D <= 32 ? 32 : (D <= 64 ? 64 : 128); }
 struct TileCtx { bool first, last; double* acc; const float* count; bool match; int lane; };
 
 // fonly != null: run only z_filter forward (fonly_backward = false) or backward on `fonly`
@@ -1509,8 +1512,9 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
             hp.gb_mean = with_grad ? grads + l.mean_b : F(pl.dz); hp.gb_std = with_grad ? grads + l.std_b : F(pl.dz);
             hp.n_rows = n; hp.D = D; hp.weight = mult * a->rec_mults[i]; hp.loss_acc = acc;
             auto kh = bfvi::gen::head_kernel;
+            const int hb = head_block(D);             // thread = column: narrow heads get narrow blocks (D = 16: 32 threads)
             BFVI_LAUNCH(kh, dim3((unsigned)((n + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                                 (unsigned)((D + 127) / 128)), dim3(128), 0, st, hp);
+                                 (unsigned)((D + hb - 1) / hb)), dim3(hb), 0, st, hp);
             ++n_launch;
             if (!with_grad) continue;
             if (int rc = dgrad(F(pl.dmean), l.mean_w, F(pl.dhd), nullptr, n, D, H, false, F(pl.hdec), grads + l.in_to_h_b)) return rc;
@@ -1612,8 +1616,9 @@ int step_large(const bfvi_model* m, const float* params, float* grads, const bfv
           hp.gb_mean = grads + l.mean_b; hp.gb_std = grads + l.std_b;
           hp.n_rows = n; hp.D = Z; hp.weight = 1.f;
           auto kh = bfvi::gen::head_kernel;
+          const int hb = head_block(Z);
           BFVI_LAUNCH(kh, dim3((unsigned)((n + bfvi::gen::kRowsPerBlock - 1) / bfvi::gen::kRowsPerBlock),
-                               (unsigned)((Z + 127) / 128)), dim3(128), 0, st, hp);
+                               (unsigned)((Z + hb - 1) / hb)), dim3(hb), 0, st, hp);
           ++n_launch;
           if (int rc = dgrad(dm, l.mean_w, F(pl.dhd), nullptr, n, Z, H, false, henc, grads + l.in_to_h_b)) return rc;
           if (int rc = wgrad(F(pl.dmeanT), hencT, n, Z, H, l.mean_w)) return rc;
