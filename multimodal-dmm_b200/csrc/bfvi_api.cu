@@ -94,6 +94,28 @@ bfvi::MlpOffsets mlp_offsets(const bfvi_mlp_layout& l) {
   return o;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) costs microseconds of host time per call; a step makes ~35 000 launches of
+// the large-dim kernels, so the attribute is raised only when a kernel needs more than it was last given (per host thread
+// and device)
+#ifndef BFVI_EMU
+template <typename K>
+inline void ensure_dyn_smem(K kernel, size_t bytes) {
+  struct Slot { const void* fn; int dev; size_t have; };
+  static thread_local Slot tab[64];
+  static thread_local int n_slots = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* fn = (const void*)kernel;
+  Slot* sl = nullptr;
+  for (int i = 0; i < n_slots; ++i)
+    if (tab[i].fn == fn && tab[i].dev == dev) { sl = &tab[i]; break; }
+  if (sl == nullptr && n_slots < 64) { sl = &tab[n_slots++]; sl->fn = fn; sl->dev = dev; sl->have = 0; }
+  if (sl == nullptr || bytes > sl->have) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (sl != nullptr) sl->have = bytes;
+  }
+}
+#endif
 int num_sms() {
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -596,7 +618,7 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
         if (ts_stages < 2) ts_stages = 2;
         const size_t smem_ts = bfvi::tc::gemm_ts_smem_bytes<BN, SPLIT>(ts_stages, bulk);
         auto kt = bfvi::tc::gemm_tf32_ts_kernel<BN, SPLIT, true>;
-        cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
+        ensure_dyn_smem(kt, smem_ts);
         kt<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem_ts, st>>>(grp, ts_stages, lag_env);
         BFVI_CHECK_CUDA();
         return BFVI_OK;
@@ -604,7 +626,7 @@ int launch_gemm_group(const bfvi::tc::GemmParams* gps, int n, cudaStream_t st) {
     }
     const size_t smem = bfvi::tc::gemm_p_smem_bytes<BN, SPLIT>(stages);
     auto k = vec ? bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, true> : bfvi::tc::gemm_tf32_p_kernel<BN, SPLIT, false>;
-    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ensure_dyn_smem(k, smem);
     k<<<dim3((unsigned)(total < slots ? total : slots)), dim3(bfvi::tc::kThreadsPhost), smem, st>>>(grp, stages, lag_env);
   }
 #endif
@@ -783,7 +805,7 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
   long long* dbg_dev = nullptr;
   if (dbg) { cudaMalloc(&dbg_dev, 32 * sizeof(long long)); cudaMemsetAsync(dbg_dev, 0, 32 * sizeof(long long), st); fp.dbg = dbg_dev; }
   auto k = keep ? bfvi::fused::gtf_fwd_kernel<true> : bfvi::fused::gtf_fwd_kernel<false>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_dyn_smem(k, smem);
   k<<<dim3(grid), dim3(bfvi::fused::kThreads), smem, st>>>(fp);
   note_dispatch("gtf_fwd_fused%s f16x3 stages=%d", keep ? "<keep>" : "", fp.n_stages);
   if (dbg) {                           // development: where do the cycles of CTA 0 go?
@@ -803,7 +825,8 @@ int fused_fwd(const FusedBufs& fb, int dir, int H, const float* z, int64_t rows,
 // input gradient dz of one transition (the KEEP forward of the same rows must have run)
 int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float* d_nl, const float* d_lin, int64_t rows,
               float* dz, cudaStream_t st) {
-  if (getenv("BFVI_DBG_SKIP_BWD")) return BFVI_OK;           // development: bisect a hang
+  static const bool skip_bwd = getenv("BFVI_DBG_SKIP_BWD") != nullptr;      // development: bisect a hang
+  if (skip_bwd) return BFVI_OK;
   bfvi::fused::BwdParams bp;
   memset(&bp, 0, sizeof(bp));
   bp.pack = fb.pack_bwd[dir]; bp.d_g = d_g; bp.d_nl = d_nl; bp.d_lin = d_lin; bp.relu_bits = fb.bits; bp.dz = dz;
@@ -820,7 +843,7 @@ int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float
   const int64_t tiles = (rows + 127) / 128;
   const int sms = num_sms() > 0 ? num_sms() : 1;
   auto k = bfvi::fused::gtf_bwd_kernel;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_dyn_smem(k, smem);
   k<<<dim3((unsigned)(tiles < sms ? tiles : sms)), dim3(bfvi::fused::kThreads), smem, st>>>(bp);
   note_dispatch("gtf_bwd_fused tf32 stages=%d", bp.n_stages);
   BFVI_CHECK_CUDA();
@@ -830,7 +853,8 @@ int fused_bwd(const FusedBufs& fb, int dir, int H, const float* d_g, const float
 // fused_fwd(keep) / fused_bwd
 int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float* dw_non0, float* dw_gate2, float* dw_non2,
                 float* gb_gate0, float* gb_non0, cudaStream_t st) {
-  if (getenv("BFVI_DBG_SKIP_WGRAD")) return BFVI_OK;         // development: bisect a hang
+  static const bool skip_wgrad = getenv("BFVI_DBG_SKIP_WGRAD") != nullptr;  // development: bisect a hang
+  if (skip_wgrad) return BFVI_OK;
   bfvi::fused::Wgrad16Params wp;
   memset(&wp, 0, sizeof(wp));
   const int U = H / 64;
@@ -857,7 +881,7 @@ int fused_wgrad(const FusedBufs& fb, int H, int64_t rows, float* dw_gate0, float
   const size_t smem = (size_t)wp.n_stages * bfvi::fused::kWgStageBytes + bfvi::fused::kAtomBytes + 1024;
   const int items = tiles * wp.n_slices;
   auto k = bfvi::fused::wgrad16_kernel;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ensure_dyn_smem(k, smem);
   k<<<dim3((unsigned)(items < sms ? items : sms)), dim3(bfvi::fused::kWgThreads), smem, st>>>(wp);
   note_dispatch("wgrad16 f16-mn");
   BFVI_CHECK_CUDA();
