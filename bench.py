@@ -1,6 +1,6 @@
 """bench.py — BFVI ELBO fwd+bwd sequence-timesteps/sec (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1|c5]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c3|c2|c1|c4|c5]
                     [--batch B] [--scaling weak|strong] [--precision fused|tf32|tf32x3]
 
 One "step" = MultiDMM.step(...) + (loss / sum(lengths)).backward() exactly as
@@ -14,6 +14,9 @@ Workloads (BASELINE.json `configs`, made concrete in SURVEY.md §8d):
                batch actually timed is stated in config.workload.
   c2           spirals model (M=2, D=1, Z=5, H=20), T=100, B=4096 per GPU, 50 % uniformly missing + burst.
   c1           spirals defaults (spirals.py:31-50): T=100, B=100, burst_delete(0.1).
+  c4           Weizmann-shaped video model (BASELINE configs[3]): conv image encoders / decoders as custom torch modules,
+               Bernoulli + Categorical likelihoods, dropped modalities, Z=H=256, T=25, B=25 — an auxiliary line through
+               the composed path (the conv modules are cuDNN; no roofline object).
   c5           inference only (BASELINE configs[4]): MultiDMM.forward as Trainer.evaluate calls it (fsmooth, MAP
                estimate, 25 particles in the filtering pass) on the C3-dims model, T=1000, B=1024 per GPU;
                metric bfvi_forward_seq_timesteps_per_sec (forward only), ranks run independent shards.
@@ -149,7 +152,44 @@ C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 2048
 C5 = Workload('c5', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 1024, make_c3_batch, 1.0 / (16 * 8),
               'C5: inference-only forward (fsmooth, sample=False, flt_particles=25) of the scaled MDMM, M=8 D=16 Z=64 H=512, '
               'T=1000, B=%(B)d per GPU, N(0,1) data, Philox noise', (24, 100))
-WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3, 'c5': C5}
+# C4 (BASELINE configs[3]): Weizmann-shaped video model — conv image encoders / decoders (torch / cuDNN modules passed as
+# custom encoders= / decoders=, weizmann.py:53-77), Bernoulli + Categorical likelihoods, dropped modalities — through the
+# composed path: our temporal core (fused z_filter), likelihood kernels and categorical encoder / decoder kernels around it
+C4_MODS = ['video', 'mask', 'action']
+C4_DIMS = {'video': (3, 64, 64), 'mask': (1, 64, 64), 'action': 10}
+C4_DISTS = {'video': 'Bernoulli', 'mask': 'Bernoulli', 'action': 'Categorical'}
+C4_REC = {'video': 1.0, 'mask': 1.0, 'action': 10.0}
+
+
+def make_c4_batch(b_dim, t_max=25, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    targets = {'video': torch.rand(t_max, b_dim, 3, 64, 64, generator=g),
+               'mask': (torch.rand(t_max, b_dim, 1, 64, 64, generator=g) > 0.5).float(),
+               'action': torch.randint(0, 10, (t_max, b_dim, 1), generator=g).float()}
+    inputs = {'video': targets['video'].clone(),                       # mask and action are dropped (all NaN),
+              'mask': torch.full_like(targets['mask'], float('nan')),  # trainer.py:289-290
+              'action': torch.full_like(targets['action'], float('nan'))}
+    burst = int(0.2 * t_max)                                           # burst_delete(0.2) on the video
+    start = torch.randint(0, t_max, (b_dim,), generator=g)
+    for b in range(b_dim):
+        inputs['video'][start[b]:start[b] + burst, b] = float('nan')
+    return inputs, targets, torch.ones(t_max, b_dim, 1, dtype=torch.bool), [t_max] * b_dim
+
+
+def build_c4_model(models_pkg, device, z_dim=256, h_dim=256):
+    """Same construction as weizmann.py:53-77."""
+    c = models_pkg.common
+    enc = {'video': c.ImageEncoder(z_dim, True), 'mask': c.ImageEncoder(z_dim, True, n_channels=1)}
+    dec = {'video': c.ImageDecoder(z_dim), 'mask': c.ImageDecoder(z_dim, n_channels=1)}
+    return models_pkg.MultiDMM(C4_MODS, dims=[C4_DIMS[m] for m in C4_MODS], dists=[C4_DISTS[m] for m in C4_MODS],
+                               encoders=enc, decoders=dec, z_dim=z_dim, h_dim=h_dim, device=device)
+
+
+C4 = Workload('c4', C4_MODS, [3 * 64 * 64, 64 * 64, 10], 256, 256, 25, 25, make_c4_batch, 1.0,
+              'C4: Weizmann-shaped video BFVI step (video 3x64x64 + silhouette mask Bernoulli, 10-way action Categorical; conv '
+              'encoders / decoders as custom torch modules; mask and action dropped from the inputs, burst_delete(0.2) on the '
+              'video), Z=H=256, T=25, B=%(B)d per GPU, K=25, K_match=50', (8, 25))
+WORKLOADS = {'c1': C1, 'c2': C2, 'c3': C3, 'c4': C4, 'c5': C5}
 METRIC_FORWARD = 'bfvi_forward_seq_timesteps_per_sec'
 
 
@@ -252,9 +292,12 @@ def reference_step_time(wl, b_dim, t_max, steps, warmup, threads):
     ref_models = ref_shim.import_reference_models()
     torch.set_num_threads(threads)
     inputs, targets, mask, lengths = wl.make(b_dim, t_max, 1)
-    rec = {m: wl.rec for m in wl.mods}
+    rec = dict(C4_REC) if wl.key == 'c4' else {m: wl.rec for m in wl.mods}
     torch.manual_seed(1)
-    model = ref_models.MultiDMM(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, device=torch.device('cpu'))
+    if wl.key == 'c4':
+        model = build_c4_model(ref_models, torch.device('cpu'))
+    else:
+        model = ref_models.MultiDMM(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, device=torch.device('cpu'))
     model.train()
     times = []
     for i in range(warmup + steps):
@@ -361,6 +404,8 @@ def main():
 
     # ---- model + data (identical weights on every rank; per-rank data shard) ------
     torch.manual_seed(1)
+    if wl.key == 'c4':
+        return run_weizmann(args, wl, models, dev, rank, local_rank, world, dist)
     model = models.MultiDMM(wl.mods, wl.dims, h_dim=wl.h, z_dim=wl.z, device=dev).train()
     large = wl.key == 'c3'
     if large:
@@ -529,6 +574,93 @@ def main():
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_weizmann(args, wl, models, dev, rank, local_rank, world, dist):
+    """--workload c4: MultiDMM.step + backward of the Weizmann-shaped model through the composed path (custom conv modules
+    are torch / cuDNN; the temporal core, the Bernoulli / categorical likelihoods and the categorical encoder / decoder are
+    this library's kernels).  Data parallel like the other training workloads: one all-reduce of the gradients per step."""
+    from multimodal_dmm_b200 import _lib
+    model = build_c4_model(models, dev).train()
+    b_dim, t_max = per_gpu_batch(args, wl, world), wl.t_max
+    inputs_h, targets_h, mask_h, lengths = wl.make(b_dim, t_max, 1 + rank)
+    pin = lambda d: {k: v.pin_memory() for k, v in d.items()}
+    inputs_h, targets_h = pin(inputs_h), pin(targets_h)
+    mask_d = mask_h.to(dev)
+    inputs_d = {k: v.to(dev) for k, v in inputs_h.items()}
+    targets_d = {k: v.to(dev) for k, v in targets_h.items()}
+    n_global = float(sum(lengths) * world)
+    params = [p for p in model.parameters() if p.requires_grad]
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def one_step(inp, tgt):
+        loss = model.step(inp, mask_d, KLD_MULT, C4_REC, targets=tgt, lengths=lengths,
+                          train_particles=wl.k_train, match_particles=wl.k_match)
+        (loss / n_global).backward()
+        if dist is not None:                           # (custom modules keep their own .grad tensors: flatten, one all-reduce)
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+        for p in params:
+            p.grad = None
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_step(inputs_d, targets_d)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        one_step(inputs_d, targets_d)
+        ev[i][1].record()
+    barrier()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    dispatch = _lib.load().last_dispatch()
+    e2e_steps = args.e2e_steps if args.e2e_steps > 0 else min(args.steps, 5)
+    h2d = sum(v.numel() * 4 for v in inputs_h.values()) + sum(v.numel() * 4 for v in targets_h.values())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        inp = {k: v.to(dev, non_blocking=True) for k, v in inputs_h.items()}
+        tgt = {k: v.to(dev, non_blocking=True) for k, v in targets_h.items()}
+        float(one_step(inp, tgt).detach())
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t[0].item(), t[1].item()
+    if rank != 0:
+        return
+    seq_ts = b_dim * t_max * world
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        b_ref, t_ref = wl.ref_sample
+        r = reference_step_time(wl, b_ref, t_ref, 2, 1, cores)
+        if r is not None:
+            cpu_baseline = {'value': r[1] / r[0], 'unit': UNIT, 'cores': cores, 'kind': 'reference',
+                            'sample': "the reference's own MultiDMM.step + backward of the C4 model at B=%d, T=%d on %d torch "
+                                      'threads, 1 warm-up + 2 timed steps' % (b_ref, t_ref, cores)}
+    print(json.dumps({
+        'metric': METRIC, 'value': seq_ts / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
+        'dtype': 'fp32 conv modules (torch / cuDNN) around the tcgen05 temporal core (3xTF32, fp32-class)', 'data': 'synthetic',
+        'config': config_of(wl, b_dim, world, args.scaling), 'clocks': clocks,
+        'e2e': {'value': seq_ts / (ms_e2e * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
+                'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
+        'gpu_launches': None, 'roofline': None,
+        'note': 'auxiliary line: the conv encoders / decoders of this workload are library (cuDNN) code, SURVEY 8f-3; the temporal '
+                'core, the likelihood kernels and the categorical encoder / decoder are ours',
+        'dispatch': dispatch, 'cpu_baseline': cpu_baseline}))
 
 
 def run_inference(args, wl, model, dev, rank, local_rank, world, dist):
