@@ -527,8 +527,8 @@ def main():
         # rows ONE particle-pass time step launches: (1 + M) chain sets x batch tile x K particles
         tile = b_dim
         for d in dispatch:
-            if d.startswith('step:batch_tiles='):
-                tile = int(d.split('x')[-1])
+            if d.startswith('step:batch_tiles='):          # "step:batch_tiles=<n> x <sequences per tile> lanes=<l>"
+                tile = int(d.split('x')[-1].split()[0])
         rows = (1 + len(wl.mods)) * tile * wl.k_train
         kernel_probe = gtf_kernel_rooflines(model, wl, rows, peaks)
         dom = kernel_probe['gtf_fwd_kernel<keep>']
