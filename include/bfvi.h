@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define BFVI_VERSION 130 /* 0.3.0: bfvi_mlp_* (encoder / decoder modules by pointer), fused transitions in bfvi_forward;
+#define BFVI_VERSION 140 /* 0.4.0: image modules (bfvi_conv_*, bfvi_bn2d_*, bfvi_sigmoid_bwd, bfvi_chan_bias_grad);
+                            0.3.0: bfvi_mlp_* (encoder / decoder modules by pointer), fused transitions in bfvi_forward;
                             0.2.0: fused on-chip GTF kernels, training precision modes, batch tiles, bfvi_sizeof / bfvi_last_dispatch */
 
 #define BFVI_MAX_MODS 16
@@ -204,7 +205,7 @@ const char* bfvi_last_error(void);
  * handing the library a short struct (multimodal-dmm_b200/_lib.py does; INTEGRATION.md shows it). */
 enum {
   BFVI_STRUCT_MODEL = 0, BFVI_STRUCT_LAYOUT, BFVI_STRUCT_EXPERT, BFVI_STRUCT_NOISE, BFVI_STRUCT_FILTER_ARGS,
-  BFVI_STRUCT_STEP_ARGS, BFVI_STRUCT_FORWARD_ARGS
+  BFVI_STRUCT_STEP_ARGS, BFVI_STRUCT_FORWARD_ARGS, BFVI_STRUCT_CONV_GEOM
 };
 size_t bfvi_sizeof(int32_t which);
 
@@ -496,6 +497,49 @@ int bfvi_mlp_bwd(const bfvi_mlp_desc* desc, const bfvi_mlp_grads* grads, const f
 int bfvi_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                    float grad_scale, float max_norm, float* norm_scratch, void* stream);
+
+/* ---- Image modules of the Weizmann / vidTIMIT models (models/common.py:70-175) --------------------------------------
+ * common.Conv = nn.Conv2d -> BatchNorm2d -> ReLU, common.Deconv = nn.ConvTranspose2d -> BatchNorm2d -> ReLU, the
+ * decoder's final nn.Sigmoid; FP32 NCHW tensors, dilation 1, groups 1, output_padding 0.  One geometry serves both layer
+ * kinds: a SMALL map (Conv2d output / ConvTranspose2d input) and a BIG map (Conv2d input / ConvTranspose2d output)
+ * with  h_big = h_small * stride - padding + kh, and ONE weight layout w[c_small][c_big][k][k] = nn.Conv2d.weight
+ * (out, in, k, k) = nn.ConvTranspose2d.weight (in, out, k, k).
+ *                               Conv2d (models/common.py:75-78)      ConvTranspose2d (models/common.py:96-99)
+ *   bfvi_conv_gather            forward (bias, x -> y)               input gradient (bias = NULL, dy -> dx)
+ *   bfvi_conv_scatter           input gradient (bias = NULL)         forward (bias; act = BFVI_ACT_SIGMOID fuses the
+ *                                                                    decoder's final sigmoid, models/common.py:148)
+ *   bfvi_conv_wgrad             dw += (small = dy, big = x)          dw += (small = x, big = dy)
+ *   bfvi_chan_bias_grad         db += sum over images and pixels of dy (either layer)
+ * Direct FP32 convolutions (the reference's convolutions are FP32, not TF32); kernel sizes up to 7. */
+typedef struct bfvi_conv_geom {
+  int32_t n;                          /* images (T * B frames) */
+  int32_t c_small, h_small, w_small;
+  int32_t c_big, h_big, w_big;
+  int32_t kernel, stride, padding;
+} bfvi_conv_geom;
+enum { BFVI_ACT_NONE = 0, BFVI_ACT_SIGMOID = 2 };
+int bfvi_conv_gather(const bfvi_conv_geom* geom, const float* big, const float* w, const float* bias, float* small,
+                     int32_t act, void* stream);
+int bfvi_conv_scatter(const bfvi_conv_geom* geom, const float* small, const float* w, const float* bias, float* big,
+                      int32_t act, void* stream);
+int bfvi_conv_wgrad(const bfvi_conv_geom* geom, const float* small, const float* big, float* dw, void* stream);
+/* scratch of the per-channel reductions below (8-byte aligned device memory) */
+size_t bfvi_chan_scratch(int32_t channels);
+int bfvi_chan_bias_grad(const float* dy, int32_t N, int32_t C, int64_t HW, float* db, void* scratch, size_t scratch_bytes,
+                        void* stream);
+/* nn.BatchNorm2d (+ the ReLU that follows it in common.Conv / common.Deconv, models/common.py:79-84, 100-105) on x
+ * (N, C, HW).  training != 0: batch statistics (biased variance), running_mean / running_var blended with `momentum`
+ * (unbiased variance) when given; training == 0: the running statistics.  mean_rstd (C, 2) receives (mean, 1 / sqrt(var +
+ * eps)) for the backward.  Deterministic: per-channel partial sums in double, fixed order.
+ * bfvi_bn2d_bwd: dy is the gradient at y; relu != 0 masks it where y <= 0; d_gamma / d_beta are ACCUMULATED (nullable). */
+int bfvi_bn2d_fwd(const float* x, int32_t N, int32_t C, int64_t HW, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, int32_t training, float momentum, float eps, int32_t relu,
+                  float* y, float* mean_rstd, void* scratch, size_t scratch_bytes, void* stream);
+int bfvi_bn2d_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, int32_t N,
+                  int32_t C, int64_t HW, int32_t training, int32_t relu, float* dx, float* d_gamma, float* d_beta,
+                  void* scratch, size_t scratch_bytes, void* stream);
+/* dx = dp * p * (1 - p): backward of the sigmoid fused into bfvi_conv_scatter */
+int bfvi_sigmoid_bwd(const float* p, const float* dp, int64_t n, float* dx, void* stream);
 
 /* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
  * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */

@@ -118,6 +118,13 @@ class MlpGrads(C.Structure):          # bfvi_mlp_grads
 
 
 HEAD_GAUSSIAN, HEAD_SOFTMAX = 0, 1
+ACT_NONE, ACT_SIGMOID = 0, 2
+
+
+class ConvGeom(C.Structure):
+    """bfvi_conv_geom: small map = Conv2d output / ConvTranspose2d input, big map = the other side."""
+    _fields_ = [(n, C.c_int32) for n in ('n', 'c_small', 'h_small', 'w_small', 'c_big', 'h_big', 'w_big',
+                                         'kernel', 'stride', 'padding')]
 
 
 class BfviError(RuntimeError):
@@ -125,7 +132,7 @@ class BfviError(RuntimeError):
 
 
 # order of the BFVI_STRUCT_* enum (bfvi_sizeof)
-STRUCTS = (Model, Layout, Expert, Noise, FilterArgs, StepArgs, ForwardArgs)
+STRUCTS = (Model, Layout, Expert, Noise, FilterArgs, StepArgs, ForwardArgs, ConvGeom)
 
 
 # every symbol include/bfvi.h declares (tests check that the library exports them all)
@@ -203,6 +210,18 @@ SYMBOLS = {
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_float), C.c_void_p]),
     'bfvi_adam_step': (C.c_int, [C.c_void_p] * 4 + [C.c_int64] + [C.c_float] * 5 + [C.c_int32, C.c_float, C.c_float,
                                                                                     C.c_void_p, C.c_void_p]),
+    'bfvi_conv_gather': (C.c_int, [C.POINTER(ConvGeom)] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    'bfvi_conv_scatter': (C.c_int, [C.POINTER(ConvGeom)] + [C.c_void_p] * 4 + [C.c_int32, C.c_void_p]),
+    'bfvi_conv_wgrad': (C.c_int, [C.POINTER(ConvGeom)] + [C.c_void_p] * 3 + [C.c_void_p]),
+    'bfvi_chan_scratch': (C.c_size_t, [C.c_int32]),
+    'bfvi_chan_bias_grad': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p]),
+    'bfvi_bn2d_fwd': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 4
+                      + [C.c_int32, C.c_float, C.c_float, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                         C.c_void_p]),
+    'bfvi_bn2d_bwd': (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
+                      + [C.c_void_p] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
+    'bfvi_sigmoid_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_dump_noise': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -8,7 +8,11 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libbfvi_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3']
+              '--shared', '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--threads', '2']
+
+
+# translation units of the one library (everything else under csrc/ is a header they include)
+UNITS = [os.path.join(CSRC, 'bfvi_api.cu'), os.path.join(CSRC, 'bfvi_conv.cu')]
 
 
 def sources():
@@ -27,7 +31,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     if out is not None:
         nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
         subprocess.run([nvcc] + NVCC_FLAGS + ['-D%s' % d for d in defines] +
-                       [os.path.join(CSRC, 'bfvi_api.cu'), '-o', out], check=True)
+                       UNITS + ['-o', out], check=True)
         return out
     if not force and up_to_date():
         return OUT
@@ -35,7 +39,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libbfvi_b200.so')
     cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [
-        os.path.join(CSRC, 'bfvi_api.cu'), '-o', OUT]
+        ] + UNITS + ['-o', OUT]
     subprocess.run(cmd, check=True)
     return OUT
 

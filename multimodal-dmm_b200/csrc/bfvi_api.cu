@@ -14,6 +14,7 @@
 #include "bfvi_generic.cuh"
 #include "bfvi_fused.cuh"
 #include "bfvi_data.cuh"
+#include "bfvi_internal.h"
 
 namespace {
 
@@ -42,6 +43,20 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
+
+}  // namespace
+namespace bfvi {
+int report_error(int code, const char* fmt, ...) {        // the other translation units' way to bfvi_last_error()
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+}  // namespace bfvi
+namespace {
 
 #define BFVI_CHECK_CUDA()                                                                 \
   do {                                                                                    \
@@ -1892,6 +1907,7 @@ size_t bfvi_sizeof(int32_t which) {
     case BFVI_STRUCT_FILTER_ARGS: return sizeof(bfvi_filter_args);
     case BFVI_STRUCT_STEP_ARGS: return sizeof(bfvi_step_args);
     case BFVI_STRUCT_FORWARD_ARGS: return sizeof(bfvi_forward_args);
+    case BFVI_STRUCT_CONV_GEOM: return sizeof(bfvi_conv_geom);
     default: return 0;
   }
 }

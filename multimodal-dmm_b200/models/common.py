@@ -2,9 +2,14 @@
 (models/common.py:9-68).  In the fused path these modules only OWN the weights
 (aliased onto the flat CUDA parameter buffer); their `forward` methods exist for
 composition with custom user modules and run as ordinary device ops."""
+import ctypes as C
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from .. import _lib
 
 
 class CategoricalMLP(nn.Module):
@@ -57,17 +62,218 @@ class GaussianGTF(nn.Module):
 
 
 # ---------------------------------------------------------------------------------------
-# Image modules of the Weizmann model (models/common.py:70-175).  They are injected by the
-# caller as custom `encoders=` / `decoders=` (weizmann.py:64-76, which looks them up as
-# `models.common.ImageEncoder / ImageDecoder`), stay ordinary torch / cuDNN modules and hand
-# their (mean, std) / pixel probabilities to the fused temporal core (out of
-# scope for the kernels; "next" item §8f-3).  Module names follow the reference so that
-# state_dict keys — including the doubly registered `conv` / `net.0` entry — match.
+# Image modules of the Weizmann / vidTIMIT models (models/common.py:70-175).  The caller injects
+# them as custom `encoders=` / `decoders=` (weizmann.py:64-76 looks them up as
+# `models.common.ImageEncoder / ImageDecoder`).  The nn.Conv2d / nn.ConvTranspose2d /
+# nn.BatchNorm2d / nn.Linear sub-modules OWN the weights and buffers under the reference's
+# state_dict keys — including the doubly registered `conv` / `net.0` entry — and, on a CUDA
+# device, every layer runs through this library's kernels (include/bfvi.h: bfvi_conv_*,
+# bfvi_bn2d_*, bfvi_sigmoid_bwd, bfvi_linear_tf32 / bfvi_wgrad_tf32): no cuDNN, no cuBLAS.
+# On CPU tensors (constructing a model, state_dict round trips, the reference-side tests)
+# the sub-modules run as the plain torch modules they are.
 # ---------------------------------------------------------------------------------------
+# layer kinds served by libbfvi_b200 on CUDA tensors; BFVI_IMAGE_KERNELS="conv" / "" is a measurement aid (the torch /
+# cuDNN modules beside the kernels, tools/time_conv.py)
+IMAGE_KERNELS = {k: k in os.environ.get('BFVI_IMAGE_KERNELS', 'conv,dense').split(',') for k in ('conv', 'dense')}
+
+
+def _library():
+    return _lib.load()
+
+
+def _use_kernels(x, kind):
+    return x.is_cuda and IMAGE_KERNELS[kind]
+
+
+def _stream(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream if t.is_cuda else 0)
+
+
+def _scratch(lib, channels, like):
+    n = lib.dll.bfvi_chan_scratch(channels)
+    return torch.empty(n // 8 + 1, dtype=torch.float64, device=like.device), C.c_size_t(n)
+
+
+def _square(v, what):
+    a, b = (v, v) if isinstance(v, int) else tuple(v)
+    if a != b:
+        raise _lib.BfviError('image kernels: %s must be square, got %r' % (what, v))
+    return int(a)
+
+
+def _layer_geometry(layer):
+    """(kernel, stride, padding, transposed) of an nn.Conv2d / nn.ConvTranspose2d the kernels serve."""
+    transposed = isinstance(layer, nn.ConvTranspose2d)
+    if _square(layer.dilation, 'dilation') != 1 or layer.groups != 1 or layer.padding_mode != 'zeros' or \
+            isinstance(layer.padding, str) or (transposed and _square(layer.output_padding, 'output_padding') != 0):
+        raise _lib.BfviError('image kernels: dilation 1, groups 1, zero padding, output_padding 0 only')
+    return (_square(layer.kernel_size, 'kernel_size'), _square(layer.stride, 'stride'),
+            _square(layer.padding, 'padding'), transposed)
+
+
+class _ConvFn(torch.autograd.Function):
+    """nn.Conv2d / nn.ConvTranspose2d forward + backward (models/common.py:75-78, 96-99) through
+    bfvi_conv_gather / _scatter / _wgrad and bfvi_chan_bias_grad; `sigmoid` fuses the decoder's
+    final nn.Sigmoid (models/common.py:148) into the transposed convolution."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, k, s, p, transposed, sigmoid):
+        lib = _library()
+        x, w = x.detach().contiguous().float(), w.detach().contiguous().float()
+        b = None if b is None else b.detach().contiguous().float()
+        g = _lib.ConvGeom()
+        g.n, g.kernel, g.stride, g.padding = x.shape[0], k, s, p
+        if transposed:
+            g.c_small, g.h_small, g.w_small = x.shape[1:]
+            g.c_big, g.h_big, g.w_big = w.shape[1], (x.shape[2] - 1) * s - 2 * p + k, (x.shape[3] - 1) * s - 2 * p + k
+            y = torch.empty(g.n, g.c_big, g.h_big, g.w_big, device=x.device)
+            lib.call('bfvi_conv_scatter', C.byref(g), _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y),
+                     _lib.ACT_SIGMOID if sigmoid else _lib.ACT_NONE, _stream(x))
+        else:
+            g.c_big, g.h_big, g.w_big = x.shape[1:]
+            g.c_small, g.h_small, g.w_small = w.shape[0], (x.shape[2] + 2 * p - k) // s + 1, (x.shape[3] + 2 * p - k) // s + 1
+            y = torch.empty(g.n, g.c_small, g.h_small, g.w_small, device=x.device)
+            lib.call('bfvi_conv_gather', C.byref(g), _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y),
+                     _lib.ACT_SIGMOID if sigmoid else _lib.ACT_NONE, _stream(x))
+        ctx.geom, ctx.transposed, ctx.sigmoid, ctx.has_bias = g, transposed, sigmoid, b is not None
+        ctx.save_for_backward(x, w, y if sigmoid else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _library()
+        x, w, y = ctx.saved_tensors
+        g, st = ctx.geom, _stream(x)
+        dy = dy.contiguous().float()
+        if ctx.sigmoid:
+            pre = torch.empty_like(dy)
+            lib.call('bfvi_sigmoid_bwd', _lib.ptr(y), _lib.ptr(dy), dy.numel(), _lib.ptr(pre), st)
+            dy = pre
+        small, big = (x, dy) if ctx.transposed else (dy, x)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            lib.call('bfvi_conv_gather' if ctx.transposed else 'bfvi_conv_scatter', C.byref(g), _lib.ptr(dy), _lib.ptr(w),
+                     None, _lib.ptr(dx), _lib.ACT_NONE, st)
+        dw = torch.zeros_like(w)
+        lib.call('bfvi_conv_wgrad', C.byref(g), _lib.ptr(small), _lib.ptr(big), _lib.ptr(dw), st)
+        db = None
+        if ctx.has_bias:
+            db = torch.zeros(dy.shape[1], device=dy.device)
+            sc, n = _scratch(lib, dy.shape[1], dy)
+            lib.call('bfvi_chan_bias_grad', _lib.ptr(dy), dy.shape[0], dy.shape[1], dy.shape[2] * dy.shape[3],
+                     _lib.ptr(db), _lib.ptr(sc), n, st)
+        return dx, dw, db, None, None, None, None, None
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """nn.BatchNorm2d [-> nn.ReLU] (models/common.py:79-84) through bfvi_bn2d_fwd / _bwd; the running
+    statistics of `bn` are updated in place by the kernel like torch does."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, bn, relu):
+        lib = _library()
+        x = x.detach().contiguous().float()
+        N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+        training = bn.training or bn.running_mean is None
+        momentum = 0.0 if bn.momentum is None else float(bn.momentum)
+        track = training and bn.track_running_stats and bn.running_mean is not None
+        if track:
+            bn.num_batches_tracked.add_(1)
+            if bn.momentum is None:                              # cumulative moving average
+                momentum = 1.0 / float(bn.num_batches_tracked.item())
+        gamma = None if gamma is None else gamma.detach().contiguous().float()
+        beta = None if beta is None else beta.detach().contiguous().float()
+        y = torch.empty_like(x)
+        save = torch.empty(Cc, 2, device=x.device)
+        sc, n = _scratch(lib, Cc, x)
+        lib.call('bfvi_bn2d_fwd', _lib.ptr(x), N, Cc, HW, _lib.ptr(gamma), _lib.ptr(beta),
+                 _lib.ptr(bn.running_mean if (track or not training) else None),
+                 _lib.ptr(bn.running_var if (track or not training) else None), int(training), momentum, float(bn.eps),
+                 int(relu), _lib.ptr(y), _lib.ptr(save), _lib.ptr(sc), n, _stream(x))
+        ctx.training, ctx.relu = training, relu
+        ctx.save_for_backward(x, y, gamma, save)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _library()
+        x, y, gamma, save = ctx.saved_tensors
+        N, Cc, HW = x.shape[0], x.shape[1], x.shape[2] * x.shape[3]
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(x)
+        dg = torch.zeros(Cc, device=x.device)
+        db = torch.zeros(Cc, device=x.device)
+        sc, n = _scratch(lib, Cc, x)
+        lib.call('bfvi_bn2d_bwd', _lib.ptr(dy), _lib.ptr(x), _lib.ptr(y), _lib.ptr(save), _lib.ptr(gamma), N, Cc, HW,
+                 int(ctx.training), int(ctx.relu), _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(db), _lib.ptr(sc), n, _stream(x))
+        return dx, (dg if gamma is not None else None), (db if ctx.needs_input_grad[2] else None), None, None
+
+
+class _DenseFn(torch.autograd.Function):
+    """nn.Linear [-> nn.ReLU] (models/common.py:127-133, 146-149: feat_to_z_mean / feat_to_z_std.0 /
+    z_to_feat.0) on the tcgen05 tensor cores, error-compensated 3xTF32 (FP32-class): bfvi_linear_tf32
+    forward and input gradient, bfvi_wgrad_tf32 weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, relu):
+        lib = _library()
+        x, w = x.detach().contiguous().float(), w.detach().contiguous().float()
+        b = None if b is None else b.detach().contiguous().float()
+        rows, n_in, n_out = x.shape[0], x.shape[1], w.shape[0]
+        y = torch.empty(rows, n_out, device=x.device)
+        lib.call('bfvi_linear_tf32', _lib.ptr(x), n_in, _lib.ptr(w), n_in, _lib.ptr(b), _lib.ptr(y), n_out, rows, n_in,
+                 n_out, 1 if relu else 0, _stream(x))
+        ctx.relu, ctx.has_bias = relu, b is not None
+        ctx.save_for_backward(x, w, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _library()
+        x, w, y = ctx.saved_tensors
+        rows, n_in, n_out = x.shape[0], x.shape[1], w.shape[0]
+        dy = dy.contiguous().float()
+        if ctx.relu:
+            dy = dy * (y > 0)
+        st = _stream(x)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            w_t = w.t().contiguous()                              # (n_in, n_out): dx = dy w
+            lib.call('bfvi_linear_tf32', _lib.ptr(dy), n_out, _lib.ptr(w_t), n_out, None, _lib.ptr(dx), n_in, rows, n_out,
+                     n_in, 0, st)
+        dw = torch.empty_like(w)
+        dy_t, x_t = dy.t().contiguous(), x.t().contiguous()       # the contraction runs over the rows
+        lib.call('bfvi_wgrad_tf32', _lib.ptr(dy_t), rows, _lib.ptr(x_t), rows, _lib.ptr(dw), n_in, rows, n_out, n_in, 0, 0,
+                 st)
+        return dx, dw, (dy.sum(0) if ctx.has_bias else None), None
+
+
+def _dense(layer, x, relu=False):
+    if _use_kernels(x, 'dense'):
+        return _DenseFn.apply(x, layer.weight, layer.bias, relu)
+    y = layer(x)
+    return torch.relu(y) if relu else y
+
+
 def _conv_block(module, layer, n_out, last):
     """layer [-> BatchNorm2d -> ReLU]; the bare layer when it is the last of a stack."""
     module.net = layer if last else nn.Sequential(layer, nn.BatchNorm2d(n_out), nn.ReLU())
     nn.init.xavier_uniform_(layer.weight)
+
+
+def _run_block(module, layer, x, sigmoid=False):
+    """common.Conv / common.Deconv forward: the layer, then BatchNorm2d -> ReLU unless it is the last one."""
+    if not _use_kernels(x, 'conv'):
+        y = module.net(x)
+        return torch.sigmoid(y) if sigmoid else y
+    k, s, p, transposed = _layer_geometry(layer)
+    y = _ConvFn.apply(x, layer.weight, layer.bias, k, s, p, transposed, sigmoid)
+    if module.net is not layer:
+        bn = module.net[1]
+        y = _BatchNormFn.apply(y, bn.weight, bn.bias, bn, True)
+    return y
 
 
 class Conv(nn.Module):
@@ -79,7 +285,7 @@ class Conv(nn.Module):
         _conv_block(self, self.conv, n_kernels, last)
 
     def forward(self, x):
-        return self.net(x)
+        return _run_block(self, self.conv, x)
 
 
 class Deconv(nn.Module):
@@ -90,8 +296,8 @@ class Deconv(nn.Module):
         self.deconv = nn.ConvTranspose2d(n_channels, n_kernels, kernel_size, stride, padding)
         _conv_block(self, self.deconv, n_kernels, last)
 
-    def forward(self, x):
-        return self.net(x)
+    def forward(self, x, sigmoid=False):
+        return _run_block(self, self.deconv, x, sigmoid)
 
 
 def _stack_widths(n_kernels, n_layers):
@@ -122,7 +328,7 @@ class ImageEncoder(nn.Module):
         if not self.gauss_out:
             return feats
         flat = feats.reshape(-1, self.feat_dim)
-        return self.feat_to_z_mean(flat), self.feat_to_z_std(flat)
+        return _dense(self.feat_to_z_mean, flat), F.softplus(_dense(self.feat_to_z_std[0], flat))
 
 
 class ImageDecoder(nn.Module):
@@ -141,5 +347,8 @@ class ImageDecoder(nn.Module):
         nn.init.xavier_uniform_(self.z_to_feat[0].weight)
 
     def forward(self, z):
-        feats = self.z_to_feat(z).reshape(-1, *self.feat_shape)
-        return (self.deconv_stack(feats),)
+        x = _dense(self.z_to_feat[0], z, relu=True).reshape(-1, *self.feat_shape)
+        blocks = list(self.deconv_stack)[:-1]                    # the trailing nn.Sigmoid is fused into the last block
+        for i, blk in enumerate(blocks):
+            x = blk(x, sigmoid=(i == len(blocks) - 1))
+        return (x,)

@@ -17,7 +17,7 @@ def build(force=False):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     cmd = ['g++', '-std=c++17', '-O1', '-g', '-fPIC', '-shared', '-DBFVI_EMU', '-x', 'c++',
-           '-I', HERE, '-I', CSRC, os.path.join(CSRC, 'bfvi_api.cu'), '-o', OUT]
+           '-I', HERE, '-I', CSRC, os.path.join(CSRC, 'bfvi_api.cu'), os.path.join(CSRC, 'bfvi_conv.cu'), '-o', OUT]
     subprocess.run(cmd, check=True)
     return OUT
 

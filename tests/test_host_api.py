@@ -51,7 +51,7 @@ def test_cabi_library_exports_every_declared_symbol():
     assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
     for name in declared:
         assert hasattr(lib.dll, name)
-    assert lib.dll.bfvi_version() == int(re.search(r'#define BFVI_VERSION (\d+)', header).group(1)) == 130
+    assert lib.dll.bfvi_version() == int(re.search(r'#define BFVI_VERSION (\d+)', header).group(1)) == 140
 
 
 def test_layout_and_argument_errors():
