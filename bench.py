@@ -16,7 +16,8 @@ Workloads (BASELINE.json `configs`, made concrete in SURVEY.md §8d):
   c1           spirals defaults (spirals.py:31-50): T=100, B=100, burst_delete(0.1).
   c4           Weizmann-shaped video model (BASELINE configs[3]): conv image encoders / decoders as custom torch modules,
                Bernoulli + Categorical likelihoods, dropped modalities, Z=H=256, T=25, B=25 — an auxiliary line through
-               the composed path (the conv modules are cuDNN; no roofline object).
+               the composed path (conv / BatchNorm / dense layers of the image modules on this library's FP32 kernels,
+               bfvi_conv_* / bfvi_bn2d_* / bfvi_dense_*; no roofline object).
   c5           inference only (BASELINE configs[4]): MultiDMM.forward as Trainer.evaluate calls it (fsmooth, MAP
                estimate, 25 particles in the filtering pass) on the C3-dims model, T=1000, B=1024 per GPU;
                metric bfvi_forward_seq_timesteps_per_sec (forward only), ranks run independent shards.
@@ -152,8 +153,8 @@ C3 = Workload('c3', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 2048
 C5 = Workload('c5', ['m%d' % i for i in range(8)], [16] * 8, 64, 512, 1000, 1024, make_c3_batch, 1.0 / (16 * 8),
               'C5: inference-only forward (fsmooth, sample=False, flt_particles=25) of the scaled MDMM, M=8 D=16 Z=64 H=512, '
               'T=1000, B=%(B)d per GPU, N(0,1) data, Philox noise', (24, 100))
-# C4 (BASELINE configs[3]): Weizmann-shaped video model — conv image encoders / decoders (torch / cuDNN modules passed as
-# custom encoders= / decoders=, weizmann.py:53-77), Bernoulli + Categorical likelihoods, dropped modalities — through the
+# C4 (BASELINE configs[3]): Weizmann-shaped video model — conv image encoders / decoders (common.ImageEncoder / ImageDecoder passed as
+# custom encoders= / decoders=, weizmann.py:53-77; their layers run on bfvi_conv_* / bfvi_bn2d_* / bfvi_dense_*), Bernoulli + Categorical likelihoods, dropped modalities — through the
 # composed path: our temporal core (fused z_filter), likelihood kernels and categorical encoder / decoder kernels around it
 C4_MODS = ['video', 'mask', 'action']
 C4_DIMS = {'video': (3, 64, 64), 'mask': (1, 64, 64), 'action': 10}
@@ -577,9 +578,9 @@ def main():
 
 
 def run_weizmann(args, wl, models, dev, rank, local_rank, world, dist):
-    """--workload c4: MultiDMM.step + backward of the Weizmann-shaped model through the composed path (custom conv modules
-    are torch / cuDNN; the temporal core, the Bernoulli / categorical likelihoods and the categorical encoder / decoder are
-    this library's kernels).  Data parallel like the other training workloads: one all-reduce of the gradients per step."""
+    """--workload c4: MultiDMM.step + backward of the Weizmann-shaped model through the composed path (the image modules'
+    convolutions, BatchNorm -> ReLU and dense layers, the temporal core, the Bernoulli / categorical likelihoods and the
+    categorical encoder / decoder are all this library's kernels).  Data parallel like the other training workloads: one all-reduce of the gradients per step."""
     from multimodal_dmm_b200 import _lib
     model = build_c4_model(models, dev).train()
     b_dim, t_max = per_gpu_batch(args, wl, world), wl.t_max
@@ -653,13 +654,13 @@ def run_weizmann(args, wl, models, dev, rank, local_rank, world, dist):
     print(json.dumps({
         'metric': METRIC, 'value': seq_ts / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
-        'dtype': 'fp32 conv modules (torch / cuDNN) around the tcgen05 temporal core (3xTF32, fp32-class)', 'data': 'synthetic',
+        'dtype': 'fp32 image modules (direct FFMA convolutions, bfvi_conv_*) around the tcgen05 temporal core (3xTF32, fp32-class)', 'data': 'synthetic',
         'config': config_of(wl, b_dim, world, args.scaling), 'clocks': clocks,
         'e2e': {'value': seq_ts / (ms_e2e * 1e-3), 'unit': UNIT, 'steps': e2e_steps,
                 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4},
         'gpu_launches': None, 'roofline': None,
-        'note': 'auxiliary line: the conv encoders / decoders of this workload are library (cuDNN) code, SURVEY 8f-3; the temporal '
-                'core, the likelihood kernels and the categorical encoder / decoder are ours',
+        'note': 'auxiliary line: image encoders / decoders (SURVEY 8f-3), temporal core, likelihood kernels and the categorical '
+                'encoder / decoder all run on this library (no cuDNN / cuBLAS on the path)',
         'dispatch': dispatch, 'cpu_baseline': cpu_baseline}))
 
 

@@ -541,6 +541,18 @@ int bfvi_bn2d_bwd(const float* dy, const float* x, const float* y, const float* 
 /* dx = dp * p * (1 - p): backward of the sigmoid fused into bfvi_conv_scatter */
 int bfvi_sigmoid_bwd(const float* p, const float* dp, int64_t n, float* dx, void* stream);
 
+/* nn.Linear [-> nn.ReLU] of the image modules (feat_to_z_mean / feat_to_z_std.0 / z_to_feat.0, models/common.py:127-133,
+ * 146-149) in FP32 on the FFMA pipe: x (rows, n_in), w (n_out, n_in), y (rows, n_out), all dense row-major.  (The contraction
+ * over feat_dim = 4096 leaves the tensor cores' 3xTF32 product at 2e-5 of the result — enough to flip BatchNorm -> ReLU masks
+ * downstream; these layers are 4 % of the image modules' arithmetic.)
+ * bfvi_dense_bwd: dy is the gradient at y; relu != 0 masks it where y <= 0 into dy_masked (rows, n_out; scratch the caller
+ * provides); dx (nullable) is written, dw and db (nullable) are ACCUMULATED; scratch as bfvi_chan_scratch(n_out). */
+int bfvi_dense_fwd(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t n_in, int32_t n_out,
+                   int32_t relu, void* stream);
+int bfvi_dense_bwd(const float* x, const float* w, const float* y, const float* dy, float* dy_masked, int64_t rows,
+                   int32_t n_in, int32_t n_out, int32_t relu, float* dx, float* dw, float* db, void* scratch,
+                   size_t scratch_bytes, void* stream);
+
 /* FP32 FFMA throughput probe: `blocks` CTAs x 256 threads x iters x 16 FMAs
  * (measurement aid: the roofline denominator of the FFMA-bound small-dim path). */
 int bfvi_ffma_probe(float* out, int32_t iters, int32_t blocks, void* stream);

@@ -222,6 +222,9 @@ SYMBOLS = {
     'bfvi_bn2d_bwd': (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int64, C.c_int32, C.c_int32]
                       + [C.c_void_p] * 3 + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'bfvi_sigmoid_bwd': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    'bfvi_dense_fwd': (C.c_int, [C.c_void_p] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    'bfvi_dense_bwd': (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 3
+                       + [C.c_void_p, C.c_size_t, C.c_void_p]),
     'bfvi_ffma_probe': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     'bfvi_dump_noise': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

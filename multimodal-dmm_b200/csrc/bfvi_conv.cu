@@ -250,3 +250,68 @@ int bfvi_sigmoid_bwd(const float* p, const float* dp, int64_t n, float* dx, void
 }
 
 }  // extern "C"
+
+namespace {
+void launch_dense(bfvi::conv::DenseParams p, cudaStream_t st) {
+  const dim3 grid((unsigned)((p.N + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile),
+                  (unsigned)((p.M + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile));
+  auto k = bfvi::conv::dense_gemm_kernel;
+  BFVI_LAUNCH(k, grid, dim3(256), 0, st, p);
+}
+int check_dense(int64_t rows, int32_t n_in, int32_t n_out) {
+  if (rows < 1 || n_in < 1 || n_out < 1) return report_error(BFVI_ERR_ARG, "empty dense layer");
+  if (rows > 64ll * 65535) return report_error(BFVI_ERR_UNSUPPORTED, "up to 4 193 240 rows per call");
+  return BFVI_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int bfvi_dense_fwd(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t n_in, int32_t n_out,
+                   int32_t relu, void* stream) {
+  if (int rc = check_dense(rows, n_in, n_out)) return rc;
+  if (!x || !w || !y) return report_error(BFVI_ERR_ARG, "null tensor");
+  bfvi::conv::DenseParams p;
+  memset(&p, 0, sizeof(p));
+  p.A = x; p.sai = n_in; p.sal = 1; p.a_l_contig = 1;
+  p.B = w; p.sbj = n_in; p.sbl = 1; p.b_l_contig = 1;
+  p.C = y; p.ldc = n_out; p.M = (int)rows; p.N = n_out; p.K = n_in; p.bias = bias; p.relu = relu != 0;
+  launch_dense(p, (cudaStream_t)stream);
+  BFVI_CONV_CHECK_CUDA();
+  return BFVI_OK;
+}
+
+int bfvi_dense_bwd(const float* x, const float* w, const float* y, const float* dy, float* dy_masked, int64_t rows,
+                   int32_t n_in, int32_t n_out, int32_t relu, float* dx, float* dw, float* db, void* scratch, size_t bytes,
+                   void* stream) {
+  if (int rc = check_dense(rows, n_in, n_out)) return rc;
+  if (!x || !w || !dy || !dw) return report_error(BFVI_ERR_ARG, "null tensor");
+  if (relu && (!y || !dy_masked)) return report_error(BFVI_ERR_ARG, "the ReLU backward needs y and the dy_masked buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (relu) {
+    const long long n = (long long)rows * n_out;
+    long long blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    auto k = bfvi::conv::relu_mask_kernel;
+    BFVI_LAUNCH(k, dim3((unsigned)blocks), dim3(256), 0, st, dy, y, n, dy_masked);
+    dy = dy_masked;
+  }
+  bfvi::conv::DenseParams p;
+  if (dx != nullptr) {                       // dx (rows, n_in) = dy w
+    memset(&p, 0, sizeof(p));
+    p.A = dy; p.sai = n_out; p.sal = 1; p.a_l_contig = 1;
+    p.B = w; p.sbj = 1; p.sbl = n_in; p.b_l_contig = 0;
+    p.C = dx; p.ldc = n_in; p.M = (int)rows; p.N = n_in; p.K = n_out;
+    launch_dense(p, st);
+  }
+  memset(&p, 0, sizeof(p));                  // dw (n_out, n_in) += dy^T x
+  p.A = dy; p.sai = 1; p.sal = n_out; p.a_l_contig = 0;
+  p.B = x; p.sbj = 1; p.sbl = n_in; p.b_l_contig = 0;
+  p.C = dw; p.ldc = n_in; p.M = n_out; p.N = n_in; p.K = (int)rows; p.accumulate = 1;
+  launch_dense(p, st);
+  BFVI_CONV_CHECK_CUDA();
+  if (db != nullptr) return bfvi_chan_bias_grad(dy, (int32_t)rows, n_out, 1, db, scratch, bytes, stream);
+  return BFVI_OK;
+}
+
+}  // extern "C"

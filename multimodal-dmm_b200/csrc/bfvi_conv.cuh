@@ -395,5 +395,77 @@ __global__ void __launch_bounds__(256) sigmoid_bwd_kernel(const float* __restric
   }
 }
 
+
+// ---- dense layers of the image modules (feat_to_z_mean / feat_to_z_std.0 / z_to_feat.0, models/common.py:127-133, 146-149)
+// C[i, j] (+)= act(sum_l A(i, l) * B(j, l) + bias[j]) in FP32 on the FFMA pipe, operands addressed by two strides each so
+// that one kernel serves y = x W^T + b, dx = dy W and dW = dy^T x without transposed copies.  Why not the tcgen05 TF32
+// GEMM of bfvi_tc.cuh: the contraction over feat_dim = 4096 leaves the error-compensated 3xTF32 product at 2e-5 of the
+// result (tensor-core accumulation, measured: profiles/r2_dense_accuracy.json), which flips enough BatchNorm -> ReLU masks
+// downstream to move the gradients by 3e-3; the reference computes these layers in FP32.
+// 64 x 64 output tile per CTA, 16-deep operand tiles in shared memory (l-major), 4 x 4 outputs per thread.
+struct DenseParams {
+  const float* A; long long sai, sal; int a_l_contig;
+  const float* B; long long sbj, sbl; int b_l_contig;
+  float* C; long long ldc;
+  int M, N, K;
+  const float* bias; int relu, accumulate;
+};
+constexpr int kDenseTile = 64, kDenseK = 16, kDensePitch = 68;
+__global__ void __launch_bounds__(256) dense_gemm_kernel(DenseParams p) {
+  __shared__ __align__(16) float As[kDenseK][kDensePitch];
+  __shared__ __align__(16) float Bs[kDenseK][kDensePitch];
+  const int i0 = (int)blockIdx.y * kDenseTile, j0 = (int)blockIdx.x * kDenseTile;
+  const int tx = (int)threadIdx.x & 15, ty = (int)threadIdx.x >> 4;
+  float acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  for (int l0 = 0; l0 < p.K; l0 += kDenseK) {
+#pragma unroll
+    for (int e = (int)threadIdx.x; e < kDenseTile * kDenseK; e += 256) {
+      int i, l;
+      if (p.a_l_contig) { l = e % kDenseK; i = e / kDenseK; } else { i = e % kDenseTile; l = e / kDenseTile; }
+      As[l][i] = (i0 + i < p.M && l0 + l < p.K) ? p.A[(long long)(i0 + i) * p.sai + (long long)(l0 + l) * p.sal] : 0.f;
+      int j, m;
+      if (p.b_l_contig) { m = e % kDenseK; j = e / kDenseK; } else { j = e % kDenseTile; m = e / kDenseTile; }
+      Bs[m][j] = (j0 + j < p.N && l0 + m < p.K) ? p.B[(long long)(j0 + j) * p.sbj + (long long)(l0 + m) * p.sbl] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int l = 0; l < kDenseK; ++l) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[l][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[l][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty * 4 + r;
+    if (i >= p.M) continue;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int j = j0 + tx * 4 + c;
+      if (j >= p.N) continue;
+      float v = acc[r][c] + (p.bias != nullptr ? p.bias[j] : 0.f);
+      if (p.relu) v = v > 0.f ? v : (v != v ? v : 0.f);
+      float* out = p.C + (long long)i * p.ldc + j;
+      *out = p.accumulate ? *out + v : v;
+    }
+  }
+}
+
+// out = dy where y > 0, else 0: the gradient through the ReLU that follows z_to_feat.0 (models/common.py:147)
+__global__ void __launch_bounds__(256) relu_mask_kernel(const float* __restrict__ dy, const float* __restrict__ y, long long n,
+                                                        float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256)
+    out[i] = y[i] > 0.f ? dy[i] : 0.f;
+}
+
 }  // namespace conv
 }  // namespace bfvi

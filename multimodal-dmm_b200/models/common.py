@@ -68,7 +68,7 @@ class GaussianGTF(nn.Module):
 # nn.BatchNorm2d / nn.Linear sub-modules OWN the weights and buffers under the reference's
 # state_dict keys — including the doubly registered `conv` / `net.0` entry — and, on a CUDA
 # device, every layer runs through this library's kernels (include/bfvi.h: bfvi_conv_*,
-# bfvi_bn2d_*, bfvi_sigmoid_bwd, bfvi_linear_tf32 / bfvi_wgrad_tf32): no cuDNN, no cuBLAS.
+# bfvi_bn2d_*, bfvi_sigmoid_bwd, bfvi_dense_*): no cuDNN, no cuBLAS.
 # On CPU tensors (constructing a model, state_dict round trips, the reference-side tests)
 # the sub-modules run as the plain torch modules they are.
 # ---------------------------------------------------------------------------------------
@@ -212,8 +212,8 @@ class _BatchNormFn(torch.autograd.Function):
 
 class _DenseFn(torch.autograd.Function):
     """nn.Linear [-> nn.ReLU] (models/common.py:127-133, 146-149: feat_to_z_mean / feat_to_z_std.0 /
-    z_to_feat.0) on the tcgen05 tensor cores, error-compensated 3xTF32 (FP32-class): bfvi_linear_tf32
-    forward and input gradient, bfvi_wgrad_tf32 weight gradient."""
+    z_to_feat.0) through bfvi_dense_fwd / _bwd: FP32 like the reference (the 4096-long contraction
+    on the TF32 tensor cores, even error-compensated, flips ReLU masks downstream)."""
 
     @staticmethod
     def forward(ctx, x, w, b, relu):
@@ -222,8 +222,8 @@ class _DenseFn(torch.autograd.Function):
         b = None if b is None else b.detach().contiguous().float()
         rows, n_in, n_out = x.shape[0], x.shape[1], w.shape[0]
         y = torch.empty(rows, n_out, device=x.device)
-        lib.call('bfvi_linear_tf32', _lib.ptr(x), n_in, _lib.ptr(w), n_in, _lib.ptr(b), _lib.ptr(y), n_out, rows, n_in,
-                 n_out, 1 if relu else 0, _stream(x))
+        lib.call('bfvi_dense_fwd', _lib.ptr(x), _lib.ptr(w), _lib.ptr(b), _lib.ptr(y), rows, n_in, n_out, int(relu),
+                 _stream(x))
         ctx.relu, ctx.has_bias = relu, b is not None
         ctx.save_for_backward(x, w, y if relu else None)
         return y
@@ -234,20 +234,14 @@ class _DenseFn(torch.autograd.Function):
         x, w, y = ctx.saved_tensors
         rows, n_in, n_out = x.shape[0], x.shape[1], w.shape[0]
         dy = dy.contiguous().float()
-        if ctx.relu:
-            dy = dy * (y > 0)
-        st = _stream(x)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            w_t = w.t().contiguous()                              # (n_in, n_out): dx = dy w
-            lib.call('bfvi_linear_tf32', _lib.ptr(dy), n_out, _lib.ptr(w_t), n_out, None, _lib.ptr(dx), n_in, rows, n_out,
-                     n_in, 0, st)
-        dw = torch.empty_like(w)
-        dy_t, x_t = dy.t().contiguous(), x.t().contiguous()       # the contraction runs over the rows
-        lib.call('bfvi_wgrad_tf32', _lib.ptr(dy_t), rows, _lib.ptr(x_t), rows, _lib.ptr(dw), n_in, rows, n_out, n_in, 0, 0,
-                 st)
-        return dx, dw, (dy.sum(0) if ctx.has_bias else None), None
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w)
+        db = torch.zeros(n_out, device=x.device) if ctx.has_bias else None
+        masked = torch.empty_like(dy) if ctx.relu else None
+        sc, n = _scratch(lib, n_out, x)
+        lib.call('bfvi_dense_bwd', _lib.ptr(x), _lib.ptr(w), _lib.ptr(y), _lib.ptr(dy), _lib.ptr(masked), rows, n_in, n_out,
+                 int(ctx.relu), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(sc), n, _stream(x))
+        return dx, dw, db, None
 
 
 def _dense(layer, x, relu=False):

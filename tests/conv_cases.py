@@ -34,6 +34,15 @@ BN_CASES = {
 }
 
 
+# name: (rows, n_in, n_out, relu)
+DENSE_CASES = {
+    'dense_odd_relu': (37, 19, 70, True),
+    'dense_odd': (5, 130, 3, False),
+    'dense_feat_to_z': (6, 4096, 256, False),       # Weizmann feat_to_z_mean / feat_to_z_std.0
+    'dense_z_to_feat': (20, 256, 4096, True),       # Weizmann z_to_feat.0 -> ReLU
+}
+
+
 def small_size(big, k, s, p, transposed):
     if not transposed:
         return (big + 2 * p - k) // s + 1
@@ -214,3 +223,31 @@ def check_modules(common, device, tol, img_size=16, n_kernels=8, z_dim=12, frame
     bad = {k: v for k, v in worst.items() if not v < tol}
     assert not bad, bad
     return worst
+
+
+def check_dense(case, lib, device, tol):
+    rows, n_in, n_out, relu = DENSE_CASES[case]
+    dev = torch.device(device)
+    gen = torch.Generator().manual_seed(2)
+    r = lambda *sh: torch.randn(*sh, generator=gen)
+    x, w, b, dy = r(rows, n_in), r(n_out, n_in) / n_in ** 0.5, 0.2 * r(n_out), r(rows, n_out)
+    x64, w64, b64 = (t.double().requires_grad_(True) for t in (x, w, b))
+    y64 = F.linear(x64, w64, b64)
+    if relu:
+        y64 = torch.relu(y64)
+    y64.backward(dy.double())
+    st = stream_of(dev)
+    xd, wd, bd, dyd = (t.to(dev).contiguous() for t in (x, w, b, dy))
+    y = torch.full((rows, n_out), float('nan'), device=dev)
+    lib.call('bfvi_dense_fwd', _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(y), rows, n_in, n_out, int(relu), st)
+    dx = torch.full_like(xd, float('nan'))
+    dw, db = torch.ones_like(wd), torch.ones_like(bd)          # += semantics
+    masked = torch.empty_like(dyd) if relu else None
+    sc, n = scratch_for(lib, n_out, dev)
+    lib.call('bfvi_dense_bwd', _lib.ptr(xd), _lib.ptr(wd), _lib.ptr(y), _lib.ptr(dyd), _lib.ptr(masked), rows, n_in, n_out,
+             int(relu), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(sc), C.c_size_t(n), st)
+    if dev.type == 'cuda':
+        torch.cuda.synchronize()
+    errs = {'y': rel(y, y64.detach()), 'dx': rel(dx, x64.grad), 'dw': rel(dw - 1, w64.grad), 'db': rel(db - 1, b64.grad)}
+    assert all(e < tol for e in errs.values()), (case, errs)
+    return errs

@@ -32,6 +32,11 @@ def test_batchnorm_relu_matches_torch(lib, case):
     conv_cases.check_bn(case, lib, 'cpu', 2e-6)
 
 
+@pytest.mark.parametrize('case', ['dense_odd_relu', 'dense_odd'])
+def test_dense_layer_matches_torch(lib, case):
+    conv_cases.check_dense(case, lib, 'cpu', 2e-6)
+
+
 def test_argument_errors(lib):
     g, _ = conv_cases.geom('conv3s2_odd')
     x = torch.zeros(8)

@@ -1,5 +1,5 @@
 """Image-module kernels on B200 (bfvi_conv_*, bfvi_bn2d_*, bfvi_sigmoid_bwd, bfvi_chan_bias_grad; the dense layers on
-bfvi_linear_tf32 / bfvi_wgrad_tf32) against torch fp64 on the CPU: every layer kind of models/common.py:70-175 at the
+bfvi_dense_fwd / _bwd) against torch fp64 on the CPU: every layer kind of models/common.py:70-175 at the
 Weizmann sizes and at odd sizes, then the ImageEncoder / ImageDecoder modules end to end."""
 import os
 
@@ -25,6 +25,11 @@ def test_deconv_sigmoid_epilogue(case):
 @pytest.mark.parametrize('case', sorted(conv_cases.BN_CASES))
 def test_batchnorm_relu_matches_torch(case):
     conv_cases.check_bn(case, _lib.load(), 'cuda:0', 1e-5)
+
+
+@pytest.mark.parametrize('case', sorted(conv_cases.DENSE_CASES))
+def test_dense_layer_matches_torch(case):
+    conv_cases.check_dense(case, _lib.load(), 'cuda:0', 2e-6)
 
 
 @pytest.mark.parametrize('size', ['small', 'weizmann'])
