@@ -253,8 +253,19 @@ int bfvi_sigmoid_bwd(const float* p, const float* dp, int64_t n, float* dx, void
 
 namespace {
 void launch_dense(bfvi::conv::DenseParams p, cudaStream_t st) {
-  const dim3 grid((unsigned)((p.N + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile),
-                  (unsigned)((p.M + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile));
+  dim3 grid((unsigned)((p.N + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile),
+            (unsigned)((p.M + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile));
+  // few output tiles and a long contraction (feat_to_z at 625 frames: 40 tiles, K = 4096): slices of K on the other SMs
+  const long long tiles = (long long)grid.x * grid.y;
+  if (!p.relu && tiles * 2 <= 148 && p.K >= 1024) {
+    long long splits = 296 / tiles;
+    if (splits > p.K / 256) splits = p.K / 256;
+    if (splits > 1) {
+      p.k_per_split = (int)(((p.K + splits - 1) / splits + bfvi::conv::kDenseK - 1) / bfvi::conv::kDenseK * bfvi::conv::kDenseK);
+      grid.z = (unsigned)((p.K + p.k_per_split - 1) / p.k_per_split);
+      if (!p.accumulate) cudaMemsetAsync(p.C, 0, sizeof(float) * (size_t)p.M * (size_t)p.ldc, st);
+    }
+  }
   auto k = bfvi::conv::dense_gemm_kernel;
   BFVI_LAUNCH(k, grid, dim3(256), 0, st, p);
 }

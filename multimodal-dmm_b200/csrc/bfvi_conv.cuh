@@ -135,6 +135,21 @@ __global__ void __launch_bounds__(kThreads) conv_scatter_kernel(Geom g, const fl
 #pragma unroll
   for (int c = 0; c < CT; ++c) acc[c] = (bias != nullptr && cb0 + c < g.Cb) ? bias[cb0 + c] : 0.f;
   const float* simg = small + (size_t)n * g.Cs * g.Hs * g.Ws;
+  // the taps that land on this pixel: kh = kh0 + a*s with (H + p - kh) = s*h, 0 <= h < Hs (and the same along W);
+  // at k4 s2 that is 2 x 2 of the 16 taps, found once per thread, not once per channel
+  constexpr int TAPS = (KT && ST) ? (KT + ST - 1) / ST : 7;
+  const int kh0 = (H + g.p) % s, kw0 = (W + g.p) % s;
+  int hh[TAPS], ww[TAPS];
+  bool hv[TAPS], wv[TAPS];
+#pragma unroll
+  for (int a = 0; a < TAPS; ++a) {
+    const int kh = kh0 + a * s, th = H + g.p - kh;
+    hh[a] = th / s;
+    hv[a] = kh < k && th >= 0 && hh[a] < g.Hs;
+    const int kw = kw0 + a * s, tw = W + g.p - kw;
+    ww[a] = tw / s;
+    wv[a] = kw < k && tw >= 0 && ww[a] < g.Ws;
+  }
   for (int c0 = 0; c0 < g.Cs; c0 += cs_chunk) {
     const int cn = g.Cs - c0 < cs_chunk ? g.Cs - c0 : cs_chunk;
     __syncthreads();
@@ -149,19 +164,13 @@ __global__ void __launch_bounds__(kThreads) conv_scatter_kernel(Geom g, const fl
       const float* sch = simg + (size_t)(c0 + cs) * g.Hs * g.Ws;
       const float* wcs = wsm + (size_t)cs * kk * CT;
 #pragma unroll
-      for (int kh = 0; kh < k; ++kh) {
-        const int th = H + g.p - kh;
-        if (th < 0 || th % s != 0) continue;
-        const int h = th / s;
-        if (h >= g.Hs) continue;
+      for (int a = 0; a < TAPS; ++a) {
+        if (!hv[a]) continue;
 #pragma unroll
-        for (int kw = 0; kw < k; ++kw) {
-          const int tw = W + g.p - kw;
-          if (tw < 0 || tw % s != 0) continue;
-          const int x = tw / s;
-          if (x >= g.Ws) continue;
-          const float v = sch[(size_t)h * g.Ws + x];
-          const float4* wp = reinterpret_cast<const float4*>(wcs + (kh * k + kw) * CT);
+        for (int b = 0; b < TAPS; ++b) {
+          if (!wv[b]) continue;
+          const float v = sch[(size_t)hh[a] * g.Ws + ww[b]];
+          const float4* wp = reinterpret_cast<const float4*>(wcs + ((kh0 + a * s) * k + kw0 + b * s) * CT);
 #pragma unroll
           for (int c4 = 0; c4 < CT / 4; ++c4) {
             const float4 q = wp[c4];
@@ -203,11 +212,17 @@ __global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(Geom g, const
 #pragma unroll
     for (int t = 0; t < KK; ++t) acc[r][t] = 0.f;
   const size_t splane = (size_t)g.Hs * g.Ws, bplane = (size_t)g.Hb * g.Wb;
+  // (n, oh, ow) of this thread's pixel, advanced by 256 pixels per iteration in mixed radix (no division in the loop)
+  const int step_w = kWgradThreads % g.Ws, step_h = (kWgradThreads / g.Ws) % g.Hs, step_n = kWgradThreads / (g.Ws * g.Hs);
+  int ow, oh, n;
+  {
+    const long long first = lo + threadIdx.x;
+    ow = (int)(first % g.Ws);
+    const long long t = first / g.Ws;
+    oh = (int)(t % g.Hs);
+    n = (int)(t / g.Hs);
+  }
   for (long long pix = lo + threadIdx.x; pix < hi; pix += kWgradThreads) {
-    const int ow = (int)(pix % g.Ws);
-    const long long t = pix / g.Ws;
-    const int oh = (int)(t % g.Hs);
-    const int n = (int)(t / g.Hs);
     float sv[CSR];
 #pragma unroll
     for (int r = 0; r < CSR; ++r)
@@ -229,6 +244,11 @@ __global__ void __launch_bounds__(kWgradThreads) conv_wgrad_kernel(Geom g, const
         for (int r = 0; r < CSR; ++r) acc[r][kh * (KT ? KT : 7) + kw] = fmaf(sv[r], v, acc[r][kh * (KT ? KT : 7) + kw]);
       }
     }
+    ow += step_w;
+    if (ow >= g.Ws) { ow -= g.Ws; ++oh; }
+    oh += step_h;
+    if (oh >= g.Hs) { oh -= g.Hs; ++n; }
+    n += step_n;
   }
   __shared__ float red[kWgradThreads / 32][CSR * KK];
   const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5;
@@ -270,8 +290,11 @@ __global__ void __launch_bounds__(256) chan_reduce_kernel(ReduceParams p) {
   double s0 = 0.0, s1 = 0.0;
   float mean = 0.f, rstd = 0.f;
   if (p.mode == 1) { mean = p.mean_rstd[2 * c]; rstd = p.mean_rstd[2 * c + 1]; }
-  for (long long i = lo + threadIdx.x; i < hi; i += 256) {
-    const long long n = i / p.HW, q = i - n * p.HW;
+  // (image, offset in the plane) advanced by 256 elements per iteration without a division
+  long long n = (lo + threadIdx.x) / p.HW, q = (lo + threadIdx.x) - n * p.HW;
+  const long long step_n = 256 / p.HW, step_q = 256 - step_n * p.HW;
+  for (long long i = lo + threadIdx.x; i < hi; i += 256, n += step_n, q += step_q) {
+    if (q >= p.HW) { q -= p.HW; ++n; }
     const size_t at = ((size_t)n * p.C + c) * (size_t)p.HW + (size_t)q;
     if (p.mode == 0) {
       const float v = p.a[at];
@@ -409,6 +432,7 @@ struct DenseParams {
   float* C; long long ldc;
   int M, N, K;
   const float* bias; int relu, accumulate;
+  int k_per_split;      // gridDim.z > 1: each z-slice contracts k_per_split of K and adds its tile with atomicAdd
 };
 constexpr int kDenseTile = 64, kDenseK = 16, kDensePitch = 68;
 __global__ void __launch_bounds__(256) dense_gemm_kernel(DenseParams p) {
@@ -421,15 +445,18 @@ __global__ void __launch_bounds__(256) dense_gemm_kernel(DenseParams p) {
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-  for (int l0 = 0; l0 < p.K; l0 += kDenseK) {
+  const bool split = gridDim.z > 1;
+  const int l_lo = split ? (int)blockIdx.z * p.k_per_split : 0;
+  const int l_hi = split ? (l_lo + p.k_per_split < p.K ? l_lo + p.k_per_split : p.K) : p.K;
+  for (int l0 = l_lo; l0 < l_hi; l0 += kDenseK) {
 #pragma unroll
     for (int e = (int)threadIdx.x; e < kDenseTile * kDenseK; e += 256) {
       int i, l;
       if (p.a_l_contig) { l = e % kDenseK; i = e / kDenseK; } else { i = e % kDenseTile; l = e / kDenseTile; }
-      As[l][i] = (i0 + i < p.M && l0 + l < p.K) ? p.A[(long long)(i0 + i) * p.sai + (long long)(l0 + l) * p.sal] : 0.f;
+      As[l][i] = (i0 + i < p.M && l0 + l < l_hi) ? p.A[(long long)(i0 + i) * p.sai + (long long)(l0 + l) * p.sal] : 0.f;
       int j, m;
       if (p.b_l_contig) { m = e % kDenseK; j = e / kDenseK; } else { j = e % kDenseTile; m = e / kDenseTile; }
-      Bs[m][j] = (j0 + j < p.N && l0 + m < p.K) ? p.B[(long long)(j0 + j) * p.sbj + (long long)(l0 + m) * p.sbl] : 0.f;
+      Bs[m][j] = (j0 + j < p.N && l0 + m < l_hi) ? p.B[(long long)(j0 + j) * p.sbj + (long long)(l0 + m) * p.sbl] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -452,9 +479,10 @@ __global__ void __launch_bounds__(256) dense_gemm_kernel(DenseParams p) {
     for (int c = 0; c < 4; ++c) {
       const int j = j0 + tx * 4 + c;
       if (j >= p.N) continue;
-      float v = acc[r][c] + (p.bias != nullptr ? p.bias[j] : 0.f);
-      if (p.relu) v = v > 0.f ? v : (v != v ? v : 0.f);
+      float v = acc[r][c] + ((p.bias != nullptr && blockIdx.z == 0) ? p.bias[j] : 0.f);
       float* out = p.C + (long long)i * p.ldc + j;
+      if (split) { atomicAdd(out, v); continue; }             // host side: no ReLU, C zeroed unless accumulating
+      if (p.relu) v = v > 0.f ? v : (v != v ? v : 0.f);
       *out = p.accumulate ? *out + v : v;
     }
   }

@@ -38,6 +38,7 @@ BN_CASES = {
 DENSE_CASES = {
     'dense_odd_relu': (37, 19, 70, True),
     'dense_odd': (5, 130, 3, False),
+    'dense_splitk': (3, 1100, 5, False),            # one output tile, long contraction: K slices + atomicAdd
     'dense_feat_to_z': (6, 4096, 256, False),       # Weizmann feat_to_z_mean / feat_to_z_std.0
     'dense_z_to_feat': (20, 256, 4096, True),       # Weizmann z_to_feat.0 -> ReLU
 }

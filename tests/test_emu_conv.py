@@ -32,7 +32,7 @@ def test_batchnorm_relu_matches_torch(lib, case):
     conv_cases.check_bn(case, lib, 'cpu', 2e-6)
 
 
-@pytest.mark.parametrize('case', ['dense_odd_relu', 'dense_odd'])
+@pytest.mark.parametrize('case', ['dense_odd_relu', 'dense_odd', 'dense_splitk'])
 def test_dense_layer_matches_torch(lib, case):
     conv_cases.check_dense(case, lib, 'cpu', 2e-6)
 
