@@ -198,6 +198,11 @@ typedef struct bfvi_step_args {
 enum { BFVI_PREC_TF32X3 = 0, BFVI_PREC_TF32 = 1, BFVI_PREC_FUSED = 2 };
 
 int bfvi_version(void);
+/* 16 hex digits of the SHA-256 over the sources this binary was compiled from (csrc/ in name order, then this header),
+ * stamped by multimodal-dmm_b200/build.py; "unknown" for a build that did not stamp it.  The binary is git-ignored but
+ * ships to the GPU box: multimodal-dmm_b200/_lib.py::source_id() recomputes the digest from the tree and the host-API test
+ * asserts they agree, so a stale library cannot pass for the current sources. */
+const char* bfvi_build_id(void);
 const char* bfvi_last_error(void);
 
 /* sizeof() of the argument structs as THIS build of the library sees them: a binding (ctypes / cgo / JNI

@@ -138,6 +138,7 @@ STRUCTS = (Model, Layout, Expert, Noise, FilterArgs, StepArgs, ForwardArgs, Conv
 # every symbol include/bfvi.h declares (tests check that the library exports them all)
 SYMBOLS = {
     'bfvi_version': (C.c_int, []),
+    'bfvi_build_id': (C.c_char_p, []),
     'bfvi_last_error': (C.c_char_p, []),
     'bfvi_last_dispatch': (C.c_char_p, []),
     'bfvi_sizeof': (C.c_size_t, [C.c_int32]),
@@ -247,6 +248,10 @@ class Library(object):
                 raise BfviError('%s: ctypes struct %s is %d bytes, the library expects %d (binding out of date)'
                                 % (path, cls.__name__, C.sizeof(cls), want))
 
+    def build_id(self):
+        """digest of the sources this binary was compiled from ('unknown' when the build did not stamp one)"""
+        return self.dll.bfvi_build_id().decode('ascii', 'replace')
+
     def last_dispatch(self):
         return self.dll.bfvi_last_dispatch().decode('utf-8', 'replace').split(';')
 
@@ -262,6 +267,19 @@ class Library(object):
         return lay
 
 
+def source_id():
+    """The digest build.py stamps into the library, recomputed from the source tree beside this file (None when the
+    sources are not there)."""
+    import importlib.util
+    path = os.path.join(_HERE, 'build.py')
+    if not os.path.isdir(os.path.join(_HERE, 'csrc')) or not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location('_bfvi_build_id', path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.source_id()
+
+
 _lib = None
 
 
@@ -274,6 +292,11 @@ def load():
                 '%s is missing: build it with `python -c "import __graft_entry__ as g; g.build()"` '
                 '(nvcc, sm_100a).  There is no CPU fallback.' % LIB_PATH)
         _lib = Library(LIB_PATH)
+        want = source_id() if LIB_PATH.startswith(_HERE) else None
+        if want is not None and _lib.build_id() not in ('unknown', want):
+            import warnings
+            warnings.warn('%s was built from other sources (library %s, tree %s): rebuild with '
+                          '`python -c "import __graft_entry__ as g; g.build()"`' % (LIB_PATH, _lib.build_id(), want))
     return _lib
 
 

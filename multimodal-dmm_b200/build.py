@@ -20,6 +20,18 @@ def sources():
         os.path.join(os.path.dirname(HERE), 'include', 'bfvi.h')]
 
 
+def source_id():
+    """16 hex digits of the SHA-256 over csrc/ (name order) and include/bfvi.h: stamped into the library as
+    bfvi_build_id() so that a binary can be matched to the sources it was built from."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sources():
+        h.update(os.path.basename(path).encode() + b'\0')
+        with open(path, 'rb') as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def up_to_date():
     return os.path.exists(OUT) and all(
         os.path.getmtime(OUT) >= os.path.getmtime(s) for s in sources())
@@ -39,7 +51,7 @@ def build(force=False, verbose=False, defines=(), out=None):
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libbfvi_b200.so')
     cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + [
-        ] + UNITS + ['-o', OUT]
+        '-DBFVI_SOURCE_ID="%s"' % source_id()] + UNITS + ['-o', OUT]
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -1896,6 +1896,10 @@ int filter_impl(const bfvi_model* m, const bfvi_layout& lay, const float* params
 extern "C" {
 
 int bfvi_version(void) { return BFVI_VERSION; }
+#ifndef BFVI_SOURCE_ID
+#define BFVI_SOURCE_ID "unknown"
+#endif
+const char* bfvi_build_id(void) { return BFVI_SOURCE_ID; }
 const char* bfvi_last_error(void) { return g_err.c_str(); }
 const char* bfvi_last_dispatch(void) { return g_dispatch.c_str(); }
 size_t bfvi_sizeof(int32_t which) {

@@ -52,6 +52,8 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib.dll, name)
     assert lib.dll.bfvi_version() == int(re.search(r'#define BFVI_VERSION (\d+)', header).group(1)) == 140
+    # the shipped binary is git-ignored: its stamp must match the sources in the tree
+    assert lib.build_id() == _lib.source_id() and len(lib.build_id()) == 16
 
 
 def test_layout_and_argument_errors():
