@@ -61,3 +61,51 @@ def test_image_encoder_decoder_modules_through_the_kernels(lib, monkeypatch):
     monkeypatch.setattr(common, '_use_kernels', lambda x, kind: x.dtype == torch.float32)
     worst = conv_cases.check_modules(common, 'cpu', 2e-5)
     assert len(worst) > 30
+
+
+def test_layer_options_of_the_autograd_functions(lib, monkeypatch):
+    """bias-free convolutions, a BatchNorm2d without affine parameters and with a cumulative moving average
+    (momentum=None), a BatchNorm2d that tracks no running statistics: the module options _ConvFn / _BatchNormFn accept."""
+    import torch.nn as nn
+    import multimodal_dmm_b200.models.common as common
+    monkeypatch.setattr(common, '_library', lambda: lib)
+    torch.manual_seed(11)
+    conv = nn.Conv2d(3, 5, 3, 2, 1, bias=False)
+    deconv = nn.ConvTranspose2d(5, 2, 4, 2, 1, bias=False)
+    bn_cma = nn.BatchNorm2d(5, affine=False, momentum=None)
+    bn_free = nn.BatchNorm2d(2, track_running_stats=False)
+    ref = [__import__('copy').deepcopy(m).double() for m in (conv, deconv, bn_cma, bn_free)]
+    for step in range(2):
+        x = torch.randn(4, 3, 8, 8)
+        r = torch.randn(4, 2, 8, 8)              # a random projection: sum(y^2) of a normalised y has a vanishing gradient
+        # kernels
+        k, s, p, tr = common._layer_geometry(conv)
+        y = common._ConvFn.apply(x.clone().requires_grad_(True), conv.weight, None, k, s, p, tr, False)
+        y = common._BatchNormFn.apply(y, None, None, bn_cma, True)
+        k, s, p, tr = common._layer_geometry(deconv)
+        y = common._ConvFn.apply(y, deconv.weight, None, k, s, p, tr, False)
+        y = common._BatchNormFn.apply(y, bn_free.weight, bn_free.bias, bn_free, False)
+        for m in (conv, deconv, bn_free):
+            m.zero_grad()
+        (y * r).sum().backward()
+        # torch fp64
+        y64 = ref[3](ref[1](torch.relu(ref[2](ref[0](x.double())))))
+        for m in ref:
+            m.zero_grad()
+        (y64 * r.double()).sum().backward()
+        assert conv_cases.rel(y, y64) < 2e-6
+        assert conv_cases.rel(conv.weight.grad, ref[0].weight.grad) < 2e-5
+        assert conv_cases.rel(deconv.weight.grad, ref[1].weight.grad) < 2e-5
+        assert conv_cases.rel(bn_free.weight.grad, ref[3].weight.grad) < 2e-5
+        assert conv_cases.rel(bn_cma.running_mean, ref[2].running_mean) < 2e-6
+        assert conv_cases.rel(bn_cma.running_var, ref[2].running_var) < 2e-6
+        assert int(bn_cma.num_batches_tracked) == step + 1
+
+
+def test_unsupported_layer_options_fail_loudly():
+    import torch.nn as nn
+    import multimodal_dmm_b200.models.common as common
+    for layer in (nn.Conv2d(3, 4, 3, dilation=2), nn.Conv2d(4, 4, 3, groups=2), nn.Conv2d(3, 4, (3, 5)),
+                  nn.ConvTranspose2d(3, 4, 4, 2, 1, output_padding=1), nn.Conv2d(3, 4, 3, padding='same')):
+        with pytest.raises(_lib.BfviError):
+            common._layer_geometry(layer)
