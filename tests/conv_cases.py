@@ -252,3 +252,39 @@ def check_dense(case, lib, device, tol):
     errs = {'y': rel(y, y64.detach()), 'dx': rel(dx, x64.grad), 'dw': rel(dw - 1, w64.grad), 'db': rel(db - 1, b64.grad)}
     assert all(e < tol for e in errs.values()), (case, errs)
     return errs
+
+
+def check_golden_image(common, device, tol, check_init=False):
+    """common.ImageEncoder / ImageDecoder on `device` against the fixture oracle/make_golden_image.py wrote from the
+    UNMODIFIED reference's modules in float64 (tests/golden/image_modules.pt): two training passes (outputs, parameter
+    gradients, BatchNorm buffers) and the evaluation-mode pass, from the reference's own initial weights."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, 'oracle'))
+    import make_golden_image as gi
+    fx = torch.load(os.path.join(root, 'tests', 'golden', 'image_modules.pt'), weights_only=False)
+    cfg = fx['cfg']
+    enc, dec = gi.build(common, cfg)
+    if check_init:                           # same constructor order -> the reference's seeded initial values, bit for bit
+        for mod, key in ((enc, 'enc'), (dec, 'dec')):
+            sd = mod.state_dict()
+            assert list(sd.keys()) == list(fx['init'][key].keys())
+            assert all(torch.equal(sd[k], v) for k, v in fx['init'][key].items()), key
+    enc.load_state_dict(fx['init']['enc'])
+    dec.load_state_dict(fx['init']['dec'])
+    enc, dec = enc.to(device), dec.to(device)
+    got = gi.run(enc, dec, cfg, lambda t: t.to(device))
+    worst, floor = {}, None
+    for step, (g, r) in enumerate(zip(got['steps'], fx['ref']['steps'])):
+        assert set(g) == set(r)
+        floor = 1e-9 * max(v.norm().item() for k, v in r.items() if k.startswith('grad '))
+        for k in r:
+            if k.startswith('grad ') and r[k].norm().item() < floor:
+                continue                      # convolution bias in front of a BatchNorm: zero gradient up to rounding
+            worst['%d %s' % (step, k)] = rel(g[k], r[k])
+    for k, v in fx['ref']['eval'].items():
+        worst['eval ' + k] = rel(got['eval'][k], v)
+    bad = {k: v for k, v in worst.items() if not v < tol}
+    assert not bad, bad
+    return worst

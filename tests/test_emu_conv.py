@@ -109,3 +109,14 @@ def test_unsupported_layer_options_fail_loudly():
                   nn.ConvTranspose2d(3, 4, 4, 2, 1, output_padding=1), nn.Conv2d(3, 4, 3, padding='same')):
         with pytest.raises(_lib.BfviError):
             common._layer_geometry(layer)
+
+
+def test_image_modules_match_the_reference_golden(lib, monkeypatch):
+    """the reference's own ImageEncoder / ImageDecoder (float64, oracle/make_golden_image.py) against ours through the
+    emulated kernels: identical seeded initial values, then outputs / gradients / running statistics of two training
+    passes and the evaluation pass"""
+    import multimodal_dmm_b200.models.common as common
+    monkeypatch.setattr(common, '_library', lambda: lib)
+    monkeypatch.setattr(common, '_use_kernels', lambda x, kind: True)
+    worst = conv_cases.check_golden_image(common, 'cpu', 2e-5, check_init=True)
+    assert len(worst) > 60

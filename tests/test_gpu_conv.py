@@ -41,3 +41,9 @@ def test_image_encoder_decoder_modules(size):
         dict(img_size=64, n_kernels=64, z_dim=256, frames=6)
     worst = conv_cases.check_modules(common, 'cuda:0', 1e-4, **kw)
     assert len(worst) > 30
+
+
+def test_image_modules_match_the_reference_golden():
+    """tests/golden/image_modules.pt: the UNMODIFIED reference's ImageEncoder / ImageDecoder in float64"""
+    worst = conv_cases.check_golden_image(common, 'cuda:0', 2e-4)
+    assert len(worst) > 60
