@@ -1,7 +1,8 @@
-"""BASELINE config 4 (Weizmann-shaped): conv image encoders / decoders as custom torch modules,
-Bernoulli + Categorical modalities, a dropped modality — the composed, differentiable path
-encode -> z_filter (fused temporal core, large-dim family) -> decode against the REFERENCE's
-golden loss, posterior and gradients (oracle/make_golden_weizmann.py)."""
+"""BASELINE config 4 (Weizmann-shaped): conv image encoders / decoders passed as custom modules (their layers run
+on this library's bfvi_conv_* / bfvi_bn2d_* / bfvi_dense_* kernels, models/common.py), Bernoulli + Categorical
+modalities, a dropped modality — the composed, differentiable path encode -> z_filter (fused temporal core,
+large-dim family) -> decode against the REFERENCE's golden loss, posterior and gradients
+(oracle/make_golden_weizmann.py)."""
 import os
 import sys
 
