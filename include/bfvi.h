@@ -515,7 +515,11 @@ int bfvi_adam_step(float* params, const float* grads, float* exp_avg, float* exp
  *                                                                    decoder's final sigmoid, models/common.py:148)
  *   bfvi_conv_wgrad             dw += (small = dy, big = x)          dw += (small = x, big = dy)
  *   bfvi_chan_bias_grad         db += sum over images and pixels of dy (either layer)
- * Direct FP32 convolutions (the reference's convolutions are FP32, not TF32); kernel sizes up to 7. */
+ * Direct FP32 convolutions (the reference's convolutions are FP32, not TF32); kernel sizes up to 7.
+ * Summation order: bfvi_conv_wgrad adds the partial sums of its pixel splits with float atomics, and bfvi_dense_* slices a
+ * long contraction over idle SMs the same way when there are few output tiles, so the last bits of those results can
+ * differ from run to run (like cuDNN's default backward algorithms).  BFVI_DETERMINISTIC=1 in the environment (read per
+ * call) keeps one writer per output element: bit-identical runs, less parallelism on small problems. */
 typedef struct bfvi_conv_geom {
   int32_t n;                          /* images (T * B frames) */
   int32_t c_small, h_small, w_small;

@@ -1,6 +1,7 @@
 // bfvi_conv.cu — C entries of the image-module kernels (bfvi_conv.cuh): Conv2d / ConvTranspose2d passes, BatchNorm2d
 // (+ ReLU) forward / backward, the sigmoid backward and per-channel bias gradients.  Second translation unit of
 // libbfvi_b200.so; errors go through the library's bfvi_last_error().
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/bfvi.h"
@@ -18,6 +19,13 @@ using bfvi::report_error;
     if (e_ != cudaSuccess) return report_error(BFVI_ERR_CUDA, "CUDA error: %s (%s:%d)",              \
                                                cudaGetErrorString(e_), __FILE__, __LINE__);          \
   } while (0)
+
+// BFVI_DETERMINISTIC=1: no cross-CTA float atomics (one pixel split per weight-gradient tile, no K slices in the dense
+// GEMMs): run-to-run bit-identical results at the price of parallelism on the small problems.  Read per call.
+bool deterministic() {
+  const char* e = getenv("BFVI_DETERMINISTIC");
+  return e != nullptr && atoi(e) != 0;
+}
 
 int check_geom(const bfvi_conv_geom* g, Geom* out) {
   if (g == nullptr) return report_error(BFVI_ERR_ARG, "geometry is null");
@@ -76,6 +84,7 @@ void launch_wgrad(const Geom& g, const float* small, const float* big, float* dw
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
+  if (deterministic()) splits = 1;
   const long long per = (total + splits - 1) / splits;
   const dim3 grid((unsigned)g.Cb, (unsigned)((g.Cs + CSR - 1) / CSR), (unsigned)splits);
   auto k = bfvi::conv::conv_wgrad_kernel<KT, CSR>;
@@ -257,7 +266,7 @@ void launch_dense(bfvi::conv::DenseParams p, cudaStream_t st) {
             (unsigned)((p.M + bfvi::conv::kDenseTile - 1) / bfvi::conv::kDenseTile));
   // few output tiles and a long contraction (feat_to_z at 625 frames: 40 tiles, K = 4096): slices of K on the other SMs
   const long long tiles = (long long)grid.x * grid.y;
-  if (!p.relu && tiles * 2 <= 148 && p.K >= 1024) {
+  if (!p.relu && tiles * 2 <= 148 && p.K >= 1024 && !deterministic()) {
     long long splits = 296 / tiles;
     if (splits > p.K / 256) splits = p.K / 256;
     if (splits > 1) {

@@ -94,6 +94,19 @@ def _scratch(lib, channels, like):
     return torch.empty(n // 8 + 1, dtype=torch.float64, device=like.device), C.c_size_t(n)
 
 
+def _check_determinism(what):
+    """torch.use_deterministic_algorithms(True) and float atomics do not go together: the library keeps one writer per
+    output element under BFVI_DETERMINISTIC=1 (include/bfvi.h); without it follow torch's convention (raise / warn)."""
+    if torch.are_deterministic_algorithms_enabled() and os.environ.get('BFVI_DETERMINISTIC', '0') in ('', '0'):
+        msg = ('%s accumulates partial sums with float atomics; set BFVI_DETERMINISTIC=1 for run-to-run identical '
+               'results under torch.use_deterministic_algorithms(True)' % what)
+        if torch.is_deterministic_algorithms_warn_only_enabled():
+            import warnings
+            warnings.warn(msg)
+        else:
+            raise RuntimeError(msg)
+
+
 def _square(v, what):
     a, b = (v, v) if isinstance(v, int) else tuple(v)
     if a != b:
@@ -141,6 +154,7 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
+        _check_determinism('bfvi_conv_wgrad')
         lib = _library()
         x, w, y = ctx.saved_tensors
         g, st = ctx.geom, _stream(x)
@@ -217,6 +231,7 @@ class _DenseFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, relu):
+        _check_determinism('bfvi_dense_fwd')
         lib = _library()
         x, w = x.detach().contiguous().float(), w.detach().contiguous().float()
         b = None if b is None else b.detach().contiguous().float()

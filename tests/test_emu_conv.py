@@ -120,3 +120,22 @@ def test_image_modules_match_the_reference_golden(lib, monkeypatch):
     monkeypatch.setattr(common, '_use_kernels', lambda x, kind: True)
     worst = conv_cases.check_golden_image(common, 'cpu', 2e-5, check_init=True)
     assert len(worst) > 60
+
+
+def test_deterministic_mode(lib, monkeypatch):
+    """BFVI_DETERMINISTIC=1 (one writer per output element: no pixel splits, no K slices) computes the same results; under
+    torch.use_deterministic_algorithms(True) the autograd functions insist on it"""
+    import multimodal_dmm_b200.models.common as common
+    monkeypatch.setenv('BFVI_DETERMINISTIC', '1')
+    conv_cases.check_conv('conv3s2_odd', lib, 'cpu', 2e-6)
+    conv_cases.check_dense('dense_splitk', lib, 'cpu', 2e-6)
+    monkeypatch.delenv('BFVI_DETERMINISTIC')
+    monkeypatch.setattr(common, '_library', lambda: lib)
+    torch.use_deterministic_algorithms(True)
+    try:
+        with pytest.raises(RuntimeError, match='BFVI_DETERMINISTIC'):
+            common._DenseFn.apply(torch.zeros(2, 3), torch.zeros(4, 3), None, False)
+        monkeypatch.setenv('BFVI_DETERMINISTIC', '1')
+        assert common._DenseFn.apply(torch.ones(2, 3), torch.ones(4, 3), None, False).sum().item() == 24.0
+    finally:
+        torch.use_deterministic_algorithms(False)
