@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_shim               # noqa: E402
 
-OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'image_modules.pt')
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'image', 'modules.pt')
 CFG = dict(seed=21, z_dim=12, img_size=16, n_channels=3, n_kernels=8, frames=6, steps=2)
 
 

@@ -256,14 +256,14 @@ def check_dense(case, lib, device, tol):
 
 def check_golden_image(common, device, tol, check_init=False):
     """common.ImageEncoder / ImageDecoder on `device` against the fixture oracle/make_golden_image.py wrote from the
-    UNMODIFIED reference's modules in float64 (tests/golden/image_modules.pt): two training passes (outputs, parameter
+    UNMODIFIED reference's modules in float64 (tests/golden/image/modules.pt): two training passes (outputs, parameter
     gradients, BatchNorm buffers) and the evaluation-mode pass, from the reference's own initial weights."""
     import os
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, os.path.join(root, 'oracle'))
     import make_golden_image as gi
-    fx = torch.load(os.path.join(root, 'tests', 'golden', 'image_modules.pt'), weights_only=False)
+    fx = torch.load(os.path.join(root, 'tests', 'golden', 'image', 'modules.pt'), weights_only=False)
     cfg = fx['cfg']
     enc, dec = gi.build(common, cfg)
     if check_init:                           # same constructor order -> the reference's seeded initial values, bit for bit

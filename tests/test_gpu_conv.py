@@ -44,7 +44,7 @@ def test_image_encoder_decoder_modules(size):
 
 
 def test_image_modules_match_the_reference_golden():
-    """tests/golden/image_modules.pt: the UNMODIFIED reference's ImageEncoder / ImageDecoder in float64"""
+    """tests/golden/image/modules.pt: the UNMODIFIED reference's ImageEncoder / ImageDecoder in float64"""
     worst = conv_cases.check_golden_image(common, 'cuda:0', 2e-4)
     assert len(worst) > 60
 
