@@ -3,6 +3,7 @@
 (aliased onto the flat CUDA parameter buffer); their `forward` methods exist for
 composition with custom user modules and run as ordinary device ops."""
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -94,6 +95,19 @@ def _scratch(lib, channels, like):
     return torch.empty(n // 8 + 1, dtype=torch.float64, device=like.device), C.c_size_t(n)
 
 
+def _on_tensor_device(fn):
+    """Kernels launch on the CURRENT device: make that the device of the call's first tensor (a model on cuda:1
+    while cuda:0 is current must not launch on cuda:0 with cuda:1 pointers)."""
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        t = next((a for a in args if torch.is_tensor(a)), None)
+        if t is not None and t.is_cuda:
+            with torch.cuda.device(t.device):
+                return fn(ctx, *args)
+        return fn(ctx, *args)
+    return wrapped
+
+
 def _check_determinism(what):
     """torch.use_deterministic_algorithms(True) and float atomics do not go together: the library keeps one writer per
     output element under BFVI_DETERMINISTIC=1 (include/bfvi.h); without it follow torch's convention (raise / warn)."""
@@ -130,6 +144,7 @@ class _ConvFn(torch.autograd.Function):
     final nn.Sigmoid (models/common.py:148) into the transposed convolution."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, w, b, k, s, p, transposed, sigmoid):
         lib = _library()
         x, w = x.detach().contiguous().float(), w.detach().contiguous().float()
@@ -153,6 +168,7 @@ class _ConvFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         _check_determinism('bfvi_conv_wgrad')
         lib = _library()
@@ -185,6 +201,7 @@ class _BatchNormFn(torch.autograd.Function):
     statistics of `bn` are updated in place by the kernel like torch does."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, gamma, beta, bn, relu):
         lib = _library()
         x = x.detach().contiguous().float()
@@ -210,6 +227,7 @@ class _BatchNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         lib = _library()
         x, y, gamma, save = ctx.saved_tensors
@@ -230,6 +248,7 @@ class _DenseFn(torch.autograd.Function):
     on the TF32 tensor cores, even error-compensated, flips ReLU masks downstream)."""
 
     @staticmethod
+    @_on_tensor_device
     def forward(ctx, x, w, b, relu):
         _check_determinism('bfvi_dense_fwd')
         lib = _library()
@@ -244,6 +263,7 @@ class _DenseFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_tensor_device
     def backward(ctx, dy):
         lib = _library()
         x, w, y = ctx.saved_tensors
