@@ -6,6 +6,7 @@ import multimodal_dmm_b200.models.common as common
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.timeout(180)
 def test_no_library_convolution_or_gemm_on_the_image_path():
     """A forward + backward of ImageEncoder -> ImageDecoder launches this library's kernels (bfvi::conv::*) for every
     convolution, BatchNorm and dense layer: no cuDNN / cuBLAS / CUTLASS kernel name shows up in the profile.
